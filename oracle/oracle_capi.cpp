@@ -1,0 +1,441 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  extern "C" surface of the CPU restatement, bound with ctypes by
+// tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference).  Never linked into
+// or called by the product library.  PARITY UNPINNED (see stomp_oracle.hpp).
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "stomp_oracle.hpp"
+
+using namespace oracle;
+
+extern "C" {
+
+struct oracle_config {
+    int32_t num_time_steps, num_dimensions;
+    int32_t min_rollouts, max_rollouts, num_rollouts_per_iteration, num_iterations;
+    double movement_duration, control_cost_weight, min_cost_improvement;
+    double noise_stddev[32], noise_decay[32], noise_min_stddev[32];
+    int32_t use_noise_adaptation, use_openmp;
+    int32_t use_cumulative_costs;   // reference default 1 (PolicyImprovement.cpp:56)
+    int32_t use_projection;         // reference default 0 (PolicyImprovement.cpp:57)
+    int32_t per_timestep_minmax;    // 0 = shipped behaviour; 1 = variant commented out at :518-528
+    int32_t dense_control_costs;    // 1 = keep the reference's O(N^2) evaluation forms (CPU baseline)
+    uint64_t seed;
+};
+
+}  // extern "C"
+
+namespace {
+
+struct OracleHandle {
+    oracle_config cfg;
+    StompConfig sc;
+    std::shared_ptr<SphereSdfTask> task;
+    std::unique_ptr<Stomp> stomp;
+    // StompPlanner::solve loop state (StompPlanner.cpp:96-141)
+    double old_cost = 0, cost_improvement = 0, current_cost = 0;
+    int num_iterations = 0;
+};
+
+StompConfig to_stomp_config(const oracle_config& c)
+{
+    StompConfig s;
+    s.num_time_steps_ = c.num_time_steps;
+    s.num_dimensions_ = c.num_dimensions;
+    s.min_rollouts_ = c.min_rollouts;
+    s.max_rollouts_ = c.max_rollouts;
+    s.num_rollouts_per_iteration_ = c.num_rollouts_per_iteration;
+    s.num_iterations_ = c.num_iterations;
+    s.movement_duration_ = c.movement_duration;
+    s.control_cost_weight_ = c.control_cost_weight;
+    s.min_cost_improvement_ = c.min_cost_improvement;
+    s.noise_stddev_.assign(c.noise_stddev, c.noise_stddev + c.num_dimensions);
+    s.noise_decay_.assign(c.noise_decay, c.noise_decay + c.num_dimensions);
+    s.noise_min_stddev_.assign(c.noise_min_stddev, c.noise_min_stddev + c.num_dimensions);
+    s.use_noise_adaptation_ = c.use_noise_adaptation != 0;
+    s.use_openmp_ = c.use_openmp != 0;
+    return s;
+}
+
+void apply_switches(OracleHandle* h)
+{
+    PolicyImprovement& pi = h->stomp->policy_improvement_;
+    pi.dense_control_costs_ = h->cfg.dense_control_costs != 0;
+    pi.per_timestep_minmax_ = h->cfg.per_timestep_minmax != 0;
+    pi.setCostCumulation(h->cfg.use_cumulative_costs != 0);
+    if ((h->cfg.use_projection != 0) != pi.use_projection_) {
+        pi.use_projection_ = h->cfg.use_projection != 0;
+        pi.preComputeProjectionMatrices();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void* oracle_create(const oracle_config* cfg)
+{
+    if (!cfg || cfg->num_dimensions <= 0 || cfg->num_dimensions > 32 || cfg->num_time_steps <= 1) return nullptr;
+    OracleHandle* h = new OracleHandle();
+    h->cfg = *cfg;
+    h->sc = to_stomp_config(*cfg);
+    h->task.reset(new SphereSdfTask(h->sc));
+    h->task->stompInitialize();
+    return h;
+}
+
+void oracle_destroy(void* hp) { delete static_cast<OracleHandle*>(hp); }
+
+int oracle_set_chain(void* hp, int D, const double* origin_xyz, const double* origin_rpy, const double* axis,
+                     const int32_t* parent, const int32_t* prismatic, const double* lower, const double* upper)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (D != h->cfg.num_dimensions) return -1;
+    h->task->joints_.assign(D, JointSpec());
+    h->task->lower_limits_.assign(lower, lower + D);
+    h->task->upper_limits_.assign(upper, upper + D);
+    for (int d = 0; d < D; ++d) {
+        JointSpec& j = h->task->joints_[d];
+        j.parent = parent ? parent[d] : (d == 0 ? -1 : d - 1);
+        if (!(j.parent == -1 || j.parent == d - 1)) return -2;
+        j.prismatic = prismatic ? prismatic[d] : 0;
+        for (int i = 0; i < 3; ++i) { j.o[i] = origin_xyz[3 * d + i]; j.axis[i] = axis[3 * d + i]; }
+        const double* rpy = origin_rpy + 3 * d;
+        j.fixed_rot_identity = (rpy[0] == 0.0 && rpy[1] == 0.0 && rpy[2] == 0.0) ? 1 : 0;
+        rpy_to_matrix(rpy, j.A);
+        j.axis_kind = classify_axis(j.axis);
+        j.lower = lower[d]; j.upper = upper[d];
+    }
+    return 0;
+}
+
+int oracle_set_spheres(void* hp, int S, const int32_t* link, const double* xyz, const double* radius)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    h->task->spheres_.assign(S, SphereSpec());
+    for (int s = 0; s < S; ++s) {
+        if (link[s] < 0 || link[s] >= h->cfg.num_dimensions) return -1;
+        if (s > 0 && link[s] < link[s - 1]) return -2;   // must be sorted by link
+        SphereSpec& sp = h->task->spheres_[s];
+        sp.link = link[s];
+        for (int i = 0; i < 3; ++i) sp.l[i] = xyz[3 * s + i];
+        sp.r = radius[s];
+    }
+    return 0;
+}
+
+// the grid is NOT copied: the caller keeps it alive for the lifetime of the handle
+int oracle_set_sdf(void* hp, const int32_t* dims, const double* origin, double voxel, const float* grid)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    SdfSpec& g = h->task->sdf_;
+    g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+    g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
+    g.inv_h = 1.0 / voxel;
+    g.grid = grid;
+    return 0;
+}
+
+// StompPlanner::setStartGoalTrajectory (StompPlanner.cpp:177-184)
+int oracle_set_start_goal(void* hp, const double* start, const double* goal)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    const int D = h->cfg.num_dimensions;
+    h->task->updateTrajectory(Vec(start, start + D), Vec(goal, goal + D));
+    h->task->input_initial_trajectory_ = h->task->initial_trajectory_;
+    h->task->createPolicy();
+    return 0;
+}
+
+// StompPlanner::updateInitialTrajectory (StompPlanner.cpp:186-208); trajectory is [D][T]
+int oracle_set_initial_trajectory(void* hp, const double* traj)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    const int D = h->cfg.num_dimensions, T = h->cfg.num_time_steps, P = TRAJECTORY_PADDING;
+    for (int d = 0; d < D; ++d) {
+        for (int i = 0; i < P; ++i) {
+            h->task->initial_trajectory_[d][i] = traj[(size_t)d * T] * 1.0;
+            h->task->initial_trajectory_[d][P + T + i] = traj[(size_t)d * T + T - 1] * 1.0;
+        }
+        for (int i = 0; i < T; ++i) h->task->initial_trajectory_[d][P + i] = traj[(size_t)d * T + i];
+    }
+    h->task->input_initial_trajectory_ = h->task->initial_trajectory_;
+    h->task->updatePolicy();
+    return 0;
+}
+
+// host-side policy products (a14): any output may be null.  R, Rinv, L: [T][T]; params_all: [D][N];
+// mincc: [D][T]; linear: [D][T]
+int oracle_get_policy(void* hp, double* R, double* Rinv, double* L, double* params_all, double* mincc, double* linear)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->task->policy_) return -1;
+    const CovariantMovementPrimitive& p = *h->task->policy_;
+    const int T = p.num_vars_free_, N = p.num_vars_all_, D = p.num_dimensions_;
+    if (R) std::memcpy(R, p.control_costs_[0].a.data(), sizeof(double) * T * T);
+    if (Rinv) std::memcpy(Rinv, p.inv_control_costs_[0].a.data(), sizeof(double) * T * T);
+    if (L) { Mat Lm = llt_lower(p.inv_control_costs_[0]); std::memcpy(L, Lm.a.data(), sizeof(double) * T * T); }
+    for (int d = 0; d < D; ++d) {
+        if (params_all) std::memcpy(params_all + (size_t)d * N, p.parameters_all_[d].data(), sizeof(double) * N);
+        if (mincc) std::memcpy(mincc + (size_t)d * T, p.min_control_cost_parameters_free_[d].data(), sizeof(double) * T);
+        if (linear) std::memcpy(linear + (size_t)d * T, p.linear_control_costs_[d].data(), sizeof(double) * T);
+    }
+    return 0;
+}
+
+double oracle_get_movement_dt(void* hp)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    return h->task->policy_ ? h->task->policy_->movement_dt_ : 0.0;
+}
+
+// start of StompPlanner::solve (StompPlanner.cpp:65-73,96-99): a new Stomp per solve
+int oracle_begin_solve(void* hp)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->task->policy_) return -1;
+    h->stomp.reset(new Stomp());
+    h->stomp->initialize(h->sc, h->task, h->cfg.seed);
+    apply_switches(h);
+    h->old_cost = 0; h->cost_improvement = 0; h->current_cost = 0; h->num_iterations = 0;
+    return 0;
+}
+
+// replace the Cholesky factor used for sampling (parity tests share one L between oracle and GPU)
+int oracle_set_cholesky(void* hp, const double* L)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->stomp) return -1;
+    const int T = h->cfg.num_time_steps;
+    for (auto& g : h->stomp->policy_improvement_.noise_generators_)
+        std::memcpy(g.covariance_cholesky_.a.data(), L, sizeof(double) * T * T);
+    return 0;
+}
+
+// one pass of the loop body of StompPlanner::solve (StompPlanner.cpp:101-118).  Returns 1 when the stop
+// criterion fires, 0 otherwise.  noise / epsilon: [num_rollouts_gen][D][T] or null.
+int oracle_iterate(void* hp, int iteration, const double* injected_noise, const double* epsilon)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->stomp) return -1;
+    NoiseSource src; src.injected = injected_noise; src.epsilon = epsilon;
+    h->num_iterations++;
+    h->stomp->runSingleIteration(iteration, src);
+    h->current_cost = h->stomp->getNoiselessRolloutTotalCost();
+    h->cost_improvement = h->current_cost - h->old_cost;
+    h->old_cost = h->current_cost;
+    if ((h->current_cost < 1) && (std::fabs(h->cost_improvement) < h->sc.min_cost_improvement_)) return 1;
+    return 0;
+}
+
+// end of StompPlanner::solve (:148-173): solution = last parameters; returns 1 = PATH_FOUND, 0 = NO_PATH_FOUND
+int oracle_finish_solve(void* hp, double* solution /*[D][T]*/, int32_t* iterations_used)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    const int D = h->cfg.num_dimensions, T = h->cfg.num_time_steps;
+    const CovariantMovementPrimitive& p = *h->task->policy_;
+    if (solution)
+        for (int d = 0; d < D; ++d)
+            for (int i = 0; i < T; ++i) solution[(size_t)d * T + i] = p.parameters_all_[d][i + (DIFF_RULE_LENGTH - 1)];
+    if (iterations_used) *iterations_used = h->num_iterations;
+    h->stomp.reset();
+    return ((h->current_cost < 1) && (std::fabs(h->cost_improvement) <= h->sc.min_cost_improvement_)) ? 1 : 0;
+}
+
+// whole StompPlanner::solve with the internal generator; returns status as oracle_finish_solve.
+// seconds_out = wall time of the iteration loop only (where the reference times: MotionPlanners.cpp:506-512
+// brackets solve(); the one-time Stomp::initialize is reported separately in setup_seconds_out)
+int oracle_solve(void* hp, int max_iterations, int honour_stop, double* solution, int32_t* iterations_used,
+                 double* seconds_out, double* setup_seconds_out)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    auto t0 = std::chrono::steady_clock::now();
+    if (oracle_begin_solve(hp) != 0) return -1;
+    auto t1 = std::chrono::steady_clock::now();
+    for (int i = 0; i < max_iterations; ++i) {
+        int stop = oracle_iterate(hp, i, nullptr, nullptr);
+        if (stop && honour_stop) break;
+    }
+    auto t2 = std::chrono::steady_clock::now();
+    if (seconds_out) *seconds_out = std::chrono::duration<double>(t2 - t1).count();
+    if (setup_seconds_out) *setup_seconds_out = std::chrono::duration<double>(t1 - t0).count();
+    (void)h;
+    return oracle_finish_solve(hp, solution, iterations_used);
+}
+
+int oracle_num_rollouts(void* hp, int32_t* num_rollouts, int32_t* num_rollouts_gen)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->stomp) return -1;
+    *num_rollouts = h->stomp->policy_improvement_.num_rollouts_;
+    *num_rollouts_gen = h->stomp->policy_improvement_.num_rollouts_gen_;
+    return 0;
+}
+
+// field ids: 0 parameters_noise [n][D][T]; 1 noise [n][D][T]; 2 control_costs [n][D][T];
+// 3 probabilities [n][D][T]; 4 cumulative_costs [n][D][T]; 5 total_costs [n][D][T];
+// 6 state_costs [n][T]; 7 full_probabilities [n][D]; 8 full_costs [n][D]; 9 total_cost [n];
+// 10 parameters_noise_projected [n][D][T]; 11 noise_projected [n][D][T]
+int oracle_get_rollout_field(void* hp, int field, double* out)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->stomp) return -1;
+    const PolicyImprovement& pi = h->stomp->policy_improvement_;
+    const int n = pi.num_rollouts_, D = pi.num_dimensions_, T = pi.num_time_steps_;
+    for (int r = 0; r < n; ++r) {
+        const Rollout& ro = pi.rollouts_[r];
+        const std::vector<Vec>* f = nullptr;
+        switch (field) {
+            case 0: f = &ro.parameters_noise_; break;
+            case 1: f = &ro.noise_; break;
+            case 2: f = &ro.control_costs_; break;
+            case 3: f = &ro.probabilities_; break;
+            case 4: f = &ro.cumulative_costs_; break;
+            case 5: f = &ro.total_costs_; break;
+            case 10: f = &ro.parameters_noise_projected_; break;
+            case 11: f = &ro.noise_projected_; break;
+            case 6: std::memcpy(out + (size_t)r * T, ro.state_costs_.data(), sizeof(double) * T); continue;
+            case 7: std::memcpy(out + (size_t)r * D, ro.full_probabilities_.data(), sizeof(double) * D); continue;
+            case 8: std::memcpy(out + (size_t)r * D, ro.full_costs_.data(), sizeof(double) * D); continue;
+            case 9: out[r] = ro.total_cost_; continue;
+            default: return -2;
+        }
+        for (int d = 0; d < D; ++d) std::memcpy(out + ((size_t)r * D + d) * T, (*f)[d].data(), sizeof(double) * T);
+    }
+    return 0;
+}
+
+int oracle_get_rollout_validity(void* hp, uint8_t* out /*[num_rollouts_gen]*/)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->stomp) return -1;
+    std::memcpy(out, h->stomp->rollout_validity_.data(), h->stomp->rollout_validity_.size());
+    return 0;
+}
+
+int oracle_get_updates(void* hp, double* out /*[D][T]*/)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->stomp) return -1;
+    const PolicyImprovement& pi = h->stomp->policy_improvement_;
+    for (int d = 0; d < pi.num_dimensions_; ++d)
+        for (int t = 0; t < pi.num_time_steps_; ++t) out[(size_t)d * pi.num_time_steps_ + t] = pi.parameter_updates_[d](0, t);
+    return 0;
+}
+
+int oracle_get_parameters(void* hp, double* out /*[D][T]*/)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    std::vector<Vec> p;
+    h->task->policy_->getParameters(p);
+    for (size_t d = 0; d < p.size(); ++d) std::memcpy(out + d * p[d].size(), p[d].data(), sizeof(double) * p[d].size());
+    return 0;
+}
+
+int oracle_get_stddevs(void* hp, double* out /*[D]*/)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->stomp) return -1;
+    const Vec& s = h->stomp->policy_improvement_.adapted_stddevs_;
+    std::memcpy(out, s.data(), sizeof(double) * s.size());
+    return 0;
+}
+
+int oracle_get_noiseless(void* hp, double* total_cost, int32_t* valid, double* state_costs /*[T] or null*/,
+                         double* control_costs /*[D][T] or null*/, double* best_cost /* or null */)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->stomp) return -1;
+    const PolicyImprovement& pi = h->stomp->policy_improvement_;
+    *total_cost = pi.noiseless_rollout_.total_cost_;
+    *valid = h->stomp->last_noiseless_rollout_valid_ ? 1 : 0;
+    const int T = pi.num_time_steps_;
+    if (state_costs) std::memcpy(state_costs, pi.noiseless_rollout_.state_costs_.data(), sizeof(double) * T);
+    if (control_costs)
+        for (int d = 0; d < pi.num_dimensions_; ++d)
+            std::memcpy(control_costs + (size_t)d * T, pi.noiseless_rollout_.control_costs_[d].data(), sizeof(double) * T);
+    if (best_cost) *best_cost = h->stomp->best_noiseless_cost_;
+    return 0;
+}
+
+// ---- kernel-level checkers -----------------------------------------------------------------------
+
+void oracle_sincos(double x, double* s, double* c) { det_sincos(x, s, c); }
+
+int oracle_sphere_centres(void* hp, const double* q, double* centres /*[S][3]*/)
+{
+    static_cast<OracleHandle*>(hp)->task->sphereCentres(q, centres);
+    return 0;
+}
+
+// theta: [K][D][T]; costs: [K][T]; verdict: [K][T] (1 = in collision); validity: [K]
+int oracle_state_costs(void* hp, const double* theta, int K, double* costs, uint8_t* verdict, uint8_t* validity, int threads)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    const int D = h->cfg.num_dimensions, T = h->cfg.num_time_steps;
+    (void)threads;
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
+    for (int k = 0; k < K; ++k) {
+        std::vector<double> q(D);
+        for (int t = 0; t < T; ++t) {
+            for (int d = 0; d < D; ++d) q[d] = theta[((size_t)k * D + d) * T + t];
+            bool hit = h->task->stateCollides(q.data());
+            if (costs) costs[(size_t)k * T + t] = hit ? 1.0 : 0.0;
+            if (verdict) verdict[(size_t)k * T + t] = hit ? 1 : 0;
+            if (validity && t == T - 1) validity[k] = hit ? 0 : 1;
+        }
+    }
+    return 0;
+}
+
+// control costs of trajectories x = parameters + noise_projected, [K][D][T] each -> out [K][D][T]
+int oracle_control_costs(void* hp, const double* parameters /*[D][T]*/, const double* noise /*[K][D][T]*/, int K,
+                         double weight, double* out, int dense_form)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h->task->policy_) return -1;
+    const int D = h->cfg.num_dimensions, T = h->cfg.num_time_steps;
+    std::vector<Vec> p(D), n(D), cc;
+    for (int d = 0; d < D; ++d) p[d].assign(parameters + (size_t)d * T, parameters + (size_t)(d + 1) * T);
+    for (int k = 0; k < K; ++k) {
+        for (int d = 0; d < D; ++d) n[d].assign(noise + ((size_t)k * D + d) * T, noise + ((size_t)k * D + d + 1) * T);
+        h->task->policy_->computeControlCosts(p, n, weight, cc, dense_form != 0);
+        for (int d = 0; d < D; ++d) std::memcpy(out + ((size_t)k * D + d) * T, cc[d].data(), sizeof(double) * T);
+    }
+    return 0;
+}
+
+// standalone factorisations (host-logic tests of the product's own LU / LLT)
+int oracle_full_piv_lu_inverse(const double* A, int n, double* out)
+{
+    Mat m(n, n);
+    std::memcpy(m.a.data(), A, sizeof(double) * n * n);
+    Mat inv = full_piv_lu_inverse(m);
+    std::memcpy(out, inv.a.data(), sizeof(double) * n * n);
+    return 0;
+}
+
+int oracle_llt_lower(const double* A, int n, double* out)
+{
+    Mat m(n, n);
+    std::memcpy(m.a.data(), A, sizeof(double) * n * n);
+    Mat L = llt_lower(m);
+    std::memcpy(out, L.a.data(), sizeof(double) * n * n);
+    return 0;
+}
+
+int oracle_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"
