@@ -1,0 +1,230 @@
+/*
+ * stomp_b200.h — C ABI of the B200-native STOMP rollout loop.
+ *
+ * Drop-in boundary for the hot path of rock-planning/motion_planners: everything that
+ * stomp::Stomp::runSingleIteration does per iteration (reference src/planners/stomp/src/Stomp.cpp:274-301)
+ * — PolicyImprovement::generateRollouts, the Task::execute rollout cost, computeRolloutCumulativeCosts /
+ * computeRolloutProbabilities and computeParameterUpdates / CovariantMovementPrimitive::updateParameters —
+ * runs in hand-written sm_100a CUDA kernels behind these entry points.  The reference has no FFI of its
+ * own (it is one C++ process); these are the calls our StompPlanner (include/wrapper/stomp/StompPlanner.hpp,
+ * same public API as reference src/planners/include/wrapper/stomp/StompPlanner.hpp:15-89) makes where the
+ * reference's StompPlanner::solve (src/planners/src/wrappers/stomp/StompPlanner.cpp:65-174) drives
+ * stomp::Stomp.  INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status (0 = ok, negative =
+ * error, never throws or aborts); all host buffers are caller-owned, row-major, FP64 unless stated;
+ * one engine <-> one host thread <-> one GPU.  There is NO CPU fallback: without a CUDA device
+ * stomp_b200_create fails with STOMP_B200_ERR_NO_DEVICE.
+ *
+ * Index names: Q queries held by this engine, K' = rollouts used in the current update (generated +
+ * reused + the appended noise-less one), G = rollouts generated in the current iteration, D joints,
+ * T time steps, N = T + 12 (TRAJECTORY_PADDING = 6 on both sides, reference StompUtils.hpp:57), S spheres.
+ */
+#ifndef STOMP_B200_H_
+#define STOMP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STOMP_B200_ABI_VERSION 1
+#define STOMP_B200_MAX_DIMS 32      /* joints per planning group */
+#define STOMP_B200_MAX_SPHERES 128  /* collision spheres */
+#define STOMP_B200_MAX_TIME_STEPS 256
+
+enum stomp_b200_status {
+    STOMP_B200_OK = 0,
+    STOMP_B200_ERR_INVALID_ARGUMENT = -1,
+    STOMP_B200_ERR_NO_DEVICE = -2,       /* no CUDA device / driver: the product path has no CPU fallback */
+    STOMP_B200_ERR_CUDA = -3,            /* a CUDA call failed; see stomp_b200_last_error */
+    STOMP_B200_ERR_NOT_READY = -4,       /* chain / spheres / SDF / policy / begin_solve missing */
+    STOMP_B200_ERR_UNSUPPORTED = -5,     /* valid in the reference, not built yet (listed in DESIGN.md) */
+    STOMP_B200_ERR_NCCL = -6,
+    STOMP_B200_ERR_OUT_OF_MEMORY = -7
+};
+
+typedef struct stomp_b200_engine stomp_b200_engine;
+
+/* Mirrors stomp::StompConfig (reference src/planners/stomp/include/stomp/StompConfig.hpp:19-42) plus the
+ * switches the reference hard-codes in PolicyImprovement's constructor (PolicyImprovement.cpp:52-58). */
+typedef struct stomp_b200_config {
+    int32_t abi_version;                 /* STOMP_B200_ABI_VERSION */
+    int32_t num_time_steps;              /* T  (num_time_steps_) */
+    int32_t num_dimensions;              /* D  (num_dimensions_) */
+    int32_t min_rollouts;                /* min_rollouts_ */
+    int32_t max_rollouts;                /* max_rollouts_ */
+    int32_t num_rollouts_per_iteration;  /* num_rollouts_per_iteration_ */
+    int32_t num_queries;                 /* Q_total: independent planning queries (batch mode); 1 = the reference */
+    double movement_duration;            /* movement_duration_ */
+    double control_cost_weight;          /* control_cost_weight_ */
+    double min_cost_improvement;         /* min_cost_improvement_ (stop rule, StompPlanner.cpp:117) */
+    double noise_stddev[STOMP_B200_MAX_DIMS];
+    double noise_decay[STOMP_B200_MAX_DIMS];
+    double noise_min_stddev[STOMP_B200_MAX_DIMS];
+    double derivative_weights[4];        /* position, velocity, acceleration, jerk; the reference task sets
+                                            {0,0,1,0} for every joint and time step (OptimizationTask.cpp:32-33) */
+    double cost_scaling_h;               /* 10.0 (PolicyImprovement.cpp:55) */
+    int32_t use_noise_adaptation;        /* use_noise_adaptation_ */
+    int32_t use_cumulative_costs;        /* 1 (PolicyImprovement.cpp:56) */
+    int32_t use_projection;              /* 0 (PolicyImprovement.cpp:57); 1 = M-matrix projected noise / update */
+    int32_t per_timestep_minmax;         /* 0 = shipped global min/max; 1 = variant commented out at :518-528 */
+    int32_t device;                      /* CUDA device ordinal */
+    int32_t world_size;                  /* ranks (one per GPU) sharing this solve; 1 = single GPU */
+    int32_t rank;
+    int32_t shard_mode;                  /* 0: rollouts of one query sharded over ranks (needs stomp_b200_comm_init);
+                                            1: queries sharded over ranks, no collective */
+    int32_t keep_debug_tensors;          /* 1: keep per-(k,d,t) control costs, unit noise and epsilon for read-back */
+    uint64_t seed;                       /* Philox seed of the on-device sampler */
+} stomp_b200_config;
+
+void stomp_b200_default_config(stomp_b200_config* cfg);
+int stomp_b200_abi_version(void);
+const char* stomp_b200_status_string(int status);
+/* text of the last failure on this engine (CUDA / NCCL error strings included); never NULL */
+const char* stomp_b200_last_error(const stomp_b200_engine* e);
+
+/* ---- lifecycle --------------------------------------------------------------------------------------
+ * create: what StompPlanner::initializePlanner + `new OptimizationTask` set up
+ * (StompPlanner.cpp:15-38, OptimizationTask.cpp:8-44), on the device. */
+int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out);
+int stomp_b200_destroy(stomp_b200_engine* e);
+
+/* ---- robot + scene: replaces robot_model::RobotModel::updateJointGroup + isStateValid ------------------
+ * (call sites OptimizationTask.cpp:190,192).  Joints are URDF joints in chain order
+ * (reference test/data/kuka_iiwa.urdf:162-210): origin xyz / rpy, axis, limits.  parent[d] is d-1, or -1
+ * for a joint that hangs off the fixed base frame (a second arm restarts the chain that way).
+ * prismatic may be NULL (all revolute).  lower/upper are what OptimizationTask::filter clamps to
+ * (OptimizationTask.cpp:85-106). */
+int stomp_b200_set_chain(stomp_b200_engine* e, int32_t num_joints, const double* origin_xyz /*[D][3]*/,
+                         const double* origin_rpy /*[D][3]*/, const double* axis /*[D][3]*/,
+                         const int32_t* parent /*[D]*/, const int32_t* prismatic /*[D] or NULL*/,
+                         const double* lower /*[D]*/, const double* upper /*[D]*/);
+/* link[s] = joint whose child link carries sphere s; must be sorted ascending (grasped-object spheres are
+ * spheres on the tip link). */
+int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int32_t* link /*[S]*/,
+                           const double* centre_xyz /*[S][3]*/, const double* radius /*[S]*/);
+/* FP32 signed distance grid, x fastest: grid[(z*ny + y)*nx + x]; origin = min corner of voxel (0,0,0).
+ * Nearest-voxel lookup, coordinates clamped to the grid.  The grid is copied to the device. */
+int stomp_b200_set_sdf(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
+                       const float* grid);
+
+/* ---- policy: the host-computed products of CovariantMovementPrimitive::initialize ----------------------
+ * (CovariantMovementPrimitive.cpp:57-74,136-301; computed by stomp_b200_host_policy below or by the
+ * C++ stomp::CovariantMovementPrimitive in include/stomp/).  R = control_costs_, Rinv = inv_control_costs_,
+ * L = chol(Rinv) (MultivariateGaussian.hpp:81); identical for every joint and query.  Rinv may be NULL
+ * unless use_projection. */
+int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R /*[T][T]*/,
+                                         const double* Rinv /*[T][T] or NULL*/, const double* L /*[T][T]*/);
+/* per query (local index): parameters_all_ [D][N] (padding = start / goal) and
+ * min_control_cost_parameters_free_ [D][T] */
+int stomp_b200_set_policy(stomp_b200_engine* e, int32_t query, const double* parameters_all /*[D][N]*/,
+                          const double* min_control_cost /*[D][T]*/);
+
+/* Host-side (CPU, one-time per query shape) CovariantMovementPrimitive::initialize +
+ * computeLinearControlCosts + (optionally) setToMinControlCost.  initial_all [D][N] is the padded
+ * initial trajectory (OptimizationTask::updateTrajectory, OptimizationTask.cpp:46-66).  Any output may
+ * be NULL.  No device needed. */
+int stomp_b200_host_policy(int32_t num_time_steps, int32_t num_dimensions, double movement_duration,
+                           const double derivative_weights[4], const double* initial_all /*[D][N]*/,
+                           int32_t set_to_min_control_cost, double* R, double* Rinv, double* L,
+                           double* parameters_all_out /*[D][N]*/, double* min_control_cost_out /*[D][T]*/);
+/* OptimizationTask::updateTrajectory (OptimizationTask.cpp:46-66): linear interpolation + padding */
+int stomp_b200_host_initial_trajectory(int32_t num_time_steps, int32_t num_dimensions, const double* start,
+                                       const double* goal, double* initial_all /*[D][N]*/);
+
+/* ---- the loop: StompPlanner::solve (StompPlanner.cpp:65-174) --------------------------------------------
+ * begin_solve = `new stomp::Stomp` + Stomp::initialize (Stomp.cpp:56-94): resets the rollout bookkeeping,
+ * the adapted noise and the noise-less rollout. */
+int stomp_b200_begin_solve(stomp_b200_engine* e);
+
+/* One Stomp::runSingleIteration (Stomp.cpp:274-301) for every query of the engine, then the wrapper's
+ * bookkeeping (StompPlanner.cpp:107-118).  Synchronous.  Noise sources, first non-NULL wins:
+ *   unit_noise [Q][G][D][T]: the output of MultivariateGaussian::sample (L*eps, zero mean) — parity mode;
+ *   epsilon    [Q][G][D][T]: standard normals, pushed through L on the device;
+ *   neither: Philox4x32-10 normals generated on the device.
+ * G = stomp_b200_next_num_generated(e).  Outputs (any may be NULL), per query:
+ * noiseless_total_cost (getNoiselessRolloutTotalCost), noiseless_valid (last_noiseless_rollout_valid_),
+ * stop (1 when the stop rule of StompPlanner.cpp:117 fired in this or an earlier iteration). */
+int stomp_b200_iterate(stomp_b200_engine* e, int32_t iteration, const double* unit_noise, const double* epsilon,
+                       double* noiseless_total_cost /*[Q]*/, uint8_t* noiseless_valid /*[Q]*/, int32_t* stop /*[Q]*/);
+int32_t stomp_b200_next_num_generated(const stomp_b200_engine* e);
+
+/* num_iterations passes of the loop body with the on-device sampler, queued without host round trips;
+ * a query whose stop rule fired is frozen (honour_stop != 0) exactly as `break` leaves it in the
+ * reference.  Returns after the last kernel finished. */
+int stomp_b200_run(stomp_b200_engine* e, int32_t first_iteration, int32_t num_iterations, int32_t honour_stop);
+
+/* end of StompPlanner::solve (:148-173): solution = parameters_all_[d][6+t] (the LAST parameters, not the
+ * best noise-less ones); status 1 = PATH_FOUND, 0 = NO_PATH_FOUND; iterations_used = getNumOfIterationsUsed. */
+int stomp_b200_finish_solve(stomp_b200_engine* e, double* solution /*[Q][D][T]*/, int32_t* status /*[Q]*/,
+                            int32_t* iterations_used /*[Q]*/, double* noiseless_total_cost /*[Q]*/);
+
+/* ---- read-backs of the state of the last iteration (parity tests; stomp::Rollout fields,
+ * PolicyImprovement.hpp:49-68).  Leading dimension is always the local query. */
+enum stomp_b200_tensor {
+    STOMP_B200_ROLLOUTS = 0,            /* parameters_noise_          [Q][K'][D][T] */
+    STOMP_B200_NOISE = 1,               /* noise_                     [Q][K'][D][T] */
+    STOMP_B200_STATE_COSTS = 2,         /* state_costs_               [Q][K'][T]    */
+    STOMP_B200_VERDICTS = 3,            /* 1 = in collision, uint8    [Q][K'][T]    */
+    STOMP_B200_CONTROL_COSTS = 4,       /* control_costs_             [Q][K'][D][T] (keep_debug_tensors) */
+    STOMP_B200_CUMULATIVE_COSTS = 5,    /* cumulative_costs_[d](0)    [Q][K'][D]  (cumulative mode: constant over t) */
+    STOMP_B200_FULL_COSTS = 6,          /* full_costs_                [Q][K'][D]    */
+    STOMP_B200_TOTAL_COST = 7,          /* total_cost_                [Q][K']       */
+    STOMP_B200_PROBABILITIES = 8,       /* probabilities_             [Q][K'][D][T] */
+    STOMP_B200_FULL_PROBABILITIES = 9,  /* full_probabilities_        [Q][K'][D]    */
+    STOMP_B200_UPDATES = 10,            /* parameter_updates_[d].row(0) [Q][D][T]   */
+    STOMP_B200_PARAMETERS = 11,         /* policy parameters (free)   [Q][D][T]     */
+    STOMP_B200_PARAMETERS_ALL = 12,     /* parameters_all_            [Q][D][N]     */
+    STOMP_B200_STDDEVS = 13,            /* adapted_stddevs_           [Q][D]        */
+    STOMP_B200_NOISELESS_STATE_COSTS = 14, /* noiseless_rollout_.state_costs_ [Q][T] */
+    STOMP_B200_NOISELESS_CONTROL_COSTS = 15, /*                       [Q][D][T]     */
+    STOMP_B200_UNIT_NOISE = 16,         /* L*eps of the generated rollouts [Q][G][D][T] (keep_debug_tensors) */
+    STOMP_B200_EPSILON = 17,            /* eps of the generated rollouts   [Q][G][D][T] (keep_debug_tensors) */
+    STOMP_B200_ROLLOUT_VALIDITY = 18    /* execute()'s validity, uint8     [Q][G]       */
+};
+int stomp_b200_num_rollouts(const stomp_b200_engine* e, int32_t* num_rollouts /*K'*/, int32_t* num_generated /*G*/);
+/* copies the tensor to host memory; out_bytes must equal its size */
+int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_t out_bytes);
+
+/* ---- the cost kernel on its own (Task::execute for arbitrary trajectories; also what
+ * MotionPlanners::checkStartState / checkGoalState need with K = 1, T = 1) -------------------------------
+ * theta [K][D][Tq] host; outputs host, any may be NULL. */
+int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_t num_trajectories,
+                               int32_t num_steps, double* state_costs /*[K][Tq]*/, uint8_t* verdicts /*[K][Tq]*/,
+                               uint8_t* validity /*[K]*/);
+/* sphere centres in the world frame for n joint configurations q [n][D] -> [n][S][3] */
+int stomp_b200_sphere_centres(stomp_b200_engine* e, const double* q, int32_t n, double* centres);
+
+/* ---- multi-GPU (shard_mode 0): one engine per rank; rank 0 makes the id, the host side broadcasts it ---- */
+#define STOMP_B200_COMM_ID_BYTES 128
+int stomp_b200_comm_unique_id(void* id_out /*[128]*/);
+int stomp_b200_comm_init(stomp_b200_engine* e, const void* id /*[128]*/);
+
+/* ---- measurement ----------------------------------------------------------------------------------- */
+enum stomp_b200_kernel {
+    STOMP_B200_KERNEL_SAMPLE = 0,       /* generateRollouts: L*eps contraction + mean shift + clamp */
+    STOMP_B200_KERNEL_COST = 1,         /* rollout cost: FK + sphere/SDF + control stencil + row sums */
+    STOMP_B200_KERNEL_WEIGHTS = 2,      /* computeRolloutProbabilities */
+    STOMP_B200_KERNEL_UPDATE = 3,       /* probability-weighted sums + n^T R n */
+    STOMP_B200_KERNEL_APPLY = 4,        /* updateParameters + noise adaptation + noise-less rollout */
+    STOMP_B200_KERNEL_REUSE = 5,        /* importance sort + gather of reused rollouts */
+    STOMP_B200_KERNEL_COUNT = 6
+};
+/* when on, every launch of the kernels above is bracketed by CUDA events on the engine's stream */
+int stomp_b200_set_profiling(stomp_b200_engine* e, int32_t on);
+int stomp_b200_kernel_stats(stomp_b200_engine* e, int32_t kernel, double* total_ms, int64_t* launches);
+int stomp_b200_reset_kernel_stats(stomp_b200_engine* e);
+/* total kernel launches issued by this engine since creation */
+int64_t stomp_b200_launch_count(const stomp_b200_engine* e);
+/* device-side timing of a region on the engine's stream: begin / end record events, end returns ms */
+int stomp_b200_timer_begin(stomp_b200_engine* e);
+int stomp_b200_timer_end(stomp_b200_engine* e, double* elapsed_ms);
+int stomp_b200_synchronize(stomp_b200_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STOMP_B200_H_ */

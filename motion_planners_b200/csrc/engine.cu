@@ -1,0 +1,1080 @@
+// Host orchestration + C ABI (include/stomp_b200.h) of the B200 STOMP rollout loop.
+//
+// One engine = one GPU = one CUDA stream.  The per-iteration sequence mirrors
+// stomp::Stomp::runSingleIteration (reference src/planners/stomp/src/Stomp.cpp:274-301):
+//   doGenRollouts  -> [reuse_rollouts_kernel] sample_rollouts_kernel | shift_rollouts_kernel
+//   doExecuteRollouts + setRolloutCosts -> rollout_cost_kernel [reused_control_cost_kernel]
+//   improvePolicy  -> [allgather] rollout_weights_kernel, weighted_update_kernel, reduce_partials_kernel [allreduce]
+//   updateParameters + doNoiselessRollout -> apply_update_kernel
+// The rollout bookkeeping (PolicyImprovement.cpp:170-186,304-308) is host integer arithmetic and stays here.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include "../../include/stomp_b200.h"
+#include "../host/policy_core.hpp"
+#include "kernels.cuh"
+
+using namespace stomp_b200;
+
+namespace {
+
+struct SigmaIt { double v[STOMP_B200_MAX_DIMS]; };
+
+__global__ void set_sigma_by_value_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ SigmaIt s)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.Q * p.D) return;
+    if (query_frozen(p, e / p.D)) return;
+    p.sigma[e] = s.v[e % p.D];
+    store_sampler_coefficients(p, e / p.D, e % p.D, s.v[e % p.D]);
+}
+
+__global__ void reset_solve_state_kernel(const __grid_constant__ LoopParams p)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= p.Q) return;
+    p.old_cost[q] = 0.0;
+    p.last_improvement[q] = 0.0;
+    p.best_cost[q] = 1.7976931348623157e308;
+    p.stop[q] = 0;
+    p.iters_used[q] = 0;
+    p.nl_total[q] = 0.0;
+    p.nl_valid[q] = 0;
+}
+
+// NCCL is bound at run time (dlopen) so that a single-GPU process never needs the library and a Python
+// host that already loaded its own libnccl.so.2 shares it.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err)
+    {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !AllReduce || !GetErrorString) {
+            err = "libnccl.so.2 lacks a required symbol";
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+struct ProfiledLaunch { int kernel; cudaEvent_t a, b; };
+
+}  // namespace
+
+struct stomp_b200_engine {
+    stomp_b200_config cfg;
+    int T = 0, D = 0, N = 0, Q = 0, slots = 0, gslots = 0, sumw = 0;
+    int query_offset = 0;
+    bool reuse_possible = false;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    std::vector<void*> allocations;
+
+    RobotParams robot;
+    SdfParams sdf;
+    float* d_sdf = nullptr;
+    bool have_chain = false, have_spheres = false, have_sdf = false, have_matrices = false;
+    std::vector<uint8_t> have_policy;
+
+    LoopParams base;                // pointers + constants; per-iteration fields filled in iterate
+    double* proj2[2] = {nullptr, nullptr};
+    double* state2[2] = {nullptr, nullptr};
+    uint8_t* verdict2[2] = {nullptr, nullptr};
+    int cur = 0;
+    int32_t* d_order = nullptr;
+    double* d_partial = nullptr;
+    int chunk = 32, max_chunks = 1;
+    double* d_theta_all_init = nullptr;   // policy as uploaded by set_policy (restored by begin_solve? no: the policy persists)
+
+    // PolicyImprovement bookkeeping (PolicyImprovement.cpp:170-186)
+    bool solving = false;
+    int num_rollouts = 0;           // num_rollouts_ after the previous iteration (global)
+    int last_gen = 0, last_local = 0, last_noiseless_slot = -1;
+    bool noiseless_valid = false, adapted_valid = false;
+
+    // pinned host mirrors of the per-query scalars
+    double* h_cost = nullptr; uint8_t* h_valid = nullptr; int32_t* h_stop = nullptr; int32_t* h_iters = nullptr;
+    double* h_impr = nullptr;
+
+    // measurement
+    bool profiling = false;
+    std::vector<ProfiledLaunch> pending;
+    double kernel_ms[STOMP_B200_KERNEL_COUNT] = {0};
+    int64_t kernel_launches[STOMP_B200_KERNEL_COUNT] = {0};
+    int64_t launch_count = 0;
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+
+    ncclComm_t comm = nullptr;
+};
+
+namespace {
+
+#define CUDA_TRY(e, call)                                                                                    \
+    do {                                                                                                     \
+        cudaError_t _err = (call);                                                                           \
+        if (_err != cudaSuccess) {                                                                           \
+            (e)->last_error = std::string(#call) + ": " + cudaGetErrorString(_err);                          \
+            return _err == cudaErrorMemoryAllocation ? STOMP_B200_ERR_OUT_OF_MEMORY : STOMP_B200_ERR_CUDA;   \
+        }                                                                                                    \
+    } while (0)
+
+#define NCCL_TRY(e, call)                                                                \
+    do {                                                                                 \
+        ncclResult_t _r = (call);                                                        \
+        if (_r != ncclSuccess) {                                                         \
+            (e)->last_error = std::string(#call) + ": " + g_nccl.GetErrorString(_r);     \
+            return STOMP_B200_ERR_NCCL;                                                  \
+        }                                                                                \
+    } while (0)
+
+int fail(stomp_b200_engine* e, int code, const char* msg)
+{
+    if (e) e->last_error = msg;
+    return code;
+}
+
+template <class Tp>
+int dev_alloc(stomp_b200_engine* e, Tp** out, size_t count)
+{
+    void* p = nullptr;
+    CUDA_TRY(e, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(Tp)));
+    CUDA_TRY(e, cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(Tp), e->stream));
+    e->allocations.push_back(p);
+    *out = static_cast<Tp*>(p);
+    return 0;
+}
+
+struct Scope {   // brackets one kernel launch with events when profiling is on
+    stomp_b200_engine* e; int kernel; cudaEvent_t a = nullptr, b = nullptr;
+    Scope(stomp_b200_engine* e_, int k) : e(e_), kernel(k)
+    {
+        if (e->profiling) {
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            cudaEventRecord(a, e->stream);
+        }
+    }
+    ~Scope()
+    {
+        e->launch_count++;
+        e->kernel_launches[kernel]++;
+        if (e->profiling) {
+            cudaEventRecord(b, e->stream);
+            e->pending.push_back({kernel, a, b});
+        }
+    }
+};
+
+void resolve_profile(stomp_b200_engine* e)
+{
+    for (auto& pl : e->pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(pl.b);
+        if (cudaEventElapsedTime(&ms, pl.a, pl.b) == cudaSuccess) e->kernel_ms[pl.kernel] += ms;
+        cudaEventDestroy(pl.a);
+        cudaEventDestroy(pl.b);
+    }
+    e->pending.clear();
+}
+
+int check_launch(stomp_b200_engine* e, const char* what)
+{
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        e->last_error = std::string(what) + ": " + cudaGetErrorString(err);
+        return STOMP_B200_ERR_CUDA;
+    }
+    return 0;
+}
+
+template <bool kPhilox>
+int launch_sample(stomp_b200_engine* e, const LoopParams& lp)
+{
+    const int ncols = lp.num_gen * lp.D;
+    dim3 grid((ncols + 63) / 64, lp.Q);
+    const int need = (lp.T + 15) / 16;
+    Scope s(e, STOMP_B200_KERNEL_SAMPLE);
+    if (need <= 2) sample_rollouts_kernel<2, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
+    else if (need <= 4) sample_rollouts_kernel<4, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
+    else if (need <= 7) sample_rollouts_kernel<7, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
+    else if (need <= 10) sample_rollouts_kernel<10, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
+    else if (need <= 13) sample_rollouts_kernel<13, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
+    else sample_rollouts_kernel<16, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
+    return check_launch(e, "sample_rollouts_kernel");
+}
+
+int rollouts_per_cta(const stomp_b200_engine* e, int num_gen)
+{
+    int R = std::max(1, 512 / e->T);
+    // keep at least ~2 CTAs per SM worth of work items when the rollout count is small
+    while (R > 1 && (num_gen + R - 1) / R < 296) --R;
+    return R;
+}
+
+enum NoiseMode { kNoisePhilox = 0, kNoiseUnit = 1, kNoiseEpsilon = 2 };
+
+// one Stomp::runSingleIteration for all local queries, queued on the stream (no host synchronisation)
+int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop)
+{
+    const stomp_b200_config& c = e->cfg;
+    const int world = c.shard_mode == 0 ? c.world_size : 1;
+    // ---- PolicyImprovement::generateRollouts bookkeeping (PolicyImprovement.cpp:170-186) ----
+    const int prev = e->num_rollouts;
+    int gen = c.num_rollouts_per_iteration;
+    int reused = prev;
+    if (prev + gen < c.min_rollouts) gen = c.min_rollouts - prev;
+    if (prev + gen > c.max_rollouts) reused = prev - (prev + gen - c.max_rollouts);
+    if (reused < 0) reused = 0;
+    if (world > 1 && (reused != 0 || gen % world != 0))
+        return fail(e, STOMP_B200_ERR_UNSUPPORTED, "rollout sharding needs min = max = per-iteration rollouts, divisible by world_size");
+    if (!e->reuse_possible && reused != 0) return fail(e, STOMP_B200_ERR_UNSUPPORTED, "internal: reuse without reuse buffers");
+    const int gen_local = gen / world;
+    int n = reused + gen;
+    const bool have_nl = e->noiseless_valid;
+    const int nl_gslot = have_nl ? n : -1;
+    if (have_nl) ++n;
+
+    LoopParams lp = e->base;
+    lp.num_gen = gen_local;
+    lp.gen_global = gen;
+    lp.gen_offset = (world > 1) ? c.rank * gen_local : 0;
+    lp.num_rollouts = n;
+    lp.noiseless_slot = have_nl ? gen_local + reused : -1;
+    lp.noiseless_gslot = nl_gslot;
+    lp.num_local = gen_local + reused + (have_nl ? 1 : 0);
+    lp.honour_stop = honour_stop;
+    lp.iteration = iteration;
+    lp.store_unit = c.keep_debug_tensors;
+
+    // ---- noise magnitude (Stomp.cpp:179, PolicyImprovement.cpp:162-163) ----
+    if (!e->adapted_valid) {
+        SigmaIt s;
+        for (int d = 0; d < e->D; ++d) s.v[d] = c.noise_stddev[d] * std::pow(c.noise_decay[d], iteration - 1);
+        Scope sc(e, STOMP_B200_KERNEL_APPLY);
+        set_sigma_by_value_kernel<<<(e->Q * e->D + 127) / 128, 128, 0, e->stream>>>(lp, s);
+        if (int rc = check_launch(e, "set_sigma_kernel")) return rc;
+    }
+
+    // ---- reused rollouts (PolicyImprovement.cpp:188-255) ----
+    if (e->reuse_possible) {
+        const int src = e->cur, dst = 1 - e->cur;
+        lp.proj = e->proj2[dst]; lp.state_costs = e->state2[dst]; lp.verdicts = e->verdict2[dst];
+        if (reused > 0) {
+            ReuseParams rp;
+            rp.prev = prev; rp.reused = reused; rp.gen = gen_local;
+            rp.src_proj = e->proj2[src]; rp.src_state = e->state2[src]; rp.src_verdict = e->verdict2[src];
+            rp.src_total = lp.total_cost; rp.order = e->d_order;
+            Scope sc(e, STOMP_B200_KERNEL_REUSE);
+            reuse_rollouts_kernel<<<e->Q, 256, sizeof(double) * (size_t)prev, e->stream>>>(lp, rp);
+            if (int rc = check_launch(e, "reuse_rollouts_kernel")) return rc;
+        }
+        e->cur = dst;
+        e->base.proj = lp.proj; e->base.state_costs = lp.state_costs; e->base.verdicts = lp.verdicts;
+    }
+
+    // ---- generate (K1-K3) ----
+    if (mode == kNoiseUnit) {
+        Scope sc(e, STOMP_B200_KERNEL_SAMPLE);
+        const int per_query = gen_local * e->D * e->T;
+        dim3 grid(std::min(1024, (per_query + 255) / 256), e->Q);
+        shift_rollouts_kernel<<<grid, 256, 0, e->stream>>>(lp, e->robot);
+        if (int rc = check_launch(e, "shift_rollouts_kernel")) return rc;
+    } else if (mode == kNoiseEpsilon) {
+        if (int rc = launch_sample<false>(e, lp)) return rc;
+    } else {
+        if (int rc = launch_sample<true>(e, lp)) return rc;
+    }
+
+    // ---- execute + control costs + row sums (K4-K6) ----
+    {
+        const int R = rollouts_per_cta(e, gen_local);
+        const int threads = std::max(64, ((R * e->T + 31) / 32) * 32);
+        const size_t smem = sizeof(double) * ((size_t)R * e->D * e->N + (size_t)R * e->T);
+        dim3 grid((gen_local + R - 1) / R + 1, e->Q);
+        Scope sc(e, STOMP_B200_KERNEL_COST);
+        rollout_cost_kernel<<<grid, threads, smem, e->stream>>>(lp, e->robot, e->sdf, R);
+        if (int rc = check_launch(e, "rollout_cost_kernel")) return rc;
+    }
+    if (reused > 0) {
+        const int warps = 8;
+        const size_t smem = sizeof(double) * (size_t)warps * (e->N + e->T);
+        dim3 grid(std::min(148, (reused * e->D + warps - 1) / warps), e->Q);
+        Scope sc(e, STOMP_B200_KERNEL_REUSE);
+        reused_control_cost_kernel<<<grid, warps * 32, smem, e->stream>>>(lp, gen_local, reused);
+        if (int rc = check_launch(e, "reused_control_cost_kernel")) return rc;
+    }
+
+    // ---- exchange 1: per-rollout cost scalars ----
+    if (world > 1) {
+        if (!e->comm) return fail(e, STOMP_B200_ERR_NOT_READY, "world_size > 1 needs stomp_b200_comm_init");
+        const size_t count = (size_t)gen_local * e->sumw;
+        NCCL_TRY(e, g_nccl.AllGather(lp.sums + (size_t)c.rank * count, lp.sums, count, ncclFloat64, e->comm, e->stream));
+    }
+
+    // ---- probabilities (K7) ----
+    {
+        Scope sc(e, STOMP_B200_KERNEL_WEIGHTS);
+        rollout_weights_kernel<<<dim3(e->D, e->Q), 256, 0, e->stream>>>(lp);
+        if (int rc = check_launch(e, "rollout_weights_kernel")) return rc;
+    }
+    // ---- weighted sums (K8) ----
+    {
+        const int nchunks = std::max(1, (lp.num_local + e->chunk - 1) / e->chunk);
+        const size_t smem = sizeof(double) * ((size_t)kUpdateWarps * (e->T + 2 * kRBand) + (size_t)kUpdateWarps * (e->T + 1));
+        {
+            Scope sc(e, STOMP_B200_KERNEL_UPDATE);
+            weighted_update_kernel<<<dim3(nchunks, e->D, e->Q), kUpdateWarps * 32, smem, e->stream>>>(lp, e->d_partial, e->chunk, nchunks);
+            if (int rc = check_launch(e, "weighted_update_kernel")) return rc;
+        }
+        {
+            Scope sc(e, STOMP_B200_KERNEL_UPDATE);
+            reduce_partials_kernel<<<dim3(e->D, e->Q), 256, 0, e->stream>>>(lp, e->d_partial, nchunks);
+            if (int rc = check_launch(e, "reduce_partials_kernel")) return rc;
+        }
+    }
+    // ---- exchange 2: update rows + adaptation numerators ----
+    if (world > 1) {
+        const size_t count = (size_t)e->Q * e->D * (e->T + 1);
+        NCCL_TRY(e, g_nccl.AllReduce(lp.updbuf, lp.updbuf, count, ncclFloat64, ncclSum, e->comm, e->stream));
+    }
+    // ---- apply + noise-less rollout (K9, K10) ----
+    {
+        const size_t smem = sizeof(double) * ((size_t)e->D * e->N + e->T + e->sumw);
+        Scope sc(e, STOMP_B200_KERNEL_APPLY);
+        apply_update_kernel<<<e->Q, 256, smem, e->stream>>>(lp, e->robot, e->sdf);
+        if (int rc = check_launch(e, "apply_update_kernel")) return rc;
+    }
+
+    e->num_rollouts = n;
+    e->last_gen = gen_local;
+    e->last_local = lp.num_local;
+    e->last_noiseless_slot = lp.noiseless_slot;
+    e->noiseless_valid = true;
+    if (c.use_noise_adaptation) e->adapted_valid = true;
+    return 0;
+}
+
+int ready_to_solve(stomp_b200_engine* e)
+{
+    if (!e->have_chain || !e->have_spheres || !e->have_sdf || !e->have_matrices)
+        return fail(e, STOMP_B200_ERR_NOT_READY, "chain, spheres, SDF and control-cost matrices must be set first");
+    for (int q = 0; q < e->Q; ++q)
+        if (!e->have_policy[q]) return fail(e, STOMP_B200_ERR_NOT_READY, "stomp_b200_set_policy missing for a query");
+    return 0;
+}
+
+int fetch_query_scalars(stomp_b200_engine* e)
+{
+    const LoopParams& b = e->base;
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_cost, b.nl_total, sizeof(double) * e->Q, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_valid, b.nl_valid, e->Q, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_stop, b.stop, sizeof(int32_t) * e->Q, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_iters, b.iters_used, sizeof(int32_t) * e->Q, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_impr, b.last_improvement, sizeof(double) * e->Q, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    resolve_profile(e);
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int stomp_b200_abi_version(void) { return STOMP_B200_ABI_VERSION; }
+
+void stomp_b200_default_config(stomp_b200_config* cfg)
+{
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->abi_version = STOMP_B200_ABI_VERSION;
+    cfg->num_queries = 1;
+    cfg->movement_duration = 5.0;
+    cfg->control_cost_weight = 0.001;
+    cfg->min_cost_improvement = 0.01;
+    for (int d = 0; d < STOMP_B200_MAX_DIMS; ++d) { cfg->noise_stddev[d] = 0.1; cfg->noise_decay[d] = 1.0; cfg->noise_min_stddev[d] = 0.01; }
+    cfg->derivative_weights[2] = 1.0;
+    cfg->cost_scaling_h = 10.0;
+    cfg->use_noise_adaptation = 1;
+    cfg->use_cumulative_costs = 1;
+    cfg->world_size = 1;
+    cfg->seed = 2024;
+}
+
+const char* stomp_b200_status_string(int status)
+{
+    switch (status) {
+        case STOMP_B200_OK: return "ok";
+        case STOMP_B200_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case STOMP_B200_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case STOMP_B200_ERR_CUDA: return "CUDA error";
+        case STOMP_B200_ERR_NOT_READY: return "engine not ready";
+        case STOMP_B200_ERR_UNSUPPORTED: return "not supported by this build";
+        case STOMP_B200_ERR_NCCL: return "NCCL error";
+        case STOMP_B200_ERR_OUT_OF_MEMORY: return "out of device memory";
+        default: return "unknown status";
+    }
+}
+
+const char* stomp_b200_last_error(const stomp_b200_engine* e) { return e ? e->last_error.c_str() : "null engine"; }
+
+int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
+{
+    if (!cfg || !out) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (cfg->abi_version != STOMP_B200_ABI_VERSION) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (cfg->num_dimensions < 1 || cfg->num_dimensions > STOMP_B200_MAX_DIMS) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (cfg->num_time_steps < 2 || cfg->num_time_steps > STOMP_B200_MAX_TIME_STEPS) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (cfg->num_rollouts_per_iteration < 1 || cfg->max_rollouts < cfg->num_rollouts_per_iteration ||
+        cfg->min_rollouts > cfg->max_rollouts || cfg->min_rollouts < 1)
+        return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (cfg->num_queries < 1 || cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+        return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (cfg->shard_mode != 0 && cfg->shard_mode != 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (cfg->use_projection || !cfg->use_cumulative_costs || cfg->per_timestep_minmax)
+        return STOMP_B200_ERR_UNSUPPORTED;   // switches the reference ships disabled; DESIGN.md "out of scope"
+    if (cfg->shard_mode == 0 && cfg->world_size > 1 && cfg->num_queries != 1) return STOMP_B200_ERR_UNSUPPORTED;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return STOMP_B200_ERR_NO_DEVICE;
+    if (cfg->device < 0 || cfg->device >= ndev) return STOMP_B200_ERR_INVALID_ARGUMENT;
+
+    stomp_b200_engine* e = new stomp_b200_engine();
+    e->cfg = *cfg;
+    e->T = cfg->num_time_steps; e->D = cfg->num_dimensions; e->N = e->T + 2 * kPad;
+    e->sumw = 1 + 2 * e->D;
+    if (cfg->shard_mode == 1 && cfg->world_size > 1) {
+        const int per = (cfg->num_queries + cfg->world_size - 1) / cfg->world_size;
+        e->query_offset = std::min(cfg->num_queries, cfg->rank * per);
+        e->Q = std::max(0, std::min(cfg->num_queries, e->query_offset + per) - e->query_offset);
+        if (e->Q == 0) { delete e; return STOMP_B200_ERR_INVALID_ARGUMENT; }
+    } else {
+        e->Q = cfg->num_queries;
+    }
+    const int world = cfg->shard_mode == 0 ? cfg->world_size : 1;
+    e->reuse_possible = cfg->num_rollouts_per_iteration < cfg->max_rollouts || cfg->min_rollouts > cfg->num_rollouts_per_iteration;
+    if (world > 1 && e->reuse_possible) { delete e; return STOMP_B200_ERR_UNSUPPORTED; }
+    e->gslots = cfg->max_rollouts + 1;
+    e->slots = (world > 1 ? cfg->max_rollouts / world : cfg->max_rollouts) + 1;
+    e->have_policy.assign(e->Q, 0);
+
+#define CREATE_TRY(call)                       \
+    do {                                       \
+        int _rc = (call);                      \
+        if (_rc != 0) {                        \
+            stomp_b200_destroy(e);             \
+            return _rc;                        \
+        }                                      \
+    } while (0)
+#define CREATE_CUDA(call)                                                          \
+    do {                                                                           \
+        cudaError_t _err = (call);                                                 \
+        if (_err != cudaSuccess) {                                                 \
+            std::fprintf(stderr, "stomp_b200_create: %s: %s\n", #call, cudaGetErrorString(_err)); \
+            stomp_b200_destroy(e);                                                 \
+            return STOMP_B200_ERR_CUDA;                                            \
+        }                                                                          \
+    } while (0)
+
+    CREATE_CUDA(cudaSetDevice(cfg->device));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreate(&e->timer_a));
+    CREATE_CUDA(cudaEventCreate(&e->timer_b));
+
+    const size_t Q = e->Q, T = e->T, D = e->D, N = e->N, S = e->slots, GS = e->gslots;
+    LoopParams& b = e->base;
+    std::memset(&b, 0, sizeof(b));
+    b.T = e->T; b.D = e->D; b.N = e->N; b.Q = e->Q; b.slots = e->slots; b.gslots = e->gslots; b.sumw = e->sumw;
+    b.query_offset = e->query_offset;
+    b.control_cost_weight = cfg->control_cost_weight;
+    b.dt = cfg->movement_duration / (cfg->num_time_steps + 1);
+    b.cost_scaling_h = cfg->cost_scaling_h;
+    b.min_cost_improvement = cfg->min_cost_improvement;
+    b.use_noise_adaptation = cfg->use_noise_adaptation;
+    b.seed = cfg->seed;
+    b.noiseless_slot = -1;
+
+    double* tmp = nullptr;
+    CREATE_TRY(dev_alloc(e, &b.theta_all, Q * D * N));
+    CREATE_TRY(dev_alloc(e, &tmp, Q * D * T)); b.mincc = tmp;
+    CREATE_TRY(dev_alloc(e, &b.rollouts, Q * S * D * T));
+    CREATE_TRY(dev_alloc(e, &b.noise, Q * S * D * T));
+    for (int i = 0; i < (e->reuse_possible ? 2 : 1); ++i) {
+        CREATE_TRY(dev_alloc(e, &e->state2[i], Q * S * T));
+        CREATE_TRY(dev_alloc(e, &e->verdict2[i], Q * S * T));
+        if (e->reuse_possible) CREATE_TRY(dev_alloc(e, &e->proj2[i], Q * S * D * T));
+    }
+    b.state_costs = e->state2[0]; b.verdicts = e->verdict2[0]; b.proj = e->proj2[0];
+    CREATE_TRY(dev_alloc(e, &b.validity, Q * S));
+    if (cfg->keep_debug_tensors) CREATE_TRY(dev_alloc(e, &b.control_costs, Q * S * D * T));
+    CREATE_TRY(dev_alloc(e, &b.sums, Q * GS * e->sumw));
+    CREATE_TRY(dev_alloc(e, &b.total_cost, Q * GS));
+    CREATE_TRY(dev_alloc(e, &b.prob, Q * GS * D));
+    CREATE_TRY(dev_alloc(e, &b.fprob, Q * GS * D));
+    CREATE_TRY(dev_alloc(e, &b.fprob_sum, Q * D));
+    CREATE_TRY(dev_alloc(e, &b.sigma, Q * D));
+    CREATE_TRY(dev_alloc(e, &b.coef, Q * D * 3));
+    CREATE_TRY(dev_alloc(e, &b.updbuf, Q * D * (T + 1)));
+    CREATE_TRY(dev_alloc(e, &b.updates, Q * D * T));
+    const size_t gen_cap = (size_t)std::max(cfg->num_rollouts_per_iteration, cfg->min_rollouts) / world + 1;
+    CREATE_TRY(dev_alloc(e, &b.unit_noise, Q * gen_cap * D * T));
+    CREATE_TRY(dev_alloc(e, &b.epsilon, Q * gen_cap * D * T));
+    CREATE_TRY(dev_alloc(e, &b.nl_state, Q * T));
+    CREATE_TRY(dev_alloc(e, &b.nl_verdict, Q * T));
+    CREATE_TRY(dev_alloc(e, &b.nl_control, Q * D * T));
+    CREATE_TRY(dev_alloc(e, &b.nl_sums, Q * e->sumw));
+    CREATE_TRY(dev_alloc(e, &b.nl_total, Q));
+    CREATE_TRY(dev_alloc(e, &b.nl_valid, Q));
+    CREATE_TRY(dev_alloc(e, &b.old_cost, Q));
+    CREATE_TRY(dev_alloc(e, &b.last_improvement, Q));
+    CREATE_TRY(dev_alloc(e, &b.best_cost, Q));
+    CREATE_TRY(dev_alloc(e, &b.stop, Q));
+    CREATE_TRY(dev_alloc(e, &b.iters_used, Q));
+    CREATE_TRY(dev_alloc(e, &e->d_order, Q * S));
+    e->chunk = 32;
+    e->max_chunks = (int)((S + e->chunk - 1) / e->chunk);
+    CREATE_TRY(dev_alloc(e, &e->d_partial, Q * e->max_chunks * D * (T + 1)));
+
+    // control-cost operator: banded differentiation matrices of the active rules (StompUtils.cpp:6-23)
+    {
+        std::vector<double> band((size_t)kMaxRules * N * 7, 0.0);
+        b.num_rules = 0;
+        for (int r = 0; r < kMaxRules; ++r) {
+            host::DiffBand db = host::differentiation_band(e->N, r, b.dt);
+            std::copy(db.c.begin(), db.c.end(), band.begin() + (size_t)r * N * 7);
+            if (cfg->derivative_weights[r] != 0.0) {
+                b.rule_id[b.num_rules] = r;
+                b.rule_sqrt_w[b.num_rules] = std::sqrt(cfg->derivative_weights[r]);
+                b.num_rules++;
+            }
+        }
+        CREATE_TRY(dev_alloc(e, &tmp, band.size())); b.diff_band = tmp;
+        CREATE_CUDA(cudaMemcpyAsync(tmp, band.data(), sizeof(double) * band.size(), cudaMemcpyHostToDevice, e->stream));
+        CREATE_TRY(dev_alloc(e, &tmp, D)); b.min_stddev = tmp;
+        CREATE_CUDA(cudaMemcpyAsync(tmp, cfg->noise_min_stddev, sizeof(double) * D, cudaMemcpyHostToDevice, e->stream));
+        CREATE_TRY(dev_alloc(e, &tmp, T * T)); b.Lt = tmp;
+        CREATE_TRY(dev_alloc(e, &tmp, T * (2 * kRBand + 1))); b.Rband = tmp;
+        CREATE_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    CREATE_CUDA(cudaMallocHost(&e->h_cost, sizeof(double) * Q));
+    CREATE_CUDA(cudaMallocHost(&e->h_impr, sizeof(double) * Q));
+    CREATE_CUDA(cudaMallocHost(&e->h_valid, Q));
+    CREATE_CUDA(cudaMallocHost(&e->h_stop, sizeof(int32_t) * Q));
+    CREATE_CUDA(cudaMallocHost(&e->h_iters, sizeof(int32_t) * Q));
+    CREATE_CUDA(cudaFuncSetAttribute(rollout_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CREATE_CUDA(cudaFuncSetAttribute(apply_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CREATE_CUDA(cudaFuncSetAttribute(reuse_rollouts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    std::memset(&e->robot, 0, sizeof(e->robot));
+    std::memset(&e->sdf, 0, sizeof(e->sdf));
+    CREATE_CUDA(cudaStreamSynchronize(e->stream));
+#undef CREATE_TRY
+#undef CREATE_CUDA
+    *out = e;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_destroy(stomp_b200_engine* e)
+{
+    if (!e) return STOMP_B200_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    resolve_profile(e);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (void* p : e->allocations) cudaFree(p);
+    if (e->d_sdf) cudaFree(e->d_sdf);
+    if (e->h_cost) cudaFreeHost(e->h_cost);
+    if (e->h_impr) cudaFreeHost(e->h_impr);
+    if (e->h_valid) cudaFreeHost(e->h_valid);
+    if (e->h_stop) cudaFreeHost(e->h_stop);
+    if (e->h_iters) cudaFreeHost(e->h_iters);
+    if (e->timer_a) cudaEventDestroy(e->timer_a);
+    if (e->timer_b) cudaEventDestroy(e->timer_b);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return STOMP_B200_OK;
+}
+
+// fixed rotation of a URDF joint origin: Rz(yaw) * Ry(pitch) * Rx(roll)
+static void rpy_matrix(const double rpy[3], double A[9])
+{
+    double sr, cr, sp, cp, sy, cy;
+    det_sincos(rpy[0], sr, cr);
+    det_sincos(rpy[1], sp, cp);
+    det_sincos(rpy[2], sy, cy);
+    A[0] = cy * cp; A[1] = cy * sp * sr - sy * cr; A[2] = cy * sp * cr + sy * sr;
+    A[3] = sy * cp; A[4] = sy * sp * sr + cy * cr; A[5] = sy * sp * cr - cy * sr;
+    A[6] = -sp;     A[7] = cp * sr;                A[8] = cp * cr;
+}
+
+int stomp_b200_set_chain(stomp_b200_engine* e, int32_t num_joints, const double* origin_xyz, const double* origin_rpy,
+                         const double* axis, const int32_t* parent, const int32_t* prismatic, const double* lower,
+                         const double* upper)
+{
+    if (!e || !origin_xyz || !origin_rpy || !axis || !lower || !upper) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (num_joints != e->D) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "num_joints != num_dimensions");
+    RobotParams& r = e->robot;
+    r.num_joints = num_joints;
+    for (int d = 0; d < num_joints; ++d) {
+        JointParams& j = r.joint[d];
+        j.parent = parent ? parent[d] : (d == 0 ? -1 : d - 1);
+        if (!(j.parent == -1 || j.parent == d - 1))
+            return fail(e, STOMP_B200_ERR_UNSUPPORTED, "parent[d] must be d-1 or -1 (serial chains, restartable)");
+        j.prismatic = prismatic ? prismatic[d] : 0;
+        const double* a = axis + 3 * d;
+        for (int i = 0; i < 3; ++i) { j.o[i] = origin_xyz[3 * d + i]; j.axis[i] = a[i]; }
+        const double* rpy = origin_rpy + 3 * d;
+        j.fixed_rot_identity = (rpy[0] == 0.0 && rpy[1] == 0.0 && rpy[2] == 0.0) ? 1 : 0;
+        rpy_matrix(rpy, j.A);
+        if (j.fixed_rot_identity) { j.A[0] = j.A[4] = j.A[8] = 1.0; j.A[1] = j.A[2] = j.A[3] = j.A[5] = j.A[6] = j.A[7] = 0.0; }
+        int kind = kAxisGeneral;
+        if (a[1] == 0.0 && a[2] == 0.0 && a[0] == 1.0) kind = kAxisX;
+        else if (a[0] == 0.0 && a[2] == 0.0 && a[1] == 1.0) kind = kAxisY;
+        else if (a[0] == 0.0 && a[1] == 0.0 && a[2] == 1.0) kind = kAxisZ;
+        else if (a[1] == 0.0 && a[2] == 0.0 && a[0] == -1.0) kind = kAxisNegX;
+        else if (a[0] == 0.0 && a[2] == 0.0 && a[1] == -1.0) kind = kAxisNegY;
+        else if (a[0] == 0.0 && a[1] == 0.0 && a[2] == -1.0) kind = kAxisNegZ;
+        j.axis_kind = kind;
+        r.lower[d] = lower[d];
+        r.upper[d] = upper[d];
+    }
+    e->have_chain = true;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int32_t* link, const double* centre_xyz,
+                           const double* radius)
+{
+    if (!e || !link || !centre_xyz || !radius) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (num_spheres < 1 || num_spheres > STOMP_B200_MAX_SPHERES) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "sphere count out of range");
+    RobotParams& r = e->robot;
+    r.num_spheres = num_spheres;
+    for (int d = 0; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = 0;
+    for (int s = 0; s < num_spheres; ++s) {
+        if (link[s] < 0 || link[s] >= e->D) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "sphere link out of range");
+        if (s > 0 && link[s] < link[s - 1]) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "spheres must be sorted by link");
+        for (int i = 0; i < 3; ++i) r.sphere[s].l[i] = centre_xyz[3 * s + i];
+        r.sphere[s].r = radius[s];
+        r.sphere_begin[link[s] + 1] = s + 1;
+    }
+    for (int d = 1; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = std::max(r.sphere_begin[d], r.sphere_begin[d - 1]);
+    e->have_spheres = true;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_set_sdf(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size, const float* grid)
+{
+    if (!e || !dims || !origin || !grid || !(voxel_size > 0.0)) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    const size_t count = (size_t)dims[0] * dims[1] * dims[2];
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (e->d_sdf) { cudaFree(e->d_sdf); e->d_sdf = nullptr; }
+    CUDA_TRY(e, cudaMalloc(&e->d_sdf, count * sizeof(float)));
+    CUDA_TRY(e, cudaMemcpy(e->d_sdf, grid, count * sizeof(float), cudaMemcpyHostToDevice));
+    e->sdf.grid = e->d_sdf;
+    e->sdf.nx = dims[0]; e->sdf.ny = dims[1]; e->sdf.nz = dims[2];
+    e->sdf.ox = origin[0]; e->sdf.oy = origin[1]; e->sdf.oz = origin[2];
+    e->sdf.inv_h = 1.0 / voxel_size;
+    e->have_sdf = true;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R, const double* Rinv, const double* L)
+{
+    (void)Rinv;
+    if (!e || !R || !L) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    const int T = e->T;
+    std::vector<double> Lt((size_t)T * T), band((size_t)T * (2 * kRBand + 1), 0.0);
+    for (int t = 0; t < T; ++t)
+        for (int u = 0; u < T; ++u) {
+            Lt[(size_t)u * T + t] = (u <= t) ? L[(size_t)t * T + u] : 0.0;
+            const int o = u - t + kRBand;
+            if (o >= 0 && o <= 2 * kRBand) band[(size_t)t * (2 * kRBand + 1) + o] = R[(size_t)t * T + u];
+            else if (R[(size_t)t * T + u] != 0.0)
+                return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "R has entries outside the 13-wide band of 7-tap rules");
+        }
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.Lt), Lt.data(), sizeof(double) * Lt.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.Rband), band.data(), sizeof(double) * band.size(), cudaMemcpyHostToDevice));
+    e->have_matrices = true;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_set_policy(stomp_b200_engine* e, int32_t query, const double* parameters_all, const double* min_control_cost)
+{
+    if (!e || !parameters_all || !min_control_cost) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (query < 0 || query >= e->Q) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "query index out of range");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaMemcpy(e->base.theta_all + (size_t)query * e->D * e->N, parameters_all, sizeof(double) * e->D * e->N, cudaMemcpyHostToDevice));
+    CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.mincc) + (size_t)query * e->D * e->T, min_control_cost, sizeof(double) * e->D * e->T, cudaMemcpyHostToDevice));
+    e->have_policy[query] = 1;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_host_policy(int32_t num_time_steps, int32_t num_dimensions, double movement_duration,
+                           const double derivative_weights[4], const double* initial_all, int32_t set_to_min_control_cost,
+                           double* R, double* Rinv, double* L, double* parameters_all_out, double* min_control_cost_out)
+{
+    if (!derivative_weights || !initial_all || num_time_steps < 2 || num_dimensions < 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    host::PolicyCore pc;
+    if (!pc.initialize(num_time_steps, num_dimensions, movement_duration, derivative_weights, initial_all))
+        return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (set_to_min_control_cost) pc.setToMinControlCost();
+    else pc.updateMinControlCostParameters(pc.params_all.data());
+    const size_t T = num_time_steps;
+    if (R) std::memcpy(R, pc.R.data(), sizeof(double) * T * T);
+    if (Rinv) std::memcpy(Rinv, pc.Rinv.data(), sizeof(double) * T * T);
+    if (L) std::memcpy(L, pc.L.data(), sizeof(double) * T * T);
+    if (parameters_all_out) std::memcpy(parameters_all_out, pc.params_all.data(), sizeof(double) * pc.params_all.size());
+    if (min_control_cost_out) std::memcpy(min_control_cost_out, pc.mincc.data(), sizeof(double) * pc.mincc.size());
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_host_initial_trajectory(int32_t num_time_steps, int32_t num_dimensions, const double* start,
+                                       const double* goal, double* initial_all)
+{
+    if (!start || !goal || !initial_all || num_time_steps < 2 || num_dimensions < 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    host::linear_initial_trajectory(num_time_steps, num_dimensions, start, goal, initial_all);
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_begin_solve(stomp_b200_engine* e)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (int rc = ready_to_solve(e)) return rc;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    e->num_rollouts = 0;
+    e->noiseless_valid = false;
+    e->adapted_valid = false;
+    e->last_gen = 0; e->last_local = 0; e->last_noiseless_slot = -1;
+    reset_solve_state_kernel<<<(e->Q + 127) / 128, 128, 0, e->stream>>>(e->base);
+    e->launch_count++;
+    if (int rc = check_launch(e, "reset_solve_state_kernel")) return rc;
+    e->solving = true;
+    return STOMP_B200_OK;
+}
+
+int32_t stomp_b200_next_num_generated(const stomp_b200_engine* e)
+{
+    if (!e) return 0;
+    const stomp_b200_config& c = e->cfg;
+    int gen = c.num_rollouts_per_iteration;
+    if (e->num_rollouts + gen < c.min_rollouts) gen = c.min_rollouts - e->num_rollouts;
+    const int world = c.shard_mode == 0 ? c.world_size : 1;
+    return gen / world;
+}
+
+int stomp_b200_iterate(stomp_b200_engine* e, int32_t iteration, const double* unit_noise, const double* epsilon,
+                       double* noiseless_total_cost, uint8_t* noiseless_valid, int32_t* stop)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!e->solving) return fail(e, STOMP_B200_ERR_NOT_READY, "stomp_b200_begin_solve first");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    const size_t count = (size_t)e->Q * stomp_b200_next_num_generated(e) * e->D * e->T;
+    int mode = kNoisePhilox;
+    if (unit_noise) {
+        mode = kNoiseUnit;
+        CUDA_TRY(e, cudaMemcpyAsync(e->base.unit_noise, unit_noise, sizeof(double) * count, cudaMemcpyHostToDevice, e->stream));
+    } else if (epsilon) {
+        mode = kNoiseEpsilon;
+        CUDA_TRY(e, cudaMemcpyAsync(e->base.epsilon, epsilon, sizeof(double) * count, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (int rc = iterate_async(e, iteration, mode, 0)) return rc;
+    if (int rc = fetch_query_scalars(e)) return rc;
+    for (int q = 0; q < e->Q; ++q) {
+        if (noiseless_total_cost) noiseless_total_cost[q] = e->h_cost[q];
+        if (noiseless_valid) noiseless_valid[q] = e->h_valid[q];
+        if (stop) stop[q] = e->h_stop[q];
+    }
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_run(stomp_b200_engine* e, int32_t first_iteration, int32_t num_iterations, int32_t honour_stop)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!e->solving) return fail(e, STOMP_B200_ERR_NOT_READY, "stomp_b200_begin_solve first");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    for (int i = 0; i < num_iterations; ++i)
+        if (int rc = iterate_async(e, first_iteration + i, kNoisePhilox, honour_stop ? 1 : 0)) return rc;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    resolve_profile(e);
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_finish_solve(stomp_b200_engine* e, double* solution, int32_t* status, int32_t* iterations_used,
+                            double* noiseless_total_cost)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (int rc = fetch_query_scalars(e)) return rc;
+    if (solution) {
+        // parameters_all_[d][6 + t]  (StompPlanner.cpp:148-163)
+        CUDA_TRY(e, cudaMemcpy2D(solution, sizeof(double) * e->T, e->base.theta_all + kPad, sizeof(double) * e->N,
+                                 sizeof(double) * e->T, (size_t)e->Q * e->D, cudaMemcpyDeviceToHost));
+    }
+    for (int q = 0; q < e->Q; ++q) {
+        if (status)
+            status[q] = ((e->h_cost[q] < 1) && (std::fabs(e->h_impr[q]) <= e->cfg.min_cost_improvement)) ? 1 : 0;
+        if (iterations_used) iterations_used[q] = e->h_iters[q];
+        if (noiseless_total_cost) noiseless_total_cost[q] = e->h_cost[q];
+    }
+    e->solving = false;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_num_rollouts(const stomp_b200_engine* e, int32_t* num_rollouts, int32_t* num_generated)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (num_rollouts) *num_rollouts = e->num_rollouts;
+    if (num_generated) *num_generated = e->last_gen;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_t out_bytes)
+{
+    if (!e || !out) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    resolve_profile(e);
+    const LoopParams& b = e->base;
+    const size_t Q = e->Q, T = e->T, D = e->D, N = e->N;
+    const size_t nl = e->last_local;      // local rollouts of the last iteration
+    const size_t ng = e->num_rollouts;    // rollouts in the rollout-indexed tables
+    // copy `rows` rows of `row_bytes` per query out of a [Q][stride_rows] table
+    auto per_query = [&](const void* src, size_t rows, size_t stride_rows, size_t row_bytes) -> int {
+        if (out_bytes != Q * rows * row_bytes) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "out_bytes does not match the tensor size");
+        if (rows == 0) return 0;
+        CUDA_TRY(e, cudaMemcpy2D(out, rows * row_bytes, src, stride_rows * row_bytes, rows * row_bytes, Q, cudaMemcpyDeviceToHost));
+        return 0;
+    };
+    auto from_sums = [&](int kind) -> int {   // 5 cumulative, 6 full, 7 total
+        const size_t width = kind == 7 ? 1 : D;
+        if (out_bytes != Q * ng * width * sizeof(double)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "out_bytes does not match the tensor size");
+        std::vector<double> s(Q * e->gslots * e->sumw);
+        CUDA_TRY(e, cudaMemcpy(s.data(), b.sums, sizeof(double) * s.size(), cudaMemcpyDeviceToHost));
+        double* o = static_cast<double*>(out);
+        for (size_t q = 0; q < Q; ++q)
+            for (size_t k = 0; k < ng; ++k) {
+                const double* r = s.data() + (q * e->gslots + k) * e->sumw;
+                if (kind == 7) {
+                    double c = r[0];
+                    for (size_t d = 0; d < D; ++d) c += r[1 + d];
+                    o[q * ng + k] = c;
+                } else {
+                    for (size_t d = 0; d < D; ++d) o[(q * ng + k) * D + d] = kind == 5 ? 1.0 * r[1 + D + d] : r[0] + r[1 + d];
+                }
+            }
+        return 0;
+    };
+    switch (tensor) {
+        case STOMP_B200_ROLLOUTS: return per_query(b.rollouts, nl * D, (size_t)e->slots * D, T * sizeof(double));
+        case STOMP_B200_NOISE: return per_query(b.noise, nl * D, (size_t)e->slots * D, T * sizeof(double));
+        case STOMP_B200_STATE_COSTS: return per_query(b.state_costs, nl, e->slots, T * sizeof(double));
+        case STOMP_B200_VERDICTS: return per_query(b.verdicts, nl, e->slots, T);
+        case STOMP_B200_CONTROL_COSTS:
+            if (!b.control_costs) return fail(e, STOMP_B200_ERR_NOT_READY, "control costs need keep_debug_tensors");
+            return per_query(b.control_costs, nl * D, (size_t)e->slots * D, T * sizeof(double));
+        case STOMP_B200_CUMULATIVE_COSTS: return from_sums(5);
+        case STOMP_B200_FULL_COSTS: return from_sums(6);
+        case STOMP_B200_TOTAL_COST: return from_sums(7);
+        case STOMP_B200_PROBABILITIES: {
+            if (out_bytes != Q * ng * D * T * sizeof(double)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "out_bytes does not match the tensor size");
+            std::vector<double> pr(Q * e->gslots * D);
+            CUDA_TRY(e, cudaMemcpy(pr.data(), b.prob, sizeof(double) * pr.size(), cudaMemcpyDeviceToHost));
+            double* o = static_cast<double*>(out);
+            for (size_t q = 0; q < Q; ++q)
+                for (size_t k = 0; k < ng; ++k)
+                    for (size_t d = 0; d < D; ++d)
+                        for (size_t t = 0; t < T; ++t) o[((q * ng + k) * D + d) * T + t] = pr[(q * e->gslots + k) * D + d];
+            return 0;
+        }
+        case STOMP_B200_FULL_PROBABILITIES: return per_query(b.fprob, ng, e->gslots, D * sizeof(double));
+        case STOMP_B200_UPDATES: return per_query(b.updates, 1, 1, D * T * sizeof(double));
+        case STOMP_B200_PARAMETERS:
+            if (out_bytes != Q * D * T * sizeof(double)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "out_bytes does not match the tensor size");
+            CUDA_TRY(e, cudaMemcpy2D(out, sizeof(double) * T, b.theta_all + kPad, sizeof(double) * N, sizeof(double) * T, Q * D, cudaMemcpyDeviceToHost));
+            return 0;
+        case STOMP_B200_PARAMETERS_ALL: return per_query(b.theta_all, 1, 1, D * N * sizeof(double));
+        case STOMP_B200_STDDEVS: return per_query(b.sigma, 1, 1, D * sizeof(double));
+        case STOMP_B200_NOISELESS_STATE_COSTS: return per_query(b.nl_state, 1, 1, T * sizeof(double));
+        case STOMP_B200_NOISELESS_CONTROL_COSTS: return per_query(b.nl_control, 1, 1, D * T * sizeof(double));
+        case STOMP_B200_UNIT_NOISE: {
+            const size_t cap = (size_t)std::max(e->cfg.num_rollouts_per_iteration, e->cfg.min_rollouts) / (e->cfg.shard_mode == 0 ? e->cfg.world_size : 1) + 1;
+            (void)cap;
+            // staging layout is [Q][G][D][T] with G = rollouts generated in the last iteration (dense)
+            if (out_bytes != Q * e->last_gen * D * T * sizeof(double)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "out_bytes does not match the tensor size");
+            CUDA_TRY(e, cudaMemcpy(out, b.unit_noise, out_bytes, cudaMemcpyDeviceToHost));
+            return 0;
+        }
+        case STOMP_B200_EPSILON:
+            if (out_bytes != Q * e->last_gen * D * T * sizeof(double)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "out_bytes does not match the tensor size");
+            CUDA_TRY(e, cudaMemcpy(out, b.epsilon, out_bytes, cudaMemcpyDeviceToHost));
+            return 0;
+        case STOMP_B200_ROLLOUT_VALIDITY: return per_query(b.validity, e->last_gen, e->slots, 1);
+        default: return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "unknown tensor id");
+    }
+}
+
+int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_t num_trajectories, int32_t num_steps,
+                               double* state_costs, uint8_t* verdicts, uint8_t* validity)
+{
+    if (!e || !theta || num_trajectories < 1 || num_steps < 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!e->have_chain || !e->have_spheres || !e->have_sdf) return fail(e, STOMP_B200_ERR_NOT_READY, "chain, spheres and SDF must be set first");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    const size_t states = (size_t)num_trajectories * num_steps;
+    double* d_theta = nullptr; double* d_cost = nullptr; uint8_t* d_verdict = nullptr; uint8_t* d_valid = nullptr;
+    int rc = STOMP_B200_OK;
+    auto cleanup = [&]() { cudaFree(d_theta); cudaFree(d_cost); cudaFree(d_verdict); cudaFree(d_valid); };
+#define EVAL_TRY(call) do { cudaError_t _err = (call); if (_err != cudaSuccess) { e->last_error = std::string(#call) + ": " + cudaGetErrorString(_err); cleanup(); return STOMP_B200_ERR_CUDA; } } while (0)
+    EVAL_TRY(cudaMalloc(&d_theta, sizeof(double) * states * e->D));
+    EVAL_TRY(cudaMalloc(&d_cost, sizeof(double) * states));
+    EVAL_TRY(cudaMalloc(&d_verdict, states));
+    EVAL_TRY(cudaMalloc(&d_valid, num_trajectories));
+    EVAL_TRY(cudaMemcpyAsync(d_theta, theta, sizeof(double) * states * e->D, cudaMemcpyHostToDevice, e->stream));
+    {
+        Scope sc(e, STOMP_B200_KERNEL_COST);
+        evaluate_states_kernel<<<(unsigned)((states + 127) / 128), 128, 0, e->stream>>>(e->robot, e->sdf, d_theta, num_trajectories, num_steps, d_cost, d_verdict, d_valid);
+    }
+    EVAL_TRY(cudaGetLastError());
+    if (state_costs) EVAL_TRY(cudaMemcpyAsync(state_costs, d_cost, sizeof(double) * states, cudaMemcpyDeviceToHost, e->stream));
+    if (verdicts) EVAL_TRY(cudaMemcpyAsync(verdicts, d_verdict, states, cudaMemcpyDeviceToHost, e->stream));
+    if (validity) EVAL_TRY(cudaMemcpyAsync(validity, d_valid, num_trajectories, cudaMemcpyDeviceToHost, e->stream));
+    EVAL_TRY(cudaStreamSynchronize(e->stream));
+#undef EVAL_TRY
+    cleanup();
+    resolve_profile(e);
+    return rc;
+}
+
+int stomp_b200_sphere_centres(stomp_b200_engine* e, const double* q, int32_t n, double* centres)
+{
+    if (!e || !q || !centres || n < 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!e->have_chain || !e->have_spheres) return fail(e, STOMP_B200_ERR_NOT_READY, "chain and spheres must be set first");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    double* d_q = nullptr; double* d_c = nullptr;
+    const size_t out_count = (size_t)n * e->robot.num_spheres * 3;
+    CUDA_TRY(e, cudaMalloc(&d_q, sizeof(double) * n * e->D));
+    cudaError_t err = cudaMalloc(&d_c, sizeof(double) * out_count);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_q, q, sizeof(double) * n * e->D, cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) {
+        sphere_centres_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(e->robot, d_q, n, d_c);
+        e->launch_count++;
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(centres, d_c, sizeof(double) * out_count, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(d_q); cudaFree(d_c);
+    if (err != cudaSuccess) { e->last_error = std::string("sphere_centres: ") + cudaGetErrorString(err); return STOMP_B200_ERR_CUDA; }
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_comm_unique_id(void* id_out)
+{
+    if (!id_out) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    std::string err;
+    if (!g_nccl.load(err)) return STOMP_B200_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == STOMP_B200_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return STOMP_B200_ERR_NCCL;
+    std::memcpy(id_out, &id, sizeof(id));
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_comm_init(stomp_b200_engine* e, const void* id)
+{
+    if (!e || !id) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!g_nccl.load(e->last_error)) return STOMP_B200_ERR_NCCL;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    NCCL_TRY(e, g_nccl.CommInitRank(&e->comm, e->cfg.world_size, uid, e->cfg.rank));
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_set_profiling(stomp_b200_engine* e, int32_t on)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(e->stream);
+    resolve_profile(e);
+    e->profiling = on != 0;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_kernel_stats(stomp_b200_engine* e, int32_t kernel, double* total_ms, int64_t* launches)
+{
+    if (!e || kernel < 0 || kernel >= STOMP_B200_KERNEL_COUNT) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(e->stream);
+    resolve_profile(e);
+    if (total_ms) *total_ms = e->kernel_ms[kernel];
+    if (launches) *launches = e->kernel_launches[kernel];
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_reset_kernel_stats(stomp_b200_engine* e)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(e->stream);
+    resolve_profile(e);
+    for (int k = 0; k < STOMP_B200_KERNEL_COUNT; ++k) { e->kernel_ms[k] = 0; e->kernel_launches[k] = 0; }
+    return STOMP_B200_OK;
+}
+
+int64_t stomp_b200_launch_count(const stomp_b200_engine* e) { return e ? e->launch_count : 0; }
+
+int stomp_b200_timer_begin(stomp_b200_engine* e)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    CUDA_TRY(e, cudaEventRecord(e->timer_a, e->stream));
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_timer_end(stomp_b200_engine* e, double* elapsed_ms)
+{
+    if (!e || !elapsed_ms) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(e, cudaEventRecord(e->timer_b, e->stream));
+    CUDA_TRY(e, cudaEventSynchronize(e->timer_b));
+    float ms = 0.f;
+    CUDA_TRY(e, cudaEventElapsedTime(&ms, e->timer_a, e->timer_b));
+    *elapsed_ms = ms;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_synchronize(stomp_b200_engine* e)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    resolve_profile(e);
+    return STOMP_B200_OK;
+}
+
+}  // extern "C"

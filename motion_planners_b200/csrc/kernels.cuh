@@ -1,0 +1,844 @@
+// sm_100a kernels of the STOMP rollout loop.  One translation unit (engine.cu) includes this file and is
+// compiled with -fmad=false: fused multiply-adds appear only where fma() is written (kinematics.cuh
+// states why).  Each kernel names the reference loop it replaces; paths are
+// relative to /root/reference/src/planners/.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "kinematics.cuh"
+
+namespace stomp_b200 {
+
+constexpr int kPad = 6;                 // TRAJECTORY_PADDING, stomp/include/stomp/StompUtils.hpp:57
+constexpr int kMaxRules = 4;            // NUM_DIFF_RULES
+constexpr int kRBand = 6;               // half bandwidth of R = sum D^T W D (7-tap rules)
+
+// shape + pointers shared by every kernel (device memory; layouts in DESIGN.md "Data layout in HBM")
+struct LoopParams {
+    int32_t T, D, N, Q;
+    int32_t slots;            // rollout slots per query in the local tensors (max_rollouts + 1)
+    int32_t gslots;           // slots per query in the rollout-indexed scalar tables (global over ranks)
+    int32_t sumw;             // 1 + 2*D doubles per rollout: S, C_d[D], cum_d[D]
+    int32_t num_gen;          // G: rollouts generated this iteration (local)
+    int32_t num_rollouts;     // K': rollouts used in the update (global over ranks)
+    int32_t num_local;        // local rollout slots in use (generated + reused + noise-less)
+    int32_t gen_offset;       // global index of local generated rollout 0 (rank * G)
+    int32_t noiseless_slot;   // local slot of the appended noise-less rollout, -1 if none
+    int32_t noiseless_gslot;  // its global slot
+    int32_t honour_stop;
+    int32_t iteration;
+    int32_t store_control;    // write per-(k,d,t) control costs
+    int32_t store_unit;       // write unit noise / epsilon (debug)
+    int32_t use_noise_adaptation;
+    int32_t query_offset;     // global index of local query 0
+    int32_t gen_global;       // generated rollouts per query over all ranks (Philox column numbering)
+    double control_cost_weight, dt, cost_scaling_h, min_cost_improvement;
+    uint64_t seed;
+
+    double* theta_all;        // [Q][D][N]
+    const double* mincc;      // [Q][D][T]
+    double* rollouts;         // [Q][slots][D][T]   parameters_noise_
+    double* noise;            // [Q][slots][D][T]   noise_
+    double* proj;             // [Q][slots][D][T]   parameters_noise_projected_ (reuse only) or null
+    double* state_costs;      // [Q][slots][T]
+    uint8_t* verdicts;        // [Q][slots][T]
+    uint8_t* validity;        // [Q][slots]
+    double* control_costs;    // [Q][slots][D][T] or null
+    double* sums;             // [Q][gslots][sumw]
+    double* total_cost;       // [Q][gslots]
+    double* prob;             // [Q][gslots][D]
+    double* fprob;            // [Q][gslots][D]
+    double* fprob_sum;        // [Q][D]
+    double* sigma;            // [Q][D]  adapted_stddevs_
+    double* coef;             // [Q][D][3] p1, p2, new_stddev of the mean-shifted sampler (PolicyImprovement.cpp:262-269)
+    double* updbuf;           // [Q][D][T+1]  update row + numerator of the noise adaptation
+    double* updates;          // [Q][D][T]    last applied update (read-back)
+    double* unit_noise;       // [Q][G][D][T] staging (injected) / debug
+    double* epsilon;          // [Q][G][D][T] staging (injected) / debug
+    // noise-less rollout record
+    double* nl_state;         // [Q][T]
+    uint8_t* nl_verdict;      // [Q][T]
+    double* nl_control;       // [Q][D][T]
+    double* nl_sums;          // [Q][sumw]
+    double* nl_total;         // [Q]
+    uint8_t* nl_valid;        // [Q]
+    double* old_cost;         // [Q]
+    double* last_improvement; // [Q]
+    double* best_cost;        // [Q]
+    int32_t* stop;            // [Q]
+    int32_t* iters_used;      // [Q]
+    // control-cost operator
+    const double* diff_band;  // [rules][N][7]
+    const double* Lt;         // [T][T]  Lt[u][t] = L[t][u]
+    const double* Rband;      // [T][13] Rband[t][o] = R[t][t-6+o]
+    const double* min_stddev; // [D]
+    int32_t num_rules;
+    int32_t rule_id[kMaxRules];
+    double rule_sqrt_w[kMaxRules];
+};
+
+__device__ __forceinline__ bool query_frozen(const LoopParams& p, int q) { return p.honour_stop && p.stop[q] != 0; }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide reductions for blockDim.x <= 1024 (scratch: 32 doubles of shared memory); result on all threads
+template <int OP>   // 0 sum, 1 min, 2 max
+__device__ __forceinline__ double block_reduce(double v, double* scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    v = (OP == 0) ? warp_sum(v) : (OP == 1) ? warp_min(v) : warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double r = scratch[0];
+    for (int w = 1; w < nwarps; ++w) r = (OP == 0) ? (r + scratch[w]) : (OP == 1) ? fmin(r, scratch[w]) : fmax(r, scratch[w]);
+    return r;
+}
+
+// parameters of the mean-shifted sampling for one joint (PolicyImprovement.cpp:260-269)
+__device__ __forceinline__ void store_sampler_coefficients(const LoopParams& p, int q, int d, double sd)
+{
+    const double l1 = p.control_cost_weight;
+    const double l2 = 1.0 / (sd * sd);
+    double* cf = p.coef + ((size_t)q * p.D + d) * 3;
+    cf[0] = l1 / (l1 + l2);
+    cf[1] = l2 / (l1 + l2);
+    cf[2] = 1.0 / sqrt(l1 + l2);
+}
+
+// =====================================================================================================
+// Philox4x32-10 + Box-Muller
+// =====================================================================================================
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+{
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+// four standard normals for column `column` (global (query, rollout, joint) index), time steps 4*u4..4*u4+3
+__device__ __forceinline__ void philox_normals(uint64_t seed, uint32_t iteration, uint32_t column, uint32_t u4, double z[4])
+{
+    const uint4 r = philox4x32_10(make_uint4(column, u4, iteration, 0x53544F4Du),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u4f = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
+    float sa, ca, sb, cb;
+    sincospif(2.0f * u2, &sa, &ca);
+    sincospif(2.0f * u4f, &sb, &cb);
+    z[0] = (double)(ra * ca);
+    z[1] = (double)(ra * sa);
+    z[2] = (double)(rb * cb);
+    z[3] = (double)(rb * sb);
+}
+
+// =====================================================================================================
+// K1 + K2 + K3: PolicyImprovement::generateRollouts sampling loop (stomp/src/PolicyImprovement.cpp:258-286),
+// MultivariateGaussian::sample (stomp/include/stomp/MultivariateGaussian.hpp:91-97), OptimizationTask::filter
+// (src/wrappers/stomp/OptimizationTask.cpp:85-106) and computeNoise (PolicyImprovement.cpp:803-810).
+// =====================================================================================================
+
+// mean-shifted sample + joint-limit clamp + noise for one element; unit = (L*eps)[t]
+__device__ __forceinline__ void shift_clamp_store(const LoopParams& p, const RobotParams& robot, int q, int k, int d, int t,
+                                                  double unit)
+{
+    const double* cf = p.coef + ((size_t)q * p.D + d) * 3;
+    const double p1 = cf[0], p2 = cf[1], new_stddev = cf[2];
+    const double theta = p.theta_all[((size_t)q * p.D + d) * p.N + kPad + t];
+    const double mcc = p.mincc[((size_t)q * p.D + d) * p.T + t];
+    double v = p1 * mcc + p2 * theta + new_stddev * unit;
+    if (v < robot.lower[d]) v = robot.lower[d];
+    if (v > robot.upper[d]) v = robot.upper[d];
+    const size_t o = (((size_t)q * p.slots + k) * p.D + d) * p.T + t;
+    const double nz = v - theta;
+    p.rollouts[o] = v;
+    p.noise[o] = nz;
+    if (p.proj) p.proj[o] = theta + nz;          // computeProjectedNoise with M = I (PolicyImprovement.cpp:430-440)
+}
+
+// Contraction N^T[c][t] = sum_u E^T[c][u] * Lt[u][t] over the G*D columns c = (k, d) of one query, all T
+// rows at once, fused with the epilogue above.  256 threads: ty = tid/16 owns 4 columns, tx = tid%16 owns the
+// time steps tx + 16*j, j < NT.  Lt is upper triangular: chunk kc of the u loop only touches j >= kc.
+template <int NT, bool kPhilox>
+__global__ void __launch_bounds__(256)
+sample_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot)
+{
+    constexpr int BM = 64, BK = 16, BN = NT * 16;
+    __shared__ double As[BK][BM + 2];
+    __shared__ double Bs[BK][BN];
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D;
+    const int ncols = p.num_gen * D;
+    const int c0 = blockIdx.x * BM;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+    double acc[4][NT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j] = 0.0;
+
+    const int nchunks = (T + BK - 1) / BK;
+    const int lc = tid >> 2;              // column of the tile this thread fills
+    const int lu = (tid & 3) * 4;         // first of its 4 u rows
+    for (int kc = 0; kc < nchunks; ++kc) {
+        const int u0 = kc * BK;
+        // ---- A tile: 64 columns x 16 u ----
+        {
+            const int c = c0 + lc;
+            double z[4] = {0.0, 0.0, 0.0, 0.0};
+            if (c < ncols) {
+                const int k = c / D, d = c - k * D;
+                if (kPhilox) {
+                    const uint32_t gcol = (uint32_t)((((size_t)(p.query_offset + q)) * p.gen_global + (p.gen_offset + k)) * D + d);
+                    philox_normals(p.seed, (uint32_t)p.iteration, gcol, (uint32_t)((u0 + lu) >> 2), z);
+                    if (p.store_unit) {
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            if (u0 + lu + m < T) p.epsilon[(((size_t)q * p.num_gen + k) * D + d) * T + u0 + lu + m] = z[m];
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        if (u0 + lu + m < T) z[m] = p.epsilon[(((size_t)q * p.num_gen + k) * D + d) * T + u0 + lu + m];
+                }
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (u0 + lu + m >= T) z[m] = 0.0;
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) As[lu + m][lc] = z[m];
+        }
+        // ---- B tile: 16 u x BN t of Lt (zero outside the matrix) ----
+        for (int e = tid; e < BK * BN; e += 256) {
+            const int u = e / BN, t = e - u * BN;
+            double v = 0.0;
+            if (u0 + u < T && t < T && t >= u0 + u) v = p.Lt[(size_t)(u0 + u) * T + t];
+            Bs[u][t] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < BK; ++u) {
+            double a[4], b[NT];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[u][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                if (j >= kc) b[j] = Bs[u][tx + 16 * j];
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                if (j >= kc) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                }
+        }
+        __syncthreads();
+    }
+    // ---- epilogue ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty * 4 + i;
+        if (c >= ncols) continue;
+        const int k = c / D, d = c - k * D;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int t = tx + 16 * j;
+            if (t >= T) continue;
+            if (p.store_unit) p.unit_noise[(((size_t)q * p.num_gen + k) * D + d) * T + t] = acc[i][j];
+            shift_clamp_store(p, robot, q, k, d, t, acc[i][j]);
+        }
+    }
+}
+
+// injected unit noise (parity mode): epilogue only
+__global__ void __launch_bounds__(256)
+shift_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot)
+{
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    const int per_query = p.num_gen * p.D * p.T;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per_query; e += gridDim.x * blockDim.x) {
+        const int t = e % p.T;
+        const int kd = e / p.T;
+        const int d = kd % p.D, k = kd / p.D;
+        shift_clamp_store(p, robot, q, k, d, t, p.unit_noise[(size_t)q * per_query + e]);
+    }
+}
+
+// =====================================================================================================
+// K4: state verdict — FK of the chain, sphere centres, SDF lookups
+// (what robot_model does for OptimizationTask::computeCollisionCost, OptimizationTask.cpp:183-204)
+// =====================================================================================================
+template <class JointValue>
+__device__ __forceinline__ bool state_collides(const RobotParams& robot, const SdfParams& sdf, JointValue joint_value)
+{
+    Frame f;
+    frame_identity(f);
+    bool hit = false;
+    for (int d = 0; d < robot.num_joints; ++d) {
+        apply_joint(f, robot.joint[d], joint_value(d));
+        for (int s = robot.sphere_begin[d]; s < robot.sphere_begin[d + 1]; ++s) {
+            double cx, cy, cz;
+            sphere_centre(f, robot.sphere[s], cx, cy, cz);
+            const double dist = (double)__ldg(sdf.grid + sdf_index(sdf, cx, cy, cz));
+            hit |= (dist - robot.sphere[s].r) < 0.0;
+        }
+    }
+    return hit;
+}
+
+// control cost of padded row i of one (rollout, joint): CovariantMovementPrimitive::computeControlCosts
+// (stomp/src/CovariantMovementPrimitive.cpp:363-377): costs_all[i] = sum_rules dt*w*(Ax*Ax),
+// Ax = (D_rule x)[i] * sqrt(w_rule).  x = padded trajectory (shared memory), band in column order.
+__device__ __forceinline__ double control_cost_row(const LoopParams& p, const double* x, int i)
+{
+    const double dtw = p.dt * p.control_cost_weight;
+    double c = 0.0;
+    for (int r = 0; r < p.num_rules; ++r) {
+        const double* band = p.diff_band + ((size_t)p.rule_id[r] * p.N + i) * 7;
+        double s = 0.0;
+        const int lo = max(0, i - 3), hi = min(p.N - 1, i + 3);
+        for (int j = lo; j <= hi; ++j) s += __ldg(band + (j - i + 3)) * x[j];
+        const double Ax = s * p.rule_sqrt_w[r];
+        c += dtw * (Ax * Ax);
+    }
+    return c;
+}
+
+// One (rollout, joint) task for one warp: per-timestep control costs folded as the reference does
+// (padding rows into the first / last free step), their sum C_d and cum_d = sum_t (state + control).
+// x: padded trajectory of this (rollout, joint) in shared memory; state: state costs [T] in shared memory.
+__device__ __forceinline__ void control_cost_task(const LoopParams& p, const double* x, const double* state, int lane,
+                                                  double* control_out /*[T] global or null*/, double& C_d, double& cum_d)
+{
+    const int T = p.T, N = p.N;
+    double free_sum = 0.0, cum_sum = 0.0, pad_sum = 0.0;
+    for (int i = lane; i < N; i += 32) {
+        const double c = control_cost_row(p, x, i);
+        if (i >= kPad && i < kPad + T) {
+            free_sum += c;
+            cum_sum += state[i - kPad] + c;
+            if (control_out) control_out[i - kPad] = c;
+        } else {
+            pad_sum += c;
+        }
+    }
+    free_sum = warp_sum(free_sum);
+    cum_sum = warp_sum(cum_sum);
+    pad_sum = warp_sum(pad_sum);
+    C_d = free_sum + pad_sum;
+    cum_d = cum_sum + pad_sum;
+    if (control_out) {
+        __syncwarp();
+        if (lane == 0) {   // fold the padding rows exactly in the reference's order (:373-377)
+            double first = control_out[0], last = control_out[T - 1];
+            if (T == 1) {
+                for (int i = 0; i < kPad; ++i) { first += control_cost_row(p, x, i); first += control_cost_row(p, x, N - (i + 1)); }
+                control_out[0] = first;
+            } else {
+                for (int i = 0; i < kPad; ++i) { first += control_cost_row(p, x, i); last += control_cost_row(p, x, N - (i + 1)); }
+                control_out[0] = first;
+                control_out[T - 1] = last;
+            }
+        }
+    }
+}
+
+// K4 + K5 + K6: Stomp::doExecuteRollouts (stomp/src/Stomp.cpp:206-229) -> Task::execute, then
+// PolicyImprovement::computeRolloutControlCosts / computeRolloutCumulativeCosts (PolicyImprovement.cpp:442-495)
+// for the generated rollouts.  One CTA = R rollouts of one query; thread (r, t) evaluates one state.
+// The extra CTA blockIdx.x == gridDim.x - 1 appends the noise-less rollout record (PolicyImprovement.cpp:304-308).
+__global__ void __launch_bounds__(512)
+rollout_cost_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
+                    const __grid_constant__ SdfParams sdf, int R)
+{
+    extern __shared__ double smem[];
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D, N = p.N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+    if (blockIdx.x == gridDim.x - 1) {
+        // ---- append the noise-less rollout as slot noiseless_slot ----
+        if (p.noiseless_slot < 0) return;
+        const int k = p.noiseless_slot;
+        for (int e = tid; e < D * T; e += blockDim.x) {
+            const int d = e / T, t = e - d * T;
+            const double th = p.theta_all[((size_t)q * D + d) * N + kPad + t];
+            const size_t o = (((size_t)q * p.slots + k) * D) * T + e;
+            p.rollouts[o] = th;
+            p.noise[o] = 0.0;
+            if (p.proj) p.proj[o] = th;
+            if (p.control_costs) p.control_costs[o] = p.nl_control[(size_t)q * D * T + e];
+        }
+        for (int t = tid; t < T; t += blockDim.x) {
+            p.state_costs[((size_t)q * p.slots + k) * T + t] = p.nl_state[(size_t)q * T + t];
+            p.verdicts[((size_t)q * p.slots + k) * T + t] = p.nl_verdict[(size_t)q * T + t];
+        }
+        for (int e = tid; e < p.sumw; e += blockDim.x)
+            p.sums[((size_t)q * p.gslots + p.noiseless_gslot) * p.sumw + e] = p.nl_sums[(size_t)q * p.sumw + e];
+        return;
+    }
+
+    double* sx = smem;                           // [R][D][N] padded trajectories
+    double* sstate = smem + (size_t)R * D * N;   // [R][T]
+    const int k0 = blockIdx.x * R;
+    const int nr = min(R, p.num_gen - k0);
+
+    // ---- load: padding from the policy, free block <- noisy parameters (OptimizationTask.cpp:155-163) ----
+    for (int e = tid; e < nr * D * N; e += blockDim.x) {
+        const int i = e % N;
+        const int rd = e / N;
+        const int d = rd % D, r = rd / D;
+        double v;
+        if (i >= kPad && i < kPad + T) v = p.rollouts[(((size_t)q * p.slots + (k0 + r)) * D + d) * T + (i - kPad)];
+        else v = p.theta_all[((size_t)q * D + d) * N + i];
+        sx[e] = v;
+    }
+    __syncthreads();
+
+    // ---- K4: one state per thread ----
+    if (tid < nr * T) {
+        const int r = tid / T, t = tid - r * T;
+        const double* xq = sx + (size_t)r * D * N + kPad + t;
+        const bool hit = state_collides(robot, sdf, [&](int d) { return xq[(size_t)d * N]; });
+        const double cost = hit ? 1.0 : 0.0;
+        sstate[r * T + t] = cost;
+        const size_t o = ((size_t)q * p.slots + (k0 + r)) * T + t;
+        p.state_costs[o] = cost;
+        p.verdicts[o] = hit ? 1 : 0;
+        if (t == T - 1) p.validity[(size_t)q * p.slots + (k0 + r)] = hit ? 0 : 1;   // last timestep only (:192-202)
+    }
+    __syncthreads();
+
+    // ---- the control cost is evaluated on parameters_ + noise_projected_, not on the noisy parameters
+    // (PolicyImprovement.cpp:812-817): x = theta + (noisy - theta) ----
+    for (int e = tid; e < nr * D * T; e += blockDim.x) {
+        const int t = e % T;
+        const int rd = e / T;
+        const int d = rd % D;
+        const double th = p.theta_all[((size_t)q * D + d) * N + kPad + t];
+        double* xp = sx + (size_t)rd * N + kPad + t;
+        *xp = th + (*xp - th);
+    }
+    __syncthreads();
+
+    // ---- K5 + K6: warp tasks.  tasks [0, nr*D): control cost of (r, d); [nr*D, nr*D + nr): state cost sum ----
+    for (int task = warp; task < nr * D + nr; task += nwarps) {
+        if (task < nr * D) {
+            const int r = task / D, d = task - r * D;
+            const int k = k0 + r;
+            double C_d, cum_d;
+            double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
+            control_cost_task(p, sx + (size_t)task * N, sstate + r * T, lane, cc_out, C_d, cum_d);
+            if (lane == 0) {
+                double* s = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
+                s[1 + d] = C_d;
+                s[1 + D + d] = cum_d;
+            }
+        } else {
+            const int r = task - nr * D;
+            double s = 0.0;
+            for (int t = lane; t < T; t += 32) s += sstate[r * T + t];
+            s = warp_sum(s);
+            if (lane == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k0 + r)) * p.sumw] = s;
+        }
+    }
+}
+
+// stand-alone verdicts for arbitrary trajectories theta [K][D][Tq] (stomp_b200_evaluate_states)
+__global__ void __launch_bounds__(128)
+evaluate_states_kernel(const __grid_constant__ RobotParams robot, const __grid_constant__ SdfParams sdf,
+                       const double* __restrict__ theta, int K, int Tq, double* __restrict__ costs,
+                       uint8_t* __restrict__ verdicts, uint8_t* __restrict__ validity)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)K * Tq) return;
+    const int k = (int)(idx / Tq), t = (int)(idx - (size_t)k * Tq);
+    const int D = robot.num_joints;
+    const double* base = theta + (size_t)k * D * Tq + t;
+    const bool hit = state_collides(robot, sdf, [&](int d) { return base[(size_t)d * Tq]; });
+    if (costs) costs[idx] = hit ? 1.0 : 0.0;
+    if (verdicts) verdicts[idx] = hit ? 1 : 0;
+    if (validity && t == Tq - 1) validity[k] = hit ? 0 : 1;
+}
+
+__global__ void sphere_centres_kernel(const __grid_constant__ RobotParams robot, const double* __restrict__ q, int n,
+                                      double* __restrict__ centres)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Frame f;
+    frame_identity(f);
+    for (int d = 0; d < robot.num_joints; ++d) {
+        apply_joint(f, robot.joint[d], q[(size_t)i * robot.num_joints + d]);
+        for (int s = robot.sphere_begin[d]; s < robot.sphere_begin[d + 1]; ++s) {
+            double cx, cy, cz;
+            sphere_centre(f, robot.sphere[s], cx, cy, cz);
+            double* o = centres + ((size_t)i * robot.num_spheres + s) * 3;
+            o[0] = cx; o[1] = cy; o[2] = cz;
+        }
+    }
+}
+
+// =====================================================================================================
+// Reused rollouts (PolicyImprovement.cpp:188-255): control costs are recomputed for ALL rollouts every
+// iteration (computeRolloutControlCosts, :442-449) on parameters_ + noise_projected_ with the new
+// parameters.  One warp per (slot, joint) over the reused slots [first, first + count).
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+reused_control_cost_kernel(const __grid_constant__ LoopParams p, int first, int count)
+{
+    extern __shared__ double smem[];
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D, N = p.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    double* x = smem + (size_t)warp * (N + T);
+    double* st = x + N;
+    for (int task = blockIdx.x * nwarps + warp; task < count * D; task += gridDim.x * nwarps) {
+        const int r = task / D, d = task - r * D, k = first + r;
+        for (int i = lane; i < N; i += 32) {
+            const double th = p.theta_all[((size_t)q * D + d) * N + i];
+            double v = th;
+            if (i >= kPad && i < kPad + T) v = th + p.noise[(((size_t)q * p.slots + k) * D + d) * T + (i - kPad)];
+            x[i] = v;
+        }
+        for (int t = lane; t < T; t += 32) st[t] = p.state_costs[((size_t)q * p.slots + k) * T + t];
+        __syncwarp();
+        double C_d, cum_d;
+        double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
+        control_cost_task(p, x, st, lane, cc_out, C_d, cum_d);
+        double s = 0.0;
+        for (int t = lane; t < T; t += 32) s += st[t];
+        s = warp_sum(s);
+        if (lane == 0) {
+            double* o = p.sums + ((size_t)q * p.gslots + k) * p.sumw;
+            o[0] = s;
+            o[1 + d] = C_d;
+            o[1 + D + d] = cum_d;
+        }
+        __syncwarp();
+    }
+}
+
+// importance weights of the previous rollouts, rank by (-w, index), gather the best `reused` ones behind
+// the generated block of the other buffer set and re-base their noise on the new parameters
+// (PolicyImprovement.cpp:188-255).  One CTA per query.
+struct ReuseParams {
+    int32_t prev, reused, gen;
+    const double* src_proj; const double* src_state; const uint8_t* src_verdict; const double* src_total;
+    int32_t* order;           // [Q][slots] scratch
+};
+__global__ void __launch_bounds__(256)
+reuse_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ ReuseParams rp)
+{
+    __shared__ double scratch[32];
+    extern __shared__ double w[];      // [prev]
+    const int q = blockIdx.x;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D, N = p.N, tid = threadIdx.x;
+    const double* total = rp.src_total + (size_t)q * p.gslots;
+    double mn = 1e300, mx = -1e300;
+    for (int r = tid; r < rp.prev; r += blockDim.x) { mn = fmin(mn, total[r]); mx = fmax(mx, total[r]); }
+    mn = block_reduce<1>(mn, scratch);
+    mx = block_reduce<2>(mx, scratch);
+    double den = mx - mn;
+    if (den < 1e-8) den = 1e-8;
+    for (int r = tid; r < rp.prev; r += blockDim.x) w[r] = -exp(((-p.cost_scaling_h) * (total[r] - mn)) / den);
+    __syncthreads();
+    int32_t* order = rp.order + (size_t)q * p.slots;
+    for (int r = tid; r < rp.prev; r += blockDim.x) {
+        int rank = 0;
+        const double wr = w[r];
+        for (int s = 0; s < rp.prev; ++s) rank += (w[s] < wr) || (w[s] == wr && s < r);
+        if (rank < rp.reused) order[rank] = r;
+    }
+    __syncthreads();
+    for (int e = tid; e < rp.reused * D * T; e += blockDim.x) {
+        const int t = e % T;
+        const int rd = e / T;
+        const int d = rd % D, r = rd / D;
+        const int src = order[r], dst = rp.gen + r;
+        const double pj = rp.src_proj[(((size_t)q * p.slots + src) * D + d) * T + t];
+        const double th = p.theta_all[((size_t)q * D + d) * N + kPad + t];
+        const double nz = pj - th;
+        const size_t o = (((size_t)q * p.slots + dst) * D + d) * T + t;
+        p.proj[o] = pj;
+        p.noise[o] = nz;
+        p.rollouts[o] = th + nz;
+    }
+    for (int e = tid; e < rp.reused * T; e += blockDim.x) {
+        const int t = e % T, r = e / T;
+        const int src = order[r], dst = rp.gen + r;
+        p.state_costs[((size_t)q * p.slots + dst) * T + t] = rp.src_state[((size_t)q * p.slots + src) * T + t];
+        p.verdicts[((size_t)q * p.slots + dst) * T + t] = rp.src_verdict[((size_t)q * p.slots + src) * T + t];
+    }
+}
+
+// =====================================================================================================
+// K7: PolicyImprovement::computeRolloutProbabilities (PolicyImprovement.cpp:497-582), cumulative-cost mode:
+// cumulative_costs_[d] is constant over t (:480), so one probability per (rollout, joint).
+// grid (D, Q); also total_cost_ (:451-462) by the d == 0 CTA.
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+rollout_weights_kernel(const __grid_constant__ LoopParams p)
+{
+    __shared__ double scratch[32];
+    const int d = blockIdx.x, q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    const int D = p.D, n = p.num_rollouts, tid = threadIdx.x;
+    const double* sums = p.sums + (size_t)q * p.gslots * p.sumw;
+    double* prob = p.prob + (size_t)q * p.gslots * D;
+    double* fprob = p.fprob + (size_t)q * p.gslots * D;
+    const double h = p.cost_scaling_h;
+
+    double mn = 1e300, mx = -1e300, fmn = 1e300, fmx = -1e300;
+    for (int k = tid; k < n; k += blockDim.x) {
+        const double* s = sums + (size_t)k * p.sumw;
+        const double cum = 1.0 * s[1 + D + d];
+        const double full = s[0] + s[1 + d];
+        mn = fmin(mn, cum); mx = fmax(mx, cum);
+        fmn = fmin(fmn, full); fmx = fmax(fmx, full);
+        if (d == 0) {
+            double cost = s[0];
+            for (int dd = 0; dd < D; ++dd) cost += s[1 + dd];
+            p.total_cost[(size_t)q * p.gslots + k] = cost;
+        }
+    }
+    mn = block_reduce<1>(mn, scratch); mx = block_reduce<2>(mx, scratch);
+    fmn = block_reduce<1>(fmn, scratch); fmx = block_reduce<2>(fmx, scratch);
+    double den = mx - mn, fden = fmx - fmn;
+    if (den < 1e-8) den = 1e-8;
+    if (fden < 1e-8) fden = 1e-8;
+    double psum = 0.0, fsum = 0.0;
+    for (int k = tid; k < n; k += blockDim.x) {
+        const double* s = sums + (size_t)k * p.sumw;
+        const double pr = 1.0 * exp(((-h) * (1.0 * s[1 + D + d] - mn)) / den);      // importance_weight_ = 1
+        const double fp = 1.0 * exp(((-h) * ((s[0] + s[1 + d]) - fmn)) / fden);
+        prob[(size_t)k * D + d] = pr;
+        fprob[(size_t)k * D + d] = fp;
+        psum += pr; fsum += fp;
+    }
+    psum = block_reduce<0>(psum, scratch);
+    fsum = block_reduce<0>(fsum, scratch);
+    double fnorm = 0.0;
+    for (int k = tid; k < n; k += blockDim.x) {
+        prob[(size_t)k * D + d] /= psum;
+        const double f = fprob[(size_t)k * D + d] / fsum;
+        fprob[(size_t)k * D + d] = f;
+        fnorm += f;
+    }
+    fnorm = block_reduce<0>(fnorm, scratch);
+    if (tid == 0) p.fprob_sum[(size_t)q * D + d] = fnorm;
+}
+
+// =====================================================================================================
+// K8: PolicyImprovement::computeParameterUpdates (PolicyImprovement.cpp:584-711): probability-weighted
+// noise sums and the noise-adaptation numerator sum_k Pfull * (n^T R n).  grid (chunks, D, Q); one warp
+// per rollout of the chunk, lanes stride over t; partial [Q][chunks][D][T+1] (last entry: numerator).
+// =====================================================================================================
+constexpr int kUpdateWarps = 8;
+constexpr int kMaxTPerLane = STOMP_B200_MAX_TIME_STEPS / 32;
+__global__ void __launch_bounds__(kUpdateWarps * 32)
+weighted_update_kernel(const __grid_constant__ LoopParams p, double* __restrict__ partial, int chunk, int nchunks)
+{
+    extern __shared__ double smem[];
+    const int d = blockIdx.y, q = blockIdx.z, c = blockIdx.x;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sn = smem + (size_t)warp * (T + 2 * kRBand);        // noise row with zero halo
+    double* spart = smem + (size_t)kUpdateWarps * (T + 2 * kRBand);   // [warps][T+1]
+    double acc[kMaxTPerLane];
+#pragma unroll
+    for (int i = 0; i < kMaxTPerLane; ++i) acc[i] = 0.0;
+    double numer = 0.0;
+    for (int i = lane; i < T + 2 * kRBand; i += 32) sn[i] = 0.0;
+    __syncwarp();
+    const int k_end = min(p.num_local, (c + 1) * chunk);
+    for (int k = c * chunk + warp; k < k_end; k += kUpdateWarps) {
+        // local slot -> slot in the rollout-indexed tables
+        const int g = (k == p.noiseless_slot) ? p.noiseless_gslot : (k < p.num_gen ? p.gen_offset + k : k);
+        const double pr = p.prob[((size_t)q * p.gslots + g) * D + d];
+        const double* nz = p.noise + (((size_t)q * p.slots + k) * D + d) * T;
+#pragma unroll
+        for (int i = 0; i < kMaxTPerLane; ++i) {
+            const int t = lane + 32 * i;
+            if (t < T) {
+                const double v = nz[t];
+                sn[kRBand + t] = v;
+                acc[i] += v * pr;
+            }
+        }
+        if (p.use_noise_adaptation) {
+            __syncwarp();
+            double quad = 0.0;
+#pragma unroll
+            for (int i = 0; i < kMaxTPerLane; ++i) {
+                const int t = lane + 32 * i;
+                if (t < T) {
+                    const double* rb = p.Rband + (size_t)t * (2 * kRBand + 1);
+                    double s = 0.0;
+#pragma unroll
+                    for (int o = 0; o < 2 * kRBand + 1; ++o) s += __ldg(rb + o) * sn[t + o];
+                    quad += sn[kRBand + t] * s;
+                }
+            }
+            quad = warp_sum(quad);
+            numer += p.fprob[((size_t)q * p.gslots + g) * D + d] * quad;
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxTPerLane; ++i) {
+        const int t = lane + 32 * i;
+        if (t < T) spart[(size_t)warp * (T + 1) + t] = acc[i];
+    }
+    if (lane == 0) spart[(size_t)warp * (T + 1) + T] = numer;
+    __syncthreads();
+    double* out = partial + (((size_t)q * nchunks + c) * D + d) * (T + 1);
+    for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
+        double s = spart[t];
+        for (int w = 1; w < kUpdateWarps; ++w) s += spart[(size_t)w * (T + 1) + t];
+        out[t] = s;
+    }
+}
+
+// sum of the chunk partials in chunk order -> updbuf [Q][D][T+1]   (grid (D, Q))
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const __grid_constant__ LoopParams p, const double* __restrict__ partial, int nchunks)
+{
+    const int d = blockIdx.x, q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D;
+    for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < nchunks; ++c) s += partial[(((size_t)q * nchunks + c) * D + d) * (T + 1) + t];
+        p.updbuf[((size_t)q * D + d) * (T + 1) + t] = s;
+    }
+}
+
+// =====================================================================================================
+// K8 tail + K9 + K10: noise adaptation (PolicyImprovement.cpp:656-679), CovariantMovementPrimitive::
+// updateParameters (stomp/src/CovariantMovementPrimitive.cpp:476-479), Stomp::doNoiselessRollout
+// (stomp/src/Stomp.cpp:253-272) + setNoiselessRolloutCosts (PolicyImprovement.cpp:401-419) and the wrapper's
+// stop rule (src/wrappers/stomp/StompPlanner.cpp:107-118).  One CTA per query.
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+apply_update_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
+                    const __grid_constant__ SdfParams sdf)
+{
+    extern __shared__ double smem[];
+    const int q = blockIdx.x;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D, N = p.N, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    double* sx = smem;                      // [D][N]
+    double* sstate = smem + (size_t)D * N;  // [T]
+    double* ssum = sstate + T;              // [1 + 2D]
+
+    // noise adaptation
+    if (p.use_noise_adaptation && tid < D) {
+        const int d = tid;
+        const double numer = p.updbuf[((size_t)q * D + d) * (T + 1) + T];
+        const double denom = p.fprob_sum[(size_t)q * D + d];
+        const double frob_stddev = sqrt(numer / (denom * T));
+        const double update_rate = 0.2;
+        double sd = (1.0 - update_rate) * p.sigma[(size_t)q * D + d] + update_rate * frob_stddev;
+        if (sd < p.min_stddev[d]) sd = p.min_stddev[d];
+        p.sigma[(size_t)q * D + d] = sd;
+        store_sampler_coefficients(p, q, d, sd);
+    }
+    // parameters += update (time-step weights and divisor are exactly 1: PolicyImprovement.cpp:533,684-704)
+    for (int e = tid; e < D * N; e += blockDim.x) {
+        const int d = e / N, i = e - d * N;
+        double v = p.theta_all[((size_t)q * D + d) * N + i];
+        if (i >= kPad && i < kPad + T) {
+            double u = p.updbuf[((size_t)q * D + d) * (T + 1) + (i - kPad)];
+            u *= 1.0;
+            u /= 1.0;
+            p.updates[((size_t)q * D + d) * T + (i - kPad)] = u;
+            v += 1.0 * u;
+            p.theta_all[((size_t)q * D + d) * N + i] = v;
+        }
+        sx[e] = v;
+    }
+    __syncthreads();
+    // noise-less rollout: state costs
+    for (int t = tid; t < T; t += blockDim.x) {
+        const double* xq = sx + kPad + t;
+        const bool hit = state_collides(robot, sdf, [&](int d) { return xq[(size_t)d * N]; });
+        sstate[t] = hit ? 1.0 : 0.0;
+        p.nl_state[(size_t)q * T + t] = sstate[t];
+        p.nl_verdict[(size_t)q * T + t] = hit ? 1 : 0;
+        if (t == T - 1) p.nl_valid[q] = hit ? 0 : 1;
+    }
+    __syncthreads();
+    // control costs (noise = 0: parameters + 0.0 is exact) and sums
+    for (int task = warp; task < D + 1; task += nwarps) {
+        if (task < D) {
+            double C_d, cum_d;
+            control_cost_task(p, sx + (size_t)task * N, sstate, lane, p.nl_control + ((size_t)q * D + task) * T, C_d, cum_d);
+            if (lane == 0) { ssum[1 + task] = C_d; ssum[1 + D + task] = cum_d; }
+        } else {
+            double s = 0.0;
+            for (int t = lane; t < T; t += 32) s += sstate[t];
+            s = warp_sum(s);
+            if (lane == 0) ssum[0] = s;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < p.sumw; e += blockDim.x) p.nl_sums[(size_t)q * p.sumw + e] = ssum[e];
+    if (tid == 0) {
+        double cost = ssum[0];
+        for (int d = 0; d < D; ++d) cost += ssum[1 + d];
+        p.nl_total[q] = cost;
+        if (cost < p.best_cost[q]) p.best_cost[q] = cost;
+        const double improvement = cost - p.old_cost[q];
+        p.old_cost[q] = cost;
+        p.last_improvement[q] = improvement;
+        p.iters_used[q] += 1;
+        if ((cost < 1) && (fabs(improvement) < p.min_cost_improvement)) p.stop[q] = 1;
+    }
+}
+
+// sigma <- noise_stddev * decay^(it-1) while the adapted value is not valid (PolicyImprovement.cpp:162-163)
+__global__ void set_sigma_kernel(const __grid_constant__ LoopParams p, const double* __restrict__ sigma_it)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.Q * p.D) return;
+    if (query_frozen(p, e / p.D)) return;
+    p.sigma[e] = sigma_it[e % p.D];
+    store_sampler_coefficients(p, e / p.D, e % p.D, sigma_it[e % p.D]);
+}
+
+}  // namespace stomp_b200

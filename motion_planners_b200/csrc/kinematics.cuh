@@ -1,0 +1,204 @@
+// Device-side forward kinematics + sphere / SDF verdict for the rollout cost kernel.
+//
+// This is the B200 replacement for robot_model::RobotModel::updateJointGroup + isStateValid, which the
+// reference calls once per (rollout, timestep) from OptimizationTask::computeCollisionCost
+// (reference src/planners/src/wrappers/stomp/OptimizationTask.cpp:183-204).
+//
+// Arithmetic contract (DESIGN.md "FK arithmetic"): every operation below is a single IEEE-754 binary64
+// operation issued explicitly — fma() where a fused multiply-add is meant, a plain * or + otherwise —
+// and this translation unit is compiled with -fmad=false so that ptxas neither fuses nor splits any of
+// them.  A CPU that issues the same sequence gets bit-identical sphere centres, hence bit-identical
+// collision verdicts.
+#pragma once
+#include <cstdint>
+
+#include "../../include/stomp_b200.h"
+
+namespace stomp_b200 {
+
+enum AxisKind : int32_t { kAxisX = 0, kAxisY = 1, kAxisZ = 2, kAxisNegX = 3, kAxisNegY = 4, kAxisNegZ = 5, kAxisGeneral = 6 };
+
+// one URDF joint, preprocessed on the host at stomp_b200_set_chain
+struct JointParams {
+    double o[3];      // origin xyz in the parent link frame
+    double A[9];      // fixed rotation from rpy (row major)
+    double axis[3];
+    int32_t parent;   // -1: chain restarts at the base frame
+    int32_t axis_kind;
+    int32_t fixed_rot_identity;
+    int32_t prismatic;
+};
+
+struct SphereParams {
+    double l[3];      // centre in the link frame
+    double r;
+};
+
+// passed by value as a __grid_constant__ kernel parameter: lives in the constant bank, every access is
+// warp-uniform
+struct RobotParams {
+    int32_t num_joints;
+    int32_t num_spheres;
+    int32_t sphere_begin[STOMP_B200_MAX_DIMS + 1];   // spheres of joint d: [sphere_begin[d], sphere_begin[d+1])
+    double lower[STOMP_B200_MAX_DIMS];
+    double upper[STOMP_B200_MAX_DIMS];
+    JointParams joint[STOMP_B200_MAX_DIMS];
+    SphereParams sphere[STOMP_B200_MAX_SPHERES];
+};
+
+struct SdfParams {
+    const float* grid;
+    int32_t nx, ny, nz;
+    double ox, oy, oz;
+    double inv_h;
+};
+
+// Deterministic sin/cos (also run on the host for the fixed rpy rotations of stomp_b200_set_chain, so
+// that the whole FK is one arithmetic): 3-term Cody-Waite reduction by pi/2, then the degree-13 / degree-14 minimax
+// polynomials on [-pi/4, pi/4] (coefficients of Sun's fdlibm kernels; mathematical constants).
+__host__ __device__ __forceinline__ void det_sincos(double x, double& s_out, double& c_out)
+{
+    const double k = rint(x * 6.36619772367581382433e-01);
+    const double nk = -k;
+    double r = fma(nk, 1.57079632673412561417e+00, x);
+    r = fma(nk, 6.07710050630396597660e-11, r);
+    r = fma(nk, 2.02226624871116645580e-21, r);
+    const double z = r * r;
+
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double rz = r * z;
+    const double sr = fma(rz, ps, r);
+
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double zz = z * z;
+    const double half = fma(z, -0.5, 1.0);
+    const double cr = fma(zz, pc, half);
+
+    const int q = (int)((long long)k & 3);
+    const bool swap = q & 1;
+    const double a = swap ? cr : sr;
+    const double b = swap ? sr : cr;
+    s_out = (q & 2) ? -a : a;
+    // q: 0 -> c = cr ; 1 -> c = -sr ; 2 -> c = -cr ; 3 -> c = sr
+    c_out = ((q == 1) || (q == 2)) ? -b : b;
+}
+
+struct Frame {
+    double r00, r01, r02, r10, r11, r12, r20, r21, r22;
+    double px, py, pz;
+};
+
+__device__ __forceinline__ void frame_identity(Frame& f)
+{
+    f.r00 = 1.0; f.r01 = 0.0; f.r02 = 0.0;
+    f.r10 = 0.0; f.r11 = 1.0; f.r12 = 0.0;
+    f.r20 = 0.0; f.r21 = 0.0; f.r22 = 1.0;
+    f.px = 0.0; f.py = 0.0; f.pz = 0.0;
+}
+
+// rotate two columns (a, b) of the frame: a' = c*a + s*b ; b' = c*b - s*a   (row by row)
+#define STOMP_B200_ROT2(a, b, s, ns, c)          \
+    {                                            \
+        const double _a = (a), _b = (b);         \
+        (a) = fma((s), _b, (c) * _a);            \
+        (b) = fma((ns), _a, (c) * _b);           \
+    }
+
+__device__ __forceinline__ void apply_joint(Frame& f, const JointParams& j, double q)
+{
+    if (j.parent < 0) frame_identity(f);
+    // p += R * o
+    f.px = fma(f.r02, j.o[2], fma(f.r01, j.o[1], fma(f.r00, j.o[0], f.px)));
+    f.py = fma(f.r12, j.o[2], fma(f.r11, j.o[1], fma(f.r10, j.o[0], f.py)));
+    f.pz = fma(f.r22, j.o[2], fma(f.r21, j.o[1], fma(f.r20, j.o[0], f.pz)));
+    if (!j.fixed_rot_identity) {   // R = R * A
+        const double n00 = fma(f.r02, j.A[6], fma(f.r01, j.A[3], f.r00 * j.A[0]));
+        const double n01 = fma(f.r02, j.A[7], fma(f.r01, j.A[4], f.r00 * j.A[1]));
+        const double n02 = fma(f.r02, j.A[8], fma(f.r01, j.A[5], f.r00 * j.A[2]));
+        const double n10 = fma(f.r12, j.A[6], fma(f.r11, j.A[3], f.r10 * j.A[0]));
+        const double n11 = fma(f.r12, j.A[7], fma(f.r11, j.A[4], f.r10 * j.A[1]));
+        const double n12 = fma(f.r12, j.A[8], fma(f.r11, j.A[5], f.r10 * j.A[2]));
+        const double n20 = fma(f.r22, j.A[6], fma(f.r21, j.A[3], f.r20 * j.A[0]));
+        const double n21 = fma(f.r22, j.A[7], fma(f.r21, j.A[4], f.r20 * j.A[1]));
+        const double n22 = fma(f.r22, j.A[8], fma(f.r21, j.A[5], f.r20 * j.A[2]));
+        f.r00 = n00; f.r01 = n01; f.r02 = n02;
+        f.r10 = n10; f.r11 = n11; f.r12 = n12;
+        f.r20 = n20; f.r21 = n21; f.r22 = n22;
+    }
+    if (j.prismatic) {   // p += q * (R * axis)
+        const double dx = fma(f.r02, j.axis[2], fma(f.r01, j.axis[1], f.r00 * j.axis[0]));
+        const double dy = fma(f.r12, j.axis[2], fma(f.r11, j.axis[1], f.r10 * j.axis[0]));
+        const double dz = fma(f.r22, j.axis[2], fma(f.r21, j.axis[1], f.r20 * j.axis[0]));
+        f.px = fma(q, dx, f.px);
+        f.py = fma(q, dy, f.py);
+        f.pz = fma(q, dz, f.pz);
+        return;
+    }
+    double s, c;
+    det_sincos(q, s, c);
+    int kind = j.axis_kind;
+    if (kind >= kAxisNegX && kind <= kAxisNegZ) { s = -s; kind -= 3; }
+    const double ns = -s;
+    if (kind == kAxisZ) {          // col0' = c*col0 + s*col1 ; col1' = c*col1 - s*col0
+        STOMP_B200_ROT2(f.r00, f.r01, s, ns, c)
+        STOMP_B200_ROT2(f.r10, f.r11, s, ns, c)
+        STOMP_B200_ROT2(f.r20, f.r21, s, ns, c)
+    } else if (kind == kAxisY) {   // col0' = c*col0 - s*col2 ; col2' = c*col2 + s*col0
+        STOMP_B200_ROT2(f.r00, f.r02, ns, s, c)
+        STOMP_B200_ROT2(f.r10, f.r12, ns, s, c)
+        STOMP_B200_ROT2(f.r20, f.r22, ns, s, c)
+    } else if (kind == kAxisX) {   // col1' = c*col1 + s*col2 ; col2' = c*col2 - s*col1
+        STOMP_B200_ROT2(f.r01, f.r02, s, ns, c)
+        STOMP_B200_ROT2(f.r11, f.r12, s, ns, c)
+        STOMP_B200_ROT2(f.r21, f.r22, s, ns, c)
+    } else {                       // Rodrigues: Q = c*I + s*[a]x + (1-c)*a a^T ; R = R*Q
+        const double ax = j.axis[0], ay = j.axis[1], az = j.axis[2];
+        const double v = 1.0 - c;
+        const double vx = v * ax, vy = v * ay, vz = v * az;
+        const double q00 = fma(vx, ax, c),          q01 = fma(vx, ay, -(s * az)), q02 = fma(vx, az, s * ay);
+        const double q10 = fma(vy, ax, s * az),     q11 = fma(vy, ay, c),         q12 = fma(vy, az, -(s * ax));
+        const double q20 = fma(vz, ax, -(s * ay)),  q21 = fma(vz, ay, s * ax),    q22 = fma(vz, az, c);
+        const double n00 = fma(f.r02, q20, fma(f.r01, q10, f.r00 * q00));
+        const double n01 = fma(f.r02, q21, fma(f.r01, q11, f.r00 * q01));
+        const double n02 = fma(f.r02, q22, fma(f.r01, q12, f.r00 * q02));
+        const double n10 = fma(f.r12, q20, fma(f.r11, q10, f.r10 * q00));
+        const double n11 = fma(f.r12, q21, fma(f.r11, q11, f.r10 * q01));
+        const double n12 = fma(f.r12, q22, fma(f.r11, q12, f.r10 * q02));
+        const double n20 = fma(f.r22, q20, fma(f.r21, q10, f.r20 * q00));
+        const double n21 = fma(f.r22, q21, fma(f.r21, q11, f.r20 * q01));
+        const double n22 = fma(f.r22, q22, fma(f.r21, q12, f.r20 * q02));
+        f.r00 = n00; f.r01 = n01; f.r02 = n02;
+        f.r10 = n10; f.r11 = n11; f.r12 = n12;
+        f.r20 = n20; f.r21 = n21; f.r22 = n22;
+    }
+}
+
+__device__ __forceinline__ void sphere_centre(const Frame& f, const SphereParams& sp, double& cx, double& cy, double& cz)
+{
+    cx = fma(f.r02, sp.l[2], fma(f.r01, sp.l[1], fma(f.r00, sp.l[0], f.px)));
+    cy = fma(f.r12, sp.l[2], fma(f.r11, sp.l[1], fma(f.r10, sp.l[0], f.py)));
+    cz = fma(f.r22, sp.l[2], fma(f.r21, sp.l[1], fma(f.r20, sp.l[0], f.pz)));
+}
+
+// nearest-voxel lookup, coordinates clamped to the grid
+__device__ __forceinline__ size_t sdf_index(const SdfParams& g, double cx, double cy, double cz)
+{
+    double fx = (cx - g.ox) * g.inv_h;
+    double fy = (cy - g.oy) * g.inv_h;
+    double fz = (cz - g.oz) * g.inv_h;
+    fx = fmin(fmax(fx, 0.0), (double)(g.nx - 1));
+    fy = fmin(fmax(fy, 0.0), (double)(g.ny - 1));
+    fz = fmin(fmax(fz, 0.0), (double)(g.nz - 1));
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    return ((size_t)iz * (size_t)g.ny + (size_t)iy) * (size_t)g.nx + (size_t)ix;
+}
+
+}  // namespace stomp_b200

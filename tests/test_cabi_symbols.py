@@ -1,0 +1,64 @@
+"""The C-ABI library loads on a machine without a GPU, exports every symbol include/stomp_b200.h
+declares, and fails loudly (no CPU fallback) when asked to compute without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from motion_planners_b200 import binding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "stomp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(stomp_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _declared() == sorted(binding.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    L = binding.lib()
+    for name in _declared():
+        assert hasattr(L, name), name
+    assert L.stomp_b200_abi_version() == 1
+
+
+def test_config_struct_layout_matches_the_header():
+    cfg = binding.default_config()
+    assert cfg.abi_version == 1 and cfg.num_queries == 1 and cfg.world_size == 1
+    assert cfg.cost_scaling_h == 10.0 and cfg.use_cumulative_costs == 1 and cfg.use_projection == 0
+    assert list(cfg.derivative_weights) == [0.0, 0.0, 1.0, 0.0]
+    assert cfg.noise_decay[31] == 1.0 and cfg.seed == 2024
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="this test is about machines without a GPU")
+def test_no_device_means_an_error_not_a_fallback():
+    with pytest.raises(binding.StompB200Error) as err:
+        binding.Engine(num_time_steps=20, num_dimensions=7, min_rollouts=4, max_rollouts=4, num_rollouts_per_iteration=4)
+    assert err.value.code == binding.ERR_NO_DEVICE
+
+
+def test_invalid_configurations_are_rejected_before_touching_the_device():
+    L = binding.lib()
+    cfg = binding.default_config()
+    h = ctypes.c_void_p()
+    cfg.num_time_steps, cfg.num_dimensions = 20, 40      # too many joints
+    cfg.min_rollouts = cfg.max_rollouts = cfg.num_rollouts_per_iteration = 4
+    assert L.stomp_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    cfg.num_dimensions, cfg.use_projection = 7, 1         # shipped-disabled switch, not built
+    assert L.stomp_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == binding.ERR_UNSUPPORTED
+    assert L.stomp_b200_status_string(-2).decode().startswith("no CUDA device")

@@ -1,0 +1,290 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): costs, probabilities and updated trajectories within 1e-9 relative
+in FP64; the collision / no-collision verdict per timestep bit-exact."""
+import numpy as np
+import pytest
+
+from motion_planners_b200 import binding, problems as P
+from oracle.binding import Oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def _pair(pb, min_r=None, max_r=None, per_it=None, **kw):
+    K = pb.num_rollouts
+    min_r, max_r, per_it = min_r or K, max_r or K, per_it or K
+    T, D = pb.num_time_steps, pb.chain.num_dimensions
+    okw = {k: v for k, v in kw.items() if k in ("use_noise_adaptation", "noise_decay")}
+    o = Oracle(num_time_steps=T, num_dimensions=D, min_rollouts=min_r, max_rollouts=max_r,
+               num_rollouts_per_iteration=per_it, noise_stddev=pb.noise_stddev, **okw)
+    o.set_problem(pb)
+    pol = o.policy()
+    ekw = {k: v for k, v in kw.items() if k in ("use_noise_adaptation", "noise_decay")}
+    e = binding.engine_for_problem(pb, min_rollouts=min_r, max_rollouts=max_r, per_iteration=per_it, policy=pol,
+                                   keep_debug_tensors=True, **ekw)
+    return o, e, pol
+
+
+def _compare_iteration(o, e, cost, valid):
+    num, gen = o.num_rollouts()
+    assert e.num_rollouts() == (num, gen)
+    np.testing.assert_allclose(e.tensor("rollouts")[0][:gen], o.field("parameters_noise")[:gen], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(e.tensor("noise")[0], o.field("noise"), rtol=1e-12, atol=1e-15)
+    # verdicts: bit-exact
+    np.testing.assert_array_equal(e.tensor("verdicts")[0].astype(bool), o.field("state_costs") > 0.5)
+    np.testing.assert_array_equal(e.tensor("state_costs")[0], o.field("state_costs"))
+    np.testing.assert_array_equal(e.tensor("rollout_validity")[0], o.rollout_validity())
+    np.testing.assert_allclose(e.tensor("control_costs")[0], o.field("control_costs"), rtol=RTOL, atol=1e-18)
+    np.testing.assert_allclose(e.tensor("cumulative_costs")[0], o.field("cumulative_costs")[:, :, 0], rtol=RTOL)
+    np.testing.assert_allclose(e.tensor("full_costs")[0], o.field("full_costs"), rtol=RTOL)
+    np.testing.assert_allclose(e.tensor("total_cost")[0], o.field("total_cost"), rtol=RTOL)
+    np.testing.assert_allclose(e.tensor("probabilities")[0], o.field("probabilities"), rtol=RTOL, atol=1e-300)
+    np.testing.assert_allclose(e.tensor("full_probabilities")[0], o.field("full_probabilities"), rtol=RTOL, atol=1e-300)
+    np.testing.assert_allclose(e.tensor("updates")[0], o.updates(), rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(e.tensor("parameters")[0], o.parameters(), rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(e.tensor("stddevs")[0], o.stddevs(), rtol=RTOL)
+    nl = o.noiseless()
+    np.testing.assert_allclose(cost[0], nl["total_cost"], rtol=RTOL)
+    assert bool(valid[0]) == nl["valid"]
+    np.testing.assert_array_equal(e.tensor("noiseless_state_costs")[0], nl["state_costs"])
+    np.testing.assert_allclose(e.tensor("noiseless_control_costs")[0], nl["control_costs"], rtol=RTOL, atol=1e-18)
+
+
+def test_sphere_centres_are_bit_identical():
+    chain, spheres = P.dual_arm_chain(), P.dual_arm_spheres()
+    chain.axis[2] = np.array([1.0, 2.0, 2.0]) / 3.0      # general axis
+    chain.origin_rpy[4] = [0.3, -0.2, 0.7]               # fixed rotation
+    chain.axis[9] = [-1.0, 0.0, 0.0]                     # negated axis
+    chain.prismatic[12] = 1
+    o = Oracle(num_time_steps=10, num_dimensions=14, min_rollouts=2, max_rollouts=2, num_rollouts_per_iteration=2,
+               noise_stddev=np.ones(14))
+    o.set_chain(chain)
+    o.set_spheres(spheres)
+    e = binding.Engine(num_time_steps=10, num_dimensions=14, min_rollouts=2, max_rollouts=2, num_rollouts_per_iteration=2)
+    e.set_chain(chain)
+    e.set_spheres(spheres)
+    rng = np.random.default_rng(5)
+    q = rng.uniform(-3.1, 3.1, (512, 14))
+    q[0] = 0.0
+    q[1] = 1e4 * rng.standard_normal(14)                 # far outside the joint range: reduction still agrees
+    got = e.sphere_centres(q)
+    ref = np.stack([o.sphere_centres(x) for x in q])
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+
+
+@pytest.mark.parametrize("shape", ["iiwa", "dual_arm"])
+def test_state_verdicts_are_bit_exact(shape, medium_problem):
+    pb = medium_problem if shape == "iiwa" else P.dual_arm_problem(K=8, T=30, sdf_n=96)
+    o, e, _ = _pair(pb)
+    D = pb.chain.num_dimensions
+    rng = np.random.default_rng(3)
+    theta = rng.uniform(pb.chain.lower[None, :, None], pb.chain.upper[None, :, None], (64, D, pb.num_time_steps))
+    costs, verdicts, validity = e.evaluate_states(theta)
+    rc, rv, rval = o.state_costs(theta, threads=4)
+    np.testing.assert_array_equal(verdicts, rv)
+    np.testing.assert_array_equal(costs, rc)
+    np.testing.assert_array_equal(validity, rval)
+    assert 0.02 < costs.mean() < 0.98
+    # K = 1, T = 1: the start / goal validity query of MotionPlanners::checkStartState
+    c1, v1, val1 = e.evaluate_states(np.atleast_2d(pb.start).reshape(-1, D)[0][None, :, None])
+    assert c1.shape == (1, 1) and val1[0] == 1
+
+
+def test_iterations_with_injected_noise(medium_problem):
+    pb = medium_problem
+    T, D, K = pb.num_time_steps, pb.chain.num_dimensions, pb.num_rollouts
+    o, e, pol = _pair(pb)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(11)
+    for it in range(5):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((K, D, T)))
+        if it == 2:
+            unit *= 8.0      # push many samples onto the joint limits (filter / clamp path)
+        o.iterate(it, noise=unit)
+        cost, valid, stop = e.iterate(it, noise=unit[None])
+        _compare_iteration(o, e, cost, valid)
+    assert e.num_rollouts() == (K + 1, K)
+
+
+def test_shipped_yml_shape_with_rollout_reuse(small_problem):
+    # reference test/config/stomp.yml:3-5: min 5, max 50, 10 per iteration -> 10, 21, 32, 43, 51, 51 rollouts
+    pb = small_problem
+    T, D = pb.num_time_steps, pb.chain.num_dimensions
+    o, e, pol = _pair(pb, 5, 50, 10)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(7)
+    counts = []
+    for it in range(8):
+        assert e.next_num_generated() == 10
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((10, D, T)))
+        o.iterate(it, noise=unit)
+        cost, valid, stop = e.iterate(it, noise=unit[None])
+        _compare_iteration(o, e, cost, valid)
+        counts.append(e.num_rollouts()[0])
+    assert counts == [10, 21, 32, 43, 51, 51, 51, 51]
+
+
+def test_min_rollouts_above_per_iteration(small_problem):
+    # first iteration generates min_rollouts (PolicyImprovement.cpp:175-180)
+    pb = small_problem
+    T, D = pb.num_time_steps, pb.chain.num_dimensions
+    o, e, pol = _pair(pb, 12, 20, 4)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(8)
+    for it in range(5):
+        g = e.next_num_generated()
+        assert g == (12 if it == 0 else 4)
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((g, D, T)))
+        o.iterate(it, noise=unit)
+        cost, valid, _ = e.iterate(it, noise=unit[None])
+        _compare_iteration(o, e, cost, valid)
+
+
+def test_no_adaptation_and_noise_decay(small_problem):
+    pb = small_problem
+    T, D = pb.num_time_steps, pb.chain.num_dimensions
+    o, e, pol = _pair(P.single_arm_problem(K=16, T=20, sdf_n=64), use_noise_adaptation=False, noise_decay=np.full(7, 0.9))
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(9)
+    for it in range(4):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((16, D, T)))
+        o.iterate(it, noise=unit)
+        cost, valid, _ = e.iterate(it, noise=unit[None])
+        _compare_iteration(o, e, cost, valid)
+    np.testing.assert_allclose(e.tensor("stddevs")[0], pb.noise_stddev * 0.9 ** 2, rtol=1e-15)
+
+
+def test_epsilon_goes_through_the_cholesky_factor_on_the_device(medium_problem):
+    pb = medium_problem
+    T, D, K = pb.num_time_steps, pb.chain.num_dimensions, pb.num_rollouts
+    o, e, pol = _pair(pb)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(13)
+    for it in range(2):
+        eps = rng.standard_normal((K, D, T))
+        cost, valid, _ = e.iterate(it, epsilon=eps[None])
+        unit = e.tensor("unit_noise")[0]
+        ref = np.einsum("tu,kdu->kdt", pol["L"], eps)
+        np.testing.assert_allclose(unit, ref, rtol=1e-12, atol=1e-14 * abs(ref).max())
+        o.iterate(it, noise=unit)           # downstream of the contraction the loop is compared as usual
+        _compare_iteration(o, e, cost, valid)
+
+
+def test_on_device_sampler(medium_problem):
+    pb = medium_problem
+    T, D, K = pb.num_time_steps, pb.chain.num_dimensions, pb.num_rollouts
+    o, e, pol = _pair(pb)
+    o.begin_solve(); e.begin_solve()
+    all_eps = []
+    for it in range(3):
+        cost, valid, _ = e.iterate(it)
+        eps = e.tensor("epsilon")[0]
+        unit = e.tensor("unit_noise")[0]
+        ref = np.einsum("tu,kdu->kdt", pol["L"], eps)
+        np.testing.assert_allclose(unit, ref, rtol=1e-12, atol=1e-14 * abs(ref).max())
+        o.iterate(it, noise=unit)
+        _compare_iteration(o, e, cost, valid)
+        all_eps.append(eps)
+    z = np.concatenate([a.ravel() for a in all_eps])
+    n = z.size
+    assert abs(z.mean()) < 5.0 / np.sqrt(n)
+    assert abs(z.var() - 1.0) < 5.0 * np.sqrt(2.0 / n)
+    assert abs((z ** 4).mean() - 3.0) < 0.2
+    assert not np.array_equal(all_eps[0], all_eps[1])          # the iteration is part of the counter
+    # same seed, same numbers; another seed, other numbers
+    e2 = binding.engine_for_problem(pb, policy=pol, keep_debug_tensors=True)
+    e2.begin_solve(); e2.iterate(0)
+    np.testing.assert_array_equal(e2.tensor("epsilon")[0], all_eps[0])
+    e3 = binding.engine_for_problem(pb, policy=pol, keep_debug_tensors=True, seed=7)
+    e3.begin_solve(); e3.iterate(0)
+    assert not np.array_equal(e3.tensor("epsilon")[0], all_eps[0])
+
+
+def test_run_equals_iterate_and_stop_rule_freezes_the_query(small_problem):
+    pb = P.single_arm_problem(K=32, T=20, sdf_n=64)
+    pol = None
+    a = binding.engine_for_problem(pb, keep_debug_tensors=True)
+    b = binding.engine_for_problem(pb, keep_debug_tensors=True)
+    a.begin_solve(); b.begin_solve()
+    stops = []
+    for it in range(12):
+        cost, valid, stop = a.iterate(it)
+        stops.append(bool(stop[0]))
+    b.run(0, 12, honour_stop=False)
+    np.testing.assert_array_equal(a.tensor("parameters"), b.tensor("parameters"))
+    ra, rb = a.finish_solve(), b.finish_solve()
+    np.testing.assert_array_equal(ra["solution"], rb["solution"])
+    assert ra["iterations"][0] == 12
+    # with the stop rule honoured the query freezes at the first iteration that satisfied it
+    c = binding.engine_for_problem(pb)
+    c.begin_solve()
+    c.run(0, 12, honour_stop=True)
+    rc = c.finish_solve()
+    if any(stops):
+        first = stops.index(True)
+        assert rc["iterations"][0] == first + 1
+        assert rc["found"][0]
+    else:
+        assert rc["iterations"][0] == 12
+
+
+def test_batch_of_queries_equals_separate_engines():
+    Q, K, T = 6, 16, 40
+    pb = P.batch_problem(Q=Q, K=K, T=T, sdf_n=64)
+    batch = binding.engine_for_problem(pb, keep_debug_tensors=True)
+    batch.begin_solve()
+    units = []
+    for it in range(4):
+        batch.iterate(it)
+        units.append(batch.tensor("unit_noise"))
+    got = batch.finish_solve()
+    assert got["solution"].shape == (Q, 7, T)
+    for q in range(Q):
+        single = P.Problem(pb.chain, pb.spheres, pb.sdf, pb.start[q], pb.goal[q], pb.noise_stddev, T, K)
+        # the same query alone, fed the unit noise the batch engine drew for it: bitwise the same trajectory
+        e = binding.engine_for_problem(single)
+        e.begin_solve()
+        for it in range(4):
+            e.iterate(it, noise=units[it][q][None])
+        np.testing.assert_array_equal(e.finish_solve()["solution"][0], got["solution"][q])
+        # and the oracle (its own policy products: agreement limited by the conditioning of R)
+        o = Oracle(num_time_steps=T, num_dimensions=7, min_rollouts=K, max_rollouts=K, num_rollouts_per_iteration=K,
+                   noise_stddev=pb.noise_stddev)
+        o.set_problem(single)
+        o.begin_solve()
+        for it in range(4):
+            o.iterate(it, noise=units[it][q])
+        np.testing.assert_allclose(got["solution"][q], o.parameters(), rtol=0, atol=1e-7)
+
+
+def test_full_size_properties_config3():
+    # BASELINE config 3 shape: K=4096, T=100, 7-DoF, 256^3 SDF — size-independent properties
+    pb = P.single_arm_problem(K=4096, T=100, sdf_n=256)
+    e = binding.engine_for_problem(pb)
+    e.begin_solve()
+    for it in range(3):
+        cost, valid, stop = e.iterate(it)
+        p = e.tensor("probabilities")[0]
+        np.testing.assert_allclose(p.sum(0), 1.0, rtol=1e-11)
+        np.testing.assert_allclose(e.tensor("full_probabilities")[0].sum(0), 1.0, rtol=1e-11)
+        assert np.all(p == p[:, :, :1])
+        np.testing.assert_allclose(p.min(0)[:, 0] / p.max(0)[:, 0], np.exp(-10.0), rtol=1e-9)
+        sc = e.tensor("state_costs")[0]
+        assert set(np.unique(sc)) <= {0.0, 1.0}
+        np.testing.assert_array_equal(sc > 0.5, e.tensor("verdicts")[0].astype(bool))
+        rl = e.tensor("rollouts")[0]
+        assert np.all(rl >= pb.chain.lower[None, :, None]) and np.all(rl <= pb.chain.upper[None, :, None])
+        # the verdict kernel on its own agrees with the loop's verdicts (idempotence of the cost path)
+        _, v2, _ = e.evaluate_states(rl[:256])
+        np.testing.assert_array_equal(v2, e.tensor("verdicts")[0][:256])
+    n, g = e.num_rollouts()
+    assert (n, g) == (4097, 4096)
+    # a sample of the full-size rollouts against the oracle's verdicts
+    o = Oracle(num_time_steps=100, num_dimensions=7, min_rollouts=4, max_rollouts=4, num_rollouts_per_iteration=4,
+               noise_stddev=pb.noise_stddev)
+    o.set_problem(pb)
+    _, rv, _ = o.state_costs(rl[::64], threads=4)
+    np.testing.assert_array_equal(rv, e.tensor("verdicts")[0][::64][: rv.shape[0]])
