@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the STOMP rollout loop (BASELINE.json metric: rollout-timesteps/s and ms/iteration,
+K=4096, T=100, 7-DoF, 256^3 SDF, at 1/2/4/8 GPUs).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path through the C ABI
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+
+A "step" is one STOMP iteration (Stomp::runSingleIteration): generate K rollouts, cost them, weight them,
+update the trajectory, cost the noise-less rollout.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "stomp_rollout_timesteps_per_sec"
+UNIT = "rollout-timesteps/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric is quoted on; fits one GPU
+    "c3": dict(kind="single", K=4096, T=100, sdf_n=256, label="STOMP 7-DoF iiwa, K=4096 rollouts, T=100, 256^3 SDF"),
+    "c2": dict(kind="single", K=128, T=100, sdf_n=128, label="STOMP 7-DoF iiwa, K=128 rollouts, T=100, 128^3 SDF"),
+    "c4": dict(kind="batch", Q=1024, K=64, T=200, sdf_n=128, label="1024 independent 7-DoF queries, K=64, T=200"),
+    "c5": dict(kind="dual", K=2048, T=150, sdf_n=512, label="dual-arm 14-DoF, K=2048, T=150, 512^3 SDF"),
+}
+
+
+def make_problem(name):
+    from motion_planners_b200 import problems as P
+    w = WORKLOADS[name]
+    if w["kind"] == "single":
+        return P.single_arm_problem(K=w["K"], T=w["T"], sdf_n=w["sdf_n"])
+    if w["kind"] == "batch":
+        return P.batch_problem(Q=w["Q"], K=w["K"], T=w["T"], sdf_n=w["sdf_n"])
+    return P.dual_arm_problem(K=w["K"], T=w["T"], sdf_n=w["sdf_n"])
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            sm, mx, reasons = [], [], set()
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        return out
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def dist_max(dist, value, local):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def dist_barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(local)
+
+
+def broadcast_bytes(dist, payload, local):
+    if dist is None:
+        return payload
+    import torch
+    t = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+    if dist.get_rank() == 0:
+        t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+class L2Flusher:
+    """Writes a buffer larger than the 126 MB L2 between timed iterations."""
+
+    def __init__(self, local, nbytes=256 << 20):
+        import torch
+        self.torch = torch
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{local}")
+        self.val = 0
+
+    def flush(self):
+        self.val = (self.val + 1) % 251
+        self.buf.fill_(self.val)
+        self.torch.cuda.synchronize()
+
+
+def cpu_baseline(problem, workload, threads, sample_rollouts, iterations, dense=True):
+    """The reference's CPU path (oracle port) on a bounded sample of the workload: same T, D, spheres and
+    SDF, `sample_rollouts` rollouts per iteration.  Timed around the iteration loop, where the reference
+    times (MotionPlanners.cpp:506-512); one-time policy setup excluded."""
+    from oracle.binding import Oracle
+    T, D = problem.num_time_steps, problem.chain.num_dimensions
+    o = Oracle(num_time_steps=T, num_dimensions=D, min_rollouts=sample_rollouts, max_rollouts=sample_rollouts,
+               num_rollouts_per_iteration=sample_rollouts, noise_stddev=problem.noise_stddev,
+               use_openmp=threads > 1, dense_control_costs=dense, seed=42)
+    if threads > 1:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    o.set_problem(problem, query=0)
+    res = o.solve(iterations, honour_stop=False)
+    states = sample_rollouts * T * iterations
+    return states / res["seconds"], res["seconds"]
+
+
+def run_reference(args):
+    rank, world, local, dist = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    from oracle import binding as ob
+    problem = make_problem(args.workload)
+    w = WORKLOADS[args.workload]
+    threads = ob.max_threads()
+    T = problem.num_time_steps
+    sample = min(w["K"], args.reference_sample)
+    # warm-up + timed steps; every step is one iteration over the bounded sample
+    cpu_baseline(problem, args.workload, threads, sample, max(1, args.warmup))
+    rate, seconds = cpu_baseline(problem, args.workload, threads, sample, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "name": args.workload},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} of {w['K']} rollouts per iteration, same T / D / spheres / SDF; "
+                                   f"OpenMP over rollouts in Task::execute as the reference (Stomp.cpp:210); dense "
+                                   f"O(N^2) control-cost and n^T R n forms kept"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference (Eigen/Boost/robot_model/FCL) cannot be built in this image; this is the oracle port of "
+                "its algorithm with the sphere-vs-SDF task in place of the FCL query",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    from motion_planners_b200 import binding
+    rank, world, local, dist = dist_setup(args.gpus)
+    w = WORKLOADS[args.workload]
+    problem = make_problem(args.workload)
+    T, D, K = problem.num_time_steps, problem.chain.num_dimensions, problem.num_rollouts
+    S = len(problem.spheres.link)
+    Q = problem.num_queries
+    shard_mode = 1 if w["kind"] == "batch" else 0
+    eng = binding.engine_for_problem(problem, device=local, world_size=world, rank=rank, shard_mode=shard_mode)
+    if world > 1 and shard_mode == 0:
+        uid = binding.comm_unique_id() if rank == 0 else bytes(128)
+        eng.comm_init(broadcast_bytes(dist, uid, local))
+    states_per_step = Q * K * T                       # whole job, all ranks
+    flusher = L2Flusher(local) if args.l2 == "flush" else None
+
+    # ---- warm-up ----
+    eng.begin_solve()
+    eng.run(0, args.warmup)
+    it = args.warmup
+
+    # ---- timed region: device-side (value) ----
+    sampler = ClockSampler(local)
+    dist_barrier(dist, local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    total_ms = 0.0
+    if flusher is None:
+        eng.timer_begin()
+        eng.run(it, args.steps)
+        total_ms = eng.timer_end()
+        it += args.steps
+    else:
+        for _ in range(args.steps):
+            flusher.flush()
+            eng.timer_begin()
+            eng.run(it, 1)
+            total_ms += eng.timer_end()
+            it += 1
+    launches = eng.launch_count() - launches0
+    dist_barrier(dist, local)
+    total_ms = dist_max(dist, total_ms, local)
+    value = states_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- steady state (no flush, iterations queued back to back: how solve() runs) ----
+    dist_barrier(dist, local)
+    eng.timer_begin()
+    eng.run(it, args.steps)
+    steady_ms = dist_max(dist, eng.timer_end(), local)
+    it += args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel pass for the roofline of the dominant kernel (rollout cost) ----
+    eng.set_profiling(True)
+    eng.reset_kernel_stats()
+    for _ in range(args.steps):
+        if flusher is not None:
+            flusher.flush()
+        eng.run(it, 1)
+        it += 1
+    stats = eng.kernel_stats()
+    eng.set_profiling(False)
+    eng.finish_solve()
+
+    # ---- end to end: the call sequence StompPlanner::solve makes, host buffers in and out ----
+    e2e_iters = args.steps
+    pol = eng.policy
+    h2d = (pol["params_all"].nbytes + pol["mincc"].nbytes) * eng.Q
+    d2h = eng.Q * (D * T * 8 + 8 + 4 + 4) + e2e_iters * eng.Q * 13
+    dist_barrier(dist, local)
+    t0 = time.perf_counter()
+    for ql in range(eng.Q):
+        eng.set_policy(ql, pol["params_all"], pol["mincc"])          # H2D
+    eng.begin_solve()
+    for i in range(e2e_iters):
+        eng.iterate(i)                                               # D2H: noise-less cost, validity, stop flag
+    eng.finish_solve()                                               # D2H: solution
+    e2e_s = dist_max(dist, time.perf_counter() - t0, local)
+    dist_barrier(dist, local)
+
+    if rank != 0:
+        eng.close()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    cost_ms, cost_n = stats["cost"]
+    states_per_launch = (eng.Q * K * T) // (world if shard_mode == 0 else 1)
+    alg_bytes = (8 * D + 4 * S + 9) * states_per_launch
+    achieved = alg_bytes / (cost_ms / max(cost_n, 1) * 1e-3) / 1e9 if cost_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("rollout_cost_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    base_rate, base_s = (None, None)
+    cb = None
+    if not args.skip_cpu_baseline:
+        from oracle import binding as ob
+        threads = ob.max_threads()
+        sample = min(K, args.cpu_sample)
+        base_rate, base_s = cpu_baseline(problem, args.workload, threads, sample, 5)
+        one_rate, _ = cpu_baseline(problem, args.workload, 1, max(8, sample // 8), 2)
+        cb = {"value": base_rate, "unit": UNIT, "cores": threads, "kind": "port",
+              "sample": f"{sample} of {K} rollouts x 5 iterations, same T / D / spheres / SDF, OpenMP over rollouts",
+              "single_thread_value": one_rate}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak" if shard_mode == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "name": args.workload, "K": K, "T": T, "D": D, "S": S, "Q": Q,
+                   "sdf": list(map(int, problem.sdf.dims)), "sharding": ("queries" if shard_mode == 1 else "rollouts") if world > 1 else "none",
+                   "l2": "flushed (256 MiB write) between timed iterations" if flusher else "not flushed",
+                   "noise": "on-device Philox4x32-10"},
+        "clocks": clocks,
+        "e2e": {"value": states_per_step * e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_iters,
+                "d2h_bytes_per_step": d2h / e2e_iters,
+                "what": "set_policy + begin_solve + one stomp_b200_iterate per step (noise-less cost / validity / stop "
+                        "flag read back every step) + finish_solve (solution read back), host wall clock"},
+        "gpu_launches": int(launches),
+        "steady_state": {"value": states_per_step * args.steps / (steady_ms * 1e-3), "ms_per_step": steady_ms / args.steps,
+                         "what": "same steps queued back to back without L2 flushes, as solve() runs them"},
+        "roofline": {"kernel": "rollout_cost_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic,
+                     "peak_kind": peak_kind, "algorithmic_bytes_per_state": 8 * D + 4 * S + 9,
+                     "states_per_launch": states_per_launch, "avg_launch_ms": cost_ms / max(cost_n, 1)},
+        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in stats.items()},
+        "cpu_baseline": cb,
+    }
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--l2", default="flush", choices=["flush", "keep"])
+    ap.add_argument("--cpu-sample", type=int, default=2048, dest="cpu_sample")
+    ap.add_argument("--reference-sample", type=int, default=1024, dest="reference_sample")
+    ap.add_argument("--skip-cpu-baseline", action="store_true", dest="skip_cpu_baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

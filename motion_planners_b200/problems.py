@@ -158,13 +158,13 @@ def _obstacle_distance(pts, kind, centre, size):
 IIWA_BLOCKER = (0, np.array([-0.17, 0.03, 1.31]), np.array([0.15, 0.15, 0.15]))
 
 
-def make_obstacles(seed=1234, count=16, keep_clear=None, clear_margin=0.05, blockers=()):
+def make_obstacles(seed=1234, count=16, keep_clear=None, clear_margin=0.05, blockers=(), urdf_box=True):
     """`count` random spheres / boxes in [-1.5,1.5]^3 + the URDF's box_1 (kuka_iiwa.urdf:29-56).
 
     Rejected if within 0.35 m of the base column or (keep_clear = [(centres[S,3], radii[S]), ...])
     touching the robot at the given configurations."""
     rng = np.random.default_rng(seed)
-    obstacles = [(1, np.array([0.5, 0.0, 0.5]), np.array([0.1, 0.1, 0.3]))] + list(blockers)
+    obstacles = ([(1, np.array([0.5, 0.0, 0.5]), np.array([0.1, 0.1, 0.3]))] if urdf_box else []) + list(blockers)
     fixed = len(obstacles)
     while len(obstacles) < count + fixed:
         kind = int(rng.integers(0, 2))
@@ -217,9 +217,9 @@ class Problem:
     name: str = ""
 
 
-def _scene(chain, spheres, configs, n, seed, blockers=()):
+def _scene(chain, spheres, configs, n, seed, blockers=(), urdf_box=True):
     keep = [(sphere_centres_numpy(chain, spheres, q), spheres.radius) for q in configs]
-    return make_sdf(n, make_obstacles(seed=seed, keep_clear=keep, blockers=blockers))
+    return make_sdf(n, make_obstacles(seed=seed, keep_clear=keep, blockers=blockers, urdf_box=urdf_box))
 
 
 def single_arm_problem(K=128, T=100, sdf_n=128, seed=1234, name="") -> Problem:
@@ -235,7 +235,8 @@ def dual_arm_problem(K=2048, T=150, sdf_n=512, seed=1234) -> Problem:
     chain, spheres = dual_arm_chain(), dual_arm_spheres()
     start = np.concatenate([IIWA_START, IIWA_START * np.array([-1, 1, -1, 1, -1, 1, -1])])
     goal = np.concatenate([IIWA_GOAL, IIWA_GOAL * np.array([-1, 1, -1, 1, -1, 1, -1])])
-    sdf = _scene(chain, spheres, [start, goal], sdf_n, seed)
+    # the URDF's box_1 stands where the two mirrored arms start; the dual-arm scene leaves it out
+    sdf = _scene(chain, spheres, [start, goal], sdf_n, seed, urdf_box=False)
     return Problem(chain, spheres, sdf, start, goal, np.concatenate([IIWA_NOISE_STDDEV, IIWA_NOISE_STDDEV]),
                    T, K, name=f"dual14_K{K}_T{T}_sdf{sdf_n}")
 

@@ -31,8 +31,8 @@ def _pair(pb, min_r=None, max_r=None, per_it=None, **kw):
 def _compare_iteration(o, e, cost, valid):
     num, gen = o.num_rollouts()
     assert e.num_rollouts() == (num, gen)
-    np.testing.assert_allclose(e.tensor("rollouts")[0][:gen], o.field("parameters_noise")[:gen], rtol=1e-12, atol=1e-14)
-    np.testing.assert_allclose(e.tensor("noise")[0], o.field("noise"), rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(e.tensor("rollouts")[0][:gen], o.field("parameters_noise")[:gen], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(e.tensor("noise")[0], o.field("noise"), rtol=RTOL, atol=1e-12)
     # verdicts: bit-exact
     np.testing.assert_array_equal(e.tensor("verdicts")[0].astype(bool), o.field("state_costs") > 0.5)
     np.testing.assert_array_equal(e.tensor("state_costs")[0], o.field("state_costs"))
@@ -89,8 +89,9 @@ def test_state_verdicts_are_bit_exact(shape, medium_problem):
     np.testing.assert_array_equal(validity, rval)
     assert 0.02 < costs.mean() < 0.98
     # K = 1, T = 1: the start / goal validity query of MotionPlanners::checkStartState
-    c1, v1, val1 = e.evaluate_states(np.atleast_2d(pb.start).reshape(-1, D)[0][None, :, None])
-    assert c1.shape == (1, 1) and val1[0] == 1
+    for q, free in ((pb.start, True), (pb.goal, True)):
+        c1, v1, val1 = e.evaluate_states(q[None, :, None])
+        assert c1.shape == (1, 1) and bool(val1[0]) == free and bool(v1[0, 0]) != free
 
 
 def test_iterations_with_injected_noise(medium_problem):
