@@ -1,0 +1,43 @@
+// motion_planners::MotionPlanners — the facade test_motion_planners drives (reference
+// include/motion_planners/MotionPlanners.hpp:24-224), reduced to the calls on the STOMP path:
+// initialize, assignPlanningRequest (joint-space start / goal), setStartAndGoal, solve (wall-clock timed,
+// reference src/MotionPlanners.cpp:503-515), usePredictedTrajectory, reInitializePlanner.
+#pragma once
+#include <memory>
+#include <string>
+
+#include <base/JointsTrajectory.hpp>
+#include <base/samples/Joints.hpp>
+#include <motion_planners/Config.hpp>
+#include <abstract/AbstractPlanner.hpp>
+#include <PlannerFactory.hpp>
+#include <robot_model/RobotModel.hpp>
+
+namespace motion_planners {
+
+class MotionPlanners {
+public:
+    explicit MotionPlanners(Config config);
+    ~MotionPlanners();
+    bool initialize(PlannerStatus& planner_status);
+    bool reInitializePlanner();
+    bool reInitializePlanner(const int& num_time_steps);
+    bool assignPlanningRequest(const base::samples::Joints& start_jointvalues, const base::samples::Joints& target_jointvalues,
+                               PlannerStatus& planner_status);
+    bool usePredictedTrajectory(base::JointsTrajectory& input_trajectory, PlannerStatus& planner_status);
+    void setStartAndGoal();
+    bool solve(base::JointsTrajectory& solution, PlannerStatus& planner_status, double& time_taken);
+    std::shared_ptr<robot_model::RobotModel> getRobotModel() { return robot_model_; }
+
+    AbstractPlannerPtr planner_;
+
+private:
+    bool checkStartState(const base::samples::Joints& current_robot_status, PlannerStatus& planner_status);
+    bool checkGoalState(const base::samples::Joints& goal, PlannerStatus& planner_status);
+    Config config_;
+    std::shared_ptr<robot_model::RobotModel> robot_model_;
+    base::samples::Joints initial_joint_status_, goal_joint_status_;
+    ConstraintPlanning constrainted_target_;
+};
+
+}  // namespace motion_planners

@@ -1,0 +1,98 @@
+// Shim for robot_model/RobotModel.hpp (planning/robot_model is an un-vendored dependency of the
+// reference: manifest.xml:10-20).  It keeps the members the STOMP path calls —
+// getPlanningGroupName / getPlanningGroupJointsName / getPlanningGroupJointInformation / getJointLimits /
+// getWorldFrameName / getBaseFrameName / getTipFrameName / updateJointGroup / isStateValid
+// (reference OptimizationTask.cpp:11-14,190-192, AbstractPlanner.cpp:13-27) — and replaces KDL + FCL by
+// what the CUDA path consumes: the joint chain, link spheres and a signed distance field.
+// updateJointGroup + isStateValid are answered by the same CUDA verdict kernel the planner uses
+// (stomp_b200_evaluate_states): there is no CPU collision checker in this build.
+#pragma once
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <base/Eigen.hpp>
+#include <base/samples/Joints.hpp>
+#include <robot_model/RobotModelConfig.hpp>
+
+struct stomp_b200_engine;
+
+namespace urdf {
+struct Joint {
+    enum Type { UNKNOWN, REVOLUTE, CONTINUOUS, PRISMATIC, FLOATING, PLANAR, FIXED };
+    std::string name, parent_link_name, child_link_name;
+    int type = UNKNOWN;
+    double origin_xyz[3] = {0, 0, 0}, origin_rpy[3] = {0, 0, 0}, axis[3] = {1, 0, 0};
+    double lower = 0, upper = 0, velocity = 0, effort = 0;
+};
+}  // namespace urdf
+
+namespace robot_model {
+
+struct CollisionSphere { int link; double xyz[3]; double radius; };      // link = index of the chain joint
+struct Obstacle { int kind; double centre[3]; double size[3]; std::string name; };   // kind 0 sphere (size[0] = r), 1 box (half extents)
+
+struct SignedDistanceField {
+    int dims[3] = {0, 0, 0};
+    double origin[3] = {0, 0, 0};
+    double voxel = 0;
+    std::vector<float> grid;   // x fastest
+};
+
+class RobotModel {
+public:
+    explicit RobotModel(const RobotModelConfig& config);
+    ~RobotModel();
+    bool initialization();    // loads URDF chain, spheres, environment; builds the SDF
+
+    // ---- the reference's interface -------------------------------------------------------------
+    std::string getPlanningGroupName() const { return config_.planning_group_name; }
+    void getPlanningGroupJointsName(const std::string& group, std::vector<std::string>& names) const;
+    bool getPlanningGroupJointInformation(const std::string& group, std::vector<std::pair<std::string, urdf::Joint> >& joints,
+                                          std::vector<std::string>& names) const;
+    bool getPlanningGroupJointInformation(const std::string& group, std::vector<std::pair<std::string, urdf::Joint> >& joints) const;
+    bool getJointLimits(std::vector<double>& lower, std::vector<double>& upper) const;
+    std::string getWorldFrameName() const { return world_frame_; }
+    std::string getBaseFrameName() const { return base_link_; }
+    std::string getTipFrameName() const { return tip_link_; }
+    void updateJointGroup(const std::vector<std::string>& names, const base::VectorXd& positions);
+    void updateJointGroup(const base::samples::Joints& joints);
+    bool isStateValid(double& collision_cost);
+
+    // ---- what the CUDA path consumes -------------------------------------------------------------
+    const std::vector<urdf::Joint>& chain() const { return chain_; }
+    const std::vector<CollisionSphere>& spheres() const { return spheres_; }
+    const SignedDistanceField& sdf() const { return sdf_; }
+    const std::vector<Obstacle>& obstacles() const { return obstacles_; }
+    // programmatic setup (instead of files)
+    void setChain(const std::vector<urdf::Joint>& chain, const std::string& base_link, const std::string& tip_link);
+    void setSpheres(const std::vector<CollisionSphere>& spheres);
+    void addObstacle(const Obstacle& o) { obstacles_.push_back(o); sdf_dirty_ = true; }
+    void setSdfGrid(int resolution, const double lower[3], const double upper[3]);
+    void setSdf(const SignedDistanceField& sdf);
+    bool buildSdf();   // exact signed distance of the obstacle union at the voxel centres (one-time, host)
+    // push chain / spheres / SDF into an engine (used by the planner and by isStateValid)
+    int configureEngine(stomp_b200_engine* engine) const;
+    int device() const { return config_.device; }
+
+private:
+    bool loadUrdf(const std::string& path);
+    bool loadSpheres(const std::string& path);
+    bool loadEnvironment(const std::string& path);
+    bool ensureValidityEngine();
+
+    RobotModelConfig config_;
+    std::string world_frame_, base_link_, tip_link_;
+    std::vector<urdf::Joint> all_joints_, chain_;
+    std::vector<CollisionSphere> spheres_;
+    std::vector<Obstacle> obstacles_;
+    SignedDistanceField sdf_;
+    int sdf_resolution_ = 64;
+    double sdf_lower_[3] = {-1.5, -1.5, -1.5}, sdf_upper_[3] = {1.5, 1.5, 1.5};
+    bool sdf_dirty_ = true;
+    std::vector<double> joint_state_;
+    stomp_b200_engine* validity_engine_ = nullptr;
+};
+
+}  // namespace robot_model
