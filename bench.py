@@ -140,12 +140,8 @@ def dist_barrier(dist, local):
 def broadcast_bytes(dist, payload, local):
     if dist is None:
         return payload
-    import torch
-    t = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
-    if dist.get_rank() == 0:
-        t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
-    dist.broadcast(t, 0)
-    return bytes(t.cpu().numpy().tobytes())
+    from motion_planners_b200 import sharding
+    return sharding.broadcast_bytes(dist, payload, 128, f"cuda:{local}")
 
 
 class L2Flusher:

@@ -36,10 +36,14 @@ def test_test_motion_planners_finds_a_path():
     assert out.returncode == 0, out.stdout + out.stderr
     assert "Path Found" in out.stdout
     assert "Number of timestep :20. Number of joints = 7" in out.stdout
-    rows = [l.split() for l in out.stdout.splitlines() if len(l.split()) == 7]
+    def _floats(line):
+        try:
+            return [float(x) for x in line.split()]
+        except ValueError:
+            return []
+    rows = [r for r in map(_floats, out.stdout.splitlines()) if len(r) == 7]
     assert len(rows) == 20
-    first = [float(x) for x in rows[0]]
-    last = [float(x) for x in rows[-1]]
+    first, last = rows[0], rows[-1]
     start = [0.5, 0.5, 0.5, -1.5, 0.5, 0.5, 0.5]
     goal = [-1.5, -1.5, -1.5, 1.5, -1.5, -1.5, -0.5]
     assert max(abs(a - b) for a, b in zip(first, start)) < 0.35
