@@ -106,8 +106,10 @@ struct stomp_b200_engine {
     uint8_t* verdict2[2] = {nullptr, nullptr};
     int cur = 0;
     int32_t* d_order = nullptr;
-    double* d_partial = nullptr;
-    int chunk = 32, max_chunks = 1;
+    int max_chunks = 1;
+    cudaStream_t side_stream = nullptr;      // noise-less rollout, overlapped with the next iteration's sampling + costs
+    cudaEvent_t ev_applied = nullptr, ev_noiseless = nullptr;
+    bool noiseless_pending = false;          // ev_noiseless recorded and not yet waited for by the main stream
     double* d_theta_all_init = nullptr;   // policy as uploaded by set_policy (restored by begin_solve? no: the policy persists)
 
     // PolicyImprovement bookkeeping (PolicyImprovement.cpp:170-186)
@@ -311,12 +313,17 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     // ---- execute + control costs + row sums (K4-K6) ----
     {
         const int R = rollouts_per_cta(e, gen_local);
-        const int threads = std::max(64, ((R * e->T + 31) / 32) * 32);
         const size_t smem = sizeof(double) * ((size_t)R * e->D * e->N + (size_t)R * e->T);
-        dim3 grid((gen_local + R - 1) / R + 1, e->Q);
+        dim3 grid((gen_local + R - 1) / R, e->Q);
+        dim3 block(e->T, R);
         Scope sc(e, STOMP_B200_KERNEL_COST);
-        rollout_cost_kernel<<<grid, threads, smem, e->stream>>>(lp, e->robot, e->sdf, R);
+        rollout_cost_kernel<<<grid, block, smem, e->stream>>>(lp, e->robot, e->sdf);
         if (int rc = check_launch(e, "rollout_cost_kernel")) return rc;
+    }
+    // ---- the noise-less rollout of the previous iteration is needed from here on ----
+    if (e->noiseless_pending) {
+        CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_noiseless, 0));
+        e->noiseless_pending = false;
     }
     if (reused > 0) {
         const int warps = 8;
@@ -336,36 +343,47 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
 
     // ---- probabilities (K7) ----
     {
+        lp.wblocks = (n + 255) / 256;
         Scope sc(e, STOMP_B200_KERNEL_WEIGHTS);
-        rollout_weights_kernel<<<dim3(e->D, e->Q), 256, 0, e->stream>>>(lp);
+        rollout_weights_kernel<<<dim3(lp.wblocks, e->D, e->Q), 256, 0, e->stream>>>(lp);
         if (int rc = check_launch(e, "rollout_weights_kernel")) return rc;
     }
     // ---- weighted sums (K8) ----
+    const int nchunks = std::max(1, (lp.num_local + lp.chunk - 1) / lp.chunk);
+    lp.nchunks = nchunks;
     {
-        const int nchunks = std::max(1, (lp.num_local + e->chunk - 1) / e->chunk);
-        const size_t smem = sizeof(double) * ((size_t)kUpdateWarps * (e->T + 2 * kRBand) + (size_t)kUpdateWarps * (e->T + 1));
-        {
-            Scope sc(e, STOMP_B200_KERNEL_UPDATE);
-            weighted_update_kernel<<<dim3(nchunks, e->D, e->Q), kUpdateWarps * 32, smem, e->stream>>>(lp, e->d_partial, e->chunk, nchunks);
-            if (int rc = check_launch(e, "weighted_update_kernel")) return rc;
-        }
-        {
-            Scope sc(e, STOMP_B200_KERNEL_UPDATE);
-            reduce_partials_kernel<<<dim3(e->D, e->Q), 256, 0, e->stream>>>(lp, e->d_partial, nchunks);
-            if (int rc = check_launch(e, "reduce_partials_kernel")) return rc;
-        }
+        const size_t smem = sizeof(double) * ((size_t)kUpdateWarps * (e->T + kRBand) + (size_t)kUpdateWarps * (e->T + 1));
+        Scope sc(e, STOMP_B200_KERNEL_UPDATE);
+        weighted_update_kernel<<<dim3(nchunks, e->D, e->Q), kUpdateWarps * 32, smem, e->stream>>>(lp);
+        if (int rc = check_launch(e, "weighted_update_kernel")) return rc;
     }
     // ---- exchange 2: update rows + adaptation numerators ----
     if (world > 1) {
+        {
+            Scope sc(e, STOMP_B200_KERNEL_UPDATE);
+            reduce_partials_kernel<<<dim3(e->D, e->Q), 256, 0, e->stream>>>(lp, nchunks);
+            if (int rc = check_launch(e, "reduce_partials_kernel")) return rc;
+        }
         const size_t count = (size_t)e->Q * e->D * (e->T + 1);
         NCCL_TRY(e, g_nccl.AllReduce(lp.updbuf, lp.updbuf, count, ncclFloat64, ncclSum, e->comm, e->stream));
     }
-    // ---- apply + noise-less rollout (K9, K10) ----
+    // ---- apply (K9) ----
     {
-        const size_t smem = sizeof(double) * ((size_t)e->D * e->N + e->T + e->sumw);
         Scope sc(e, STOMP_B200_KERNEL_APPLY);
-        apply_update_kernel<<<e->Q, 256, smem, e->stream>>>(lp, e->robot, e->sdf);
+        apply_update_kernel<<<e->Q, 256, 0, e->stream>>>(lp, world > 1 ? 0 : 1, nchunks);
         if (int rc = check_launch(e, "apply_update_kernel")) return rc;
+    }
+    // ---- noise-less rollout (K10) on the side stream: overlaps the next iteration's sampling and costs ----
+    {
+        CUDA_TRY(e, cudaEventRecord(e->ev_applied, e->stream));
+        CUDA_TRY(e, cudaStreamWaitEvent(e->side_stream, e->ev_applied, 0));
+        const size_t smem = sizeof(double) * ((size_t)e->D * e->N + e->T + e->sumw);
+        e->launch_count++;
+        e->kernel_launches[STOMP_B200_KERNEL_APPLY]++;
+        noiseless_rollout_kernel<<<e->Q, 256, smem, e->side_stream>>>(lp, e->robot, e->sdf);
+        if (int rc = check_launch(e, "noiseless_rollout_kernel")) return rc;
+        CUDA_TRY(e, cudaEventRecord(e->ev_noiseless, e->side_stream));
+        e->noiseless_pending = true;
     }
 
     e->num_rollouts = n;
@@ -386,9 +404,19 @@ int ready_to_solve(stomp_b200_engine* e)
     return 0;
 }
 
+int join_side_stream(stomp_b200_engine* e)
+{
+    if (e->noiseless_pending) {
+        CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_noiseless, 0));
+        e->noiseless_pending = false;
+    }
+    return 0;
+}
+
 int fetch_query_scalars(stomp_b200_engine* e)
 {
     const LoopParams& b = e->base;
+    if (int rc = join_side_stream(e)) return rc;
     CUDA_TRY(e, cudaMemcpyAsync(e->h_cost, b.nl_total, sizeof(double) * e->Q, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(e->h_valid, b.nl_valid, e->Q, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaMemcpyAsync(e->h_stop, b.stop, sizeof(int32_t) * e->Q, cudaMemcpyDeviceToHost, e->stream));
@@ -503,6 +531,9 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
 
     CREATE_CUDA(cudaSetDevice(cfg->device));
     CREATE_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_applied, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_noiseless, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreate(&e->timer_a));
     CREATE_CUDA(cudaEventCreate(&e->timer_b));
 
@@ -556,9 +587,13 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.stop, Q));
     CREATE_TRY(dev_alloc(e, &b.iters_used, Q));
     CREATE_TRY(dev_alloc(e, &e->d_order, Q * S));
-    e->chunk = 32;
-    e->max_chunks = (int)((S + e->chunk - 1) / e->chunk);
-    CREATE_TRY(dev_alloc(e, &e->d_partial, Q * e->max_chunks * D * (T + 1)));
+    b.chunk = 64;
+    e->max_chunks = (int)((S + b.chunk - 1) / b.chunk);
+    CREATE_TRY(dev_alloc(e, &b.partial, Q * e->max_chunks * D * (T + 1)));
+    const size_t wblocks_cap = (GS + 255) / 256;
+    CREATE_TRY(dev_alloc(e, &b.wpart, Q * D * wblocks_cap * 2));
+    CREATE_TRY(dev_alloc(e, &b.wticket, Q * D));
+    b.world_size = world;
 
     // control-cost operator: banded differentiation matrices of the active rules (StompUtils.cpp:6-23)
     {
@@ -587,7 +622,7 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_CUDA(cudaMallocHost(&e->h_stop, sizeof(int32_t) * Q));
     CREATE_CUDA(cudaMallocHost(&e->h_iters, sizeof(int32_t) * Q));
     CREATE_CUDA(cudaFuncSetAttribute(rollout_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CREATE_CUDA(cudaFuncSetAttribute(apply_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CREATE_CUDA(cudaFuncSetAttribute(noiseless_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CREATE_CUDA(cudaFuncSetAttribute(reuse_rollouts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     std::memset(&e->robot, 0, sizeof(e->robot));
     std::memset(&e->sdf, 0, sizeof(e->sdf));
@@ -602,6 +637,7 @@ int stomp_b200_destroy(stomp_b200_engine* e)
 {
     if (!e) return STOMP_B200_OK;
     cudaSetDevice(e->cfg.device);
+    if (e->side_stream) cudaStreamSynchronize(e->side_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     resolve_profile(e);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
@@ -614,6 +650,9 @@ int stomp_b200_destroy(stomp_b200_engine* e)
     if (e->h_iters) cudaFreeHost(e->h_iters);
     if (e->timer_a) cudaEventDestroy(e->timer_a);
     if (e->timer_b) cudaEventDestroy(e->timer_b);
+    if (e->ev_applied) cudaEventDestroy(e->ev_applied);
+    if (e->ev_noiseless) cudaEventDestroy(e->ev_noiseless);
+    if (e->side_stream) cudaStreamDestroy(e->side_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return STOMP_B200_OK;
@@ -646,7 +685,12 @@ int stomp_b200_set_chain(stomp_b200_engine* e, int32_t num_joints, const double*
             return fail(e, STOMP_B200_ERR_UNSUPPORTED, "parent[d] must be d-1 or -1 (serial chains, restartable)");
         j.prismatic = prismatic ? prismatic[d] : 0;
         const double* a = axis + 3 * d;
-        for (int i = 0; i < 3; ++i) { j.o[i] = origin_xyz[3 * d + i]; j.axis[i] = a[i]; }
+        j.o_mask = 0;
+        for (int i = 0; i < 3; ++i) {
+            j.o[i] = origin_xyz[3 * d + i];
+            j.axis[i] = a[i];
+            if (j.o[i] != 0.0) j.o_mask |= 1 << i;
+        }
         const double* rpy = origin_rpy + 3 * d;
         j.fixed_rot_identity = (rpy[0] == 0.0 && rpy[1] == 0.0 && rpy[2] == 0.0) ? 1 : 0;
         rpy_matrix(rpy, j.A);
@@ -677,7 +721,11 @@ int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int3
     for (int s = 0; s < num_spheres; ++s) {
         if (link[s] < 0 || link[s] >= e->D) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "sphere link out of range");
         if (s > 0 && link[s] < link[s - 1]) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "spheres must be sorted by link");
-        for (int i = 0; i < 3; ++i) r.sphere[s].l[i] = centre_xyz[3 * s + i];
+        r.sphere[s].mask = 0;
+        for (int i = 0; i < 3; ++i) {
+            r.sphere[s].l[i] = centre_xyz[3 * s + i];
+            if (r.sphere[s].l[i] != 0.0) r.sphere[s].mask |= 1 << i;
+        }
         r.sphere[s].r = radius[s];
         r.sphere_begin[link[s] + 1] = s + 1;
     }
@@ -698,8 +746,9 @@ int stomp_b200_set_sdf(stomp_b200_engine* e, const int32_t dims[3], const double
     CUDA_TRY(e, cudaMemcpy(e->d_sdf, grid, count * sizeof(float), cudaMemcpyHostToDevice));
     e->sdf.grid = e->d_sdf;
     e->sdf.nx = dims[0]; e->sdf.ny = dims[1]; e->sdf.nz = dims[2];
-    e->sdf.ox = origin[0]; e->sdf.oy = origin[1]; e->sdf.oz = origin[2];
     e->sdf.inv_h = 1.0 / voxel_size;
+    e->sdf.offx = -(origin[0] * e->sdf.inv_h); e->sdf.offy = -(origin[1] * e->sdf.inv_h); e->sdf.offz = -(origin[2] * e->sdf.inv_h);
+    e->sdf.wide_index = count >= ((size_t)1 << 31) ? 1 : 0;
     e->have_sdf = true;
     return STOMP_B200_OK;
 }
@@ -719,6 +768,11 @@ int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R, 
             else if (R[(size_t)t * T + u] != 0.0)
                 return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "R has entries outside the 13-wide band of 7-tap rules");
         }
+    int hw = 0;
+    for (int t = 0; t < T; ++t)
+        for (int o = 1; o <= kRBand; ++o)
+            if (band[(size_t)t * (2 * kRBand + 1) + kRBand + o] != 0.0) hw = std::max(hw, o);
+    e->base.rband_halfwidth = hw;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.Lt), Lt.data(), sizeof(double) * Lt.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.Rband), band.data(), sizeof(double) * band.size(), cudaMemcpyHostToDevice));
@@ -774,6 +828,7 @@ int stomp_b200_begin_solve(stomp_b200_engine* e)
     e->noiseless_valid = false;
     e->adapted_valid = false;
     e->last_gen = 0; e->last_local = 0; e->last_noiseless_slot = -1;
+    if (int rc = join_side_stream(e)) return rc;
     reset_solve_state_kernel<<<(e->Q + 127) / 128, 128, 0, e->stream>>>(e->base);
     e->launch_count++;
     if (int rc = check_launch(e, "reset_solve_state_kernel")) return rc;
@@ -823,6 +878,7 @@ int stomp_b200_run(stomp_b200_engine* e, int32_t first_iteration, int32_t num_it
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     for (int i = 0; i < num_iterations; ++i)
         if (int rc = iterate_async(e, first_iteration + i, kNoisePhilox, honour_stop ? 1 : 0)) return rc;
+    if (int rc = join_side_stream(e)) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     resolve_profile(e);
     return STOMP_B200_OK;
@@ -861,9 +917,10 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
 {
     if (!e || !out) return STOMP_B200_ERR_INVALID_ARGUMENT;
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (int rc = join_side_stream(e)) return rc;
+    const LoopParams& b = e->base;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     resolve_profile(e);
-    const LoopParams& b = e->base;
     const size_t Q = e->Q, T = e->T, D = e->D, N = e->N;
     const size_t nl = e->last_local;      // local rollouts of the last iteration
     const size_t ng = e->num_rollouts;    // rollouts in the rollout-indexed tables
@@ -1021,6 +1078,7 @@ int stomp_b200_comm_init(stomp_b200_engine* e, const void* id)
 int stomp_b200_set_profiling(stomp_b200_engine* e, int32_t on)
 {
     if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    join_side_stream(e);
     cudaStreamSynchronize(e->stream);
     resolve_profile(e);
     e->profiling = on != 0;
@@ -1052,6 +1110,7 @@ int stomp_b200_timer_begin(stomp_b200_engine* e)
 {
     if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (int rc = join_side_stream(e)) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     CUDA_TRY(e, cudaEventRecord(e->timer_a, e->stream));
     return STOMP_B200_OK;
@@ -1060,6 +1119,7 @@ int stomp_b200_timer_begin(stomp_b200_engine* e)
 int stomp_b200_timer_end(stomp_b200_engine* e, double* elapsed_ms)
 {
     if (!e || !elapsed_ms) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (int rc = join_side_stream(e)) return rc;
     CUDA_TRY(e, cudaEventRecord(e->timer_b, e->stream));
     CUDA_TRY(e, cudaEventSynchronize(e->timer_b));
     float ms = 0.f;
@@ -1072,6 +1132,7 @@ int stomp_b200_synchronize(stomp_b200_engine* e)
 {
     if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (int rc = join_side_stream(e)) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     resolve_profile(e);
     return STOMP_B200_OK;

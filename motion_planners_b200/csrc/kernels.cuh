@@ -50,9 +50,16 @@ struct LoopParams {
     double* prob;             // [Q][gslots][D]
     double* fprob;            // [Q][gslots][D]
     double* fprob_sum;        // [Q][D]
+    double* wpart;            // [Q][D][wblocks][2] per-CTA sums of the unnormalised weights
+    uint32_t* wticket;        // [Q][D] arrival counters of rollout_weights_kernel
+    int32_t wblocks;          // CTAs per (query, joint) of rollout_weights_kernel
+    int32_t rband_halfwidth;  // largest o with R[t][t+o] != 0 (4 for the acceleration rule)
+    int32_t world_size;
     double* sigma;            // [Q][D]  adapted_stddevs_
     double* coef;             // [Q][D][3] p1, p2, new_stddev of the mean-shifted sampler (PolicyImprovement.cpp:262-269)
-    double* updbuf;           // [Q][D][T+1]  update row + numerator of the noise adaptation
+    double* updbuf;           // [Q][D][T+1]  update row + numerator of the noise adaptation (after the all-reduce)
+    double* partial;          // [Q][chunks][D][T+1] per-chunk partial sums of weighted_update_kernel
+    int32_t nchunks, chunk;
     double* updates;          // [Q][D][T]    last applied update (read-back)
     double* unit_noise;       // [Q][G][D][T] staging (injected) / debug
     double* epsilon;          // [Q][G][D][T] staging (injected) / debug
@@ -303,9 +310,11 @@ __device__ __forceinline__ bool state_collides(const RobotParams& robot, const S
     Frame f;
     frame_identity(f);
     bool hit = false;
-    for (int d = 0; d < robot.num_joints; ++d) {
+    const int nj = robot.num_joints;
+    for (int d = 0; d < nj; ++d) {
         apply_joint(f, robot.joint[d], joint_value(d));
-        for (int s = robot.sphere_begin[d]; s < robot.sphere_begin[d + 1]; ++s) {
+        const int s1 = robot.sphere_begin[d + 1];
+        for (int s = robot.sphere_begin[d]; s < s1; ++s) {
             double cx, cy, cz;
             sphere_centre(f, robot.sphere[s], cx, cy, cz);
             const double dist = (double)__ldg(sdf.grid + sdf_index(sdf, cx, cy, cz));
@@ -315,10 +324,24 @@ __device__ __forceinline__ bool state_collides(const RobotParams& robot, const S
     return hit;
 }
 
-// control cost of padded row i of one (rollout, joint): CovariantMovementPrimitive::computeControlCosts
-// (stomp/src/CovariantMovementPrimitive.cpp:363-377): costs_all[i] = sum_rules dt*w*(Ax*Ax),
-// Ax = (D_rule x)[i] * sqrt(w_rule).  x = padded trajectory (shared memory), band in column order.
-__device__ __forceinline__ double control_cost_row(const LoopParams& p, const double* x, int i)
+// ---- control costs: CovariantMovementPrimitive::computeControlCosts (stomp/src/CovariantMovementPrimitive.cpp:
+// 363-377): costs_all[i] = sum_rules dt*w*(Ax*Ax), Ax = (D_rule x)[i] * sqrt(w_rule), band in column order.
+// Interior rows (3 <= i < N-3) of a differentiation matrix all carry the same 7 coefficients; with one
+// active rule (the shipped task: acceleration only) they live in registers and exact-zero taps are skipped
+// (s + 0*x == s).  Boundary rows and multi-rule configurations read the band table.
+struct StencilRegs { double c[7]; double sqrt_w; bool single; };
+
+__device__ __forceinline__ StencilRegs load_stencil(const LoopParams& p)
+{
+    StencilRegs st;
+    st.single = (p.num_rules == 1) && (p.N >= 8);
+    st.sqrt_w = p.rule_sqrt_w[0];
+#pragma unroll
+    for (int o = 0; o < 7; ++o) st.c[o] = st.single ? __ldg(p.diff_band + ((size_t)p.rule_id[0] * p.N + 3) * 7 + o) : 0.0;
+    return st;
+}
+
+__device__ __forceinline__ double control_cost_row_table(const LoopParams& p, const double* x, int i)
 {
     const double dtw = p.dt * p.control_cost_weight;
     double c = 0.0;
@@ -333,16 +356,30 @@ __device__ __forceinline__ double control_cost_row(const LoopParams& p, const do
     return c;
 }
 
+__device__ __forceinline__ double control_cost_row(const LoopParams& p, const StencilRegs& st, const double* x, int i)
+{
+    if (st.single && i >= 3 && i < p.N - 3) {
+        double s = 0.0;
+#pragma unroll
+        for (int o = 0; o < 7; ++o)
+            if (st.c[o] != 0.0) s += st.c[o] * x[i - 3 + o];
+        const double Ax = s * st.sqrt_w;
+        return (p.dt * p.control_cost_weight) * (Ax * Ax);
+    }
+    return control_cost_row_table(p, x, i);
+}
+
 // One (rollout, joint) task for one warp: per-timestep control costs folded as the reference does
 // (padding rows into the first / last free step), their sum C_d and cum_d = sum_t (state + control).
 // x: padded trajectory of this (rollout, joint) in shared memory; state: state costs [T] in shared memory.
-__device__ __forceinline__ void control_cost_task(const LoopParams& p, const double* x, const double* state, int lane,
-                                                  double* control_out /*[T] global or null*/, double& C_d, double& cum_d)
+__device__ __forceinline__ void control_cost_task(const LoopParams& p, const StencilRegs& st, const double* x,
+                                                  const double* state, int lane, double* control_out /*[T] global or null*/,
+                                                  double& C_d, double& cum_d)
 {
     const int T = p.T, N = p.N;
     double free_sum = 0.0, cum_sum = 0.0, pad_sum = 0.0;
     for (int i = lane; i < N; i += 32) {
-        const double c = control_cost_row(p, x, i);
+        const double c = control_cost_row(p, st, x, i);
         if (i >= kPad && i < kPad + T) {
             free_sum += c;
             cum_sum += state[i - kPad] + c;
@@ -360,74 +397,46 @@ __device__ __forceinline__ void control_cost_task(const LoopParams& p, const dou
         __syncwarp();
         if (lane == 0) {   // fold the padding rows exactly in the reference's order (:373-377)
             double first = control_out[0], last = control_out[T - 1];
-            if (T == 1) {
-                for (int i = 0; i < kPad; ++i) { first += control_cost_row(p, x, i); first += control_cost_row(p, x, N - (i + 1)); }
-                control_out[0] = first;
-            } else {
-                for (int i = 0; i < kPad; ++i) { first += control_cost_row(p, x, i); last += control_cost_row(p, x, N - (i + 1)); }
-                control_out[0] = first;
-                control_out[T - 1] = last;
-            }
+            for (int i = 0; i < kPad; ++i) { first += control_cost_row(p, st, x, i); last += control_cost_row(p, st, x, N - (i + 1)); }
+            control_out[0] = first;
+            control_out[T - 1] = last;
         }
     }
 }
 
 // K4 + K5 + K6: Stomp::doExecuteRollouts (stomp/src/Stomp.cpp:206-229) -> Task::execute, then
 // PolicyImprovement::computeRolloutControlCosts / computeRolloutCumulativeCosts (PolicyImprovement.cpp:442-495)
-// for the generated rollouts.  One CTA = R rollouts of one query; thread (r, t) evaluates one state.
-// The extra CTA blockIdx.x == gridDim.x - 1 appends the noise-less rollout record (PolicyImprovement.cpp:304-308).
-__global__ void __launch_bounds__(512)
+// for the generated rollouts.  One CTA = blockDim.y rollouts of one query; thread (x = t, y = r) evaluates one
+// state; cooperative phases walk (rollout, joint) rows warp by warp (no per-element index division).
+__global__ void __launch_bounds__(512, 2)
 rollout_cost_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
-                    const __grid_constant__ SdfParams sdf, int R)
+                    const __grid_constant__ SdfParams sdf)
 {
     extern __shared__ double smem[];
     const int q = blockIdx.y;
     if (query_frozen(p, q)) return;
-    const int T = p.T, D = p.D, N = p.N;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-
-    if (blockIdx.x == gridDim.x - 1) {
-        // ---- append the noise-less rollout as slot noiseless_slot ----
-        if (p.noiseless_slot < 0) return;
-        const int k = p.noiseless_slot;
-        for (int e = tid; e < D * T; e += blockDim.x) {
-            const int d = e / T, t = e - d * T;
-            const double th = p.theta_all[((size_t)q * D + d) * N + kPad + t];
-            const size_t o = (((size_t)q * p.slots + k) * D) * T + e;
-            p.rollouts[o] = th;
-            p.noise[o] = 0.0;
-            if (p.proj) p.proj[o] = th;
-            if (p.control_costs) p.control_costs[o] = p.nl_control[(size_t)q * D * T + e];
-        }
-        for (int t = tid; t < T; t += blockDim.x) {
-            p.state_costs[((size_t)q * p.slots + k) * T + t] = p.nl_state[(size_t)q * T + t];
-            p.verdicts[((size_t)q * p.slots + k) * T + t] = p.nl_verdict[(size_t)q * T + t];
-        }
-        for (int e = tid; e < p.sumw; e += blockDim.x)
-            p.sums[((size_t)q * p.gslots + p.noiseless_gslot) * p.sumw + e] = p.nl_sums[(size_t)q * p.sumw + e];
-        return;
-    }
-
+    const int T = p.T, D = p.D, N = p.N, R = blockDim.y;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = (blockDim.x * blockDim.y + 31) >> 5;
     double* sx = smem;                           // [R][D][N] padded trajectories
     double* sstate = smem + (size_t)R * D * N;   // [R][T]
     const int k0 = blockIdx.x * R;
     const int nr = min(R, p.num_gen - k0);
+    const int nrows = nr * D;
 
     // ---- load: padding from the policy, free block <- noisy parameters (OptimizationTask.cpp:155-163) ----
-    for (int e = tid; e < nr * D * N; e += blockDim.x) {
-        const int i = e % N;
-        const int rd = e / N;
-        const int d = rd % D, r = rd / D;
-        double v;
-        if (i >= kPad && i < kPad + T) v = p.rollouts[(((size_t)q * p.slots + (k0 + r)) * D + d) * T + (i - kPad)];
-        else v = p.theta_all[((size_t)q * D + d) * N + i];
-        sx[e] = v;
+    for (int rd = warp; rd < nrows; rd += nwarps) {
+        const int r = rd / D, d = rd - r * D;
+        const double* free_src = p.rollouts + (((size_t)q * p.slots + (k0 + r)) * D + d) * T - kPad;
+        const double* pad_src = p.theta_all + ((size_t)q * D + d) * N;
+        double* dst = sx + (size_t)rd * N;
+        for (int i = lane; i < N; i += 32) dst[i] = (i >= kPad && i < kPad + T) ? free_src[i] : pad_src[i];
     }
     __syncthreads();
 
     // ---- K4: one state per thread ----
-    if (tid < nr * T) {
-        const int r = tid / T, t = tid - r * T;
+    if ((int)threadIdx.y < nr && (int)threadIdx.x < T) {
+        const int r = threadIdx.y, t = threadIdx.x;
         const double* xq = sx + (size_t)r * D * N + kPad + t;
         const bool hit = state_collides(robot, sdf, [&](int d) { return xq[(size_t)d * N]; });
         const double cost = hit ? 1.0 : 0.0;
@@ -439,39 +448,55 @@ rollout_cost_kernel(const __grid_constant__ LoopParams p, const __grid_constant_
     }
     __syncthreads();
 
-    // ---- the control cost is evaluated on parameters_ + noise_projected_, not on the noisy parameters
-    // (PolicyImprovement.cpp:812-817): x = theta + (noisy - theta) ----
-    for (int e = tid; e < nr * D * T; e += blockDim.x) {
-        const int t = e % T;
-        const int rd = e / T;
-        const int d = rd % D;
-        const double th = p.theta_all[((size_t)q * D + d) * N + kPad + t];
-        double* xp = sx + (size_t)rd * N + kPad + t;
-        *xp = th + (*xp - th);
-    }
-    __syncthreads();
-
-    // ---- K5 + K6: warp tasks.  tasks [0, nr*D): control cost of (r, d); [nr*D, nr*D + nr): state cost sum ----
-    for (int task = warp; task < nr * D + nr; task += nwarps) {
-        if (task < nr * D) {
-            const int r = task / D, d = task - r * D;
-            const int k = k0 + r;
-            double C_d, cum_d;
-            double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
-            control_cost_task(p, sx + (size_t)task * N, sstate + r * T, lane, cc_out, C_d, cum_d);
-            if (lane == 0) {
-                double* s = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
-                s[1 + d] = C_d;
-                s[1 + D + d] = cum_d;
-            }
-        } else {
-            const int r = task - nr * D;
-            double s = 0.0;
-            for (int t = lane; t < T; t += 32) s += sstate[r * T + t];
-            s = warp_sum(s);
-            if (lane == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k0 + r)) * p.sumw] = s;
+    // ---- K5 + K6: warp tasks over (r, d).  The control cost is evaluated on parameters_ + noise_projected_,
+    // not on the noisy parameters (PolicyImprovement.cpp:812-817): x = theta + (noisy - theta), converted in
+    // place row by row by the warp that owns the row ----
+    const StencilRegs st = load_stencil(p);
+    for (int rd = warp; rd < nrows; rd += nwarps) {
+        const int r = rd / D, d = rd - r * D, k = k0 + r;
+        double* x = sx + (size_t)rd * N;
+        const double* th = p.theta_all + ((size_t)q * D + d) * N;
+        for (int i = kPad + lane; i < kPad + T; i += 32) { const double tv = th[i]; x[i] = tv + (x[i] - tv); }
+        __syncwarp();
+        double C_d, cum_d;
+        double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
+        control_cost_task(p, st, x, sstate + r * T, lane, cc_out, C_d, cum_d);
+        if (lane == 0) {
+            double* s = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
+            s[1 + d] = C_d;
+            s[1 + D + d] = cum_d;
         }
     }
+    for (int r = warp; r < nr; r += nwarps) {
+        double s = 0.0;
+        for (int t = lane; t < T; t += 32) s += sstate[r * T + t];
+        s = warp_sum(s);
+        if (lane == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k0 + r)) * p.sumw] = s;
+    }
+}
+
+// the noise-less rollout record written out as the regular rollout slot the reference appends
+// (PolicyImprovement.cpp:304-308): parameters = the current policy parameters, zero noise, the recorded costs.
+// Called by one CTA of rollout_weights_kernel (before the update changes the parameters); the loop itself
+// reads the record, the slot serves rollout reuse and read-backs.
+__device__ __forceinline__ void materialise_noiseless(const LoopParams& p, int q, int tid, int nthreads)
+{
+    const int T = p.T, D = p.D, N = p.N, k = p.noiseless_slot;
+    for (int e = tid; e < D * T; e += nthreads) {
+        const int d = e / T, t = e - d * T;
+        const double th = p.theta_all[((size_t)q * D + d) * N + kPad + t];
+        const size_t o = (((size_t)q * p.slots + k) * D) * T + e;
+        p.rollouts[o] = th;
+        p.noise[o] = 0.0;
+        if (p.proj) p.proj[o] = th;
+        if (p.control_costs) p.control_costs[o] = p.nl_control[(size_t)q * D * T + e];
+    }
+    for (int t = tid; t < T; t += nthreads) {
+        p.state_costs[((size_t)q * p.slots + k) * T + t] = p.nl_state[(size_t)q * T + t];
+        p.verdicts[((size_t)q * p.slots + k) * T + t] = p.nl_verdict[(size_t)q * T + t];
+    }
+    for (int e = tid; e < p.sumw; e += nthreads)
+        p.sums[((size_t)q * p.gslots + p.noiseless_gslot) * p.sumw + e] = p.nl_sums[(size_t)q * p.sumw + e];
 }
 
 // stand-alone verdicts for arbitrary trajectories theta [K][D][Tq] (stomp_b200_evaluate_states)
@@ -523,7 +548,8 @@ reused_control_cost_kernel(const __grid_constant__ LoopParams p, int first, int 
     const int T = p.T, D = p.D, N = p.N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     double* x = smem + (size_t)warp * (N + T);
-    double* st = x + N;
+    double* stc = x + N;
+    const StencilRegs st = load_stencil(p);
     for (int task = blockIdx.x * nwarps + warp; task < count * D; task += gridDim.x * nwarps) {
         const int r = task / D, d = task - r * D, k = first + r;
         for (int i = lane; i < N; i += 32) {
@@ -532,13 +558,13 @@ reused_control_cost_kernel(const __grid_constant__ LoopParams p, int first, int 
             if (i >= kPad && i < kPad + T) v = th + p.noise[(((size_t)q * p.slots + k) * D + d) * T + (i - kPad)];
             x[i] = v;
         }
-        for (int t = lane; t < T; t += 32) st[t] = p.state_costs[((size_t)q * p.slots + k) * T + t];
+        for (int t = lane; t < T; t += 32) stc[t] = p.state_costs[((size_t)q * p.slots + k) * T + t];
         __syncwarp();
         double C_d, cum_d;
         double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
-        control_cost_task(p, x, st, lane, cc_out, C_d, cum_d);
+        control_cost_task(p, st, x, stc, lane, cc_out, C_d, cum_d);
         double s = 0.0;
-        for (int t = lane; t < T; t += 32) s += st[t];
+        for (int t = lane; t < T; t += 32) s += stc[t];
         s = warp_sum(s);
         if (lane == 0) {
             double* o = p.sums + ((size_t)q * p.gslots + k) * p.sumw;
@@ -607,87 +633,113 @@ reuse_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constan
 // =====================================================================================================
 // K7: PolicyImprovement::computeRolloutProbabilities (PolicyImprovement.cpp:497-582), cumulative-cost mode:
 // cumulative_costs_[d] is constant over t (:480), so one probability per (rollout, joint).
-// grid (D, Q); also total_cost_ (:451-462) by the d == 0 CTA.
+// grid (wblocks, D, Q): every CTA finds the global min / max of its joint (redundantly, K' values), weighs its
+// own 256 rollouts, leaves a partial sum; the last CTA to arrive sums the partials in block order and
+// normalises (deterministic).  The noise-less rollout is read from its record, not from a slot.
 // =====================================================================================================
+__device__ __forceinline__ const double* cost_row(const LoopParams& p, int q, int k)
+{
+    return (k == p.noiseless_gslot) ? p.nl_sums + (size_t)q * p.sumw : p.sums + ((size_t)q * p.gslots + k) * p.sumw;
+}
+
 __global__ void __launch_bounds__(256)
 rollout_weights_kernel(const __grid_constant__ LoopParams p)
 {
     __shared__ double scratch[32];
-    const int d = blockIdx.x, q = blockIdx.y;
+    __shared__ unsigned s_ticket;
+    const int d = blockIdx.y, q = blockIdx.z;
     if (query_frozen(p, q)) return;
     const int D = p.D, n = p.num_rollouts, tid = threadIdx.x;
-    const double* sums = p.sums + (size_t)q * p.gslots * p.sumw;
     double* prob = p.prob + (size_t)q * p.gslots * D;
     double* fprob = p.fprob + (size_t)q * p.gslots * D;
     const double h = p.cost_scaling_h;
+    if (blockIdx.x == 0 && d == 0 && p.noiseless_slot >= 0) materialise_noiseless(p, q, tid, blockDim.x);
 
     double mn = 1e300, mx = -1e300, fmn = 1e300, fmx = -1e300;
     for (int k = tid; k < n; k += blockDim.x) {
-        const double* s = sums + (size_t)k * p.sumw;
+        const double* s = cost_row(p, q, k);
         const double cum = 1.0 * s[1 + D + d];
         const double full = s[0] + s[1 + d];
         mn = fmin(mn, cum); mx = fmax(mx, cum);
         fmn = fmin(fmn, full); fmx = fmax(fmx, full);
-        if (d == 0) {
-            double cost = s[0];
-            for (int dd = 0; dd < D; ++dd) cost += s[1 + dd];
-            p.total_cost[(size_t)q * p.gslots + k] = cost;
-        }
     }
     mn = block_reduce<1>(mn, scratch); mx = block_reduce<2>(mx, scratch);
     fmn = block_reduce<1>(fmn, scratch); fmx = block_reduce<2>(fmx, scratch);
     double den = mx - mn, fden = fmx - fmn;
     if (den < 1e-8) den = 1e-8;
     if (fden < 1e-8) fden = 1e-8;
-    double psum = 0.0, fsum = 0.0;
-    for (int k = tid; k < n; k += blockDim.x) {
-        const double* s = sums + (size_t)k * p.sumw;
-        const double pr = 1.0 * exp(((-h) * (1.0 * s[1 + D + d] - mn)) / den);      // importance_weight_ = 1
-        const double fp = 1.0 * exp(((-h) * ((s[0] + s[1 + d]) - fmn)) / fden);
+
+    double pr = 0.0, fp = 0.0;
+    const int k = blockIdx.x * blockDim.x + tid;
+    if (k < n) {
+        const double* s = cost_row(p, q, k);
+        pr = 1.0 * exp(((-h) * (1.0 * s[1 + D + d] - mn)) / den);      // importance_weight_ = 1
+        fp = 1.0 * exp(((-h) * ((s[0] + s[1 + d]) - fmn)) / fden);
         prob[(size_t)k * D + d] = pr;
         fprob[(size_t)k * D + d] = fp;
-        psum += pr; fsum += fp;
+        if (d == 0) {   // total_cost_ (:451-462)
+            double cost = s[0];
+            for (int dd = 0; dd < D; ++dd) cost += s[1 + dd];
+            p.total_cost[(size_t)q * p.gslots + k] = cost;
+        }
     }
-    psum = block_reduce<0>(psum, scratch);
-    fsum = block_reduce<0>(fsum, scratch);
+    const double psum_blk = block_reduce<0>(pr, scratch);
+    const double fsum_blk = block_reduce<0>(fp, scratch);
+    double* part = p.wpart + (((size_t)q * D + d) * p.wblocks) * 2;
+    if (tid == 0) {
+        part[2 * blockIdx.x] = psum_blk;
+        part[2 * blockIdx.x + 1] = fsum_blk;
+        __threadfence();
+        s_ticket = atomicAdd(p.wticket + (size_t)q * D + d, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    // ---- last CTA of this (query, joint): normalise ----
+    __threadfence();
+    double psum = 0.0, fsum = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) { psum += __ldcg(part + 2 * b); fsum += __ldcg(part + 2 * b + 1); }
     double fnorm = 0.0;
-    for (int k = tid; k < n; k += blockDim.x) {
-        prob[(size_t)k * D + d] /= psum;
-        const double f = fprob[(size_t)k * D + d] / fsum;
-        fprob[(size_t)k * D + d] = f;
+    for (int kk = tid; kk < n; kk += blockDim.x) {
+        prob[(size_t)kk * D + d] = __ldcg(prob + (size_t)kk * D + d) / psum;
+        const double f = __ldcg(fprob + (size_t)kk * D + d) / fsum;
+        fprob[(size_t)kk * D + d] = f;
         fnorm += f;
     }
     fnorm = block_reduce<0>(fnorm, scratch);
-    if (tid == 0) p.fprob_sum[(size_t)q * D + d] = fnorm;
+    if (tid == 0) {
+        p.fprob_sum[(size_t)q * D + d] = fnorm;
+        p.wticket[(size_t)q * D + d] = 0;
+    }
 }
 
 // =====================================================================================================
 // K8: PolicyImprovement::computeParameterUpdates (PolicyImprovement.cpp:584-711): probability-weighted
 // noise sums and the noise-adaptation numerator sum_k Pfull * (n^T R n).  grid (chunks, D, Q); one warp
 // per rollout of the chunk, lanes stride over t; partial [Q][chunks][D][T+1] (last entry: numerator).
+// n^T R n uses the symmetry of the band: sum_t n_t (R_tt n_t + 2 sum_{o>0} R_{t,t+o} n_{t+o}).
 // =====================================================================================================
 constexpr int kUpdateWarps = 8;
 constexpr int kMaxTPerLane = STOMP_B200_MAX_TIME_STEPS / 32;
 __global__ void __launch_bounds__(kUpdateWarps * 32)
-weighted_update_kernel(const __grid_constant__ LoopParams p, double* __restrict__ partial, int chunk, int nchunks)
+weighted_update_kernel(const __grid_constant__ LoopParams p)
 {
     extern __shared__ double smem[];
     const int d = blockIdx.y, q = blockIdx.z, c = blockIdx.x;
     if (query_frozen(p, q)) return;
-    const int T = p.T, D = p.D;
+    const int T = p.T, D = p.D, hw = p.rband_halfwidth;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sn = smem + (size_t)warp * (T + 2 * kRBand);        // noise row with zero halo
-    double* spart = smem + (size_t)kUpdateWarps * (T + 2 * kRBand);   // [warps][T+1]
+    double* sn = smem + (size_t)warp * (T + kRBand);                  // noise row, zero tail
+    double* spart = smem + (size_t)kUpdateWarps * (T + kRBand);      // [warps][T+1]
     double acc[kMaxTPerLane];
 #pragma unroll
     for (int i = 0; i < kMaxTPerLane; ++i) acc[i] = 0.0;
     double numer = 0.0;
-    for (int i = lane; i < T + 2 * kRBand; i += 32) sn[i] = 0.0;
+    for (int i = lane; i < T + kRBand; i += 32) sn[i] = 0.0;
     __syncwarp();
-    const int k_end = min(p.num_local, (c + 1) * chunk);
-    for (int k = c * chunk + warp; k < k_end; k += kUpdateWarps) {
-        // local slot -> slot in the rollout-indexed tables
-        const int g = (k == p.noiseless_slot) ? p.noiseless_gslot : (k < p.num_gen ? p.gen_offset + k : k);
+    const int k_end = min(p.num_local, (c + 1) * p.chunk);
+    for (int k = c * p.chunk + warp; k < k_end; k += kUpdateWarps) {
+        if (k == p.noiseless_slot) continue;   // zero noise: contributes nothing (PolicyImprovement.cpp:407-410)
+        const int g = (k < p.num_gen) ? p.gen_offset + k : k;   // local slot -> slot in the rollout-indexed tables
         const double pr = p.prob[((size_t)q * p.gslots + g) * D + d];
         const double* nz = p.noise + (((size_t)q * p.slots + k) * D + d) * T;
 #pragma unroll
@@ -695,7 +747,7 @@ weighted_update_kernel(const __grid_constant__ LoopParams p, double* __restrict_
             const int t = lane + 32 * i;
             if (t < T) {
                 const double v = nz[t];
-                sn[kRBand + t] = v;
+                sn[t] = v;
                 acc[i] += v * pr;
             }
         }
@@ -706,11 +758,10 @@ weighted_update_kernel(const __grid_constant__ LoopParams p, double* __restrict_
             for (int i = 0; i < kMaxTPerLane; ++i) {
                 const int t = lane + 32 * i;
                 if (t < T) {
-                    const double* rb = p.Rband + (size_t)t * (2 * kRBand + 1);
+                    const double* rb = p.Rband + (size_t)t * (2 * kRBand + 1) + kRBand;
                     double s = 0.0;
-#pragma unroll
-                    for (int o = 0; o < 2 * kRBand + 1; ++o) s += __ldg(rb + o) * sn[t + o];
-                    quad += sn[kRBand + t] * s;
+                    for (int o = 1; o <= hw; ++o) s += __ldg(rb + o) * sn[t + o];
+                    quad += sn[t] * (__ldg(rb) * sn[t] + 2.0 * s);
                 }
             }
             quad = warp_sum(quad);
@@ -725,7 +776,7 @@ weighted_update_kernel(const __grid_constant__ LoopParams p, double* __restrict_
     }
     if (lane == 0) spart[(size_t)warp * (T + 1) + T] = numer;
     __syncthreads();
-    double* out = partial + (((size_t)q * nchunks + c) * D + d) * (T + 1);
+    double* out = p.partial + (((size_t)q * p.nchunks + c) * D + d) * (T + 1);
     for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
         double s = spart[t];
         for (int w = 1; w < kUpdateWarps; ++w) s += spart[(size_t)w * (T + 1) + t];
@@ -733,29 +784,67 @@ weighted_update_kernel(const __grid_constant__ LoopParams p, double* __restrict_
     }
 }
 
-// sum of the chunk partials in chunk order -> updbuf [Q][D][T+1]   (grid (D, Q))
+// sum of the chunk partials in chunk order -> updbuf [Q][D][T+1]; only needed in front of the all-reduce
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(const __grid_constant__ LoopParams p, const double* __restrict__ partial, int nchunks)
+reduce_partials_kernel(const __grid_constant__ LoopParams p, int nchunks)
 {
     const int d = blockIdx.x, q = blockIdx.y;
     if (query_frozen(p, q)) return;
     const int T = p.T, D = p.D;
     for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
         double s = 0.0;
-        for (int c = 0; c < nchunks; ++c) s += partial[(((size_t)q * nchunks + c) * D + d) * (T + 1) + t];
+        for (int c = 0; c < nchunks; ++c) s += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 1) + t];
         p.updbuf[((size_t)q * D + d) * (T + 1) + t] = s;
     }
 }
 
 // =====================================================================================================
-// K8 tail + K9 + K10: noise adaptation (PolicyImprovement.cpp:656-679), CovariantMovementPrimitive::
-// updateParameters (stomp/src/CovariantMovementPrimitive.cpp:476-479), Stomp::doNoiselessRollout
-// (stomp/src/Stomp.cpp:253-272) + setNoiselessRolloutCosts (PolicyImprovement.cpp:401-419) and the wrapper's
-// stop rule (src/wrappers/stomp/StompPlanner.cpp:107-118).  One CTA per query.
+// K8 tail + K9: noise adaptation (PolicyImprovement.cpp:656-679) and CovariantMovementPrimitive::
+// updateParameters (stomp/src/CovariantMovementPrimitive.cpp:476-479).  One CTA per query.  from_partials:
+// sum the chunk partials here (single GPU); otherwise read the all-reduced updbuf.
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-apply_update_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
-                    const __grid_constant__ SdfParams sdf)
+apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int nchunks)
+{
+    const int q = blockIdx.x;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D, N = p.N, tid = threadIdx.x;
+    for (int e = tid; e < D * (T + 1); e += blockDim.x) {
+        const int d = e / (T + 1), t = e - d * (T + 1);
+        double u;
+        if (from_partials) {
+            u = 0.0;
+            for (int c = 0; c < nchunks; ++c) u += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 1) + t];
+        } else {
+            u = p.updbuf[((size_t)q * D + d) * (T + 1) + t];
+        }
+        if (t < T) {
+            // time-step weights and divisor are exactly 1 (PolicyImprovement.cpp:533,684-704)
+            u *= 1.0;
+            u /= 1.0;
+            p.updates[((size_t)q * D + d) * T + t] = u;
+            p.theta_all[((size_t)q * D + d) * N + kPad + t] += 1.0 * u;
+        } else if (p.use_noise_adaptation) {
+            const double denom = p.fprob_sum[(size_t)q * D + d];
+            const double frob_stddev = sqrt(u / (denom * T));
+            const double update_rate = 0.2;
+            double sd = (1.0 - update_rate) * p.sigma[(size_t)q * D + d] + update_rate * frob_stddev;
+            if (sd < p.min_stddev[d]) sd = p.min_stddev[d];
+            p.sigma[(size_t)q * D + d] = sd;
+            store_sampler_coefficients(p, q, d, sd);
+        }
+    }
+}
+
+// =====================================================================================================
+// K10: Stomp::doNoiselessRollout (stomp/src/Stomp.cpp:253-272) + setNoiselessRolloutCosts
+// (PolicyImprovement.cpp:401-419) and the wrapper's stop rule (src/wrappers/stomp/StompPlanner.cpp:107-118).
+// One CTA per query; runs on the engine's side stream, overlapped with the next iteration's sampling and
+// rollout costs (its result is first needed by the next rollout_weights_kernel).
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
+                         const __grid_constant__ SdfParams sdf)
 {
     extern __shared__ double smem[];
     const int q = blockIdx.x;
@@ -765,35 +854,8 @@ apply_update_kernel(const __grid_constant__ LoopParams p, const __grid_constant_
     double* sx = smem;                      // [D][N]
     double* sstate = smem + (size_t)D * N;  // [T]
     double* ssum = sstate + T;              // [1 + 2D]
-
-    // noise adaptation
-    if (p.use_noise_adaptation && tid < D) {
-        const int d = tid;
-        const double numer = p.updbuf[((size_t)q * D + d) * (T + 1) + T];
-        const double denom = p.fprob_sum[(size_t)q * D + d];
-        const double frob_stddev = sqrt(numer / (denom * T));
-        const double update_rate = 0.2;
-        double sd = (1.0 - update_rate) * p.sigma[(size_t)q * D + d] + update_rate * frob_stddev;
-        if (sd < p.min_stddev[d]) sd = p.min_stddev[d];
-        p.sigma[(size_t)q * D + d] = sd;
-        store_sampler_coefficients(p, q, d, sd);
-    }
-    // parameters += update (time-step weights and divisor are exactly 1: PolicyImprovement.cpp:533,684-704)
-    for (int e = tid; e < D * N; e += blockDim.x) {
-        const int d = e / N, i = e - d * N;
-        double v = p.theta_all[((size_t)q * D + d) * N + i];
-        if (i >= kPad && i < kPad + T) {
-            double u = p.updbuf[((size_t)q * D + d) * (T + 1) + (i - kPad)];
-            u *= 1.0;
-            u /= 1.0;
-            p.updates[((size_t)q * D + d) * T + (i - kPad)] = u;
-            v += 1.0 * u;
-            p.theta_all[((size_t)q * D + d) * N + i] = v;
-        }
-        sx[e] = v;
-    }
+    for (int e = tid; e < D * N; e += blockDim.x) sx[e] = p.theta_all[(size_t)q * D * N + e];
     __syncthreads();
-    // noise-less rollout: state costs
     for (int t = tid; t < T; t += blockDim.x) {
         const double* xq = sx + kPad + t;
         const bool hit = state_collides(robot, sdf, [&](int d) { return xq[(size_t)d * N]; });
@@ -804,10 +866,11 @@ apply_update_kernel(const __grid_constant__ LoopParams p, const __grid_constant_
     }
     __syncthreads();
     // control costs (noise = 0: parameters + 0.0 is exact) and sums
+    const StencilRegs st = load_stencil(p);
     for (int task = warp; task < D + 1; task += nwarps) {
         if (task < D) {
             double C_d, cum_d;
-            control_cost_task(p, sx + (size_t)task * N, sstate, lane, p.nl_control + ((size_t)q * D + task) * T, C_d, cum_d);
+            control_cost_task(p, st, sx + (size_t)task * N, sstate, lane, p.nl_control + ((size_t)q * D + task) * T, C_d, cum_d);
             if (lane == 0) { ssum[1 + task] = C_d; ssum[1 + D + task] = cum_d; }
         } else {
             double s = 0.0;
@@ -829,16 +892,6 @@ apply_update_kernel(const __grid_constant__ LoopParams p, const __grid_constant_
         p.iters_used[q] += 1;
         if ((cost < 1) && (fabs(improvement) < p.min_cost_improvement)) p.stop[q] = 1;
     }
-}
-
-// sigma <- noise_stddev * decay^(it-1) while the adapted value is not valid (PolicyImprovement.cpp:162-163)
-__global__ void set_sigma_kernel(const __grid_constant__ LoopParams p, const double* __restrict__ sigma_it)
-{
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= p.Q * p.D) return;
-    if (query_frozen(p, e / p.D)) return;
-    p.sigma[e] = sigma_it[e % p.D];
-    store_sampler_coefficients(p, e / p.D, e % p.D, sigma_it[e % p.D]);
 }
 
 }  // namespace stomp_b200

@@ -27,11 +27,15 @@ struct JointParams {
     int32_t axis_kind;
     int32_t fixed_rot_identity;
     int32_t prismatic;
+    int32_t o_mask;   // bit i set <=> o[i] != 0 (a zero component contributes fma(r, 0, p) == p: skipped)
+    int32_t pad_;
 };
 
 struct SphereParams {
     double l[3];      // centre in the link frame
     double r;
+    int32_t mask;     // bit i set <=> l[i] != 0
+    int32_t pad_;
 };
 
 // passed by value as a __grid_constant__ kernel parameter: lives in the constant bank, every access is
@@ -49,7 +53,8 @@ struct RobotParams {
 struct SdfParams {
     const float* grid;
     int32_t nx, ny, nz;
-    double ox, oy, oz;
+    int32_t wide_index;        // 1 when nx*ny*nz does not fit 31 bits
+    double offx, offy, offz;   // -(origin * inv_h)
     double inv_h;
 };
 
@@ -115,10 +120,11 @@ __device__ __forceinline__ void frame_identity(Frame& f)
 __device__ __forceinline__ void apply_joint(Frame& f, const JointParams& j, double q)
 {
     if (j.parent < 0) frame_identity(f);
-    // p += R * o
-    f.px = fma(f.r02, j.o[2], fma(f.r01, j.o[1], fma(f.r00, j.o[0], f.px)));
-    f.py = fma(f.r12, j.o[2], fma(f.r11, j.o[1], fma(f.r10, j.o[0], f.py)));
-    f.pz = fma(f.r22, j.o[2], fma(f.r21, j.o[1], fma(f.r20, j.o[0], f.pz)));
+    // p += R * o, component by component in the order x, y, z; exact-zero components are skipped
+    // (fma(r, 0, p) == p for finite r, so the result is the one the unskipped sequence gives)
+    if (j.o_mask & 1) { f.px = fma(f.r00, j.o[0], f.px); f.py = fma(f.r10, j.o[0], f.py); f.pz = fma(f.r20, j.o[0], f.pz); }
+    if (j.o_mask & 2) { f.px = fma(f.r01, j.o[1], f.px); f.py = fma(f.r11, j.o[1], f.py); f.pz = fma(f.r21, j.o[1], f.pz); }
+    if (j.o_mask & 4) { f.px = fma(f.r02, j.o[2], f.px); f.py = fma(f.r12, j.o[2], f.py); f.pz = fma(f.r22, j.o[2], f.pz); }
     if (!j.fixed_rot_identity) {   // R = R * A
         const double n00 = fma(f.r02, j.A[6], fma(f.r01, j.A[3], f.r00 * j.A[0]));
         const double n01 = fma(f.r02, j.A[7], fma(f.r01, j.A[4], f.r00 * j.A[1]));
@@ -183,22 +189,22 @@ __device__ __forceinline__ void apply_joint(Frame& f, const JointParams& j, doub
 
 __device__ __forceinline__ void sphere_centre(const Frame& f, const SphereParams& sp, double& cx, double& cy, double& cz)
 {
-    cx = fma(f.r02, sp.l[2], fma(f.r01, sp.l[1], fma(f.r00, sp.l[0], f.px)));
-    cy = fma(f.r12, sp.l[2], fma(f.r11, sp.l[1], fma(f.r10, sp.l[0], f.py)));
-    cz = fma(f.r22, sp.l[2], fma(f.r21, sp.l[1], fma(f.r20, sp.l[0], f.pz)));
+    cx = f.px; cy = f.py; cz = f.pz;
+    if (sp.mask & 1) { cx = fma(f.r00, sp.l[0], cx); cy = fma(f.r10, sp.l[0], cy); cz = fma(f.r20, sp.l[0], cz); }
+    if (sp.mask & 2) { cx = fma(f.r01, sp.l[1], cx); cy = fma(f.r11, sp.l[1], cy); cz = fma(f.r21, sp.l[1], cz); }
+    if (sp.mask & 4) { cx = fma(f.r02, sp.l[2], cx); cy = fma(f.r12, sp.l[2], cy); cz = fma(f.r22, sp.l[2], cz); }
 }
 
-// nearest-voxel lookup, coordinates clamped to the grid
+// nearest-voxel lookup: voxel coordinate f = c * (1/h) - origin/h (one fma), truncated and clamped to the
+// grid.  cvt.rzi.s32.f64 saturates and maps NaN to 0, so clamping the integer equals clamping the double
+// to [0, n-1] first (what the CPU statement of the same rule does).
 __device__ __forceinline__ size_t sdf_index(const SdfParams& g, double cx, double cy, double cz)
 {
-    double fx = (cx - g.ox) * g.inv_h;
-    double fy = (cy - g.oy) * g.inv_h;
-    double fz = (cz - g.oz) * g.inv_h;
-    fx = fmin(fmax(fx, 0.0), (double)(g.nx - 1));
-    fy = fmin(fmax(fy, 0.0), (double)(g.ny - 1));
-    fz = fmin(fmax(fz, 0.0), (double)(g.nz - 1));
-    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
-    return ((size_t)iz * (size_t)g.ny + (size_t)iy) * (size_t)g.nx + (size_t)ix;
+    const int ix = min(max(__double2int_rz(fma(cx, g.inv_h, g.offx)), 0), g.nx - 1);
+    const int iy = min(max(__double2int_rz(fma(cy, g.inv_h, g.offy)), 0), g.ny - 1);
+    const int iz = min(max(__double2int_rz(fma(cz, g.inv_h, g.offz)), 0), g.nz - 1);
+    if (g.wide_index) return ((size_t)iz * (size_t)g.ny + (size_t)iy) * (size_t)g.nx + (size_t)ix;
+    return (size_t)(unsigned)((iz * g.ny + iy) * g.nx + ix);
 }
 
 }  // namespace stomp_b200

@@ -103,6 +103,7 @@ struct SdfSpec {
     int32_t nx, ny, nz;  // x fastest
     double ox, oy, oz;   // world position of the min corner of voxel (0,0,0)
     double inv_h;        // 1 / voxel size
+    double offx, offy, offz;   // -(origin * inv_h): voxel coordinate = fma(c, inv_h, off)
     const float* grid;
 };
 
@@ -217,9 +218,9 @@ static inline void sphere_centre(const Frame& f, const SphereSpec& sp, double c[
 // nearest-voxel SDF lookup; coordinates clamped to the grid
 static inline size_t sdf_index(const SdfSpec& g, const double c[3])
 {
-    double fx = (c[0] - g.ox) * g.inv_h;
-    double fy = (c[1] - g.oy) * g.inv_h;
-    double fz = (c[2] - g.oz) * g.inv_h;
+    double fx = spec_fma(c[0], g.inv_h, g.offx);
+    double fy = spec_fma(c[1], g.inv_h, g.offy);
+    double fz = spec_fma(c[2], g.inv_h, g.offz);
     fx = std::fmin(std::fmax(fx, 0.0), (double)(g.nx - 1));
     fy = std::fmin(std::fmax(fy, 0.0), (double)(g.ny - 1));
     fz = std::fmin(std::fmax(fz, 0.0), (double)(g.nz - 1));

@@ -137,6 +137,7 @@ int oracle_set_sdf(void* hp, const int32_t* dims, const double* origin, double v
     g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
     g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
     g.inv_h = 1.0 / voxel;
+    g.offx = -(g.ox * g.inv_h); g.offy = -(g.oy * g.inv_h); g.offz = -(g.oz * g.inv_h);
     g.grid = grid;
     return 0;
 }
