@@ -217,6 +217,13 @@ enum stomp_b200_kernel {
 int stomp_b200_set_profiling(stomp_b200_engine* e, int32_t on);
 int stomp_b200_kernel_stats(stomp_b200_engine* e, int32_t kernel, double* total_ms, int64_t* launches);
 int stomp_b200_reset_kernel_stats(stomp_b200_engine* e);
+/* In-pipeline timeline: while on, every kernel stamps %globaltimer at its first CTA start and last CTA end;
+ * get_timeline returns, oldest first, [iteration][8 kernels][begin, end] in microseconds relative to the first
+ * stamp (-1 where a kernel did not run) for the last <= 64 iterations; kernels: 0 sample, 1 cost, 2 weights,
+ * 3 update, 4 apply, 5 noise-less rollout, 6 reuse, 7 unused.  set_timeline(on) clears the ring. */
+#define STOMP_B200_TIMELINE_KERNELS 8
+int stomp_b200_set_timeline(stomp_b200_engine* e, int32_t on);
+int stomp_b200_get_timeline(stomp_b200_engine* e, int32_t max_iterations, double* begin_end_us, int32_t* num_iterations);
 /* total kernel launches issued by this engine since creation */
 int64_t stomp_b200_launch_count(const stomp_b200_engine* e);
 /* device-side timing of a region on the engine's stream: begin / end record events, end returns ms */

@@ -35,7 +35,7 @@ SYMBOLS = [
     "stomp_b200_next_num_generated", "stomp_b200_run", "stomp_b200_finish_solve", "stomp_b200_num_rollouts",
     "stomp_b200_get_tensor", "stomp_b200_evaluate_states", "stomp_b200_sphere_centres", "stomp_b200_comm_unique_id",
     "stomp_b200_comm_init", "stomp_b200_set_profiling", "stomp_b200_kernel_stats", "stomp_b200_reset_kernel_stats",
-    "stomp_b200_launch_count", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
+    "stomp_b200_set_timeline", "stomp_b200_get_timeline", "stomp_b200_launch_count", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
 ]
 
 
@@ -102,6 +102,8 @@ def lib():
         L.stomp_b200_set_profiling.argtypes = [vp, C.c_int32]
         L.stomp_b200_kernel_stats.argtypes = [vp, C.c_int32, dp, C.POINTER(C.c_int64)]
         L.stomp_b200_reset_kernel_stats.argtypes = [vp]
+        L.stomp_b200_set_timeline.argtypes = [vp, C.c_int32]
+        L.stomp_b200_get_timeline.argtypes = [vp, C.c_int32, dp, ip]
         L.stomp_b200_launch_count.argtypes = [vp]
         L.stomp_b200_launch_count.restype = C.c_int64
         L.stomp_b200_timer_begin.argtypes = [vp]
@@ -361,6 +363,16 @@ class Engine:
 
     def reset_kernel_stats(self):
         self._check(lib().stomp_b200_reset_kernel_stats(self.h), "stomp_b200_reset_kernel_stats")
+
+    def set_timeline(self, on):
+        self._check(lib().stomp_b200_set_timeline(self.h, int(on)), "stomp_b200_set_timeline")
+
+    def timeline(self, max_iterations=64):
+        """[iterations][8 kernels][begin, end] in microseconds (oldest first; -1 where a kernel did not run)."""
+        out = np.empty((max_iterations, 8, 2))
+        n = C.c_int32(0)
+        self._check(lib().stomp_b200_get_timeline(self.h, max_iterations, _dp(out), C.byref(n)), "stomp_b200_get_timeline")
+        return out[:n.value]
 
     def launch_count(self):
         return lib().stomp_b200_launch_count(self.h)

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <limits>
@@ -107,6 +108,8 @@ struct stomp_b200_engine {
     int cur = 0;
     int32_t* d_order = nullptr;
     int max_chunks = 1;
+    int num_sms = 148;
+    bool use_dmma = true;                    // STOMP_B200_SAMPLER=simt selects the FMA-pipe contraction
     cudaStream_t side_stream = nullptr;      // noise-less rollout, overlapped with the next iteration's sampling + costs
     cudaEvent_t ev_applied = nullptr, ev_noiseless = nullptr;
     bool noiseless_pending = false;          // ev_noiseless recorded and not yet waited for by the main stream
@@ -130,8 +133,14 @@ struct stomp_b200_engine {
     int64_t launch_count = 0;
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
 
+    // in-pipeline timeline: ring of the last kTimelineRing iterations
+    unsigned long long* d_timeline = nullptr;
+    bool timeline_on = false;
+    long long timeline_count = 0;
+
     ncclComm_t comm = nullptr;
 };
+constexpr int kTimelineRing = 64;
 
 namespace {
 
@@ -212,9 +221,31 @@ int check_launch(stomp_b200_engine* e, const char* what)
     return 0;
 }
 
+size_t dmma_smem_bytes(int T)
+{
+    const int T4 = (T + 3) & ~3;
+    return sizeof(double) * ((size_t)T4 * kSlabT + (size_t)kDmmaWarps * 8 * kEStride);
+}
+
+// FP64 tensor-core contraction (DMMA); used whenever the Lt slab fits in shared memory
+template <bool kPhilox>
+int launch_sample_dmma(stomp_b200_engine* e, const LoopParams& lp)
+{
+    const long long total_cols = (long long)lp.Q * lp.num_gen * lp.D;
+    const int ntiles = (int)((total_cols + 7) / 8);
+    const int nslabs = (lp.T + kSlabT - 1) / kSlabT;
+    const size_t smem = dmma_smem_bytes(lp.T);
+    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    dim3 grid(std::max(1, std::min((ntiles + kDmmaWarps - 1) / kDmmaWarps, e->num_sms * per_sm)), nslabs);
+    Scope s(e, STOMP_B200_KERNEL_SAMPLE);
+    sample_rollouts_dmma_kernel<kPhilox><<<grid, kDmmaWarps * 32, smem, e->stream>>>(lp, e->robot, lp.tile_counter);
+    return check_launch(e, "sample_rollouts_dmma_kernel");
+}
+
 template <bool kPhilox>
 int launch_sample(stomp_b200_engine* e, const LoopParams& lp)
 {
+    if (e->use_dmma && dmma_smem_bytes(lp.T) <= 220 * 1024) return launch_sample_dmma<kPhilox>(e, lp);
     const int ncols = lp.num_gen * lp.D;
     dim3 grid((ncols + 63) / 64, lp.Q);
     const int need = (lp.T + 15) / 16;
@@ -270,6 +301,10 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     lp.honour_stop = honour_stop;
     lp.iteration = iteration;
     lp.store_unit = c.keep_debug_tensors;
+    if (e->timeline_on) {
+        lp.timeline = e->d_timeline + (size_t)(e->timeline_count % kTimelineRing) * kTimelineKernels * 2;
+        e->timeline_count++;
+    }
 
     // ---- noise magnitude (Stomp.cpp:179, PolicyImprovement.cpp:162-163) ----
     if (!e->adapted_valid) {
@@ -315,9 +350,10 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         const int R = rollouts_per_cta(e, gen_local);
         const size_t smem = sizeof(double) * ((size_t)R * e->D * e->N + (size_t)R * e->T);
         dim3 grid((gen_local + R - 1) / R, e->Q);
-        dim3 block(e->T, R);
+        const int threads = ((R * e->T + 31) / 32) * 32;
         Scope sc(e, STOMP_B200_KERNEL_COST);
-        rollout_cost_kernel<<<grid, block, smem, e->stream>>>(lp, e->robot, e->sdf);
+        if (e->robot.simple_chain) rollout_cost_kernel<true><<<grid, threads, smem, e->stream>>>(lp, e->robot, e->sdf, R);
+        else rollout_cost_kernel<false><<<grid, threads, smem, e->stream>>>(lp, e->robot, e->sdf, R);
         if (int rc = check_launch(e, "rollout_cost_kernel")) return rc;
     }
     // ---- the noise-less rollout of the previous iteration is needed from here on ----
@@ -343,18 +379,17 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
 
     // ---- probabilities (K7) ----
     {
-        lp.wblocks = (n + 255) / 256;
         Scope sc(e, STOMP_B200_KERNEL_WEIGHTS);
-        rollout_weights_kernel<<<dim3(lp.wblocks, e->D, e->Q), 256, 0, e->stream>>>(lp);
+        rollout_weights_kernel<<<dim3(e->D, e->Q), 1024, 0, e->stream>>>(lp);
         if (int rc = check_launch(e, "rollout_weights_kernel")) return rc;
     }
     // ---- weighted sums (K8) ----
     const int nchunks = std::max(1, (lp.num_local + lp.chunk - 1) / lp.chunk);
     lp.nchunks = nchunks;
     {
-        const size_t smem = sizeof(double) * ((size_t)kUpdateWarps * (e->T + kRBand) + (size_t)kUpdateWarps * (e->T + 1));
+        const size_t smem = sizeof(double) * 2 * (size_t)lp.chunk;
         Scope sc(e, STOMP_B200_KERNEL_UPDATE);
-        weighted_update_kernel<<<dim3(nchunks, e->D, e->Q), kUpdateWarps * 32, smem, e->stream>>>(lp);
+        weighted_update_kernel<<<dim3(nchunks, e->D, e->Q), kUpdateThreads, smem, e->stream>>>(lp);
         if (int rc = check_launch(e, "weighted_update_kernel")) return rc;
     }
     // ---- exchange 2: update rows + adaptation numerators ----
@@ -370,7 +405,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     // ---- apply (K9) ----
     {
         Scope sc(e, STOMP_B200_KERNEL_APPLY);
-        apply_update_kernel<<<e->Q, 256, 0, e->stream>>>(lp, world > 1 ? 0 : 1, nchunks);
+        apply_update_kernel<<<dim3(e->D, e->Q), 128, 0, e->stream>>>(lp, world > 1 ? 0 : 1, nchunks);
         if (int rc = check_launch(e, "apply_update_kernel")) return rc;
     }
     // ---- noise-less rollout (K10) on the side stream: overlaps the next iteration's sampling and costs ----
@@ -495,7 +530,7 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     stomp_b200_engine* e = new stomp_b200_engine();
     e->cfg = *cfg;
     e->T = cfg->num_time_steps; e->D = cfg->num_dimensions; e->N = e->T + 2 * kPad;
-    e->sumw = 1 + 2 * e->D;
+    e->sumw = 1 + 3 * e->D;
     if (cfg->shard_mode == 1 && cfg->world_size > 1) {
         const int per = (cfg->num_queries + cfg->world_size - 1) / cfg->world_size;
         e->query_offset = std::min(cfg->num_queries, cfg->rank * per);
@@ -549,6 +584,7 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     b.use_noise_adaptation = cfg->use_noise_adaptation;
     b.seed = cfg->seed;
     b.noiseless_slot = -1;
+    if (const char* dbg = std::getenv("STOMP_B200_DEBUG_SKIP")) b.debug_skip = std::atoi(dbg);
 
     double* tmp = nullptr;
     CREATE_TRY(dev_alloc(e, &b.theta_all, Q * D * N));
@@ -587,12 +623,11 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.stop, Q));
     CREATE_TRY(dev_alloc(e, &b.iters_used, Q));
     CREATE_TRY(dev_alloc(e, &e->d_order, Q * S));
-    b.chunk = 64;
+    b.chunk = 128;
     e->max_chunks = (int)((S + b.chunk - 1) / b.chunk);
     CREATE_TRY(dev_alloc(e, &b.partial, Q * e->max_chunks * D * (T + 1)));
-    const size_t wblocks_cap = (GS + 255) / 256;
-    CREATE_TRY(dev_alloc(e, &b.wpart, Q * D * wblocks_cap * 2));
-    CREATE_TRY(dev_alloc(e, &b.wticket, Q * D));
+    CREATE_TRY(dev_alloc(e, &b.tile_counter, 4));
+    CREATE_TRY(dev_alloc(e, &e->d_timeline, (size_t)kTimelineRing * kTimelineKernels * 2));
     b.world_size = world;
 
     // control-cost operator: banded differentiation matrices of the active rules (StompUtils.cpp:6-23)
@@ -608,6 +643,12 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
                 b.num_rules++;
             }
         }
+        b.st_n = 0;
+        if (b.num_rules == 1 && e->N >= 8) {
+            const double* row = band.data() + ((size_t)b.rule_id[0] * N + 3) * 7;   // any interior row
+            for (int o = 0; o < 7; ++o)
+                if (row[o] != 0.0) { b.st_off[b.st_n] = o - 3; b.st_coef[b.st_n] = row[o]; b.st_n++; }
+        }
         CREATE_TRY(dev_alloc(e, &tmp, band.size())); b.diff_band = tmp;
         CREATE_CUDA(cudaMemcpyAsync(tmp, band.data(), sizeof(double) * band.size(), cudaMemcpyHostToDevice, e->stream));
         CREATE_TRY(dev_alloc(e, &tmp, D)); b.min_stddev = tmp;
@@ -621,7 +662,17 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_CUDA(cudaMallocHost(&e->h_valid, Q));
     CREATE_CUDA(cudaMallocHost(&e->h_stop, sizeof(int32_t) * Q));
     CREATE_CUDA(cudaMallocHost(&e->h_iters, sizeof(int32_t) * Q));
-    CREATE_CUDA(cudaFuncSetAttribute(rollout_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    {
+        cudaDeviceProp prop;
+        CREATE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+        e->num_sms = prop.multiProcessorCount;
+        const char* sampler = std::getenv("STOMP_B200_SAMPLER");
+        e->use_dmma = !(sampler && std::string(sampler) == "simt");
+    }
+    CREATE_CUDA(cudaFuncSetAttribute(sample_rollouts_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    CREATE_CUDA(cudaFuncSetAttribute(sample_rollouts_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    CREATE_CUDA(cudaFuncSetAttribute(rollout_cost_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CREATE_CUDA(cudaFuncSetAttribute(rollout_cost_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CREATE_CUDA(cudaFuncSetAttribute(noiseless_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CREATE_CUDA(cudaFuncSetAttribute(reuse_rollouts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     std::memset(&e->robot, 0, sizeof(e->robot));
@@ -706,6 +757,9 @@ int stomp_b200_set_chain(stomp_b200_engine* e, int32_t num_joints, const double*
         r.lower[d] = lower[d];
         r.upper[d] = upper[d];
     }
+    r.simple_chain = 1;
+    for (int d = 0; d < num_joints; ++d)
+        if (r.joint[d].prismatic || !r.joint[d].fixed_rot_identity || r.joint[d].axis_kind == kAxisGeneral) r.simple_chain = 0;
     e->have_chain = true;
     return STOMP_B200_OK;
 }
@@ -773,6 +827,12 @@ int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R, 
         for (int o = 1; o <= kRBand; ++o)
             if (band[(size_t)t * (2 * kRBand + 1) + kRBand + o] != 0.0) hw = std::max(hw, o);
     e->base.rband_halfwidth = hw;
+    // R built from the 7-tap rules is Toeplitz inside its band: keep the diagonals as kernel parameters
+    e->base.r_toeplitz = 1;
+    for (int o = 0; o <= kRBand; ++o) e->base.r_diag[o] = band[kRBand + o];
+    for (int t = 0; t < T && e->base.r_toeplitz; ++t)
+        for (int o = 0; o <= kRBand && t + o < T; ++o)
+            if (band[(size_t)t * (2 * kRBand + 1) + kRBand + o] != e->base.r_diag[o]) { e->base.r_toeplitz = 0; break; }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.Lt), Lt.data(), sizeof(double) * Lt.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.Rband), band.data(), sizeof(double) * band.size(), cudaMemcpyHostToDevice));
@@ -1082,6 +1142,47 @@ int stomp_b200_set_profiling(stomp_b200_engine* e, int32_t on)
     cudaStreamSynchronize(e->stream);
     resolve_profile(e);
     e->profiling = on != 0;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_set_timeline(stomp_b200_engine* e, int32_t on)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (int rc = join_side_stream(e)) return rc;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    // begin stamps start at the largest value (atomicMin), end stamps at zero (atomicMax)
+    std::vector<unsigned long long> init((size_t)kTimelineRing * kTimelineKernels * 2);
+    for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
+    CUDA_TRY(e, cudaMemcpy(e->d_timeline, init.data(), sizeof(unsigned long long) * init.size(), cudaMemcpyHostToDevice));
+    e->timeline_on = on != 0;
+    e->timeline_count = 0;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_get_timeline(stomp_b200_engine* e, int32_t max_iterations, double* begin_end_us, int32_t* num_iterations)
+{
+    if (!e || !begin_end_us || !num_iterations) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (int rc = join_side_stream(e)) return rc;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    const int n = (int)std::min<long long>(std::min<long long>(e->timeline_count, kTimelineRing), max_iterations);
+    std::vector<unsigned long long> raw((size_t)kTimelineRing * kTimelineKernels * 2);
+    CUDA_TRY(e, cudaMemcpy(raw.data(), e->d_timeline, sizeof(unsigned long long) * raw.size(), cudaMemcpyDeviceToHost));
+    // oldest first; microseconds relative to the first stamp returned
+    unsigned long long t0 = ~0ull;
+    const long long first = e->timeline_count - n;
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < kTimelineKernels; ++k)
+            t0 = std::min(t0, raw[((size_t)((first + i) % kTimelineRing) * kTimelineKernels + k) * 2]);
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < kTimelineKernels; ++k) {
+            const unsigned long long* r = raw.data() + ((size_t)((first + i) % kTimelineRing) * kTimelineKernels + k) * 2;
+            const bool ran = r[0] != ~0ull && r[1] != 0ull;
+            begin_end_us[((size_t)i * kTimelineKernels + k) * 2] = ran ? (double)(r[0] - t0) * 1e-3 : -1.0;
+            begin_end_us[((size_t)i * kTimelineKernels + k) * 2 + 1] = ran ? (double)(r[1] - t0) * 1e-3 : -1.0;
+        }
+    *num_iterations = n;
     return STOMP_B200_OK;
 }
 

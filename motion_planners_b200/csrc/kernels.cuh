@@ -19,7 +19,7 @@ struct LoopParams {
     int32_t T, D, N, Q;
     int32_t slots;            // rollout slots per query in the local tensors (max_rollouts + 1)
     int32_t gslots;           // slots per query in the rollout-indexed scalar tables (global over ranks)
-    int32_t sumw;             // 1 + 2*D doubles per rollout: S, C_d[D], cum_d[D]
+    int32_t sumw;             // 1 + 3*D doubles per rollout: S, C_d[D], cum_d[D], quad_d[D] (n^T R n)
     int32_t num_gen;          // G: rollouts generated this iteration (local)
     int32_t num_rollouts;     // K': rollouts used in the update (global over ranks)
     int32_t num_local;        // local rollout slots in use (generated + reused + noise-less)
@@ -50,10 +50,12 @@ struct LoopParams {
     double* prob;             // [Q][gslots][D]
     double* fprob;            // [Q][gslots][D]
     double* fprob_sum;        // [Q][D]
-    double* wpart;            // [Q][D][wblocks][2] per-CTA sums of the unnormalised weights
-    uint32_t* wticket;        // [Q][D] arrival counters of rollout_weights_kernel
-    int32_t wblocks;          // CTAs per (query, joint) of rollout_weights_kernel
+    uint32_t* tile_counter;   // [4] work counters of sample_rollouts_dmma_kernel, one per slab of time steps
+    int32_t debug_skip;       // measurement only (STOMP_B200_DEBUG_SKIP): bit 0 skip the FK phase, bit 1 skip the control phase of the cost kernel
+    unsigned long long* timeline;   // [kTimelineKernels][2] first-CTA-start / last-CTA-end %globaltimer stamps of this iteration, or null
     int32_t rband_halfwidth;  // largest o with R[t][t+o] != 0 (4 for the acceleration rule)
+    int32_t r_toeplitz;       // R[t][t+o] does not depend on t (true for R built from the 7-tap rules)
+    double r_diag[kRBand + 1]; // r_o = R[t][t+o] when r_toeplitz
     int32_t world_size;
     double* sigma;            // [Q][D]  adapted_stddevs_
     double* coef;             // [Q][D][3] p1, p2, new_stddev of the mean-shifted sampler (PolicyImprovement.cpp:262-269)
@@ -83,9 +85,38 @@ struct LoopParams {
     int32_t num_rules;
     int32_t rule_id[kMaxRules];
     double rule_sqrt_w[kMaxRules];
+    // interior rows of the single active rule as a tap list (non-zero coefficients only), see load_stencil
+    int32_t st_n;
+    int32_t st_off[7];
+    double st_coef[7];
 };
 
 __device__ __forceinline__ bool query_frozen(const LoopParams& p, int q) { return p.honour_stop && p.stop[q] != 0; }
+
+// In-pipeline timeline (stomp_b200_set_timeline): every CTA stamps %globaltimer when it starts and when it ends;
+// min / max over the CTAs give the true start and end of each kernel inside the running loop, gaps included —
+// which neither ncu (cold caches, serialised) nor event brackets (launch latency) can.
+constexpr int kTimelineKernels = 8;   // 0 sample, 1 cost, 2 weights, 3 update, 4 apply, 5 noiseless, 6 reuse, 7 sigma
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+struct TimelineScope {
+    unsigned long long* slot;
+    __device__ __forceinline__ TimelineScope(const LoopParams& p, int kernel) : slot(p.timeline ? p.timeline + 2 * kernel : nullptr)
+    {
+        if (slot && threadIdx.x == 0 && threadIdx.y == 0) atomicMin(slot, global_timer_ns());
+    }
+    __device__ __forceinline__ void end()
+    {
+        if (slot) {
+            __syncthreads();
+            if (threadIdx.x == 0 && threadIdx.y == 0) atomicMax(slot + 1, global_timer_ns());
+        }
+    }
+};
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -202,6 +233,7 @@ sample_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_consta
     __shared__ double Bs[BK][BN];
     const int q = blockIdx.y;
     if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 0);
     const int T = p.T, D = p.D;
     const int ncols = p.num_gen * D;
     const int c0 = blockIdx.x * BM;
@@ -283,6 +315,132 @@ sample_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_consta
             shift_clamp_store(p, robot, q, k, d, t, acc[i][j]);
         }
     }
+    tls.end();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same contraction on the FP64 tensor path (mma.sync.m8n8k4.f64 -> DMMA).  Measured on B200
+// (tools/fp64_peak.cu, profiles/r1_fp64_peak_b200.json): DMMA 37.0 TFLOP/s vs 35.0 TFLOP/s on the FMA pipe —
+// the same peak, but one DMMA carries the work of eight DFMA warp-instructions, and ncu showed the SIMT
+// kernel above issue/latency bound (FP64 pipe 30 % busy), i.e. the case BASELINE.json's north_star reserves
+// tensor cores for.  Per warp: one m8 tile = 8 columns (k, d) x all time steps of a 104-wide slab of t;
+// A = eps [8 cols][4 u] generated in place (Philox) or read (injected), B = Lt slab resident in shared
+// memory, C = 13 n8 tiles in registers.  Lt is upper triangular: k-step u0 only touches n8 tiles with
+// 8*nt + 7 >= u0.  Tiles are handed out by an atomic counter (reset by rollout_cost_kernel) over the
+// flattened (query, rollout, joint) column space, so the slab is loaded once per resident CTA.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kDmmaWarps = 8;
+constexpr int kSlabTiles = 13;
+constexpr int kSlabT = kSlabTiles * 8;     // 104 == 8 (mod 16): B-fragment loads are 2 wavefronts, the minimum
+constexpr int kEStride = 17;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <bool kPhilox>
+__global__ void __launch_bounds__(kDmmaWarps * 32)
+sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
+                            unsigned* __restrict__ tile_counter)
+{
+    extern __shared__ double smem[];
+    const int T = p.T, D = p.D;
+    const int T4 = (T + 3) & ~3;
+    const int slab = blockIdx.y;
+    const int t_base = slab * kSlabT;
+    const int nt_cnt = min(kSlabTiles, (T - t_base + 7) >> 3);
+    const int u_end = min(T4, (min(T, t_base + kSlabT) + 3) & ~3);   // rows of Lt below the slab's last t are zero
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    TimelineScope tls(p, 0);
+    double* sLt = smem;                                              // [T4][kSlabT]
+    double* sE = smem + (size_t)T4 * kSlabT + (size_t)warp * (8 * kEStride);
+
+    for (int e = tid; e < T4 * kSlabT; e += blockDim.x) {
+        const int u = e / kSlabT, j = e - u * kSlabT, t = t_base + j;
+        sLt[e] = (u < T && t < T && t >= u) ? p.Lt[(size_t)u * T + t] : 0.0;
+    }
+    __syncthreads();
+
+    const int ncols = p.num_gen * D;                  // columns per query
+    const long long total_cols = (long long)p.Q * ncols;
+    const int ntiles = (int)((total_cols + 7) >> 3);
+    const int r = lane >> 2, kq = lane & 3;
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(tile_counter + slab, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+        const long long cg = (long long)tile * 8 + r;  // this lane's column (row of the m8 tile)
+        const bool in_range = cg < total_cols;
+        const int q = in_range ? (int)(cg / ncols) : 0;
+        const int c = in_range ? (int)(cg - (long long)q * ncols) : 0;
+        const int k = c / D, d = c - k * D;
+        const bool live = in_range && !query_frozen(p, q);
+
+        double acc[kSlabTiles][2];
+#pragma unroll
+        for (int nt = 0; nt < kSlabTiles; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
+
+        for (int u0 = 0; u0 < u_end; u0 += 16) {
+            // ---- eps chunk [8 columns][16 u]: this lane makes 4 consecutive u of its column ----
+            double z[4] = {0.0, 0.0, 0.0, 0.0};
+            const int ub = u0 + 4 * kq;
+            if (live) {
+                double* eps_row = p.epsilon + (((size_t)q * p.num_gen + k) * D + d) * T;
+                if (kPhilox) {
+                    const uint32_t gcol = (uint32_t)((((size_t)(p.query_offset + q)) * p.gen_global + (p.gen_offset + k)) * D + d);
+                    philox_normals(p.seed, (uint32_t)p.iteration, gcol, (uint32_t)(ub >> 2), z);
+                    if (p.store_unit && slab == 0) {
+#pragma unroll
+                        for (int m = 0; m < 4; ++m)
+                            if (ub + m < T) eps_row[ub + m] = z[m];
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        if (ub + m < T) z[m] = eps_row[ub + m];
+                }
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (ub + m >= T) z[m] = 0.0;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < 4; ++m) sE[r * kEStride + 4 * kq + m] = z[m];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int uk = u0 + 4 * j;
+                if (uk < u_end) {
+                    const double a = sE[r * kEStride + 4 * j + kq];
+                    const int nt_min = uk > t_base ? (uk - t_base) >> 3 : 0;
+                    const double* brow = sLt + (size_t)(uk + kq) * kSlabT + r;
+#pragma unroll
+                    for (int nt = 0; nt < kSlabTiles; ++nt)
+                        if (nt >= nt_min && nt < nt_cnt) dmma_m8n8k4(acc[nt][0], acc[nt][1], a, brow[8 * nt]);
+                }
+            }
+        }
+        // ---- epilogue: C fragment element (row r, cols 2*kq, 2*kq + 1) of tile nt ----
+        if (live) {
+#pragma unroll
+            for (int nt = 0; nt < kSlabTiles; ++nt) {
+                if (nt < nt_cnt) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int t = t_base + 8 * nt + 2 * kq + h;
+                        if (t < T) {
+                            if (p.store_unit) p.unit_noise[(((size_t)q * p.num_gen + k) * D + d) * T + t] = acc[nt][h];
+                            shift_clamp_store(p, robot, q, k, d, t, acc[nt][h]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tls.end();
 }
 
 // injected unit noise (parity mode): epilogue only
@@ -291,6 +449,7 @@ shift_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constan
 {
     const int q = blockIdx.y;
     if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 0);
     const int per_query = p.num_gen * p.D * p.T;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per_query; e += gridDim.x * blockDim.x) {
         const int t = e % p.T;
@@ -298,13 +457,14 @@ shift_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constan
         const int d = kd % p.D, k = kd / p.D;
         shift_clamp_store(p, robot, q, k, d, t, p.unit_noise[(size_t)q * per_query + e]);
     }
+    tls.end();
 }
 
 // =====================================================================================================
 // K4: state verdict — FK of the chain, sphere centres, SDF lookups
 // (what robot_model does for OptimizationTask::computeCollisionCost, OptimizationTask.cpp:183-204)
 // =====================================================================================================
-template <class JointValue>
+template <bool kSimple, class JointValue>
 __device__ __forceinline__ bool state_collides(const RobotParams& robot, const SdfParams& sdf, JointValue joint_value)
 {
     Frame f;
@@ -312,7 +472,7 @@ __device__ __forceinline__ bool state_collides(const RobotParams& robot, const S
     bool hit = false;
     const int nj = robot.num_joints;
     for (int d = 0; d < nj; ++d) {
-        apply_joint(f, robot.joint[d], joint_value(d));
+        apply_joint<kSimple>(f, robot.joint[d], joint_value(d));
         const int s1 = robot.sphere_begin[d + 1];
         for (int s = robot.sphere_begin[d]; s < s1; ++s) {
             double cx, cy, cz;
@@ -325,22 +485,11 @@ __device__ __forceinline__ bool state_collides(const RobotParams& robot, const S
 }
 
 // ---- control costs: CovariantMovementPrimitive::computeControlCosts (stomp/src/CovariantMovementPrimitive.cpp:
-// 363-377): costs_all[i] = sum_rules dt*w*(Ax*Ax), Ax = (D_rule x)[i] * sqrt(w_rule), band in column order.
-// Interior rows (3 <= i < N-3) of a differentiation matrix all carry the same 7 coefficients; with one
-// active rule (the shipped task: acceleration only) they live in registers and exact-zero taps are skipped
-// (s + 0*x == s).  Boundary rows and multi-rule configurations read the band table.
-struct StencilRegs { double c[7]; double sqrt_w; bool single; };
-
-__device__ __forceinline__ StencilRegs load_stencil(const LoopParams& p)
-{
-    StencilRegs st;
-    st.single = (p.num_rules == 1) && (p.N >= 8);
-    st.sqrt_w = p.rule_sqrt_w[0];
-#pragma unroll
-    for (int o = 0; o < 7; ++o) st.c[o] = st.single ? __ldg(p.diff_band + ((size_t)p.rule_id[0] * p.N + 3) * 7 + o) : 0.0;
-    return st;
-}
-
+// 363-377): costs_all[i] = sum_rules dt*w*(Ax*Ax), Ax = (D_rule x)[i] * sqrt(w_rule).
+// Interior rows (3 <= i < N-3) of a differentiation matrix all carry the same coefficients; with one active
+// rule (the shipped task: acceleration only) the host passes them as a list of non-zero taps (a zero
+// coefficient contributes an exact zero).  Boundary rows and multi-rule
+// configurations read the band table in column order.
 __device__ __forceinline__ double control_cost_row_table(const LoopParams& p, const double* x, int i)
 {
     const double dtw = p.dt * p.control_cost_weight;
@@ -356,123 +505,193 @@ __device__ __forceinline__ double control_cost_row_table(const LoopParams& p, co
     return c;
 }
 
-__device__ __forceinline__ double control_cost_row(const LoopParams& p, const StencilRegs& st, const double* x, int i)
+__device__ __forceinline__ double control_cost_row(const LoopParams& p, const double* x, int i)
 {
-    if (st.single && i >= 3 && i < p.N - 3) {
+    if (p.st_n > 0 && i >= 3 && i < p.N - 3) {
         double s = 0.0;
-#pragma unroll
-        for (int o = 0; o < 7; ++o)
-            if (st.c[o] != 0.0) s += st.c[o] * x[i - 3 + o];
-        const double Ax = s * st.sqrt_w;
+        for (int j = 0; j < p.st_n; ++j) s += p.st_coef[j] * x[i + p.st_off[j]];   // mul then add, column order: the reference's arithmetic
+        const double Ax = s * p.rule_sqrt_w[0];
         return (p.dt * p.control_cost_weight) * (Ax * Ax);
     }
     return control_cost_row_table(p, x, i);
 }
 
-// One (rollout, joint) task for one warp: per-timestep control costs folded as the reference does
-// (padding rows into the first / last free step), their sum C_d and cum_d = sum_t (state + control).
+// Register-resident coefficients of one (rollout, joint) row pass: the 7 interior taps of the single active
+// rule (zeros included: c*x with c == 0 adds an exact zero, so the sum is the reference's) and the diagonals of R.
+struct RowCoefficients {
+    double c[7];
+    double r[kRBand + 1];
+    double sqrt_w, dtw;
+    bool fast;
+};
+
+__device__ __forceinline__ RowCoefficients load_row_coefficients(const LoopParams& p)
+{
+    RowCoefficients rc;
+    rc.fast = p.st_n > 0;
+#pragma unroll
+    for (int o = 0; o < 7; ++o) rc.c[o] = 0.0;
+    for (int j = 0; j < p.st_n; ++j) {
+        const int o = p.st_off[j] + 3;
+#pragma unroll
+        for (int u = 0; u < 7; ++u)
+            if (u == o) rc.c[u] = p.st_coef[j];
+    }
+#pragma unroll
+    for (int o = 0; o <= kRBand; ++o) rc.r[o] = p.r_diag[o];
+    rc.sqrt_w = p.rule_sqrt_w[0];
+    rc.dtw = p.dt * p.control_cost_weight;
+    return rc;
+}
+
+// One (rollout, joint) row for one warp: C_d = sum of the per-timestep control costs (padding rows folded into
+// the first / last free step, i.e. simply included in the sum) and cum_d = sum_t (state + control).
 // x: padded trajectory of this (rollout, joint) in shared memory; state: state costs [T] in shared memory.
-__device__ __forceinline__ void control_cost_task(const LoopParams& p, const StencilRegs& st, const double* x,
-                                                  const double* state, int lane, double* control_out /*[T] global or null*/,
-                                                  double& C_d, double& cum_d)
+__device__ __forceinline__ void control_cost_sums(const LoopParams& p, const RowCoefficients& rc, const double* x,
+                                                  const double* state, int lane, double& C_d, double& cum_d)
 {
     const int T = p.T, N = p.N;
-    double free_sum = 0.0, cum_sum = 0.0, pad_sum = 0.0;
+    double c_sum = 0.0, s_sum = 0.0;
     for (int i = lane; i < N; i += 32) {
-        const double c = control_cost_row(p, st, x, i);
-        if (i >= kPad && i < kPad + T) {
-            free_sum += c;
-            cum_sum += state[i - kPad] + c;
-            if (control_out) control_out[i - kPad] = c;
+        double c;
+        if (rc.fast && i >= 3 && i < N - 3) {
+            const double* xi = x + i - 3;
+            double s = 0.0;
+#pragma unroll
+            for (int o = 0; o < 7; ++o) s += rc.c[o] * xi[o];
+            const double Ax = s * rc.sqrt_w;
+            c = rc.dtw * (Ax * Ax);
         } else {
-            pad_sum += c;
+            c = control_cost_row_table(p, x, i);
+        }
+        c_sum += c;
+        if (i < T) s_sum += state[i];
+    }
+    c_sum = warp_sum(c_sum);
+    s_sum = warp_sum(s_sum);
+    C_d = c_sum;
+    cum_d = s_sum + c_sum;
+}
+
+// per-timestep control costs in the reference's layout and folding order (:363-377); read-backs / noise-less record
+__device__ __forceinline__ void control_cost_store(const LoopParams& p, const double* x, int lane, double* control_out /*[T]*/)
+{
+    const int T = p.T, N = p.N;
+    for (int t = lane; t < T; t += 32) control_out[t] = control_cost_row(p, x, kPad + t);
+    __syncwarp();
+    if (lane == 0) {
+        double first = control_out[0], last = control_out[T - 1];
+        for (int i = 0; i < kPad; ++i) { first += control_cost_row(p, x, i); last += control_cost_row(p, x, N - (i + 1)); }
+        control_out[0] = first;
+        control_out[T - 1] = last;
+    }
+}
+
+// n^T R n of one (rollout, joint) row for the noise adaptation (PolicyImprovement.cpp:656-663), by the warp that
+// holds the row x = theta + noise in shared memory.  The row is overwritten in place by noise = x - theta with a
+// zero tail; R is symmetric and banded: sum_t n_t (R_tt n_t + 2 sum_{o>0} R_{t,t+o} n_{t+o}).
+__device__ __forceinline__ double noise_quadratic_form(const LoopParams& p, const RowCoefficients& rc, double* x,
+                                                       const double* theta_row, int lane)
+{
+    const int T = p.T;
+    __syncwarp();
+    for (int t = lane; t < T + kPad; t += 32) x[kPad + t] = (t < T) ? x[kPad + t] - theta_row[kPad + t] : 0.0;
+    __syncwarp();
+    const double* n = x + kPad;
+    double quad = 0.0;
+    if (p.r_toeplitz) {
+        for (int t = lane; t < T; t += 32) {
+            double s = 0.0;
+#pragma unroll
+            for (int o = 1; o <= kRBand; ++o) s += rc.r[o] * n[t + o];
+            quad += n[t] * (rc.r[0] * n[t] + 2.0 * s);
+        }
+    } else {
+        const int hw = p.rband_halfwidth;
+        for (int t = lane; t < T; t += 32) {
+            const double* rb = p.Rband + (size_t)t * (2 * kRBand + 1) + kRBand;
+            double s = 0.0;
+            for (int o = 1; o <= hw; ++o) s += __ldg(rb + o) * n[t + o];
+            quad += n[t] * (__ldg(rb) * n[t] + 2.0 * s);
         }
     }
-    free_sum = warp_sum(free_sum);
-    cum_sum = warp_sum(cum_sum);
-    pad_sum = warp_sum(pad_sum);
-    C_d = free_sum + pad_sum;
-    cum_d = cum_sum + pad_sum;
-    if (control_out) {
-        __syncwarp();
-        if (lane == 0) {   // fold the padding rows exactly in the reference's order (:373-377)
-            double first = control_out[0], last = control_out[T - 1];
-            for (int i = 0; i < kPad; ++i) { first += control_cost_row(p, st, x, i); last += control_cost_row(p, st, x, N - (i + 1)); }
-            control_out[0] = first;
-            control_out[T - 1] = last;
-        }
-    }
+    return warp_sum(quad);
 }
 
 // K4 + K5 + K6: Stomp::doExecuteRollouts (stomp/src/Stomp.cpp:206-229) -> Task::execute, then
 // PolicyImprovement::computeRolloutControlCosts / computeRolloutCumulativeCosts (PolicyImprovement.cpp:442-495)
-// for the generated rollouts.  One CTA = blockDim.y rollouts of one query; thread (x = t, y = r) evaluates one
-// state; cooperative phases walk (rollout, joint) rows warp by warp (no per-element index division).
+// for the generated rollouts.  One CTA = R rollouts of one query.  Thread r*T + t evaluates state (r, t) from
+// the noisy parameters in global memory (coalesced along t); the warps then walk the (rollout, joint) rows of
+// x = theta + (noisy - theta) staged in shared memory for the control-cost stencil (the control cost is
+// evaluated on parameters_ + noise_projected_, not on the noisy parameters: PolicyImprovement.cpp:812-817).
+template <bool kSimple>
 __global__ void __launch_bounds__(512, 2)
 rollout_cost_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
-                    const __grid_constant__ SdfParams sdf)
+                    const __grid_constant__ SdfParams sdf, int R)
 {
     extern __shared__ double smem[];
     const int q = blockIdx.y;
+    if (blockIdx.x == 0 && q == 0 && threadIdx.x < 4) p.tile_counter[threadIdx.x] = 0u;   // for the next sampling launch
     if (query_frozen(p, q)) return;
-    const int T = p.T, D = p.D, N = p.N, R = blockDim.y;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarps = (blockDim.x * blockDim.y + 31) >> 5;
-    double* sx = smem;                           // [R][D][N] padded trajectories
+    TimelineScope tls(p, 1);
+    const int T = p.T, D = p.D, N = p.N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;            // blockDim.x is a multiple of 32
+    double* sx = smem;                           // [R][D][N] padded x
     double* sstate = smem + (size_t)R * D * N;   // [R][T]
     const int k0 = blockIdx.x * R;
     const int nr = min(R, p.num_gen - k0);
     const int nrows = nr * D;
 
-    // ---- load: padding from the policy, free block <- noisy parameters (OptimizationTask.cpp:155-163) ----
+    // ---- stage x rows (padding from the policy, OptimizationTask.cpp:155-163) ----
     for (int rd = warp; rd < nrows; rd += nwarps) {
         const int r = rd / D, d = rd - r * D;
-        const double* free_src = p.rollouts + (((size_t)q * p.slots + (k0 + r)) * D + d) * T - kPad;
-        const double* pad_src = p.theta_all + ((size_t)q * D + d) * N;
+        const double* src = p.rollouts + (((size_t)q * p.slots + (k0 + r)) * D + d) * T;
+        const double* th = p.theta_all + ((size_t)q * D + d) * N;
         double* dst = sx + (size_t)rd * N;
-        for (int i = lane; i < N; i += 32) dst[i] = (i >= kPad && i < kPad + T) ? free_src[i] : pad_src[i];
+        for (int t = lane; t < T; t += 32) { const double tv = th[kPad + t]; dst[kPad + t] = tv + (src[t] - tv); }
+        if (lane < 2 * kPad) { const int i = lane < kPad ? lane : T + lane; dst[i] = th[i]; }
     }
-    __syncthreads();
 
     // ---- K4: one state per thread ----
-    if ((int)threadIdx.y < nr && (int)threadIdx.x < T) {
-        const int r = threadIdx.y, t = threadIdx.x;
-        const double* xq = sx + (size_t)r * D * N + kPad + t;
-        const bool hit = state_collides(robot, sdf, [&](int d) { return xq[(size_t)d * N]; });
+    const int my_r = tid / T, my_t = tid - my_r * T;
+    if (my_r < nr && !(p.debug_skip & 1)) {
+        const double* xq = p.rollouts + ((size_t)q * p.slots + (k0 + my_r)) * D * T + my_t;
+        const bool hit = state_collides<kSimple>(robot, sdf, [&](int d) { return xq[(size_t)d * T]; });
         const double cost = hit ? 1.0 : 0.0;
-        sstate[r * T + t] = cost;
-        const size_t o = ((size_t)q * p.slots + (k0 + r)) * T + t;
+        sstate[my_r * T + my_t] = cost;
+        const size_t o = ((size_t)q * p.slots + (k0 + my_r)) * T + my_t;
         p.state_costs[o] = cost;
         p.verdicts[o] = hit ? 1 : 0;
-        if (t == T - 1) p.validity[(size_t)q * p.slots + (k0 + r)] = hit ? 0 : 1;   // last timestep only (:192-202)
+        if (my_t == T - 1) p.validity[(size_t)q * p.slots + (k0 + my_r)] = hit ? 0 : 1;   // last timestep only (:192-202)
     }
     __syncthreads();
 
-    // ---- K5 + K6: warp tasks over (r, d).  The control cost is evaluated on parameters_ + noise_projected_,
-    // not on the noisy parameters (PolicyImprovement.cpp:812-817): x = theta + (noisy - theta), converted in
-    // place row by row by the warp that owns the row ----
-    const StencilRegs st = load_stencil(p);
-    for (int rd = warp; rd < nrows; rd += nwarps) {
+    // ---- K5 + K6: one warp per (rollout, joint) row ----
+    const RowCoefficients rc = load_row_coefficients(p);
+    for (int rd = warp; rd < ((p.debug_skip & 2) ? 0 : nrows); rd += nwarps) {
         const int r = rd / D, d = rd - r * D, k = k0 + r;
-        double* x = sx + (size_t)rd * N;
-        const double* th = p.theta_all + ((size_t)q * D + d) * N;
-        for (int i = kPad + lane; i < kPad + T; i += 32) { const double tv = th[i]; x[i] = tv + (x[i] - tv); }
-        __syncwarp();
+        const double* x = sx + (size_t)rd * N;
         double C_d, cum_d;
-        double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
-        control_cost_task(p, st, x, sstate + r * T, lane, cc_out, C_d, cum_d);
+        control_cost_sums(p, rc, x, sstate + r * T, lane, C_d, cum_d);
+        if (p.control_costs) control_cost_store(p, x, lane, p.control_costs + (((size_t)q * p.slots + k) * D + d) * T);
+        double quad = 0.0;
+        if (p.use_noise_adaptation) quad = noise_quadratic_form(p, rc, sx + (size_t)rd * N, p.theta_all + ((size_t)q * D + d) * N, lane);
         if (lane == 0) {
             double* s = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
             s[1 + d] = C_d;
             s[1 + D + d] = cum_d;
+            s[1 + 2 * D + d] = quad;
         }
     }
+    // S_k (sum of 0/1 state costs, exact in any order)
     for (int r = warp; r < nr; r += nwarps) {
         double s = 0.0;
         for (int t = lane; t < T; t += 32) s += sstate[r * T + t];
         s = warp_sum(s);
         if (lane == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k0 + r)) * p.sumw] = s;
     }
+    tls.end();
 }
 
 // the noise-less rollout record written out as the regular rollout slot the reference appends
@@ -510,7 +729,7 @@ evaluate_states_kernel(const __grid_constant__ RobotParams robot, const __grid_c
     const int k = (int)(idx / Tq), t = (int)(idx - (size_t)k * Tq);
     const int D = robot.num_joints;
     const double* base = theta + (size_t)k * D * Tq + t;
-    const bool hit = state_collides(robot, sdf, [&](int d) { return base[(size_t)d * Tq]; });
+    const bool hit = state_collides<false>(robot, sdf, [&](int d) { return base[(size_t)d * Tq]; });
     if (costs) costs[idx] = hit ? 1.0 : 0.0;
     if (verdicts) verdicts[idx] = hit ? 1 : 0;
     if (validity && t == Tq - 1) validity[k] = hit ? 0 : 1;
@@ -524,7 +743,7 @@ __global__ void sphere_centres_kernel(const __grid_constant__ RobotParams robot,
     Frame f;
     frame_identity(f);
     for (int d = 0; d < robot.num_joints; ++d) {
-        apply_joint(f, robot.joint[d], q[(size_t)i * robot.num_joints + d]);
+        apply_joint<false>(f, robot.joint[d], q[(size_t)i * robot.num_joints + d]);
         for (int s = robot.sphere_begin[d]; s < robot.sphere_begin[d + 1]; ++s) {
             double cx, cy, cz;
             sphere_centre(f, robot.sphere[s], cx, cy, cz);
@@ -549,7 +768,7 @@ reused_control_cost_kernel(const __grid_constant__ LoopParams p, int first, int 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     double* x = smem + (size_t)warp * (N + T);
     double* stc = x + N;
-    const StencilRegs st = load_stencil(p);
+    const RowCoefficients rc = load_row_coefficients(p);
     for (int task = blockIdx.x * nwarps + warp; task < count * D; task += gridDim.x * nwarps) {
         const int r = task / D, d = task - r * D, k = first + r;
         for (int i = lane; i < N; i += 32) {
@@ -561,16 +780,19 @@ reused_control_cost_kernel(const __grid_constant__ LoopParams p, int first, int 
         for (int t = lane; t < T; t += 32) stc[t] = p.state_costs[((size_t)q * p.slots + k) * T + t];
         __syncwarp();
         double C_d, cum_d;
-        double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
-        control_cost_task(p, st, x, stc, lane, cc_out, C_d, cum_d);
+        control_cost_sums(p, rc, x, stc, lane, C_d, cum_d);
+        if (p.control_costs) control_cost_store(p, x, lane, p.control_costs + (((size_t)q * p.slots + k) * D + d) * T);
         double s = 0.0;
         for (int t = lane; t < T; t += 32) s += stc[t];
         s = warp_sum(s);
+        double quad = 0.0;
+        if (p.use_noise_adaptation) quad = noise_quadratic_form(p, rc, x, p.theta_all + ((size_t)q * D + d) * N, lane);
         if (lane == 0) {
             double* o = p.sums + ((size_t)q * p.gslots + k) * p.sumw;
             o[0] = s;
             o[1 + d] = C_d;
             o[1 + D + d] = cum_d;
+            o[1 + 2 * D + d] = quad;
         }
         __syncwarp();
     }
@@ -633,29 +855,29 @@ reuse_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constan
 // =====================================================================================================
 // K7: PolicyImprovement::computeRolloutProbabilities (PolicyImprovement.cpp:497-582), cumulative-cost mode:
 // cumulative_costs_[d] is constant over t (:480), so one probability per (rollout, joint).
-// grid (wblocks, D, Q): every CTA finds the global min / max of its joint (redundantly, K' values), weighs its
-// own 256 rollouts, leaves a partial sum; the last CTA to arrive sums the partials in block order and
-// normalises (deterministic).  The noise-less rollout is read from its record, not from a slot.
+// One CTA of 1024 threads per (joint, query): min / max, exp + sum, normalise — three passes over K' cost rows
+// that stay in L1.  The noise-less rollout is read from its record (and written out as a slot by the d == 0 CTA).
 // =====================================================================================================
 __device__ __forceinline__ const double* cost_row(const LoopParams& p, int q, int k)
 {
     return (k == p.noiseless_gslot) ? p.nl_sums + (size_t)q * p.sumw : p.sums + ((size_t)q * p.gslots + k) * p.sumw;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 rollout_weights_kernel(const __grid_constant__ LoopParams p)
 {
     __shared__ double scratch[32];
-    __shared__ unsigned s_ticket;
-    const int d = blockIdx.y, q = blockIdx.z;
+    const int d = blockIdx.x, q = blockIdx.y;
     if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 2);
     const int D = p.D, n = p.num_rollouts, tid = threadIdx.x;
     double* prob = p.prob + (size_t)q * p.gslots * D;
     double* fprob = p.fprob + (size_t)q * p.gslots * D;
     const double h = p.cost_scaling_h;
-    if (blockIdx.x == 0 && d == 0 && p.noiseless_slot >= 0) materialise_noiseless(p, q, tid, blockDim.x);
+    if (d == 0 && p.noiseless_slot >= 0) materialise_noiseless(p, q, tid, blockDim.x);
 
     double mn = 1e300, mx = -1e300, fmn = 1e300, fmx = -1e300;
+#pragma unroll 4
     for (int k = tid; k < n; k += blockDim.x) {
         const double* s = cost_row(p, q, k);
         const double cum = 1.0 * s[1 + D + d];
@@ -669,119 +891,88 @@ rollout_weights_kernel(const __grid_constant__ LoopParams p)
     if (den < 1e-8) den = 1e-8;
     if (fden < 1e-8) fden = 1e-8;
 
-    double pr = 0.0, fp = 0.0;
-    const int k = blockIdx.x * blockDim.x + tid;
-    if (k < n) {
+    double psum = 0.0, fsum = 0.0;
+#pragma unroll 4
+    for (int k = tid; k < n; k += blockDim.x) {
         const double* s = cost_row(p, q, k);
-        pr = 1.0 * exp(((-h) * (1.0 * s[1 + D + d] - mn)) / den);      // importance_weight_ = 1
-        fp = 1.0 * exp(((-h) * ((s[0] + s[1 + d]) - fmn)) / fden);
+        const double pr = 1.0 * exp(((-h) * (1.0 * s[1 + D + d] - mn)) / den);      // importance_weight_ = 1
+        const double fp = 1.0 * exp(((-h) * ((s[0] + s[1 + d]) - fmn)) / fden);
         prob[(size_t)k * D + d] = pr;
         fprob[(size_t)k * D + d] = fp;
+        psum += pr; fsum += fp;
         if (d == 0) {   // total_cost_ (:451-462)
             double cost = s[0];
             for (int dd = 0; dd < D; ++dd) cost += s[1 + dd];
             p.total_cost[(size_t)q * p.gslots + k] = cost;
         }
     }
-    const double psum_blk = block_reduce<0>(pr, scratch);
-    const double fsum_blk = block_reduce<0>(fp, scratch);
-    double* part = p.wpart + (((size_t)q * D + d) * p.wblocks) * 2;
-    if (tid == 0) {
-        part[2 * blockIdx.x] = psum_blk;
-        part[2 * blockIdx.x + 1] = fsum_blk;
-        __threadfence();
-        s_ticket = atomicAdd(p.wticket + (size_t)q * D + d, 1u);
-    }
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    // ---- last CTA of this (query, joint): normalise ----
-    __threadfence();
-    double psum = 0.0, fsum = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) { psum += __ldcg(part + 2 * b); fsum += __ldcg(part + 2 * b + 1); }
+    psum = block_reduce<0>(psum, scratch);
+    fsum = block_reduce<0>(fsum, scratch);
     double fnorm = 0.0;
-    for (int kk = tid; kk < n; kk += blockDim.x) {
-        prob[(size_t)kk * D + d] = __ldcg(prob + (size_t)kk * D + d) / psum;
-        const double f = __ldcg(fprob + (size_t)kk * D + d) / fsum;
-        fprob[(size_t)kk * D + d] = f;
+    for (int k = tid; k < n; k += blockDim.x) {   // each thread re-reads only what it wrote
+        prob[(size_t)k * D + d] /= psum;
+        const double f = fprob[(size_t)k * D + d] / fsum;
+        fprob[(size_t)k * D + d] = f;
         fnorm += f;
     }
     fnorm = block_reduce<0>(fnorm, scratch);
-    if (tid == 0) {
-        p.fprob_sum[(size_t)q * D + d] = fnorm;
-        p.wticket[(size_t)q * D + d] = 0;
-    }
+    if (tid == 0) p.fprob_sum[(size_t)q * D + d] = fnorm;
+    tls.end();
 }
 
 // =====================================================================================================
 // K8: PolicyImprovement::computeParameterUpdates (PolicyImprovement.cpp:584-711): probability-weighted
-// noise sums and the noise-adaptation numerator sum_k Pfull * (n^T R n).  grid (chunks, D, Q); one warp
-// per rollout of the chunk, lanes stride over t; partial [Q][chunks][D][T+1] (last entry: numerator).
-// n^T R n uses the symmetry of the band: sum_t n_t (R_tt n_t + 2 sum_{o>0} R_{t,t+o} n_{t+o}).
+// noise sums sum_k P[k,d] * noise[k,d,t] and the noise-adaptation numerator sum_k Pfull[k,d] * (n^T R n)[k,d]
+// (the quadratic forms come from the cost kernel).  grid (chunks, D, Q); thread t streams the chunk's rollouts
+// (independent coalesced loads, unrolled); partial [Q][chunks][D][T+1] (last entry: numerator).
 // =====================================================================================================
-constexpr int kUpdateWarps = 8;
-constexpr int kMaxTPerLane = STOMP_B200_MAX_TIME_STEPS / 32;
-__global__ void __launch_bounds__(kUpdateWarps * 32)
+constexpr int kUpdateThreads = 128;
+__global__ void __launch_bounds__(kUpdateThreads)
 weighted_update_kernel(const __grid_constant__ LoopParams p)
 {
-    extern __shared__ double smem[];
+    extern __shared__ double smem[];   // [chunk] probabilities, [chunk] fprob * quad
+    __shared__ double scratch[32];
     const int d = blockIdx.y, q = blockIdx.z, c = blockIdx.x;
     if (query_frozen(p, q)) return;
-    const int T = p.T, D = p.D, hw = p.rband_halfwidth;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sn = smem + (size_t)warp * (T + kRBand);                  // noise row, zero tail
-    double* spart = smem + (size_t)kUpdateWarps * (T + kRBand);      // [warps][T+1]
-    double acc[kMaxTPerLane];
-#pragma unroll
-    for (int i = 0; i < kMaxTPerLane; ++i) acc[i] = 0.0;
-    double numer = 0.0;
-    for (int i = lane; i < T + kRBand; i += 32) sn[i] = 0.0;
-    __syncwarp();
-    const int k_end = min(p.num_local, (c + 1) * p.chunk);
-    for (int k = c * p.chunk + warp; k < k_end; k += kUpdateWarps) {
-        if (k == p.noiseless_slot) continue;   // zero noise: contributes nothing (PolicyImprovement.cpp:407-410)
-        const int g = (k < p.num_gen) ? p.gen_offset + k : k;   // local slot -> slot in the rollout-indexed tables
-        const double pr = p.prob[((size_t)q * p.gslots + g) * D + d];
-        const double* nz = p.noise + (((size_t)q * p.slots + k) * D + d) * T;
-#pragma unroll
-        for (int i = 0; i < kMaxTPerLane; ++i) {
-            const int t = lane + 32 * i;
-            if (t < T) {
-                const double v = nz[t];
-                sn[t] = v;
-                acc[i] += v * pr;
-            }
+    TimelineScope tls(p, 3);
+    const int T = p.T, D = p.D, tid = threadIdx.x;
+    const int k_begin = c * p.chunk, k_end = min(p.num_local, (c + 1) * p.chunk);
+    double* sp = smem;
+    double* sq = smem + p.chunk;
+    for (int k = k_begin + tid; k < k_end; k += blockDim.x) {
+        double pr = 0.0, fq = 0.0;
+        if (k != p.noiseless_slot) {   // zero noise: contributes nothing (PolicyImprovement.cpp:407-410)
+            const int g = (k < p.num_gen) ? p.gen_offset + k : k;   // local slot -> slot in the rollout-indexed tables
+            pr = p.prob[((size_t)q * p.gslots + g) * D + d];
+            if (p.use_noise_adaptation)
+                fq = p.fprob[((size_t)q * p.gslots + g) * D + d] * p.sums[((size_t)q * p.gslots + g) * p.sumw + 1 + 2 * D + d];
         }
-        if (p.use_noise_adaptation) {
-            __syncwarp();
-            double quad = 0.0;
-#pragma unroll
-            for (int i = 0; i < kMaxTPerLane; ++i) {
-                const int t = lane + 32 * i;
-                if (t < T) {
-                    const double* rb = p.Rband + (size_t)t * (2 * kRBand + 1) + kRBand;
-                    double s = 0.0;
-                    for (int o = 1; o <= hw; ++o) s += __ldg(rb + o) * sn[t + o];
-                    quad += sn[t] * (__ldg(rb) * sn[t] + 2.0 * s);
-                }
-            }
-            quad = warp_sum(quad);
-            numer += p.fprob[((size_t)q * p.gslots + g) * D + d] * quad;
-            __syncwarp();
-        }
+        sp[k - k_begin] = pr;
+        sq[k - k_begin] = fq;
     }
-#pragma unroll
-    for (int i = 0; i < kMaxTPerLane; ++i) {
-        const int t = lane + 32 * i;
-        if (t < T) spart[(size_t)warp * (T + 1) + t] = acc[i];
-    }
-    if (lane == 0) spart[(size_t)warp * (T + 1) + T] = numer;
     __syncthreads();
     double* out = p.partial + (((size_t)q * p.nchunks + c) * D + d) * (T + 1);
-    for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
-        double s = spart[t];
-        for (int w = 1; w < kUpdateWarps; ++w) s += spart[(size_t)w * (T + 1) + t];
-        out[t] = s;
+    for (int t = tid; t < T; t += blockDim.x) {
+        const double* nz = p.noise + (((size_t)q * p.slots + k_begin) * D + d) * T + t;
+        const size_t stride = (size_t)D * T;
+        double acc = 0.0;
+        int k = 0;
+        const int nk = k_end - k_begin;
+        for (; k + 8 <= nk; k += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = nz[(size_t)(k + u) * stride];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u] * sp[k + u];
+        }
+        for (; k < nk; ++k) acc += nz[(size_t)k * stride] * sp[k];
+        out[t] = acc;
     }
+    double numer = 0.0;
+    for (int k = tid; k < k_end - k_begin; k += blockDim.x) numer += sq[k];
+    numer = block_reduce<0>(numer, scratch);
+    if (tid == 0) out[T] = numer;
+    tls.end();
 }
 
 // sum of the chunk partials in chunk order -> updbuf [Q][D][T+1]; only needed in front of the all-reduce
@@ -793,6 +984,7 @@ reduce_partials_kernel(const __grid_constant__ LoopParams p, int nchunks)
     const int T = p.T, D = p.D;
     for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
         double s = 0.0;
+#pragma unroll 8
         for (int c = 0; c < nchunks; ++c) s += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 1) + t];
         p.updbuf[((size_t)q * D + d) * (T + 1) + t] = s;
     }
@@ -800,20 +992,21 @@ reduce_partials_kernel(const __grid_constant__ LoopParams p, int nchunks)
 
 // =====================================================================================================
 // K8 tail + K9: noise adaptation (PolicyImprovement.cpp:656-679) and CovariantMovementPrimitive::
-// updateParameters (stomp/src/CovariantMovementPrimitive.cpp:476-479).  One CTA per query.  from_partials:
+// updateParameters (stomp/src/CovariantMovementPrimitive.cpp:476-479).  grid (D, Q).  from_partials:
 // sum the chunk partials here (single GPU); otherwise read the all-reduced updbuf.
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
 apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int nchunks)
 {
-    const int q = blockIdx.x;
+    const int d = blockIdx.x, q = blockIdx.y;
     if (query_frozen(p, q)) return;
-    const int T = p.T, D = p.D, N = p.N, tid = threadIdx.x;
-    for (int e = tid; e < D * (T + 1); e += blockDim.x) {
-        const int d = e / (T + 1), t = e - d * (T + 1);
+    TimelineScope tls(p, 4);
+    const int T = p.T, D = p.D, N = p.N;
+    for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
         double u;
         if (from_partials) {
             u = 0.0;
+#pragma unroll 8
             for (int c = 0; c < nchunks; ++c) u += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 1) + t];
         } else {
             u = p.updbuf[((size_t)q * D + d) * (T + 1) + t];
@@ -834,6 +1027,7 @@ apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int
             store_sampler_coefficients(p, q, d, sd);
         }
     }
+    tls.end();
 }
 
 // =====================================================================================================
@@ -849,6 +1043,7 @@ noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_cons
     extern __shared__ double smem[];
     const int q = blockIdx.x;
     if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 5);
     const int T = p.T, D = p.D, N = p.N, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     double* sx = smem;                      // [D][N]
@@ -858,7 +1053,7 @@ noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_cons
     __syncthreads();
     for (int t = tid; t < T; t += blockDim.x) {
         const double* xq = sx + kPad + t;
-        const bool hit = state_collides(robot, sdf, [&](int d) { return xq[(size_t)d * N]; });
+        const bool hit = state_collides<false>(robot, sdf, [&](int d) { return xq[(size_t)d * N]; });
         sstate[t] = hit ? 1.0 : 0.0;
         p.nl_state[(size_t)q * T + t] = sstate[t];
         p.nl_verdict[(size_t)q * T + t] = hit ? 1 : 0;
@@ -866,12 +1061,13 @@ noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_cons
     }
     __syncthreads();
     // control costs (noise = 0: parameters + 0.0 is exact) and sums
-    const StencilRegs st = load_stencil(p);
+    const RowCoefficients rc = load_row_coefficients(p);
     for (int task = warp; task < D + 1; task += nwarps) {
         if (task < D) {
             double C_d, cum_d;
-            control_cost_task(p, st, sx + (size_t)task * N, sstate, lane, p.nl_control + ((size_t)q * D + task) * T, C_d, cum_d);
-            if (lane == 0) { ssum[1 + task] = C_d; ssum[1 + D + task] = cum_d; }
+            control_cost_sums(p, rc, sx + (size_t)task * N, sstate, lane, C_d, cum_d);
+            control_cost_store(p, sx + (size_t)task * N, lane, p.nl_control + ((size_t)q * D + task) * T);
+            if (lane == 0) { ssum[1 + task] = C_d; ssum[1 + D + task] = cum_d; ssum[1 + 2 * D + task] = 0.0; }
         } else {
             double s = 0.0;
             for (int t = lane; t < T; t += 32) s += sstate[t];
@@ -892,6 +1088,7 @@ noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_cons
         p.iters_used[q] += 1;
         if ((cost < 1) && (fabs(improvement) < p.min_cost_improvement)) p.stop[q] = 1;
     }
+    tls.end();
 }
 
 }  // namespace stomp_b200

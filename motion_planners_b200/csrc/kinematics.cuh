@@ -43,6 +43,8 @@ struct SphereParams {
 struct RobotParams {
     int32_t num_joints;
     int32_t num_spheres;
+    int32_t simple_chain;     // every joint revolute, rpy == 0, axis along +-x / +-y / +-z (the usual URDF arm)
+    int32_t pad_;
     int32_t sphere_begin[STOMP_B200_MAX_DIMS + 1];   // spheres of joint d: [sphere_begin[d], sphere_begin[d+1])
     double lower[STOMP_B200_MAX_DIMS];
     double upper[STOMP_B200_MAX_DIMS];
@@ -117,6 +119,8 @@ __device__ __forceinline__ void frame_identity(Frame& f)
         (b) = fma((ns), _a, (c) * _b);           \
     }
 
+// kSimple: compiled without the fixed-rotation, prismatic and general-axis branches (RobotParams::simple_chain)
+template <bool kSimple>
 __device__ __forceinline__ void apply_joint(Frame& f, const JointParams& j, double q)
 {
     if (j.parent < 0) frame_identity(f);
@@ -125,7 +129,7 @@ __device__ __forceinline__ void apply_joint(Frame& f, const JointParams& j, doub
     if (j.o_mask & 1) { f.px = fma(f.r00, j.o[0], f.px); f.py = fma(f.r10, j.o[0], f.py); f.pz = fma(f.r20, j.o[0], f.pz); }
     if (j.o_mask & 2) { f.px = fma(f.r01, j.o[1], f.px); f.py = fma(f.r11, j.o[1], f.py); f.pz = fma(f.r21, j.o[1], f.pz); }
     if (j.o_mask & 4) { f.px = fma(f.r02, j.o[2], f.px); f.py = fma(f.r12, j.o[2], f.py); f.pz = fma(f.r22, j.o[2], f.pz); }
-    if (!j.fixed_rot_identity) {   // R = R * A
+    if (!kSimple && !j.fixed_rot_identity) {   // R = R * A
         const double n00 = fma(f.r02, j.A[6], fma(f.r01, j.A[3], f.r00 * j.A[0]));
         const double n01 = fma(f.r02, j.A[7], fma(f.r01, j.A[4], f.r00 * j.A[1]));
         const double n02 = fma(f.r02, j.A[8], fma(f.r01, j.A[5], f.r00 * j.A[2]));
@@ -139,7 +143,7 @@ __device__ __forceinline__ void apply_joint(Frame& f, const JointParams& j, doub
         f.r10 = n10; f.r11 = n11; f.r12 = n12;
         f.r20 = n20; f.r21 = n21; f.r22 = n22;
     }
-    if (j.prismatic) {   // p += q * (R * axis)
+    if (!kSimple && j.prismatic) {   // p += q * (R * axis)
         const double dx = fma(f.r02, j.axis[2], fma(f.r01, j.axis[1], f.r00 * j.axis[0]));
         const double dy = fma(f.r12, j.axis[2], fma(f.r11, j.axis[1], f.r10 * j.axis[0]));
         const double dz = fma(f.r22, j.axis[2], fma(f.r21, j.axis[1], f.r20 * j.axis[0]));
@@ -165,7 +169,7 @@ __device__ __forceinline__ void apply_joint(Frame& f, const JointParams& j, doub
         STOMP_B200_ROT2(f.r01, f.r02, s, ns, c)
         STOMP_B200_ROT2(f.r11, f.r12, s, ns, c)
         STOMP_B200_ROT2(f.r21, f.r22, s, ns, c)
-    } else {                       // Rodrigues: Q = c*I + s*[a]x + (1-c)*a a^T ; R = R*Q
+    } else if (!kSimple) {         // Rodrigues: Q = c*I + s*[a]x + (1-c)*a a^T ; R = R*Q
         const double ax = j.axis[0], ay = j.axis[1], az = j.axis[2];
         const double v = 1.0 - c;
         const double vx = v * ax, vy = v * ay, vz = v * az;

@@ -1,0 +1,35 @@
+"""In-pipeline kernel timeline of the STOMP loop (first-CTA-start / last-CTA-end %globaltimer stamps):
+    python tools/timeline.py [workload] [iterations]
+Prints the median duration of every kernel and the gaps between them, inside the running loop."""
+import sys
+import numpy as np
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+import bench
+from motion_planners_b200 import binding
+
+name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+pb = bench.make_problem(name)
+e = binding.engine_for_problem(pb, shard_mode=1 if bench.WORKLOADS[name]["kind"] == "batch" else 0)
+e.begin_solve()
+e.run(0, 5)
+e.set_timeline(True)
+e.timer_begin()
+e.run(5, iters)
+ms = e.timer_end()
+tl = e.timeline(iters)
+names = ["sample", "cost", "weights", "update", "apply", "noiseless", "reuse", "-"]
+dur = tl[:, :, 1] - tl[:, :, 0]
+print(f"workload {name}: {ms / iters * 1e3:.1f} us per iteration over {iters} iterations (events)")
+for k, n in enumerate(names):
+    if np.all(tl[:, k, 0] < 0):
+        continue
+    print(f"  {n:10s} median {np.median(dur[:, k]):8.1f} us   min {dur[:, k].min():8.1f}   max {dur[:, k].max():8.1f}")
+order = [0, 1, 2, 3, 4]
+gaps = [tl[:, b, 0] - tl[:, a, 1] for a, b in zip(order[:-1], order[1:])]
+print("  gaps sample->cost->weights->update->apply (median us):", [round(float(np.median(g)), 1) for g in gaps])
+nxt = tl[1:, 0, 0] - tl[:-1, 4, 1]
+print("  gap apply -> next sample (median us):", round(float(np.median(nxt)), 1))
+print("  iteration period (median us):", round(float(np.median(tl[1:, 0, 0] - tl[:-1, 0, 0])), 1))
+print("  noiseless start after apply end (median us):", round(float(np.median(tl[:, 5, 0] - tl[:, 4, 1])), 1),
+      " noiseless end before next weights start:", round(float(np.median(tl[1:, 2, 0] - tl[:-1, 5, 1])), 1))
