@@ -259,14 +259,6 @@ int launch_sample(stomp_b200_engine* e, const LoopParams& lp)
     return check_launch(e, "sample_rollouts_kernel");
 }
 
-int rollouts_per_cta(const stomp_b200_engine* e, int num_gen)
-{
-    int R = std::max(1, 512 / e->T);
-    // keep at least ~2 CTAs per SM worth of work items when the rollout count is small
-    while (R > 1 && (num_gen + R - 1) / R < 296) --R;
-    return R;
-}
-
 enum NoiseMode { kNoisePhilox = 0, kNoiseUnit = 1, kNoiseEpsilon = 2 };
 
 // one Stomp::runSingleIteration for all local queries, queued on the stream (no host synchronisation)
@@ -345,16 +337,24 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         if (int rc = launch_sample<true>(e, lp)) return rc;
     }
 
-    // ---- execute + control costs + row sums (K4-K6) ----
+    // ---- control costs + n^T R n of the generated rows (K5, K6), then the state costs (K4) ----
     {
-        const int R = rollouts_per_cta(e, gen_local);
-        const size_t smem = sizeof(double) * ((size_t)R * e->D * e->N + (size_t)R * e->T);
-        dim3 grid((gen_local + R - 1) / R, e->Q);
-        const int threads = ((R * e->T + 31) / 32) * 32;
+        const int rows = gen_local * e->D;
         Scope sc(e, STOMP_B200_KERNEL_COST);
-        if (e->robot.simple_chain) rollout_cost_kernel<true><<<grid, threads, smem, e->stream>>>(lp, e->robot, e->sdf, R);
-        else rollout_cost_kernel<false><<<grid, threads, smem, e->stream>>>(lp, e->robot, e->sdf, R);
-        if (int rc = check_launch(e, "rollout_cost_kernel")) return rc;
+        control_rows_kernel<<<dim3((rows * kRowLanes + 255) / 256, e->Q), 256, 0, e->stream>>>(lp);
+        if (int rc = check_launch(e, "control_rows_kernel")) return rc;
+        if (lp.control_costs) {
+            fold_control_costs_kernel<<<dim3((rows + 127) / 128, e->Q), 128, 0, e->stream>>>(lp);
+            if (int rc = check_launch(e, "fold_control_costs_kernel")) return rc;
+        }
+    }
+    {
+        const int states = gen_local * e->T;
+        dim3 grid((states + 255) / 256, e->Q);
+        Scope sc(e, STOMP_B200_KERNEL_COST);
+        if (e->robot.simple_chain) rollout_states_kernel<true><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
+        else rollout_states_kernel<false><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
+        if (int rc = check_launch(e, "rollout_states_kernel")) return rc;
     }
     // ---- the noise-less rollout of the previous iteration is needed from here on ----
     if (e->noiseless_pending) {
@@ -379,8 +379,9 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
 
     // ---- probabilities (K7) ----
     {
+        lp.wblocks = (n + 255) / 256;
         Scope sc(e, STOMP_B200_KERNEL_WEIGHTS);
-        rollout_weights_kernel<<<dim3(e->D, e->Q), 1024, 0, e->stream>>>(lp);
+        rollout_weights_kernel<<<dim3(lp.wblocks, e->D, e->Q), 256, 0, e->stream>>>(lp);
         if (int rc = check_launch(e, "rollout_weights_kernel")) return rc;
     }
     // ---- weighted sums (K8) ----
@@ -399,7 +400,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             reduce_partials_kernel<<<dim3(e->D, e->Q), 256, 0, e->stream>>>(lp, nchunks);
             if (int rc = check_launch(e, "reduce_partials_kernel")) return rc;
         }
-        const size_t count = (size_t)e->Q * e->D * (e->T + 1);
+        const size_t count = (size_t)e->Q * e->D * (e->T + 2);
         NCCL_TRY(e, g_nccl.AllReduce(lp.updbuf, lp.updbuf, count, ncclFloat64, ncclSum, e->comm, e->stream));
     }
     // ---- apply (K9) ----
@@ -606,7 +607,7 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.fprob_sum, Q * D));
     CREATE_TRY(dev_alloc(e, &b.sigma, Q * D));
     CREATE_TRY(dev_alloc(e, &b.coef, Q * D * 3));
-    CREATE_TRY(dev_alloc(e, &b.updbuf, Q * D * (T + 1)));
+    CREATE_TRY(dev_alloc(e, &b.updbuf, Q * D * (T + 2)));
     CREATE_TRY(dev_alloc(e, &b.updates, Q * D * T));
     const size_t gen_cap = (size_t)std::max(cfg->num_rollouts_per_iteration, cfg->min_rollouts) / world + 1;
     CREATE_TRY(dev_alloc(e, &b.unit_noise, Q * gen_cap * D * T));
@@ -623,9 +624,11 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.stop, Q));
     CREATE_TRY(dev_alloc(e, &b.iters_used, Q));
     CREATE_TRY(dev_alloc(e, &e->d_order, Q * S));
-    b.chunk = 128;
+    b.chunk = 64;
     e->max_chunks = (int)((S + b.chunk - 1) / b.chunk);
-    CREATE_TRY(dev_alloc(e, &b.partial, Q * e->max_chunks * D * (T + 1)));
+    CREATE_TRY(dev_alloc(e, &b.partial, Q * e->max_chunks * D * (T + 2)));
+    b.wblocks_cap = (int)((GS + 255) / 256);
+    CREATE_TRY(dev_alloc(e, &b.wpart, Q * D * b.wblocks_cap));
     CREATE_TRY(dev_alloc(e, &b.tile_counter, 4));
     CREATE_TRY(dev_alloc(e, &e->d_timeline, (size_t)kTimelineRing * kTimelineKernels * 2));
     b.world_size = world;
@@ -671,8 +674,6 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     }
     CREATE_CUDA(cudaFuncSetAttribute(sample_rollouts_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     CREATE_CUDA(cudaFuncSetAttribute(sample_rollouts_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    CREATE_CUDA(cudaFuncSetAttribute(rollout_cost_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CREATE_CUDA(cudaFuncSetAttribute(rollout_cost_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CREATE_CUDA(cudaFuncSetAttribute(noiseless_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CREATE_CUDA(cudaFuncSetAttribute(reuse_rollouts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     std::memset(&e->robot, 0, sizeof(e->robot));
@@ -1005,7 +1006,7 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
                     for (size_t d = 0; d < D; ++d) c += r[1 + d];
                     o[q * ng + k] = c;
                 } else {
-                    for (size_t d = 0; d < D; ++d) o[(q * ng + k) * D + d] = kind == 5 ? 1.0 * r[1 + D + d] : r[0] + r[1 + d];
+                    for (size_t d = 0; d < D; ++d) o[(q * ng + k) * D + d] = r[0] + r[1 + d];   // cumulative (= sum_t state + control_d) and full costs
                 }
             }
         return 0;
@@ -1021,18 +1022,28 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
         case STOMP_B200_CUMULATIVE_COSTS: return from_sums(5);
         case STOMP_B200_FULL_COSTS: return from_sums(6);
         case STOMP_B200_TOTAL_COST: return from_sums(7);
-        case STOMP_B200_PROBABILITIES: {
-            if (out_bytes != Q * ng * D * T * sizeof(double)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "out_bytes does not match the tensor size");
-            std::vector<double> pr(Q * e->gslots * D);
+        case STOMP_B200_PROBABILITIES:
+        case STOMP_B200_FULL_PROBABILITIES: {
+            // the device tables hold exp(-h (c - min) / den); divide by the sum of the per-CTA partial sums in block
+            // order, exactly as weighted_update_kernel does (probabilities_ and full_probabilities_ coincide here)
+            const size_t width = tensor == STOMP_B200_PROBABILITIES ? T : 1;
+            if (out_bytes != Q * ng * D * width * sizeof(double)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "out_bytes does not match the tensor size");
+            std::vector<double> pr(Q * e->gslots * D), part(Q * D * b.wblocks_cap);
             CUDA_TRY(e, cudaMemcpy(pr.data(), b.prob, sizeof(double) * pr.size(), cudaMemcpyDeviceToHost));
+            CUDA_TRY(e, cudaMemcpy(part.data(), b.wpart, sizeof(double) * part.size(), cudaMemcpyDeviceToHost));
+            const int wblocks = (int)((ng + 255) / 256);
             double* o = static_cast<double*>(out);
             for (size_t q = 0; q < Q; ++q)
-                for (size_t k = 0; k < ng; ++k)
-                    for (size_t d = 0; d < D; ++d)
-                        for (size_t t = 0; t < T; ++t) o[((q * ng + k) * D + d) * T + t] = pr[(q * e->gslots + k) * D + d];
+                for (size_t d = 0; d < D; ++d) {
+                    double psum = 0.0;
+                    for (int bl = 0; bl < wblocks; ++bl) psum += part[(q * D + d) * b.wblocks_cap + bl];
+                    for (size_t k = 0; k < ng; ++k) {
+                        const double v = pr[(q * e->gslots + k) * D + d] / psum;
+                        for (size_t t = 0; t < width; ++t) o[((q * ng + k) * D + d) * width + t] = v;
+                    }
+                }
             return 0;
         }
-        case STOMP_B200_FULL_PROBABILITIES: return per_query(b.fprob, ng, e->gslots, D * sizeof(double));
         case STOMP_B200_UPDATES: return per_query(b.updates, 1, 1, D * T * sizeof(double));
         case STOMP_B200_PARAMETERS:
             if (out_bytes != Q * D * T * sizeof(double)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "out_bytes does not match the tensor size");

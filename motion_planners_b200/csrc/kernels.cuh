@@ -59,8 +59,10 @@ struct LoopParams {
     int32_t world_size;
     double* sigma;            // [Q][D]  adapted_stddevs_
     double* coef;             // [Q][D][3] p1, p2, new_stddev of the mean-shifted sampler (PolicyImprovement.cpp:262-269)
-    double* updbuf;           // [Q][D][T+1]  update row + numerator of the noise adaptation (after the all-reduce)
-    double* partial;          // [Q][chunks][D][T+1] per-chunk partial sums of weighted_update_kernel
+    double* updbuf;           // [Q][D][T+2]  update row, numerator and denominator of the noise adaptation (after the all-reduce)
+    double* partial;          // [Q][chunks][D][T+2] per-chunk partial sums of weighted_update_kernel
+    double* wpart;            // [Q][D][wblocks_cap] per-CTA sums of the unnormalised weights (rollout_weights_kernel)
+    int32_t wblocks, wblocks_cap;
     int32_t nchunks, chunk;
     double* updates;          // [Q][D][T]    last applied update (read-back)
     double* unit_noise;       // [Q][G][D][T] staging (injected) / debug
@@ -618,78 +620,176 @@ __device__ __forceinline__ double noise_quadratic_form(const LoopParams& p, cons
     return warp_sum(quad);
 }
 
-// K4 + K5 + K6: Stomp::doExecuteRollouts (stomp/src/Stomp.cpp:206-229) -> Task::execute, then
-// PolicyImprovement::computeRolloutControlCosts / computeRolloutCumulativeCosts (PolicyImprovement.cpp:442-495)
-// for the generated rollouts.  One CTA = R rollouts of one query.  Thread r*T + t evaluates state (r, t) from
-// the noisy parameters in global memory (coalesced along t); the warps then walk the (rollout, joint) rows of
-// x = theta + (noisy - theta) staged in shared memory for the control-cost stencil (the control cost is
-// evaluated on parameters_ + noise_projected_, not on the noisy parameters: PolicyImprovement.cpp:812-817).
-template <bool kSimple>
-__global__ void __launch_bounds__(512, 2)
-rollout_cost_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
-                    const __grid_constant__ SdfParams sdf, int R)
+// K5 + K6: PolicyImprovement::computeRolloutControlCosts / computeRolloutCumulativeCosts
+// (PolicyImprovement.cpp:442-495) and the n^T R n of the noise adaptation (:656-663) for the generated rollouts.
+// EIGHT lanes per (rollout, joint) row, each walking one eighth of the padded trajectory x = theta + noise
+// sequentially with the 7-wide stencil window (and the 7-wide noise window) in registers: no shared memory, no
+// barriers, one 3-step shuffle reduction per row.  FP64 dependent-issue latency is long on this part, so the
+// kernel is built from many short independent chains (8 x rows threads) rather than few long ones.
+// The row also zeroes S_k (d == 0) for the state kernel that follows.
+constexpr int kRowLanes = 8;
+__global__ void __launch_bounds__(256)
+control_rows_kernel(const __grid_constant__ LoopParams p)
 {
-    extern __shared__ double smem[];
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 6);
+    const int T = p.T, D = p.D, N = p.N;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = gtid / kRowLanes, seg = gtid & (kRowLanes - 1);
+    const bool active = row < p.num_gen * D && !(p.debug_skip & 2);
+    double C_part = 0.0, quad = 0.0;
+    int k = 0, d = 0;
+    if (active) {
+        k = row / D; d = row - k * D;
+        const double* nz = p.noise + (((size_t)q * p.slots + k) * D + d) * T;
+        const double* th = p.theta_all + ((size_t)q * D + d) * N;
+        double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
+        const double dtw = p.dt * p.control_cost_weight;
+        const bool fast = p.st_n > 0;
+        double c[7];
+#pragma unroll
+        for (int o = 0; o < 7; ++o) {
+            c[o] = 0.0;
+            for (int j = 0; j < p.st_n; ++j)
+                if (p.st_off[j] + 3 == o) c[o] = p.st_coef[j];
+        }
+        const double sqrt_w = p.rule_sqrt_w[0];
+        auto xall = [&](int j) -> double {   // columns outside [0, N) are never referenced with a non-zero coefficient
+            if (j < 0 || j >= N) return 0.0;
+            return (j >= kPad && j < kPad + T) ? th[j] + nz[j - kPad] : th[j];
+        };
+        // ---- control costs of rows [i0, i1) ----
+        const int len = (N + kRowLanes - 1) / kRowLanes;
+        const int i0 = seg * len, i1 = min(N, i0 + len);
+        double w[7];   // w[o] = x_all[i - 3 + o]
+#pragma unroll
+        for (int o = 0; o < 7; ++o) w[o] = xall(i0 - 3 + o);
+        for (int i = i0; i < i1; ++i) {
+            double cost;
+            if (fast && i >= 3 && i < N - 3) {
+                double s = 0.0;
+#pragma unroll
+                for (int o = 0; o < 7; ++o) s += c[o] * w[o];   // mul then add in column order: the reference's arithmetic
+                const double Ax = s * sqrt_w;
+                cost = dtw * (Ax * Ax);
+            } else {
+                cost = 0.0;
+                for (int r = 0; r < p.num_rules; ++r) {
+                    const double* band = p.diff_band + ((size_t)p.rule_id[r] * N + i) * 7;
+                    double s = 0.0;
+#pragma unroll
+                    for (int o = 0; o < 7; ++o)
+                        if (i - 3 + o >= 0 && i - 3 + o < N) s += __ldg(band + o) * w[o];
+                    const double Ax = s * p.rule_sqrt_w[r];
+                    cost += dtw * (Ax * Ax);
+                }
+            }
+            C_part += cost;
+            // per-timestep layout for read-backs; fold_control_costs_kernel adds the padding rows in the reference's order
+            if (cc_out && i >= kPad && i < kPad + T) cc_out[i - kPad] = cost;
+#pragma unroll
+            for (int o = 0; o < 6; ++o) w[o] = w[o + 1];
+            w[6] = xall(i + 4);
+        }
+        // ---- n^T R n over t in [t0, t1): sum_t n_t (R_tt n_t + 2 sum_{o>0} R_{t,t+o} n_{t+o}) ----
+        if (p.use_noise_adaptation) {
+            const int tlen = (T + kRowLanes - 1) / kRowLanes;
+            const int t0 = seg * tlen, t1 = min(T, t0 + tlen);
+            double r[kRBand + 1], m[kRBand + 1];   // m[o] = noise[t + o]
+#pragma unroll
+            for (int o = 0; o <= kRBand; ++o) { r[o] = p.r_diag[o]; m[o] = (t0 + o < T) ? nz[t0 + o] : 0.0; }
+            for (int t = t0; t < t1; ++t) {
+                double s = 0.0;
+                if (p.r_toeplitz) {
+#pragma unroll
+                    for (int o = 1; o <= kRBand; ++o) s += r[o] * m[o];
+                    quad += m[0] * (r[0] * m[0] + 2.0 * s);
+                } else {
+                    const double* rb = p.Rband + (size_t)t * (2 * kRBand + 1) + kRBand;
+#pragma unroll
+                    for (int o = 1; o <= kRBand; ++o) s += __ldg(rb + o) * m[o];
+                    quad += m[0] * (__ldg(rb) * m[0] + 2.0 * s);
+                }
+#pragma unroll
+                for (int o = 0; o < kRBand; ++o) m[o] = m[o + 1];
+                m[kRBand] = (t + kRBand + 1 < T) ? nz[t + kRBand + 1] : 0.0;
+            }
+        }
+    }
+    // the 8 lanes of a row are adjacent: fixed-order butterfly
+#pragma unroll
+    for (int o = kRowLanes / 2; o > 0; o >>= 1) {
+        C_part += __shfl_xor_sync(0xffffffffu, C_part, o);
+        quad += __shfl_xor_sync(0xffffffffu, quad, o);
+    }
+    if (active && seg == 0) {
+        double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
+        srow[1 + d] = C_part;
+        srow[1 + 2 * D + d] = quad;
+        if (d == 0) srow[0] = 0.0;        // S_k is accumulated by rollout_states_kernel
+    }
+    tls.end();
+}
+
+// fold of the padding rows into the first / last free step in the reference's order, for the stored
+// per-timestep control costs (read-backs only; one thread per row)
+__global__ void __launch_bounds__(128)
+fold_control_costs_kernel(const __grid_constant__ LoopParams p)
+{
+    const int q = blockIdx.y;
+    if (query_frozen(p, q) || !p.control_costs) return;
+    const int T = p.T, D = p.D, N = p.N;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= p.num_gen * D) return;
+    const int k = row / D, d = row - k * D;
+    const double* nz = p.noise + (((size_t)q * p.slots + k) * D + d) * T;
+    const double* th = p.theta_all + ((size_t)q * D + d) * N;
+    double* cc = p.control_costs + (((size_t)q * p.slots + k) * D + d) * T;
+    auto xall = [&](int j) { return (j >= kPad && j < kPad + T) ? th[j] + nz[j - kPad] : th[j]; };
+    auto row_cost = [&](int i) {
+        const double dtw = p.dt * p.control_cost_weight;
+        double cost = 0.0;
+        for (int r = 0; r < p.num_rules; ++r) {
+            const double* band = p.diff_band + ((size_t)p.rule_id[r] * N + i) * 7;
+            double s = 0.0;
+            for (int j = max(0, i - 3); j <= min(N - 1, i + 3); ++j) s += __ldg(band + (j - i + 3)) * xall(j);
+            const double Ax = s * p.rule_sqrt_w[r];
+            cost += dtw * (Ax * Ax);
+        }
+        return cost;
+    };
+    double first = cc[0], last = cc[T - 1];
+    for (int i = 0; i < kPad; ++i) { first += row_cost(i); last += row_cost(N - (i + 1)); }
+    cc[0] = first;
+    cc[T - 1] = last;
+}
+
+// K4: Stomp::doExecuteRollouts (stomp/src/Stomp.cpp:206-229) -> Task::execute for every generated rollout:
+// one thread per (rollout, timestep) state, noisy parameters read coalesced along t, FK in registers, SDF
+// gathers through the read-only path, cost / verdict written back; S_k = sum_t cost accumulated with
+// atomicAdd (the terms are 0 / 1, so the double sum is exact in any order).  This is the roofline kernel:
+// 8D + 4S + 9 algorithmic bytes per state.
+template <bool kSimple>
+__global__ void __launch_bounds__(256)
+rollout_states_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
+                      const __grid_constant__ SdfParams sdf)
+{
     const int q = blockIdx.y;
     if (blockIdx.x == 0 && q == 0 && threadIdx.x < 4) p.tile_counter[threadIdx.x] = 0u;   // for the next sampling launch
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 1);
-    const int T = p.T, D = p.D, N = p.N;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarps = blockDim.x >> 5;            // blockDim.x is a multiple of 32
-    double* sx = smem;                           // [R][D][N] padded x
-    double* sstate = smem + (size_t)R * D * N;   // [R][T]
-    const int k0 = blockIdx.x * R;
-    const int nr = min(R, p.num_gen - k0);
-    const int nrows = nr * D;
-
-    // ---- stage x rows (padding from the policy, OptimizationTask.cpp:155-163) ----
-    for (int rd = warp; rd < nrows; rd += nwarps) {
-        const int r = rd / D, d = rd - r * D;
-        const double* src = p.rollouts + (((size_t)q * p.slots + (k0 + r)) * D + d) * T;
-        const double* th = p.theta_all + ((size_t)q * D + d) * N;
-        double* dst = sx + (size_t)rd * N;
-        for (int t = lane; t < T; t += 32) { const double tv = th[kPad + t]; dst[kPad + t] = tv + (src[t] - tv); }
-        if (lane < 2 * kPad) { const int i = lane < kPad ? lane : T + lane; dst[i] = th[i]; }
-    }
-
-    // ---- K4: one state per thread ----
-    const int my_r = tid / T, my_t = tid - my_r * T;
-    if (my_r < nr && !(p.debug_skip & 1)) {
-        const double* xq = p.rollouts + ((size_t)q * p.slots + (k0 + my_r)) * D * T + my_t;
+    const int T = p.T, D = p.D;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < p.num_gen * T && !(p.debug_skip & 1)) {
+        const int k = idx / T, t = idx - k * T;
+        const double* xq = p.rollouts + ((size_t)q * p.slots + k) * D * T + t;
         const bool hit = state_collides<kSimple>(robot, sdf, [&](int d) { return xq[(size_t)d * T]; });
-        const double cost = hit ? 1.0 : 0.0;
-        sstate[my_r * T + my_t] = cost;
-        const size_t o = ((size_t)q * p.slots + (k0 + my_r)) * T + my_t;
-        p.state_costs[o] = cost;
+        const size_t o = ((size_t)q * p.slots + k) * T + t;
+        p.state_costs[o] = hit ? 1.0 : 0.0;
         p.verdicts[o] = hit ? 1 : 0;
-        if (my_t == T - 1) p.validity[(size_t)q * p.slots + (k0 + my_r)] = hit ? 0 : 1;   // last timestep only (:192-202)
-    }
-    __syncthreads();
-
-    // ---- K5 + K6: one warp per (rollout, joint) row ----
-    const RowCoefficients rc = load_row_coefficients(p);
-    for (int rd = warp; rd < ((p.debug_skip & 2) ? 0 : nrows); rd += nwarps) {
-        const int r = rd / D, d = rd - r * D, k = k0 + r;
-        const double* x = sx + (size_t)rd * N;
-        double C_d, cum_d;
-        control_cost_sums(p, rc, x, sstate + r * T, lane, C_d, cum_d);
-        if (p.control_costs) control_cost_store(p, x, lane, p.control_costs + (((size_t)q * p.slots + k) * D + d) * T);
-        double quad = 0.0;
-        if (p.use_noise_adaptation) quad = noise_quadratic_form(p, rc, sx + (size_t)rd * N, p.theta_all + ((size_t)q * D + d) * N, lane);
-        if (lane == 0) {
-            double* s = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
-            s[1 + d] = C_d;
-            s[1 + D + d] = cum_d;
-            s[1 + 2 * D + d] = quad;
-        }
-    }
-    // S_k (sum of 0/1 state costs, exact in any order)
-    for (int r = warp; r < nr; r += nwarps) {
-        double s = 0.0;
-        for (int t = lane; t < T; t += 32) s += sstate[r * T + t];
-        s = warp_sum(s);
-        if (lane == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k0 + r)) * p.sumw] = s;
+        if (t == T - 1) p.validity[(size_t)q * p.slots + k] = hit ? 0 : 1;   // last timestep only (OptimizationTask.cpp:192-202)
+        if (hit) atomicAdd(p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw, 1.0);
     }
     tls.end();
 }
@@ -863,68 +963,68 @@ __device__ __forceinline__ const double* cost_row(const LoopParams& p, int q, in
     return (k == p.noiseless_gslot) ? p.nl_sums + (size_t)q * p.sumw : p.sums + ((size_t)q * p.gslots + k) * p.sumw;
 }
 
-__global__ void __launch_bounds__(1024)
+// grid (wblocks, D, Q), 256 threads: every CTA scans all K' rows for the min / max of its joint (cheap, redundant,
+// no exp), weighs its own 256 rollouts and leaves the per-CTA sums of the unnormalised weights in wpart; the
+// consumers (weighted_update_kernel, read-backs) divide by the sum of the partials taken in block order.
+__global__ void __launch_bounds__(256)
 rollout_weights_kernel(const __grid_constant__ LoopParams p)
 {
     __shared__ double scratch[32];
-    const int d = blockIdx.x, q = blockIdx.y;
+    const int d = blockIdx.y, q = blockIdx.z;
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 2);
     const int D = p.D, n = p.num_rollouts, tid = threadIdx.x;
     double* prob = p.prob + (size_t)q * p.gslots * D;
     double* fprob = p.fprob + (size_t)q * p.gslots * D;
     const double h = p.cost_scaling_h;
-    if (d == 0 && p.noiseless_slot >= 0) materialise_noiseless(p, q, tid, blockDim.x);
+    if (blockIdx.x == 0 && d == 0 && p.noiseless_slot >= 0) materialise_noiseless(p, q, tid, blockDim.x);
 
-    double mn = 1e300, mx = -1e300, fmn = 1e300, fmx = -1e300;
+    double mn = 1e300, mx = -1e300;
 #pragma unroll 4
     for (int k = tid; k < n; k += blockDim.x) {
         const double* s = cost_row(p, q, k);
-        const double cum = 1.0 * s[1 + D + d];
-        const double full = s[0] + s[1 + d];
+        const double cum = 1.0 * (s[0] + s[1 + d]);   // sum_t (state + control_d) as S + C_d; equals full_costs_[d]
         mn = fmin(mn, cum); mx = fmax(mx, cum);
-        fmn = fmin(fmn, full); fmx = fmax(fmx, full);
     }
     mn = block_reduce<1>(mn, scratch); mx = block_reduce<2>(mx, scratch);
-    fmn = block_reduce<1>(fmn, scratch); fmx = block_reduce<2>(fmx, scratch);
-    double den = mx - mn, fden = fmx - fmn;
+    double den = mx - mn;
     if (den < 1e-8) den = 1e-8;
-    if (fden < 1e-8) fden = 1e-8;
 
-    double psum = 0.0, fsum = 0.0;
-#pragma unroll 4
-    for (int k = tid; k < n; k += blockDim.x) {
+    double pr = 0.0;
+    const int k = blockIdx.x * blockDim.x + tid;
+    if (k < n) {
         const double* s = cost_row(p, q, k);
-        const double pr = 1.0 * exp(((-h) * (1.0 * s[1 + D + d] - mn)) / den);      // importance_weight_ = 1
-        const double fp = 1.0 * exp(((-h) * ((s[0] + s[1 + d]) - fmn)) / fden);
+        // cumulative_costs_[d] and full_costs_[d] are the same number in this build (S + C_d), hence one weight
+        pr = 1.0 * exp(((-h) * (1.0 * (s[0] + s[1 + d]) - mn)) / den);      // importance_weight_ = 1
         prob[(size_t)k * D + d] = pr;
-        fprob[(size_t)k * D + d] = fp;
-        psum += pr; fsum += fp;
+        fprob[(size_t)k * D + d] = pr;
         if (d == 0) {   // total_cost_ (:451-462)
             double cost = s[0];
             for (int dd = 0; dd < D; ++dd) cost += s[1 + dd];
             p.total_cost[(size_t)q * p.gslots + k] = cost;
         }
     }
-    psum = block_reduce<0>(psum, scratch);
-    fsum = block_reduce<0>(fsum, scratch);
-    double fnorm = 0.0;
-    for (int k = tid; k < n; k += blockDim.x) {   // each thread re-reads only what it wrote
-        prob[(size_t)k * D + d] /= psum;
-        const double f = fprob[(size_t)k * D + d] / fsum;
-        fprob[(size_t)k * D + d] = f;
-        fnorm += f;
-    }
-    fnorm = block_reduce<0>(fnorm, scratch);
-    if (tid == 0) p.fprob_sum[(size_t)q * D + d] = fnorm;
+    const double psum_blk = block_reduce<0>(pr, scratch);
+    if (tid == 0) p.wpart[((size_t)q * D + d) * p.wblocks_cap + blockIdx.x] = psum_blk;
     tls.end();
+}
+
+// sum of the weights of joint d in block order (what every consumer divides by)
+__device__ __forceinline__ double weight_sum(const LoopParams& p, int q, int d)
+{
+    const double* part = p.wpart + ((size_t)q * p.D + d) * p.wblocks_cap;
+    double s = 0.0;
+    for (int b = 0; b < p.wblocks; ++b) s += part[b];
+    return s;
 }
 
 // =====================================================================================================
 // K8: PolicyImprovement::computeParameterUpdates (PolicyImprovement.cpp:584-711): probability-weighted
-// noise sums sum_k P[k,d] * noise[k,d,t] and the noise-adaptation numerator sum_k Pfull[k,d] * (n^T R n)[k,d]
-// (the quadratic forms come from the cost kernel).  grid (chunks, D, Q); thread t streams the chunk's rollouts
-// (independent coalesced loads, unrolled); partial [Q][chunks][D][T+1] (last entry: numerator).
+// noise sums sum_k P[k,d] * noise[k,d,t], the noise-adaptation numerator sum_k Pfull[k,d] * (n^T R n)[k,d]
+// (quadratic forms from control_rows_kernel) and its denominator sum_k Pfull[k,d].  grid (chunks, D, Q); the
+// CTA first normalises the weights of its chunk (the tables keep the unnormalised weights; read-backs divide), then
+// thread t streams the chunk's noise rows with four independent accumulators.
+// partial [Q][chunks][D][T+2]: update row, numerator, denominator.
 // =====================================================================================================
 constexpr int kUpdateThreads = 128;
 __global__ void __launch_bounds__(kUpdateThreads)
@@ -937,41 +1037,51 @@ weighted_update_kernel(const __grid_constant__ LoopParams p)
     TimelineScope tls(p, 3);
     const int T = p.T, D = p.D, tid = threadIdx.x;
     const int k_begin = c * p.chunk, k_end = min(p.num_local, (c + 1) * p.chunk);
+    const int nk = k_end - k_begin;
     double* sp = smem;
     double* sq = smem + p.chunk;
+    if (tid == 0) scratch[0] = weight_sum(p, q, d);
+    __syncthreads();
+    const double psum = scratch[0];
+    __syncthreads();
+    double fsum_part = 0.0;
     for (int k = k_begin + tid; k < k_end; k += blockDim.x) {
-        double pr = 0.0, fq = 0.0;
-        if (k != p.noiseless_slot) {   // zero noise: contributes nothing (PolicyImprovement.cpp:407-410)
-            const int g = (k < p.num_gen) ? p.gen_offset + k : k;   // local slot -> slot in the rollout-indexed tables
-            pr = p.prob[((size_t)q * p.gslots + g) * D + d];
-            if (p.use_noise_adaptation)
-                fq = p.fprob[((size_t)q * p.gslots + g) * D + d] * p.sums[((size_t)q * p.gslots + g) * p.sumw + 1 + 2 * D + d];
-        }
-        sp[k - k_begin] = pr;
+        const int g = (k == p.noiseless_slot) ? p.noiseless_gslot : ((k < p.num_gen) ? p.gen_offset + k : k);
+        const size_t o = ((size_t)q * p.gslots + g) * D + d;
+        const double pr = p.prob[o] / psum;       // probabilities_[d] = p / p_sum  (:546-549); full_probabilities_ alike (:575-578)
+        // the noise-less rollout is replicated on every rank: only the first rank counts it in the denominator
+        if (!(k == p.noiseless_slot && p.gen_offset != 0)) fsum_part += pr;
+        double w = pr, fq = 0.0;
+        if (k == p.noiseless_slot) w = 0.0;       // zero noise: contributes nothing (PolicyImprovement.cpp:407-410)
+        else if (p.use_noise_adaptation) fq = pr * p.sums[((size_t)q * p.gslots + g) * p.sumw + 1 + 2 * D + d];
+        sp[k - k_begin] = w;
         sq[k - k_begin] = fq;
     }
     __syncthreads();
-    double* out = p.partial + (((size_t)q * p.nchunks + c) * D + d) * (T + 1);
+    double* out = p.partial + (((size_t)q * p.nchunks + c) * D + d) * (T + 2);
     for (int t = tid; t < T; t += blockDim.x) {
         const double* nz = p.noise + (((size_t)q * p.slots + k_begin) * D + d) * T + t;
         const size_t stride = (size_t)D * T;
-        double acc = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int k = 0;
-        const int nk = k_end - k_begin;
-        for (; k + 8 <= nk; k += 8) {
-            double v[8];
+        for (; k + 16 <= nk; k += 16) {
+            double v[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = nz[(size_t)(k + u) * stride];
+            for (int u = 0; u < 16; ++u) v[u] = nz[(size_t)(k + u) * stride];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc += v[u] * sp[k + u];
+            for (int u = 0; u < 16; u += 4) {
+                a0 += v[u] * sp[k + u]; a1 += v[u + 1] * sp[k + u + 1];
+                a2 += v[u + 2] * sp[k + u + 2]; a3 += v[u + 3] * sp[k + u + 3];
+            }
         }
-        for (; k < nk; ++k) acc += nz[(size_t)k * stride] * sp[k];
-        out[t] = acc;
+        for (; k < nk; ++k) a0 += nz[(size_t)k * stride] * sp[k];
+        out[t] = (a0 + a1) + (a2 + a3);
     }
     double numer = 0.0;
-    for (int k = tid; k < k_end - k_begin; k += blockDim.x) numer += sq[k];
+    for (int k = tid; k < nk; k += blockDim.x) numer += sq[k];
     numer = block_reduce<0>(numer, scratch);
-    if (tid == 0) out[T] = numer;
+    fsum_part = block_reduce<0>(fsum_part, scratch);
+    if (tid == 0) { out[T] = numer; out[T + 1] = fsum_part; }
     tls.end();
 }
 
@@ -982,11 +1092,11 @@ reduce_partials_kernel(const __grid_constant__ LoopParams p, int nchunks)
     const int d = blockIdx.x, q = blockIdx.y;
     if (query_frozen(p, q)) return;
     const int T = p.T, D = p.D;
-    for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
+    for (int t = threadIdx.x; t < T + 2; t += blockDim.x) {
         double s = 0.0;
 #pragma unroll 8
-        for (int c = 0; c < nchunks; ++c) s += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 1) + t];
-        p.updbuf[((size_t)q * D + d) * (T + 1) + t] = s;
+        for (int c = 0; c < nchunks; ++c) s += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 2) + t];
+        p.updbuf[((size_t)q * D + d) * (T + 2) + t] = s;
     }
 }
 
@@ -1003,13 +1113,18 @@ apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int
     TimelineScope tls(p, 4);
     const int T = p.T, D = p.D, N = p.N;
     for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
-        double u;
+        double u, denom = 1.0;
         if (from_partials) {
             u = 0.0;
 #pragma unroll 8
-            for (int c = 0; c < nchunks; ++c) u += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 1) + t];
+            for (int c = 0; c < nchunks; ++c) u += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 2) + t];
+            if (t == T) {
+                denom = 0.0;
+                for (int c = 0; c < nchunks; ++c) denom += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 2) + T + 1];
+            }
         } else {
-            u = p.updbuf[((size_t)q * D + d) * (T + 1) + t];
+            u = p.updbuf[((size_t)q * D + d) * (T + 2) + t];
+            denom = p.updbuf[((size_t)q * D + d) * (T + 2) + T + 1];
         }
         if (t < T) {
             // time-step weights and divisor are exactly 1 (PolicyImprovement.cpp:533,684-704)
@@ -1018,7 +1133,7 @@ apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int
             p.updates[((size_t)q * D + d) * T + t] = u;
             p.theta_all[((size_t)q * D + d) * N + kPad + t] += 1.0 * u;
         } else if (p.use_noise_adaptation) {
-            const double denom = p.fprob_sum[(size_t)q * D + d];
+            p.fprob_sum[(size_t)q * D + d] = denom;
             const double frob_stddev = sqrt(u / (denom * T));
             const double update_rate = 0.2;
             double sd = (1.0 - update_rate) * p.sigma[(size_t)q * D + d] + update_rate * frob_stddev;
