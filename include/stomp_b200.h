@@ -198,6 +198,15 @@ int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_
 /* sphere centres in the world frame for n joint configurations q [n][D] -> [n][S][3] */
 int stomp_b200_sphere_centres(stomp_b200_engine* e, const double* q, int32_t n, double* centres);
 
+/* ---- the state kernel (FK + sphere / SDF verdicts) is specialised at run time to the robot's STRUCTURE (axis
+ * kinds, zero masks, spheres per link) with NVRTC; numbers stay kernel parameters.  kind: 1 = specialised,
+ * 0 = the generic CUDA kernel (libnvrtc missing, or STOMP_B200_STATES=generic); note says which / why.
+ * source: the generated CUDA source for the engine's robot (needed includes the terminating NUL).
+ * codegen_selftest needs no device: it generates and NVRTC-compiles a structure that uses every branch. */
+int32_t stomp_b200_state_kernel_kind(stomp_b200_engine* e, char* note, size_t note_capacity);
+int stomp_b200_state_kernel_source(stomp_b200_engine* e, char* buffer, size_t capacity, size_t* needed);
+int stomp_b200_codegen_selftest(char* log, size_t log_capacity);
+
 /* ---- multi-GPU (shard_mode 0): one engine per rank; rank 0 makes the id, the host side broadcasts it ---- */
 #define STOMP_B200_COMM_ID_BYTES 128
 int stomp_b200_comm_unique_id(void* id_out /*[128]*/);

@@ -36,6 +36,7 @@ SYMBOLS = [
     "stomp_b200_get_tensor", "stomp_b200_evaluate_states", "stomp_b200_sphere_centres", "stomp_b200_comm_unique_id",
     "stomp_b200_comm_init", "stomp_b200_set_profiling", "stomp_b200_kernel_stats", "stomp_b200_reset_kernel_stats",
     "stomp_b200_set_timeline", "stomp_b200_get_timeline", "stomp_b200_launch_count", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
+    "stomp_b200_state_kernel_kind", "stomp_b200_state_kernel_source", "stomp_b200_codegen_selftest",
 ]
 
 
@@ -52,6 +53,14 @@ class Config(C.Structure):
         ("per_timestep_minmax", C.c_int32), ("device", C.c_int32), ("world_size", C.c_int32), ("rank", C.c_int32),
         ("shard_mode", C.c_int32), ("keep_debug_tensors", C.c_int32), ("seed", C.c_uint64),
     ]
+
+
+def codegen_selftest():
+    """Generates the specialised state kernel for a structure that uses every branch and compiles it with NVRTC
+    for sm_100a (no device needed).  Returns (status, log)."""
+    log = C.create_string_buffer(1 << 16)
+    rc = lib().stomp_b200_codegen_selftest(log, len(log))
+    return rc, log.value.decode()
 
 
 class StompB200Error(RuntimeError):
@@ -105,6 +114,10 @@ def lib():
         L.stomp_b200_set_timeline.argtypes = [vp, C.c_int32]
         L.stomp_b200_get_timeline.argtypes = [vp, C.c_int32, dp, ip]
         L.stomp_b200_launch_count.argtypes = [vp]
+        L.stomp_b200_state_kernel_kind.argtypes = [vp, C.c_char_p, C.c_size_t]
+        L.stomp_b200_state_kernel_kind.restype = C.c_int32
+        L.stomp_b200_state_kernel_source.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.stomp_b200_codegen_selftest.argtypes = [C.c_char_p, C.c_size_t]
         L.stomp_b200_launch_count.restype = C.c_int64
         L.stomp_b200_timer_begin.argtypes = [vp]
         L.stomp_b200_timer_end.argtypes = [vp, dp]
@@ -376,6 +389,21 @@ class Engine:
 
     def launch_count(self):
         return lib().stomp_b200_launch_count(self.h)
+
+    def state_kernel_kind(self):
+        """("specialised" | "generic", note): which state kernel the engine launches for its robot (state_codegen.hpp)."""
+        note = C.create_string_buffer(4096)
+        rc = lib().stomp_b200_state_kernel_kind(self.h, note, len(note))
+        if rc < 0:
+            self._check(rc, "stomp_b200_state_kernel_kind")
+        return ("specialised" if rc == 1 else "generic"), note.value.decode()
+
+    def state_kernel_source(self):
+        need = C.c_size_t(0)
+        self._check(lib().stomp_b200_state_kernel_source(self.h, None, 0, C.byref(need)), "stomp_b200_state_kernel_source")
+        buf = C.create_string_buffer(need.value)
+        self._check(lib().stomp_b200_state_kernel_source(self.h, buf, need.value, None), "stomp_b200_state_kernel_source")
+        return buf.value.decode()
 
     def timer_begin(self):
         self._check(lib().stomp_b200_timer_begin(self.h), "stomp_b200_timer_begin")

@@ -23,6 +23,7 @@
 #include "../../include/stomp_b200.h"
 #include "../host/policy_core.hpp"
 #include "kernels.cuh"
+#include "state_codegen.hpp"
 
 using namespace stomp_b200;
 
@@ -120,6 +121,12 @@ struct stomp_b200_engine {
     int num_rollouts = 0;           // num_rollouts_ after the previous iteration (global)
     int last_gen = 0, last_local = 0, last_noiseless_slot = -1;
     bool noiseless_valid = false, adapted_valid = false;
+    bool edge_dirty = true;         // edge_cost has to be recomputed (the policy was uploaded since)
+    // state kernel specialised to the robot structure (state_codegen.hpp); resolved at the first iteration after
+    // the chain / spheres / SDF changed
+    const codegen::SpecialisedKernel* spec = nullptr;
+    bool spec_resolved = false;
+    std::string spec_note;          // why the generic kernel is in use, when it is
 
     // pinned host mirrors of the per-query scalars
     double* h_cost = nullptr; uint8_t* h_valid = nullptr; int32_t* h_stop = nullptr; int32_t* h_iters = nullptr;
@@ -262,6 +269,20 @@ int launch_sample(stomp_b200_engine* e, const LoopParams& lp)
 enum NoiseMode { kNoisePhilox = 0, kNoiseUnit = 1, kNoiseEpsilon = 2 };
 
 // one Stomp::runSingleIteration for all local queries, queued on the stream (no host synchronisation)
+// picks the state kernel once per robot description: the run-time specialised one, or the generic one when
+// NVRTC is not available / STOMP_B200_STATES=generic (both are CUDA kernels; spec_note says which and why)
+void resolve_state_kernel(stomp_b200_engine* e)
+{
+    if (e->spec_resolved) return;
+    e->spec_resolved = true;
+    e->spec = nullptr;
+    const char* mode = std::getenv("STOMP_B200_STATES");
+    if (mode && std::strcmp(mode, "generic") == 0) { e->spec_note = "STOMP_B200_STATES=generic"; return; }
+    std::string err;
+    e->spec = codegen::specialised_state_kernel(e->robot, e->sdf.wide_index != 0, err);
+    e->spec_note = e->spec ? std::string() : err;
+}
+
 int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop)
 {
     const stomp_b200_config& c = e->cfg;
@@ -341,7 +362,25 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     {
         const int rows = gen_local * e->D;
         Scope sc(e, STOMP_B200_KERNEL_COST);
-        control_rows_kernel<<<dim3((rows * kRowLanes + 255) / 256, e->Q), 256, 0, e->stream>>>(lp);
+        if (e->edge_dirty && lp.num_rules == 1) {   // padding-only rows of the control costs: constants of a solve
+            edge_rows_kernel<<<e->Q, 64, 0, e->stream>>>(lp);
+            e->launch_count++;
+            if (int rc = check_launch(e, "edge_rows_kernel")) return rc;
+            e->edge_dirty = false;
+        }
+        // one rule with Toeplitz interior rows, Toeplitz R, even T and 16-byte aligned rows: the register-window kernel
+        const bool fast = lp.st_n > 0 && lp.num_rules == 1 && (lp.r_toeplitz || !lp.use_noise_adaptation) && e->T % 2 == 0 && e->N >= 12;
+        if (fast) {
+            bool taps5 = true;
+            for (int j = 0; j < lp.st_n; ++j) taps5 = taps5 && lp.st_off[j] > -3 && lp.st_off[j] < 3;
+            const bool rb4 = lp.rband_halfwidth <= 4;
+            const dim3 grid((rows + 7) / 8, e->Q);
+            if (taps5 && rb4) control_rows_fast_kernel<true, true><<<grid, 256, 0, e->stream>>>(lp);
+            else control_rows_fast_kernel<false, false><<<grid, 256, 0, e->stream>>>(lp);
+        } else {
+            const size_t row_smem = sizeof(double) * (size_t)kRowWarps * (control_row_x_stride(e->N) + control_row_n_stride(e->T));
+            control_rows_kernel<<<dim3((rows + kRowWarps - 1) / kRowWarps, e->Q), kRowWarps * 32, row_smem, e->stream>>>(lp);
+        }
         if (int rc = check_launch(e, "control_rows_kernel")) return rc;
         if (lp.control_costs) {
             fold_control_costs_kernel<<<dim3((rows + 127) / 128, e->Q), 128, 0, e->stream>>>(lp);
@@ -352,7 +391,17 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         const int states = gen_local * e->T;
         dim3 grid((states + 255) / 256, e->Q);
         Scope sc(e, STOMP_B200_KERNEL_COST);
-        if (e->robot.simple_chain) rollout_states_kernel<true><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
+        resolve_state_kernel(e);
+        if (e->spec) {
+            StateKernelArgs a;
+            a.rollouts = lp.rollouts; a.state_costs = lp.state_costs; a.verdicts = lp.verdicts; a.validity = lp.validity;
+            a.sums = lp.sums; a.stop = lp.stop; a.tile_counter = lp.tile_counter;
+            a.timeline = lp.timeline ? lp.timeline + 2 * 1 : nullptr;
+            a.T = lp.T; a.D = lp.D; a.slots = lp.slots; a.gslots = lp.gslots; a.sumw = lp.sumw; a.num_gen = lp.num_gen;
+            a.gen_offset = lp.gen_offset; a.honour_stop = lp.honour_stop; a.debug_skip = lp.debug_skip; a.pad_ = 0;
+            void* args[] = {&a, &e->robot, &e->sdf};
+            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, grid, dim3(256), args, 0, e->stream));
+        } else if (e->robot.simple_chain) rollout_states_kernel<true><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
         else rollout_states_kernel<false><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
         if (int rc = check_launch(e, "rollout_states_kernel")) return rc;
     }
@@ -629,6 +678,7 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.partial, Q * e->max_chunks * D * (T + 2)));
     b.wblocks_cap = (int)((GS + 255) / 256);
     CREATE_TRY(dev_alloc(e, &b.wpart, Q * D * b.wblocks_cap));
+    CREATE_TRY(dev_alloc(e, &b.edge_cost, Q * D * 6));
     CREATE_TRY(dev_alloc(e, &b.tile_counter, 4));
     CREATE_TRY(dev_alloc(e, &e->d_timeline, (size_t)kTimelineRing * kTimelineKernels * 2));
     b.world_size = world;
@@ -649,8 +699,10 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
         b.st_n = 0;
         if (b.num_rules == 1 && e->N >= 8) {
             const double* row = band.data() + ((size_t)b.rule_id[0] * N + 3) * 7;   // any interior row
-            for (int o = 0; o < 7; ++o)
+            for (int o = 0; o < 7; ++o) {
+                b.st_dense[o] = row[o];
                 if (row[o] != 0.0) { b.st_off[b.st_n] = o - 3; b.st_coef[b.st_n] = row[o]; b.st_n++; }
+            }
         }
         CREATE_TRY(dev_alloc(e, &tmp, band.size())); b.diff_band = tmp;
         CREATE_CUDA(cudaMemcpyAsync(tmp, band.data(), sizeof(double) * band.size(), cudaMemcpyHostToDevice, e->stream));
@@ -762,6 +814,7 @@ int stomp_b200_set_chain(stomp_b200_engine* e, int32_t num_joints, const double*
     for (int d = 0; d < num_joints; ++d)
         if (r.joint[d].prismatic || !r.joint[d].fixed_rot_identity || r.joint[d].axis_kind == kAxisGeneral) r.simple_chain = 0;
     e->have_chain = true;
+    e->spec_resolved = false;
     return STOMP_B200_OK;
 }
 
@@ -786,6 +839,7 @@ int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int3
     }
     for (int d = 1; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = std::max(r.sphere_begin[d], r.sphere_begin[d - 1]);
     e->have_spheres = true;
+    e->spec_resolved = false;
     return STOMP_B200_OK;
 }
 
@@ -805,6 +859,7 @@ int stomp_b200_set_sdf(stomp_b200_engine* e, const int32_t dims[3], const double
     e->sdf.offx = -(origin[0] * e->sdf.inv_h); e->sdf.offy = -(origin[1] * e->sdf.inv_h); e->sdf.offz = -(origin[2] * e->sdf.inv_h);
     e->sdf.wide_index = count >= ((size_t)1 << 31) ? 1 : 0;
     e->have_sdf = true;
+    e->spec_resolved = false;
     return STOMP_B200_OK;
 }
 
@@ -850,6 +905,7 @@ int stomp_b200_set_policy(stomp_b200_engine* e, int32_t query, const double* par
     CUDA_TRY(e, cudaMemcpy(e->base.theta_all + (size_t)query * e->D * e->N, parameters_all, sizeof(double) * e->D * e->N, cudaMemcpyHostToDevice));
     CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.mincc) + (size_t)query * e->D * e->T, min_control_cost, sizeof(double) * e->D * e->T, cudaMemcpyHostToDevice));
     e->have_policy[query] = 1;
+    e->edge_dirty = true;
     return STOMP_B200_OK;
 }
 
@@ -893,6 +949,7 @@ int stomp_b200_begin_solve(stomp_b200_engine* e)
     reset_solve_state_kernel<<<(e->Q + 127) / 128, 128, 0, e->stream>>>(e->base);
     e->launch_count++;
     if (int rc = check_launch(e, "reset_solve_state_kernel")) return rc;
+    e->edge_dirty = true;
     e->solving = true;
     return STOMP_B200_OK;
 }
@@ -1251,3 +1308,65 @@ int stomp_b200_synchronize(stomp_b200_engine* e)
 }
 
 }  // extern "C"
+
+// ---- the run-time specialised state kernel (state_codegen.hpp) ------------------------------------------
+int32_t stomp_b200_state_kernel_kind(stomp_b200_engine* e, char* note, size_t note_capacity)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!e->have_chain || !e->have_spheres || !e->have_sdf) return fail(e, STOMP_B200_ERR_NOT_READY, "chain, spheres and SDF come first");
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return fail(e, STOMP_B200_ERR_CUDA, "cudaSetDevice");
+    resolve_state_kernel(e);
+    if (note && note_capacity) {
+        std::string text = e->spec ? ("specialised, " + std::to_string(e->spec->registers) + " registers") : ("generic: " + e->spec_note);
+        std::snprintf(note, note_capacity, "%s", text.c_str());
+    }
+    return e->spec ? 1 : 0;
+}
+
+int stomp_b200_state_kernel_source(stomp_b200_engine* e, char* buffer, size_t capacity, size_t* needed)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!e->have_chain || !e->have_spheres) return fail(e, STOMP_B200_ERR_NOT_READY, "chain and spheres come first");
+    const std::string src = codegen::generate_state_kernel_source(e->robot, e->sdf.wide_index != 0);
+    if (needed) *needed = src.size() + 1;
+    if (buffer && capacity) std::snprintf(buffer, capacity, "%s", src.c_str());
+    return STOMP_B200_OK;
+}
+
+// Needs no device: generates the kernel for a synthetic structure that exercises every template branch (all axis
+// kinds, fixed rotation, prismatic joint, chain restart, every zero mask, wide index) and compiles it to an
+// sm_100a cubin with NVRTC.  The "does the generated code build" check of __graft_entry__.build().
+int stomp_b200_codegen_selftest(char* log, size_t log_capacity)
+{
+    RobotParams r;
+    std::memset(&r, 0, sizeof r);
+    r.num_joints = 8;
+    const int kinds[8] = {kAxisZ, kAxisY, kAxisX, kAxisNegX, kAxisNegY, kAxisNegZ, kAxisGeneral, kAxisZ};
+    int sph = 0;
+    for (int d = 0; d < 8; ++d) {
+        JointParams& j = r.joint[d];
+        j.axis_kind = kinds[d];
+        j.o_mask = d & 7;
+        j.fixed_rot_identity = (d == 3) ? 0 : 1;
+        j.prismatic = (d == 7) ? 1 : 0;
+        j.parent = (d == 0 || d == 4) ? -1 : d - 1;
+        r.sphere_begin[d] = sph;
+        for (int k = 0; k < (d % 3) + 1; ++k) r.sphere[sph++].mask = (d + k) & 7;
+    }
+    for (int d = 8; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = sph;
+    r.num_spheres = sph;
+    std::string all_log, err;
+    int rc = STOMP_B200_OK;
+    for (int wide = 0; wide < 2 && rc == STOMP_B200_OK; ++wide) {
+        std::vector<char> cubin;
+        std::string clog;
+        if (!codegen::compile_to_cubin(codegen::generate_state_kernel_source(r, wide != 0), cubin, clog, err)) {
+            all_log += err;
+            rc = STOMP_B200_ERR_CUDA;
+        } else {
+            all_log += "ok: " + std::to_string(cubin.size()) + " byte cubin (" + codegen::cache().nvrtc.where + ") " + clog + "\n";
+        }
+    }
+    if (log && log_capacity) std::snprintf(log, log_capacity, "%s", all_log.c_str());
+    return rc;
+}

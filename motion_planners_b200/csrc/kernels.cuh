@@ -62,6 +62,7 @@ struct LoopParams {
     double* updbuf;           // [Q][D][T+2]  update row, numerator and denominator of the noise adaptation (after the all-reduce)
     double* partial;          // [Q][chunks][D][T+2] per-chunk partial sums of weighted_update_kernel
     double* wpart;            // [Q][D][wblocks_cap] per-CTA sums of the unnormalised weights (rollout_weights_kernel)
+    double* edge_cost;        // [Q][D][6] control costs of the band-table rows (edge_rows_kernel)
     int32_t wblocks, wblocks_cap;
     int32_t nchunks, chunk;
     double* updates;          // [Q][D][T]    last applied update (read-back)
@@ -91,6 +92,7 @@ struct LoopParams {
     int32_t st_n;
     int32_t st_off[7];
     double st_coef[7];
+    double st_dense[7];       // the same taps as a dense row, offsets -3 .. +3 (zeros included)
 };
 
 __device__ __forceinline__ bool query_frozen(const LoopParams& p, int q) { return p.honour_stop && p.stop[q] != 0; }
@@ -622,112 +624,241 @@ __device__ __forceinline__ double noise_quadratic_form(const LoopParams& p, cons
 
 // K5 + K6: PolicyImprovement::computeRolloutControlCosts / computeRolloutCumulativeCosts
 // (PolicyImprovement.cpp:442-495) and the n^T R n of the noise adaptation (:656-663) for the generated rollouts.
-// EIGHT lanes per (rollout, joint) row, each walking one eighth of the padded trajectory x = theta + noise
-// sequentially with the 7-wide stencil window (and the 7-wide noise window) in registers: no shared memory, no
-// barriers, one 3-step shuffle reduction per row.  FP64 dependent-issue latency is long on this part, so the
-// kernel is built from many short independent chains (8 x rows threads) rather than few long ones.
+// One WARP per (rollout, joint) row.  The warp stages the padded trajectory x = theta + noise and the noise in
+// its own shared-memory rows with coalesced loads (consecutive lanes, consecutive time steps), then every lane
+// evaluates four consecutive elements from one 10-wide window read as five 16-byte loads — 2.5 KB of shared
+// memory traffic per row instead of 7 KB for per-element windows, no block barrier, no address-divergent
+// global load (an uncoalesced version of this loop saturates the L1 pipe, a shuffle version the SHFL pipe).
 // The row also zeroes S_k (d == 0) for the state kernel that follows.
-constexpr int kRowLanes = 8;
-__global__ void __launch_bounds__(256)
+constexpr int kRowWarps = 8;
+__host__ __device__ inline int control_row_x_stride(int N) { return 4 + ((N + 127) / 128) * 128 + 16; }   // even: every warp row stays 16-byte aligned
+__host__ __device__ inline int control_row_n_stride(int T) { return ((T + 127) / 128) * 128 + 16; }
+
+__global__ void __launch_bounds__(kRowWarps * 32)
 control_rows_kernel(const __grid_constant__ LoopParams p)
 {
+    extern __shared__ __align__(16) double smem[];
     const int q = blockIdx.y;
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 6);
     const int T = p.T, D = p.D, N = p.N;
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = gtid / kRowLanes, seg = gtid & (kRowLanes - 1);
-    const bool active = row < p.num_gen * D && !(p.debug_skip & 2);
-    double C_part = 0.0, quad = 0.0;
-    int k = 0, d = 0;
-    if (active) {
-        k = row / D; d = row - k * D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int XS = control_row_x_stride(N), NS = control_row_n_stride(T);
+    double* xs = smem + (size_t)warp * (XS + NS);   // xs[3 + i] = x_all[i]; zeros on both sides
+    double* ns = xs + XS;                           // ns[t] = noise[t]; zeros beyond T
+    const int row = blockIdx.x * kRowWarps + warp;
+    if (row < p.num_gen * D && !(p.debug_skip & 2)) {      // warp-uniform
+        const int k = row / D, d = row - k * D;
         const double* nz = p.noise + (((size_t)q * p.slots + k) * D + d) * T;
         const double* th = p.theta_all + ((size_t)q * D + d) * N;
         double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
         const double dtw = p.dt * p.control_cost_weight;
         const bool fast = p.st_n > 0;
-        double c[7];
+        double c7[7];
 #pragma unroll
         for (int o = 0; o < 7; ++o) {
-            c[o] = 0.0;
+            c7[o] = 0.0;
             for (int j = 0; j < p.st_n; ++j)
-                if (p.st_off[j] + 3 == o) c[o] = p.st_coef[j];
+                if (p.st_off[j] + 3 == o) c7[o] = p.st_coef[j];
         }
         const double sqrt_w = p.rule_sqrt_w[0];
-        auto xall = [&](int j) -> double {   // columns outside [0, N) are never referenced with a non-zero coefficient
-            if (j < 0 || j >= N) return 0.0;
-            return (j >= kPad && j < kPad + T) ? th[j] + nz[j - kPad] : th[j];
-        };
-        // ---- control costs of rows [i0, i1) ----
-        const int len = (N + kRowLanes - 1) / kRowLanes;
-        const int i0 = seg * len, i1 = min(N, i0 + len);
-        double w[7];   // w[o] = x_all[i - 3 + o]
+        // ---- stage ----
+        for (int i = lane; i < XS; i += 32) {
+            const int j = i - 3;
+            double v = 0.0;
+            if (j >= 0 && j < N) {
+                v = th[j];
+                if (j >= kPad && j < kPad + T) v = v + nz[j - kPad];
+            }
+            xs[i] = v;
+        }
+        for (int t = lane; t < NS; t += 32) ns[t] = (t < T) ? nz[t] : 0.0;
+        __syncwarp();
+        // ---- control costs: lane handles elements i0 .. i0 + 3 of every 128-wide pass ----
+        double C_part = 0.0, quad = 0.0;
+        for (int base = 0; base < N; base += 128) {
+            const int i0 = base + 4 * lane;
+            double w[10];   // w[j] = x_all[i0 - 3 + j]
+            const double2* src = reinterpret_cast<const double2*>(xs + i0);
 #pragma unroll
-        for (int o = 0; o < 7; ++o) w[o] = xall(i0 - 3 + o);
-        for (int i = i0; i < i1; ++i) {
-            double cost;
-            if (fast && i >= 3 && i < N - 3) {
-                double s = 0.0;
+            for (int j = 0; j < 5; ++j) { const double2 v = src[j]; w[2 * j] = v.x; w[2 * j + 1] = v.y; }
 #pragma unroll
-                for (int o = 0; o < 7; ++o) s += c[o] * w[o];   // mul then add in column order: the reference's arithmetic
-                const double Ax = s * sqrt_w;
-                cost = dtw * (Ax * Ax);
-            } else {
-                cost = 0.0;
-                for (int r = 0; r < p.num_rules; ++r) {
-                    const double* band = p.diff_band + ((size_t)p.rule_id[r] * N + i) * 7;
-                    double s = 0.0;
+            for (int e = 0; e < 4; ++e) {
+                const int i = i0 + e;
+                if (i < N) {
+                    double cost;
+                    if (fast && i >= 3 && i < N - 3) {
+                        double sacc = 0.0;
 #pragma unroll
-                    for (int o = 0; o < 7; ++o)
-                        if (i - 3 + o >= 0 && i - 3 + o < N) s += __ldg(band + o) * w[o];
-                    const double Ax = s * p.rule_sqrt_w[r];
-                    cost += dtw * (Ax * Ax);
+                        for (int o = 0; o < 7; ++o) sacc += c7[o] * w[e + o];   // mul then add in column order: the reference's arithmetic
+                        const double Ax = sacc * sqrt_w;
+                        cost = dtw * (Ax * Ax);
+                    } else {
+                        cost = 0.0;
+                        for (int r = 0; r < p.num_rules; ++r) {
+                            const double* band = p.diff_band + ((size_t)p.rule_id[r] * N + i) * 7;
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int o = 0; o < 7; ++o)
+                                if (i - 3 + o >= 0 && i - 3 + o < N) sacc += __ldg(band + o) * w[e + o];
+                            const double Ax = sacc * p.rule_sqrt_w[r];
+                            cost += dtw * (Ax * Ax);
+                        }
+                    }
+                    C_part += cost;
+                    // per-timestep layout for read-backs; fold_control_costs_kernel adds the padding rows in the reference's order
+                    if (cc_out && i >= kPad && i < kPad + T) cc_out[i - kPad] = cost;
                 }
             }
-            C_part += cost;
-            // per-timestep layout for read-backs; fold_control_costs_kernel adds the padding rows in the reference's order
-            if (cc_out && i >= kPad && i < kPad + T) cc_out[i - kPad] = cost;
-#pragma unroll
-            for (int o = 0; o < 6; ++o) w[o] = w[o + 1];
-            w[6] = xall(i + 4);
         }
-        // ---- n^T R n over t in [t0, t1): sum_t n_t (R_tt n_t + 2 sum_{o>0} R_{t,t+o} n_{t+o}) ----
+        // ---- n^T R n: sum_t n_t (R_tt n_t + 2 sum_{o>0} R_{t,t+o} n_{t+o}); the noise is zero outside [0, T) ----
         if (p.use_noise_adaptation) {
-            const int tlen = (T + kRowLanes - 1) / kRowLanes;
-            const int t0 = seg * tlen, t1 = min(T, t0 + tlen);
-            double r[kRBand + 1], m[kRBand + 1];   // m[o] = noise[t + o]
+            for (int base = 0; base < T; base += 128) {
+                const int t0 = base + 4 * lane;
+                double m[10];   // m[j] = noise[t0 + j]
+                const double2* src = reinterpret_cast<const double2*>(ns + t0);
 #pragma unroll
-            for (int o = 0; o <= kRBand; ++o) { r[o] = p.r_diag[o]; m[o] = (t0 + o < T) ? nz[t0 + o] : 0.0; }
-            for (int t = t0; t < t1; ++t) {
-                double s = 0.0;
-                if (p.r_toeplitz) {
+                for (int j = 0; j < 5; ++j) { const double2 v = src[j]; m[2 * j] = v.x; m[2 * j + 1] = v.y; }
 #pragma unroll
-                    for (int o = 1; o <= kRBand; ++o) s += r[o] * m[o];
-                    quad += m[0] * (r[0] * m[0] + 2.0 * s);
-                } else {
-                    const double* rb = p.Rband + (size_t)t * (2 * kRBand + 1) + kRBand;
+                for (int e = 0; e < 4; ++e) {
+                    const int t = t0 + e;
+                    if (t < T) {
+                        double sacc = 0.0;
+                        if (p.r_toeplitz) {
 #pragma unroll
-                    for (int o = 1; o <= kRBand; ++o) s += __ldg(rb + o) * m[o];
-                    quad += m[0] * (__ldg(rb) * m[0] + 2.0 * s);
+                            for (int o = 1; o <= kRBand; ++o) sacc += p.r_diag[o] * m[e + o];
+                            quad += m[e] * (p.r_diag[0] * m[e] + 2.0 * sacc);
+                        } else {
+                            const double* rb = p.Rband + (size_t)t * (2 * kRBand + 1) + kRBand;
+#pragma unroll
+                            for (int o = 1; o <= kRBand; ++o) sacc += __ldg(rb + o) * m[e + o];
+                            quad += m[e] * (__ldg(rb) * m[e] + 2.0 * sacc);
+                        }
+                    }
                 }
-#pragma unroll
-                for (int o = 0; o < kRBand; ++o) m[o] = m[o + 1];
-                m[kRBand] = (t + kRBand + 1 < T) ? nz[t + kRBand + 1] : 0.0;
             }
         }
+        C_part = warp_sum(C_part);
+        quad = warp_sum(quad);
+        if (lane == 0) {
+            double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
+            srow[1 + d] = C_part;
+            srow[1 + 2 * D + d] = quad;
+            if (d == 0) srow[0] = 0.0;        // S_k is accumulated by rollout_states_kernel
+        }
     }
-    // the 8 lanes of a row are adjacent: fixed-order butterfly
+    tls.end();
+}
+
+// costs of the band-table rows i in {0, 1, 2, N-3, N-2, N-1} of the single active rule for every (query, joint):
+// they read x_all[0..5] / x_all[N-6..N-1] only, i.e. the padding, which a solve never changes
+// (CovariantMovementPrimitive::updateParameters touches the free block only, CovariantMovementPrimitive.cpp:476-479).
+__global__ void edge_rows_kernel(const __grid_constant__ LoopParams p)
+{
+    const int q = blockIdx.x, N = p.N;
+    for (int e = threadIdx.x; e < p.D * 6; e += blockDim.x) {
+        const int d = e / 6, r = e - d * 6;
+        const int i = r < 3 ? r : N - 6 + r;
+        const double* th = p.theta_all + ((size_t)q * p.D + d) * N;
+        const double* band = p.diff_band + ((size_t)p.rule_id[0] * N + i) * 7;
+        double sacc = 0.0;
+        for (int o = 0; o < 7; ++o) {
+            const int j = i - 3 + o;
+            if (j >= 0 && j < N) sacc += band[o] * th[j];
+        }
+        const double Ax = sacc * p.rule_sqrt_w[0];
+        p.edge_cost[(size_t)q * p.D * 6 + e] = (p.dt * p.control_cost_weight) * (Ax * Ax);
+    }
+}
+
+// The same rows for the common shape — one active differentiation rule (interior rows all carry the same 7
+// taps), Toeplitz R, even T — without shared memory: lane l of the row's warp owns the padded indices
+// i0 .. i0+3 (i0 = 4l) and loads the 12-wide ALIGNED windows theta_all[i0-4 .. i0+7] and noise[i0-10 .. i0+1]
+// as six 16-byte loads each (a 16-byte pair is inside or outside the row as a whole, because T, N and
+// TRAJECTORY_PADDING are even).  Everything a lane needs — the stencil windows of its four elements and the
+// noise windows of its four n^T R n terms — is in those registers, so the row costs ~330 warp instructions
+// instead of ~1300.  Rows 0..2 and N-3..N-1 (band-table rows) only touch the fixed padding; six lanes
+// evaluate them from the table after the main pass.
+// kTaps5: taps -3 and +3 are zero (the acceleration rule).  kRb4: R[t][t+5] = R[t][t+6] = 0 (follows from it).
+template <bool kTaps5, bool kRb4>
+__global__ void __launch_bounds__(256, 4)
+control_rows_fast_kernel(const __grid_constant__ LoopParams p)
+{
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 6);
+    const int T = p.T, D = p.D, N = p.N;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row < p.num_gen * D && !(p.debug_skip & 2)) {      // warp-uniform
+        const int k = row / D, d = row - k * D;
+        const double* nz = p.noise + (((size_t)q * p.slots + k) * D + d) * T;
+        const double* th = p.theta_all + ((size_t)q * D + d) * N;
+        double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
+        const double dtw = p.dt * p.control_cost_weight;
+        const double sqrt_w = p.rule_sqrt_w[0];
+        constexpr int kNoisePairs = kRb4 ? 6 : 7;
+        constexpr int kBand = kRb4 ? 4 : kRBand;
+        double C_part = 0.0, quad = 0.0;
+        // band-table rows 0..2 and N-3..N-1 only see the fixed padding: their costs are per (query, joint) constants
+        // of the solve (edge_rows_kernel); six lanes pick them up
+        const double edge = (lane < 6) ? p.edge_cost[((size_t)q * D + d) * 6 + lane] : 0.0;
+        for (int base = 0; base < N; base += 128) {
+            const int i0 = base + 4 * lane;
+            if (i0 >= N) continue;
+            double W[12];             // W[j] = theta_all[i0 - 4 + j], then x_all
+            double M[2 * kNoisePairs];   // M[j] = noise[i0 - 10 + j], zero outside [0, T)
 #pragma unroll
-    for (int o = kRowLanes / 2; o > 0; o >>= 1) {
-        C_part += __shfl_xor_sync(0xffffffffu, C_part, o);
-        quad += __shfl_xor_sync(0xffffffffu, quad, o);
-    }
-    if (active && seg == 0) {
-        double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
-        srow[1 + d] = C_part;
-        srow[1 + 2 * D + d] = quad;
-        if (d == 0) srow[0] = 0.0;        // S_k is accumulated by rollout_states_kernel
+            for (int j = 0; j < 6; ++j) {
+                const int idx = i0 - 4 + 2 * j;
+                double2 v = make_double2(0.0, 0.0);
+                if (idx >= 0 && idx < N) v = *reinterpret_cast<const double2*>(th + idx);
+                W[2 * j] = v.x; W[2 * j + 1] = v.y;
+            }
+#pragma unroll
+            for (int j = 0; j < kNoisePairs; ++j) {
+                const int idx = i0 - 10 + 2 * j;
+                double2 v = make_double2(0.0, 0.0);
+                if (idx >= 0 && idx < T) v = *reinterpret_cast<const double2*>(nz + idx);
+                M[2 * j] = v.x; M[2 * j + 1] = v.y;
+            }
+            // x_all = theta_all + noise on the free block (adding the zero outside it leaves theta_all)
+#pragma unroll
+            for (int j = 0; j < 12; ++j) W[j] = W[j] + M[j];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = i0 + e;
+                double sacc = 0.0;
+#pragma unroll
+                for (int o = kTaps5 ? 1 : 0; o < (kTaps5 ? 6 : 7); ++o) sacc += p.st_dense[o] * W[e + o + 1];   // mul then add in column order: the reference's arithmetic
+                const double Ax = sacc * sqrt_w;
+                const double cost = dtw * (Ax * Ax);
+                if (i >= 3 && i < N - 3) {
+                    C_part += cost;
+                    // per-timestep layout for read-backs; fold_control_costs_kernel adds the padding rows in the reference's order
+                    if (cc_out && i >= kPad && i < kPad + T) cc_out[i - kPad] = cost;
+                }
+            }
+            // n^T R n terms of t = i - kPad: n_t (R_tt n_t + 2 sum_{o>0} R_{t,t+o} n_{t+o}), n_t = M[e + 4]
+            if (p.use_noise_adaptation) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int o = 1; o <= kBand; ++o) sacc += p.r_diag[o] * M[e + 4 + o];
+                    quad += M[e + 4] * (p.r_diag[0] * M[e + 4] + 2.0 * sacc);   // zero noise outside [0, T): no guard needed
+                }
+            }
+        }
+        C_part += edge;
+        C_part = warp_sum(C_part);
+        quad = warp_sum(quad);
+        if (lane == 0) {
+            double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
+            srow[1 + d] = C_part;
+            srow[1 + 2 * D + d] = quad;
+            if (d == 0) srow[0] = 0.0;        // S_k is accumulated by rollout_states_kernel
+        }
     }
     tls.end();
 }
@@ -1112,19 +1243,29 @@ apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 4);
     const int T = p.T, D = p.D, N = p.N;
+    __shared__ double s_denom;
+    for (int t = threadIdx.x; t < T + 2; t += blockDim.x) {   // entry T + 1: denominator of the noise adaptation
+        if (t != T + 1) continue;
+        double v;
+        if (from_partials) {
+            v = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < nchunks; ++c) v += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 2) + t];
+        } else {
+            v = p.updbuf[((size_t)q * D + d) * (T + 2) + t];
+        }
+        s_denom = v;
+    }
+    __syncthreads();
+    const double denom = s_denom;
     for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
-        double u, denom = 1.0;
+        double u;
         if (from_partials) {
             u = 0.0;
 #pragma unroll 8
             for (int c = 0; c < nchunks; ++c) u += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 2) + t];
-            if (t == T) {
-                denom = 0.0;
-                for (int c = 0; c < nchunks; ++c) denom += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 2) + T + 1];
-            }
         } else {
             u = p.updbuf[((size_t)q * D + d) * (T + 2) + t];
-            denom = p.updbuf[((size_t)q * D + d) * (T + 2) + T + 1];
         }
         if (t < T) {
             // time-step weights and divisor are exactly 1 (PolicyImprovement.cpp:533,684-704)

@@ -10,9 +10,18 @@
 // them.  A CPU that issues the same sequence gets bit-identical sphere centres, hence bit-identical
 // collision verdicts.
 #pragma once
+// This header is also the one in-memory header of the run-time specialised state kernel (state_codegen.hpp hands
+// its text to NVRTC with -DSTOMP_B200_NVRTC and the two capacity macros): no other include may be added below.
+#ifdef STOMP_B200_NVRTC
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef unsigned char uint8_t;
+typedef unsigned long long uint64_t;
+#else
 #include <cstdint>
 
 #include "../../include/stomp_b200.h"
+#endif
 
 namespace stomp_b200 {
 
@@ -63,28 +72,45 @@ struct SdfParams {
 // Deterministic sin/cos (also run on the host for the fixed rpy rotations of stomp_b200_set_chain, so
 // that the whole FK is one arithmetic): 3-term Cody-Waite reduction by pi/2, then the degree-13 / degree-14 minimax
 // polynomials on [-pi/4, pi/4] (coefficients of Sun's fdlibm kernels; mathematical constants).
+// On the device the constants come from a __constant__ table: a constant-bank operand costs no instruction,
+// while a 64-bit literal is materialised with two UMOVs every time the compiler runs out of uniform registers.
+#define STOMP_B200_SINCOS_TABLE                                                                                  \
+    6.36619772367581382433e-01, 1.57079632673412561417e+00, 6.07710050630396597660e-11, 2.02226624871116645580e-21, \
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06, -1.98412698298579493134e-04, \
+    8.33333333332248946124e-03, -1.66666666666666324348e-01, -1.13596475577881948265e-11, 2.08757232129817482790e-09, \
+    -2.75573143513906633035e-07, 2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02
+__constant__ double kSinCosTable[16] = {STOMP_B200_SINCOS_TABLE};
+#ifndef STOMP_B200_NVRTC
+static const double kSinCosTableHost[16] = {STOMP_B200_SINCOS_TABLE};
+#endif
+#ifdef __CUDA_ARCH__
+#define STOMP_B200_SC(i) kSinCosTable[i]
+#else
+#define STOMP_B200_SC(i) kSinCosTableHost[i]
+#endif
+
 __host__ __device__ __forceinline__ void det_sincos(double x, double& s_out, double& c_out)
 {
-    const double k = rint(x * 6.36619772367581382433e-01);
+    const double k = rint(x * STOMP_B200_SC(0));
     const double nk = -k;
-    double r = fma(nk, 1.57079632673412561417e+00, x);
-    r = fma(nk, 6.07710050630396597660e-11, r);
-    r = fma(nk, 2.02226624871116645580e-21, r);
+    double r = fma(nk, STOMP_B200_SC(1), x);
+    r = fma(nk, STOMP_B200_SC(2), r);
+    r = fma(nk, STOMP_B200_SC(3), r);
     const double z = r * r;
 
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, STOMP_B200_SC(4), STOMP_B200_SC(5));
+    ps = fma(z, ps, STOMP_B200_SC(6));
+    ps = fma(z, ps, STOMP_B200_SC(7));
+    ps = fma(z, ps, STOMP_B200_SC(8));
+    ps = fma(z, ps, STOMP_B200_SC(9));
     const double rz = r * z;
     const double sr = fma(rz, ps, r);
 
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, STOMP_B200_SC(10), STOMP_B200_SC(11));
+    pc = fma(z, pc, STOMP_B200_SC(12));
+    pc = fma(z, pc, STOMP_B200_SC(13));
+    pc = fma(z, pc, STOMP_B200_SC(14));
+    pc = fma(z, pc, STOMP_B200_SC(15));
     const double zz = z * z;
     const double half = fma(z, -0.5, 1.0);
     const double cr = fma(zz, pc, half);
@@ -210,5 +236,109 @@ __device__ __forceinline__ size_t sdf_index(const SdfParams& g, double cx, doubl
     if (g.wide_index) return ((size_t)iz * (size_t)g.ny + (size_t)iy) * (size_t)g.nx + (size_t)ix;
     return (size_t)(unsigned)((iz * g.ny + iy) * g.nx + ix);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Compile-time structured variants for the run-time specialised state kernel (state_codegen.hpp): the same
+// operations in the same order as apply_joint / sphere_centre / sdf_index above, with every structural
+// decision (axis kind, zero masks, fixed rotation, prismatic, chain restart, index width) a template
+// argument, so that the instantiated code is straight-line and every constant a direct constant-bank operand.
+// ---------------------------------------------------------------------------------------------------
+template <int kKind, int kOMask, bool kFixedRot, bool kPrismatic, bool kRestart>
+__device__ __forceinline__ void apply_joint_static(Frame& f, const JointParams& j, double q)
+{
+    if (kRestart) frame_identity(f);
+    if (kOMask & 1) { f.px = fma(f.r00, j.o[0], f.px); f.py = fma(f.r10, j.o[0], f.py); f.pz = fma(f.r20, j.o[0], f.pz); }
+    if (kOMask & 2) { f.px = fma(f.r01, j.o[1], f.px); f.py = fma(f.r11, j.o[1], f.py); f.pz = fma(f.r21, j.o[1], f.pz); }
+    if (kOMask & 4) { f.px = fma(f.r02, j.o[2], f.px); f.py = fma(f.r12, j.o[2], f.py); f.pz = fma(f.r22, j.o[2], f.pz); }
+    if (kFixedRot) {   // R = R * A
+        const double n00 = fma(f.r02, j.A[6], fma(f.r01, j.A[3], f.r00 * j.A[0]));
+        const double n01 = fma(f.r02, j.A[7], fma(f.r01, j.A[4], f.r00 * j.A[1]));
+        const double n02 = fma(f.r02, j.A[8], fma(f.r01, j.A[5], f.r00 * j.A[2]));
+        const double n10 = fma(f.r12, j.A[6], fma(f.r11, j.A[3], f.r10 * j.A[0]));
+        const double n11 = fma(f.r12, j.A[7], fma(f.r11, j.A[4], f.r10 * j.A[1]));
+        const double n12 = fma(f.r12, j.A[8], fma(f.r11, j.A[5], f.r10 * j.A[2]));
+        const double n20 = fma(f.r22, j.A[6], fma(f.r21, j.A[3], f.r20 * j.A[0]));
+        const double n21 = fma(f.r22, j.A[7], fma(f.r21, j.A[4], f.r20 * j.A[1]));
+        const double n22 = fma(f.r22, j.A[8], fma(f.r21, j.A[5], f.r20 * j.A[2]));
+        f.r00 = n00; f.r01 = n01; f.r02 = n02;
+        f.r10 = n10; f.r11 = n11; f.r12 = n12;
+        f.r20 = n20; f.r21 = n21; f.r22 = n22;
+    }
+    if (kPrismatic) {   // p += q * (R * axis)
+        const double dx = fma(f.r02, j.axis[2], fma(f.r01, j.axis[1], f.r00 * j.axis[0]));
+        const double dy = fma(f.r12, j.axis[2], fma(f.r11, j.axis[1], f.r10 * j.axis[0]));
+        const double dz = fma(f.r22, j.axis[2], fma(f.r21, j.axis[1], f.r20 * j.axis[0]));
+        f.px = fma(q, dx, f.px);
+        f.py = fma(q, dy, f.py);
+        f.pz = fma(q, dz, f.pz);
+        return;
+    }
+    double s, c;
+    det_sincos(q, s, c);
+    if (kKind >= kAxisNegX && kKind <= kAxisNegZ) s = -s;
+    constexpr int kind = (kKind >= kAxisNegX && kKind <= kAxisNegZ) ? kKind - 3 : kKind;
+    const double ns = -s;
+    if (kind == kAxisZ) {
+        STOMP_B200_ROT2(f.r00, f.r01, s, ns, c)
+        STOMP_B200_ROT2(f.r10, f.r11, s, ns, c)
+        STOMP_B200_ROT2(f.r20, f.r21, s, ns, c)
+    } else if (kind == kAxisY) {
+        STOMP_B200_ROT2(f.r00, f.r02, ns, s, c)
+        STOMP_B200_ROT2(f.r10, f.r12, ns, s, c)
+        STOMP_B200_ROT2(f.r20, f.r22, ns, s, c)
+    } else if (kind == kAxisX) {
+        STOMP_B200_ROT2(f.r01, f.r02, s, ns, c)
+        STOMP_B200_ROT2(f.r11, f.r12, s, ns, c)
+        STOMP_B200_ROT2(f.r21, f.r22, s, ns, c)
+    } else {
+        const double ax = j.axis[0], ay = j.axis[1], az = j.axis[2];
+        const double v = 1.0 - c;
+        const double vx = v * ax, vy = v * ay, vz = v * az;
+        const double q00 = fma(vx, ax, c),          q01 = fma(vx, ay, -(s * az)), q02 = fma(vx, az, s * ay);
+        const double q10 = fma(vy, ax, s * az),     q11 = fma(vy, ay, c),         q12 = fma(vy, az, -(s * ax));
+        const double q20 = fma(vz, ax, -(s * ay)),  q21 = fma(vz, ay, s * ax),    q22 = fma(vz, az, c);
+        const double n00 = fma(f.r02, q20, fma(f.r01, q10, f.r00 * q00));
+        const double n01 = fma(f.r02, q21, fma(f.r01, q11, f.r00 * q01));
+        const double n02 = fma(f.r02, q22, fma(f.r01, q12, f.r00 * q02));
+        const double n10 = fma(f.r12, q20, fma(f.r11, q10, f.r10 * q00));
+        const double n11 = fma(f.r12, q21, fma(f.r11, q11, f.r10 * q01));
+        const double n12 = fma(f.r12, q22, fma(f.r11, q12, f.r10 * q02));
+        const double n20 = fma(f.r22, q20, fma(f.r21, q10, f.r20 * q00));
+        const double n21 = fma(f.r22, q21, fma(f.r21, q11, f.r20 * q01));
+        const double n22 = fma(f.r22, q22, fma(f.r21, q12, f.r20 * q02));
+        f.r00 = n00; f.r01 = n01; f.r02 = n02;
+        f.r10 = n10; f.r11 = n11; f.r12 = n12;
+        f.r20 = n20; f.r21 = n21; f.r22 = n22;
+    }
+}
+
+// address of the voxel under one sphere centre (the gather itself is issued by the caller, so that the
+// generated kernel can batch the loads of a link)
+template <int kMask, bool kWide>
+__device__ __forceinline__ const float* sphere_voxel_static(const Frame& f, const SphereParams& sp, const SdfParams& g)
+{
+    double cx = f.px, cy = f.py, cz = f.pz;
+    if (kMask & 1) { cx = fma(f.r00, sp.l[0], cx); cy = fma(f.r10, sp.l[0], cy); cz = fma(f.r20, sp.l[0], cz); }
+    if (kMask & 2) { cx = fma(f.r01, sp.l[1], cx); cy = fma(f.r11, sp.l[1], cy); cz = fma(f.r21, sp.l[1], cz); }
+    if (kMask & 4) { cx = fma(f.r02, sp.l[2], cx); cy = fma(f.r12, sp.l[2], cy); cz = fma(f.r22, sp.l[2], cz); }
+    const int ix = min(max(__double2int_rz(fma(cx, g.inv_h, g.offx)), 0), g.nx - 1);
+    const int iy = min(max(__double2int_rz(fma(cy, g.inv_h, g.offy)), 0), g.ny - 1);
+    const int iz = min(max(__double2int_rz(fma(cz, g.inv_h, g.offz)), 0), g.nz - 1);
+    if (kWide) return g.grid + (((size_t)iz * (size_t)g.ny + (size_t)iy) * (size_t)g.nx + (size_t)ix);
+    return g.grid + (unsigned)((iz * g.ny + iy) * g.nx + ix);
+}
+
+// arguments of the specialised state kernel (the subset of LoopParams that rollout_states_kernel reads)
+struct StateKernelArgs {
+    const double* rollouts;        // [Q][slots][D][T]
+    double* state_costs;           // [Q][slots][T]
+    uint8_t* verdicts;             // [Q][slots][T]
+    uint8_t* validity;             // [Q][slots]
+    double* sums;                  // [Q][gslots][sumw]
+    const int32_t* stop;           // [Q]
+    uint32_t* tile_counter;        // [4]
+    unsigned long long* timeline;  // first-start / last-end stamps of this kernel, or null
+    int32_t T, D, slots, gslots, sumw, num_gen, gen_offset, honour_stop, debug_skip, pad_;
+};
 
 }  // namespace stomp_b200

@@ -1,0 +1,33 @@
+// Offline look at the specialised state kernel for the iiwa structure (no GPU needed):
+//   nvcc -std=c++17 -o /tmp/spec_sass tools/spec_sass.cu -ldl && /tmp/spec_sass /tmp/spec.cubin && cuobjdump -sass /tmp/spec.cubin
+#include <cstdio>
+#include "../include/stomp_b200.h"
+#include "../motion_planners_b200/csrc/state_codegen.hpp"
+using namespace stomp_b200;
+int main(int argc, char** argv)
+{
+    RobotParams r;
+    std::memset(&r, 0, sizeof r);
+    r.num_joints = 7;
+    const int kinds[7] = {kAxisZ, kAxisY, kAxisZ, kAxisNegY, kAxisZ, kAxisY, kAxisZ};
+    const int omask[7] = {0, 5, 0, 5, 0, 4, 0};
+    const int nsph[7] = {3, 3, 3, 3, 3, 2, 3};
+    const int smask[20] = {4, 4, 4, 0, 6, 6, 4, 4, 4, 0, 6, 6, 4, 4, 4, 0, 4, 4, 4, 4};
+    int s = 0;
+    for (int d = 0; d < 7; ++d) {
+        r.joint[d].axis_kind = kinds[d]; r.joint[d].o_mask = omask[d]; r.joint[d].fixed_rot_identity = 1;
+        r.joint[d].parent = d - 1;
+        r.sphere_begin[d] = s;
+        for (int k = 0; k < nsph[d]; ++k, ++s) r.sphere[s].mask = smask[s];
+    }
+    for (int d = 7; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = s;
+    r.num_spheres = s;
+    const std::string src = codegen::generate_state_kernel_source(r, false);
+    std::vector<char> cubin; std::string log, err;
+    if (!codegen::compile_to_cubin(src, cubin, log, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    if (argc > 2) { FILE* f = std::fopen(argv[2], "w"); std::fputs(src.c_str(), f); std::fclose(f); }
+    FILE* f = std::fopen(argc > 1 ? argv[1] : "/tmp/spec.cubin", "wb");
+    std::fwrite(cubin.data(), 1, cubin.size(), f); std::fclose(f);
+    std::printf("%zu bytes; log: %s\n", cubin.size(), log.c_str());
+    return 0;
+}
