@@ -113,6 +113,8 @@ struct stomp_b200_engine {
     bool use_dmma = true;                    // STOMP_B200_SAMPLER=simt selects the FMA-pipe contraction
     cudaStream_t side_stream = nullptr;      // noise-less rollout, overlapped with the next iteration's sampling + costs
     cudaEvent_t ev_applied = nullptr, ev_noiseless = nullptr;
+    cudaStream_t rows_stream = nullptr;      // control-cost rows, side by side with the state kernel
+    cudaEvent_t ev_sampled = nullptr, ev_rows = nullptr;
     bool noiseless_pending = false;          // ev_noiseless recorded and not yet waited for by the main stream
     double* d_theta_all_init = nullptr;   // policy as uploaded by set_policy (restored by begin_solve? no: the policy persists)
 
@@ -230,8 +232,7 @@ int check_launch(stomp_b200_engine* e, const char* what)
 
 size_t dmma_smem_bytes(int T)
 {
-    const int T4 = (T + 3) & ~3;
-    return sizeof(double) * ((size_t)T4 * kSlabT + (size_t)kDmmaWarps * 8 * kEStride);
+    return sizeof(double) * (size_t)dmma_slab_rows(T) * kSlabStride;
 }
 
 // FP64 tensor-core contraction (DMMA); used whenever the Lt slab fits in shared memory
@@ -242,7 +243,7 @@ int launch_sample_dmma(stomp_b200_engine* e, const LoopParams& lp)
     const int ntiles = (int)((total_cols + 7) / 8);
     const int nslabs = (lp.T + kSlabT - 1) / kSlabT;
     const size_t smem = dmma_smem_bytes(lp.T);
-    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
     dim3 grid(std::max(1, std::min((ntiles + kDmmaWarps - 1) / kDmmaWarps, e->num_sms * per_sm)), nslabs);
     Scope s(e, STOMP_B200_KERNEL_SAMPLE);
     sample_rollouts_dmma_kernel<kPhilox><<<grid, kDmmaWarps * 32, smem, e->stream>>>(lp, e->robot, lp.tile_counter);
@@ -269,6 +270,18 @@ int launch_sample(stomp_b200_engine* e, const LoopParams& lp)
 enum NoiseMode { kNoisePhilox = 0, kNoiseUnit = 1, kNoiseEpsilon = 2 };
 
 // one Stomp::runSingleIteration for all local queries, queued on the stream (no host synchronisation)
+codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
+{
+    codegen::StateKernelOptions opt;
+    opt.wide_index = e->sdf.wide_index != 0;
+    opt.magic_floor = codegen::magic_floor_is_safe(e->robot, e->sdf);
+    if (const char* f = std::getenv("STOMP_B200_STATES_FLOOR")) opt.magic_floor = opt.magic_floor && std::strcmp(f, "cvt") != 0;
+    if (const char* b = std::getenv("STOMP_B200_STATES_MIN_BLOCKS")) opt.min_blocks = std::atoi(b);   // tuning knobs
+    if (const char* l = std::getenv("STOMP_B200_STATES_LAG")) opt.compare_lag = std::max(0, std::atoi(l));
+    if (const char* j = std::getenv("STOMP_B200_STATES_STAGE")) opt.stage_joints = std::atoi(j) != 0;
+    return opt;
+}
+
 // picks the state kernel once per robot description: the run-time specialised one, or the generic one when
 // NVRTC is not available / STOMP_B200_STATES=generic (both are CUDA kernels; spec_note says which and why)
 void resolve_state_kernel(stomp_b200_engine* e)
@@ -279,7 +292,7 @@ void resolve_state_kernel(stomp_b200_engine* e)
     const char* mode = std::getenv("STOMP_B200_STATES");
     if (mode && std::strcmp(mode, "generic") == 0) { e->spec_note = "STOMP_B200_STATES=generic"; return; }
     std::string err;
-    e->spec = codegen::specialised_state_kernel(e->robot, e->sdf.wide_index != 0, err);
+    e->spec = codegen::specialised_state_kernel(e->robot, state_kernel_options(e), err);
     e->spec_note = e->spec ? std::string() : err;
 }
 
@@ -358,12 +371,21 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         if (int rc = launch_sample<true>(e, lp)) return rc;
     }
 
-    // ---- control costs + n^T R n of the generated rows (K5, K6), then the state costs (K4) ----
+    // ---- control costs + n^T R n of the generated rows (K5, K6) and the state costs (K4): independent of each
+    // other (different columns of `sums`), both latency-bound at < 50 % occupancy -> run side by side on two
+    // streams; serial on the main stream while per-kernel profiling is on ----
+    static const bool overlap_allowed = !(std::getenv("STOMP_B200_OVERLAP") && std::strcmp(std::getenv("STOMP_B200_OVERLAP"), "0") == 0);
+    const bool overlap_rows = overlap_allowed && !e->profiling && e->rows_stream != nullptr;
+    cudaStream_t rows_stream = overlap_rows ? e->rows_stream : e->stream;
+    if (overlap_rows) {
+        CUDA_TRY(e, cudaEventRecord(e->ev_sampled, e->stream));
+        CUDA_TRY(e, cudaStreamWaitEvent(rows_stream, e->ev_sampled, 0));
+    }
     {
         const int rows = gen_local * e->D;
         Scope sc(e, STOMP_B200_KERNEL_COST);
         if (e->edge_dirty && lp.num_rules == 1) {   // padding-only rows of the control costs: constants of a solve
-            edge_rows_kernel<<<e->Q, 64, 0, e->stream>>>(lp);
+            edge_rows_kernel<<<e->Q, 64, 0, rows_stream>>>(lp);
             e->launch_count++;
             if (int rc = check_launch(e, "edge_rows_kernel")) return rc;
             e->edge_dirty = false;
@@ -375,18 +397,19 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             for (int j = 0; j < lp.st_n; ++j) taps5 = taps5 && lp.st_off[j] > -3 && lp.st_off[j] < 3;
             const bool rb4 = lp.rband_halfwidth <= 4;
             const dim3 grid((rows + 7) / 8, e->Q);
-            if (taps5 && rb4) control_rows_fast_kernel<true, true><<<grid, 256, 0, e->stream>>>(lp);
-            else control_rows_fast_kernel<false, false><<<grid, 256, 0, e->stream>>>(lp);
+            if (taps5 && rb4) control_rows_fast_kernel<true, true><<<grid, 256, 0, rows_stream>>>(lp);
+            else control_rows_fast_kernel<false, false><<<grid, 256, 0, rows_stream>>>(lp);
         } else {
             const size_t row_smem = sizeof(double) * (size_t)kRowWarps * (control_row_x_stride(e->N) + control_row_n_stride(e->T));
-            control_rows_kernel<<<dim3((rows + kRowWarps - 1) / kRowWarps, e->Q), kRowWarps * 32, row_smem, e->stream>>>(lp);
+            control_rows_kernel<<<dim3((rows + kRowWarps - 1) / kRowWarps, e->Q), kRowWarps * 32, row_smem, rows_stream>>>(lp);
         }
         if (int rc = check_launch(e, "control_rows_kernel")) return rc;
         if (lp.control_costs) {
-            fold_control_costs_kernel<<<dim3((rows + 127) / 128, e->Q), 128, 0, e->stream>>>(lp);
+            fold_control_costs_kernel<<<dim3((rows + 127) / 128, e->Q), 128, 0, rows_stream>>>(lp);
             if (int rc = check_launch(e, "fold_control_costs_kernel")) return rc;
         }
     }
+    if (overlap_rows) CUDA_TRY(e, cudaEventRecord(e->ev_rows, rows_stream));
     {
         const int states = gen_local * e->T;
         dim3 grid((states + 255) / 256, e->Q);
@@ -405,6 +428,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         else rollout_states_kernel<false><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
         if (int rc = check_launch(e, "rollout_states_kernel")) return rc;
     }
+    if (overlap_rows) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_rows, 0));
     // ---- the noise-less rollout of the previous iteration is needed from here on ----
     if (e->noiseless_pending) {
         CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_noiseless, 0));
@@ -619,6 +643,9 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_CUDA(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
     CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_applied, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_noiseless, cudaEventDisableTiming));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&e->rows_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_sampled, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_rows, cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreate(&e->timer_a));
     CREATE_CUDA(cudaEventCreate(&e->timer_b));
 
@@ -742,6 +769,7 @@ int stomp_b200_destroy(stomp_b200_engine* e)
     if (!e) return STOMP_B200_OK;
     cudaSetDevice(e->cfg.device);
     if (e->side_stream) cudaStreamSynchronize(e->side_stream);
+    if (e->rows_stream) cudaStreamSynchronize(e->rows_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     resolve_profile(e);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
@@ -757,6 +785,9 @@ int stomp_b200_destroy(stomp_b200_engine* e)
     if (e->ev_applied) cudaEventDestroy(e->ev_applied);
     if (e->ev_noiseless) cudaEventDestroy(e->ev_noiseless);
     if (e->side_stream) cudaStreamDestroy(e->side_stream);
+    if (e->ev_sampled) cudaEventDestroy(e->ev_sampled);
+    if (e->ev_rows) cudaEventDestroy(e->ev_rows);
+    if (e->rows_stream) cudaStreamDestroy(e->rows_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return STOMP_B200_OK;
@@ -818,6 +849,21 @@ int stomp_b200_set_chain(stomp_b200_engine* e, int32_t num_joints, const double*
     return STOMP_B200_OK;
 }
 
+// smallest binary32 >= r (SphereParams::r_up)
+static float float_at_or_above(double r)
+{
+    float f = (float)r;                       // round to nearest
+    if ((double)f < r) {                      // step up one ulp
+        uint32_t u;
+        std::memcpy(&u, &f, sizeof u);
+        if (f == 0.0f) u = 1u;                // smallest subnormal
+        else if (f > 0.0f) u += 1u;
+        else u -= 1u;
+        std::memcpy(&f, &u, sizeof u);
+    }
+    return f;
+}
+
 int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int32_t* link, const double* centre_xyz,
                            const double* radius)
 {
@@ -835,6 +881,7 @@ int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int3
             if (r.sphere[s].l[i] != 0.0) r.sphere[s].mask |= 1 << i;
         }
         r.sphere[s].r = radius[s];
+        r.sphere[s].r_up = float_at_or_above(radius[s]);
         r.sphere_begin[link[s] + 1] = s + 1;
     }
     for (int d = 1; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = std::max(r.sphere_begin[d], r.sphere_begin[d - 1]);
@@ -1327,7 +1374,7 @@ int stomp_b200_state_kernel_source(stomp_b200_engine* e, char* buffer, size_t ca
 {
     if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
     if (!e->have_chain || !e->have_spheres) return fail(e, STOMP_B200_ERR_NOT_READY, "chain and spheres come first");
-    const std::string src = codegen::generate_state_kernel_source(e->robot, e->sdf.wide_index != 0);
+    const std::string src = codegen::generate_state_kernel_source(e->robot, state_kernel_options(e));
     if (needed) *needed = src.size() + 1;
     if (buffer && capacity) std::snprintf(buffer, capacity, "%s", src.c_str());
     return STOMP_B200_OK;
@@ -1360,7 +1407,10 @@ int stomp_b200_codegen_selftest(char* log, size_t log_capacity)
     for (int wide = 0; wide < 2 && rc == STOMP_B200_OK; ++wide) {
         std::vector<char> cubin;
         std::string clog;
-        if (!codegen::compile_to_cubin(codegen::generate_state_kernel_source(r, wide != 0), cubin, clog, err)) {
+        codegen::StateKernelOptions opt;
+        opt.wide_index = wide != 0;
+        opt.magic_floor = wide == 0;
+        if (!codegen::compile_to_cubin(codegen::generate_state_kernel_source(r, opt), cubin, clog, err)) {
             all_log += err;
             rc = STOMP_B200_ERR_CUDA;
         } else {

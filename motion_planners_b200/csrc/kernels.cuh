@@ -223,6 +223,8 @@ __device__ __forceinline__ void shift_clamp_store(const LoopParams& p, const Rob
     p.rollouts[o] = v;
     p.noise[o] = nz;
     if (p.proj) p.proj[o] = theta + nz;          // computeProjectedNoise with M = I (PolicyImprovement.cpp:430-440)
+    // S_k = sum_t state cost is accumulated with atomics by the state kernel: zeroed here, one element per rollout
+    if (d == 0 && t == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw] = 0.0;
 }
 
 // Contraction N^T[c][t] = sum_u E^T[c][u] * Lt[u][t] over the G*D columns c = (k, d) of one query, all T
@@ -323,25 +325,46 @@ sample_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The same contraction on the FP64 tensor path (mma.sync.m8n8k4.f64 -> DMMA).  Measured on B200
-// (tools/fp64_peak.cu, profiles/r1_fp64_peak_b200.json): DMMA 37.0 TFLOP/s vs 35.0 TFLOP/s on the FMA pipe —
-// the same peak, but one DMMA carries the work of eight DFMA warp-instructions, and ncu showed the SIMT
-// kernel above issue/latency bound (FP64 pipe 30 % busy), i.e. the case BASELINE.json's north_star reserves
-// tensor cores for.  Per warp: one m8 tile = 8 columns (k, d) x all time steps of a 104-wide slab of t;
-// A = eps [8 cols][4 u] generated in place (Philox) or read (injected), B = Lt slab resident in shared
-// memory, C = 13 n8 tiles in registers.  Lt is upper triangular: k-step u0 only touches n8 tiles with
-// 8*nt + 7 >= u0.  Tiles are handed out by an atomic counter (reset by rollout_cost_kernel) over the
-// flattened (query, rollout, joint) column space, so the slab is loaded once per resident CTA.
+// The same contraction on the FP64 tensor path (mma.sync.m8n8k4.f64 -> DMMA.8x8x4, the only FP64 MMA shape the
+// hardware has: ptxas splits m16n8k16 into eight of them).  Measured on B200 (tools/fp64_peak.cu,
+// profiles/r1_fp64_peak_b200.json): DMMA 37.0 TFLOP/s vs 35.0 TFLOP/s on the FMA pipe — the same peak, but one DMMA
+// carries the work of eight DFMA warp-instructions, and ncu showed the SIMT kernel above issue-bound, i.e. the
+// case BASELINE.json's north_star reserves tensor cores for.
+//
+// Per warp: one m8 tile = 8 columns (k, d) x all time steps of a 104-wide slab of t; C = 13 n8 tiles in registers;
+// B = the Lt slab, resident in shared memory for the whole kernel; tiles handed out by an atomic counter (reset
+// by the state kernel) over the flattened (query, rollout, joint) column space.
+// A = eps never touches memory: lane (r, kq) draws the four normals eps[column r][u0 + 4kq .. + 3] with one
+// Philox call per 16-wide chunk of u, and the contraction index is PERMUTED inside the chunk so that they are
+// exactly its A fragments: in step j of the chunk, k-slot kq stands for u = u0 + 4kq + j, i.e. A = z[j] and
+// B = Lt[u0 + 4kq + j][t].  (A sum over u does not care about the order of u.)  The slab's row stride is
+// 106 == 2 (mod 4) doubles, which puts the four rows 4kq + j of a B fragment on disjoint banks (2 wavefronts
+// per load, the minimum for 64-bit lanes).
+// Lt is upper triangular: a chunk only touches n8 tiles with 8 nt + 7 >= u0 - t_base; the first tile is a
+// template argument (13 straight-line bodies behind one switch), so the inner loop is LDS + DMMA with no
+// predicates.  The epilogue holds two consecutive time steps per lane and n8 tile: 16-byte loads / stores.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kDmmaWarps = 8;
 constexpr int kSlabTiles = 13;
-constexpr int kSlabT = kSlabTiles * 8;     // 104 == 8 (mod 16): B-fragment loads are 2 wavefronts, the minimum
-constexpr int kEStride = 17;
+constexpr int kSlabT = kSlabTiles * 8;     // 104
+constexpr int kSlabStride = 106;
+
+__host__ __device__ inline int dmma_slab_rows(int T) { return (T + 15) & ~15; }
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int kFirstTile>
+__device__ __forceinline__ void dmma_chunk(double (&acc)[kSlabTiles][2], const double (&z)[4], const double* __restrict__ b0)
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int nt = kFirstTile; nt < kSlabTiles; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], z[j], b0[j * kSlabStride + 8 * nt]);
+    }
 }
 
 template <bool kPhilox>
@@ -350,20 +373,18 @@ sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_c
                             unsigned* __restrict__ tile_counter)
 {
     extern __shared__ double smem[];
-    const int T = p.T, D = p.D;
-    const int T4 = (T + 3) & ~3;
+    const int T = p.T, D = p.D, N = p.N;
+    const int rows = dmma_slab_rows(T);
     const int slab = blockIdx.y;
     const int t_base = slab * kSlabT;
-    const int nt_cnt = min(kSlabTiles, (T - t_base + 7) >> 3);
-    const int u_end = min(T4, (min(T, t_base + kSlabT) + 3) & ~3);   // rows of Lt below the slab's last t are zero
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u_end = min(rows, dmma_slab_rows(min(T, t_base + kSlabT)));   // rows of Lt below the slab's last t are zero
+    const int tid = threadIdx.x, lane = tid & 31;
     TimelineScope tls(p, 0);
-    double* sLt = smem;                                              // [T4][kSlabT]
-    double* sE = smem + (size_t)T4 * kSlabT + (size_t)warp * (8 * kEStride);
+    double* sLt = smem;                                              // [rows][kSlabStride]; zero outside the matrix
 
-    for (int e = tid; e < T4 * kSlabT; e += blockDim.x) {
-        const int u = e / kSlabT, j = e - u * kSlabT, t = t_base + j;
-        sLt[e] = (u < T && t < T && t >= u) ? p.Lt[(size_t)u * T + t] : 0.0;
+    for (int e = tid; e < rows * kSlabStride; e += blockDim.x) {
+        const int u = e / kSlabStride, j = e - u * kSlabStride, t = t_base + j;
+        sLt[e] = (u < T && j < kSlabT && t < T && t >= u) ? p.Lt[(size_t)u * T + t] : 0.0;
     }
     __syncthreads();
 
@@ -371,6 +392,7 @@ sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_c
     const long long total_cols = (long long)p.Q * ncols;
     const int ntiles = (int)((total_cols + 7) >> 3);
     const int r = lane >> 2, kq = lane & 3;
+    const bool pairs = (T & 1) == 0;                  // 16-byte epilogue: every row starts on an even element
     for (;;) {
         int tile = 0;
         if (lane == 0) tile = (int)atomicAdd(tile_counter + slab, 1u);
@@ -382,63 +404,90 @@ sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_c
         const int c = in_range ? (int)(cg - (long long)q * ncols) : 0;
         const int k = c / D, d = c - k * D;
         const bool live = in_range && !query_frozen(p, q);
+        const size_t gen_row = (((size_t)q * p.num_gen + k) * D + d) * T;     // row of the [Q][G][D][T] staging tensors
+        const uint32_t gcol = (uint32_t)((((size_t)(p.query_offset + q)) * p.gen_global + (p.gen_offset + k)) * D + d);
 
         double acc[kSlabTiles][2];
 #pragma unroll
         for (int nt = 0; nt < kSlabTiles; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
 
         for (int u0 = 0; u0 < u_end; u0 += 16) {
-            // ---- eps chunk [8 columns][16 u]: this lane makes 4 consecutive u of its column ----
+            // ---- eps[column][u0 + 4kq .. + 3]: the A fragments of the chunk's four steps ----
             double z[4] = {0.0, 0.0, 0.0, 0.0};
             const int ub = u0 + 4 * kq;
             if (live) {
-                double* eps_row = p.epsilon + (((size_t)q * p.num_gen + k) * D + d) * T;
                 if (kPhilox) {
-                    const uint32_t gcol = (uint32_t)((((size_t)(p.query_offset + q)) * p.gen_global + (p.gen_offset + k)) * D + d);
                     philox_normals(p.seed, (uint32_t)p.iteration, gcol, (uint32_t)(ub >> 2), z);
                     if (p.store_unit && slab == 0) {
 #pragma unroll
                         for (int m = 0; m < 4; ++m)
-                            if (ub + m < T) eps_row[ub + m] = z[m];
+                            if (ub + m < T) p.epsilon[gen_row + ub + m] = z[m];
                     }
                 } else {
 #pragma unroll
                     for (int m = 0; m < 4; ++m)
-                        if (ub + m < T) z[m] = eps_row[ub + m];
+                        if (ub + m < T) z[m] = p.epsilon[gen_row + ub + m];
                 }
 #pragma unroll
                 for (int m = 0; m < 4; ++m)
                     if (ub + m >= T) z[m] = 0.0;
             }
-            __syncwarp();
-#pragma unroll
-            for (int m = 0; m < 4; ++m) sE[r * kEStride + 4 * kq + m] = z[m];
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int uk = u0 + 4 * j;
-                if (uk < u_end) {
-                    const double a = sE[r * kEStride + 4 * j + kq];
-                    const int nt_min = uk > t_base ? (uk - t_base) >> 3 : 0;
-                    const double* brow = sLt + (size_t)(uk + kq) * kSlabT + r;
-#pragma unroll
-                    for (int nt = 0; nt < kSlabTiles; ++nt)
-                        if (nt >= nt_min && nt < nt_cnt) dmma_m8n8k4(acc[nt][0], acc[nt][1], a, brow[8 * nt]);
-                }
+            const double* b0 = sLt + (size_t)ub * kSlabStride + r;
+            switch (u0 > t_base ? (u0 - t_base) >> 3 : 0) {      // warp-uniform
+                case 0: dmma_chunk<0>(acc, z, b0); break;
+                case 1: dmma_chunk<1>(acc, z, b0); break;
+                case 2: dmma_chunk<2>(acc, z, b0); break;
+                case 3: dmma_chunk<3>(acc, z, b0); break;
+                case 4: dmma_chunk<4>(acc, z, b0); break;
+                case 5: dmma_chunk<5>(acc, z, b0); break;
+                case 6: dmma_chunk<6>(acc, z, b0); break;
+                case 7: dmma_chunk<7>(acc, z, b0); break;
+                case 8: dmma_chunk<8>(acc, z, b0); break;
+                case 9: dmma_chunk<9>(acc, z, b0); break;
+                case 10: dmma_chunk<10>(acc, z, b0); break;
+                case 11: dmma_chunk<11>(acc, z, b0); break;
+                default: dmma_chunk<12>(acc, z, b0); break;
             }
         }
         // ---- epilogue: C fragment element (row r, cols 2*kq, 2*kq + 1) of tile nt ----
-        if (live) {
+        if (!live) continue;
+        if (pairs) {
+            const double* cf = p.coef + ((size_t)q * D + d) * 3;
+            const double p1 = cf[0], p2 = cf[1], new_stddev = cf[2];
+            const double lo = robot.lower[d], hi = robot.upper[d];
+            const double* th = p.theta_all + ((size_t)q * D + d) * N + kPad;
+            const double* mc = p.mincc + ((size_t)q * D + d) * T;
+            const size_t row = (((size_t)q * p.slots + k) * D + d) * T;
 #pragma unroll
             for (int nt = 0; nt < kSlabTiles; ++nt) {
-                if (nt < nt_cnt) {
+                const int t = t_base + 8 * nt + 2 * kq;
+                if (t < T) {
+                    const double2 th2 = *reinterpret_cast<const double2*>(th + t);
+                    const double2 mc2 = *reinterpret_cast<const double2*>(mc + t);
+                    // the arithmetic of shift_clamp_store, two time steps at once
+                    double v0 = p1 * mc2.x + p2 * th2.x + new_stddev * acc[nt][0];
+                    double v1 = p1 * mc2.y + p2 * th2.y + new_stddev * acc[nt][1];
+                    if (v0 < lo) v0 = lo;
+                    if (v0 > hi) v0 = hi;
+                    if (v1 < lo) v1 = lo;
+                    if (v1 > hi) v1 = hi;
+                    const double n0 = v0 - th2.x, n1 = v1 - th2.y;
+                    *reinterpret_cast<double2*>(p.rollouts + row + t) = make_double2(v0, v1);
+                    *reinterpret_cast<double2*>(p.noise + row + t) = make_double2(n0, n1);
+                    if (p.proj) *reinterpret_cast<double2*>(p.proj + row + t) = make_double2(th2.x + n0, th2.y + n1);
+                    if (p.store_unit) *reinterpret_cast<double2*>(p.unit_noise + gen_row + t) = make_double2(acc[nt][0], acc[nt][1]);
+                    if (d == 0 && t == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw] = 0.0;
+                }
+            }
+        } else {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int t = t_base + 8 * nt + 2 * kq + h;
-                        if (t < T) {
-                            if (p.store_unit) p.unit_noise[(((size_t)q * p.num_gen + k) * D + d) * T + t] = acc[nt][h];
-                            shift_clamp_store(p, robot, q, k, d, t, acc[nt][h]);
-                        }
+            for (int nt = 0; nt < kSlabTiles; ++nt) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = t_base + 8 * nt + 2 * kq + h;
+                    if (t < T) {
+                        if (p.store_unit) p.unit_noise[gen_row + t] = acc[nt][h];
+                        shift_clamp_store(p, robot, q, k, d, t, acc[nt][h]);
                     }
                 }
             }
@@ -629,7 +678,6 @@ __device__ __forceinline__ double noise_quadratic_form(const LoopParams& p, cons
 // evaluates four consecutive elements from one 10-wide window read as five 16-byte loads — 2.5 KB of shared
 // memory traffic per row instead of 7 KB for per-element windows, no block barrier, no address-divergent
 // global load (an uncoalesced version of this loop saturates the L1 pipe, a shuffle version the SHFL pipe).
-// The row also zeroes S_k (d == 0) for the state kernel that follows.
 constexpr int kRowWarps = 8;
 __host__ __device__ inline int control_row_x_stride(int N) { return 4 + ((N + 127) / 128) * 128 + 16; }   // even: every warp row stays 16-byte aligned
 __host__ __device__ inline int control_row_n_stride(int T) { return ((T + 127) / 128) * 128 + 16; }
@@ -744,7 +792,6 @@ control_rows_kernel(const __grid_constant__ LoopParams p)
             double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
             srow[1 + d] = C_part;
             srow[1 + 2 * D + d] = quad;
-            if (d == 0) srow[0] = 0.0;        // S_k is accumulated by rollout_states_kernel
         }
     }
     tls.end();
@@ -857,7 +904,6 @@ control_rows_fast_kernel(const __grid_constant__ LoopParams p)
             double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
             srow[1 + d] = C_part;
             srow[1 + 2 * D + d] = quad;
-            if (d == 0) srow[0] = 0.0;        // S_k is accumulated by rollout_states_kernel
         }
     }
     tls.end();

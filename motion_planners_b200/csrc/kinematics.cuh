@@ -44,8 +44,9 @@ struct SphereParams {
     double l[3];      // centre in the link frame
     double r;
     int32_t mask;     // bit i set <=> l[i] != 0
-    int32_t pad_;
+    float r_up;       // smallest binary32 >= r: for a binary32 distance d, (double)d - r < 0  <=>  d < r_up
 };
+
 
 // passed by value as a __grid_constant__ kernel parameter: lives in the constant bank, every access is
 // warp-uniform
@@ -314,16 +315,24 @@ __device__ __forceinline__ void apply_joint_static(Frame& f, const JointParams& 
 
 // address of the voxel under one sphere centre (the gather itself is issued by the caller, so that the
 // generated kernel can batch the loads of a link)
-template <int kMask, bool kWide>
+// floor of a voxel coordinate |v| < 2^31 on the FP64 pipe: v + (2^52 + 2^51) rounded towards -inf leaves
+// floor(v) in the low word.  After the clamp to [0, n-1] floor and truncation agree (both send (-1, 0) to 0), so
+// this is the same index as sdf_index's cvt.rzi — without the conversion, which runs on the quarter-rate XU pipe
+// and was the busiest pipe of the kernel (ncu, profiles/r1j).  Only instantiated when the host has bounded the
+// reach of the chain (state_codegen.hpp: magic_floor_is_safe).
+__device__ __forceinline__ int voxel_floor_magic(double v) { return __double2loint(__dadd_rd(v, 6755399441055744.0)); }
+
+template <int kMask, bool kWide, bool kMagic>
 __device__ __forceinline__ const float* sphere_voxel_static(const Frame& f, const SphereParams& sp, const SdfParams& g)
 {
     double cx = f.px, cy = f.py, cz = f.pz;
     if (kMask & 1) { cx = fma(f.r00, sp.l[0], cx); cy = fma(f.r10, sp.l[0], cy); cz = fma(f.r20, sp.l[0], cz); }
     if (kMask & 2) { cx = fma(f.r01, sp.l[1], cx); cy = fma(f.r11, sp.l[1], cy); cz = fma(f.r21, sp.l[1], cz); }
     if (kMask & 4) { cx = fma(f.r02, sp.l[2], cx); cy = fma(f.r12, sp.l[2], cy); cz = fma(f.r22, sp.l[2], cz); }
-    const int ix = min(max(__double2int_rz(fma(cx, g.inv_h, g.offx)), 0), g.nx - 1);
-    const int iy = min(max(__double2int_rz(fma(cy, g.inv_h, g.offy)), 0), g.ny - 1);
-    const int iz = min(max(__double2int_rz(fma(cz, g.inv_h, g.offz)), 0), g.nz - 1);
+    const double vx = fma(cx, g.inv_h, g.offx), vy = fma(cy, g.inv_h, g.offy), vz = fma(cz, g.inv_h, g.offz);
+    const int ix = min(max(kMagic ? voxel_floor_magic(vx) : __double2int_rz(vx), 0), g.nx - 1);
+    const int iy = min(max(kMagic ? voxel_floor_magic(vy) : __double2int_rz(vy), 0), g.ny - 1);
+    const int iz = min(max(kMagic ? voxel_floor_magic(vz) : __double2int_rz(vz), 0), g.nz - 1);
     if (kWide) return g.grid + (((size_t)iz * (size_t)g.ny + (size_t)iy) * (size_t)g.nx + (size_t)ix);
     return g.grid + (unsigned)((iz * g.ny + iy) * g.nx + ix);
 }

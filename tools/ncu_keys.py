@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Key metrics of every kernel in an `ncu --page raw --csv` export: python tools/ncu_keys.py <raw.csv> [name filter]"""
+import csv
+import sys
+
+KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'launch__waves_per_multiprocessor', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio']
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units = rows[0], rows[1]
+ki = hdr.index('Kernel Name')
+seen = set()
+for r in rows[2:]:
+    name = r[ki]
+    if len(sys.argv) > 2 and sys.argv[2] not in name:
+        continue
+    if name in seen:
+        continue
+    seen.add(name)
+    print('==', name[:90])
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            print(f'  {k:82s} {r[i]:>14s} {units[i]}')

@@ -22,7 +22,11 @@ int main(int argc, char** argv)
     }
     for (int d = 7; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = s;
     r.num_spheres = s;
-    const std::string src = codegen::generate_state_kernel_source(r, false);
+    codegen::StateKernelOptions opt;
+    opt.magic_floor = !getenv("CVT");
+    if (getenv("LAG")) opt.compare_lag = atoi(getenv("LAG"));
+    if (getenv("MINB")) opt.min_blocks = atoi(getenv("MINB"));
+    const std::string src = codegen::generate_state_kernel_source(r, opt);
     std::vector<char> cubin; std::string log, err;
     if (!codegen::compile_to_cubin(src, cubin, log, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
     if (argc > 2) { FILE* f = std::fopen(argv[2], "w"); std::fputs(src.c_str(), f); std::fclose(f); }
