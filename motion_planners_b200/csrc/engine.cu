@@ -270,6 +270,38 @@ int launch_sample(stomp_b200_engine* e, const LoopParams& lp)
 enum NoiseMode { kNoisePhilox = 0, kNoiseUnit = 1, kNoiseEpsilon = 2 };
 
 // one Stomp::runSingleIteration for all local queries, queued on the stream (no host synchronisation)
+// eight-rows-per-warp control-cost kernel (kernels.cuh): instantiated for the group counts of the usual T
+template <int kGroups>
+bool launch_rows_tile_g(stomp_b200_engine* e, const LoopParams& lp, int rows, cudaStream_t stream)
+{
+    const size_t smem = sizeof(double) * (size_t)kTileWarps * 8 * tile_noise_stride(kGroups);
+    const dim3 grid((rows + kTileWarps * 8 - 1) / (kTileWarps * 8), lp.Q);
+    static bool configured = false;       // per instantiation
+    if (!configured) {
+        if (cudaFuncSetAttribute(control_rows_tile_kernel<kGroups, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(control_rows_tile_kernel<kGroups, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return false;
+        }
+        configured = true;
+    }
+    if (smem > 200 * 1024) return false;
+    if (lp.control_costs) control_rows_tile_kernel<kGroups, true><<<grid, kTileWarps * 32, smem, stream>>>(lp);
+    else control_rows_tile_kernel<kGroups, false><<<grid, kTileWarps * 32, smem, stream>>>(lp);
+    return true;
+}
+
+bool launch_rows_tile(stomp_b200_engine* e, const LoopParams& lp, int rows, cudaStream_t stream)
+{
+    const int g = tile_groups(lp.N);
+    if (g <= 2) return launch_rows_tile_g<2>(e, lp, rows, stream);
+    if (g <= 4) return launch_rows_tile_g<4>(e, lp, rows, stream);
+    if (g <= 7) return launch_rows_tile_g<7>(e, lp, rows, stream);
+    if (g <= 11) return launch_rows_tile_g<11>(e, lp, rows, stream);
+    if (g <= 14) return launch_rows_tile_g<14>(e, lp, rows, stream);
+    return false;
+}
+
 codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
 {
     codegen::StateKernelOptions opt;
@@ -397,7 +429,10 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             for (int j = 0; j < lp.st_n; ++j) taps5 = taps5 && lp.st_off[j] > -3 && lp.st_off[j] < 3;
             const bool rb4 = lp.rband_halfwidth <= 4;
             const dim3 grid((rows + 7) / 8, e->Q);
-            if (taps5 && rb4) control_rows_fast_kernel<true, true><<<grid, 256, 0, rows_stream>>>(lp);
+            static const bool tile_allowed = !(std::getenv("STOMP_B200_ROWS") && std::strcmp(std::getenv("STOMP_B200_ROWS"), "fast") == 0);
+            if (taps5 && rb4 && tile_allowed && launch_rows_tile(e, lp, rows, rows_stream)) {
+                // launched
+            } else if (taps5 && rb4) control_rows_fast_kernel<true, true><<<grid, 256, 0, rows_stream>>>(lp);
             else control_rows_fast_kernel<false, false><<<grid, 256, 0, rows_stream>>>(lp);
         } else {
             const size_t row_smem = sizeof(double) * (size_t)kRowWarps * (control_row_x_stride(e->N) + control_row_n_stride(e->T));
@@ -452,18 +487,19 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
 
     // ---- probabilities (K7) ----
     {
-        lp.wblocks = (n + 255) / 256;
+        lp.wblocks = std::max(1, std::min(kWeightBlocksMax, (n + kWeightThreads - 1) / kWeightThreads));
         Scope sc(e, STOMP_B200_KERNEL_WEIGHTS);
-        rollout_weights_kernel<<<dim3(lp.wblocks, e->D, e->Q), 256, 0, e->stream>>>(lp);
+        rollout_weights_kernel<<<dim3(lp.wblocks, e->D, e->Q), kWeightThreads, 0, e->stream>>>(lp);
         if (int rc = check_launch(e, "rollout_weights_kernel")) return rc;
     }
     // ---- weighted sums (K8) ----
     const int nchunks = std::max(1, (lp.num_local + lp.chunk - 1) / lp.chunk);
     lp.nchunks = nchunks;
+    const bool fuse_apply = world == 1 && !e->profiling;     // the apply step rides on the update kernel's last chunk CTA
     {
-        const size_t smem = sizeof(double) * 2 * (size_t)lp.chunk;
+        const size_t smem = sizeof(double) * std::max<size_t>(2 * (size_t)lp.chunk, (size_t)e->T + 2);
         Scope sc(e, STOMP_B200_KERNEL_UPDATE);
-        weighted_update_kernel<<<dim3(nchunks, e->D, e->Q), kUpdateThreads, smem, e->stream>>>(lp);
+        weighted_update_kernel<<<dim3(nchunks, e->D, e->Q), kUpdateThreads, smem, e->stream>>>(lp, fuse_apply ? 1 : 0);
         if (int rc = check_launch(e, "weighted_update_kernel")) return rc;
     }
     // ---- exchange 2: update rows + adaptation numerators ----
@@ -477,9 +513,9 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         NCCL_TRY(e, g_nccl.AllReduce(lp.updbuf, lp.updbuf, count, ncclFloat64, ncclSum, e->comm, e->stream));
     }
     // ---- apply (K9) ----
-    {
+    if (!fuse_apply) {
         Scope sc(e, STOMP_B200_KERNEL_APPLY);
-        apply_update_kernel<<<dim3(e->D, e->Q), 128, 0, e->stream>>>(lp, world > 1 ? 0 : 1, nchunks);
+        apply_update_kernel<<<dim3(e->D, e->Q), 256, sizeof(double) * ((size_t)e->T + 2), e->stream>>>(lp, world > 1 ? 0 : 1, nchunks);
         if (int rc = check_launch(e, "apply_update_kernel")) return rc;
     }
     // ---- noise-less rollout (K10) on the side stream: overlaps the next iteration's sampling and costs ----
@@ -700,12 +736,13 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.stop, Q));
     CREATE_TRY(dev_alloc(e, &b.iters_used, Q));
     CREATE_TRY(dev_alloc(e, &e->d_order, Q * S));
-    b.chunk = 64;
+    b.chunk = 128;
     e->max_chunks = (int)((S + b.chunk - 1) / b.chunk);
     CREATE_TRY(dev_alloc(e, &b.partial, Q * e->max_chunks * D * (T + 2)));
     b.wblocks_cap = (int)((GS + 255) / 256);
     CREATE_TRY(dev_alloc(e, &b.wpart, Q * D * b.wblocks_cap));
     CREATE_TRY(dev_alloc(e, &b.edge_cost, Q * D * 6));
+    CREATE_TRY(dev_alloc(e, &b.done_counter, Q * D));
     CREATE_TRY(dev_alloc(e, &b.tile_counter, 4));
     CREATE_TRY(dev_alloc(e, &e->d_timeline, (size_t)kTimelineRing * kTimelineKernels * 2));
     b.world_size = world;
@@ -1128,14 +1165,14 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
         case STOMP_B200_TOTAL_COST: return from_sums(7);
         case STOMP_B200_PROBABILITIES:
         case STOMP_B200_FULL_PROBABILITIES: {
-            // the device tables hold exp(-h (c - min) / den); divide by the sum of the per-CTA partial sums in block
-            // order, exactly as weighted_update_kernel does (probabilities_ and full_probabilities_ coincide here)
+            // the device tables hold exp(-h (c - min) / den); divide by their sum (wpart), exactly as
+            // weighted_update_kernel does (probabilities_ and full_probabilities_ coincide here)
             const size_t width = tensor == STOMP_B200_PROBABILITIES ? T : 1;
             if (out_bytes != Q * ng * D * width * sizeof(double)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "out_bytes does not match the tensor size");
             std::vector<double> pr(Q * e->gslots * D), part(Q * D * b.wblocks_cap);
             CUDA_TRY(e, cudaMemcpy(pr.data(), b.prob, sizeof(double) * pr.size(), cudaMemcpyDeviceToHost));
             CUDA_TRY(e, cudaMemcpy(part.data(), b.wpart, sizeof(double) * part.size(), cudaMemcpyDeviceToHost));
-            const int wblocks = (int)((ng + 255) / 256);
+            const int wblocks = std::max(1, std::min(kWeightBlocksMax, ((int)ng + kWeightThreads - 1) / kWeightThreads));   // as launched
             double* o = static_cast<double*>(out);
             for (size_t q = 0; q < Q; ++q)
                 for (size_t d = 0; d < D; ++d) {

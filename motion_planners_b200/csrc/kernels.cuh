@@ -63,6 +63,7 @@ struct LoopParams {
     double* partial;          // [Q][chunks][D][T+2] per-chunk partial sums of weighted_update_kernel
     double* wpart;            // [Q][D][wblocks_cap] per-CTA sums of the unnormalised weights (rollout_weights_kernel)
     double* edge_cost;        // [Q][D][6] control costs of the band-table rows (edge_rows_kernel)
+    uint32_t* done_counter;   // [Q][D] tickets of weighted_update_kernel's chunk CTAs (zero between launches)
     int32_t wblocks, wblocks_cap;
     int32_t nchunks, chunk;
     double* updates;          // [Q][D][T]    last applied update (read-back)
@@ -909,6 +910,132 @@ control_rows_fast_kernel(const __grid_constant__ LoopParams p)
     tls.end();
 }
 
+// The rows once more, for the shipped shape of the operator (one rule whose interior taps are -2..+2 — the
+// acceleration rule — hence R five-banded and Toeplitz; even T): the leanest form.  A warp owns EIGHT consecutive
+// (rollout, joint) rows — 8 T contiguous doubles of `noise` — and copies them once, with coalesced 16-byte loads,
+// into zero-padded shared-memory rows; then lane (r, kq) walks quarter kq of row r SEQUENTIALLY with the stencil
+// and noise windows sliding through registers (fully unrolled: no register moves), four elements per pair of
+// 16-byte shared loads.  No bounds test inside the walk (the padding is zeros and the band-table rows come from
+// edge_cost), a two-step shuffle per row instead of five: ~120 warp instructions per row, ~85 % of them FP64
+// arithmetic, against ~510 for control_rows_fast_kernel.
+// Row strides are == 2 (mod 16) doubles: the 16-byte loads of a quarter-warp (2 rows x 4 quarters) hit 32
+// distinct banks.  kGroups = groups of four elements per lane = ceil(N / 16).
+// One warp per CTA: 8.3 KB of shared memory and 76 registers let 26 such CTAs live on an SM, so the 24.2 tiles per
+// SM of BASELINE config 3 (28672 rows / 8 / 148) run as ONE wave; with 8-warp CTAs (3 per SM = 24 warps) the
+// 25th tile of an SM waited for a whole CTA and doubled the kernel's time (profiles/r1q).
+constexpr int kTileWarps = 1;
+__host__ __device__ constexpr int tile_groups(int N) { return (N + 15) / 16; }
+__host__ __device__ constexpr int tile_noise_stride(int groups) { return ((16 * groups + 14 - 2 + 15) / 16) * 16 + 2; }   // >= 16 groups + 14
+
+template <int kGroups, bool kStore>
+__global__ void __launch_bounds__(kTileWarps * 32, 26)
+control_rows_tile_kernel(const __grid_constant__ LoopParams p)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 6);
+    const int T = p.T, D = p.D, N = p.N;
+    constexpr int E = 4 * kGroups;                    // elements per lane
+    constexpr int NS = tile_noise_stride(kGroups);    // ns[r][8 + t] = noise[t]; zeros elsewhere
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* ns = smem + (size_t)warp * 8 * NS;
+    const int nrows = p.num_gen * D;
+    const int c0 = (blockIdx.x * kTileWarps + warp) * 8;      // first row of this warp
+
+    if (c0 < nrows && !(p.debug_skip & 2)) {
+        // ---- stage: rows c0 .. c0+7 are contiguous in `noise` ----
+        const double* src = p.noise + ((size_t)q * p.slots * D + c0) * T;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const bool row_ok = c0 + r < nrows;
+            for (int j = 2 * lane; j < NS; j += 64) {
+                const int t = j - 8;
+                double2 v = make_double2(0.0, 0.0);
+                if (row_ok && t >= 0 && t < T) v = *reinterpret_cast<const double2*>(src + (size_t)r * T + t);
+                *reinterpret_cast<double2*>(ns + r * NS + j) = v;
+            }
+        }
+    }
+    __syncwarp();
+    const int r = lane >> 2, kq = lane & 3;
+    const int c = c0 + r;
+    if (c0 < nrows && !(p.debug_skip & 2)) {          // warp-uniform
+        const bool live = c < nrows;
+        const int k = live ? c / D : 0, d = live ? c - k * D : 0;
+        const double dtw = p.dt * p.control_cost_weight;
+        const double sqrt_w = p.rule_sqrt_w[0];
+        const double c1 = p.st_dense[1], c2 = p.st_dense[2], c3 = p.st_dense[3], c4 = p.st_dense[4], c5 = p.st_dense[5];
+        const double r0 = p.r_diag[0], r1 = p.r_diag[1], r2 = p.r_diag[2], r3 = p.r_diag[3], r4 = p.r_diag[4];
+        double edge = 0.0;
+        if (live && kq == 0) {
+            const double* ec = p.edge_cost + ((size_t)q * D + d) * 6;
+            edge = ((ec[0] + ec[1]) + (ec[2] + ec[3])) + (ec[4] + ec[5]);
+        }
+        const int i_begin = kq * E;
+        const double* nrow = ns + r * NS + i_begin;          // nrow[m] = noise[i_begin + m - 8]
+        const double* trow = p.theta_all + ((size_t)q * D + d) * N + i_begin - 2;   // trow[m] = theta_all[i_begin + m - 2] (L1-resident)
+        // 16-byte pair of theta_all at trow[m], zeros outside the row (only masked elements look there)
+        auto theta_pair = [&](int m) {
+            const int j = i_begin - 2 + m;
+            return (j >= 0 && j < N) ? *reinterpret_cast<const double2*>(trow + m) : make_double2(0.0, 0.0);
+        };
+        double* cc_out = (kStore && live) ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
+        // windows for the group at i: nw[m] = noise[i - 8 + m], m < 10 ; xw[m] = x_all[i - 2 + m], m < 8
+        double nw[10], xw[8];
+#pragma unroll
+        for (int m = 0; m < 6; m += 2) { const double2 v = *reinterpret_cast<const double2*>(nrow + m); nw[m + 4] = v.x; nw[m + 5] = v.y; }
+#pragma unroll
+        for (int m = 0; m < 4; m += 2) {
+            const double2 v = theta_pair(m);
+            xw[m + 4] = v.x + nw[m + 4]; xw[m + 5] = v.y + nw[m + 5];
+        }
+        double C0 = 0.0, C1 = 0.0, Q0 = 0.0, Q1 = 0.0;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const int i = i_begin + 4 * g;
+            // slide: four new noise values and four new x values
+#pragma unroll
+            for (int m = 0; m < 6; ++m) nw[m] = nw[m + 4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) xw[m] = xw[m + 4];
+            {
+                const double2 a = *reinterpret_cast<const double2*>(nrow + 4 * g + 6), b = *reinterpret_cast<const double2*>(nrow + 4 * g + 8);
+                nw[6] = a.x; nw[7] = a.y; nw[8] = b.x; nw[9] = b.y;
+                const double2 ta = theta_pair(4 * g + 4), tb = theta_pair(4 * g + 6);
+                // x_all[j] = theta_all[j] + noise[j - 6]: j = i + 2 + m  <->  nw[4 + m]
+                xw[4] = ta.x + nw[4]; xw[5] = ta.y + nw[5]; xw[6] = tb.x + nw[6]; xw[7] = tb.y + nw[7];
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                // element i + e: taps -2 .. +2 on x_all, mul then add in column order (the reference's arithmetic)
+                double sacc = 0.0;
+                sacc += c1 * xw[e]; sacc += c2 * xw[e + 1]; sacc += c3 * xw[e + 2]; sacc += c4 * xw[e + 3]; sacc += c5 * xw[e + 4];
+                const double Ax = sacc * sqrt_w;
+                double cost = dtw * (Ax * Ax);
+                if ((unsigned)(i + e - 3) >= (unsigned)(N - 6)) cost = 0.0;     // band-table rows and the zero padding beyond N
+                if (e & 1) C1 += cost; else C0 += cost;
+                if (kStore && cc_out && i + e >= kPad && i + e < kPad + T) cc_out[i + e - kPad] = cost;
+                // n^T R n term of t = i + e - 6: n_t = nw[2 + e]; zero outside [0, T), no guard needed
+                const double nt = nw[2 + e];
+                double qs = 0.0;
+                qs += r1 * nw[3 + e]; qs += r2 * nw[4 + e]; qs += r3 * nw[5 + e]; qs += r4 * nw[6 + e];
+                const double term = nt * (r0 * nt + 2.0 * qs);
+                if (e & 1) Q1 += term; else Q0 += term;
+            }
+        }
+        double C_part = (C0 + C1) + edge, quad = Q0 + Q1;
+        C_part += __shfl_xor_sync(0xffffffffu, C_part, 1); quad += __shfl_xor_sync(0xffffffffu, quad, 1);
+        C_part += __shfl_xor_sync(0xffffffffu, C_part, 2); quad += __shfl_xor_sync(0xffffffffu, quad, 2);
+        if (live && kq == 0) {
+            double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
+            srow[1 + d] = C_part;
+            srow[1 + 2 * D + d] = p.use_noise_adaptation ? quad : 0.0;
+        }
+    }
+    tls.end();
+}
+
 // fold of the padding rows into the first / last free step in the reference's order, for the stored
 // per-timestep control costs (read-backs only; one thread per row)
 __global__ void __launch_bounds__(128)
@@ -1140,10 +1267,14 @@ __device__ __forceinline__ const double* cost_row(const LoopParams& p, int q, in
     return (k == p.noiseless_gslot) ? p.nl_sums + (size_t)q * p.sumw : p.sums + ((size_t)q * p.gslots + k) * p.sumw;
 }
 
-// grid (wblocks, D, Q), 256 threads: every CTA scans all K' rows for the min / max of its joint (cheap, redundant,
-// no exp), weighs its own 256 rollouts and leaves the per-CTA sums of the unnormalised weights in wpart; the
-// consumers (weighted_update_kernel, read-backs) divide by the sum of the partials taken in block order.
-__global__ void __launch_bounds__(256)
+// grid (wblocks, D, Q), 512 threads.  Every CTA scans all K' rows for the min / max of its joint (two 8-byte loads per
+// row, unrolled so that they are all in flight at once: this kernel is pure L2 latency), then weighs its own slice of
+// the rollouts and leaves the sum of its unnormalised weights in wpart[block]; the consumers (weighted_update_kernel,
+// read-backs) divide by the sum of the wblocks partials taken in block order.  wblocks <= 8 keeps the redundant scans
+// cheap; one CTA per joint (tried) serialises eight L2 round trips and takes twice as long.
+constexpr int kWeightThreads = 512;
+constexpr int kWeightBlocksMax = 8;
+__global__ void __launch_bounds__(kWeightThreads)
 rollout_weights_kernel(const __grid_constant__ LoopParams p)
 {
     __shared__ double scratch[32];
@@ -1157,8 +1288,8 @@ rollout_weights_kernel(const __grid_constant__ LoopParams p)
     if (blockIdx.x == 0 && d == 0 && p.noiseless_slot >= 0) materialise_noiseless(p, q, tid, blockDim.x);
 
     double mn = 1e300, mx = -1e300;
-#pragma unroll 4
-    for (int k = tid; k < n; k += blockDim.x) {
+#pragma unroll 8
+    for (int k = tid; k < n; k += kWeightThreads) {
         const double* s = cost_row(p, q, k);
         const double cum = 1.0 * (s[0] + s[1 + d]);   // sum_t (state + control_d) as S + C_d; equals full_costs_[d]
         mn = fmin(mn, cum); mx = fmax(mx, cum);
@@ -1167,22 +1298,25 @@ rollout_weights_kernel(const __grid_constant__ LoopParams p)
     double den = mx - mn;
     if (den < 1e-8) den = 1e-8;
 
-    double pr = 0.0;
-    const int k = blockIdx.x * blockDim.x + tid;
-    if (k < n) {
+    const int per_block = (n + gridDim.x - 1) / gridDim.x;
+    const int k_end = min(n, (int)(blockIdx.x + 1) * per_block);
+    double psum = 0.0;
+#pragma unroll 2
+    for (int k = blockIdx.x * per_block + tid; k < k_end; k += kWeightThreads) {
         const double* s = cost_row(p, q, k);
         // cumulative_costs_[d] and full_costs_[d] are the same number in this build (S + C_d), hence one weight
-        pr = 1.0 * exp(((-h) * (1.0 * (s[0] + s[1 + d]) - mn)) / den);      // importance_weight_ = 1
+        const double pr = 1.0 * exp(((-h) * (1.0 * (s[0] + s[1 + d]) - mn)) / den);      // importance_weight_ = 1
         prob[(size_t)k * D + d] = pr;
         fprob[(size_t)k * D + d] = pr;
+        psum += pr;
         if (d == 0) {   // total_cost_ (:451-462)
             double cost = s[0];
             for (int dd = 0; dd < D; ++dd) cost += s[1 + dd];
             p.total_cost[(size_t)q * p.gslots + k] = cost;
         }
     }
-    const double psum_blk = block_reduce<0>(pr, scratch);
-    if (tid == 0) p.wpart[((size_t)q * D + d) * p.wblocks_cap + blockIdx.x] = psum_blk;
+    psum = block_reduce<0>(psum, scratch);
+    if (tid == 0) p.wpart[((size_t)q * D + d) * p.wblocks_cap + blockIdx.x] = psum;
     tls.end();
 }
 
@@ -1203,21 +1337,38 @@ __device__ __forceinline__ double weight_sum(const LoopParams& p, int q, int d)
 // thread t streams the chunk's noise rows with four independent accumulators.
 // partial [Q][chunks][D][T+2]: update row, numerator, denominator.
 // =====================================================================================================
-constexpr int kUpdateThreads = 128;
+constexpr int kUpdateThreads = 256;
+__device__ __forceinline__ void apply_update_body(const LoopParams& p, int q, int d, int from_partials, int nchunks, double* s_cols);
+
+// 256 threads = two halves of 128: thread (half, lt) streams time step lt of every second rollout row of the chunk with
+// 16 loads in flight, the halves are added in a fixed order.
+// fuse_apply (single GPU): the LAST chunk CTA of a (joint, query) to finish — found with a ticket counter after a
+// __threadfence — also does the work of apply_update_kernel: it sums the partials in chunk order (so the result does
+// not depend on which CTA came last) and updates the parameters and the noise magnitude.  One launch and one
+// drain / fill gap less per iteration.
+// dynamic shared memory: max(2 * chunk, T + 2) doubles.
 __global__ void __launch_bounds__(kUpdateThreads)
-weighted_update_kernel(const __grid_constant__ LoopParams p)
+weighted_update_kernel(const __grid_constant__ LoopParams p, int fuse_apply)
 {
-    extern __shared__ double smem[];   // [chunk] probabilities, [chunk] fprob * quad
+    extern __shared__ double smem[];   // [chunk] probabilities, [chunk] fprob * quad ; later [T + 2] column sums
     __shared__ double scratch[32];
+    __shared__ double s_half[128];
     const int d = blockIdx.y, q = blockIdx.z, c = blockIdx.x;
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 3);
     const int T = p.T, D = p.D, tid = threadIdx.x;
+    const int half = tid >> 7, lt = tid & 127;
     const int k_begin = c * p.chunk, k_end = min(p.num_local, (c + 1) * p.chunk);
     const int nk = k_end - k_begin;
     double* sp = smem;
     double* sq = smem + p.chunk;
-    if (tid == 0) scratch[0] = weight_sum(p, q, d);
+    if (tid < 32) {     // sum of the weights of joint d, partials in block order within a fixed butterfly
+        const double* part = p.wpart + ((size_t)q * D + d) * p.wblocks_cap;
+        double v = 0.0;
+        for (int b = tid; b < p.wblocks; b += 32) v += part[b];
+        v = warp_sum(v);
+        if (tid == 0) scratch[0] = v;
+    }
     __syncthreads();
     const double psum = scratch[0];
     __syncthreads();
@@ -1236,29 +1387,49 @@ weighted_update_kernel(const __grid_constant__ LoopParams p)
     }
     __syncthreads();
     double* out = p.partial + (((size_t)q * p.nchunks + c) * D + d) * (T + 2);
-    for (int t = tid; t < T; t += blockDim.x) {
-        const double* nz = p.noise + (((size_t)q * p.slots + k_begin) * D + d) * T + t;
-        const size_t stride = (size_t)D * T;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int k = 0;
-        for (; k + 16 <= nk; k += 16) {
-            double v[16];
+    for (int t0 = 0; t0 < T; t0 += 128) {
+        const int t = t0 + lt;
+        double acc = 0.0;
+        if (t < T) {
+            const double* nz = p.noise + (((size_t)q * p.slots + k_begin) * D + d) * T + t;
+            const size_t stride = (size_t)D * T;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = half;
+            for (; k + 30 < nk; k += 32) {       // rows k, k+2, ..., k+30
+                double v[16];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = nz[(size_t)(k + u) * stride];
+                for (int u = 0; u < 16; ++u) v[u] = nz[(size_t)(k + 2 * u) * stride];
 #pragma unroll
-            for (int u = 0; u < 16; u += 4) {
-                a0 += v[u] * sp[k + u]; a1 += v[u + 1] * sp[k + u + 1];
-                a2 += v[u + 2] * sp[k + u + 2]; a3 += v[u + 3] * sp[k + u + 3];
+                for (int u = 0; u < 16; u += 4) {
+                    a0 += v[u] * sp[k + 2 * u]; a1 += v[u + 1] * sp[k + 2 * u + 2];
+                    a2 += v[u + 2] * sp[k + 2 * u + 4]; a3 += v[u + 3] * sp[k + 2 * u + 6];
+                }
             }
+            for (; k < nk; k += 2) a0 += nz[(size_t)k * stride] * sp[k];
+            acc = (a0 + a1) + (a2 + a3);
         }
-        for (; k < nk; ++k) a0 += nz[(size_t)k * stride] * sp[k];
-        out[t] = (a0 + a1) + (a2 + a3);
+        if (half == 1) s_half[lt] = acc;
+        __syncthreads();
+        if (half == 0 && t < T) out[t] = acc + s_half[lt];
+        __syncthreads();
     }
     double numer = 0.0;
     for (int k = tid; k < nk; k += blockDim.x) numer += sq[k];
     numer = block_reduce<0>(numer, scratch);
     fsum_part = block_reduce<0>(fsum_part, scratch);
     if (tid == 0) { out[T] = numer; out[T + 1] = fsum_part; }
+    if (fuse_apply) {
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(p.done_counter + (size_t)q * D + d, 1u) == gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            apply_update_body(p, q, d, 1, (int)gridDim.x, smem);
+            if (tid == 0) p.done_counter[(size_t)q * D + d] = 0u;
+        }
+    }
     tls.end();
 }
 
@@ -1282,37 +1453,27 @@ reduce_partials_kernel(const __grid_constant__ LoopParams p, int nchunks)
 // updateParameters (stomp/src/CovariantMovementPrimitive.cpp:476-479).  grid (D, Q).  from_partials:
 // sum the chunk partials here (single GPU); otherwise read the all-reduced updbuf.
 // =====================================================================================================
-__global__ void __launch_bounds__(256)
-apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int nchunks)
+// s_cols: T + 2 doubles of shared memory.  Column sums first (all threads, 16 loads in flight each), then the update.
+__device__ __forceinline__ void apply_update_body(const LoopParams& p, int q, int d, int from_partials, int nchunks, double* s_cols)
 {
-    const int d = blockIdx.x, q = blockIdx.y;
-    if (query_frozen(p, q)) return;
-    TimelineScope tls(p, 4);
     const int T = p.T, D = p.D, N = p.N;
-    __shared__ double s_denom;
-    for (int t = threadIdx.x; t < T + 2; t += blockDim.x) {   // entry T + 1: denominator of the noise adaptation
-        if (t != T + 1) continue;
-        double v;
-        if (from_partials) {
-            v = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < nchunks; ++c) v += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 2) + t];
-        } else {
-            v = p.updbuf[((size_t)q * D + d) * (T + 2) + t];
-        }
-        s_denom = v;
-    }
     __syncthreads();
-    const double denom = s_denom;
-    for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
+    for (int t = threadIdx.x; t < T + 2; t += blockDim.x) {
         double u;
         if (from_partials) {
             u = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < nchunks; ++c) u += p.partial[(((size_t)q * p.nchunks + c) * D + d) * (T + 2) + t];
+            const double* col = p.partial + ((size_t)q * p.nchunks * D + d) * (T + 2) + t;
+            const size_t stride = (size_t)D * (T + 2);
+#pragma unroll 16
+            for (int c = 0; c < nchunks; ++c) u += __ldcg(col + (size_t)c * stride);     // chunk order
         } else {
             u = p.updbuf[((size_t)q * D + d) * (T + 2) + t];
         }
+        s_cols[t] = u;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
+        double u = s_cols[t];
         if (t < T) {
             // time-step weights and divisor are exactly 1 (PolicyImprovement.cpp:533,684-704)
             u *= 1.0;
@@ -1320,6 +1481,7 @@ apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int
             p.updates[((size_t)q * D + d) * T + t] = u;
             p.theta_all[((size_t)q * D + d) * N + kPad + t] += 1.0 * u;
         } else if (p.use_noise_adaptation) {
+            const double denom = s_cols[T + 1];
             p.fprob_sum[(size_t)q * D + d] = denom;
             const double frob_stddev = sqrt(u / (denom * T));
             const double update_rate = 0.2;
@@ -1329,6 +1491,17 @@ apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int
             store_sampler_coefficients(p, q, d, sd);
         }
     }
+}
+
+// dynamic shared memory: T + 2 doubles
+__global__ void __launch_bounds__(256)
+apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int nchunks)
+{
+    extern __shared__ double smem[];
+    const int d = blockIdx.x, q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 4);
+    apply_update_body(p, q, d, from_partials, nchunks, smem);
     tls.end();
 }
 
