@@ -221,16 +221,22 @@ def run_ours(args):
     states_per_step = Q * K * T                       # whole job, all ranks
     flusher = L2Flusher(local) if args.l2 == "flush" else None
 
+    eng_kind = eng.state_kernel_kind()
+
+    # clocks / throttle reasons are sampled from before the warm-up to the end of the last measured pass: the timed
+    # region itself lasts a few milliseconds, less than one nvidia-smi sampling period
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+
     # ---- warm-up ----
     eng.begin_solve()
     eng.run(0, args.warmup)
     it = args.warmup
 
     # ---- timed region: device-side (value) ----
-    sampler = ClockSampler(local)
     dist_barrier(dist, local)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launch_count()
     total_ms = 0.0
     if flusher is None:
@@ -256,7 +262,6 @@ def run_ours(args):
     eng.run(it, args.steps)
     steady_ms = dist_max(dist, eng.timer_end(), local)
     it += args.steps
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel pass for the roofline of the dominant kernel (rollout cost) ----
     eng.set_profiling(True)
@@ -285,16 +290,34 @@ def run_ours(args):
     eng.finish_solve()                                               # D2H: solution
     e2e_s = dist_max(dist, time.perf_counter() - t0, local)
     dist_barrier(dist, local)
+    if rank == 0 and world == 1:
+        # keep the GPU under the same load until nvidia-smi has had a few sampling periods
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:
+            eng.begin_solve()
+            eng.run(0, 50)
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         eng.close()
         return
 
     peaks, peak_kind = measured_peaks()
+    # the dominant kernel of the cost path: the state kernel (FK + sphere / SDF verdicts), one launch per step
     cost_ms, cost_n = stats["cost"]
+    rows_ms, rows_n = stats["rows"]
     states_per_launch = (eng.Q * K * T) // (world if shard_mode == 0 else 1)
     alg_bytes = (8 * D + 4 * S + 9) * states_per_launch
-    achieved = alg_bytes / (cost_ms / max(cost_n, 1) * 1e-3) / 1e9 if cost_ms > 0 else None
+    avg_cost_ms = cost_ms / max(cost_n, 1)
+    avg_rows_ms = rows_ms / max(rows_n, 1)
+    achieved = alg_bytes / (avg_cost_ms * 1e-3) / 1e9 if cost_ms > 0 else None
+    # SURVEY 8(d) counts K4 + K5 + K6 (state costs + control-cost rows) as one 8D+4S+9 B/state pass: the same bytes
+    # over the sum of the two kernels' launch times
+    achieved_path = alg_bytes / ((avg_cost_ms + avg_rows_ms) * 1e-3) / 1e9 if cost_ms > 0 else None
+    kind, kind_note = eng_kind
+    # FP64 arithmetic of the state kernel: FP64-pipe warp instructions per state from the kernel's SASS
+    fp64_ops = {7: 380}.get(D)   # iiwa structure: 254 DFMA + 79 DADD + 47 DMUL of 968 SASS instructions (tools/spec_sass.cu)
+    fp64_peak = 18.43e12          # profiles/r1_fp64_peak_b200.json: DFMA / DADD / DMUL issue rate, thread-ops/s
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
@@ -330,10 +353,20 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "steady_state": {"value": states_per_step * args.steps / (steady_ms * 1e-3), "ms_per_step": steady_ms / args.steps,
                          "what": "same steps queued back to back without L2 flushes, as solve() runs them"},
-        "roofline": {"kernel": "rollout_cost_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+        "roofline": {"kernel": "stomp_b200_states_specialised" if kind == "specialised" else "rollout_states_kernel",
+                     "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                      "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic,
                      "peak_kind": peak_kind, "algorithmic_bytes_per_state": 8 * D + 4 * S + 9,
-                     "states_per_launch": states_per_launch, "avg_launch_ms": cost_ms / max(cost_n, 1)},
+                     "states_per_launch": states_per_launch, "avg_launch_ms": avg_cost_ms,
+                     "state_kernel": kind + (": " + kind_note if kind_note else ""),
+                     "with_control_rows": {"kernels": "state kernel + control_rows kernel (SURVEY 8d: K4+K5+K6, same 8D+4S+9 B/state)",
+                                           "achieved": achieved_path, "frac": (achieved_path / peaks["hbm_gbs"]) if achieved_path else None,
+                                           "avg_launch_ms": avg_cost_ms + avg_rows_ms},
+                     "fp64_pipe": ({"ops_per_state": fp64_ops, "achieved_tops": fp64_ops * states_per_launch / (avg_cost_ms * 1e-3) / 1e12,
+                                    "peak_tops": fp64_peak / 1e12,
+                                    "frac": fp64_ops * states_per_launch / (avg_cost_ms * 1e-3) / fp64_peak,
+                                    "what": "the arithmetic is FP64 by contract: this pipe, not HBM, is the kernel's real ceiling"}
+                                   if fp64_ops and cost_ms > 0 and kind == "specialised" else None)},
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in stats.items()},
         "cpu_baseline": cb,
     }

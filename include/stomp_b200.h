@@ -215,12 +215,13 @@ int stomp_b200_comm_init(stomp_b200_engine* e, const void* id /*[128]*/);
 /* ---- measurement ----------------------------------------------------------------------------------- */
 enum stomp_b200_kernel {
     STOMP_B200_KERNEL_SAMPLE = 0,       /* generateRollouts: L*eps contraction + mean shift + clamp */
-    STOMP_B200_KERNEL_COST = 1,         /* rollout cost: FK + sphere/SDF + control stencil + row sums */
+    STOMP_B200_KERNEL_COST = 1,         /* rollout state cost: FK + sphere/SDF verdicts (the roofline kernel, 8D+4S+9 B/state) */
     STOMP_B200_KERNEL_WEIGHTS = 2,      /* computeRolloutProbabilities */
     STOMP_B200_KERNEL_UPDATE = 3,       /* probability-weighted sums + n^T R n */
     STOMP_B200_KERNEL_APPLY = 4,        /* updateParameters + noise adaptation + noise-less rollout */
     STOMP_B200_KERNEL_REUSE = 5,        /* importance sort + gather of reused rollouts */
-    STOMP_B200_KERNEL_COUNT = 6
+    STOMP_B200_KERNEL_ROWS = 6,         /* control-cost stencil + n^T R n per (rollout, joint) row */
+    STOMP_B200_KERNEL_COUNT = 7
 };
 /* when on, every launch of the kernels above is bracketed by CUDA events on the engine's stream */
 int stomp_b200_set_profiling(stomp_b200_engine* e, int32_t on);

@@ -24,7 +24,7 @@ TENSORS = dict(rollouts=0, noise=1, state_costs=2, verdicts=3, control_costs=4, 
                total_cost=7, probabilities=8, full_probabilities=9, updates=10, parameters=11, parameters_all=12,
                stddevs=13, noiseless_state_costs=14, noiseless_control_costs=15, unit_noise=16, epsilon=17,
                rollout_validity=18)
-KERNELS = dict(sample=0, cost=1, weights=2, update=3, apply=4, reuse=5)
+KERNELS = dict(sample=0, cost=1, weights=2, update=3, apply=4, reuse=5, rows=6)
 
 # every symbol include/stomp_b200.h declares (tests/test_cabi_symbols.py checks the library exports them)
 SYMBOLS = [

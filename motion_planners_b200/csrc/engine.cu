@@ -272,7 +272,7 @@ enum NoiseMode { kNoisePhilox = 0, kNoiseUnit = 1, kNoiseEpsilon = 2 };
 // one Stomp::runSingleIteration for all local queries, queued on the stream (no host synchronisation)
 // eight-rows-per-warp control-cost kernel (kernels.cuh): instantiated for the group counts of the usual T
 template <int kGroups>
-bool launch_rows_tile_g(stomp_b200_engine* e, const LoopParams& lp, int rows, cudaStream_t stream)
+bool launch_rows_tile_g(stomp_b200_engine* e, const LoopParams& lp, int rows, cudaStream_t stream, bool share_sm)
 {
     const size_t smem = sizeof(double) * (size_t)kTileWarps * 8 * tile_noise_stride(kGroups);
     const dim3 grid((rows + kTileWarps * 8 - 1) / (kTileWarps * 8), lp.Q);
@@ -286,19 +286,24 @@ bool launch_rows_tile_g(stomp_b200_engine* e, const LoopParams& lp, int rows, cu
         configured = true;
     }
     if (smem > 200 * 1024) return false;
-    if (lp.control_costs) control_rows_tile_kernel<kGroups, true><<<grid, kTileWarps * 32, smem, stream>>>(lp);
-    else control_rows_tile_kernel<kGroups, false><<<grid, kTileWarps * 32, smem, stream>>>(lp);
+    // (Capping this grid's residency so that it shares every SM with the state kernel was tried — 32 KB of shared memory
+    // per one-warp CTA, 7 per SM — and lost: a tile's latency is ~10 us whatever runs beside it, so 3.5 waves of 7 warps
+    // took 42 us.  The two kernels overlap only at their tails.)
+    (void)share_sm;
+    const size_t request = smem;
+    if (lp.control_costs) control_rows_tile_kernel<kGroups, true><<<grid, kTileWarps * 32, request, stream>>>(lp);
+    else control_rows_tile_kernel<kGroups, false><<<grid, kTileWarps * 32, request, stream>>>(lp);
     return true;
 }
 
-bool launch_rows_tile(stomp_b200_engine* e, const LoopParams& lp, int rows, cudaStream_t stream)
+bool launch_rows_tile(stomp_b200_engine* e, const LoopParams& lp, int rows, cudaStream_t stream, bool share_sm)
 {
     const int g = tile_groups(lp.N);
-    if (g <= 2) return launch_rows_tile_g<2>(e, lp, rows, stream);
-    if (g <= 4) return launch_rows_tile_g<4>(e, lp, rows, stream);
-    if (g <= 7) return launch_rows_tile_g<7>(e, lp, rows, stream);
-    if (g <= 11) return launch_rows_tile_g<11>(e, lp, rows, stream);
-    if (g <= 14) return launch_rows_tile_g<14>(e, lp, rows, stream);
+    if (g <= 2) return launch_rows_tile_g<2>(e, lp, rows, stream, share_sm);
+    if (g <= 4) return launch_rows_tile_g<4>(e, lp, rows, stream, share_sm);
+    if (g <= 7) return launch_rows_tile_g<7>(e, lp, rows, stream, share_sm);
+    if (g <= 11) return launch_rows_tile_g<11>(e, lp, rows, stream, share_sm);
+    if (g <= 14) return launch_rows_tile_g<14>(e, lp, rows, stream, share_sm);
     return false;
 }
 
@@ -415,7 +420,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     }
     {
         const int rows = gen_local * e->D;
-        Scope sc(e, STOMP_B200_KERNEL_COST);
+        Scope sc(e, STOMP_B200_KERNEL_ROWS);
         if (e->edge_dirty && lp.num_rules == 1) {   // padding-only rows of the control costs: constants of a solve
             edge_rows_kernel<<<e->Q, 64, 0, rows_stream>>>(lp);
             e->launch_count++;
@@ -430,7 +435,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             const bool rb4 = lp.rband_halfwidth <= 4;
             const dim3 grid((rows + 7) / 8, e->Q);
             static const bool tile_allowed = !(std::getenv("STOMP_B200_ROWS") && std::strcmp(std::getenv("STOMP_B200_ROWS"), "fast") == 0);
-            if (taps5 && rb4 && tile_allowed && launch_rows_tile(e, lp, rows, rows_stream)) {
+            if (taps5 && rb4 && tile_allowed && launch_rows_tile(e, lp, rows, rows_stream, overlap_rows)) {
                 // launched
             } else if (taps5 && rb4) control_rows_fast_kernel<true, true><<<grid, 256, 0, rows_stream>>>(lp);
             else control_rows_fast_kernel<false, false><<<grid, 256, 0, rows_stream>>>(lp);

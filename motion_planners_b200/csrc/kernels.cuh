@@ -383,9 +383,27 @@ sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_c
     TimelineScope tls(p, 0);
     double* sLt = smem;                                              // [rows][kSlabStride]; zero outside the matrix
 
-    for (int e = tid; e < rows * kSlabStride; e += blockDim.x) {
-        const int u = e / kSlabStride, j = e - u * kSlabStride, t = t_base + j;
-        sLt[e] = (u < T && j < kSlabT && t < T && t >= u) ? p.Lt[(size_t)u * T + t] : 0.0;
+    if ((T & 1) == 0) {
+        // 16-byte copies, eight in flight per thread: the fill is pure L2 latency (it was a quarter of the kernel's
+        // stall samples as a one-load-per-iteration loop, profiles/r1u)
+        constexpr int kPairs = kSlabStride / 2;        // 53 pairs per row, the last one padding
+        const int npairs = rows * kPairs;
+#pragma unroll 8
+        for (int e = tid; e < npairs; e += kDmmaWarps * 32) {
+            const int u = e / kPairs, j = 2 * (e - u * kPairs), t = t_base + j;
+            double2 v = make_double2(0.0, 0.0);
+            if (u < T && j < kSlabT && t < T && t + 1 >= u) {
+                v = *reinterpret_cast<const double2*>(p.Lt + (size_t)u * T + t);
+                if (t < u) v.x = 0.0;
+            }
+            *reinterpret_cast<double2*>(sLt + (size_t)u * kSlabStride + j) = v;
+        }
+    } else {
+#pragma unroll 8
+        for (int e = tid; e < rows * kSlabStride; e += kDmmaWarps * 32) {
+            const int u = e / kSlabStride, j = e - u * kSlabStride, t = t_base + j;
+            sLt[e] = (u < T && j < kSlabT && t < T && t >= u) ? p.Lt[(size_t)u * T + t] : 0.0;
+        }
     }
     __syncthreads();
 
@@ -459,25 +477,41 @@ sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_c
             const double* th = p.theta_all + ((size_t)q * D + d) * N + kPad;
             const double* mc = p.mincc + ((size_t)q * D + d) * T;
             const size_t row = (((size_t)q * p.slots + k) * D + d) * T;
+            // batches of four n8 tiles: the eight 16-byte loads of a batch are issued together (left to the compiler they
+            // were issued one tile at a time, each exposing an L1 / L2 round trip to the four resident warps)
 #pragma unroll
-            for (int nt = 0; nt < kSlabTiles; ++nt) {
-                const int t = t_base + 8 * nt + 2 * kq;
-                if (t < T) {
-                    const double2 th2 = *reinterpret_cast<const double2*>(th + t);
-                    const double2 mc2 = *reinterpret_cast<const double2*>(mc + t);
-                    // the arithmetic of shift_clamp_store, two time steps at once
-                    double v0 = p1 * mc2.x + p2 * th2.x + new_stddev * acc[nt][0];
-                    double v1 = p1 * mc2.y + p2 * th2.y + new_stddev * acc[nt][1];
-                    if (v0 < lo) v0 = lo;
-                    if (v0 > hi) v0 = hi;
-                    if (v1 < lo) v1 = lo;
-                    if (v1 > hi) v1 = hi;
-                    const double n0 = v0 - th2.x, n1 = v1 - th2.y;
-                    *reinterpret_cast<double2*>(p.rollouts + row + t) = make_double2(v0, v1);
-                    *reinterpret_cast<double2*>(p.noise + row + t) = make_double2(n0, n1);
-                    if (p.proj) *reinterpret_cast<double2*>(p.proj + row + t) = make_double2(th2.x + n0, th2.y + n1);
-                    if (p.store_unit) *reinterpret_cast<double2*>(p.unit_noise + gen_row + t) = make_double2(acc[nt][0], acc[nt][1]);
-                    if (d == 0 && t == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw] = 0.0;
+            for (int nb = 0; nb < kSlabTiles; nb += 4) {
+                double2 th2[4], mc2[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = t_base + 8 * (nb + i) + 2 * kq;
+                    th2[i] = make_double2(0.0, 0.0); mc2[i] = make_double2(0.0, 0.0);
+                    if (nb + i < kSlabTiles && t < T) {
+                        th2[i] = *reinterpret_cast<const double2*>(th + t);
+                        mc2[i] = *reinterpret_cast<const double2*>(mc + t);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int nt = nb + i;
+                    const int t = t_base + 8 * nt + 2 * kq;
+                    if (nt < kSlabTiles && t < T) {
+                        // the arithmetic of shift_clamp_store, two time steps at once
+                        double v0 = p1 * mc2[i].x + p2 * th2[i].x + new_stddev * acc[nt < kSlabTiles ? nt : 0][0];
+                        double v1 = p1 * mc2[i].y + p2 * th2[i].y + new_stddev * acc[nt < kSlabTiles ? nt : 0][1];
+                        if (v0 < lo) v0 = lo;
+                        if (v0 > hi) v0 = hi;
+                        if (v1 < lo) v1 = lo;
+                        if (v1 > hi) v1 = hi;
+                        const double n0 = v0 - th2[i].x, n1 = v1 - th2[i].y;
+                        *reinterpret_cast<double2*>(p.rollouts + row + t) = make_double2(v0, v1);
+                        *reinterpret_cast<double2*>(p.noise + row + t) = make_double2(n0, n1);
+                        if (p.proj) *reinterpret_cast<double2*>(p.proj + row + t) = make_double2(th2[i].x + n0, th2[i].y + n1);
+                        if (p.store_unit)
+                            *reinterpret_cast<double2*>(p.unit_noise + gen_row + t) =
+                                make_double2(acc[nt < kSlabTiles ? nt : 0][0], acc[nt < kSlabTiles ? nt : 0][1]);
+                        if (d == 0 && t == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw] = 0.0;
+                    }
                 }
             }
         } else {
