@@ -2,7 +2,8 @@
 
 ctypes binding of oracle/liboracle.so (the CPU restatement of the reference's STOMP loop).  Imported
 only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; the
-product package never imports it.  PARITY UNPINNED: see oracle/stomp_oracle.hpp.
+product package never imports it.  Pinned against the reference's own code (oracle/ref, oracle/ref_binding.py,
+tests/test_reference_pin.py, tests/golden): see oracle/stomp_oracle.hpp.
 """
 from __future__ import annotations
 

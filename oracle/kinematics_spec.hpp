@@ -2,10 +2,11 @@
 // product path (motion_planners_b200/, include/); only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may use it, and only as the checker / reported CPU baseline.
 //
-// PARITY UNPINNED for this file: the forward kinematics and the collision verdict of the reference live
-// in un-vendored, un-pinned third-party code (robot_model -> KDL / FCL; call sites
-// src/planners/src/wrappers/stomp/OptimizationTask.cpp:190,192) and the reference ships no golden
-// vectors for them.  This header therefore *defines* the link-sphere-vs-SDF task named by
+// PARITY STATUS OF THIS FILE — the one part of the path that stays UNPINNED: the forward kinematics and the
+// collision verdict of the reference live in un-vendored, un-pinned third-party code (robot_model -> KDL / FCL;
+// call sites src/planners/src/wrappers/stomp/OptimizationTask.cpp:190,192), absent from this image, and the
+// reference ships no golden vectors for them.  (Everything else — the STOMP loop itself — is pinned against the
+// reference's own compiled code: oracle/ref/.)  This header therefore *defines* the link-sphere-vs-SDF task named by
 // BASELINE.json's north_star; what is inherited from the reference is the semantics of the result:
 // cost 1.0 / 0.0 per timestep and validity == verdict of the LAST timestep
 // (OptimizationTask.cpp:183-204).

@@ -2,8 +2,8 @@
 
 Written from the reference's behaviour, not from oracle/stomp_oracle.cpp, and vectorised differently
 (whole-array expressions instead of ordered loops), so that a misreading of the reference in one of the
-two restatements shows up as a disagreement in tests/test_oracle_cross.py.  PARITY UNPINNED: the
-reference ships no golden vectors for this path.
+two restatements shows up as a disagreement in tests/test_oracle_cross.py.  (The C++ restatement is, in addition,
+pinned against the reference's own compiled code: oracle/ref, tests/test_reference_pin.py.)
 
 Citations are relative to /root/reference/src/planners/.
 """

@@ -1,6 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  extern "C" surface of the CPU restatement, bound with ctypes by
 // tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference).  Never linked into
-// or called by the product library.  PARITY UNPINNED (see stomp_oracle.hpp).
+// or called by the product library.  Parity status: see stomp_oracle.hpp.
 #include <chrono>
 #include <cstring>
 #include <memory>
@@ -268,6 +268,10 @@ int oracle_solve(void* hp, int max_iterations, int honour_stop, double* solution
     (void)h;
     return oracle_finish_solve(hp, solution, iterations_used);
 }
+
+// the sphere / SDF task of a handle, for oracle/ref/ref_driver.cpp (which evaluates the reference's own loop on it)
+void* oracle_task(void* hp) { return static_cast<OracleHandle*>(hp)->task.get(); }
+const void* oracle_config_of(void* hp) { return &static_cast<OracleHandle*>(hp)->cfg; }
 
 int oracle_num_rollouts(void* hp, int32_t* num_rollouts, int32_t* num_rollouts_gen)
 {

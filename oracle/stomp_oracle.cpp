@@ -1,5 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  See stomp_oracle.hpp for the header comment, the "parity
-// unpinned" statement and the rule on who may use this code.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  See stomp_oracle.hpp for the header comment, the parity
+// status (pinned against the reference's own code, oracle/ref) and the rule on who may use this code.
 #include "stomp_oracle.hpp"
 
 #include <algorithm>

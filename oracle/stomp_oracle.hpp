@@ -5,10 +5,18 @@
 // reference itself cannot be compiled here — SURVEY.md §8c).  Each function cites the reference
 // file:line it follows (paths relative to /root/reference/).
 //
-// PARITY UNPINNED: the reference ships no golden vectors / asserting tests for this path
-// (SURVEY.md §4), and cannot be built here to generate any.  The restatement is pinned instead by
-// (1) the invariants that follow from the reference code (tests/test_oracle_invariants.py),
-// (2) an independently written NumPy restatement (oracle/numpy_ref.py) compared on random shapes.
+// PARITY PINNED AGAINST THE REFERENCE'S OWN CODE.  The reference ships no golden vectors for this path
+//  and its full build needs Rock / Eigen / Boost / robot_model / FCL, none of which are in this
+// image — but its STOMP core (src/planners/stomp/src/{Stomp,PolicyImprovement,CovariantMovementPrimitive,
+// StompUtils}.cpp + headers) only needs a slice of Eigen and Boost.  oracle/ref/ compiles those UNMODIFIED
+// sources where they lie against small stand-ins (oracle/ref/shim) into oracle/_ref/libstomp_ref.so, and
+// tests/test_reference_pin.py runs whole solves through both with the same standard normals: every rollout
+// field, the update, the parameters, the adapted noise, the noise-less rollout and the stop rule agree to
+// 1e-12 relative (bit for bit in practice), with and without rollout reuse, clamping, noise decay, warm start.
+// tests/golden/*.npz are vectors written by that build (tests/golden/make_golden.py) for machines without the
+// reference.  Further pins: (1) the invariants that follow from the reference code
+// (tests/test_oracle_invariants.py), (2) an independently written NumPy restatement (oracle/numpy_ref.py).
+// What stays unpinned is the state verdict (FK + collision), see kinematics_spec.hpp.
 #pragma once
 #include <cstdint>
 #include <memory>

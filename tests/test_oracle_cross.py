@@ -1,5 +1,6 @@
 """The C++ oracle against the independently written NumPy restatement, with injected noise
-(PARITY UNPINNED by the reference: it ships no golden vectors — SURVEY.md §4)."""
+(the reference ships no golden vectors — SURVEY.md §4; the pin against its own compiled code is
+tests/test_reference_pin.py)."""
 import numpy as np
 import pytest
 

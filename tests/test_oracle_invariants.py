@@ -1,6 +1,6 @@
 """Known-answer tests for the CPU oracle: the invariants that follow directly from the reference code
 (SURVEY.md §4, items 1-10).  The reference ships no golden vectors for this path, so these — together
-with tests/test_oracle_cross.py — are what pins the restatement (PARITY UNPINNED otherwise)."""
+with tests/test_oracle_cross.py and, above all, tests/test_reference_pin.py — pin the restatement."""
 import numpy as np
 import pytest
 

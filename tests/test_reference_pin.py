@@ -1,0 +1,126 @@
+"""The CPU restatement (oracle/stomp_oracle.cpp) against the REFERENCE'S OWN CODE: /root/reference/src/planners/stomp/
+src/{Stomp,PolicyImprovement,CovariantMovementPrimitive,StompUtils}.cpp compiled unmodified against the Eigen / Boost
+stand-ins of oracle/ref/shim (oracle/ref/Makefile -> oracle/_ref/libstomp_ref.so).  Both sides are fed the same
+standard normals; every field of every rollout, the update, the parameters, the adapted noise and the noise-less
+rollout must agree to 1e-12 relative over whole solves — in practice they agree bit for bit.
+
+Runs wherever the library is (this container; the GPU box gets the prebuilt .so with the snapshot) and is skipped
+elsewhere; tests/test_golden_vectors.py holds the same comparison against committed vectors."""
+import numpy as np
+import pytest
+
+from motion_planners_b200 import problems as P
+from oracle.binding import Oracle
+from oracle import ref_binding
+
+pytestmark = pytest.mark.skipif(not ref_binding.available(), reason="oracle/_ref/libstomp_ref.so needs /root/reference to build")
+
+FIELDS = ["parameters_noise", "noise", "noise_projected", "parameters_noise_projected", "state_costs", "control_costs",
+          "total_costs", "cumulative_costs", "probabilities", "full_probabilities", "full_costs", "total_cost"]
+RTOL = 1e-12
+
+
+def _pair(pb, min_r, max_r, per_it, **kw):
+    T, D = pb.num_time_steps, pb.chain.num_dimensions
+    o = Oracle(num_time_steps=T, num_dimensions=D, min_rollouts=min_r, max_rollouts=max_r, num_rollouts_per_iteration=per_it,
+               noise_stddev=pb.noise_stddev, **kw)
+    o.set_problem(pb)
+    r = ref_binding.Reference(o)
+    r.set_start_goal(pb.start, pb.goal)
+    return o, r
+
+
+def _same(a, b, what):
+    assert a.shape == b.shape, what
+    np.testing.assert_allclose(a, b, rtol=RTOL, atol=0.0, err_msg=what)
+
+
+def _run(o, r, iterations, seed, scale_at=None):
+    rng = np.random.default_rng(seed)
+    T, D = o.T, o.D
+    o.begin_solve(); r.begin_solve()
+    counts, exact = [], True
+    for it in range(iterations):
+        G = r.next_num_generated()
+        eps = rng.standard_normal((G, D, T))
+        if scale_at is not None and it == scale_at:
+            eps *= 8.0          # pushes samples onto the joint limits: the filter / setRollouts / computeNoise path
+        stop_r, unit = r.iterate(it, eps)
+        stop_o = o.iterate(it, noise=unit)
+        assert r.num_rollouts() == o.num_rollouts()
+        for f in FIELDS:
+            a, b = r.field(f), o.field(f)
+            _same(a, b, f"iteration {it}: {f}")
+            exact = exact and np.array_equal(a, b)
+        _same(r.updates(), o.updates(), "updates")
+        _same(r.parameters(), o.parameters(), "parameters")
+        _same(r.stddevs(), o.stddevs(), "stddevs")
+        nr, no = r.noiseless(), o.noiseless()
+        assert nr["valid"] == no["valid"]
+        np.testing.assert_allclose(nr["total_cost"], no["total_cost"], rtol=RTOL)
+        np.testing.assert_allclose(nr["best_cost"], no["best_cost"], rtol=RTOL)
+        np.testing.assert_array_equal(nr["state_costs"], no["state_costs"])
+        _same(nr["control_costs"], no["control_costs"], "noise-less control costs")
+        np.testing.assert_array_equal(r.rollout_validity(), o.rollout_validity())
+        assert bool(stop_r) == bool(stop_o)
+        counts.append(r.num_rollouts()[0])
+    fr = r.finish_solve()
+    found_o, solution_o, iterations_o = o.finish_solve()
+    _same(fr["solution"], solution_o, "solution")
+    assert fr["iterations"] == iterations_o and fr["found"] == found_o
+    return counts, exact
+
+
+def test_policy_products_match_the_reference():
+    pb = P.single_arm_problem(K=8, T=100, sdf_n=64)
+    o, r = _pair(pb, 8, 8, 8)
+    po, pr = o.policy(), r.policy()
+    for k in ("R", "Rinv", "L", "params_all", "mincc", "linear"):
+        _same(pr[k], po[k], k)
+
+
+def test_whole_solve_without_reuse_matches_the_reference():
+    pb = P.single_arm_problem(K=24, T=60, sdf_n=64)
+    o, r = _pair(pb, 24, 24, 24)
+    counts, exact = _run(o, r, 6, seed=1, scale_at=2)
+    assert counts == [24, 25, 25, 25, 25, 25]
+    assert exact, "the restatement no longer matches the reference bit for bit (still within 1e-12)"
+
+
+def test_shipped_yml_shape_with_rollout_reuse_matches_the_reference():
+    # reference test/config/stomp.yml: min 5, max 50, 10 per iteration, T = 20
+    pb = P.single_arm_problem(K=10, T=20, sdf_n=64)
+    o, r = _pair(pb, 5, 50, 10)
+    counts, _ = _run(o, r, 9, seed=2)
+    assert counts == [10, 21, 32, 43, 51, 51, 51, 51, 51]
+
+
+def test_min_rollouts_above_per_iteration_matches_the_reference():
+    pb = P.single_arm_problem(K=10, T=20, sdf_n=64)
+    o, r = _pair(pb, 12, 20, 4)
+    counts, _ = _run(o, r, 6, seed=3)
+    assert counts[0] == 12
+
+
+def test_no_adaptation_and_noise_decay_matches_the_reference():
+    pb = P.single_arm_problem(K=16, T=20, sdf_n=64)
+    o, r = _pair(pb, 16, 16, 16, use_noise_adaptation=False, noise_decay=np.full(7, 0.9))
+    _run(o, r, 4, seed=4)
+
+
+def test_dual_arm_matches_the_reference():
+    pb = P.dual_arm_problem(K=12, T=30, sdf_n=64)
+    o, r = _pair(pb, 12, 12, 12)
+    _run(o, r, 3, seed=5)
+
+
+def test_warm_start_matches_the_reference():
+    # StompPlanner::updateInitialTrajectory -> updatePolicy / updateMinControlCostParameters (StompPlanner.cpp:186-208)
+    pb = P.single_arm_problem(K=12, T=30, sdf_n=64)
+    o, r = _pair(pb, 12, 12, 12)
+    _run(o, r, 2, seed=6)
+    warm = o.parameters() + 0.01
+    o.set_initial_trajectory(warm); r.set_initial_trajectory(warm)
+    for k in ("params_all", "mincc"):
+        _same(r.policy()[k], o.policy()[k], k)
+    _run(o, r, 3, seed=7)
