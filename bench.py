@@ -222,7 +222,8 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": ("the reference's own STOMP core (src/planners/stomp/src/*.cpp, unmodified) compiled against Eigen / Boost "
                  "stand-ins (oracle/ref); the FCL state query, whose libraries are not in this image, is replaced by the "
-                 "same sphere-vs-SDF task the CUDA path evaluates" if reference_kind() == "reference" else
+                 "same sphere-vs-SDF task the CUDA path evaluates; the Eigen stand-in is an unvectorised eager "
+                 "implementation, so a build against real Eigen would be faster" if reference_kind() == "reference" else
                  "oracle port of the reference's algorithm (oracle/_ref was not built: /root/reference absent at build time)"),
     }
     print(json.dumps(line), flush=True)
