@@ -230,24 +230,51 @@ int check_launch(stomp_b200_engine* e, const char* what)
     return 0;
 }
 
+// tiles per slab: the slabs of a launch are equally wide (ceil(T / 8) n8 tiles over ceil(T / 104) slabs)
+int dmma_tiles_for(int T)
+{
+    const int ntile = (T + 7) / 8;
+    const int nslabs = (ntile + kSlabTilesMax - 1) / kSlabTilesMax;
+    const int need = (ntile + nslabs - 1) / nslabs;
+    for (int cand : {4, 7, 10, 13})
+        if (cand >= need) return cand;
+    return kSlabTilesMax;
+}
+
 size_t dmma_smem_bytes(int T)
 {
-    return sizeof(double) * (size_t)dmma_slab_rows(T) * kSlabStride;
+    return sizeof(double) * (size_t)dmma_slab_rows(T) * dmma_slab_stride(dmma_tiles_for(T));
 }
 
 // FP64 tensor-core contraction (DMMA); used whenever the Lt slab fits in shared memory
+template <int kTiles, bool kPhilox>
+int launch_sample_dmma_t(stomp_b200_engine* e, const LoopParams& lp)
+{
+    static bool configured = false;      // per instantiation
+    if (!configured) {
+        CUDA_TRY(e, cudaFuncSetAttribute(sample_rollouts_dmma_kernel<kTiles, kPhilox>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        configured = true;
+    }
+    const long long total_cols = (long long)lp.Q * lp.num_gen * lp.D;
+    const int ntiles = (int)((total_cols + 7) / 8);
+    const int nslabs = (lp.T + 8 * kTiles - 1) / (8 * kTiles);
+    const size_t smem = dmma_smem_bytes(lp.T);
+    const int per_sm = smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
+    dim3 grid(std::max(1, std::min((ntiles + kDmmaWarps - 1) / kDmmaWarps, e->num_sms * per_sm)), nslabs);
+    Scope s(e, STOMP_B200_KERNEL_SAMPLE);
+    sample_rollouts_dmma_kernel<kTiles, kPhilox><<<grid, kDmmaWarps * 32, smem, e->stream>>>(lp, e->robot, lp.tile_counter);
+    return check_launch(e, "sample_rollouts_dmma_kernel");
+}
+
 template <bool kPhilox>
 int launch_sample_dmma(stomp_b200_engine* e, const LoopParams& lp)
 {
-    const long long total_cols = (long long)lp.Q * lp.num_gen * lp.D;
-    const int ntiles = (int)((total_cols + 7) / 8);
-    const int nslabs = (lp.T + kSlabT - 1) / kSlabT;
-    const size_t smem = dmma_smem_bytes(lp.T);
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
-    dim3 grid(std::max(1, std::min((ntiles + kDmmaWarps - 1) / kDmmaWarps, e->num_sms * per_sm)), nslabs);
-    Scope s(e, STOMP_B200_KERNEL_SAMPLE);
-    sample_rollouts_dmma_kernel<kPhilox><<<grid, kDmmaWarps * 32, smem, e->stream>>>(lp, e->robot, lp.tile_counter);
-    return check_launch(e, "sample_rollouts_dmma_kernel");
+    switch (dmma_tiles_for(lp.T)) {
+        case 4: return launch_sample_dmma_t<4, kPhilox>(e, lp);
+        case 7: return launch_sample_dmma_t<7, kPhilox>(e, lp);
+        case 10: return launch_sample_dmma_t<10, kPhilox>(e, lp);
+        default: return launch_sample_dmma_t<13, kPhilox>(e, lp);
+    }
 }
 
 template <bool kPhilox>
@@ -313,6 +340,8 @@ codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
     opt.wide_index = e->sdf.wide_index != 0;
     opt.magic_floor = codegen::magic_floor_is_safe(e->robot, e->sdf);
     if (const char* f = std::getenv("STOMP_B200_STATES_FLOOR")) opt.magic_floor = opt.magic_floor && std::strcmp(f, "cvt") != 0;
+    opt.inside_grid = codegen::reach_is_inside_grid(e->robot, e->sdf);
+    if (const char* c = std::getenv("STOMP_B200_STATES_CLAMP")) opt.inside_grid = opt.inside_grid && std::atoi(c) == 0;
     if (const char* b = std::getenv("STOMP_B200_STATES_MIN_BLOCKS")) opt.min_blocks = std::atoi(b);   // tuning knobs
     if (const char* l = std::getenv("STOMP_B200_STATES_LAG")) opt.compare_lag = std::max(0, std::atoi(l));
     if (const char* j = std::getenv("STOMP_B200_STATES_STAGE")) opt.stage_joints = std::atoi(j) != 0;
@@ -793,8 +822,6 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
         const char* sampler = std::getenv("STOMP_B200_SAMPLER");
         e->use_dmma = !(sampler && std::string(sampler) == "simt");
     }
-    CREATE_CUDA(cudaFuncSetAttribute(sample_rollouts_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    CREATE_CUDA(cudaFuncSetAttribute(sample_rollouts_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     CREATE_CUDA(cudaFuncSetAttribute(noiseless_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CREATE_CUDA(cudaFuncSetAttribute(reuse_rollouts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     std::memset(&e->robot, 0, sizeof(e->robot));
@@ -1452,6 +1479,7 @@ int stomp_b200_codegen_selftest(char* log, size_t log_capacity)
         codegen::StateKernelOptions opt;
         opt.wide_index = wide != 0;
         opt.magic_floor = wide == 0;
+        opt.inside_grid = wide == 0;
         if (!codegen::compile_to_cubin(codegen::generate_state_kernel_source(r, opt), cubin, clog, err)) {
             all_log += err;
             rc = STOMP_B200_ERR_CUDA;

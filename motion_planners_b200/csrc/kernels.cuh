@@ -192,10 +192,13 @@ __device__ __forceinline__ void philox_normals(uint64_t seed, uint32_t iteration
     const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u4f = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
+    // Box-Muller on the SFU (MUFU.LG2 / SIN / COS / RSQ): the library logf / sincospif made this function ~200
+    // instructions and 38 % of the sampler's instruction stream (profiles/r1y); the uniforms carry 24 bits, the
+    // intrinsics' ~2^-21 absolute error is below that resolution
+    const float ra = __fsqrt_rn(-2.0f * __logf(u1)), rb = __fsqrt_rn(-2.0f * __logf(u3));
     float sa, ca, sb, cb;
-    sincospif(2.0f * u2, &sa, &ca);
-    sincospif(2.0f * u4f, &sb, &cb);
+    __sincosf(6.28318530717958647692f * u2 - 3.14159265358979323846f, &sa, &ca);     // argument in [-pi, pi): the SFU's accurate range
+    __sincosf(6.28318530717958647692f * u4f - 3.14159265358979323846f, &sb, &cb);
     z[0] = (double)(ra * ca);
     z[1] = (double)(ra * sa);
     z[2] = (double)(rb * cb);
@@ -345,10 +348,12 @@ sample_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_consta
 // template argument (13 straight-line bodies behind one switch), so the inner loop is LDS + DMMA with no
 // predicates.  The epilogue holds two consecutive time steps per lane and n8 tile: 16-byte loads / stores.
 // ---------------------------------------------------------------------------------------------------
+// kTiles n8 tiles per slab (template argument: 13 for T = 100 / 200, 10 for T = 150, fewer for short trajectories —
+// the slabs of a launch are equally wide, so no warp multiplies against zero columns and short trajectories keep
+// fewer accumulators and more warps per SM)
 constexpr int kDmmaWarps = 8;
-constexpr int kSlabTiles = 13;
-constexpr int kSlabT = kSlabTiles * 8;     // 104
-constexpr int kSlabStride = 106;
+constexpr int kSlabTilesMax = 13;
+__host__ __device__ constexpr int dmma_slab_stride(int tiles) { return 8 * tiles + 2; }     // == 2 (mod 4)
 
 __host__ __device__ inline int dmma_slab_rows(int T) { return (T + 15) & ~15; }
 
@@ -358,22 +363,27 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int kFirstTile>
-__device__ __forceinline__ void dmma_chunk(double (&acc)[kSlabTiles][2], const double (&z)[4], const double* __restrict__ b0)
+template <int kFirstTile, int kTiles>
+__device__ __forceinline__ void dmma_chunk(double (&acc)[kTiles][2], const double (&z)[4], const double* __restrict__ b0)
 {
+    constexpr int kSlabStride = dmma_slab_stride(kTiles);
+    if (kFirstTile >= kTiles) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
-        for (int nt = kFirstTile; nt < kSlabTiles; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], z[j], b0[j * kSlabStride + 8 * nt]);
+        for (int nt = kFirstTile; nt < kTiles; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], z[j], b0[j * kSlabStride + 8 * nt]);
     }
 }
 
-template <bool kPhilox>
+template <int kTiles, bool kPhilox>
 __global__ void __launch_bounds__(kDmmaWarps * 32)
 sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
                             unsigned* __restrict__ tile_counter)
 {
     extern __shared__ double smem[];
+    constexpr int kSlabTiles = kTiles;
+    constexpr int kSlabT = 8 * kTiles;
+    constexpr int kSlabStride = dmma_slab_stride(kTiles);
     const int T = p.T, D = p.D, N = p.N;
     const int rows = dmma_slab_rows(T);
     const int slab = blockIdx.y;
@@ -453,19 +463,19 @@ sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_c
             }
             const double* b0 = sLt + (size_t)ub * kSlabStride + r;
             switch (u0 > t_base ? (u0 - t_base) >> 3 : 0) {      // warp-uniform
-                case 0: dmma_chunk<0>(acc, z, b0); break;
-                case 1: dmma_chunk<1>(acc, z, b0); break;
-                case 2: dmma_chunk<2>(acc, z, b0); break;
-                case 3: dmma_chunk<3>(acc, z, b0); break;
-                case 4: dmma_chunk<4>(acc, z, b0); break;
-                case 5: dmma_chunk<5>(acc, z, b0); break;
-                case 6: dmma_chunk<6>(acc, z, b0); break;
-                case 7: dmma_chunk<7>(acc, z, b0); break;
-                case 8: dmma_chunk<8>(acc, z, b0); break;
-                case 9: dmma_chunk<9>(acc, z, b0); break;
-                case 10: dmma_chunk<10>(acc, z, b0); break;
-                case 11: dmma_chunk<11>(acc, z, b0); break;
-                default: dmma_chunk<12>(acc, z, b0); break;
+                case 0: dmma_chunk<0, kTiles>(acc, z, b0); break;
+                case 1: dmma_chunk<1, kTiles>(acc, z, b0); break;
+                case 2: dmma_chunk<2, kTiles>(acc, z, b0); break;
+                case 3: dmma_chunk<3, kTiles>(acc, z, b0); break;
+                case 4: dmma_chunk<4, kTiles>(acc, z, b0); break;
+                case 5: dmma_chunk<5, kTiles>(acc, z, b0); break;
+                case 6: dmma_chunk<6, kTiles>(acc, z, b0); break;
+                case 7: dmma_chunk<7, kTiles>(acc, z, b0); break;
+                case 8: dmma_chunk<8, kTiles>(acc, z, b0); break;
+                case 9: dmma_chunk<9, kTiles>(acc, z, b0); break;
+                case 10: dmma_chunk<10, kTiles>(acc, z, b0); break;
+                case 11: dmma_chunk<11, kTiles>(acc, z, b0); break;
+                default: dmma_chunk<12, kTiles>(acc, z, b0); break;
             }
         }
         // ---- epilogue: C fragment element (row r, cols 2*kq, 2*kq + 1) of tile nt ----

@@ -322,7 +322,9 @@ __device__ __forceinline__ void apply_joint_static(Frame& f, const JointParams& 
 // reach of the chain (state_codegen.hpp: magic_floor_is_safe).
 __device__ __forceinline__ int voxel_floor_magic(double v) { return __double2loint(__dadd_rd(v, 6755399441055744.0)); }
 
-template <int kMask, bool kWide, bool kMagic>
+// kInside: the host has proved that no sphere centre can leave the grid (state_codegen.hpp: reach_is_inside_grid), so
+// the clamps — six VIMNMX per sphere, an eighth of the kernel's instructions — are identities and are left out.
+template <int kMask, bool kWide, bool kMagic, bool kInside>
 __device__ __forceinline__ const float* sphere_voxel_static(const Frame& f, const SphereParams& sp, const SdfParams& g)
 {
     double cx = f.px, cy = f.py, cz = f.pz;
@@ -330,9 +332,14 @@ __device__ __forceinline__ const float* sphere_voxel_static(const Frame& f, cons
     if (kMask & 2) { cx = fma(f.r01, sp.l[1], cx); cy = fma(f.r11, sp.l[1], cy); cz = fma(f.r21, sp.l[1], cz); }
     if (kMask & 4) { cx = fma(f.r02, sp.l[2], cx); cy = fma(f.r12, sp.l[2], cy); cz = fma(f.r22, sp.l[2], cz); }
     const double vx = fma(cx, g.inv_h, g.offx), vy = fma(cy, g.inv_h, g.offy), vz = fma(cz, g.inv_h, g.offz);
-    const int ix = min(max(kMagic ? voxel_floor_magic(vx) : __double2int_rz(vx), 0), g.nx - 1);
-    const int iy = min(max(kMagic ? voxel_floor_magic(vy) : __double2int_rz(vy), 0), g.ny - 1);
-    const int iz = min(max(kMagic ? voxel_floor_magic(vz) : __double2int_rz(vz), 0), g.nz - 1);
+    int ix = kMagic ? voxel_floor_magic(vx) : __double2int_rz(vx);
+    int iy = kMagic ? voxel_floor_magic(vy) : __double2int_rz(vy);
+    int iz = kMagic ? voxel_floor_magic(vz) : __double2int_rz(vz);
+    if (!kInside) {
+        ix = min(max(ix, 0), g.nx - 1);
+        iy = min(max(iy, 0), g.ny - 1);
+        iz = min(max(iz, 0), g.nz - 1);
+    }
     if (kWide) return g.grid + (((size_t)iz * (size_t)g.ny + (size_t)iy) * (size_t)g.nx + (size_t)ix);
     return g.grid + (unsigned)((iz * g.ny + iy) * g.nx + ix);
 }

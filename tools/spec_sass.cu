@@ -24,6 +24,7 @@ int main(int argc, char** argv)
     r.num_spheres = s;
     codegen::StateKernelOptions opt;
     opt.magic_floor = !getenv("CVT");
+    opt.inside_grid = !getenv("CLAMP");
     if (getenv("LAG")) opt.compare_lag = atoi(getenv("LAG"));
     if (getenv("MINB")) opt.min_blocks = atoi(getenv("MINB"));
     const std::string src = codegen::generate_state_kernel_source(r, opt);
