@@ -97,6 +97,7 @@ struct stomp_b200_engine {
     std::vector<void*> allocations;
 
     RobotParams robot;
+    JointLimits limits;             // robot.lower / upper, for the sampling kernels
     SdfParams sdf;
     float* d_sdf = nullptr;
     bool have_chain = false, have_spheres = false, have_sdf = false, have_matrices = false;
@@ -262,7 +263,7 @@ int launch_sample_dmma_t(stomp_b200_engine* e, const LoopParams& lp)
     const int per_sm = smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
     dim3 grid(std::max(1, std::min((ntiles + kDmmaWarps - 1) / kDmmaWarps, e->num_sms * per_sm)), nslabs);
     Scope s(e, STOMP_B200_KERNEL_SAMPLE);
-    sample_rollouts_dmma_kernel<kTiles, kPhilox><<<grid, kDmmaWarps * 32, smem, e->stream>>>(lp, e->robot, lp.tile_counter);
+    sample_rollouts_dmma_kernel<kTiles, kPhilox><<<grid, kDmmaWarps * 32, smem, e->stream>>>(lp, e->limits, lp.tile_counter);
     return check_launch(e, "sample_rollouts_dmma_kernel");
 }
 
@@ -285,12 +286,12 @@ int launch_sample(stomp_b200_engine* e, const LoopParams& lp)
     dim3 grid((ncols + 63) / 64, lp.Q);
     const int need = (lp.T + 15) / 16;
     Scope s(e, STOMP_B200_KERNEL_SAMPLE);
-    if (need <= 2) sample_rollouts_kernel<2, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
-    else if (need <= 4) sample_rollouts_kernel<4, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
-    else if (need <= 7) sample_rollouts_kernel<7, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
-    else if (need <= 10) sample_rollouts_kernel<10, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
-    else if (need <= 13) sample_rollouts_kernel<13, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
-    else sample_rollouts_kernel<16, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->robot);
+    if (need <= 2) sample_rollouts_kernel<2, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->limits);
+    else if (need <= 4) sample_rollouts_kernel<4, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->limits);
+    else if (need <= 7) sample_rollouts_kernel<7, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->limits);
+    else if (need <= 10) sample_rollouts_kernel<10, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->limits);
+    else if (need <= 13) sample_rollouts_kernel<13, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->limits);
+    else sample_rollouts_kernel<16, kPhilox><<<grid, 256, 0, e->stream>>>(lp, e->limits);
     return check_launch(e, "sample_rollouts_kernel");
 }
 
@@ -360,6 +361,11 @@ void resolve_state_kernel(stomp_b200_engine* e)
     std::string err;
     e->spec = codegen::specialised_state_kernel(e->robot, state_kernel_options(e), err);
     e->spec_note = e->spec ? std::string() : err;
+    if (!e->spec) {     // still a CUDA kernel, but say so: the generic kernel is ~2x slower
+        static bool told = false;
+        if (!told) std::fprintf(stderr, "stomp_b200: the specialised state kernel is unavailable, using the generic one: %s\n", err.c_str());
+        told = true;
+    }
 }
 
 int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop)
@@ -429,7 +435,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         Scope sc(e, STOMP_B200_KERNEL_SAMPLE);
         const int per_query = gen_local * e->D * e->T;
         dim3 grid(std::min(1024, (per_query + 255) / 256), e->Q);
-        shift_rollouts_kernel<<<grid, 256, 0, e->stream>>>(lp, e->robot);
+        shift_rollouts_kernel<<<grid, 256, 0, e->stream>>>(lp, e->limits);
         if (int rc = check_launch(e, "shift_rollouts_kernel")) return rc;
     } else if (mode == kNoiseEpsilon) {
         if (int rc = launch_sample<false>(e, lp)) return rc;
@@ -490,7 +496,8 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             a.sums = lp.sums; a.stop = lp.stop; a.tile_counter = lp.tile_counter;
             a.timeline = lp.timeline ? lp.timeline + 2 * 1 : nullptr;
             a.T = lp.T; a.D = lp.D; a.slots = lp.slots; a.gslots = lp.gslots; a.sumw = lp.sumw; a.num_gen = lp.num_gen;
-            a.gen_offset = lp.gen_offset; a.honour_stop = lp.honour_stop; a.debug_skip = lp.debug_skip; a.pad_ = 0;
+            a.gen_offset = lp.gen_offset; a.honour_stop = lp.honour_stop; a.debug_skip = lp.debug_skip;
+            a.row_stride = lp.T; a.rollout_stride = (int64_t)lp.D * lp.T;
             void* args[] = {&a, &e->robot, &e->sdf};
             CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, grid, dim3(256), args, 0, e->stream));
         } else if (e->robot.simple_chain) rollout_states_kernel<true><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
@@ -559,7 +566,23 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         const size_t smem = sizeof(double) * ((size_t)e->D * e->N + e->T + e->sumw);
         e->launch_count++;
         e->kernel_launches[STOMP_B200_KERNEL_APPLY]++;
-        noiseless_rollout_kernel<<<e->Q, 256, smem, e->side_stream>>>(lp, e->robot, e->sdf);
+        int states_done = 0;
+        if (e->spec) {
+            // the verdicts of the T noise-less states from the specialised state kernel, reading the padded policy rows in
+            // place (2.5x faster than the generic FK inside noiseless_rollout_kernel, which sits at the end of every
+            // isolated iteration)
+            StateKernelArgs a;
+            a.rollouts = lp.theta_all + kPad; a.state_costs = lp.nl_state; a.verdicts = lp.nl_verdict; a.validity = lp.nl_valid;
+            a.sums = nullptr; a.stop = lp.stop; a.tile_counter = nullptr; a.timeline = nullptr;
+            a.T = lp.T; a.D = lp.D; a.slots = 1; a.gslots = 1; a.sumw = lp.sumw; a.num_gen = 1; a.gen_offset = 0;
+            a.honour_stop = lp.honour_stop; a.debug_skip = 0;
+            a.row_stride = lp.N; a.rollout_stride = (int64_t)lp.D * lp.N;
+            void* args[] = {&a, &e->robot, &e->sdf};
+            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + 255) / 256, e->Q), dim3(256), args, 0, e->side_stream));
+            e->launch_count++;
+            states_done = 1;
+        }
+        noiseless_rollout_kernel<<<e->Q, 256, smem, e->side_stream>>>(lp, e->robot, e->sdf, states_done);
         if (int rc = check_launch(e, "noiseless_rollout_kernel")) return rc;
         CUDA_TRY(e, cudaEventRecord(e->ev_noiseless, e->side_stream));
         e->noiseless_pending = true;
@@ -909,6 +932,8 @@ int stomp_b200_set_chain(stomp_b200_engine* e, int32_t num_joints, const double*
         j.axis_kind = kind;
         r.lower[d] = lower[d];
         r.upper[d] = upper[d];
+        e->limits.lower[d] = lower[d];
+        e->limits.upper[d] = upper[d];
     }
     r.simple_chain = 1;
     for (int d = 0; d < num_joints; ++d)

@@ -96,6 +96,13 @@ struct LoopParams {
     double st_dense[7];       // the same taps as a dense row, offsets -3 .. +3 (zeros included)
 };
 
+// the joint limits of OptimizationTask::filter: all the sampling kernels need of the robot (0.5 KB of kernel parameters
+// instead of the 11 KB RobotParams block)
+struct JointLimits {
+    double lower[STOMP_B200_MAX_DIMS];
+    double upper[STOMP_B200_MAX_DIMS];
+};
+
 __device__ __forceinline__ bool query_frozen(const LoopParams& p, int q) { return p.honour_stop && p.stop[q] != 0; }
 
 // In-pipeline timeline (stomp_b200_set_timeline): every CTA stamps %globaltimer when it starts and when it ends;
@@ -212,7 +219,7 @@ __device__ __forceinline__ void philox_normals(uint64_t seed, uint32_t iteration
 // =====================================================================================================
 
 // mean-shifted sample + joint-limit clamp + noise for one element; unit = (L*eps)[t]
-__device__ __forceinline__ void shift_clamp_store(const LoopParams& p, const RobotParams& robot, int q, int k, int d, int t,
+__device__ __forceinline__ void shift_clamp_store(const LoopParams& p, const JointLimits& robot, int q, int k, int d, int t,
                                                   double unit)
 {
     const double* cf = p.coef + ((size_t)q * p.D + d) * 3;
@@ -236,7 +243,7 @@ __device__ __forceinline__ void shift_clamp_store(const LoopParams& p, const Rob
 // time steps tx + 16*j, j < NT.  Lt is upper triangular: chunk kc of the u loop only touches j >= kc.
 template <int NT, bool kPhilox>
 __global__ void __launch_bounds__(256)
-sample_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot)
+sample_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ JointLimits robot)
 {
     constexpr int BM = 64, BK = 16, BN = NT * 16;
     __shared__ double As[BK][BM + 2];
@@ -377,7 +384,7 @@ __device__ __forceinline__ void dmma_chunk(double (&acc)[kTiles][2], const doubl
 
 template <int kTiles, bool kPhilox>
 __global__ void __launch_bounds__(kDmmaWarps * 32)
-sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
+sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ JointLimits robot,
                             unsigned* __restrict__ tile_counter)
 {
     extern __shared__ double smem[];
@@ -543,7 +550,7 @@ sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_c
 
 // injected unit noise (parity mode): epilogue only
 __global__ void __launch_bounds__(256)
-shift_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot)
+shift_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ JointLimits robot)
 {
     const int q = blockIdx.y;
     if (query_frozen(p, q)) return;
@@ -676,10 +683,18 @@ __device__ __forceinline__ void control_cost_store(const LoopParams& p, const do
 {
     const int T = p.T, N = p.N;
     for (int t = lane; t < T; t += 32) control_out[t] = control_cost_row(p, x, kPad + t);
+    // the 2 * kPad padding rows: one lane each (twelve dependent table walks on one lane were most of the noise-less
+    // kernel's time), then lane 0 adds them in the reference's order
+    double v = 0.0;
+    if (lane < 2 * kPad) v = control_cost_row(p, x, lane < kPad ? lane : N - (lane - kPad + 1));
     __syncwarp();
+    double first = (lane == 0) ? control_out[0] : 0.0, last = (lane == 0) ? control_out[T - 1] : 0.0;
+#pragma unroll
+    for (int i = 0; i < kPad; ++i) {
+        first += __shfl_sync(0xffffffffu, v, i);
+        last += __shfl_sync(0xffffffffu, v, kPad + i);
+    }
     if (lane == 0) {
-        double first = control_out[0], last = control_out[T - 1];
-        for (int i = 0; i < kPad; ++i) { first += control_cost_row(p, x, i); last += control_cost_row(p, x, N - (i + 1)); }
         control_out[0] = first;
         control_out[T - 1] = last;
     }
@@ -1557,7 +1572,7 @@ apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
 noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
-                         const __grid_constant__ SdfParams sdf)
+                         const __grid_constant__ SdfParams sdf, int states_done)
 {
     extern __shared__ double smem[];
     const int q = blockIdx.x;
@@ -1570,13 +1585,17 @@ noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_cons
     double* ssum = sstate + T;              // [1 + 2D]
     for (int e = tid; e < D * N; e += blockDim.x) sx[e] = p.theta_all[(size_t)q * D * N + e];
     __syncthreads();
-    for (int t = tid; t < T; t += blockDim.x) {
-        const double* xq = sx + kPad + t;
-        const bool hit = state_collides<false>(robot, sdf, [&](int d) { return xq[(size_t)d * N]; });
-        sstate[t] = hit ? 1.0 : 0.0;
-        p.nl_state[(size_t)q * T + t] = sstate[t];
-        p.nl_verdict[(size_t)q * T + t] = hit ? 1 : 0;
-        if (t == T - 1) p.nl_valid[q] = hit ? 0 : 1;
+    if (states_done) {      // the specialised state kernel ran on the padded policy rows just before this launch
+        for (int t = tid; t < T; t += blockDim.x) sstate[t] = p.nl_state[(size_t)q * T + t];
+    } else {
+        for (int t = tid; t < T; t += blockDim.x) {
+            const double* xq = sx + kPad + t;
+            const bool hit = state_collides<false>(robot, sdf, [&](int d) { return xq[(size_t)d * N]; });
+            sstate[t] = hit ? 1.0 : 0.0;
+            p.nl_state[(size_t)q * T + t] = sstate[t];
+            p.nl_verdict[(size_t)q * T + t] = hit ? 1 : 0;
+            if (t == T - 1) p.nl_valid[q] = hit ? 0 : 1;
+        }
     }
     __syncthreads();
     // control costs (noise = 0: parameters + 0.0 is exact) and sums

@@ -17,6 +17,7 @@ typedef int int32_t;
 typedef unsigned int uint32_t;
 typedef unsigned char uint8_t;
 typedef unsigned long long uint64_t;
+typedef long long int64_t;
 #else
 #include <cstdint>
 
@@ -354,7 +355,9 @@ struct StateKernelArgs {
     const int32_t* stop;           // [Q]
     uint32_t* tile_counter;        // [4]
     unsigned long long* timeline;  // first-start / last-end stamps of this kernel, or null
-    int32_t T, D, slots, gslots, sumw, num_gen, gen_offset, honour_stop, debug_skip, pad_;
+    int32_t T, D, slots, gslots, sumw, num_gen, gen_offset, honour_stop, debug_skip;
+    int32_t row_stride;            // doubles between consecutive joints of one rollout (T; N for the padded policy rows)
+    int64_t rollout_stride;        // doubles between consecutive rollouts (D * T)
 };
 
 }  // namespace stomp_b200

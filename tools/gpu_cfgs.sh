@@ -3,7 +3,7 @@
 tag=${1:-x}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_$tag.log
-timeout 300 python tools/timeline.py c3 40 2>&1 | tee gpurun_out/timeline_c3_$tag.txt | grep -E "per iteration|sample |cost |reuse|weights|update|period"
+timeout 300 python tools/timeline.py c3 40 2>&1 | tee gpurun_out/timeline_c3_$tag.txt | grep -E "per iteration|sample |cost |rows|weights|update|period"
 for w in c3 c2 c4 c5; do
   timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline --workload $w > gpurun_out/bench_${w}_$tag.json 2> gpurun_out/bench_${w}_$tag.err; echo "$w rc=$?"
   python - gpurun_out/bench_${w}_$tag.json <<'PY'

@@ -18,18 +18,21 @@ e.timer_begin()
 e.run(5, iters)
 ms = e.timer_end()
 tl = e.timeline(iters)
-names = ["sample", "cost", "weights", "update", "apply", "noiseless", "reuse", "-"]
+names = ["sample", "cost", "weights", "update", "apply", "noiseless", "rows", "-"]
 dur = tl[:, :, 1] - tl[:, :, 0]
 print(f"workload {name}: {ms / iters * 1e3:.1f} us per iteration over {iters} iterations (events)")
 for k, n in enumerate(names):
     if np.all(tl[:, k, 0] < 0):
         continue
     print(f"  {n:10s} median {np.median(dur[:, k]):8.1f} us   min {dur[:, k].min():8.1f}   max {dur[:, k].max():8.1f}")
-order = [0, 1, 2, 3, 4]
+fused = bool(np.all(tl[:, 4, 0] < 0))          # single GPU: the apply step rides on the update kernel's last CTA
+last = 3 if fused else 4
+order = [0, 1, 2, 3] + ([] if fused else [4])
 gaps = [tl[:, b, 0] - tl[:, a, 1] for a, b in zip(order[:-1], order[1:])]
-print("  gaps sample->cost->weights->update->apply (median us):", [round(float(np.median(g)), 1) for g in gaps])
-nxt = tl[1:, 0, 0] - tl[:-1, 4, 1]
-print("  gap apply -> next sample (median us):", round(float(np.median(nxt)), 1))
+print("  gaps " + "->".join(names[k] for k in order) + " (median us):", [round(float(np.median(g)), 1) for g in gaps],
+      "(cost = state kernel; the control rows ('reuse' slot) run beside it on a second stream)")
+nxt = tl[1:, 0, 0] - tl[:-1, last, 1]
+print(f"  gap {names[last]} -> next sample (median us):", round(float(np.median(nxt)), 1))
 print("  iteration period (median us):", round(float(np.median(tl[1:, 0, 0] - tl[:-1, 0, 0])), 1))
-print("  noiseless start after apply end (median us):", round(float(np.median(tl[:, 5, 0] - tl[:, 4, 1])), 1),
+print(f"  noiseless start after {names[last]} end (median us):", round(float(np.median(tl[:, 5, 0] - tl[:, last, 1])), 1),
       " noiseless end before next weights start:", round(float(np.median(tl[1:, 2, 0] - tl[:-1, 5, 1])), 1))
