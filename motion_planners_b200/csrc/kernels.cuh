@@ -454,7 +454,7 @@ sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_c
             if (live) {
                 if (kPhilox) {
                     philox_normals(p.seed, (uint32_t)p.iteration, gcol, (uint32_t)(ub >> 2), z);
-                    if (p.store_unit && slab == 0) {
+                    if (p.store_unit && slab == (int)gridDim.y - 1) {      // the last slab walks every u < T
 #pragma unroll
                         for (int m = 0; m < 4; ++m)
                             if (ub + m < T) p.epsilon[gen_row + ub + m] = z[m];

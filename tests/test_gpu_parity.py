@@ -342,3 +342,31 @@ def test_specialised_state_kernel_equals_generic_kernel_and_oracle(shape, medium
         np.testing.assert_array_equal(vs[:K], rv)
         hits += int(vs.sum())
     assert hits > 0
+
+
+@pytest.mark.parametrize("T", [20, 25, 40, 60, 100, 150, 200])
+def test_trajectory_lengths_cover_every_kernel_variant(T):
+    """T selects the kernel instantiations: tiles per slab of the DMMA sampler (4 / 7 / 10 / 13, one or two slabs), groups
+    per lane of the control-cost tile kernel (2 / 4 / 7 / 11 / 14), and — for odd T — the scalar epilogue and the generic
+    control-cost kernel.  Standard normals go through the on-device Cholesky contraction; everything downstream is
+    compared with the oracle as usual.  K = 9 leaves the last 8-row / 8-column tiles ragged."""
+    pb = P.single_arm_problem(K=9, T=T, sdf_n=64)
+    D, K = pb.chain.num_dimensions, pb.num_rollouts
+    o, e, pol = _pair(pb)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(100 + T)
+    for it in range(3):
+        eps = rng.standard_normal((K, D, T))
+        cost, valid, _ = e.iterate(it, epsilon=eps[None])
+        unit = e.tensor("unit_noise")[0]
+        ref = np.einsum("tu,kdu->kdt", pol["L"], eps)
+        np.testing.assert_allclose(unit, ref, rtol=1e-12, atol=1e-14 * abs(ref).max())
+        o.iterate(it, noise=unit)
+        _compare_iteration(o, e, cost, valid)
+    # and the on-device sampler of the same shape: replayed through the oracle
+    cost, valid, _ = e.iterate(3)
+    unit = e.tensor("unit_noise")[0]
+    ref = np.einsum("tu,kdu->kdt", pol["L"], e.tensor("epsilon")[0])
+    np.testing.assert_allclose(unit, ref, rtol=1e-12, atol=1e-14 * abs(ref).max())
+    o.iterate(3, noise=unit)
+    _compare_iteration(o, e, cost, valid)
