@@ -1005,16 +1005,26 @@ control_rows_tile_kernel(const __grid_constant__ LoopParams p)
     if (c0 < nrows && !(p.debug_skip & 2)) {
         // ---- stage: rows c0 .. c0+7 are contiguous in `noise` ----
         const double* src = p.noise + ((size_t)q * p.slots * D + c0) * T;
+        // cp.async (16 bytes, zero-filled outside the row): all ~24 copies of a lane are in flight at once.  As a
+        // load-then-store loop the compiler kept one load in flight per lane and the stage alone cost 24 L2 round trips,
+        // ~6 us of a tile's ~10 us (profiles/r1u: long-scoreboard stalls on the eight STS.128).
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const bool row_ok = c0 + r < nrows;
-            for (int j = 2 * lane; j < NS; j += 64) {
-                const int t = j - 8;
-                double2 v = make_double2(0.0, 0.0);
-                if (row_ok && t >= 0 && t < T) v = *reinterpret_cast<const double2*>(src + (size_t)r * T + t);
-                *reinterpret_cast<double2*>(ns + r * NS + j) = v;
+#pragma unroll
+            for (int j0 = 0; j0 < NS; j0 += 64) {
+                const int j = j0 + 2 * lane;
+                if (j < NS) {
+                    const int t = j - 8;
+                    const bool in = row_ok && t >= 0 && t < T;
+                    const double* g = in ? src + (size_t)r * T + t : src;
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(ns + r * NS + j);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(g), "r"(in ? 16 : 0) : "memory");
+                }
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncwarp();
     const int r = lane >> 2, kq = lane & 3;
@@ -1583,6 +1593,7 @@ noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_cons
     double* sx = smem;                      // [D][N]
     double* sstate = smem + (size_t)D * N;  // [T]
     double* ssum = sstate + T;              // [1 + 2D]
+#pragma unroll 4
     for (int e = tid; e < D * N; e += blockDim.x) sx[e] = p.theta_all[(size_t)q * D * N + e];
     __syncthreads();
     if (states_done) {      // the specialised state kernel ran on the padded policy rows just before this launch

@@ -14,13 +14,26 @@ e = binding.engine_for_problem(pb, shard_mode=1 if bench.WORKLOADS[name]["kind"]
 e.begin_solve()
 e.run(0, 5)
 e.set_timeline(True)
-e.timer_begin()
-e.run(5, iters)
-ms = e.timer_end()
+flush = len(sys.argv) > 3 and sys.argv[3] == "flush"      # isolated iterations on a cold L2, as bench.py times `value`
+if flush:
+    fl = bench.L2Flusher(0)
+    ms = 0.0
+    for i in range(iters):
+        fl.flush()
+        e.timer_begin()
+        e.run(5 + i, 1)
+        ms += e.timer_end()
+else:
+    e.timer_begin()
+    e.run(5, iters)
+    ms = e.timer_end()
 tl = e.timeline(iters)
 names = ["sample", "cost", "weights", "update", "apply", "noiseless", "rows", "-"]
 dur = tl[:, :, 1] - tl[:, :, 0]
-print(f"workload {name}: {ms / iters * 1e3:.1f} us per iteration over {iters} iterations (events)")
+print(f"workload {name}: {ms / iters * 1e3:.1f} us per iteration over {iters} iterations (events){' — isolated, L2 flushed' if flush else ''}")
+t0 = tl[:, 0, 0]
+print("  start offsets from the sampler's first CTA (median us): " + "  ".join(
+    f"{names[k]} {np.median(tl[:, k, 0] - t0):.1f}..{np.median(tl[:, k, 1] - t0):.1f}" for k in range(8) if not np.all(tl[:, k, 0] < 0)))
 for k, n in enumerate(names):
     if np.all(tl[:, k, 0] < 0):
         continue
