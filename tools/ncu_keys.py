@@ -27,14 +27,21 @@ KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 ki = hdr.index('Kernel Name')
-seen = set()
+# one instance per kernel name: the longest one (a name can cover launches of very different sizes, e.g. the state
+# kernel on K*T states and on the T states of the noise-less rollout)
+di = hdr.index('gpu__time_duration.sum')
+best = {}
 for r in rows[2:]:
     name = r[ki]
     if len(sys.argv) > 2 and sys.argv[2] not in name:
         continue
-    if name in seen:
+    try:
+        dur = float(r[di].replace(',', ''))
+    except ValueError:
         continue
-    seen.add(name)
+    if name not in best or dur > best[name][0]:
+        best[name] = (dur, r)
+for name, (dur, r) in best.items():
     print('==', name[:90])
     for k in KEYS:
         if k in hdr:
