@@ -123,6 +123,7 @@ struct stomp_b200_engine {
     bool solving = false;
     int num_rollouts = 0;           // num_rollouts_ after the previous iteration (global)
     int last_gen = 0, last_local = 0, last_noiseless_slot = -1;
+    int last_wblocks = 1;           // partial sums of the weights left in wpart by the last iteration
     bool noiseless_valid = false, adapted_valid = false;
     bool edge_dirty = true;         // edge_cost has to be recomputed (the policy was uploaded since)
     // state kernel specialised to the robot structure (state_codegen.hpp); resolved at the first iteration after
@@ -493,7 +494,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         if (e->spec) {
             StateKernelArgs a;
             a.rollouts = lp.rollouts; a.state_costs = lp.state_costs; a.verdicts = lp.verdicts; a.validity = lp.validity;
-            a.sums = lp.sums; a.stop = lp.stop; a.tile_counter = lp.tile_counter;
+            a.sums = lp.sums; a.s_compact = lp.s_compact; a.stop = lp.stop; a.tile_counter = lp.tile_counter;
             a.timeline = lp.timeline ? lp.timeline + 2 * 1 : nullptr;
             a.T = lp.T; a.D = lp.D; a.slots = lp.slots; a.gslots = lp.gslots; a.sumw = lp.sumw; a.num_gen = lp.num_gen;
             a.gen_offset = lp.gen_offset; a.honour_stop = lp.honour_stop; a.debug_skip = lp.debug_skip;
@@ -526,25 +527,35 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         NCCL_TRY(e, g_nccl.AllGather(lp.sums + (size_t)c.rank * count, lp.sums, count, ncclFloat64, e->comm, e->stream));
     }
 
+    // one launch for K7-K9 when nothing sits between them (no exchange, no reused rollouts, no per-kernel profiling)
+    static const bool fuse_allowed = !(std::getenv("STOMP_B200_FUSE_WEIGHTS") && std::strcmp(std::getenv("STOMP_B200_FUSE_WEIGHTS"), "0") == 0);
+    const bool fuse_weights = fuse_allowed && world == 1 && !e->profiling && !e->reuse_possible && reused == 0;
+    const int nchunks = std::max(1, (lp.num_local + lp.chunk - 1) / lp.chunk);
+    lp.nchunks = nchunks;
+    if (fuse_weights) {
+        lp.wblocks = 1;
+        const size_t smem = sizeof(double) * std::max<size_t>(2 * (size_t)lp.chunk, (size_t)e->T + 2);
+        Scope sc(e, STOMP_B200_KERNEL_UPDATE);
+        weights_update_kernel<<<dim3(lp.nchunks, e->D, e->Q), kUpdateThreads, smem, e->stream>>>(lp);
+        if (int rc = check_launch(e, "weights_update_kernel")) return rc;
+    }
     // ---- probabilities (K7) ----
-    {
+    if (!fuse_weights) {
         lp.wblocks = std::max(1, std::min(kWeightBlocksMax, (n + kWeightThreads - 1) / kWeightThreads));
         Scope sc(e, STOMP_B200_KERNEL_WEIGHTS);
         rollout_weights_kernel<<<dim3(lp.wblocks, e->D, e->Q), kWeightThreads, 0, e->stream>>>(lp);
         if (int rc = check_launch(e, "rollout_weights_kernel")) return rc;
     }
     // ---- weighted sums (K8) ----
-    const int nchunks = std::max(1, (lp.num_local + lp.chunk - 1) / lp.chunk);
-    lp.nchunks = nchunks;
     const bool fuse_apply = world == 1 && !e->profiling;     // the apply step rides on the update kernel's last chunk CTA
-    {
+    if (!fuse_weights) {
         const size_t smem = sizeof(double) * std::max<size_t>(2 * (size_t)lp.chunk, (size_t)e->T + 2);
         Scope sc(e, STOMP_B200_KERNEL_UPDATE);
         weighted_update_kernel<<<dim3(nchunks, e->D, e->Q), kUpdateThreads, smem, e->stream>>>(lp, fuse_apply ? 1 : 0);
         if (int rc = check_launch(e, "weighted_update_kernel")) return rc;
     }
     // ---- exchange 2: update rows + adaptation numerators ----
-    if (world > 1) {
+    if (world > 1 && !fuse_weights) {
         {
             Scope sc(e, STOMP_B200_KERNEL_UPDATE);
             reduce_partials_kernel<<<dim3(e->D, e->Q), 256, 0, e->stream>>>(lp, nchunks);
@@ -554,11 +565,12 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         NCCL_TRY(e, g_nccl.AllReduce(lp.updbuf, lp.updbuf, count, ncclFloat64, ncclSum, e->comm, e->stream));
     }
     // ---- apply (K9) ----
-    if (!fuse_apply) {
+    if (!fuse_apply && !fuse_weights) {
         Scope sc(e, STOMP_B200_KERNEL_APPLY);
         apply_update_kernel<<<dim3(e->D, e->Q), 256, sizeof(double) * ((size_t)e->T + 2), e->stream>>>(lp, world > 1 ? 0 : 1, nchunks);
         if (int rc = check_launch(e, "apply_update_kernel")) return rc;
     }
+    e->last_wblocks = lp.wblocks;
     // ---- noise-less rollout (K10) on the side stream: overlaps the next iteration's sampling and costs ----
     {
         CUDA_TRY(e, cudaEventRecord(e->ev_applied, e->stream));
@@ -573,7 +585,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             // isolated iteration)
             StateKernelArgs a;
             a.rollouts = lp.theta_all + kPad; a.state_costs = lp.nl_state; a.verdicts = lp.nl_verdict; a.validity = lp.nl_valid;
-            a.sums = nullptr; a.stop = lp.stop; a.tile_counter = nullptr; a.timeline = nullptr;
+            a.sums = nullptr; a.s_compact = nullptr; a.stop = lp.stop; a.tile_counter = nullptr; a.timeline = nullptr;
             a.T = lp.T; a.D = lp.D; a.slots = 1; a.gslots = 1; a.sumw = lp.sumw; a.num_gen = 1; a.gen_offset = 0;
             a.honour_stop = lp.honour_stop; a.debug_skip = 0;
             a.row_stride = lp.N; a.rollout_stride = (int64_t)lp.D * lp.N;
@@ -800,6 +812,8 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.wpart, Q * D * b.wblocks_cap));
     CREATE_TRY(dev_alloc(e, &b.edge_cost, Q * D * 6));
     CREATE_TRY(dev_alloc(e, &b.done_counter, Q * D));
+    CREATE_TRY(dev_alloc(e, &b.s_compact, Q * GS));
+    CREATE_TRY(dev_alloc(e, &b.c_compact, Q * D * GS));
     CREATE_TRY(dev_alloc(e, &b.tile_counter, 4));
     CREATE_TRY(dev_alloc(e, &e->d_timeline, (size_t)kTimelineRing * kTimelineKernels * 2));
     b.world_size = world;
@@ -1229,7 +1243,7 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
             std::vector<double> pr(Q * e->gslots * D), part(Q * D * b.wblocks_cap);
             CUDA_TRY(e, cudaMemcpy(pr.data(), b.prob, sizeof(double) * pr.size(), cudaMemcpyDeviceToHost));
             CUDA_TRY(e, cudaMemcpy(part.data(), b.wpart, sizeof(double) * part.size(), cudaMemcpyDeviceToHost));
-            const int wblocks = std::max(1, std::min(kWeightBlocksMax, ((int)ng + kWeightThreads - 1) / kWeightThreads));   // as launched
+            const int wblocks = e->last_wblocks;   // as launched
             double* o = static_cast<double*>(out);
             for (size_t q = 0; q < Q; ++q)
                 for (size_t d = 0; d < D; ++d) {

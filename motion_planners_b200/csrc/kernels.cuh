@@ -64,6 +64,8 @@ struct LoopParams {
     double* wpart;            // [Q][D][wblocks_cap] per-CTA sums of the unnormalised weights (rollout_weights_kernel)
     double* edge_cost;        // [Q][D][6] control costs of the band-table rows (edge_rows_kernel)
     uint32_t* done_counter;   // [Q][D] tickets of weighted_update_kernel's chunk CTAs (zero between launches)
+    double* s_compact;        // [Q][gslots]    S_k      } compact mirrors of the two columns of `sums` that the weights
+    double* c_compact;        // [Q][D][gslots] C_{k,d}  } need, contiguous in k (weights_update_kernel); null when unused
     int32_t wblocks, wblocks_cap;
     int32_t nchunks, chunk;
     double* updates;          // [Q][D][T]    last applied update (read-back)
@@ -235,7 +237,10 @@ __device__ __forceinline__ void shift_clamp_store(const LoopParams& p, const Joi
     p.noise[o] = nz;
     if (p.proj) p.proj[o] = theta + nz;          // computeProjectedNoise with M = I (PolicyImprovement.cpp:430-440)
     // S_k = sum_t state cost is accumulated with atomics by the state kernel: zeroed here, one element per rollout
-    if (d == 0 && t == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw] = 0.0;
+    if (d == 0 && t == 0) {
+        p.sums[((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw] = 0.0;
+        if (p.s_compact) p.s_compact[(size_t)q * p.gslots + (p.gen_offset + k)] = 0.0;
+    }
 }
 
 // Contraction N^T[c][t] = sum_u E^T[c][u] * Lt[u][t] over the G*D columns c = (k, d) of one query, all T
@@ -527,7 +532,10 @@ sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_c
                         if (p.store_unit)
                             *reinterpret_cast<double2*>(p.unit_noise + gen_row + t) =
                                 make_double2(acc[nt < kSlabTiles ? nt : 0][0], acc[nt < kSlabTiles ? nt : 0][1]);
-                        if (d == 0 && t == 0) p.sums[((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw] = 0.0;
+                        if (d == 0 && t == 0) {
+                            p.sums[((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw] = 0.0;
+                            if (p.s_compact) p.s_compact[(size_t)q * p.gslots + (p.gen_offset + k)] = 0.0;
+                        }
                     }
                 }
             }
@@ -851,6 +859,7 @@ control_rows_kernel(const __grid_constant__ LoopParams p)
         if (lane == 0) {
             double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
             srow[1 + d] = C_part;
+            if (p.c_compact) p.c_compact[((size_t)q * D + d) * p.gslots + (p.gen_offset + k)] = C_part;
             srow[1 + 2 * D + d] = quad;
         }
     }
@@ -963,6 +972,7 @@ control_rows_fast_kernel(const __grid_constant__ LoopParams p)
         if (lane == 0) {
             double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
             srow[1 + d] = C_part;
+            if (p.c_compact) p.c_compact[((size_t)q * D + d) * p.gslots + (p.gen_offset + k)] = C_part;
             srow[1 + 2 * D + d] = quad;
         }
     }
@@ -1099,6 +1109,7 @@ control_rows_tile_kernel(const __grid_constant__ LoopParams p)
         if (live && kq == 0) {
             double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
             srow[1 + d] = C_part;
+            if (p.c_compact) p.c_compact[((size_t)q * D + d) * p.gslots + (p.gen_offset + k)] = C_part;
             srow[1 + 2 * D + d] = p.use_noise_adaptation ? quad : 0.0;
         }
     }
@@ -1163,6 +1174,7 @@ rollout_states_kernel(const __grid_constant__ LoopParams p, const __grid_constan
         p.verdicts[o] = hit ? 1 : 0;
         if (t == T - 1) p.validity[(size_t)q * p.slots + k] = hit ? 0 : 1;   // last timestep only (OptimizationTask.cpp:192-202)
         if (hit) atomicAdd(p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw, 1.0);
+        if (hit && p.s_compact) atomicAdd(p.s_compact + (size_t)q * p.gslots + (p.gen_offset + k), 1.0);
     }
     tls.end();
 }
@@ -1502,6 +1514,115 @@ weighted_update_kernel(const __grid_constant__ LoopParams p, int fuse_apply)
     tls.end();
 }
 
+// K7 + K8 + K9 in one launch (single GPU, no rollout reuse): computeRolloutProbabilities, computeParameterUpdates and
+// updateParameters.  grid (chunks, D, Q), 256 threads.  Every CTA finds the min / max of its joint's costs itself — a
+// coalesced scan of the compact mirrors s_compact / c_compact (2 x 8 K' bytes, L2 hits after the first CTA) — weighs
+// the rollouts of its chunk (exp), streams their noise rows, and leaves the UNNORMALISED partial sums
+//   out[t] = sum_k p_k noise_k[t],  out[T] = sum_k p_k (n^T R n)_k,  out[T+1] = sum_k p_k
+// in `partial`; the last CTA of the (joint, query) adds the chunks in chunk order and divides by sum_k p_k
+// (probabilities_ = p / p_sum, PolicyImprovement.cpp:546-549; the division commutes with the sum over k up to
+// rounding).  Replaces rollout_weights_kernel -> gap -> weighted_update_kernel: one launch, one exposed L2 scan less.
+__global__ void __launch_bounds__(kUpdateThreads)
+weights_update_kernel(const __grid_constant__ LoopParams p)
+{
+    extern __shared__ double smem[];   // [chunk] weights, [chunk] weight * quad ; later [T + 2] column sums
+    __shared__ double scratch[32];
+    __shared__ double s_half[128];
+    const int d = blockIdx.y, q = blockIdx.z, c = blockIdx.x;
+    if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 3);
+    const int T = p.T, D = p.D, tid = threadIdx.x, n = p.num_rollouts;
+    const int half = tid >> 7, lt = tid & 127;
+    const int k_begin = c * p.chunk, k_end = min(p.num_local, (c + 1) * p.chunk);
+    const int nk = k_end - k_begin;
+    double* sp = smem;
+    double* sq = smem + p.chunk;
+    if (c == 0 && d == 0 && p.noiseless_slot >= 0) materialise_noiseless(p, q, tid, blockDim.x);
+
+    // ---- min / max of cumulative_costs_[d] = S + C_d over all rollouts (PolicyImprovement.cpp:501-513) ----
+    const double* S = p.s_compact + (size_t)q * p.gslots;
+    const double* C = p.c_compact + ((size_t)q * D + d) * p.gslots;
+    const double* nl = p.nl_sums + (size_t)q * p.sumw;
+    auto cum_of = [&](int g) { return (g == p.noiseless_gslot) ? 1.0 * (nl[0] + nl[1 + d]) : 1.0 * (S[g] + C[g]); };
+    double mn = 1e300, mx = -1e300;
+#pragma unroll 8
+    for (int k = tid; k < n; k += kUpdateThreads) {
+        const double cum = cum_of(k);
+        mn = fmin(mn, cum); mx = fmax(mx, cum);
+    }
+    mn = block_reduce<1>(mn, scratch); mx = block_reduce<2>(mx, scratch);
+    double den = mx - mn;
+    if (den < 1e-8) den = 1e-8;
+    const double h = p.cost_scaling_h;
+
+    // ---- unnormalised weights of this chunk ----
+    double psum_part = 0.0;
+    for (int k = k_begin + tid; k < k_end; k += blockDim.x) {
+        const int g = (k == p.noiseless_slot) ? p.noiseless_gslot : ((k < p.num_gen) ? p.gen_offset + k : k);
+        const double pr = 1.0 * exp(((-h) * (cum_of(g) - mn)) / den);      // importance_weight_ = 1
+        const size_t o = ((size_t)q * p.gslots + g) * D + d;
+        p.prob[o] = pr;
+        p.fprob[o] = pr;
+        psum_part += pr;
+        double w = pr, fq = 0.0;
+        if (k == p.noiseless_slot) w = 0.0;       // zero noise: contributes nothing (PolicyImprovement.cpp:407-410)
+        else if (p.use_noise_adaptation) fq = pr * p.sums[((size_t)q * p.gslots + g) * p.sumw + 1 + 2 * D + d];
+        sp[k - k_begin] = w;
+        sq[k - k_begin] = fq;
+        if (d == 0) {   // total_cost_ (:451-462)
+            const double* s = cost_row(p, q, g);
+            double cost = s[0];
+            for (int dd = 0; dd < D; ++dd) cost += s[1 + dd];
+            p.total_cost[(size_t)q * p.gslots + g] = cost;
+        }
+    }
+    __syncthreads();
+    double* out = p.partial + (((size_t)q * p.nchunks + c) * D + d) * (T + 2);
+    for (int t0 = 0; t0 < T; t0 += 128) {
+        const int t = t0 + lt;
+        double acc = 0.0;
+        if (t < T) {
+            const double* nz = p.noise + (((size_t)q * p.slots + k_begin) * D + d) * T + t;
+            const size_t stride = (size_t)D * T;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = half;
+            for (; k + 30 < nk; k += 32) {       // rows k, k+2, ..., k+30
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = nz[(size_t)(k + 2 * u) * stride];
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    a0 += v[u] * sp[k + 2 * u]; a1 += v[u + 1] * sp[k + 2 * u + 2];
+                    a2 += v[u + 2] * sp[k + 2 * u + 4]; a3 += v[u + 3] * sp[k + 2 * u + 6];
+                }
+            }
+            for (; k < nk; k += 2) a0 += nz[(size_t)k * stride] * sp[k];
+            acc = (a0 + a1) + (a2 + a3);
+        }
+        if (half == 1) s_half[lt] = acc;
+        __syncthreads();
+        if (half == 0 && t < T) out[t] = acc + s_half[lt];
+        __syncthreads();
+    }
+    double numer = 0.0;
+    for (int k = tid; k < nk; k += blockDim.x) numer += sq[k];
+    numer = block_reduce<0>(numer, scratch);
+    psum_part = block_reduce<0>(psum_part, scratch);
+    if (tid == 0) { out[T] = numer; out[T + 1] = psum_part; }
+
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(p.done_counter + (size_t)q * D + d, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        apply_update_body(p, q, d, 2, (int)gridDim.x, smem);
+        if (tid == 0) p.done_counter[(size_t)q * D + d] = 0u;
+    }
+    tls.end();
+}
+
 // sum of the chunk partials in chunk order -> updbuf [Q][D][T+1]; only needed in front of the all-reduce
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const __grid_constant__ LoopParams p, int nchunks)
@@ -1541,8 +1662,13 @@ __device__ __forceinline__ void apply_update_body(const LoopParams& p, int q, in
         s_cols[t] = u;
     }
     __syncthreads();
+    // from_partials == 2 (weights_update_kernel): the sums carry unnormalised weights; divide by their total, which is
+    // also what the read-backs of the probabilities divide by
+    const double psum = (from_partials == 2) ? s_cols[T + 1] : 1.0;
+    if (from_partials == 2 && threadIdx.x == 0) p.wpart[((size_t)q * D + d) * p.wblocks_cap] = psum;
     for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
         double u = s_cols[t];
+        if (from_partials == 2) u = u / psum;
         if (t < T) {
             // time-step weights and divisor are exactly 1 (PolicyImprovement.cpp:533,684-704)
             u *= 1.0;
@@ -1550,7 +1676,7 @@ __device__ __forceinline__ void apply_update_body(const LoopParams& p, int q, in
             p.updates[((size_t)q * D + d) * T + t] = u;
             p.theta_all[((size_t)q * D + d) * N + kPad + t] += 1.0 * u;
         } else if (p.use_noise_adaptation) {
-            const double denom = s_cols[T + 1];
+            const double denom = (from_partials == 2) ? s_cols[T + 1] / psum : s_cols[T + 1];
             p.fprob_sum[(size_t)q * D + d] = denom;
             const double frob_stddev = sqrt(u / (denom * T));
             const double update_rate = 0.2;

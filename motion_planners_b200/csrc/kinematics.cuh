@@ -352,6 +352,7 @@ struct StateKernelArgs {
     uint8_t* verdicts;             // [Q][slots][T]
     uint8_t* validity;             // [Q][slots]
     double* sums;                  // [Q][gslots][sumw]
+    double* s_compact;             // [Q][gslots] mirror of S_k for the fused weights + update kernel, or null
     const int32_t* stop;           // [Q]
     uint32_t* tile_counter;        // [4]
     unsigned long long* timeline;  // first-start / last-end stamps of this kernel, or null

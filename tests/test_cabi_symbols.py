@@ -62,3 +62,12 @@ def test_invalid_configurations_are_rejected_before_touching_the_device():
     cfg.num_dimensions, cfg.use_projection = 7, 1         # shipped-disabled switch, not built
     assert L.stomp_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == binding.ERR_UNSUPPORTED
     assert L.stomp_b200_status_string(-2).decode().startswith("no CUDA device")
+
+
+def test_generated_state_kernel_compiles_for_sm_100a_without_a_device():
+    """csrc/state_codegen.hpp: the state kernel is generated per robot structure and compiled with NVRTC at run time.
+    The self-test generates it for a structure that uses every template branch (all axis kinds, fixed rotation,
+    prismatic joint, chain restart, every zero mask, narrow and wide voxel index) and compiles both to sm_100a cubins."""
+    rc, log = binding.codegen_selftest()
+    assert rc == 0, log
+    assert log.count("byte cubin") == 2

@@ -40,7 +40,7 @@ for k, n in enumerate(names):
     print(f"  {n:10s} median {np.median(dur[:, k]):8.1f} us   min {dur[:, k].min():8.1f}   max {dur[:, k].max():8.1f}")
 fused = bool(np.all(tl[:, 4, 0] < 0))          # single GPU: the apply step rides on the update kernel's last CTA
 last = 3 if fused else 4
-order = [0, 1, 2, 3] + ([] if fused else [4])
+order = [k for k in [0, 1, 2, 3] + ([] if fused else [4]) if not np.all(tl[:, k, 0] < 0)]   # weights is absent when K7-K9 run as one kernel
 gaps = [tl[:, b, 0] - tl[:, a, 1] for a, b in zip(order[:-1], order[1:])]
 print("  gaps " + "->".join(names[k] for k in order) + " (median us):", [round(float(np.median(g)), 1) for g in gaps],
       "(cost = state kernel; the control rows ('reuse' slot) run beside it on a second stream)")
@@ -48,4 +48,4 @@ nxt = tl[1:, 0, 0] - tl[:-1, last, 1]
 print(f"  gap {names[last]} -> next sample (median us):", round(float(np.median(nxt)), 1))
 print("  iteration period (median us):", round(float(np.median(tl[1:, 0, 0] - tl[:-1, 0, 0])), 1))
 print(f"  noiseless start after {names[last]} end (median us):", round(float(np.median(tl[:, 5, 0] - tl[:, last, 1])), 1),
-      " noiseless end before next weights start:", round(float(np.median(tl[1:, 2, 0] - tl[:-1, 5, 1])), 1))
+      " noiseless end before the next weights / update start:", round(float(np.median(tl[1:, 2 if 2 in order else 3, 0] - tl[:-1, 5, 1])), 1))
