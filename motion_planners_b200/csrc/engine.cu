@@ -124,6 +124,7 @@ struct stomp_b200_engine {
     int num_rollouts = 0;           // num_rollouts_ after the previous iteration (global)
     int last_gen = 0, last_local = 0, last_noiseless_slot = -1;
     int last_wblocks = 1;           // partial sums of the weights left in wpart by the last iteration
+    bool fuse_weights_allowed = true;   // STOMP_B200_FUSE_WEIGHTS=0 at creation keeps K7 / K8 / K9 as separate kernels
     bool noiseless_valid = false, adapted_valid = false;
     bool edge_dirty = true;         // edge_cost has to be recomputed (the policy was uploaded since)
     // state kernel specialised to the robot structure (state_codegen.hpp); resolved at the first iteration after
@@ -528,8 +529,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     }
 
     // one launch for K7-K9 when nothing sits between them (no exchange, no reused rollouts, no per-kernel profiling)
-    static const bool fuse_allowed = !(std::getenv("STOMP_B200_FUSE_WEIGHTS") && std::strcmp(std::getenv("STOMP_B200_FUSE_WEIGHTS"), "0") == 0);
-    const bool fuse_weights = fuse_allowed && world == 1 && !e->profiling && !e->reuse_possible && reused == 0;
+    const bool fuse_weights = e->fuse_weights_allowed && world == 1 && !e->profiling && !e->reuse_possible && reused == 0;
     const int nchunks = std::max(1, (lp.num_local + lp.chunk - 1) / lp.chunk);
     lp.nchunks = nchunks;
     if (fuse_weights) {
@@ -711,9 +711,11 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     e->T = cfg->num_time_steps; e->D = cfg->num_dimensions; e->N = e->T + 2 * kPad;
     e->sumw = 1 + 3 * e->D;
     if (cfg->shard_mode == 1 && cfg->world_size > 1) {
-        const int per = (cfg->num_queries + cfg->world_size - 1) / cfg->world_size;
-        e->query_offset = std::min(cfg->num_queries, cfg->rank * per);
-        e->Q = std::max(0, std::min(cfg->num_queries, e->query_offset + per) - e->query_offset);
+        // balanced contiguous blocks: floor(Q / G) queries per rank, the first Q mod G ranks one more (no rank is left
+        // empty as long as Q >= G; ceil-sized blocks left the last of 8 ranks without work at Q = 25)
+        const int per = cfg->num_queries / cfg->world_size, rem = cfg->num_queries % cfg->world_size;
+        e->query_offset = cfg->rank * per + std::min(cfg->rank, rem);
+        e->Q = per + (cfg->rank < rem ? 1 : 0);
         if (e->Q == 0) { delete e; return STOMP_B200_ERR_INVALID_ARGUMENT; }
     } else {
         e->Q = cfg->num_queries;
@@ -861,6 +863,7 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     }
     CREATE_CUDA(cudaFuncSetAttribute(noiseless_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CREATE_CUDA(cudaFuncSetAttribute(reuse_rollouts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    if (const char* f = std::getenv("STOMP_B200_FUSE_WEIGHTS")) e->fuse_weights_allowed = std::strcmp(f, "0") != 0;
     std::memset(&e->robot, 0, sizeof(e->robot));
     std::memset(&e->sdf, 0, sizeof(e->sdf));
     CREATE_CUDA(cudaStreamSynchronize(e->stream));

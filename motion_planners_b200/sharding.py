@@ -23,11 +23,10 @@ def rollout_shard(num_rollouts: int, world_size: int, rank: int):
 
 
 def query_shard(num_queries: int, world_size: int, rank: int):
-    """(offset, count) of the queries rank owns: contiguous blocks of ceil(Q / G), the last ranks may get fewer
-    (mirrors stomp_b200_create, csrc/engine.cu)."""
-    per = (num_queries + world_size - 1) // world_size
-    offset = min(num_queries, rank * per)
-    return offset, min(num_queries, offset + per) - offset
+    """(offset, count) of the queries rank owns: balanced contiguous blocks — floor(Q / G) each, the first Q mod G ranks
+    one more (mirrors stomp_b200_create, csrc/engine.cu)."""
+    per, rem = divmod(num_queries, world_size)
+    return rank * per + min(rank, rem), per + (1 if rank < rem else 0)
 
 
 def global_slot(local_slot: int, num_generated_local: int, rank: int, world_size: int, has_noiseless: bool):

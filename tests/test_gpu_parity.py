@@ -370,3 +370,25 @@ def test_trajectory_lengths_cover_every_kernel_variant(T):
     np.testing.assert_allclose(unit, ref, rtol=1e-12, atol=1e-14 * abs(ref).max())
     o.iterate(3, noise=unit)
     _compare_iteration(o, e, cost, valid)
+
+
+def test_unfused_weights_and_update_kernels_match_the_fused_kernel(monkeypatch):
+    """Single-GPU runs use weights_update_kernel (K7-K9 in one launch); multi-GPU, rollout reuse and the per-kernel
+    profiling pass use rollout_weights_kernel -> weighted_update_kernel -> apply_update_kernel.  K' = 1101 makes the
+    unfused weights kernel run three CTAs per joint (partial sums in wpart) and the update nine chunks."""
+    pb = P.single_arm_problem(K=1100, T=40, sdf_n=64)
+    fused = binding.engine_for_problem(pb, keep_debug_tensors=True)
+    monkeypatch.setenv("STOMP_B200_FUSE_WEIGHTS", "0")
+    unfused = binding.engine_for_problem(pb, keep_debug_tensors=True)
+    monkeypatch.delenv("STOMP_B200_FUSE_WEIGHTS")
+    fused.begin_solve(); unfused.begin_solve()
+    for it in range(4):
+        c1, v1, s1 = fused.iterate(it)
+        c2, v2, s2 = unfused.iterate(it)
+        np.testing.assert_array_equal(fused.tensor("epsilon")[0], unfused.tensor("epsilon")[0])
+        np.testing.assert_array_equal(fused.tensor("verdicts")[0], unfused.tensor("verdicts")[0])
+        for name in ("total_cost", "probabilities", "full_probabilities", "updates", "parameters", "stddevs"):
+            np.testing.assert_allclose(fused.tensor(name)[0], unfused.tensor(name)[0], rtol=1e-9, atol=1e-13, err_msg=name)
+        np.testing.assert_allclose(c1, c2, rtol=1e-9)
+        p = fused.tensor("probabilities")[0]
+        np.testing.assert_allclose(p.sum(0), 1.0, rtol=1e-11)

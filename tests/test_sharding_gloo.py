@@ -25,7 +25,9 @@ def test_partitions():
     shards = [sharding.query_shard(1024, 8, r) for r in range(8)]
     assert shards[0] == (0, 128) and shards[7] == (896, 128)
     odd = [sharding.query_shard(10, 4, r) for r in range(4)]
-    assert odd == [(0, 3), (3, 3), (6, 3), (9, 1)] and sum(c for _, c in odd) == 10
+    assert odd == [(0, 3), (3, 3), (6, 2), (8, 2)] and sum(c for _, c in odd) == 10       # balanced: no rank starves
+    uneven = [sharding.query_shard(25, 8, r) for r in range(8)]                               # ceil-sized blocks left rank 7 empty
+    assert [c for _, c in uneven] == [4, 3, 3, 3, 3, 3, 3, 3] and uneven[7] == (22, 3)
     assert sharding.global_slot(5, 512, 3, 8, True) == 3 * 512 + 5
     assert sharding.global_slot(512, 512, 3, 8, True) == 4096     # the noise-less rollout comes last
     with pytest.raises(IndexError):
