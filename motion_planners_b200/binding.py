@@ -214,9 +214,8 @@ class Engine:
             self.h = None
             raise StompB200Error(rc, "stomp_b200_create", lib().stomp_b200_status_string(rc).decode())
         if world_size > 1 and shard_mode == 1:
-            per = (num_queries + world_size - 1) // world_size
-            self.query_offset = min(num_queries, rank * per)
-            self.Q = min(num_queries, self.query_offset + per) - self.query_offset
+            from . import sharding
+            self.query_offset, self.Q = sharding.query_shard(num_queries, world_size, rank)   # as stomp_b200_create
         else:
             self.query_offset, self.Q = 0, num_queries
 
