@@ -8,6 +8,10 @@ start / goal of reference test/test_motion_planners.cpp:212-215.  Nothing here i
 from __future__ import annotations
 
 import dataclasses
+import hashlib
+import os
+import tempfile
+
 import numpy as np
 
 TRAJECTORY_PADDING = 6
@@ -187,6 +191,21 @@ def make_sdf(n=128, obstacles=None, lo=-1.5, hi=1.5, slab=16) -> Sdf:
     if obstacles is None:
         obstacles = make_obstacles()
     h = (hi - lo) / n
+    # The exact field of a 256^3 scene takes half a minute of NumPy (512^3: four minutes) and every rank of a benchmark
+    # builds the same one: large grids are kept on disk, keyed by everything they depend on.
+    cache_path = None
+    if n >= 128 and os.environ.get("STOMP_B200_SDF_CACHE", "1") != "0":
+        key = hashlib.sha256(repr((n, lo, hi, [(k, np.asarray(c, dtype=np.float64).tolist(), np.asarray(sz, dtype=np.float64).tolist())
+                                               for k, c, sz in obstacles])).encode()).hexdigest()[:24]
+        cache_dir = os.environ.get("STOMP_B200_CACHE_DIR", os.path.join(tempfile.gettempdir(), "stomp_b200_cache"))
+        cache_path = os.path.join(cache_dir, f"sdf_{n}_{key}.npy")
+        try:
+            grid = np.load(cache_path)
+            if grid.shape == (n, n, n) and grid.dtype == np.float32:
+                return Sdf(dims=np.array([n, n, n], dtype=np.int32), origin=np.array([lo, lo, lo], dtype=np.float64),
+                           voxel=float(h), grid=grid)
+        except (OSError, ValueError):
+            pass
     c = lo + (np.arange(n, dtype=np.float64) + 0.5) * h
     grid = np.empty((n, n, n), dtype=np.float32)
     for z0 in range(0, n, slab):
@@ -197,6 +216,15 @@ def make_sdf(n=128, obstacles=None, lo=-1.5, hi=1.5, slab=16) -> Sdf:
         for kind, centre, size in obstacles:
             dist = np.minimum(dist, _obstacle_distance(pts, kind, centre, size))
         grid[z0:z1] = dist.astype(np.float32)
+    if cache_path is not None:
+        try:
+            os.makedirs(os.path.dirname(cache_path), exist_ok=True)
+            tmp = f"{cache_path}.{os.getpid()}.tmp"
+            with open(tmp, "wb") as f:
+                np.save(f, grid)
+            os.replace(tmp, cache_path)
+        except OSError:
+            pass
     return Sdf(dims=np.array([n, n, n], dtype=np.int32), origin=np.array([lo, lo, lo], dtype=np.float64),
                voxel=float(h), grid=grid)
 
