@@ -348,6 +348,7 @@ codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
     if (const char* b = std::getenv("STOMP_B200_STATES_MIN_BLOCKS")) opt.min_blocks = std::atoi(b);   // tuning knobs
     if (const char* l = std::getenv("STOMP_B200_STATES_LAG")) opt.compare_lag = std::max(0, std::atoi(l));
     if (const char* j = std::getenv("STOMP_B200_STATES_STAGE")) opt.stage_joints = std::atoi(j) != 0;
+    if (const char* t = std::getenv("STOMP_B200_STATES_BLOCK")) { const int v = std::atoi(t); if (v == 64 || v == 128 || v == 256) opt.block_threads = v; }
     return opt;
 }
 
@@ -501,7 +502,8 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             a.gen_offset = lp.gen_offset; a.honour_stop = lp.honour_stop; a.debug_skip = lp.debug_skip;
             a.row_stride = lp.T; a.rollout_stride = (int64_t)lp.D * lp.T;
             void* args[] = {&a, &e->robot, &e->sdf};
-            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, grid, dim3(256), args, 0, e->stream));
+            const int bt = e->spec->block_threads;
+            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((states + bt - 1) / bt, e->Q), dim3(bt), args, 0, e->stream));
         } else if (e->robot.simple_chain) rollout_states_kernel<true><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
         else rollout_states_kernel<false><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
         if (int rc = check_launch(e, "rollout_states_kernel")) return rc;
@@ -590,7 +592,8 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             a.honour_stop = lp.honour_stop; a.debug_skip = 0;
             a.row_stride = lp.N; a.rollout_stride = (int64_t)lp.D * lp.N;
             void* args[] = {&a, &e->robot, &e->sdf};
-            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + 255) / 256, e->Q), dim3(256), args, 0, e->side_stream));
+            const int bt = e->spec->block_threads;
+            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + bt - 1) / bt, e->Q), dim3(bt), args, 0, e->side_stream));
             e->launch_count++;
             states_done = 1;
         }
