@@ -198,8 +198,8 @@ def cpu_baseline(problem, workload, threads, sample_rollouts, iterations, dense=
 
 
 def run_reference(args):
-    rank, world, local, dist = dist_setup(args.gpus)
-    if rank != 0:
+    # under torchrun rank 0 alone runs the CPU arm; no process group is needed (or created) for it
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import binding as ob
     problem = make_problem(args.workload)
