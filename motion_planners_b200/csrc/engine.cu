@@ -1,11 +1,16 @@
 // Host orchestration + C ABI (include/stomp_b200.h) of the B200 STOMP rollout loop.
 //
-// One engine = one GPU = one CUDA stream.  The per-iteration sequence mirrors
+// One engine = one GPU; a main stream plus two helper streams (control-cost rows beside the state kernel; the
+// noise-less rollout under the next iteration's sampling).  The per-iteration sequence mirrors
 // stomp::Stomp::runSingleIteration (reference src/planners/stomp/src/Stomp.cpp:274-301):
-//   doGenRollouts  -> [reuse_rollouts_kernel] sample_rollouts_kernel | shift_rollouts_kernel
-//   doExecuteRollouts + setRolloutCosts -> rollout_cost_kernel [reused_control_cost_kernel]
-//   improvePolicy  -> [allgather] rollout_weights_kernel, weighted_update_kernel, reduce_partials_kernel [allreduce]
-//   updateParameters + doNoiselessRollout -> apply_update_kernel
+//   doGenRollouts      -> [reuse_rollouts_kernel] sample_rollouts_dmma_kernel (| sample_rollouts_kernel | shift_rollouts_kernel)
+//   doExecuteRollouts  -> stomp_b200_states_specialised (generated, state_codegen.hpp; | rollout_states_kernel)
+//   setRolloutCosts    -> control_rows_tile_kernel (| control_rows_fast_kernel | control_rows_kernel) [reused_control_cost_kernel]
+//   improvePolicy + updateParameters
+//                      -> weights_update_kernel on one GPU; with several GPUs, rollout reuse or per-kernel profiling:
+//                         [allgather] rollout_weights_kernel, weighted_update_kernel, reduce_partials_kernel, [allreduce],
+//                         apply_update_kernel
+//   doNoiselessRollout -> the state kernel on the T noise-less states + noiseless_rollout_kernel (side stream)
 // The rollout bookkeeping (PolicyImprovement.cpp:170-186,304-308) is host integer arithmetic and stays here.
 #include <algorithm>
 #include <cmath>
