@@ -255,6 +255,15 @@ int ref_begin_solve(void* hp)
     return 0;
 }
 
+// Stomp::setCostCumulation (Stomp.cpp / PolicyImprovement.cpp:451-495): false = per-time-step costs and probabilities
+int ref_set_cost_cumulation(void* hp, int use_cumulative_costs)
+{
+    RefHandle* h = static_cast<RefHandle*>(hp);
+    if (!h->stomp) return -1;
+    h->stomp->setCostCumulation(use_cumulative_costs != 0);
+    return 0;
+}
+
 // how many rollouts the next runSingleIteration will generate (PolicyImprovement.cpp:170-186)
 int ref_next_num_generated(void* hp)
 {

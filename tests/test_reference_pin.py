@@ -35,10 +35,12 @@ def _same(a, b, what):
     np.testing.assert_allclose(a, b, rtol=RTOL, atol=0.0, err_msg=what)
 
 
-def _run(o, r, iterations, seed, scale_at=None):
+def _run(o, r, iterations, seed, scale_at=None, cumulative=True):
     rng = np.random.default_rng(seed)
     T, D = o.T, o.D
     o.begin_solve(); r.begin_solve()
+    if not cumulative:
+        r.set_cost_cumulation(False)         # the oracle takes the switch at construction (use_cumulative_costs=False)
     counts, exact = [], True
     for it in range(iterations):
         G = r.next_num_generated()
@@ -52,6 +54,9 @@ def _run(o, r, iterations, seed, scale_at=None):
             a, b = r.field(f), o.field(f)
             _same(a, b, f"iteration {it}: {f}")
             exact = exact and np.array_equal(a, b)
+        if not cumulative:
+            p = o.field("probabilities")
+            assert not np.all(p == p[:, :, :1]), "per-time-step mode must give time-varying probabilities"
         _same(r.updates(), o.updates(), "updates")
         _same(r.parameters(), o.parameters(), "parameters")
         _same(r.stddevs(), o.stddevs(), "stddevs")
@@ -124,3 +129,12 @@ def test_warm_start_matches_the_reference():
     for k in ("params_all", "mincc"):
         _same(r.policy()[k], o.policy()[k], k)
     _run(o, r, 3, seed=7)
+
+
+def test_per_timestep_costs_match_the_reference():
+    # Stomp::setCostCumulation(false): cumulative_costs_[d] = total_costs_[d], probabilities vary with the time step
+    # (PolicyImprovement.cpp:473-481,497-582).  Not what StompPlanner ships (and not built on the GPU yet: SURVEY 8f
+    # rank 4), but it pins the restatement's other branch.
+    pb = P.single_arm_problem(K=12, T=30, sdf_n=64)
+    o, r = _pair(pb, 12, 12, 12, use_cumulative_costs=False)
+    _run(o, r, 4, seed=8, cumulative=False)
