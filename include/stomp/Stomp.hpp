@@ -36,6 +36,8 @@ public:
     double getNoiselessRolloutTotalCost() { return noiseless_total_cost_; }
     bool getLastNoiselessRolloutValid() const { return last_noiseless_rollout_valid_; }
     void getAdaptedStddevs(std::vector<double>& stddevs);
+    // reference Stomp.cpp:356-359; false = per-time-step costs and probabilities (one GPU, no rollout reuse)
+    void setCostCumulation(bool use_cumulative_costs);
     bool getParameters(std::vector<base::VectorXd>& parameters);   // current policy parameters (free part) from the device
     bool runUntilValid(int max_iterations, int iterations_after_collision_free);
     bool stopRuleFired() const { return stop_; }

@@ -68,7 +68,7 @@ typedef struct stomp_b200_config {
                                             {0,0,1,0} for every joint and time step (OptimizationTask.cpp:32-33) */
     double cost_scaling_h;               /* 10.0 (PolicyImprovement.cpp:55) */
     int32_t use_noise_adaptation;        /* use_noise_adaptation_ */
-    int32_t use_cumulative_costs;        /* 1 (PolicyImprovement.cpp:56) */
+    int32_t use_cumulative_costs;        /* 1 (PolicyImprovement.cpp:56); 0 = per-time-step costs: one GPU, no rollout reuse */
     int32_t use_projection;              /* 0 (PolicyImprovement.cpp:57); 1 = M-matrix projected noise / update */
     int32_t per_timestep_minmax;         /* 0 = shipped global min/max; 1 = variant commented out at :518-528 */
     int32_t device;                      /* CUDA device ordinal */
@@ -156,6 +156,11 @@ int32_t stomp_b200_next_num_generated(const stomp_b200_engine* e);
  * a query whose stop rule fired is frozen (honour_stop != 0) exactly as `break` leaves it in the
  * reference.  Returns after the last kernel finished. */
 int stomp_b200_run(stomp_b200_engine* e, int32_t first_iteration, int32_t num_iterations, int32_t honour_stop);
+
+/* Stomp::setCostCumulation (stomp/src/Stomp.cpp:356-359): 1 = costs summed over the trajectory (the default), 0 = costs
+ * and probabilities per time step (PolicyImprovement.cpp:473-481).  0 is built for one GPU without rollout reuse, else
+ * STOMP_B200_ERR_UNSUPPORTED.  Also settable at creation (stomp_b200_config::use_cumulative_costs). */
+int stomp_b200_set_cost_cumulation(stomp_b200_engine* e, int32_t use_cumulative_costs);
 
 /* end of StompPlanner::solve (:148-173): solution = parameters_all_[d][6+t] (the LAST parameters, not the
  * best noise-less ones); status 1 = PATH_FOUND, 0 = NO_PATH_FOUND; iterations_used = getNumOfIterationsUsed. */

@@ -37,6 +37,7 @@ SYMBOLS = [
     "stomp_b200_comm_init", "stomp_b200_set_profiling", "stomp_b200_kernel_stats", "stomp_b200_reset_kernel_stats",
     "stomp_b200_set_timeline", "stomp_b200_get_timeline", "stomp_b200_launch_count", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
     "stomp_b200_state_kernel_kind", "stomp_b200_state_kernel_source", "stomp_b200_codegen_selftest",
+    "stomp_b200_set_cost_cumulation",
 ]
 
 
@@ -118,6 +119,7 @@ def lib():
         L.stomp_b200_state_kernel_kind.restype = C.c_int32
         L.stomp_b200_state_kernel_source.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.stomp_b200_codegen_selftest.argtypes = [C.c_char_p, C.c_size_t]
+        L.stomp_b200_set_cost_cumulation.argtypes = [vp, C.c_int32]
         L.stomp_b200_launch_count.restype = C.c_int64
         L.stomp_b200_timer_begin.argtypes = [vp]
         L.stomp_b200_timer_end.argtypes = [vp, dp]
@@ -388,6 +390,10 @@ class Engine:
 
     def launch_count(self):
         return lib().stomp_b200_launch_count(self.h)
+
+    def set_cost_cumulation(self, use_cumulative_costs: bool):
+        """stomp::Stomp::setCostCumulation."""
+        self._check(lib().stomp_b200_set_cost_cumulation(self.h, int(use_cumulative_costs)), "stomp_b200_set_cost_cumulation")
 
     def state_kernel_kind(self):
         """("specialised" | "generic", note): which state kernel the engine launches for its robot (state_codegen.hpp)."""

@@ -536,7 +536,8 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     }
 
     // one launch for K7-K9 when nothing sits between them (no exchange, no reused rollouts, no per-kernel profiling)
-    const bool fuse_weights = e->fuse_weights_allowed && world == 1 && !e->profiling && !e->reuse_possible && reused == 0;
+    const bool per_timestep = !c.use_cumulative_costs;
+    const bool fuse_weights = e->fuse_weights_allowed && world == 1 && !e->profiling && !e->reuse_possible && reused == 0 && !per_timestep;
     const int nchunks = std::max(1, (lp.num_local + lp.chunk - 1) / lp.chunk);
     lp.nchunks = nchunks;
     if (fuse_weights) {
@@ -554,8 +555,14 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         if (int rc = check_launch(e, "rollout_weights_kernel")) return rc;
     }
     // ---- weighted sums (K8) ----
-    const bool fuse_apply = world == 1 && !e->profiling;     // the apply step rides on the update kernel's last chunk CTA
-    if (!fuse_weights) {
+    const bool fuse_apply = world == 1 && !e->profiling && !per_timestep;     // the apply step rides on the update kernel's last chunk CTA
+    if (per_timestep) {      // Stomp::setCostCumulation(false): probabilities per time step
+        Scope sc(e, STOMP_B200_KERNEL_UPDATE);
+        pertimestep_minmax_kernel<<<dim3(e->D, e->Q), 1024, 0, e->stream>>>(lp);
+        if (int rc = check_launch(e, "pertimestep_minmax_kernel")) return rc;
+        pertimestep_update_kernel<<<dim3((e->T + 127) / 128, e->D, e->Q), 128, 0, e->stream>>>(lp);
+        if (int rc = check_launch(e, "pertimestep_update_kernel")) return rc;
+    } else if (!fuse_weights) {
         const size_t smem = sizeof(double) * std::max<size_t>(2 * (size_t)lp.chunk, (size_t)e->T + 2);
         Scope sc(e, STOMP_B200_KERNEL_UPDATE);
         weighted_update_kernel<<<dim3(nchunks, e->D, e->Q), kUpdateThreads, smem, e->stream>>>(lp, fuse_apply ? 1 : 0);
@@ -574,7 +581,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     // ---- apply (K9) ----
     if (!fuse_apply && !fuse_weights) {
         Scope sc(e, STOMP_B200_KERNEL_APPLY);
-        apply_update_kernel<<<dim3(e->D, e->Q), 256, sizeof(double) * ((size_t)e->T + 2), e->stream>>>(lp, world > 1 ? 0 : 1, nchunks);
+        apply_update_kernel<<<dim3(e->D, e->Q), 256, sizeof(double) * ((size_t)e->T + 2), e->stream>>>(lp, (world > 1 || per_timestep) ? 0 : 1, nchunks);
         if (int rc = check_launch(e, "apply_update_kernel")) return rc;
     }
     e->last_wblocks = lp.wblocks;
@@ -706,8 +713,12 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     if (cfg->num_queries < 1 || cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
         return STOMP_B200_ERR_INVALID_ARGUMENT;
     if (cfg->shard_mode != 0 && cfg->shard_mode != 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
-    if (cfg->use_projection || !cfg->use_cumulative_costs || cfg->per_timestep_minmax)
+    if (cfg->use_projection || cfg->per_timestep_minmax)
         return STOMP_B200_ERR_UNSUPPORTED;   // switches the reference ships disabled; DESIGN.md "out of scope"
+    // Stomp::setCostCumulation(false): built for the plain case (one GPU, no rollout reuse)
+    if (!cfg->use_cumulative_costs && (cfg->world_size > 1 || cfg->num_rollouts_per_iteration < cfg->max_rollouts ||
+                                       cfg->min_rollouts > cfg->num_rollouts_per_iteration))
+        return STOMP_B200_ERR_UNSUPPORTED;
     if (cfg->shard_mode == 0 && cfg->world_size > 1 && cfg->num_queries != 1) return STOMP_B200_ERR_UNSUPPORTED;
 
     int ndev = 0;
@@ -790,7 +801,11 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     }
     b.state_costs = e->state2[0]; b.verdicts = e->verdict2[0]; b.proj = e->proj2[0];
     CREATE_TRY(dev_alloc(e, &b.validity, Q * S));
-    if (cfg->keep_debug_tensors) CREATE_TRY(dev_alloc(e, &b.control_costs, Q * S * D * T));
+    if (cfg->keep_debug_tensors || !cfg->use_cumulative_costs) CREATE_TRY(dev_alloc(e, &b.control_costs, Q * S * D * T));
+    if (!cfg->use_cumulative_costs) {
+        CREATE_TRY(dev_alloc(e, &b.pt_prob, Q * GS * D * T));
+        CREATE_TRY(dev_alloc(e, &b.pt_minden, Q * D * 2));
+    }
     CREATE_TRY(dev_alloc(e, &b.sums, Q * GS * e->sumw));
     CREATE_TRY(dev_alloc(e, &b.total_cost, Q * GS));
     CREATE_TRY(dev_alloc(e, &b.prob, Q * GS * D));
@@ -1242,10 +1257,14 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
         case STOMP_B200_CONTROL_COSTS:
             if (!b.control_costs) return fail(e, STOMP_B200_ERR_NOT_READY, "control costs need keep_debug_tensors");
             return per_query(b.control_costs, nl * D, (size_t)e->slots * D, T * sizeof(double));
-        case STOMP_B200_CUMULATIVE_COSTS: return from_sums(5);
+        case STOMP_B200_CUMULATIVE_COSTS:
+            if (!e->cfg.use_cumulative_costs) return fail(e, STOMP_B200_ERR_UNSUPPORTED, "per-time-step mode: cumulative costs = state costs + control costs, read those");
+            return from_sums(5);
         case STOMP_B200_FULL_COSTS: return from_sums(6);
         case STOMP_B200_TOTAL_COST: return from_sums(7);
         case STOMP_B200_PROBABILITIES:
+            if (!e->cfg.use_cumulative_costs) return per_query(b.pt_prob, ng * D, (size_t)e->gslots * D, T * sizeof(double));
+            // fall through
         case STOMP_B200_FULL_PROBABILITIES: {
             // the device tables hold exp(-h (c - min) / den); divide by their sum (wpart), exactly as
             // weighted_update_kernel does (probabilities_ and full_probabilities_ coincide here)
@@ -1539,4 +1558,23 @@ int stomp_b200_codegen_selftest(char* log, size_t log_capacity)
     }
     if (log && log_capacity) std::snprintf(log, log_capacity, "%s", all_log.c_str());
     return rc;
+}
+
+// Stomp::setCostCumulation (reference src/planners/stomp/src/Stomp.cpp:356-359): 1 = costs summed over the trajectory
+// (the default, PolicyImprovement.cpp:56), 0 = costs and probabilities per time step.  Takes effect at the next iteration.
+int stomp_b200_set_cost_cumulation(stomp_b200_engine* e, int32_t use_cumulative_costs)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!use_cumulative_costs) {
+        if (e->cfg.world_size > 1 || e->reuse_possible)
+            return fail(e, STOMP_B200_ERR_UNSUPPORTED, "per-time-step costs are built for one GPU without rollout reuse");
+        CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+        LoopParams& b = e->base;
+        const size_t Q = e->Q, T = e->T, D = e->D, S = e->slots, GS = e->gslots;
+        if (!b.control_costs) { if (int rc = dev_alloc(e, &b.control_costs, Q * S * D * T)) return rc; }
+        if (!b.pt_prob) { if (int rc = dev_alloc(e, &b.pt_prob, Q * GS * D * T)) return rc; }
+        if (!b.pt_minden) { if (int rc = dev_alloc(e, &b.pt_minden, Q * D * 2)) return rc; }
+    }
+    e->cfg.use_cumulative_costs = use_cumulative_costs ? 1 : 0;
+    return STOMP_B200_OK;
 }

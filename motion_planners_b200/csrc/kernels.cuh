@@ -64,6 +64,8 @@ struct LoopParams {
     double* wpart;            // [Q][D][wblocks_cap] per-CTA sums of the unnormalised weights (rollout_weights_kernel)
     double* edge_cost;        // [Q][D][6] control costs of the band-table rows (edge_rows_kernel)
     uint32_t* done_counter;   // [Q][D] tickets of weighted_update_kernel's chunk CTAs (zero between launches)
+    double* pt_prob;          // [Q][gslots][D][T] probabilities_ in per-time-step mode (use_cumulative_costs == 0), else null
+    double* pt_minden;        // [Q][D][2] min and max(max - min, 1e-8) of the per-time-step costs
     double* s_compact;        // [Q][gslots]    S_k      } compact mirrors of the two columns of `sums` that the weights
     double* c_compact;        // [Q][D][gslots] C_{k,d}  } need, contiguous in k (weights_update_kernel); null when unused
     int32_t wblocks, wblocks_cap;
@@ -1621,6 +1623,76 @@ weights_update_kernel(const __grid_constant__ LoopParams p)
         if (tid == 0) p.done_counter[(size_t)q * D + d] = 0u;
     }
     tls.end();
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Per-time-step costs: Stomp::setCostCumulation(false).  cumulative_costs_[d] = total_costs_[d] = state + control_d per
+// time step (PolicyImprovement.cpp:473-481); min / max per joint over all rollouts AND time steps (:501-513);
+// probabilities per time step, normalised over the rollouts of that time step (:530-549); the update row is
+// sum_r noise[r][d][t] * P[r][d][t] (:590-596).  full_probabilities_ (noise adaptation) stay those of the summed costs
+// and come from rollout_weights_kernel.  Not a shipped configuration: simple kernels, rollouts walked in index order
+// like the reference does.  Needs the per-time-step control costs (control_costs, folded) of every slot.
+// -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+pertimestep_minmax_kernel(const __grid_constant__ LoopParams p)      // grid (D, Q)
+{
+    __shared__ double scratch[32];
+    const int d = blockIdx.x, q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D, n = p.num_local;
+    double mn = 1e300, mx = -1e300;
+    for (int e = threadIdx.x; e < n * T; e += blockDim.x) {
+        const int k = e / T, t = e - k * T;
+        const double c = 1.0 * (p.state_costs[((size_t)q * p.slots + k) * T + t] + p.control_costs[(((size_t)q * p.slots + k) * D + d) * T + t]);
+        mn = fmin(mn, c); mx = fmax(mx, c);
+    }
+    mn = block_reduce<1>(mn, scratch); mx = block_reduce<2>(mx, scratch);
+    if (threadIdx.x == 0) {
+        double den = mx - mn;
+        if (den < 1e-8) den = 1e-8;
+        p.pt_minden[((size_t)q * D + d) * 2] = mn;
+        p.pt_minden[((size_t)q * D + d) * 2 + 1] = den;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+pertimestep_update_kernel(const __grid_constant__ LoopParams p)      // grid (ceil(T / 128), D, Q)
+{
+    const int d = blockIdx.y, q = blockIdx.z;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D, n = p.num_local;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double mn = p.pt_minden[((size_t)q * D + d) * 2], den = p.pt_minden[((size_t)q * D + d) * 2 + 1];
+    const double h = p.cost_scaling_h;
+    double* upd = p.updbuf + ((size_t)q * D + d) * (T + 2);
+    if (t < T) {
+        auto weight = [&](int k) {
+            const double c = 1.0 * (p.state_costs[((size_t)q * p.slots + k) * T + t] + p.control_costs[(((size_t)q * p.slots + k) * D + d) * T + t]);
+            return 1.0 * exp(((-h) * (c - mn)) / den);      // importance_weight_ = 1
+        };
+        double psum = 0.0;
+        for (int k = 0; k < n; ++k) psum += weight(k);
+        double u = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double pr = weight(k) / psum;
+            p.pt_prob[(((size_t)q * p.gslots + k) * D + d) * T + t] = pr;
+            u += p.noise[(((size_t)q * p.slots + k) * D + d) * T + t] * pr;     // the noise-less slot carries zero noise
+        }
+        upd[t] = u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {      // noise adaptation: sum_r Pfull (n^T R n), sum_r Pfull (:656-663)
+        const double* part = p.wpart + ((size_t)q * D + d) * p.wblocks_cap;
+        double wsum = 0.0;
+        for (int b = 0; b < p.wblocks; ++b) wsum += part[b];
+        double numer = 0.0, denom = 0.0;
+        for (int k = threadIdx.x; k < n; k += 32) {
+            const double pf = p.fprob[((size_t)q * p.gslots + k) * D + d] / wsum;
+            denom += pf;
+            if (k != p.noiseless_slot && p.use_noise_adaptation) numer += pf * p.sums[((size_t)q * p.gslots + k) * p.sumw + 1 + 2 * D + d];
+        }
+        numer = warp_sum(numer); denom = warp_sum(denom);
+        if (threadIdx.x == 0) { upd[T] = numer; upd[T + 1] = denom; }
+    }
 }
 
 // sum of the chunk partials in chunk order -> updbuf [Q][D][T+1]; only needed in front of the all-reduce

@@ -161,4 +161,11 @@ bool Stomp::runUntilValid(int max_iterations, int iterations_after_collision_fre
     return success;
 }
 
+void Stomp::setCostCumulation(bool use_cumulative_costs)
+{
+    if (!engine_) return;
+    const int rc = stomp_b200_set_cost_cumulation(engine_, use_cumulative_costs ? 1 : 0);
+    if (rc) LOG_ERROR_S << "[Stomp]: setCostCumulation: " << stomp_b200_status_string(rc) << ": " << stomp_b200_last_error(engine_);
+}
+
 }  // namespace stomp

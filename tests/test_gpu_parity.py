@@ -392,3 +392,50 @@ def test_unfused_weights_and_update_kernels_match_the_fused_kernel(monkeypatch):
         np.testing.assert_allclose(c1, c2, rtol=1e-9)
         p = fused.tensor("probabilities")[0]
         np.testing.assert_allclose(p.sum(0), 1.0, rtol=1e-11)
+
+
+def test_per_timestep_costs_mode():
+    """Stomp::setCostCumulation(false) (PolicyImprovement.cpp:473-481): costs and probabilities per time step.  Not what
+    StompPlanner ships; the oracle's branch is pinned against the reference's own code (tests/test_reference_pin.py)."""
+    pb = P.single_arm_problem(K=24, T=40, sdf_n=64)
+    T, D, K = pb.num_time_steps, pb.chain.num_dimensions, pb.num_rollouts
+    o = Oracle(num_time_steps=T, num_dimensions=D, min_rollouts=K, max_rollouts=K, num_rollouts_per_iteration=K,
+               noise_stddev=pb.noise_stddev, use_cumulative_costs=False)
+    o.set_problem(pb)
+    pol = o.policy()
+    e = binding.engine_for_problem(pb, policy=pol, keep_debug_tensors=True, use_cumulative_costs=False)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(21)
+    for it in range(4):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((K, D, T)))
+        o.iterate(it, noise=unit)
+        cost, valid, _ = e.iterate(it, noise=unit[None])
+        p_ref = o.field("probabilities")
+        assert not np.all(p_ref == p_ref[:, :, :1])
+        np.testing.assert_array_equal(e.tensor("verdicts")[0].astype(bool), o.field("state_costs") > 0.5)
+        _assert_control_costs(e.tensor("control_costs")[0], o.field("control_costs"))
+        np.testing.assert_allclose(e.tensor("probabilities")[0], p_ref, rtol=RTOL, atol=1e-300)
+        np.testing.assert_allclose(e.tensor("probabilities")[0].sum(0), 1.0, rtol=1e-11)
+        np.testing.assert_allclose(e.tensor("full_probabilities")[0], o.field("full_probabilities"), rtol=RTOL, atol=1e-300)
+        np.testing.assert_allclose(e.tensor("updates")[0], o.updates(), rtol=RTOL, atol=1e-13)
+        np.testing.assert_allclose(e.tensor("parameters")[0], o.parameters(), rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(e.tensor("stddevs")[0], o.stddevs(), rtol=RTOL)
+        np.testing.assert_allclose(cost[0], o.noiseless()["total_cost"], rtol=RTOL)
+    # the same switch at run time (Stomp::setCostCumulation after initialize), on an engine created in the default mode
+    o2 = Oracle(num_time_steps=T, num_dimensions=D, min_rollouts=K, max_rollouts=K, num_rollouts_per_iteration=K,
+                noise_stddev=pb.noise_stddev, use_cumulative_costs=False)
+    o2.set_problem(pb)
+    e2 = binding.engine_for_problem(pb, policy=pol)
+    o2.begin_solve(); e2.begin_solve()
+    e2.set_cost_cumulation(False)
+    for it in range(2):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((K, D, T)))
+        o2.iterate(it, noise=unit)
+        e2.iterate(it, noise=unit[None])
+        np.testing.assert_allclose(e2.tensor("probabilities")[0], o2.field("probabilities"), rtol=RTOL, atol=1e-300)
+        np.testing.assert_allclose(e2.tensor("parameters")[0], o2.parameters(), rtol=RTOL, atol=1e-12)
+    # the combinations that are not built say so
+    with pytest.raises(binding.StompB200Error) as err:
+        binding.Engine(num_time_steps=T, num_dimensions=D, min_rollouts=5, max_rollouts=50, num_rollouts_per_iteration=10,
+                       use_cumulative_costs=False)
+    assert err.value.code == binding.ERR_UNSUPPORTED
