@@ -439,3 +439,21 @@ def test_per_timestep_costs_mode():
         binding.Engine(num_time_steps=T, num_dimensions=D, min_rollouts=5, max_rollouts=50, num_rollouts_per_iteration=10,
                        use_cumulative_costs=False)
     assert err.value.code == binding.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("K,T", [(1, 4), (2, 10), (5, 2)])
+def test_smallest_shapes(K, T):
+    """One rollout, two time steps: the ragged ends of every kernel (single tiles, windows that are mostly padding)."""
+    pb = P.single_arm_problem(K=K, T=T, sdf_n=64)
+    D = pb.chain.num_dimensions
+    o, e, pol = _pair(pb)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(300 + 10 * K + T)
+    for it in range(3):
+        eps = rng.standard_normal((K, D, T))
+        cost, valid, _ = e.iterate(it, epsilon=eps[None])
+        unit = e.tensor("unit_noise")[0]
+        ref = np.einsum("tu,kdu->kdt", pol["L"], eps)
+        np.testing.assert_allclose(unit, ref, rtol=1e-12, atol=1e-14 * max(abs(ref).max(), 1e-300))
+        o.iterate(it, noise=unit)
+        _compare_iteration(o, e, cost, valid)
