@@ -457,3 +457,29 @@ def test_smallest_shapes(K, T):
         np.testing.assert_allclose(unit, ref, rtol=1e-12, atol=1e-14 * max(abs(ref).max(), 1e-300))
         o.iterate(it, noise=unit)
         _compare_iteration(o, e, cost, valid)
+
+
+def test_longest_trajectory_and_the_fallback_kernels(monkeypatch):
+    """T = STOMP_B200_MAX_TIME_STEPS = 256: three slabs in the DMMA sampler, and N = 268 is past the control-cost tile
+    kernel's instantiations, so control_rows_fast_kernel runs.  Then T = 100 with the FMA-pipe sampler
+    (STOMP_B200_SAMPLER=simt) and the generic state kernel (STOMP_B200_STATES=generic): the fallbacks agree with the
+    oracle like the default kernels do."""
+    def check(pb, iterations):
+        D, K, T = pb.chain.num_dimensions, pb.num_rollouts, pb.num_time_steps
+        o, e, pol = _pair(pb)
+        o.begin_solve(); e.begin_solve()
+        rng = np.random.default_rng(500 + T)
+        for it in range(iterations):
+            eps = rng.standard_normal((K, D, T))
+            cost, valid, _ = e.iterate(it, epsilon=eps[None])
+            unit = e.tensor("unit_noise")[0]
+            ref = np.einsum("tu,kdu->kdt", pol["L"], eps)
+            np.testing.assert_allclose(unit, ref, rtol=1e-12, atol=1e-14 * abs(ref).max())
+            o.iterate(it, noise=unit)
+            _compare_iteration(o, e, cost, valid)
+        return e
+    check(P.single_arm_problem(K=3, T=256, sdf_n=64), 2)
+    monkeypatch.setenv("STOMP_B200_SAMPLER", "simt")
+    monkeypatch.setenv("STOMP_B200_STATES", "generic")
+    e = check(P.single_arm_problem(K=10, T=100, sdf_n=64), 2)
+    assert e.state_kernel_kind()[0] == "generic"
