@@ -483,3 +483,29 @@ def test_longest_trajectory_and_the_fallback_kernels(monkeypatch):
     monkeypatch.setenv("STOMP_B200_STATES", "generic")
     e = check(P.single_arm_problem(K=10, T=100, sdf_n=64), 2)
     assert e.state_kernel_kind()[0] == "generic"
+
+
+def test_largest_robot():
+    """STOMP_B200_MAX_DIMS = 32 joints, STOMP_B200_MAX_SPHERES = 128 spheres: the generated state kernel at its largest,
+    against the generic kernel's sphere centres (bit-identical) and the oracle's loop."""
+    D, S = 32, 128
+    rng = np.random.default_rng(77)
+    axes = np.array([[0, 0, 1], [0, 1, 0], [1, 0, 0], [0, -1, 0]], dtype=np.float64)
+    chain = P.Chain(origin_xyz=np.concatenate([[[0.0, 0.0, 0.1]], np.tile([[0.0, 0.01, 0.04]], (D - 1, 1))]),
+                    origin_rpy=np.zeros((D, 3)), axis=np.stack([axes[d % 4] for d in range(D)]),
+                    parent=np.arange(-1, D - 1, dtype=np.int32), prismatic=np.zeros(D, dtype=np.int32),
+                    lower=np.full(D, -1.0), upper=np.full(D, 1.0), names=[f"j{d}" for d in range(D)])
+    spheres = P.Spheres(link=np.repeat(np.arange(D, dtype=np.int32), S // D),
+                        xyz=rng.uniform(-0.02, 0.02, (S, 3)) * np.array([1.0, 0.0, 1.0]), radius=np.full(S, 0.03))
+    base = P.single_arm_problem(K=6, T=20, sdf_n=64)
+    pb = P.Problem(chain, spheres, base.sdf, np.full(D, -0.3), np.full(D, 0.4), np.full(D, 0.3), 20, 6)
+    o, e, pol = _pair(pb)
+    assert e.state_kernel_kind()[0] == "specialised"
+    q = rng.uniform(-1.0, 1.0, (16, D))
+    assert np.array_equal(e.sphere_centres(q).view(np.uint64), np.stack([o.sphere_centres(x) for x in q]).view(np.uint64))
+    o.begin_solve(); e.begin_solve()
+    for it in range(3):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((6, D, 20)))
+        o.iterate(it, noise=unit)
+        cost, valid, _ = e.iterate(it, noise=unit[None])
+        _compare_iteration(o, e, cost, valid)
