@@ -344,7 +344,9 @@ def run_ours(args):
     achieved_path = alg_bytes / ((avg_cost_ms + avg_rows_ms) * 1e-3) / 1e9 if cost_ms > 0 else None
     kind, kind_note = eng_kind
     # FP64 arithmetic of the state kernel: FP64-pipe warp instructions per state from the kernel's SASS
-    fp64_ops = {7: 380}.get(D)   # iiwa structure: 254 DFMA + 79 DADD + 47 DMUL of 968 SASS instructions (tools/spec_sass.cu)
+    # FP64-pipe instructions of the generated kernel, counted in its SASS (tools/spec_sass.cu): iiwa 254 DFMA + 79 DADD +
+    # 47 DMUL of 840; dual arm with the grasped object (DUAL=1) 640 + 186 + 110 of 1792
+    fp64_ops = {(7, 20): 380, (14, 48): 936}.get((D, S))
     fp64_peak = 18.43e12          # profiles/r1_fp64_peak_b200.json: DFMA / DADD / DMUL issue rate, thread-ops/s
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")

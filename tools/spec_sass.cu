@@ -8,6 +8,7 @@ int main(int argc, char** argv)
 {
     RobotParams r;
     std::memset(&r, 0, sizeof r);
+    const bool dual = getenv("DUAL") != nullptr;      // BASELINE config 5: two arms, 8 grasped-object spheres on the first tip
     r.num_joints = 7;
     const int kinds[7] = {kAxisZ, kAxisY, kAxisZ, kAxisNegY, kAxisZ, kAxisY, kAxisZ};
     const int omask[7] = {0, 5, 0, 5, 0, 4, 0};
@@ -20,7 +21,19 @@ int main(int argc, char** argv)
         r.sphere_begin[d] = s;
         for (int k = 0; k < nsph[d]; ++k, ++s) r.sphere[s].mask = smask[s];
     }
-    for (int d = 7; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = s;
+    if (dual) {
+        for (int k = 0; k < 8; ++k, ++s) r.sphere[s].mask = 7;                      // object spheres: full offsets
+        r.sphere_begin[7] = s;
+        for (int d = 0; d < 7; ++d) {
+            r.joint[7 + d].axis_kind = kinds[d]; r.joint[7 + d].o_mask = d == 0 ? 2 : omask[d]; r.joint[7 + d].fixed_rot_identity = 1;
+            r.joint[7 + d].parent = d == 0 ? -1 : 7 + d - 1;
+            r.sphere_begin[7 + d] = s;
+            for (int k = 0; k < nsph[d]; ++k, ++s) r.sphere[s].mask = smask[r.sphere_begin[d] + k < 20 ? (r.sphere_begin[7 + d] - r.sphere_begin[7]) + k : 0];
+        }
+        r.num_joints = 14;
+        r.joint[0].o_mask = 2;                                                         // bases at y = -+0.4
+    }
+    for (int d = r.num_joints; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = s;
     r.num_spheres = s;
     codegen::StateKernelOptions opt;
     opt.magic_floor = !getenv("CVT");
