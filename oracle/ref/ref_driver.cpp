@@ -264,6 +264,18 @@ int ref_set_cost_cumulation(void* hp, int use_cumulative_costs)
     return 0;
 }
 
+// PolicyImprovement::use_projection_ has no setter in the reference (constructor default false, PolicyImprovement.cpp:57);
+// the driver flips the private member and recomputes the projection matrices (:750-801) so that the restatement's
+// use_projection branch (M = R^-1 with scaled columns, noise_projected = M noise) is pinned as well.
+int ref_set_projection(void* hp, int use_projection)
+{
+    RefHandle* h = static_cast<RefHandle*>(hp);
+    if (!h->stomp) return -1;
+    h->stomp->policy_improvement_.use_projection_ = use_projection != 0;
+    h->stomp->policy_improvement_.preComputeProjectionMatrices();
+    return 0;
+}
+
 // how many rollouts the next runSingleIteration will generate (PolicyImprovement.cpp:170-186)
 int ref_next_num_generated(void* hp)
 {

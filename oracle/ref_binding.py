@@ -53,6 +53,7 @@ def lib():
         L.ref_get_policy.argtypes = [vp, dp, dp, dp, dp, dp, dp]
         L.ref_begin_solve.argtypes = [vp]
         L.ref_set_cost_cumulation.argtypes = [vp, C.c_int]
+        L.ref_set_projection.argtypes = [vp, C.c_int]
         L.ref_next_num_generated.argtypes = [vp]
         L.ref_iterate.argtypes = [vp, C.c_int, dp, C.c_int]
         L.ref_get_unit_noise.argtypes = [vp, dp]
@@ -110,6 +111,10 @@ class Reference:
     def set_cost_cumulation(self, use_cumulative_costs: bool):
         """stomp::Stomp::setCostCumulation; call after begin_solve (a new stomp::Stomp is made per solve)."""
         assert lib().ref_set_cost_cumulation(self.h, int(use_cumulative_costs)) == 0
+
+    def set_projection(self, use_projection: bool):
+        """Flips PolicyImprovement::use_projection_ (no setter in the reference) and recomputes the projection matrices."""
+        assert lib().ref_set_projection(self.h, int(use_projection)) == 0
 
     def next_num_generated(self):
         return lib().ref_next_num_generated(self.h)

@@ -35,10 +35,12 @@ def _same(a, b, what):
     np.testing.assert_allclose(a, b, rtol=RTOL, atol=0.0, err_msg=what)
 
 
-def _run(o, r, iterations, seed, scale_at=None, cumulative=True):
+def _run(o, r, iterations, seed, scale_at=None, cumulative=True, projection=False):
     rng = np.random.default_rng(seed)
     T, D = o.T, o.D
     o.begin_solve(); r.begin_solve()
+    if projection:
+        r.set_projection(True)               # the oracle takes the switch at construction (use_projection=True)
     if not cumulative:
         r.set_cost_cumulation(False)         # the oracle takes the switch at construction (use_cumulative_costs=False)
     counts, exact = [], True
@@ -138,3 +140,12 @@ def test_per_timestep_costs_match_the_reference():
     pb = P.single_arm_problem(K=12, T=30, sdf_n=64)
     o, r = _pair(pb, 12, 12, 12, use_cumulative_costs=False)
     _run(o, r, 4, seed=8, cumulative=False)
+
+
+def test_projection_branch_matches_the_reference():
+    # use_projection_ = true (PolicyImprovement.cpp:421-440,706,750-801): M = R^-1 with columns scaled by 1 / (T R^-1[p,p]),
+    # noise_projected = M noise, update row = M (sum_r P noise).  Disabled in the reference (no setter) and not built
+    # on the GPU; pinned here so that the restatement's branch is ready when it is.
+    pb = P.single_arm_problem(K=12, T=30, sdf_n=64)
+    o, r = _pair(pb, 12, 12, 12, use_projection=True)
+    _run(o, r, 3, seed=9, projection=True)
