@@ -71,3 +71,11 @@ def test_generated_state_kernel_compiles_for_sm_100a_without_a_device():
     rc, log = binding.codegen_selftest()
     assert rc == 0, log
     assert log.count("byte cubin") == 2
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/stomp_b200.h must compile as C99 on its own (no C++, no torch types)."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "stomp_b200.h")
+    out = subprocess.run(["gcc", "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", hdr], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
