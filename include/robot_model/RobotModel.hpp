@@ -68,6 +68,11 @@ public:
     // programmatic setup (instead of files)
     void setChain(const std::vector<urdf::Joint>& chain, const std::string& base_link, const std::string& tip_link);
     void setSpheres(const std::vector<CollisionSphere>& spheres);
+    // self collision: sphere pairs checked against each other.  Derived from the links the spheres sit on: every pair
+    // of different links, except links joined by one joint and the pairs an SRDF disables (link names).
+    void disableCollisions(const std::string& link1, const std::string& link2);
+    void setSelfCollision(bool on) { config_.self_collision = on; }
+    std::vector<std::pair<int, int> > selfCollisionPairs() const;
     void addObstacle(const Obstacle& o) { obstacles_.push_back(o); sdf_dirty_ = true; }
     void setSdfGrid(int resolution, const double lower[3], const double upper[3]);
     void setSdf(const SignedDistanceField& sdf);
@@ -79,6 +84,7 @@ public:
 private:
     bool loadUrdf(const std::string& path);
     bool loadSpheres(const std::string& path);
+    bool loadSrdf(const std::string& path);
     bool loadEnvironment(const std::string& path);
     bool ensureValidityEngine();
 
@@ -86,6 +92,7 @@ private:
     std::string world_frame_, base_link_, tip_link_;
     std::vector<urdf::Joint> all_joints_, chain_;
     std::vector<CollisionSphere> spheres_;
+    std::vector<std::pair<std::string, std::string> > disabled_link_pairs_;
     std::vector<Obstacle> obstacles_;
     SignedDistanceField sdf_;
     int sdf_resolution_ = 64;

@@ -9,12 +9,14 @@ namespace robot_model {
 
 struct RobotModelConfig {
     std::string urdf_file;
-    std::string srdf_file;            // accepted, unused: disabled self-collision pairs do not apply to link-vs-SDF checks
+    std::string srdf_file;            // its disable_collisions entries are honoured when self_collision is on
     std::string planning_group_name;
     std::string base_link;            // chain root; empty = the URDF's root link
     std::string tip_link;             // chain tip; empty = follow the movable joints to the end
     std::string spheres_file;         // YAML: spheres: { <link name>: [x, y, z, r, x, y, z, r, ...] }
     std::string environment_file;     // YAML: sdf: { resolution, lower, upper }, obstacles: { name: [sphere|box, ...] }
+    bool self_collision = false;      // also check link spheres against each other (all link pairs except joined links
+                                      // and the SRDF's disabled pairs); off: link spheres vs. environment only
     int device = 0;                   // CUDA device used for state validity queries
 };
 

@@ -200,6 +200,15 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
 int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_t num_trajectories,
                                int32_t num_steps, double* state_costs /*[K][Tq]*/, uint8_t* verdicts /*[K][Tq]*/,
                                uint8_t* validity /*[K]*/);
+/* ---- self collision (the "self" half of robot_model's isStateValid; which link pairs are checked is the host's
+ * business: the reference's SRDF lists the disabled ones, test/data/kuka_iiwa.srdf:46-70).  pairs [num_pairs][2] are
+ * indices into the sphere list of stomp_b200_set_spheres; a state is then in collision when a sphere is inside an
+ * obstacle OR |c_i - c_j|^2 < (r_i + r_j)^2 for a listed pair.  Applies to the loop, the noise-less rollout and
+ * stomp_b200_evaluate_states.  num_pairs == 0 switches the check off (the default); stomp_b200_set_spheres clears the
+ * list.  While a list is set the state kernel is the generic-FK self-collision kernel
+ * (stomp_b200_state_kernel_kind returns 2). */
+int stomp_b200_set_self_collision(stomp_b200_engine* e, int32_t num_pairs, const int32_t* pairs /*[num_pairs][2]*/);
+
 /* sphere centres in the world frame for n joint configurations q [n][D] -> [n][S][3] */
 int stomp_b200_sphere_centres(stomp_b200_engine* e, const double* q, int32_t n, double* centres);
 

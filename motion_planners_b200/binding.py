@@ -37,7 +37,7 @@ SYMBOLS = [
     "stomp_b200_comm_init", "stomp_b200_set_profiling", "stomp_b200_kernel_stats", "stomp_b200_reset_kernel_stats",
     "stomp_b200_set_timeline", "stomp_b200_get_timeline", "stomp_b200_launch_count", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
     "stomp_b200_state_kernel_kind", "stomp_b200_state_kernel_source", "stomp_b200_codegen_selftest",
-    "stomp_b200_set_cost_cumulation",
+    "stomp_b200_set_cost_cumulation", "stomp_b200_set_self_collision",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
         L.stomp_b200_set_chain.argtypes = [vp, C.c_int32, dp, dp, dp, ip, ip, dp, dp]
         L.stomp_b200_set_spheres.argtypes = [vp, C.c_int32, ip, dp, dp]
         L.stomp_b200_set_sdf.argtypes = [vp, ip, dp, C.c_double, C.POINTER(C.c_float)]
+        L.stomp_b200_set_self_collision.argtypes = [vp, C.c_int32, ip]
         L.stomp_b200_set_control_cost_matrices.argtypes = [vp, dp, dp, dp]
         L.stomp_b200_set_policy.argtypes = [vp, C.c_int32, dp, dp]
         L.stomp_b200_host_policy.argtypes = [C.c_int32, C.c_int32, C.c_double, dp, dp, C.c_int32, dp, dp, dp, dp, dp]
@@ -251,6 +252,12 @@ class Engine:
         self._check(lib().stomp_b200_set_spheres(self.h, len(link), _ip(link), _dp(xyz), _dp(rad)), "stomp_b200_set_spheres")
         self.S = len(link)
 
+    def set_self_collision(self, pairs):
+        """pairs [n][2]: sphere indices checked against each other (problems.self_collision_pairs); empty = off.
+        Call after set_spheres / set_problem (which clear the list)."""
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        self._check(lib().stomp_b200_set_self_collision(self.h, len(pr), _ip(pr)), "stomp_b200_set_self_collision")
+
     def set_sdf(self, sdf):
         grid = np.ascontiguousarray(sdf.grid, dtype=np.float32)
         dims = np.ascontiguousarray(sdf.dims, dtype=np.int32)
@@ -396,12 +403,12 @@ class Engine:
         self._check(lib().stomp_b200_set_cost_cumulation(self.h, int(use_cumulative_costs)), "stomp_b200_set_cost_cumulation")
 
     def state_kernel_kind(self):
-        """("specialised" | "generic", note): which state kernel the engine launches for its robot (state_codegen.hpp)."""
+        """("specialised" | "generic" | "self-collision", note): which state kernel the engine launches for its robot (state_codegen.hpp)."""
         note = C.create_string_buffer(4096)
         rc = lib().stomp_b200_state_kernel_kind(self.h, note, len(note))
         if rc < 0:
             self._check(rc, "stomp_b200_state_kernel_kind")
-        return ("specialised" if rc == 1 else "generic"), note.value.decode()
+        return {1: "specialised", 2: "self-collision"}.get(rc, "generic"), note.value.decode()
 
     def state_kernel_source(self):
         need = C.c_size_t(0)

@@ -105,6 +105,9 @@ struct stomp_b200_engine {
     JointLimits limits;             // robot.lower / upper, for the sampling kernels
     SdfParams sdf;
     float* d_sdf = nullptr;
+    SelfPairs self_pairs = {nullptr, nullptr, 0, 0};   // stomp_b200_set_self_collision; n == 0: world collisions only
+    int2* d_pair_ij = nullptr;
+    double* d_pair_limit2 = nullptr;
     bool have_chain = false, have_spheres = false, have_sdf = false, have_matrices = false;
     std::vector<uint8_t> have_policy;
 
@@ -236,6 +239,15 @@ int check_launch(stomp_b200_engine* e, const char* what)
         return STOMP_B200_ERR_CUDA;
     }
     return 0;
+}
+
+// the state kernel with the sphere-pair rule (stomp_b200_set_self_collision), its centre storage sized to the robot
+void launch_states_self_collision(stomp_b200_engine* e, const StateKernelArgs& a, dim3 grid, cudaStream_t stream)
+{
+    const int S = e->robot.num_spheres;
+    if (S <= 32) states_self_collision_kernel<32><<<grid, 128, 0, stream>>>(a, e->robot, e->sdf, e->self_pairs);
+    else if (S <= 64) states_self_collision_kernel<64><<<grid, 128, 0, stream>>>(a, e->robot, e->sdf, e->self_pairs);
+    else states_self_collision_kernel<STOMP_B200_MAX_SPHERES><<<grid, 128, 0, stream>>>(a, e->robot, e->sdf, e->self_pairs);
 }
 
 // tiles per slab: the slabs of a launch are equally wide (ceil(T / 8) n8 tiles over ceil(T / 104) slabs)
@@ -498,14 +510,16 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         dim3 grid((states + 255) / 256, e->Q);
         Scope sc(e, STOMP_B200_KERNEL_COST);
         resolve_state_kernel(e);
-        if (e->spec) {
-            StateKernelArgs a;
-            a.rollouts = lp.rollouts; a.state_costs = lp.state_costs; a.verdicts = lp.verdicts; a.validity = lp.validity;
-            a.sums = lp.sums; a.s_compact = lp.s_compact; a.stop = lp.stop; a.tile_counter = lp.tile_counter;
-            a.timeline = lp.timeline ? lp.timeline + 2 * 1 : nullptr;
-            a.T = lp.T; a.D = lp.D; a.slots = lp.slots; a.gslots = lp.gslots; a.sumw = lp.sumw; a.num_gen = lp.num_gen;
-            a.gen_offset = lp.gen_offset; a.honour_stop = lp.honour_stop; a.debug_skip = lp.debug_skip;
-            a.row_stride = lp.T; a.rollout_stride = (int64_t)lp.D * lp.T;
+        StateKernelArgs a;
+        a.rollouts = lp.rollouts; a.state_costs = lp.state_costs; a.verdicts = lp.verdicts; a.validity = lp.validity;
+        a.sums = lp.sums; a.s_compact = lp.s_compact; a.stop = lp.stop; a.tile_counter = lp.tile_counter;
+        a.timeline = lp.timeline ? lp.timeline + 2 * 1 : nullptr;
+        a.T = lp.T; a.D = lp.D; a.slots = lp.slots; a.gslots = lp.gslots; a.sumw = lp.sumw; a.num_gen = lp.num_gen;
+        a.gen_offset = lp.gen_offset; a.honour_stop = lp.honour_stop; a.debug_skip = lp.debug_skip;
+        a.row_stride = lp.T; a.rollout_stride = (int64_t)lp.D * lp.T;
+        if (e->self_pairs.n > 0) {
+            launch_states_self_collision(e, a, dim3((states + 127) / 128, e->Q), e->stream);
+        } else if (e->spec) {
             void* args[] = {&a, &e->robot, &e->sdf};
             const int bt = e->spec->block_threads;
             CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((states + bt - 1) / bt, e->Q), dim3(bt), args, 0, e->stream));
@@ -593,7 +607,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         e->launch_count++;
         e->kernel_launches[STOMP_B200_KERNEL_APPLY]++;
         int states_done = 0;
-        if (e->spec) {
+        if (e->self_pairs.n > 0 || e->spec) {
             // the verdicts of the T noise-less states from the specialised state kernel, reading the padded policy rows in
             // place (2.5x faster than the generic FK inside noiseless_rollout_kernel, which sits at the end of every
             // isolated iteration)
@@ -603,10 +617,16 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             a.T = lp.T; a.D = lp.D; a.slots = 1; a.gslots = 1; a.sumw = lp.sumw; a.num_gen = 1; a.gen_offset = 0;
             a.honour_stop = lp.honour_stop; a.debug_skip = 0;
             a.row_stride = lp.N; a.rollout_stride = (int64_t)lp.D * lp.N;
-            void* args[] = {&a, &e->robot, &e->sdf};
-            const int bt = e->spec->block_threads;
-            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + bt - 1) / bt, e->Q), dim3(bt), args, 0, e->side_stream));
-            e->launch_count++;
+            if (e->self_pairs.n > 0) {
+                launch_states_self_collision(e, a, dim3((lp.T + 127) / 128, e->Q), e->side_stream);
+                if (int rc = check_launch(e, "states_self_collision_kernel")) return rc;
+                e->launch_count++;
+            } else {
+                void* args[] = {&a, &e->robot, &e->sdf};
+                const int bt = e->spec->block_threads;
+                CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + bt - 1) / bt, e->Q), dim3(bt), args, 0, e->side_stream));
+                e->launch_count++;
+            }
             states_done = 1;
         }
         noiseless_rollout_kernel<<<e->Q, 256, smem, e->side_stream>>>(lp, e->robot, e->sdf, states_done);
@@ -907,6 +927,8 @@ int stomp_b200_destroy(stomp_b200_engine* e)
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* p : e->allocations) cudaFree(p);
     if (e->d_sdf) cudaFree(e->d_sdf);
+    if (e->d_pair_ij) cudaFree(e->d_pair_ij);
+    if (e->d_pair_limit2) cudaFree(e->d_pair_limit2);
     if (e->h_cost) cudaFreeHost(e->h_cost);
     if (e->h_impr) cudaFreeHost(e->h_impr);
     if (e->h_valid) cudaFreeHost(e->h_valid);
@@ -1021,6 +1043,41 @@ int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int3
     for (int d = 1; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = std::max(r.sphere_begin[d], r.sphere_begin[d - 1]);
     e->have_spheres = true;
     e->spec_resolved = false;
+    e->self_pairs.n = 0;   // indices and radii of an earlier pair list no longer apply
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_set_self_collision(stomp_b200_engine* e, int32_t num_pairs, const int32_t* pairs)
+{
+    if (!e || num_pairs < 0 || (num_pairs > 0 && !pairs)) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!e->have_spheres) return fail(e, STOMP_B200_ERR_NOT_READY, "stomp_b200_set_spheres comes first");
+    const int S = e->robot.num_spheres;
+    if (num_pairs > S * (S - 1) / 2) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "more pairs than distinct sphere pairs");
+    std::vector<int2> ij((size_t)num_pairs);
+    std::vector<double> limit2((size_t)num_pairs);
+    for (int p = 0; p < num_pairs; ++p) {
+        int i = pairs[2 * p], j = pairs[2 * p + 1];
+        if (i > j) std::swap(i, j);
+        if (i < 0 || j >= S || i == j) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "self-collision pair: sphere index out of range");
+        ij[p] = make_int2(i, j);
+        const double sum = e->robot.sphere[i].r + e->robot.sphere[j].r;
+        limit2[p] = sum * sum;
+    }
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (e->side_stream) CUDA_TRY(e, cudaStreamSynchronize(e->side_stream));
+    e->self_pairs.n = 0;
+    if (e->d_pair_ij) { cudaFree(e->d_pair_ij); e->d_pair_ij = nullptr; }
+    if (e->d_pair_limit2) { cudaFree(e->d_pair_limit2); e->d_pair_limit2 = nullptr; }
+    if (num_pairs > 0) {
+        CUDA_TRY(e, cudaMalloc(&e->d_pair_ij, sizeof(int2) * (size_t)num_pairs));
+        CUDA_TRY(e, cudaMalloc(&e->d_pair_limit2, sizeof(double) * (size_t)num_pairs));
+        CUDA_TRY(e, cudaMemcpy(e->d_pair_ij, ij.data(), sizeof(int2) * (size_t)num_pairs, cudaMemcpyHostToDevice));
+        CUDA_TRY(e, cudaMemcpy(e->d_pair_limit2, limit2.data(), sizeof(double) * (size_t)num_pairs, cudaMemcpyHostToDevice));
+        e->self_pairs.ij = e->d_pair_ij;
+        e->self_pairs.limit2 = e->d_pair_limit2;
+        e->self_pairs.n = num_pairs;
+    }
     return STOMP_B200_OK;
 }
 
@@ -1319,6 +1376,7 @@ int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_
     if (!e->have_chain || !e->have_spheres || !e->have_sdf) return fail(e, STOMP_B200_ERR_NOT_READY, "chain, spheres and SDF must be set first");
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     const size_t states = (size_t)num_trajectories * num_steps;
+    if (e->self_pairs.n > 0 && states > (size_t)0x7fffff00) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "too many states for one call with self collision on");
     double* d_theta = nullptr; double* d_cost = nullptr; uint8_t* d_verdict = nullptr; uint8_t* d_valid = nullptr;
     int rc = STOMP_B200_OK;
     auto cleanup = [&]() { cudaFree(d_theta); cudaFree(d_cost); cudaFree(d_verdict); cudaFree(d_valid); };
@@ -1330,6 +1388,15 @@ int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_
     EVAL_TRY(cudaMemcpyAsync(d_theta, theta, sizeof(double) * states * e->D, cudaMemcpyHostToDevice, e->stream));
     {
         Scope sc(e, STOMP_B200_KERNEL_COST);
+        if (e->self_pairs.n > 0) {
+            StateKernelArgs a;
+            a.rollouts = d_theta; a.state_costs = d_cost; a.verdicts = d_verdict; a.validity = d_valid;
+            a.sums = nullptr; a.s_compact = nullptr; a.stop = nullptr; a.tile_counter = nullptr; a.timeline = nullptr;
+            a.T = num_steps; a.D = e->D; a.slots = num_trajectories; a.gslots = 1; a.sumw = 1; a.num_gen = num_trajectories;
+            a.gen_offset = 0; a.honour_stop = 0; a.debug_skip = 0;
+            a.row_stride = num_steps; a.rollout_stride = (int64_t)e->D * num_steps;
+            launch_states_self_collision(e, a, dim3((unsigned)((states + 127) / 128), 1), e->stream);
+        } else
         evaluate_states_kernel<<<(unsigned)((states + 127) / 128), 128, 0, e->stream>>>(e->robot, e->sdf, d_theta, num_trajectories, num_steps, d_cost, d_verdict, d_valid);
     }
     EVAL_TRY(cudaGetLastError());
@@ -1503,8 +1570,10 @@ int32_t stomp_b200_state_kernel_kind(stomp_b200_engine* e, char* note, size_t no
     resolve_state_kernel(e);
     if (note && note_capacity) {
         std::string text = e->spec ? ("specialised, " + std::to_string(e->spec->registers) + " registers") : ("generic: " + e->spec_note);
+        if (e->self_pairs.n > 0) text = "self-collision kernel (" + std::to_string(e->self_pairs.n) + " sphere pairs), generic FK";
         std::snprintf(note, note_capacity, "%s", text.c_str());
     }
+    if (e->self_pairs.n > 0) return 2;
     return e->spec ? 1 : 0;
 }
 

@@ -1222,6 +1222,86 @@ evaluate_states_kernel(const __grid_constant__ RobotParams robot, const __grid_c
     if (validity && t == Tq - 1) validity[k] = hit ? 0 : 1;
 }
 
+// =====================================================================================================
+// Self collision (the "self" half of robot_model's isStateValid, with the SRDF's disabled
+// link pairs removed on the host — reference test/data/kuka_iiwa.srdf:46-70).  A state is in collision when a
+// link sphere is inside an obstacle (as above) OR two spheres of a listed pair overlap:
+//   |c_i - c_j|^2 < (r_i + r_j)^2,   |.|^2 = fma(dz, dz, fma(dy, dy, dx * dx)),   the limit squared on the host.
+// Replaces the state kernel (generated or generic) at all of its call sites while a pair list is set; the
+// argument block is the generated kernel's, so the noisy rollouts, the padded policy rows of the noise-less
+// rollout and stomp_b200_evaluate_states all go through this one kernel.  First version: generic FK, sphere
+// centres in thread-local memory, pairs walked in list order (warp-uniform loads); the pair loop is skipped for
+// states an obstacle already condemns.
+// =====================================================================================================
+struct SelfPairs {
+    const int2* ij;          // [n] sphere indices, x < y
+    const double* limit2;    // [n] (r_x + r_y)^2
+    int32_t n;
+    int32_t pad_;
+};
+
+template <int kSphereCapacity>   // thread-local centre storage, sized by the host to the robot (32 / 64 / 128 spheres)
+__global__ void __launch_bounds__(128)
+states_self_collision_kernel(const __grid_constant__ StateKernelArgs a, const __grid_constant__ RobotParams robot,
+                             const __grid_constant__ SdfParams sdf, const __grid_constant__ SelfPairs pairs)
+{
+    const int q = blockIdx.y;
+    if (a.tile_counter && blockIdx.x == 0 && q == 0 && threadIdx.x < 4) a.tile_counter[threadIdx.x] = 0u;
+    if (a.honour_stop && a.stop[q] != 0) return;
+    if (a.timeline && threadIdx.x == 0) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        atomicMin(a.timeline, t0);
+    }
+    const int T = a.T;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < a.num_gen * T && !(a.debug_skip & 1)) {
+        const int k = idx / T, t = idx - k * T;
+        const double* xq = a.rollouts + ((size_t)q * a.slots + k) * a.rollout_stride + t;
+        const size_t rs = (size_t)a.row_stride;
+        double c[3 * kSphereCapacity];
+        Frame f;
+        frame_identity(f);
+        bool hit = false;
+        const int nj = robot.num_joints;
+        for (int d = 0; d < nj; ++d) {
+            apply_joint<false>(f, robot.joint[d], xq[(size_t)d * rs]);
+            const int s1 = robot.sphere_begin[d + 1];
+            for (int s = robot.sphere_begin[d]; s < s1; ++s) {
+                double cx, cy, cz;
+                sphere_centre(f, robot.sphere[s], cx, cy, cz);
+                c[3 * s] = cx; c[3 * s + 1] = cy; c[3 * s + 2] = cz;
+                const double dist = (double)__ldg(sdf.grid + sdf_index(sdf, cx, cy, cz));
+                hit |= (dist - robot.sphere[s].r) < 0.0;
+            }
+        }
+        if (!hit) {
+            for (int pr = 0; pr < pairs.n; ++pr) {
+                const int2 ij = __ldg(pairs.ij + pr);
+                const double dx = c[3 * ij.x] - c[3 * ij.y];
+                const double dy = c[3 * ij.x + 1] - c[3 * ij.y + 1];
+                const double dz = c[3 * ij.x + 2] - c[3 * ij.y + 2];
+                const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                if (d2 < __ldg(pairs.limit2 + pr)) { hit = true; break; }
+            }
+        }
+        const size_t o = ((size_t)q * a.slots + k) * T + t;
+        if (a.state_costs) a.state_costs[o] = hit ? 1.0 : 0.0;
+        if (a.verdicts) a.verdicts[o] = hit ? 1 : 0;
+        if (a.validity && t == T - 1) a.validity[(size_t)q * a.slots + k] = hit ? 0 : 1;
+        if (hit && a.sums) atomicAdd(a.sums + ((size_t)q * a.gslots + (a.gen_offset + k)) * a.sumw, 1.0);
+        if (hit && a.s_compact) atomicAdd(a.s_compact + (size_t)q * a.gslots + (a.gen_offset + k), 1.0);
+    }
+    if (a.timeline) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            atomicMax(a.timeline + 1, t1);
+        }
+    }
+}
+
 __global__ void sphere_centres_kernel(const __grid_constant__ RobotParams robot, const double* __restrict__ q, int n,
                                       double* __restrict__ centres)
 {

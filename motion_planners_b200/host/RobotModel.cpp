@@ -96,6 +96,7 @@ bool RobotModel::initialization()
     if (!config_.urdf_file.empty() && !loadUrdf(config_.urdf_file)) return false;
     if (chain_.empty()) { LOG_ERROR_S << "[RobotModel]: no kinematic chain"; return false; }
     if (!config_.spheres_file.empty() && !loadSpheres(config_.spheres_file)) return false;
+    if (config_.self_collision && !config_.srdf_file.empty() && !loadSrdf(config_.srdf_file)) return false;
     if (!config_.environment_file.empty() && !loadEnvironment(config_.environment_file)) return false;
     if (spheres_.empty()) { LOG_ERROR_S << "[RobotModel]: no collision spheres"; return false; }
     if (sdf_dirty_ && !buildSdf()) return false;
@@ -201,6 +202,47 @@ bool RobotModel::loadUrdf(const std::string& path)
         sdf_dirty_ = true;
     }
     return !chain_.empty();
+}
+
+// the SRDF's <disable_collisions link1=".." link2=".."/> entries (reference test/data/kuka_iiwa.srdf:46-70)
+bool RobotModel::loadSrdf(const std::string& path)
+{
+    std::ifstream f(path.c_str());
+    if (!f) { LOG_ERROR_S << "[RobotModel]: cannot open SRDF " << path; return false; }
+    std::stringstream buf;
+    buf << f.rdbuf();
+    const std::string xml = buf.str();
+    size_t pos = 0;
+    XmlTag tag;
+    while (next_tag(xml, pos, tag))
+        if (tag.name == "disable_collisions" && !tag.closing && tag.attr.count("link1") && tag.attr.count("link2"))
+            disableCollisions(tag.attr["link1"], tag.attr["link2"]);
+    return true;
+}
+
+void RobotModel::disableCollisions(const std::string& link1, const std::string& link2)
+{
+    disabled_link_pairs_.push_back(std::make_pair(link1, link2));
+}
+
+std::vector<std::pair<int, int> > RobotModel::selfCollisionPairs() const
+{
+    std::vector<std::pair<int, int> > pairs;
+    if (!config_.self_collision) return pairs;
+    auto disabled = [&](int a, int b) {
+        const std::string& la = chain_[a].child_link_name;
+        const std::string& lb = chain_[b].child_link_name;
+        for (const auto& d : disabled_link_pairs_)
+            if ((d.first == la && d.second == lb) || (d.first == lb && d.second == la)) return true;
+        return false;
+    };
+    for (size_t i = 0; i < spheres_.size(); ++i)
+        for (size_t j = i + 1; j < spheres_.size(); ++j) {
+            const int a = spheres_[i].link, b = spheres_[j].link;    // sorted by link: a <= b
+            if (a == b || b == a + 1 || disabled(a, b)) continue;     // same link, joined by one joint, SRDF
+            pairs.push_back(std::make_pair((int)i, (int)j));
+        }
+    return pairs;
 }
 
 bool RobotModel::loadSpheres(const std::string& path)
@@ -386,6 +428,13 @@ int RobotModel::configureEngine(stomp_b200_engine* engine) const
     if (rc) return rc;
     rc = stomp_b200_set_spheres(engine, S, link.data(), sxyz.data(), rad.data());
     if (rc) return rc;
+    const std::vector<std::pair<int, int> > pairs = selfCollisionPairs();
+    if (!pairs.empty()) {
+        std::vector<int32_t> flat;
+        for (const auto& p : pairs) { flat.push_back(p.first); flat.push_back(p.second); }
+        rc = stomp_b200_set_self_collision(engine, (int32_t)pairs.size(), flat.data());
+        if (rc) return rc;
+    }
     return stomp_b200_set_sdf(engine, sdf_.dims, sdf_.origin, sdf_.voxel, sdf_.grid.data());
 }
 

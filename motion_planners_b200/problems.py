@@ -115,6 +115,24 @@ def dual_arm_spheres() -> Spheres:
     return Spheres(link=link, xyz=xyz, radius=rad)
 
 
+def self_collision_pairs(chain: Chain, spheres: Spheres, disabled_links=(), skip_adjacent=True) -> np.ndarray:
+    """Sphere pairs [n][2] to check against each other: all pairs on different links, minus links joined by one
+    joint (skip_adjacent) and minus the link pairs listed in `disabled_links` (what an SRDF's disable_collisions
+    entries say; reference test/data/kuka_iiwa.srdf:46-70).  Links are named by the index of the joint they hang on."""
+    off = {(min(a, b), max(a, b)) for a, b in disabled_links}
+    out = []
+    link = spheres.link
+    for i in range(len(link)):
+        for j in range(i + 1, len(link)):
+            a, b = int(link[i]), int(link[j])
+            if a == b or (a, b) in off:
+                continue
+            if skip_adjacent and chain.parent[b] == a:
+                continue
+            out.append((i, j))
+    return np.asarray(out, dtype=np.int32).reshape(-1, 2)
+
+
 def _rot(axis, q):
     a = np.asarray(axis, dtype=np.float64)
     a = a / np.linalg.norm(a)

@@ -58,6 +58,7 @@ def lib():
         L.oracle_set_chain.argtypes = [vp, C.c_int, dp, dp, dp, ip, ip, dp, dp]
         L.oracle_set_spheres.argtypes = [vp, C.c_int, ip, dp, dp]
         L.oracle_set_sdf.argtypes = [vp, ip, dp, C.c_double, C.POINTER(C.c_float)]
+        L.oracle_set_self_collision.argtypes = [vp, C.c_int, ip]
         L.oracle_set_start_goal.argtypes = [vp, dp, dp]
         L.oracle_set_initial_trajectory.argtypes = [vp, dp]
         L.oracle_get_policy.argtypes = [vp, dp, dp, dp, dp, dp, dp]
@@ -155,6 +156,12 @@ class Oracle:
         rc = lib().oracle_set_spheres(self.h, len(link), _ip(link), _dp(xyz), _dp(rad))
         assert rc == 0, rc
         self.S = len(link)
+
+    def set_self_collision(self, pairs):
+        """pairs: [n][2] sphere indices checked against each other; empty switches the check off"""
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        rc = lib().oracle_set_self_collision(self.h, len(pr), _ip(pr))
+        assert rc == 0, rc
 
     def set_sdf(self, sdf):
         grid = np.ascontiguousarray(sdf.grid, dtype=np.float32)

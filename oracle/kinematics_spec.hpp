@@ -235,4 +235,29 @@ static inline bool sphere_collides(const SdfSpec& g, const double c[3], double r
     return (d - radius) < 0.0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Self collision (the "self" half of robot_model's isStateValid; the reference's SRDF lists the link
+// pairs that are NOT checked: test/data/kuka_iiwa.srdf:46-70).  A pair of link spheres (i, j) collides
+// when the squared distance of the centres is below (r_i + r_j)^2.  SPEC: op order is normative.
+// ---------------------------------------------------------------------------------------------
+struct SelfPairSpec {
+    int32_t i, j;        // sphere indices, i < j
+    double limit2;       // (r_i + r_j)^2, computed once on the host as s = r_i + r_j; s * s
+};
+
+static inline double self_pair_limit2(double ri, double rj)
+{
+    double s = ri + rj;
+    return s * s;
+}
+
+static inline bool self_pair_collides(const double* centres /*[S][3]*/, const SelfPairSpec& pr)
+{
+    const double* a = centres + 3 * pr.i;
+    const double* b = centres + 3 * pr.j;
+    double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+    double d2 = spec_fma(dz, dz, spec_fma(dy, dy, dx * dx));
+    return d2 < pr.limit2;
+}
+
 }  // namespace oracle

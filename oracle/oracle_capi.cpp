@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  extern "C" surface of the CPU restatement, bound with ctypes by
 // tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference).  Never linked into
 // or called by the product library.  Parity status: see stomp_oracle.hpp.
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <memory>
@@ -125,6 +126,24 @@ int oracle_set_spheres(void* hp, int S, const int32_t* link, const double* xyz, 
         sp.link = link[s];
         for (int i = 0; i < 3; ++i) sp.l[i] = xyz[3 * s + i];
         sp.r = radius[s];
+    }
+    return 0;
+}
+
+// sphere pairs checked against each other (self collision); n == 0 switches the check off
+int oracle_set_self_collision(void* hp, int n, const int32_t* pairs /*[n][2]*/)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    const int S = (int)h->task->spheres_.size();
+    h->task->self_pairs_.clear();
+    for (int p = 0; p < n; ++p) {
+        int i = pairs[2 * p], j = pairs[2 * p + 1];
+        if (i > j) std::swap(i, j);
+        if (i < 0 || j >= S || i == j) return -1;
+        SelfPairSpec pr;
+        pr.i = i; pr.j = j;
+        pr.limit2 = self_pair_limit2(h->task->spheres_[i].r, h->task->spheres_[j].r);
+        h->task->self_pairs_.push_back(pr);
     }
     return 0;
 }

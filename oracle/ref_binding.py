@@ -32,7 +32,9 @@ def build() -> bool:
 
 
 def available() -> bool:
-    return os.path.exists(_LIB_PATH) or build()
+    """make decides whether the library is stale (it links the oracle's sources too); without the reference
+    sources — on the GPU box — the prebuilt file is used as it travelled"""
+    return build()
 
 
 _lib = None

@@ -920,6 +920,12 @@ bool SphereSdfTask::stateCollides(const double* q) const
             ++s;
         }
     }
+    if (!self_pairs_.empty()) {
+        std::vector<double> centres(3 * spheres_.size());
+        sphereCentres(q, centres.data());
+        for (const SelfPairSpec& pr : self_pairs_)
+            if (self_pair_collides(centres.data(), pr)) hit = true;
+    }
     return hit;
 }
 

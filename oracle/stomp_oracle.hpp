@@ -231,6 +231,7 @@ public:
     std::vector<Mat> derivative_costs_;
     std::vector<JointSpec> joints_;
     std::vector<SphereSpec> spheres_;   // sorted by link
+    std::vector<SelfPairSpec> self_pairs_;   // empty: world collisions only
     SdfSpec sdf_ {};
     std::vector<float> sdf_storage_;
     Vec lower_limits_, upper_limits_;

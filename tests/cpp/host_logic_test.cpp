@@ -73,6 +73,32 @@ int main(int argc, char** argv)
     CHECK(at(0.5, 0.0, 0.5) < -0.05);          // inside box_1
     CHECK(at(-0.17, 0.03, 1.31) < -0.1);       // inside the blocker sphere
     CHECK(at(0.0, 0.0, 0.0) > 0.3);            // free space at the base
+    // self collision: off by default; on -> every pair of spheres on different, not directly joined links; the SRDF's
+    // disable_collisions entries remove link pairs (either order of the names)
+    CHECK(robot->selfCollisionPairs().empty());
+    {
+        auto count_links = [&](const std::vector<std::pair<int, int> >& pairs, int a, int b) {
+            int n = 0;
+            for (const auto& p : pairs) n += robot->spheres()[p.first].link == a && robot->spheres()[p.second].link == b;
+            return n;
+        };
+        robot->setSelfCollision(true);
+        const auto all = robot->selfCollisionPairs();
+        // spheres per link: 3 3 3 3 3 2 3 -> pairs over different links 20*19/2 - (6*3 + 1) = 171; joined links: 9*4 + 6 + 6 = 48
+        CHECK(all.size() == 171u - 48u);
+        CHECK(count_links(all, 0, 1) == 0 && count_links(all, 0, 2) == 9 && count_links(all, 4, 6) == 9 && count_links(all, 3, 5) == 6);
+        for (const auto& p : all) CHECK(p.first < p.second);
+        robot_model::RobotModelConfig rs = rc;
+        rs.srdf_file = test_dir + "/data/iiwa_chain.srdf";
+        rs.self_collision = true;
+        robot_model::RobotModel with_srdf(rs);
+        CHECK(with_srdf.initialization());
+        const auto fewer = with_srdf.selfCollisionPairs();
+        // removed: (0,2) (1,3) (2,4): 9 each, (3,5): 6, (4,6) written as link_7/link_5: 9
+        CHECK(fewer.size() == all.size() - 42u);
+        CHECK(count_links(fewer, 0, 2) == 0 && count_links(fewer, 4, 6) == 0 && count_links(fewer, 0, 3) == 9 && count_links(fewer, 1, 6) == 9);
+        robot->setSelfCollision(false);
+    }
     std::puts("ok robot_model");
 
     // ---- CovariantMovementPrimitive against the C-ABI host policy ----
