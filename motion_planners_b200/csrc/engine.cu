@@ -105,9 +105,8 @@ struct stomp_b200_engine {
     JointLimits limits;             // robot.lower / upper, for the sampling kernels
     SdfParams sdf;
     float* d_sdf = nullptr;
-    SelfPairs self_pairs = {nullptr, nullptr, 0, 0};   // stomp_b200_set_self_collision; n == 0: world collisions only
-    int2* d_pair_ij = nullptr;
-    double* d_pair_limit2 = nullptr;
+    SelfPairs self_pairs = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};   // stomp_b200_set_self_collision; n == 0: world collisions only
+    std::vector<void*> self_pair_buffers;
     bool have_chain = false, have_spheres = false, have_sdf = false, have_matrices = false;
     std::vector<uint8_t> have_policy;
 
@@ -242,12 +241,19 @@ int check_launch(stomp_b200_engine* e, const char* what)
 }
 
 // the state kernel with the sphere-pair rule (stomp_b200_set_self_collision), its centre storage sized to the robot
+template <int kCap>
+void launch_states_self_collision_t(stomp_b200_engine* e, const StateKernelArgs& a, dim3 grid, cudaStream_t stream)
+{
+    if (e->robot.simple_chain) states_self_collision_kernel<kCap, true><<<grid, 128, 0, stream>>>(a, e->robot, e->sdf, e->self_pairs);
+    else states_self_collision_kernel<kCap, false><<<grid, 128, 0, stream>>>(a, e->robot, e->sdf, e->self_pairs);
+}
+
 void launch_states_self_collision(stomp_b200_engine* e, const StateKernelArgs& a, dim3 grid, cudaStream_t stream)
 {
     const int S = e->robot.num_spheres;
-    if (S <= 32) states_self_collision_kernel<32><<<grid, 128, 0, stream>>>(a, e->robot, e->sdf, e->self_pairs);
-    else if (S <= 64) states_self_collision_kernel<64><<<grid, 128, 0, stream>>>(a, e->robot, e->sdf, e->self_pairs);
-    else states_self_collision_kernel<STOMP_B200_MAX_SPHERES><<<grid, 128, 0, stream>>>(a, e->robot, e->sdf, e->self_pairs);
+    if (S <= 32) launch_states_self_collision_t<32>(e, a, grid, stream);
+    else if (S <= 64) launch_states_self_collision_t<64>(e, a, grid, stream);
+    else launch_states_self_collision_t<STOMP_B200_MAX_SPHERES>(e, a, grid, stream);
 }
 
 // tiles per slab: the slabs of a launch are equally wide (ceil(T / 8) n8 tiles over ceil(T / 104) slabs)
@@ -927,8 +933,7 @@ int stomp_b200_destroy(stomp_b200_engine* e)
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* p : e->allocations) cudaFree(p);
     if (e->d_sdf) cudaFree(e->d_sdf);
-    if (e->d_pair_ij) cudaFree(e->d_pair_ij);
-    if (e->d_pair_limit2) cudaFree(e->d_pair_limit2);
+    for (void* p : e->self_pair_buffers) cudaFree(p);
     if (e->h_cost) cudaFreeHost(e->h_cost);
     if (e->h_impr) cudaFreeHost(e->h_impr);
     if (e->h_valid) cudaFreeHost(e->h_valid);
@@ -1051,32 +1056,82 @@ int stomp_b200_set_self_collision(stomp_b200_engine* e, int32_t num_pairs, const
 {
     if (!e || num_pairs < 0 || (num_pairs > 0 && !pairs)) return STOMP_B200_ERR_INVALID_ARGUMENT;
     if (!e->have_spheres) return fail(e, STOMP_B200_ERR_NOT_READY, "stomp_b200_set_spheres comes first");
-    const int S = e->robot.num_spheres;
+    const RobotParams& r = e->robot;
+    const int S = r.num_spheres, D = e->D;
     if (num_pairs > S * (S - 1) / 2) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "more pairs than distinct sphere pairs");
+    std::vector<int> link_of((size_t)S, 0);
+    for (int d = 0; d < D; ++d)
+        for (int s = r.sphere_begin[d]; s < r.sphere_begin[d + 1]; ++s) link_of[s] = d;
     std::vector<int2> ij((size_t)num_pairs);
-    std::vector<double> limit2((size_t)num_pairs);
     for (int p = 0; p < num_pairs; ++p) {
         int i = pairs[2 * p], j = pairs[2 * p + 1];
         if (i > j) std::swap(i, j);
         if (i < 0 || j >= S || i == j) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "self-collision pair: sphere index out of range");
         ij[p] = make_int2(i, j);
-        const double sum = e->robot.sphere[i].r + e->robot.sphere[j].r;
+    }
+    // blocks by link pair (spheres are sorted by link, so link_of is monotone in the sphere index)
+    std::stable_sort(ij.begin(), ij.end(), [&](const int2& u, const int2& v) {
+        return std::make_pair(link_of[u.x], link_of[u.y]) < std::make_pair(link_of[v.x], link_of[v.y]);
+    });
+    std::vector<double> limit2((size_t)num_pairs);
+    for (int p = 0; p < num_pairs; ++p) {
+        const double sum = r.sphere[ij[p].x].r + r.sphere[ij[p].y].r;
         limit2[p] = sum * sum;
+    }
+    // one bounding sphere per link around its collision spheres, in the link frame; the radius is inflated (1e-9 relative +
+    // 1e-9 m) — orders of magnitude above the rounding of the centres, so the cull is conservative
+    std::vector<double> bound(4 * (size_t)D, 0.0), bound_radius((size_t)D, 0.0);
+    for (int d = 0; d < D; ++d) {
+        const int s0 = r.sphere_begin[d], s1 = r.sphere_begin[d + 1];
+        if (s1 <= s0) continue;
+        for (int i = 0; i < 3; ++i) {
+            double m = 0.0;
+            for (int s = s0; s < s1; ++s) m += r.sphere[s].l[i];
+            bound[4 * d + i] = m / (s1 - s0);
+        }
+        double radius = 0.0;
+        for (int s = s0; s < s1; ++s) {
+            double d2 = 0.0;
+            for (int i = 0; i < 3; ++i) { const double t = r.sphere[s].l[i] - bound[4 * d + i]; d2 += t * t; }
+            radius = std::max(radius, std::sqrt(d2) + r.sphere[s].r);
+        }
+        bound_radius[d] = radius * (1.0 + 1e-9) + 1e-9;
+    }
+    std::vector<int4> block;
+    std::vector<double> block_limit2;
+    for (int p = 0; p < num_pairs; ++p) {
+        const int la = link_of[ij[p].x], lb = link_of[ij[p].y];
+        if (block.empty() || block.back().x != la || block.back().y != lb) {
+            block.push_back(make_int4(la, lb, p, p));
+            const double sum = bound_radius[la] + bound_radius[lb];
+            block_limit2.push_back(sum * sum);
+        }
+        block.back().w = p + 1;
     }
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     if (e->side_stream) CUDA_TRY(e, cudaStreamSynchronize(e->side_stream));
-    e->self_pairs.n = 0;
-    if (e->d_pair_ij) { cudaFree(e->d_pair_ij); e->d_pair_ij = nullptr; }
-    if (e->d_pair_limit2) { cudaFree(e->d_pair_limit2); e->d_pair_limit2 = nullptr; }
+    e->self_pairs = SelfPairs{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+    for (void* p : e->self_pair_buffers) cudaFree(p);
+    e->self_pair_buffers.clear();
     if (num_pairs > 0) {
-        CUDA_TRY(e, cudaMalloc(&e->d_pair_ij, sizeof(int2) * (size_t)num_pairs));
-        CUDA_TRY(e, cudaMalloc(&e->d_pair_limit2, sizeof(double) * (size_t)num_pairs));
-        CUDA_TRY(e, cudaMemcpy(e->d_pair_ij, ij.data(), sizeof(int2) * (size_t)num_pairs, cudaMemcpyHostToDevice));
-        CUDA_TRY(e, cudaMemcpy(e->d_pair_limit2, limit2.data(), sizeof(double) * (size_t)num_pairs, cudaMemcpyHostToDevice));
-        e->self_pairs.ij = e->d_pair_ij;
-        e->self_pairs.limit2 = e->d_pair_limit2;
-        e->self_pairs.n = num_pairs;
+        auto upload = [&](const void* src, size_t bytes, const void** dst) -> int {
+            void* d = nullptr;
+            CUDA_TRY(e, cudaMalloc(&d, bytes));
+            e->self_pair_buffers.push_back(d);
+            CUDA_TRY(e, cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+            *dst = d;
+            return 0;
+        };
+        SelfPairs sp{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+        if (int rc = upload(ij.data(), sizeof(int2) * ij.size(), (const void**)&sp.ij)) return rc;
+        if (int rc = upload(limit2.data(), sizeof(double) * limit2.size(), (const void**)&sp.limit2)) return rc;
+        if (int rc = upload(block.data(), sizeof(int4) * block.size(), (const void**)&sp.block)) return rc;
+        if (int rc = upload(block_limit2.data(), sizeof(double) * block_limit2.size(), (const void**)&sp.block_limit2)) return rc;
+        if (int rc = upload(bound.data(), sizeof(double) * bound.size(), (const void**)&sp.link_bound)) return rc;
+        sp.n = num_pairs;
+        sp.nblocks = (int32_t)block.size();
+        e->self_pairs = sp;
     }
     return STOMP_B200_OK;
 }

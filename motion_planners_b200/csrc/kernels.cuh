@@ -1229,18 +1229,23 @@ evaluate_states_kernel(const __grid_constant__ RobotParams robot, const __grid_c
 //   |c_i - c_j|^2 < (r_i + r_j)^2,   |.|^2 = fma(dz, dz, fma(dy, dy, dx * dx)),   the limit squared on the host.
 // Replaces the state kernel (generated or generic) at all of its call sites while a pair list is set; the
 // argument block is the generated kernel's, so the noisy rollouts, the padded policy rows of the noise-less
-// rollout and stomp_b200_evaluate_states all go through this one kernel.  First version: generic FK, sphere
-// centres in thread-local memory, pairs walked in list order (warp-uniform loads); the pair loop is skipped for
-// states an obstacle already condemns.
+// rollout and stomp_b200_evaluate_states all go through this one kernel.
+// Sphere centres and one bounding sphere per link live in thread-local memory (L1).  The host sorts the pairs into
+// blocks by link pair; a block is only walked when the two links' bounding spheres overlap.  The bounding radii are
+// inflated by far more than the rounding of the centres, so the cull never removes a pair that the exact rule
+// accepts: verdicts stay those of the plain list walk (what the oracle does).  Measured on the dual-arm workload
+// (K=2048, T=150, 560 pairs): 635 us as a plain list walk.
 // =====================================================================================================
 struct SelfPairs {
-    const int2* ij;          // [n] sphere indices, x < y
-    const double* limit2;    // [n] (r_x + r_y)^2
-    int32_t n;
-    int32_t pad_;
+    const int2* ij;              // [n] sphere indices, x < y, sorted by (link of x, link of y)
+    const double* limit2;        // [n] (r_x + r_y)^2
+    const int4* block;           // [nblocks] (link a, link b, first pair, end pair)
+    const double* block_limit2;  // [nblocks] (bound_a + bound_b)^2 of the inflated bounding radii
+    const double* link_bound;    // [D][4] bounding sphere of a link's spheres in the link frame: x, y, z, (unused)
+    int32_t n, nblocks;
 };
 
-template <int kSphereCapacity>   // thread-local centre storage, sized by the host to the robot (32 / 64 / 128 spheres)
+template <int kSphereCapacity, bool kSimple>   // thread-local centre storage sized by the host to the robot (32 / 64 / 128)
 __global__ void __launch_bounds__(128)
 states_self_collision_kernel(const __grid_constant__ StateKernelArgs a, const __grid_constant__ RobotParams robot,
                              const __grid_constant__ SdfParams sdf, const __grid_constant__ SelfPairs pairs)
@@ -1260,12 +1265,17 @@ states_self_collision_kernel(const __grid_constant__ StateKernelArgs a, const __
         const double* xq = a.rollouts + ((size_t)q * a.slots + k) * a.rollout_stride + t;
         const size_t rs = (size_t)a.row_stride;
         double c[3 * kSphereCapacity];
+        double bc[3 * STOMP_B200_MAX_DIMS];
         Frame f;
         frame_identity(f);
         bool hit = false;
         const int nj = robot.num_joints;
         for (int d = 0; d < nj; ++d) {
-            apply_joint<false>(f, robot.joint[d], xq[(size_t)d * rs]);
+            apply_joint<kSimple>(f, robot.joint[d], xq[(size_t)d * rs]);
+            const double bx = __ldg(pairs.link_bound + 4 * d), by = __ldg(pairs.link_bound + 4 * d + 1), bz = __ldg(pairs.link_bound + 4 * d + 2);
+            bc[3 * d] = fma(f.r02, bz, fma(f.r01, by, fma(f.r00, bx, f.px)));
+            bc[3 * d + 1] = fma(f.r12, bz, fma(f.r11, by, fma(f.r10, bx, f.py)));
+            bc[3 * d + 2] = fma(f.r22, bz, fma(f.r21, by, fma(f.r20, bx, f.pz)));
             const int s1 = robot.sphere_begin[d + 1];
             for (int s = robot.sphere_begin[d]; s < s1; ++s) {
                 double cx, cy, cz;
@@ -1275,8 +1285,13 @@ states_self_collision_kernel(const __grid_constant__ StateKernelArgs a, const __
                 hit |= (dist - robot.sphere[s].r) < 0.0;
             }
         }
-        if (!hit) {
-            for (int pr = 0; pr < pairs.n; ++pr) {
+        for (int b = 0; b < pairs.nblocks && !hit; ++b) {
+            const int4 blk = __ldg(pairs.block + b);
+            const double ex = bc[3 * blk.x] - bc[3 * blk.y];
+            const double ey = bc[3 * blk.x + 1] - bc[3 * blk.y + 1];
+            const double ez = bc[3 * blk.x + 2] - bc[3 * blk.y + 2];
+            if (!(fma(ez, ez, fma(ey, ey, ex * ex)) < __ldg(pairs.block_limit2 + b))) continue;   // links too far apart
+            for (int pr = blk.z; pr < blk.w; ++pr) {
                 const int2 ij = __ldg(pairs.ij + pr);
                 const double dx = c[3 * ij.x] - c[3 * ij.y];
                 const double dy = c[3 * ij.x + 1] - c[3 * ij.y + 1];
