@@ -381,11 +381,12 @@ template <int kFirstTile, int kTiles>
 __device__ __forceinline__ void dmma_chunk(double (&acc)[kTiles][2], const double (&z)[4], const double* __restrict__ b0)
 {
     constexpr int kSlabStride = dmma_slab_stride(kTiles);
-    if (kFirstTile >= kTiles) return;
+    if constexpr (kFirstTile < kTiles) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4; ++j) {
 #pragma unroll
-        for (int nt = kFirstTile; nt < kTiles; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], z[j], b0[j * kSlabStride + 8 * nt]);
+            for (int nt = kFirstTile; nt < kTiles; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], z[j], b0[j * kSlabStride + 8 * nt]);
+        }
     }
 }
 
