@@ -180,8 +180,8 @@ def cpu_baseline(problem, workload, threads, sample_rollouts, iterations, dense=
     o = Oracle(num_time_steps=T, num_dimensions=D, min_rollouts=sample_rollouts, max_rollouts=sample_rollouts,
                num_rollouts_per_iteration=sample_rollouts, noise_stddev=problem.noise_stddev,
                use_openmp=threads > 1, dense_control_costs=dense, seed=42)
-    if threads > 1:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+    from oracle import binding as ob_
+    ob_.set_num_threads(max(1, threads))     # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
     o.set_problem(problem, query=0)
     states = sample_rollouts * T * iterations
     if reference_kind() == "reference":
@@ -204,7 +204,7 @@ def run_reference(args):
     from oracle import binding as ob
     problem = make_problem(args.workload)
     w = WORKLOADS[args.workload]
-    threads = ob.max_threads()
+    threads = ob.set_num_threads(ob.host_cores())
     T = problem.num_time_steps
     sample = min(w["K"], args.reference_sample)
     # warm-up + timed steps; every step is one iteration over the bounded sample
@@ -229,6 +229,84 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def sharded_parity_check(problem, shard_mode, world, rank, local, dist, iterations=3):
+    """N > 1 only: the sharded run against a single-GPU run of the same problem on this rank's GPU, before anything is
+    timed.  Rollout sharding: same Philox samples by construction (the counters use the global rollout index), so the
+    local verdicts / rollouts are the matching slice of the single-GPU ones and the rollout-indexed tables, the update
+    and the parameters agree within 1e-9.  Query sharding: bit for bit.  Returns (ok, detail); all ranks agree on ok."""
+    import numpy as np
+    from motion_planners_b200 import binding, problems as P, sharding
+    ok, detail = True, ""
+    try:
+        if shard_mode == 0:
+            single = binding.engine_for_problem(problem, device=local, keep_debug_tensors=False)
+            shard = binding.engine_for_problem(problem, device=local, world_size=world, rank=rank, shard_mode=0)
+            uid = binding.comm_unique_id() if rank == 0 else bytes(128)
+            shard.comm_init(broadcast_bytes(dist, uid, local))
+            K = problem.num_rollouts
+            off, cnt = sharding.rollout_shard(K, world, rank)
+            single.begin_solve(); shard.begin_solve()
+            for it in range(iterations):
+                c1, v1, _ = single.iterate(it)
+                c2, v2, _ = shard.iterate(it)
+                np.testing.assert_array_equal(shard.tensor("verdicts")[0][:cnt], single.tensor("verdicts")[0][off:off + cnt])
+                np.testing.assert_allclose(shard.tensor("rollouts")[0][:cnt], single.tensor("rollouts")[0][off:off + cnt], rtol=1e-9, atol=1e-12)
+                np.testing.assert_allclose(shard.tensor("total_cost")[0], single.tensor("total_cost")[0], rtol=1e-9)
+                np.testing.assert_allclose(shard.tensor("probabilities")[0][:, :, 0], single.tensor("probabilities")[0][:, :, 0], rtol=1e-9, atol=1e-300)
+                np.testing.assert_allclose(shard.tensor("updates")[0], single.tensor("updates")[0], rtol=1e-9, atol=1e-13)
+                np.testing.assert_allclose(shard.tensor("parameters")[0], single.tensor("parameters")[0], rtol=1e-9, atol=1e-12)
+                np.testing.assert_allclose(shard.tensor("stddevs")[0], single.tensor("stddevs")[0], rtol=1e-9)
+                np.testing.assert_allclose(c2, c1, rtol=1e-9)
+                assert bool(v1[0]) == bool(v2[0])
+            single.close(); shard.close()
+            detail = f"rollout sharding: {iterations} iterations at K={K}, verdicts identical, costs / probabilities / update / parameters within 1e-9 of the single-GPU run"
+        else:
+            Qs = 4 * world + 1
+            sub = P.Problem(problem.chain, problem.spheres, problem.sdf, problem.start[:Qs], problem.goal[:Qs], problem.noise_stddev,
+                            problem.num_time_steps, problem.num_rollouts, num_queries=Qs)
+            whole = binding.engine_for_problem(sub, device=local)
+            part = binding.engine_for_problem(sub, device=local, world_size=world, rank=rank, shard_mode=1)
+            whole.begin_solve(); part.begin_solve()
+            whole.run(0, iterations); part.run(0, iterations)
+            a, b = whole.finish_solve(), part.finish_solve()
+            np.testing.assert_array_equal(b["solution"], a["solution"][part.query_offset:part.query_offset + part.Q])
+            np.testing.assert_array_equal(b["cost"], a["cost"][part.query_offset:part.query_offset + part.Q])
+            whole.close(); part.close()
+            detail = f"query sharding: {Qs} queries x {iterations} iterations, solutions bit for bit those of one engine"
+    except Exception as exc:      # a failed comparison must not hide the timing; it is reported in the line
+        ok, detail = False, f"{type(exc).__name__}: {str(exc)[:300]}"
+    # every rank must have passed
+    import torch
+    t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    all_ok = bool(t.item() > 0.5)
+    if ok and not all_ok:
+        detail = "another rank failed: " + detail
+    return all_ok, detail
+
+
+def query_sharded_c4(args, rank, world, local, dist, steps):
+    """BASELINE configs[3] — 1024 independent queries (K=64, T=200), queries sharded over the ranks, no collective —
+    measured next to the main workload so that its scaling is in the driver's own lines.  Device time, max over ranks,
+    L2 not flushed (the working set of one rank's share, 0.73 GB at N=1, is beyond L2 anyway)."""
+    from motion_planners_b200 import binding
+    w = WORKLOADS["c4"]
+    problem = make_problem("c4")
+    eng = binding.engine_for_problem(problem, device=local, world_size=world, rank=rank, shard_mode=1)
+    eng.begin_solve()
+    eng.run(0, 3)
+    dist_barrier(dist, local)
+    eng.timer_begin()
+    eng.run(3, steps)
+    ms = dist_max(dist, eng.timer_end(), local)
+    eng.finish_solve()
+    eng.close()
+    states = w["Q"] * w["K"] * w["T"]
+    return {"workload": w["label"], "value": states * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "steps": steps, "n_gpus": world, "sharding": "queries" if world > 1 else "none", "scaling": "strong (1024 queries in total)",
+            "l2": "not flushed: the working set is beyond L2"}
+
+
 def run_ours(args):
     from motion_planners_b200 import binding
     rank, world, local, dist = dist_setup(args.gpus)
@@ -238,6 +316,9 @@ def run_ours(args):
     S = len(problem.spheres.link)
     Q = problem.num_queries
     shard_mode = 1 if w["kind"] == "batch" else 0
+    parity_ok, parity_detail = (None, "single GPU: nothing is sharded")
+    if world > 1:
+        parity_ok, parity_detail = sharded_parity_check(problem, shard_mode, world, rank, local, dist)
     eng = binding.engine_for_problem(problem, device=local, world_size=world, rank=rank, shard_mode=shard_mode)
     if world > 1 and shard_mode == 0:
         uid = binding.comm_unique_id() if rank == 0 else bytes(128)
@@ -325,6 +406,12 @@ def run_ours(args):
             eng.begin_solve()
             eng.run(0, 50)
     clocks = sampler.stop() if rank == 0 else None
+    c4 = None
+    if args.workload != "c4" and not args.skip_c4:
+        try:
+            c4 = query_sharded_c4(args, rank, world, local, dist, max(5, min(args.steps, 20)))
+        except Exception as exc:
+            c4 = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
 
     if rank != 0:
         eng.close()
@@ -359,7 +446,7 @@ def run_ours(args):
     cb = None
     if not args.skip_cpu_baseline:
         from oracle import binding as ob
-        threads = ob.max_threads()
+        threads = ob.set_num_threads(ob.host_cores())
         sample = min(K, args.cpu_sample)
         base_rate, base_s = cpu_baseline(problem, args.workload, threads, sample, 5)
         one_rate, _ = cpu_baseline(problem, args.workload, 1, max(8, sample // 8), 2)
@@ -381,6 +468,8 @@ def run_ours(args):
                 "what": "set_policy + begin_solve + one stomp_b200_iterate per step (noise-less cost / validity / stop "
                         "flag read back every step) + finish_solve (solution read back), host wall clock"},
         "gpu_launches": int(launches),
+        "parity_ok": parity_ok, "parity": parity_detail,
+        "query_sharded_c4": c4,
         "steady_state": {"value": states_per_step * args.steps / (steady_ms * 1e-3), "ms_per_step": steady_ms / args.steps,
                          "what": "same steps queued back to back without L2 flushes, as solve() runs them"},
         "roofline": {"kernel": "stomp_b200_states_specialised" if kind == "specialised" else "rollout_states_kernel",
@@ -415,6 +504,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=2048, dest="cpu_sample")
     ap.add_argument("--reference-sample", type=int, default=1024, dest="reference_sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true", dest="skip_cpu_baseline")
+    ap.add_argument("--skip-c4", action="store_true", dest="skip_c4")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -111,6 +111,24 @@ int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int3
 int stomp_b200_set_sdf(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
                        const float* grid);
 
+/* ---- environment -> distance field, built on the device --------------------------------
+ * The reference hands its world to FCL as collision objects: primitives, meshes, an octomap
+ * (src/MotionPlanners.cpp:162-173 assignOctomapPlanningScene / updateOctomap, :416-495 handleCollisionObjectInWorld /
+ * handleGraspObject; include/motion_planners/Config.hpp:14-35).  Here they become the distance field the state kernel
+ * gathers from, without a host grid or a host-to-device copy of it:
+ *   primitives: kind[i] 0 = sphere (size[i][0] = radius), 1 = box (size[i] = half extents); exact signed distance of
+ *     the union at every voxel centre origin + (i + 0.5) * voxel_size, FP64, rounded to binary32;
+ *   occupancy [nz][ny][nx] uint8 (a voxelised mesh, or the leaves of an octomap at the grid's resolution): exact
+ *     Euclidean distance transform, centre to centre, positive outside the occupied set and negative inside.
+ * get_sdf copies the grid back (tests / inspection); any output may be NULL. */
+int stomp_b200_build_sdf_primitives(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
+                                    int32_t num_primitives, const int32_t* kind /*[n]*/, const double* centre /*[n][3]*/,
+                                    const double* size /*[n][3]*/);
+int stomp_b200_build_sdf_occupancy(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
+                                   const uint8_t* occupied /*[nz][ny][nx]*/);
+int stomp_b200_get_sdf(stomp_b200_engine* e, float* out, size_t count, int32_t dims_out[3], double origin_out[3],
+                       double* voxel_size_out);
+
 /* ---- policy: the host-computed products of CovariantMovementPrimitive::initialize ----------------------
  * (CovariantMovementPrimitive.cpp:57-74,136-301; computed by stomp_b200_host_policy below or by the
  * C++ stomp::CovariantMovementPrimitive in include/stomp/).  R = control_costs_, Rinv = inv_control_costs_,

@@ -38,6 +38,7 @@ SYMBOLS = [
     "stomp_b200_set_timeline", "stomp_b200_get_timeline", "stomp_b200_launch_count", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
     "stomp_b200_state_kernel_kind", "stomp_b200_state_kernel_source", "stomp_b200_codegen_selftest",
     "stomp_b200_set_cost_cumulation", "stomp_b200_set_self_collision",
+    "stomp_b200_build_sdf_primitives", "stomp_b200_build_sdf_occupancy", "stomp_b200_get_sdf",
 ]
 
 
@@ -94,6 +95,9 @@ def lib():
         L.stomp_b200_set_spheres.argtypes = [vp, C.c_int32, ip, dp, dp]
         L.stomp_b200_set_sdf.argtypes = [vp, ip, dp, C.c_double, C.POINTER(C.c_float)]
         L.stomp_b200_set_self_collision.argtypes = [vp, C.c_int32, ip]
+        L.stomp_b200_build_sdf_primitives.argtypes = [vp, ip, dp, C.c_double, C.c_int32, ip, dp, dp]
+        L.stomp_b200_build_sdf_occupancy.argtypes = [vp, ip, dp, C.c_double, u8p]
+        L.stomp_b200_get_sdf.argtypes = [vp, C.POINTER(C.c_float), C.c_size_t, ip, dp, dp]
         L.stomp_b200_set_control_cost_matrices.argtypes = [vp, dp, dp, dp]
         L.stomp_b200_set_policy.argtypes = [vp, C.c_int32, dp, dp]
         L.stomp_b200_host_policy.argtypes = [C.c_int32, C.c_int32, C.c_double, dp, dp, C.c_int32, dp, dp, dp, dp, dp]
@@ -259,11 +263,41 @@ class Engine:
         self._check(lib().stomp_b200_set_self_collision(self.h, len(pr), _ip(pr)), "stomp_b200_set_self_collision")
 
     def set_sdf(self, sdf):
+        """A host grid is uploaded; a lazy Sdf (grid None, primitives listed) is built on the device."""
+        if sdf.grid is None:
+            return self.build_sdf_primitives(sdf.dims, sdf.origin, sdf.voxel, *sdf.primitive_arrays())
         grid = np.ascontiguousarray(sdf.grid, dtype=np.float32)
         dims = np.ascontiguousarray(sdf.dims, dtype=np.int32)
         org = _c64(sdf.origin)
         self._check(lib().stomp_b200_set_sdf(self.h, _ip(dims), _dp(org), float(sdf.voxel),
                                              grid.ctypes.data_as(C.POINTER(C.c_float))), "stomp_b200_set_sdf")
+
+    def build_sdf_primitives(self, dims, origin, voxel, kind, centre, size):
+        """Distance field of a union of spheres / boxes, built on the device."""
+        dims = np.ascontiguousarray(dims, dtype=np.int32)
+        org, kind = _c64(origin), np.ascontiguousarray(kind, dtype=np.int32)
+        centre, size = _c64(centre).reshape(-1, 3), _c64(size).reshape(-1, 3)
+        self._check(lib().stomp_b200_build_sdf_primitives(self.h, _ip(dims), _dp(org), float(voxel), len(kind), _ip(kind),
+                                                          _dp(centre), _dp(size)), "stomp_b200_build_sdf_primitives")
+
+    def build_sdf_occupancy(self, occupied, origin, voxel):
+        """Signed Euclidean distance transform of an occupancy grid [nz][ny][nx] (uint8), built on the device."""
+        occ = np.ascontiguousarray(occupied, dtype=np.uint8)
+        dims = np.array(occ.shape[::-1], dtype=np.int32)
+        org = _c64(origin)
+        self._check(lib().stomp_b200_build_sdf_occupancy(self.h, _ip(dims), _dp(org), float(voxel),
+                                                         occ.ctypes.data_as(C.POINTER(C.c_uint8))), "stomp_b200_build_sdf_occupancy")
+
+    def get_sdf(self):
+        """(grid float32 [nz][ny][nx], origin[3], voxel) of the field the engine holds."""
+        dims = np.zeros(3, dtype=np.int32)
+        org = np.zeros(3)
+        vox = C.c_double(0)
+        self._check(lib().stomp_b200_get_sdf(self.h, None, 0, _ip(dims), _dp(org), C.byref(vox)), "stomp_b200_get_sdf")
+        out = np.empty((int(dims[2]), int(dims[1]), int(dims[0])), dtype=np.float32)
+        self._check(lib().stomp_b200_get_sdf(self.h, out.ctypes.data_as(C.POINTER(C.c_float)), out.size, None, None, None),
+                    "stomp_b200_get_sdf")
+        return out, org, vox.value
 
     def set_matrices(self, R, Rinv, L):
         R, L = _c64(R), _c64(L)

@@ -28,6 +28,7 @@
 #include "../../include/stomp_b200.h"
 #include "../host/policy_core.hpp"
 #include "kernels.cuh"
+#include "sdf_builder.cuh"
 #include "state_codegen.hpp"
 
 using namespace stomp_b200;
@@ -105,6 +106,8 @@ struct stomp_b200_engine {
     JointLimits limits;             // robot.lower / upper, for the sampling kernels
     SdfParams sdf;
     float* d_sdf = nullptr;
+    size_t sdf_count = 0;
+    double sdf_origin[3] = {0, 0, 0}, sdf_voxel = 0;
     SelfPairs self_pairs = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};   // stomp_b200_set_self_collision; n == 0: world collisions only
     std::vector<void*> self_pair_buffers;
     bool have_chain = false, have_spheres = false, have_sdf = false, have_matrices = false;
@@ -1136,23 +1139,126 @@ int stomp_b200_set_self_collision(stomp_b200_engine* e, int32_t num_pairs, const
     return STOMP_B200_OK;
 }
 
-int stomp_b200_set_sdf(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size, const float* grid)
+// (re)allocates the device grid and records its geometry; the caller fills it
+static int adopt_sdf_geometry(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size)
 {
-    if (!e || !dims || !origin || !grid || !(voxel_size > 0.0)) return STOMP_B200_ERR_INVALID_ARGUMENT;
-    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     const size_t count = (size_t)dims[0] * dims[1] * dims[2];
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    if (e->d_sdf) { cudaFree(e->d_sdf); e->d_sdf = nullptr; }
-    CUDA_TRY(e, cudaMalloc(&e->d_sdf, count * sizeof(float)));
-    CUDA_TRY(e, cudaMemcpy(e->d_sdf, grid, count * sizeof(float), cudaMemcpyHostToDevice));
+    if (e->side_stream) CUDA_TRY(e, cudaStreamSynchronize(e->side_stream));
+    if (e->d_sdf && e->sdf_count != count) { cudaFree(e->d_sdf); e->d_sdf = nullptr; }
+    if (!e->d_sdf) {
+        e->have_sdf = false;
+        CUDA_TRY(e, cudaMalloc(&e->d_sdf, count * sizeof(float)));
+        e->sdf_count = count;
+    }
     e->sdf.grid = e->d_sdf;
     e->sdf.nx = dims[0]; e->sdf.ny = dims[1]; e->sdf.nz = dims[2];
     e->sdf.inv_h = 1.0 / voxel_size;
     e->sdf.offx = -(origin[0] * e->sdf.inv_h); e->sdf.offy = -(origin[1] * e->sdf.inv_h); e->sdf.offz = -(origin[2] * e->sdf.inv_h);
     e->sdf.wide_index = count >= ((size_t)1 << 31) ? 1 : 0;
-    e->have_sdf = true;
+    e->sdf_origin[0] = origin[0]; e->sdf_origin[1] = origin[1]; e->sdf_origin[2] = origin[2];
+    e->sdf_voxel = voxel_size;
     e->spec_resolved = false;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_set_sdf(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size, const float* grid)
+{
+    if (!e || !dims || !origin || !grid || !(voxel_size > 0.0)) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (int rc = adopt_sdf_geometry(e, dims, origin, voxel_size)) return rc;
+    CUDA_TRY(e, cudaMemcpy(e->d_sdf, grid, e->sdf_count * sizeof(float), cudaMemcpyHostToDevice));
+    e->have_sdf = true;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_build_sdf_primitives(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
+                                    int32_t num_primitives, const int32_t* kind, const double* centre, const double* size)
+{
+    if (!e || !dims || !origin || !(voxel_size > 0.0) || num_primitives < 0) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (num_primitives > 0 && (!kind || !centre || !size)) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || dims[1] > 65535 || dims[2] > 65535) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (num_primitives > kMaxPrimitives) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "too many primitives for one call (256)");
+    for (int i = 0; i < num_primitives; ++i)
+        if (kind[i] != 0 && kind[i] != 1) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "primitive kind must be 0 (sphere) or 1 (box)");
+    if (int rc = adopt_sdf_geometry(e, dims, origin, voxel_size)) return rc;
+    std::vector<PrimitiveList> host(1);
+    PrimitiveList& pl = host[0];
+    std::memset(&pl, 0, sizeof pl);
+    pl.n = num_primitives;
+    for (int i = 0; i < num_primitives; ++i) {
+        pl.kind[i] = kind[i];
+        for (int a = 0; a < 3; ++a) { pl.centre[i][a] = centre[3 * i + a]; pl.size[i][a] = size[3 * i + a]; }
+    }
+    PrimitiveList* d_list = nullptr;
+    CUDA_TRY(e, cudaMalloc(&d_list, sizeof(PrimitiveList)));
+    cudaError_t err = cudaMemcpy(d_list, &pl, sizeof(PrimitiveList), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) {
+        build_sdf_primitives_kernel<<<dim3((dims[0] + 127) / 128, dims[1], dims[2]), 128, 0, e->stream>>>(
+            e->d_sdf, dims[0], dims[1], dims[2], origin[0], origin[1], origin[2], voxel_size, d_list);
+        e->launch_count++;
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(d_list);
+    if (err != cudaSuccess) { e->last_error = std::string("build_sdf_primitives: ") + cudaGetErrorString(err); return STOMP_B200_ERR_CUDA; }
+    e->have_sdf = true;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_build_sdf_occupancy(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
+                                   const uint8_t* occupied)
+{
+    if (!e || !dims || !origin || !occupied || !(voxel_size > 0.0)) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || dims[0] > 1024 || dims[1] > 1024 || dims[2] > 1024)
+        return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "occupancy grids are limited to 1024 voxels per axis (exact int32 squared distances)");
+    if (int rc = adopt_sdf_geometry(e, dims, origin, voxel_size)) return rc;
+    const size_t count = e->sdf_count;
+    const int nx = dims[0], ny = dims[1], nz = dims[2];
+    uint8_t* d_occ = nullptr; int32_t* d_a = nullptr; int32_t* d_b = nullptr; int32_t* d_c = nullptr;
+    auto cleanup = [&]() { cudaFree(d_occ); cudaFree(d_a); cudaFree(d_b); cudaFree(d_c); };
+    cudaError_t err = cudaMalloc(&d_occ, count);
+    if (err == cudaSuccess) err = cudaMalloc(&d_a, count * sizeof(int32_t));
+    if (err == cudaSuccess) err = cudaMalloc(&d_b, count * sizeof(int32_t));
+    if (err == cudaSuccess) err = cudaMalloc(&d_c, count * sizeof(int32_t));
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_occ, occupied, count, cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) {
+        const unsigned blocks = (unsigned)((count + 255) / 256);
+        edt_seed_kernel<<<blocks, 256, 0, e->stream>>>(d_occ, d_a, d_b, count);
+        // three separable passes per transform: x (lines of nx, one per (y, z)), y, z; ping-pong through d_c
+        auto transform = [&](int32_t* buf) {
+            edt_pass_kernel<<<dim3(ny, nz), 256, sizeof(int32_t) * nx, e->stream>>>(buf, d_c, nx, 1, ny, nx, (long long)nx * ny);
+            edt_pass_kernel<<<dim3(nx, nz), 256, sizeof(int32_t) * ny, e->stream>>>(d_c, buf, ny, nx, nx, 1, (long long)nx * ny);
+            edt_pass_kernel<<<dim3(nx, ny), 256, sizeof(int32_t) * nz, e->stream>>>(buf, d_c, nz, (long long)nx * ny, nx, 1, nx);
+            cudaMemcpyAsync(buf, d_c, count * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream);
+        };
+        transform(d_a);
+        transform(d_b);
+        finish_edt_kernel<<<blocks, 256, 0, e->stream>>>(d_occ, d_a, d_b, e->d_sdf, voxel_size, count);
+        e->launch_count += 8;
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cleanup();
+    if (err != cudaSuccess) { e->last_error = std::string("build_sdf_occupancy: ") + cudaGetErrorString(err); return STOMP_B200_ERR_CUDA; }
+    e->have_sdf = true;
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_get_sdf(stomp_b200_engine* e, float* out, size_t count, int32_t dims_out[3], double origin_out[3], double* voxel_size_out)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!e->have_sdf) return fail(e, STOMP_B200_ERR_NOT_READY, "no distance field set");
+    if (dims_out) { dims_out[0] = e->sdf.nx; dims_out[1] = e->sdf.ny; dims_out[2] = e->sdf.nz; }
+    if (origin_out) { origin_out[0] = e->sdf_origin[0]; origin_out[1] = e->sdf_origin[1]; origin_out[2] = e->sdf_origin[2]; }
+    if (voxel_size_out) *voxel_size_out = e->sdf_voxel;
+    if (out) {
+        if (count != e->sdf_count) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "count does not match the grid");
+        CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+        CUDA_TRY(e, cudaMemcpy(out, e->d_sdf, count * sizeof(float), cudaMemcpyDeviceToHost));
+    }
     return STOMP_B200_OK;
 }
 

@@ -84,6 +84,11 @@ def lib():
         L.oracle_full_piv_lu_inverse.argtypes = [dp, C.c_int, dp]
         L.oracle_llt_lower.argtypes = [dp, C.c_int, dp]
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_set_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.argtypes = [C.c_int]
+        L.oracle_set_sdf_primitives.argtypes = [vp, ip, dp, C.c_double, C.c_int, ip, dp, dp]
+        L.oracle_build_sdf_primitives.argtypes = [ip, dp, C.c_double, C.c_int, ip, dp, dp, C.POINTER(C.c_float)]
+        L.oracle_build_sdf_occupancy.argtypes = [ip, C.c_double, u8p, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -163,7 +168,24 @@ class Oracle:
         rc = lib().oracle_set_self_collision(self.h, len(pr), _ip(pr))
         assert rc == 0, rc
 
-    def set_sdf(self, sdf):
+    def set_sdf(self, sdf, analytic=None):
+        """A host grid is used as it is.  A lazy Sdf (grid None, primitives listed) is either built here (OpenMP) or, for
+        `analytic` (default: grids of >= 2^28 voxels), evaluated from the primitives at the voxel each lookup hits."""
+        if sdf.grid is None:
+            kind, centre, size = sdf.primitive_arrays()
+            dims = np.ascontiguousarray(sdf.dims, dtype=np.int32)
+            org = _c64(sdf.origin)
+            count = int(dims[0]) * int(dims[1]) * int(dims[2])
+            if analytic is None:
+                analytic = count >= (1 << 28)
+            if analytic:
+                self._keep.append((kind, centre, size))
+                rc = lib().oracle_set_sdf_primitives(self.h, _ip(dims), _dp(org), float(sdf.voxel), len(kind), _ip(kind),
+                                                     _dp(centre), _dp(size))
+                assert rc == 0, rc
+                return
+            sdf = type(sdf)(dims=sdf.dims, origin=sdf.origin, voxel=sdf.voxel,
+                            grid=build_sdf_primitives(dims, org, sdf.voxel, kind, centre, size), obstacles=sdf.obstacles)
         grid = np.ascontiguousarray(sdf.grid, dtype=np.float32)
         dims = np.ascontiguousarray(sdf.dims, dtype=np.int32)
         org = _c64(sdf.origin)
@@ -294,6 +316,29 @@ class Oracle:
         return out
 
 
+def build_sdf_primitives(dims, origin, voxel, kind, centre, size):
+    """float32 [nz][ny][nx]: exact signed distance of the primitive union at the voxel centres (OpenMP)."""
+    dims = np.ascontiguousarray(dims, dtype=np.int32)
+    org, kind = _c64(origin), np.ascontiguousarray(kind, dtype=np.int32)
+    centre, size = _c64(centre).reshape(-1, 3), _c64(size).reshape(-1, 3)
+    out = np.empty((int(dims[2]), int(dims[1]), int(dims[0])), dtype=np.float32)
+    rc = lib().oracle_build_sdf_primitives(_ip(dims), _dp(org), float(voxel), len(kind), _ip(kind), _dp(centre), _dp(size),
+                                           out.ctypes.data_as(C.POINTER(C.c_float)))
+    assert rc == 0
+    return out
+
+
+def build_sdf_occupancy(occupied, voxel):
+    """float32 [nz][ny][nx]: signed Euclidean distance transform of an occupancy grid (centre to centre, metres)."""
+    occ = np.ascontiguousarray(occupied, dtype=np.uint8)
+    dims = np.array(occ.shape[::-1], dtype=np.int32)
+    out = np.empty(occ.shape, dtype=np.float32)
+    rc = lib().oracle_build_sdf_occupancy(_ip(dims), float(voxel), occ.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                          out.ctypes.data_as(C.POINTER(C.c_float)))
+    assert rc == 0
+    return out
+
+
 def det_sincos(x):
     s, c = C.c_double(0), C.c_double(0)
     lib().oracle_sincos(float(x), C.byref(s), C.byref(c))
@@ -316,3 +361,16 @@ def llt_lower(A):
 
 def max_threads():
     return lib().oracle_max_threads()
+
+
+def host_cores():
+    """Cores this process may run on (the CPU arm uses all of them, whatever OMP_NUM_THREADS the launcher exported)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_num_threads(n):
+    """OpenMP thread count of the oracle (and of oracle/_ref, which shares the OpenMP runtime); returns the count in effect."""
+    return lib().oracle_set_num_threads(int(n))

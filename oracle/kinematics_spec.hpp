@@ -100,13 +100,47 @@ struct SphereSpec {
     double r;            // radius
 };
 
+// one world primitive (what the reference hands to FCL through handleCollisionObjectInWorld,
+// src/MotionPlanners.cpp:416-460): kind 0 sphere (s[0] = radius), 1 box (s = half extents)
+struct PrimitiveSpec {
+    int32_t kind;
+    double c[3];
+    double s[3];
+};
+
 struct SdfSpec {
     int32_t nx, ny, nz;  // x fastest
     double ox, oy, oz;   // world position of the min corner of voxel (0,0,0)
     double inv_h;        // 1 / voxel size
     double offx, offy, offz;   // -(origin * inv_h): voxel coordinate = fma(c, inv_h, off)
-    const float* grid;
+    const float* grid;   // null: the field is evaluated from the primitives at the voxel centre on every lookup
+    double h;                    // voxel size (analytic mode)
+    const PrimitiveSpec* prims;  // analytic mode
+    int32_t num_prims;
 };
+
+// SPEC of the primitive distance field (op order normative; the CUDA builder issues the same operations):
+// signed distance from p to one primitive, negative inside
+static inline double primitive_distance(const PrimitiveSpec& pr, double px, double py, double pz)
+{
+    const double dx = px - pr.c[0], dy = py - pr.c[1], dz = pz - pr.c[2];
+    if (pr.kind == 0) return std::sqrt((dx * dx + dy * dy) + dz * dz) - pr.s[0];
+    const double qx = std::fabs(dx) - pr.s[0], qy = std::fabs(dy) - pr.s[1], qz = std::fabs(dz) - pr.s[2];
+    const double ox = std::fmax(qx, 0.0), oy = std::fmax(qy, 0.0), oz = std::fmax(qz, 0.0);
+    const double outside = std::sqrt((ox * ox + oy * oy) + oz * oz);
+    const double inside = std::fmin(std::fmax(std::fmax(qx, qy), qz), 0.0);
+    return outside + inside;
+}
+
+// value of voxel (ix, iy, iz): (float) min_i d_i(origin + (i + 0.5) * h), primitives in list order
+static inline float primitive_field_value(const PrimitiveSpec* prims, int n, double ox, double oy, double oz, double h,
+                                          int ix, int iy, int iz)
+{
+    const double px = ox + ((double)ix + 0.5) * h, py = oy + ((double)iy + 0.5) * h, pz = oz + ((double)iz + 0.5) * h;
+    double d = INFINITY;
+    for (int i = 0; i < n; ++i) d = std::fmin(d, primitive_distance(prims[i], px, py, pz));
+    return (float)d;
+}
 
 struct Frame { double R[9]; double p[3]; };
 
@@ -231,7 +265,16 @@ static inline size_t sdf_index(const SdfSpec& g, const double c[3])
 
 static inline bool sphere_collides(const SdfSpec& g, const double c[3], double radius)
 {
-    double d = (double)g.grid[sdf_index(g, c)];
+    const size_t idx = sdf_index(g, c);
+    double d;
+    if (g.grid) {
+        d = (double)g.grid[idx];
+    } else {   // analytic mode: the number the built grid holds at this voxel
+        const size_t plane = (size_t)g.nx * (size_t)g.ny;
+        const int iz = (int)(idx / plane), iy = (int)((idx - (size_t)iz * plane) / (size_t)g.nx);
+        const int ix = (int)(idx - (size_t)iz * plane - (size_t)iy * (size_t)g.nx);
+        d = (double)primitive_field_value(g.prims, g.num_prims, g.ox, g.oy, g.oz, g.h, ix, iy, iz);
+    }
     return (d - radius) < 0.0;
 }
 

@@ -38,6 +38,7 @@ struct OracleHandle {
     StompConfig sc;
     std::shared_ptr<SphereSdfTask> task;
     std::unique_ptr<Stomp> stomp;
+    std::vector<PrimitiveSpec> prims;   // analytic distance field (oracle_set_sdf_primitives)
     // StompPlanner::solve loop state (StompPlanner.cpp:96-141)
     double old_cost = 0, cost_improvement = 0, current_cost = 0;
     int num_iterations = 0;
@@ -158,6 +159,94 @@ int oracle_set_sdf(void* hp, const int32_t* dims, const double* origin, double v
     g.inv_h = 1.0 / voxel;
     g.offx = -(g.ox * g.inv_h); g.offy = -(g.oy * g.inv_h); g.offz = -(g.oz * g.inv_h);
     g.grid = grid;
+    g.h = voxel; g.prims = nullptr; g.num_prims = 0;
+    return 0;
+}
+
+// the distance field of a primitive world, evaluated lazily at the voxel a lookup hits (no grid in memory: the
+// >= 2^31-voxel index test); same numbers as oracle_build_sdf_primitives writes
+int oracle_set_sdf_primitives(void* hp, const int32_t* dims, const double* origin, double voxel, int n, const int32_t* kind,
+                              const double* centre, const double* size)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    h->prims.assign(n, PrimitiveSpec());
+    for (int i = 0; i < n; ++i) {
+        h->prims[i].kind = kind[i];
+        for (int a = 0; a < 3; ++a) { h->prims[i].c[a] = centre[3 * i + a]; h->prims[i].s[a] = size[3 * i + a]; }
+    }
+    SdfSpec& g = h->task->sdf_;
+    g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
+    g.ox = origin[0]; g.oy = origin[1]; g.oz = origin[2];
+    g.inv_h = 1.0 / voxel;
+    g.offx = -(g.ox * g.inv_h); g.offy = -(g.oy * g.inv_h); g.offz = -(g.oz * g.inv_h);
+    g.grid = nullptr;
+    g.h = voxel;
+    g.prims = h->prims.data();
+    g.num_prims = n;
+    return 0;
+}
+
+// exact signed distance of a union of primitives at every voxel centre (kinematics_spec.hpp: primitive_field_value);
+// OpenMP over z slabs
+int oracle_build_sdf_primitives(const int32_t* dims, const double* origin, double voxel, int n, const int32_t* kind,
+                                const double* centre, const double* size, float* out)
+{
+    std::vector<PrimitiveSpec> prims(n);
+    for (int i = 0; i < n; ++i) {
+        prims[i].kind = kind[i];
+        for (int a = 0; a < 3; ++a) { prims[i].c[a] = centre[3 * i + a]; prims[i].s[a] = size[3 * i + a]; }
+    }
+    const int nx = dims[0], ny = dims[1], nz = dims[2];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x)
+                out[((size_t)z * ny + y) * nx + x] = primitive_field_value(prims.data(), n, origin[0], origin[1], origin[2], voxel, x, y, z);
+    return 0;
+}
+
+// exact Euclidean distance transform of an occupancy grid [nz][ny][nx], signed (positive outside, negative inside),
+// centre to centre, in metres: h * sqrt(min squared voxel distance), rounded to binary32.  Brute force per line with the
+// same three separable min-plus passes over integer squared distances as the CUDA builder (exact, so the order of the
+// candidates does not matter).
+int oracle_build_sdf_occupancy(const int32_t* dims, double voxel, const uint8_t* occ, float* out)
+{
+    const int nx = dims[0], ny = dims[1], nz = dims[2];
+    const size_t count = (size_t)nx * ny * nz;
+    const int INF = 0x3fffffff;
+    auto transform = [&](std::vector<int32_t>& f) {
+        std::vector<int32_t> g(count);
+        auto pass = [&](const std::vector<int32_t>& in, std::vector<int32_t>& o, int n_line, size_t stride_line, int n_a, size_t stride_a, int n_b, size_t stride_b) {
+#pragma omp parallel for collapse(2) schedule(static)
+            for (int b = 0; b < n_b; ++b)
+                for (int a = 0; a < n_a; ++a) {
+                    const size_t base = (size_t)a * stride_a + (size_t)b * stride_b;
+                    for (int i = 0; i < n_line; ++i) {
+                        int best = INF;
+                        for (int j = 0; j < n_line; ++j) {
+                            const int v = in[base + (size_t)j * stride_line];
+                            if (v >= INF) continue;
+                            const int cand = v + (i - j) * (i - j);
+                            if (cand < best) best = cand;
+                        }
+                        o[base + (size_t)i * stride_line] = best;
+                    }
+                }
+        };
+        pass(f, g, nx, 1, ny, nx, nz, (size_t)nx * ny);
+        pass(g, f, ny, nx, nx, 1, nz, (size_t)nx * ny);
+        pass(f, g, nz, (size_t)nx * ny, nx, 1, ny, nx);
+        f.swap(g);
+    };
+    std::vector<int32_t> to_occ(count), to_free(count);
+    for (size_t i = 0; i < count; ++i) { to_occ[i] = occ[i] ? 0 : INF; to_free[i] = occ[i] ? INF : 0; }
+    transform(to_occ);
+    transform(to_free);
+    for (size_t i = 0; i < count; ++i) {
+        const double d2 = (double)(occ[i] ? to_free[i] : to_occ[i]);
+        const double d = voxel * std::sqrt(d2);
+        out[i] = (float)(occ[i] ? -d : d);
+    }
     return 0;
 }
 
@@ -458,6 +547,19 @@ int oracle_max_threads(void)
 #ifdef _OPENMP
     return omp_get_max_threads();
 #else
+    return 1;
+#endif
+}
+
+// thread count of every later parallel region of this process (torchrun exports OMP_NUM_THREADS=1 to its workers; the
+// CPU arm of bench.py sets the count it reports explicitly); returns the count in effect
+int oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
     return 1;
 #endif
 }
