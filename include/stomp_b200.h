@@ -69,8 +69,10 @@ typedef struct stomp_b200_config {
     double cost_scaling_h;               /* 10.0 (PolicyImprovement.cpp:55) */
     int32_t use_noise_adaptation;        /* use_noise_adaptation_ */
     int32_t use_cumulative_costs;        /* 1 (PolicyImprovement.cpp:56); 0 = per-time-step costs: one GPU, no rollout reuse */
-    int32_t use_projection;              /* 0 (PolicyImprovement.cpp:57); 1 = M-matrix projected noise / update */
-    int32_t per_timestep_minmax;         /* 0 = shipped global min/max; 1 = variant commented out at :518-528 */
+    int32_t use_projection;              /* 0 (PolicyImprovement.cpp:57); 1 = M-matrix projected noise / update
+                                            (PolicyImprovement.cpp:421-440,706,750-801); needs Rinv */
+    int32_t per_timestep_minmax;         /* 0 = shipped global min/max; 1 = variant commented out at :518-528 (differs
+                                            from 0 only with use_cumulative_costs == 0) */
     int32_t device;                      /* CUDA device ordinal */
     int32_t world_size;                  /* ranks (one per GPU) sharing this solve; 1 = single GPU */
     int32_t rank;
@@ -133,7 +135,8 @@ int stomp_b200_get_sdf(stomp_b200_engine* e, float* out, size_t count, int32_t d
  * (CovariantMovementPrimitive.cpp:57-74,136-301; computed by stomp_b200_host_policy below or by the
  * C++ stomp::CovariantMovementPrimitive in include/stomp/).  R = control_costs_, Rinv = inv_control_costs_,
  * L = chol(Rinv) (MultivariateGaussian.hpp:81); identical for every joint and query.  Rinv may be NULL
- * unless use_projection. */
+ * unless use_projection (then the projection matrix and its inverse are formed from it here,
+ * PolicyImprovement::preComputeProjectionMatrices). */
 int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R /*[T][T]*/,
                                          const double* Rinv /*[T][T] or NULL*/, const double* L /*[T][T]*/);
 /* per query (local index): parameters_all_ [D][N] (padding = start / goal) and
@@ -206,7 +209,9 @@ enum stomp_b200_tensor {
     STOMP_B200_NOISELESS_CONTROL_COSTS = 15, /*                       [Q][D][T]     */
     STOMP_B200_UNIT_NOISE = 16,         /* L*eps of the generated rollouts [Q][G][D][T] (keep_debug_tensors) */
     STOMP_B200_EPSILON = 17,            /* eps of the generated rollouts   [Q][G][D][T] (keep_debug_tensors) */
-    STOMP_B200_ROLLOUT_VALIDITY = 18    /* execute()'s validity, uint8     [Q][G]       */
+    STOMP_B200_ROLLOUT_VALIDITY = 18,   /* execute()'s validity, uint8     [Q][G]       */
+    STOMP_B200_NOISE_PROJECTED = 19,    /* noise_projected_ = M * noise_   [Q][K'][D][T] (use_projection) */
+    STOMP_B200_ROLLOUTS_PROJECTED = 20  /* parameters_noise_projected_     [Q][K'][D][T] (configurations with rollout reuse) */
 };
 int stomp_b200_num_rollouts(const stomp_b200_engine* e, int32_t* num_rollouts /*K'*/, int32_t* num_generated /*G*/);
 /* copies the tensor to host memory; out_bytes must equal its size */

@@ -23,7 +23,7 @@ ERR_UNSUPPORTED = -5
 TENSORS = dict(rollouts=0, noise=1, state_costs=2, verdicts=3, control_costs=4, cumulative_costs=5, full_costs=6,
                total_cost=7, probabilities=8, full_probabilities=9, updates=10, parameters=11, parameters_all=12,
                stddevs=13, noiseless_state_costs=14, noiseless_control_costs=15, unit_noise=16, epsilon=17,
-               rollout_validity=18)
+               rollout_validity=18, noise_projected=19, rollouts_projected=20)
 KERNELS = dict(sample=0, cost=1, weights=2, update=3, apply=4, reuse=5, rows=6)
 
 # every symbol include/stomp_b200.h declares (tests/test_cabi_symbols.py checks the library exports them)
@@ -373,7 +373,8 @@ class Engine:
             "total_cost": (Q, n), "probabilities": (Q, n, D, T), "full_probabilities": (Q, n, D),
             "updates": (Q, D, T), "parameters": (Q, D, T), "parameters_all": (Q, D, N), "stddevs": (Q, D),
             "noiseless_state_costs": (Q, T), "noiseless_control_costs": (Q, D, T), "unit_noise": (Q, g, D, T),
-            "epsilon": (Q, g, D, T), "rollout_validity": (Q, g),
+            "epsilon": (Q, g, D, T), "rollout_validity": (Q, g), "noise_projected": (Q, nl, D, T),
+            "rollouts_projected": (Q, nl, D, T),
         }
         dtype = np.uint8 if name in ("verdicts", "rollout_validity") else np.float64
         out = np.empty(shapes[name], dtype=dtype)

@@ -115,6 +115,7 @@ struct stomp_b200_engine {
 
     LoopParams base;                // pointers + constants; per-iteration fields filled in iterate
     double* proj2[2] = {nullptr, nullptr};
+    double* d_Mproj = nullptr; double* d_Minv = nullptr;   // projection_matrix_ / its inverse (use_projection only)
     double* state2[2] = {nullptr, nullptr};
     uint8_t* verdict2[2] = {nullptr, nullptr};
     int cur = 0;
@@ -491,26 +492,43 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             if (int rc = check_launch(e, "edge_rows_kernel")) return rc;
             e->edge_dirty = false;
         }
-        // one rule with Toeplitz interior rows, Toeplitz R, even T and 16-byte aligned rows: the register-window kernel
-        const bool fast = lp.st_n > 0 && lp.num_rules == 1 && (lp.r_toeplitz || !lp.use_noise_adaptation) && e->T % 2 == 0 && e->N >= 12;
-        if (fast) {
-            bool taps5 = true;
-            for (int j = 0; j < lp.st_n; ++j) taps5 = taps5 && lp.st_off[j] > -3 && lp.st_off[j] < 3;
-            const bool rb4 = lp.rband_halfwidth <= 4;
-            const dim3 grid((rows + 7) / 8, e->Q);
-            static const bool tile_allowed = !(std::getenv("STOMP_B200_ROWS") && std::strcmp(std::getenv("STOMP_B200_ROWS"), "fast") == 0);
-            if (taps5 && rb4 && tile_allowed && launch_rows_tile(e, lp, rows, rows_stream, overlap_rows)) {
-                // launched
-            } else if (taps5 && rb4) control_rows_fast_kernel<true, true><<<grid, 256, 0, rows_stream>>>(lp);
-            else control_rows_fast_kernel<false, false><<<grid, 256, 0, rows_stream>>>(lp);
+        auto launch_rows = [&](const LoopParams& rl) -> int {
+            // one rule with Toeplitz interior rows, Toeplitz R, even T and 16-byte aligned rows: the register-window kernel
+            const bool fast = rl.st_n > 0 && rl.num_rules == 1 && (rl.r_toeplitz || !rl.use_noise_adaptation) && e->T % 2 == 0 && e->N >= 12;
+            if (fast) {
+                bool taps5 = true;
+                for (int j = 0; j < rl.st_n; ++j) taps5 = taps5 && rl.st_off[j] > -3 && rl.st_off[j] < 3;
+                const bool rb4 = rl.rband_halfwidth <= 4;
+                const dim3 grid((rows + 7) / 8, e->Q);
+                static const bool tile_allowed = !(std::getenv("STOMP_B200_ROWS") && std::strcmp(std::getenv("STOMP_B200_ROWS"), "fast") == 0);
+                if (taps5 && rb4 && tile_allowed && launch_rows_tile(e, rl, rows, rows_stream, overlap_rows)) {
+                    // launched
+                } else if (taps5 && rb4) control_rows_fast_kernel<true, true><<<grid, 256, 0, rows_stream>>>(rl);
+                else control_rows_fast_kernel<false, false><<<grid, 256, 0, rows_stream>>>(rl);
+            } else {
+                const size_t row_smem = sizeof(double) * (size_t)kRowWarps * (control_row_x_stride(e->N) + control_row_n_stride(e->T));
+                control_rows_kernel<<<dim3((rows + kRowWarps - 1) / kRowWarps, e->Q), kRowWarps * 32, row_smem, rows_stream>>>(rl);
+            }
+            if (int rc = check_launch(e, "control_rows_kernel")) return rc;
+            if (rl.control_costs) {
+                fold_control_costs_kernel<<<dim3((rows + 127) / 128, e->Q), 128, 0, rows_stream>>>(rl);
+                if (int rc = check_launch(e, "fold_control_costs_kernel")) return rc;
+            }
+            return 0;
+        };
+        if (lp.Mproj) {
+            // M-projection (PolicyImprovement.cpp:421-440): noise_projected_ = M * noise_ for the generated rollouts, then
+            // the control costs from parameters_ + noise_projected_ (:812-817) and n^T R n from noise_ (:656-663)
+            project_noise_dmma_kernel<<<dim3((rows + 31) / 32, (e->T + 63) / 64, e->Q), 128, 0, rows_stream>>>(lp);
+            e->launch_count++;
+            if (int rc = check_launch(e, "project_noise_dmma_kernel")) return rc;
+            LoopParams cpass = lp; cpass.rows_noise = lp.noise_proj; cpass.rows_mask = 1;
+            if (int rc = launch_rows(cpass)) return rc;
+            LoopParams qpass = lp; qpass.rows_noise = lp.noise; qpass.rows_mask = 2; qpass.control_costs = nullptr;
+            e->launch_count++;
+            if (int rc = launch_rows(qpass)) return rc;
         } else {
-            const size_t row_smem = sizeof(double) * (size_t)kRowWarps * (control_row_x_stride(e->N) + control_row_n_stride(e->T));
-            control_rows_kernel<<<dim3((rows + kRowWarps - 1) / kRowWarps, e->Q), kRowWarps * 32, row_smem, rows_stream>>>(lp);
-        }
-        if (int rc = check_launch(e, "control_rows_kernel")) return rc;
-        if (lp.control_costs) {
-            fold_control_costs_kernel<<<dim3((rows + 127) / 128, e->Q), 128, 0, rows_stream>>>(lp);
-            if (int rc = check_launch(e, "fold_control_costs_kernel")) return rc;
+            if (int rc = launch_rows(lp)) return rc;
         }
     }
     if (overlap_rows) CUDA_TRY(e, cudaEventRecord(e->ev_rows, rows_stream));
@@ -742,8 +760,6 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     if (cfg->num_queries < 1 || cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
         return STOMP_B200_ERR_INVALID_ARGUMENT;
     if (cfg->shard_mode != 0 && cfg->shard_mode != 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
-    if (cfg->use_projection || cfg->per_timestep_minmax)
-        return STOMP_B200_ERR_UNSUPPORTED;   // switches the reference ships disabled; DESIGN.md "out of scope"
     // Stomp::setCostCumulation(false): built for the plain case (one GPU, no rollout reuse)
     if (!cfg->use_cumulative_costs && (cfg->world_size > 1 || cfg->num_rollouts_per_iteration < cfg->max_rollouts ||
                                        cfg->min_rollouts > cfg->num_rollouts_per_iteration))
@@ -823,6 +839,15 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &tmp, Q * D * T)); b.mincc = tmp;
     CREATE_TRY(dev_alloc(e, &b.rollouts, Q * S * D * T));
     CREATE_TRY(dev_alloc(e, &b.noise, Q * S * D * T));
+    b.rows_noise = b.noise;
+    b.rows_mask = 3;
+    b.per_timestep_minmax = cfg->per_timestep_minmax ? 1 : 0;
+    if (cfg->use_projection) {
+        CREATE_TRY(dev_alloc(e, &b.noise_proj, Q * S * D * T));
+        CREATE_TRY(dev_alloc(e, &e->d_Mproj, T * T));
+        CREATE_TRY(dev_alloc(e, &e->d_Minv, T * T));
+        // Mproj / Minv stay null in `base` until stomp_b200_set_control_cost_matrices has filled them
+    }
     for (int i = 0; i < (e->reuse_possible ? 2 : 1); ++i) {
         CREATE_TRY(dev_alloc(e, &e->state2[i], Q * S * T));
         CREATE_TRY(dev_alloc(e, &e->verdict2[i], Q * S * T));
@@ -1264,10 +1289,26 @@ int stomp_b200_get_sdf(stomp_b200_engine* e, float* out, size_t count, int32_t d
 
 int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R, const double* Rinv, const double* L)
 {
-    (void)Rinv;
     if (!e || !R || !L) return STOMP_B200_ERR_INVALID_ARGUMENT;
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     const int T = e->T;
+    if (e->cfg.use_projection) {
+        // PolicyImprovement::preComputeProjectionMatrices (PolicyImprovement.cpp:750-801): M = R^-1 with column p scaled by
+        // 1 / (T * R^-1[p][p]); its inverse by LU with complete pivoting, as Eigen's fullPivLu().inverse() (:795)
+        if (!Rinv) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "use_projection needs Rinv");
+        host::Dense M(T, T), Minv;
+        for (int pcol = 0; pcol < T; ++pcol) {
+            const double column_max = Rinv[(size_t)pcol * T + pcol];
+            const double f = 1.0 / (T * column_max);
+            for (int i = 0; i < T; ++i) M.at(i, pcol) = Rinv[(size_t)i * T + pcol] * f;
+        }
+        if (!host::invert_full_pivot(M, Minv)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "the projection matrix is singular");
+        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+        CUDA_TRY(e, cudaMemcpy(e->d_Mproj, M.data(), sizeof(double) * T * T, cudaMemcpyHostToDevice));
+        CUDA_TRY(e, cudaMemcpy(e->d_Minv, Minv.data(), sizeof(double) * T * T, cudaMemcpyHostToDevice));
+        e->base.Mproj = e->d_Mproj;
+        e->base.Minv = e->d_Minv;
+    }
     std::vector<double> Lt((size_t)T * T), band((size_t)T * (2 * kRBand + 1), 0.0);
     for (int t = 0; t < T; ++t)
         for (int u = 0; u < T; ++u) {
@@ -1526,6 +1567,12 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
             CUDA_TRY(e, cudaMemcpy(out, b.epsilon, out_bytes, cudaMemcpyDeviceToHost));
             return 0;
         case STOMP_B200_ROLLOUT_VALIDITY: return per_query(b.validity, e->last_gen, e->slots, 1);
+        case STOMP_B200_NOISE_PROJECTED:
+            if (!b.noise_proj) return fail(e, STOMP_B200_ERR_NOT_READY, "noise_projected_ exists with use_projection only (it is noise_ otherwise)");
+            return per_query(b.noise_proj, nl * D, (size_t)e->slots * D, T * sizeof(double));
+        case STOMP_B200_ROLLOUTS_PROJECTED:
+            if (!b.proj) return fail(e, STOMP_B200_ERR_NOT_READY, "parameters_noise_projected_ is kept in configurations with rollout reuse only");
+            return per_query(b.proj, nl * D, (size_t)e->slots * D, T * sizeof(double));
         default: return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "unknown tensor id");
     }
 }

@@ -98,6 +98,14 @@ struct LoopParams {
     int32_t st_off[7];
     double st_coef[7];
     double st_dense[7];       // the same taps as a dense row, offsets -3 .. +3 (zeros included)
+    // M-matrix projection (PolicyImprovement::use_projection_, PolicyImprovement.cpp:421-440,706,750-801); all null / 0
+    // in the shipped configuration, where M is the identity
+    const double* Mproj;      // [T][T] projection_matrix_ = R^-1 with column p scaled by 1 / (T * R^-1[p][p]), row major
+    const double* Minv;       // [T][T] inv_projection_matrix_
+    double* noise_proj;       // [Q][slots][D][T] noise_projected_ = M * noise_
+    const double* rows_noise; // what the control-cost row kernels read: noise (default) or noise_proj
+    int32_t rows_mask;        // bit 0: write C_d (control-cost sums), bit 1: write n^T R n; 3 = both (one pass, M = I)
+    int32_t per_timestep_minmax;   // per-time-step costs only: min / max per time step (variant at PolicyImprovement.cpp:518-528)
 };
 
 // the joint limits of OptimizationTask::filter: all the sampling kernels need of the robot (0.5 KB of kernel parameters
@@ -559,6 +567,70 @@ sample_rollouts_dmma_kernel(const __grid_constant__ LoopParams p, const __grid_c
     tls.end();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// PolicyImprovement::computeProjectedNoise (PolicyImprovement.cpp:421-440) with use_projection_:
+//   noise_projected_[c][t] = sum_u M[t][u] * noise_[c][u],  parameters_noise_projected_ = parameters_ + noise_projected_
+// for the G * D generated columns c = (k, d) of every query: the second contraction of the loop, dense this time (M =
+// R^-1 with scaled columns), on the same FP64 tensor path as the sampler (mma.sync.m8n8k4.f64).  CTA tile 32 columns x
+// 64 time steps, four warps of 8 columns each (8 n8 tiles = 16 accumulators), u walked in chunks of 16 through two
+// shared-memory tiles; reads `noise` (after the joint-limit clamp: the clamp is why this is not folded into L).
+// Not a shipped configuration (the reference constructs use_projection_ = false, PolicyImprovement.cpp:57): built for
+// completeness and correctness, sized so that it never dominates (2 x the sampler's flops).
+// grid (ceil(G D / 32), ceil(T / 64), Q), 128 threads.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+project_noise_dmma_kernel(const __grid_constant__ LoopParams p)
+{
+    constexpr int BM = 32, BN = 64, BK = 16;
+    __shared__ double As[BM][BK + 2];        // As[c][u]; the + 2 keeps the four k-slots of a fragment on different banks
+    __shared__ double Bs[BK][BN + 2];        // Bs[u][t] = M[t0 + t][u0 + u]
+    const int q = blockIdx.z;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D;
+    const int ncols = p.num_gen * D;
+    const int c0 = blockIdx.x * BM, t0 = blockIdx.y * BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = lane >> 2, kq = lane & 3;
+    const double* nz = p.noise + (size_t)q * p.slots * D * T;      // rows c of [slots * D][T]; generated rows come first
+    double acc[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = 0.0; acc[nt][1] = 0.0; }
+    for (int u0 = 0; u0 < T; u0 += BK) {
+        for (int e = tid; e < BM * BK; e += 128) {
+            const int c = e / BK, u = e - c * BK;
+            As[c][u] = (c0 + c < ncols && u0 + u < T) ? nz[(size_t)(c0 + c) * T + u0 + u] : 0.0;
+        }
+        for (int e = tid; e < BK * BN; e += 128) {
+            const int t = e / BK, u = e - t * BK;           // consecutive threads walk u: M rows are contiguous in u
+            Bs[u][t] = (t0 + t < T && u0 + u < T) ? p.Mproj[(size_t)(t0 + t) * T + u0 + u] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < BK / 4; ++j) {
+            const double a = As[warp * 8 + r][4 * j + kq];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], a, Bs[4 * j + kq][8 * nt + r]);
+        }
+        __syncthreads();
+    }
+    const int c = c0 + warp * 8 + r;
+    if (c < ncols) {
+        const int k = c / D, d = c - k * D;
+        const size_t row = (((size_t)q * p.slots + k) * D + d) * T;
+        const double* th = p.theta_all + ((size_t)q * D + d) * p.N + kPad;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = t0 + 8 * nt + 2 * kq + h;
+                if (t < T) {
+                    p.noise_proj[row + t] = acc[nt][h];
+                    if (p.proj) p.proj[row + t] = th[t] + acc[nt][h];
+                }
+            }
+    }
+}
+
 // injected unit noise (parity mode): epilogue only
 __global__ void __launch_bounds__(256)
 shift_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ JointLimits robot)
@@ -768,7 +840,7 @@ control_rows_kernel(const __grid_constant__ LoopParams p)
     const int row = blockIdx.x * kRowWarps + warp;
     if (row < p.num_gen * D && !(p.debug_skip & 2)) {      // warp-uniform
         const int k = row / D, d = row - k * D;
-        const double* nz = p.noise + (((size_t)q * p.slots + k) * D + d) * T;
+        const double* nz = p.rows_noise + (((size_t)q * p.slots + k) * D + d) * T;
         const double* th = p.theta_all + ((size_t)q * D + d) * N;
         double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
         const double dtw = p.dt * p.control_cost_weight;
@@ -861,9 +933,11 @@ control_rows_kernel(const __grid_constant__ LoopParams p)
         quad = warp_sum(quad);
         if (lane == 0) {
             double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
-            srow[1 + d] = C_part;
-            if (p.c_compact) p.c_compact[((size_t)q * D + d) * p.gslots + (p.gen_offset + k)] = C_part;
-            srow[1 + 2 * D + d] = quad;
+            if (p.rows_mask & 1) {
+                srow[1 + d] = C_part;
+                if (p.c_compact) p.c_compact[((size_t)q * D + d) * p.gslots + (p.gen_offset + k)] = C_part;
+            }
+            if (p.rows_mask & 2) srow[1 + 2 * D + d] = quad;
         }
     }
     tls.end();
@@ -911,7 +985,7 @@ control_rows_fast_kernel(const __grid_constant__ LoopParams p)
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row < p.num_gen * D && !(p.debug_skip & 2)) {      // warp-uniform
         const int k = row / D, d = row - k * D;
-        const double* nz = p.noise + (((size_t)q * p.slots + k) * D + d) * T;
+        const double* nz = p.rows_noise + (((size_t)q * p.slots + k) * D + d) * T;
         const double* th = p.theta_all + ((size_t)q * D + d) * N;
         double* cc_out = p.control_costs ? p.control_costs + (((size_t)q * p.slots + k) * D + d) * T : nullptr;
         const double dtw = p.dt * p.control_cost_weight;
@@ -974,9 +1048,11 @@ control_rows_fast_kernel(const __grid_constant__ LoopParams p)
         quad = warp_sum(quad);
         if (lane == 0) {
             double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
-            srow[1 + d] = C_part;
-            if (p.c_compact) p.c_compact[((size_t)q * D + d) * p.gslots + (p.gen_offset + k)] = C_part;
-            srow[1 + 2 * D + d] = quad;
+            if (p.rows_mask & 1) {
+                srow[1 + d] = C_part;
+                if (p.c_compact) p.c_compact[((size_t)q * D + d) * p.gslots + (p.gen_offset + k)] = C_part;
+            }
+            if (p.rows_mask & 2) srow[1 + 2 * D + d] = quad;
         }
     }
     tls.end();
@@ -1017,7 +1093,7 @@ control_rows_tile_kernel(const __grid_constant__ LoopParams p)
 
     if (c0 < nrows && !(p.debug_skip & 2)) {
         // ---- stage: rows c0 .. c0+7 are contiguous in `noise` ----
-        const double* src = p.noise + ((size_t)q * p.slots * D + c0) * T;
+        const double* src = p.rows_noise + ((size_t)q * p.slots * D + c0) * T;
         // cp.async (16 bytes, zero-filled outside the row): all ~24 copies of a lane are in flight at once.  As a
         // load-then-store loop the compiler kept one load in flight per lane and the stage alone cost 24 L2 round trips,
         // ~6 us of a tile's ~10 us (profiles/r1u: long-scoreboard stalls on the eight STS.128).
@@ -1111,9 +1187,11 @@ control_rows_tile_kernel(const __grid_constant__ LoopParams p)
         C_part += __shfl_xor_sync(0xffffffffu, C_part, 2); quad += __shfl_xor_sync(0xffffffffu, quad, 2);
         if (live && kq == 0) {
             double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
-            srow[1 + d] = C_part;
-            if (p.c_compact) p.c_compact[((size_t)q * D + d) * p.gslots + (p.gen_offset + k)] = C_part;
-            srow[1 + 2 * D + d] = p.use_noise_adaptation ? quad : 0.0;
+            if (p.rows_mask & 1) {
+                srow[1 + d] = C_part;
+                if (p.c_compact) p.c_compact[((size_t)q * D + d) * p.gslots + (p.gen_offset + k)] = C_part;
+            }
+            if (p.rows_mask & 2) srow[1 + 2 * D + d] = p.use_noise_adaptation ? quad : 0.0;
         }
     }
     tls.end();
@@ -1130,7 +1208,7 @@ fold_control_costs_kernel(const __grid_constant__ LoopParams p)
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= p.num_gen * D) return;
     const int k = row / D, d = row - k * D;
-    const double* nz = p.noise + (((size_t)q * p.slots + k) * D + d) * T;
+    const double* nz = p.rows_noise + (((size_t)q * p.slots + k) * D + d) * T;
     const double* th = p.theta_all + ((size_t)q * D + d) * N;
     double* cc = p.control_costs + (((size_t)q * p.slots + k) * D + d) * T;
     auto xall = [&](int j) { return (j >= kPad && j < kPad + T) ? th[j] + nz[j - kPad] : th[j]; };
@@ -1195,6 +1273,7 @@ __device__ __forceinline__ void materialise_noiseless(const LoopParams& p, int q
         const size_t o = (((size_t)q * p.slots + k) * D) * T + e;
         p.rollouts[o] = th;
         p.noise[o] = 0.0;
+        if (p.noise_proj) p.noise_proj[o] = 0.0;
         if (p.proj) p.proj[o] = th;
         if (p.control_costs) p.control_costs[o] = p.nl_control[(size_t)q * D * T + e];
     }
@@ -1354,10 +1433,12 @@ reused_control_cost_kernel(const __grid_constant__ LoopParams p, int first, int 
     const RowCoefficients rc = load_row_coefficients(p);
     for (int task = blockIdx.x * nwarps + warp; task < count * D; task += gridDim.x * nwarps) {
         const int r = task / D, d = task - r * D, k = first + r;
+        // control costs see parameters_ + noise_projected_ (PolicyImprovement.cpp:812-817), the quadratic form noise_
+        const double* cc_noise = p.noise_proj ? p.noise_proj : p.noise;
         for (int i = lane; i < N; i += 32) {
             const double th = p.theta_all[((size_t)q * D + d) * N + i];
             double v = th;
-            if (i >= kPad && i < kPad + T) v = th + p.noise[(((size_t)q * p.slots + k) * D + d) * T + (i - kPad)];
+            if (i >= kPad && i < kPad + T) v = th + cc_noise[(((size_t)q * p.slots + k) * D + d) * T + (i - kPad)];
             x[i] = v;
         }
         for (int t = lane; t < T; t += 32) stc[t] = p.state_costs[((size_t)q * p.slots + k) * T + t];
@@ -1369,7 +1450,14 @@ reused_control_cost_kernel(const __grid_constant__ LoopParams p, int first, int 
         for (int t = lane; t < T; t += 32) s += stc[t];
         s = warp_sum(s);
         double quad = 0.0;
-        if (p.use_noise_adaptation) quad = noise_quadratic_form(p, rc, x, p.theta_all + ((size_t)q * D + d) * N, lane);
+        if (p.use_noise_adaptation) {
+            if (p.noise_proj) {      // x held parameters + M * noise: rebuild it with the unprojected noise
+                __syncwarp();
+                for (int t = lane; t < T; t += 32)
+                    x[kPad + t] = p.theta_all[((size_t)q * D + d) * N + kPad + t] + p.noise[(((size_t)q * p.slots + k) * D + d) * T + t];
+            }
+            quad = noise_quadratic_form(p, rc, x, p.theta_all + ((size_t)q * D + d) * N, lane);
+        }
         if (lane == 0) {
             double* o = p.sums + ((size_t)q * p.gslots + k) * p.sumw;
             o[0] = s;
@@ -1419,11 +1507,20 @@ reuse_rollouts_kernel(const __grid_constant__ LoopParams p, const __grid_constan
         const int rd = e / T;
         const int d = rd % D, r = rd / D;
         const int src = order[r], dst = rp.gen + r;
-        const double pj = rp.src_proj[(((size_t)q * p.slots + src) * D + d) * T + t];
-        const double th = p.theta_all[((size_t)q * D + d) * N + kPad + t];
-        const double nz = pj - th;
+        const double* pjrow = rp.src_proj + (((size_t)q * p.slots + src) * D + d) * T;
+        const double* throw_ = p.theta_all + ((size_t)q * D + d) * N + kPad;
+        const double pj = pjrow[t];
+        const double th = throw_[t];
+        double nz = pj - th;                 // noise_projected_ = parameters_noise_projected_ - parameters_ (:201-203)
         const size_t o = (((size_t)q * p.slots + dst) * D + d) * T + t;
         p.proj[o] = pj;
+        if (p.Minv) {                        // noise_ = inv_projection_matrix_ * noise_projected_ (:204)
+            p.noise_proj[o] = nz;
+            const double* mi = p.Minv + (size_t)t * T;
+            double acc = 0.0;
+            for (int j = 0; j < T; ++j) acc += mi[j] * (pjrow[j] - throw_[j]);
+            nz = acc;
+        }
         p.noise[o] = nz;
         p.rollouts[o] = th + nz;
     }
@@ -1758,20 +1855,33 @@ pertimestep_update_kernel(const __grid_constant__ LoopParams p)      // grid (ce
     if (query_frozen(p, q)) return;
     const int T = p.T, D = p.D, n = p.num_local;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const double mn = p.pt_minden[((size_t)q * D + d) * 2], den = p.pt_minden[((size_t)q * D + d) * 2 + 1];
+    double mn = p.pt_minden[((size_t)q * D + d) * 2], den = p.pt_minden[((size_t)q * D + d) * 2 + 1];
     const double h = p.cost_scaling_h;
     double* upd = p.updbuf + ((size_t)q * D + d) * (T + 2);
     if (t < T) {
-        auto weight = [&](int k) {
-            const double c = 1.0 * (p.state_costs[((size_t)q * p.slots + k) * T + t] + p.control_costs[(((size_t)q * p.slots + k) * D + d) * T + t]);
-            return 1.0 * exp(((-h) * (c - mn)) / den);      // importance_weight_ = 1
+        auto cost_of = [&](int k) {
+            return 1.0 * (p.state_costs[((size_t)q * p.slots + k) * T + t] + p.control_costs[(((size_t)q * p.slots + k) * D + d) * T + t]);
         };
+        if (p.per_timestep_minmax) {     // min / max over the rollouts of THIS time step (the variant at PolicyImprovement.cpp:518-528)
+            double lo = cost_of(0), hi = lo;
+            for (int k = 1; k < n; ++k) { const double c = cost_of(k); lo = fmin(lo, c); hi = fmax(hi, c); }
+            mn = lo;
+            den = hi - lo;
+            if (den < 1e-8) den = 1e-8;
+        }
+        // the unnormalised weights are parked in pt_prob (one exp per rollout), normalised in the second walk
+        double* pt = p.pt_prob + (((size_t)q * p.gslots) * D + d) * T + t;
+        const size_t pt_stride = (size_t)D * T;
         double psum = 0.0;
-        for (int k = 0; k < n; ++k) psum += weight(k);
+        for (int k = 0; k < n; ++k) {
+            const double w = 1.0 * exp(((-h) * (cost_of(k) - mn)) / den);      // importance_weight_ = 1
+            pt[(size_t)k * pt_stride] = w;
+            psum += w;
+        }
         double u = 0.0;
         for (int k = 0; k < n; ++k) {
-            const double pr = weight(k) / psum;
-            p.pt_prob[(((size_t)q * p.gslots + k) * D + d) * T + t] = pr;
+            const double pr = pt[(size_t)k * pt_stride] / psum;
+            pt[(size_t)k * pt_stride] = pr;
             u += p.noise[(((size_t)q * p.slots + k) * D + d) * T + t] * pr;     // the noise-less slot carries zero noise
         }
         upd[t] = u;
@@ -1834,13 +1944,33 @@ __device__ __forceinline__ void apply_update_body(const LoopParams& p, int q, in
     // also what the read-backs of the probabilities divide by
     const double psum = (from_partials == 2) ? s_cols[T + 1] : 1.0;
     if (from_partials == 2 && threadIdx.x == 0) p.wpart[((size_t)q * D + d) * p.wblocks_cap] = psum;
-    for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
-        double u = s_cols[t];
-        if (from_partials == 2) u = u / psum;
-        if (t < T) {
-            // time-step weights and divisor are exactly 1 (PolicyImprovement.cpp:533,684-704)
+    if (p.Mproj) {
+        // parameter_updates_.row(0) = projection_matrix_ * row(0) (PolicyImprovement.cpp:706): normalise the row in
+        // place first (the branch below then sees the finished row), every thread then forms its own dot product
+        __syncthreads();
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+            double u = s_cols[t];
+            if (from_partials == 2) u = u / psum;
             u *= 1.0;
             u /= 1.0;
+            s_cols[t] = u;
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < T + 1; t += blockDim.x) {
+        double u = s_cols[t];
+        if (from_partials == 2 && !(p.Mproj && t < T)) u = u / psum;
+        if (t < T) {
+            if (p.Mproj) {
+                const double* mrow = p.Mproj + (size_t)t * T;
+                double acc = 0.0;
+                for (int j = 0; j < T; ++j) acc += mrow[j] * s_cols[j];
+                u = acc;
+            } else {
+                // time-step weights and divisor are exactly 1 (PolicyImprovement.cpp:533,684-704)
+                u *= 1.0;
+                u /= 1.0;
+            }
             p.updates[((size_t)q * D + d) * T + t] = u;
             p.theta_all[((size_t)q * D + d) * N + kPad + t] += 1.0 * u;
         } else if (p.use_noise_adaptation) {

@@ -509,3 +509,115 @@ def test_largest_robot():
         o.iterate(it, noise=unit)
         cost, valid, _ = e.iterate(it, noise=unit[None])
         _compare_iteration(o, e, cost, valid)
+
+
+def _projection_pair(pb, min_r=None, max_r=None, per_it=None, **okw):
+    K = pb.num_rollouts
+    min_r, max_r, per_it = min_r or K, max_r or K, per_it or K
+    T, D = pb.num_time_steps, pb.chain.num_dimensions
+    o = Oracle(num_time_steps=T, num_dimensions=D, min_rollouts=min_r, max_rollouts=max_r,
+               num_rollouts_per_iteration=per_it, noise_stddev=pb.noise_stddev, **okw)
+    o.set_problem(pb)
+    pol = o.policy()
+    e = binding.engine_for_problem(pb, min_rollouts=min_r, max_rollouts=max_r, per_iteration=per_it, policy=pol,
+                                   keep_debug_tensors=True, **okw)
+    return o, e, pol
+
+
+@pytest.mark.parametrize("T", [20, 100, 150])
+def test_m_matrix_projection(T):
+    """PolicyImprovement::use_projection_ (PolicyImprovement.cpp:421-440,706,750-801): noise_projected_ = M * noise_ feeds the
+    control costs, the update row is multiplied by M.  The oracle's branch is pinned against the reference's own code
+    (tests/test_reference_pin.py); here the CUDA path against the oracle.  T = 150 leaves ragged tiles in the DMMA
+    projection kernel (64-wide time tiles, 32-column tiles with K * D = 63)."""
+    pb = P.single_arm_problem(K=9, T=T, sdf_n=64)
+    D, K = pb.chain.num_dimensions, pb.num_rollouts
+    o, e, pol = _projection_pair(pb, use_projection=True)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(40 + T)
+    for it in range(4):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((K, D, T)))
+        if it == 1:
+            unit *= 6.0          # clamped samples: the projection sees the noise AFTER the joint-limit filter
+        o.iterate(it, noise=unit)
+        cost, valid, _ = e.iterate(it, noise=unit[None])
+        ref = o.field("noise_projected")
+        assert not np.allclose(ref, o.field("noise"))          # M really is not the identity
+        np.testing.assert_allclose(e.tensor("noise_projected")[0], ref, rtol=RTOL, atol=1e-13 * abs(ref).max())
+        _compare_iteration(o, e, cost, valid)
+    # without the switch the same inputs give another trajectory
+    o2, e2, _ = _projection_pair(pb)
+    o2.begin_solve(); o2.iterate(0, noise=unit)
+    assert not np.allclose(o2.parameters(), o.parameters())
+
+
+def test_m_matrix_projection_with_rollout_reuse(small_problem):
+    """Reused rollouts under projection: noise_ = M^-1 (parameters_noise_projected_ - parameters_) (PolicyImprovement.cpp:
+    201-204), shipped yml rollout counts."""
+    pb = small_problem
+    T, D = pb.num_time_steps, pb.chain.num_dimensions
+    o, e, pol = _projection_pair(pb, 5, 50, 10, use_projection=True)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(17)
+    for it in range(7):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((10, D, T)))
+        o.iterate(it, noise=unit)
+        cost, valid, _ = e.iterate(it, noise=unit[None])
+        n, g = o.num_rollouts()
+        ref = o.field("noise_projected")
+        np.testing.assert_allclose(e.tensor("noise_projected")[0], ref, rtol=1e-8, atol=1e-11 * abs(ref).max())
+        np.testing.assert_allclose(e.tensor("rollouts_projected")[0], o.field("parameters_noise_projected"), rtol=1e-8, atol=1e-11)
+        # M^-1 is ill conditioned (M ~ R^-1): the reused rollouts' noise_ carries that into everything downstream, so the
+        # whole-iteration comparison of this case is held to 1e-6 of the tensor scale, not 1e-9
+        np.testing.assert_allclose(e.tensor("noise")[0], o.field("noise"), rtol=1e-6, atol=1e-6 * abs(o.field("noise")).max())
+        np.testing.assert_array_equal(e.tensor("verdicts")[0].astype(bool), o.field("state_costs") > 0.5)
+        np.testing.assert_allclose(e.tensor("total_cost")[0], o.field("total_cost"), rtol=1e-6)
+        np.testing.assert_allclose(e.tensor("parameters")[0], o.parameters(), rtol=1e-6, atol=1e-9)
+    assert e.num_rollouts()[0] == 51
+
+
+def test_per_timestep_minmax_variant():
+    """The min / max variant the reference keeps commented out (PolicyImprovement.cpp:518-528), in per-time-step cost mode
+    (in cumulative mode it coincides with the shipped rule): min and max over the rollouts of each time step."""
+    pb = P.single_arm_problem(K=24, T=40, sdf_n=64)
+    T, D, K = pb.num_time_steps, pb.chain.num_dimensions, pb.num_rollouts
+    o, e, pol = _projection_pair(pb, use_cumulative_costs=False, per_timestep_minmax=True)
+    o_plain, _, _ = _projection_pair(pb, use_cumulative_costs=False)
+    o.begin_solve(); e.begin_solve(); o_plain.begin_solve()
+    rng = np.random.default_rng(23)
+    for it in range(3):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((K, D, T)))
+        o.iterate(it, noise=unit)
+        cost, valid, _ = e.iterate(it, noise=unit[None])
+        np.testing.assert_allclose(e.tensor("probabilities")[0], o.field("probabilities"), rtol=RTOL, atol=1e-300)
+        np.testing.assert_allclose(e.tensor("updates")[0], o.updates(), rtol=RTOL, atol=1e-13)
+        np.testing.assert_allclose(e.tensor("parameters")[0], o.parameters(), rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(e.tensor("stddevs")[0], o.stddevs(), rtol=RTOL)
+        np.testing.assert_allclose(cost[0], o.noiseless()["total_cost"], rtol=RTOL)
+    o_plain.iterate(0, noise=unit)
+    assert not np.allclose(o_plain.parameters(), o.parameters())      # the variant is a different rule
+    # in cumulative mode the switch changes nothing (cumulative_costs_ is constant over t)
+    o3, e3, pol3 = _projection_pair(pb, per_timestep_minmax=True)
+    o3.begin_solve(); e3.begin_solve()
+    for it in range(2):
+        unit = np.einsum("tu,kdu->kdt", pol3["L"], rng.standard_normal((K, D, T)))
+        o3.iterate(it, noise=unit)
+        cost, valid, _ = e3.iterate(it, noise=unit[None])
+        _compare_iteration(o3, e3, cost, valid)
+
+
+def test_projection_in_per_timestep_mode():
+    pb = P.single_arm_problem(K=12, T=40, sdf_n=64)
+    T, D, K = pb.num_time_steps, pb.chain.num_dimensions, pb.num_rollouts
+    o, e, pol = _projection_pair(pb, use_cumulative_costs=False, use_projection=True)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(29)
+    for it in range(3):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((K, D, T)))
+        o.iterate(it, noise=unit)
+        cost, valid, _ = e.iterate(it, noise=unit[None])
+        _assert_control_costs(e.tensor("control_costs")[0], o.field("control_costs"))
+        np.testing.assert_allclose(e.tensor("probabilities")[0], o.field("probabilities"), rtol=RTOL, atol=1e-300)
+        np.testing.assert_allclose(e.tensor("updates")[0], o.updates(), rtol=RTOL, atol=1e-13)
+        np.testing.assert_allclose(e.tensor("parameters")[0], o.parameters(), rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(cost[0], o.noiseless()["total_cost"], rtol=RTOL)
