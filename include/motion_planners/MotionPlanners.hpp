@@ -34,6 +34,9 @@ public:
 private:
     bool checkStartState(const base::samples::Joints& current_robot_status, PlannerStatus& planner_status);
     bool checkGoalState(const base::samples::Joints& goal, PlannerStatus& planner_status);
+    bool checkNaN(const base::samples::Joints& joint_value) const;
+    bool selectPlanningGroupJoints(const base::samples::Joints& given, const char* what, base::samples::Joints& out,
+                                   bool& within_limits) const;
     Config config_;
     std::shared_ptr<robot_model::RobotModel> robot_model_;
     base::samples::Joints initial_joint_status_, goal_joint_status_;

@@ -63,7 +63,9 @@ public:
     // ---- what the CUDA path consumes -------------------------------------------------------------
     const std::vector<urdf::Joint>& chain() const { return chain_; }
     const std::vector<CollisionSphere>& spheres() const { return spheres_; }
-    const SignedDistanceField& sdf() const { return sdf_; }
+    // host copy of the distance field, for inspection: (re)built on the host when the scene changed since.  The engines
+    // never read it — they build their field on the device from the same scene (configureScene)
+    const SignedDistanceField& sdf();
     const std::vector<Obstacle>& obstacles() const { return obstacles_; }
     // programmatic setup (instead of files)
     void setChain(const std::vector<urdf::Joint>& chain, const std::string& base_link, const std::string& tip_link);
@@ -73,12 +75,25 @@ public:
     void disableCollisions(const std::string& link1, const std::string& link2);
     void setSelfCollision(bool on) { config_.self_collision = on; }
     std::vector<std::pair<int, int> > selfCollisionPairs() const;
-    void addObstacle(const Obstacle& o) { obstacles_.push_back(o); sdf_dirty_ = true; }
+    // ---- the scene: world objects of the reference (MotionPlanners::handleCollisionObjectInWorld / updateOctomap,
+    // src/MotionPlanners.cpp:162-173,416-460) as what the distance field is built from.  Every change bumps the scene
+    // revision; engines compare it with the revision they were configured at and rebuild their field (on the device)
+    // before the next query / solve, so a change takes effect immediately, as in the reference.
+    void addObstacle(const Obstacle& o) { obstacles_.push_back(o); sceneChanged(); }
+    bool removeObstacle(const std::string& name);
+    void clearObstacles() { obstacles_.clear(); sceneChanged(); }
+    // occupancy world [nz][ny][nx] (a voxelised mesh, or an octomap's leaves at the grid's resolution): the field is then
+    // its exact Euclidean distance transform; primitives present at the same time are voxelised into it
+    void setOccupancy(const int dims[3], const double origin[3], double voxel, const std::vector<unsigned char>& occupied);
+    void clearOccupancy() { occupancy_.clear(); sceneChanged(); }
     void setSdfGrid(int resolution, const double lower[3], const double upper[3]);
-    void setSdf(const SignedDistanceField& sdf);
-    bool buildSdf();   // exact signed distance of the obstacle union at the voxel centres (one-time, host)
-    // push chain / spheres / SDF into an engine (used by the planner and by isStateValid)
+    void setSdf(const SignedDistanceField& sdf);   // an explicit field (wins over obstacles / occupancy until the scene changes)
+    bool buildSdf();   // host statement of the primitive field (same formulas as the device builder); fills sdf()
+    unsigned long sceneRevision() const { return scene_revision_; }
+    // push chain / spheres / self-collision pairs / scene into an engine (used by the planner and by isStateValid)
     int configureEngine(stomp_b200_engine* engine) const;
+    // the scene alone: distance field built on the device (primitives: exact union distance; occupancy: exact EDT)
+    int configureScene(stomp_b200_engine* engine) const;
     int device() const { return config_.device; }
 
 private:
@@ -87,6 +102,8 @@ private:
     bool loadSrdf(const std::string& path);
     bool loadEnvironment(const std::string& path);
     bool ensureValidityEngine();
+    void sceneChanged() { sdf_dirty_ = true; sdf_explicit_ = false; ++scene_revision_; }
+    void gridGeometry(int dims[3], double origin[3], double& voxel) const;
 
     RobotModelConfig config_;
     std::string world_frame_, base_link_, tip_link_;
@@ -98,6 +115,12 @@ private:
     int sdf_resolution_ = 64;
     double sdf_lower_[3] = {-1.5, -1.5, -1.5}, sdf_upper_[3] = {1.5, 1.5, 1.5};
     bool sdf_dirty_ = true;
+    bool sdf_explicit_ = false;             // sdf_ was handed in by setSdf and is what the engines get
+    unsigned long scene_revision_ = 1;
+    unsigned long validity_revision_ = 0;   // scene revision validity_engine_ was configured at
+    std::vector<unsigned char> occupancy_;  // [nz][ny][nx], empty: primitive world
+    int occ_dims_[3] = {0, 0, 0};
+    double occ_origin_[3] = {0, 0, 0}, occ_voxel_ = 0;
     std::vector<double> joint_state_;
     stomp_b200_engine* validity_engine_ = nullptr;
 };

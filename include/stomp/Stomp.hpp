@@ -32,6 +32,10 @@ public:
     bool runSingleIteration(int iteration_number);
     // num_iterations iterations queued on the device without host round trips; frozen at the wrapper's stop rule
     bool runIterations(int first_iteration, int num_iterations, bool honour_stop, int& iterations_used);
+    // the whole solve loop on the device (stomp_b200_solve): up to max_iterations iterations, stop rule honoured on the
+    // device, then the policy is synchronised back; pathFound() / getNoiselessRolloutTotalCost() / iterationsUsed() hold
+    // the outcome
+    bool solveOnDevice(int max_iterations, int& iterations_used);
     void getAllRollouts(std::vector<Rollout>& rollouts);
     double getNoiselessRolloutTotalCost() { return noiseless_total_cost_; }
     bool getLastNoiselessRolloutValid() const { return last_noiseless_rollout_valid_; }

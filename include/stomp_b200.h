@@ -178,6 +178,14 @@ int32_t stomp_b200_next_num_generated(const stomp_b200_engine* e);
  * reference.  Returns after the last kernel finished. */
 int stomp_b200_run(stomp_b200_engine* e, int32_t first_iteration, int32_t num_iterations, int32_t honour_stop);
 
+/* The whole iteration loop of StompPlanner::solve (StompPlanner.cpp:96-141) on the device: up to max_iterations
+ * iterations with the on-device sampler and the stop rule honoured per query (a stopped query is frozen exactly where
+ * the reference's `break` leaves it: parameters, noise-less cost, iteration count).  The host looks at the stop flags
+ * every poll_every iterations (<= 0: 8) — one pinned read-back and one synchronisation — and stops queueing once every
+ * query has stopped; iterations queued past a query's stop are no-ops for it.  iterations_run (may be NULL) =
+ * iterations queued; the per-query counts come from stomp_b200_finish_solve. */
+int stomp_b200_solve(stomp_b200_engine* e, int32_t max_iterations, int32_t poll_every, int32_t* iterations_run);
+
 /* Stomp::setCostCumulation (stomp/src/Stomp.cpp:356-359): 1 = costs summed over the trajectory (the default), 0 = costs
  * and probabilities per time step (PolicyImprovement.cpp:473-481).  0 is built for one GPU without rollout reuse, else
  * STOMP_B200_ERR_UNSUPPORTED.  Also settable at creation (stomp_b200_config::use_cumulative_costs). */

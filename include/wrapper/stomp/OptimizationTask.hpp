@@ -56,6 +56,7 @@ private:
     std::vector<double> lower_limits_, upper_limits_;
     ConstraintPlanning constraints_;
     stomp_b200_engine* engine_ = nullptr;
+    unsigned long scene_revision_ = 0;    // robot_model_->sceneRevision() the engine's distance field was built at
 };
 
 }  // namespace motion_planners

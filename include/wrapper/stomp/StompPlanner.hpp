@@ -31,6 +31,8 @@ public:
     const stomp::StompConfig& getStompConfig() const { return stomp_config_; }
 
 private:
+    bool solveWithDumps(PlannerStatus& planner_status, bool& path_found);   // host-driven loop with the per-iteration debug files
+    void fillSolution(base::JointsTrajectory& solution) const;
     boost::shared_ptr<stomp::Stomp> stomp_;
     stomp::StompConfig stomp_config_;
     stomp::DebugConfig debug_config_;

@@ -32,7 +32,7 @@ SYMBOLS = [
     "stomp_b200_create", "stomp_b200_destroy", "stomp_b200_set_chain", "stomp_b200_set_spheres", "stomp_b200_set_sdf",
     "stomp_b200_set_control_cost_matrices", "stomp_b200_set_policy", "stomp_b200_host_policy",
     "stomp_b200_host_initial_trajectory", "stomp_b200_begin_solve", "stomp_b200_iterate",
-    "stomp_b200_next_num_generated", "stomp_b200_run", "stomp_b200_finish_solve", "stomp_b200_num_rollouts",
+    "stomp_b200_next_num_generated", "stomp_b200_run", "stomp_b200_solve", "stomp_b200_finish_solve", "stomp_b200_num_rollouts",
     "stomp_b200_get_tensor", "stomp_b200_evaluate_states", "stomp_b200_sphere_centres", "stomp_b200_comm_unique_id",
     "stomp_b200_comm_init", "stomp_b200_set_profiling", "stomp_b200_kernel_stats", "stomp_b200_reset_kernel_stats",
     "stomp_b200_set_timeline", "stomp_b200_get_timeline", "stomp_b200_launch_count", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
@@ -107,6 +107,7 @@ def lib():
         L.stomp_b200_next_num_generated.argtypes = [vp]
         L.stomp_b200_next_num_generated.restype = C.c_int32
         L.stomp_b200_run.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+        L.stomp_b200_solve.argtypes = [vp, C.c_int32, C.c_int32, ip]
         L.stomp_b200_finish_solve.argtypes = [vp, dp, ip, ip, dp]
         L.stomp_b200_num_rollouts.argtypes = [vp, ip, ip]
         L.stomp_b200_get_tensor.argtypes = [vp, C.c_int32, vp, C.c_size_t]
@@ -348,6 +349,13 @@ class Engine:
 
     def run(self, first_iteration, num_iterations, honour_stop=False):
         self._check(lib().stomp_b200_run(self.h, first_iteration, num_iterations, int(honour_stop)), "stomp_b200_run")
+
+    def solve(self, max_iterations, poll_every=0):
+        """The StompPlanner::solve loop on the device (stop rule honoured, stop flags polled every `poll_every` iterations);
+        returns the iterations queued."""
+        n = C.c_int32(0)
+        self._check(lib().stomp_b200_solve(self.h, int(max_iterations), int(poll_every), C.byref(n)), "stomp_b200_solve")
+        return n.value
 
     def finish_solve(self):
         sol = np.empty((self.Q, self.D, self.T))

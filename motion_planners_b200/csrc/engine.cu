@@ -19,6 +19,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <limits>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -101,6 +102,7 @@ struct stomp_b200_engine {
     cudaStream_t stream = nullptr;
     std::string last_error;
     std::vector<void*> allocations;
+    std::set<const void*> smem_opted_in;   // kernels whose dynamic shared-memory limit was raised on this engine's device
 
     RobotParams robot;
     JointLimits limits;             // robot.lower / upper, for the sampling kernels
@@ -147,6 +149,9 @@ struct stomp_b200_engine {
     // pinned host mirrors of the per-query scalars
     double* h_cost = nullptr; uint8_t* h_valid = nullptr; int32_t* h_stop = nullptr; int32_t* h_iters = nullptr;
     double* h_impr = nullptr;
+    unsigned char* h_scalars = nullptr;      // the pinned block the five mirrors above point into
+    unsigned char* d_scalars = nullptr;      // its device counterpart (LoopParams nl_total / last_improvement / stop / iters_used / nl_valid)
+    size_t scalar_bytes = 0;
 
     // measurement
     bool profiling = false;
@@ -162,6 +167,10 @@ struct stomp_b200_engine {
     long long timeline_count = 0;
 
     ncclComm_t comm = nullptr;
+
+    // grow-only scratch of stomp_b200_evaluate_states
+    double* eval_theta = nullptr; double* eval_cost = nullptr; uint8_t* eval_verdict = nullptr; uint8_t* eval_valid = nullptr;
+    size_t eval_cap_theta = 0, eval_cap_states = 0, eval_cap_traj = 0;
 };
 constexpr int kTimelineRing = 64;
 
@@ -280,10 +289,11 @@ size_t dmma_smem_bytes(int T)
 template <int kTiles, bool kPhilox>
 int launch_sample_dmma_t(stomp_b200_engine* e, const LoopParams& lp)
 {
-    static bool configured = false;      // per instantiation
-    if (!configured) {
+    // the attribute is per device: remembered per engine (one engine = one device), not per process
+    const void* fn = (const void*)sample_rollouts_dmma_kernel<kTiles, kPhilox>;
+    if (!e->smem_opted_in.count(fn)) {
         CUDA_TRY(e, cudaFuncSetAttribute(sample_rollouts_dmma_kernel<kTiles, kPhilox>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        configured = true;
+        e->smem_opted_in.insert(fn);
     }
     const long long total_cols = (long long)lp.Q * lp.num_gen * lp.D;
     const int ntiles = (int)((total_cols + 7) / 8);
@@ -333,14 +343,14 @@ bool launch_rows_tile_g(stomp_b200_engine* e, const LoopParams& lp, int rows, cu
 {
     const size_t smem = sizeof(double) * (size_t)kTileWarps * 8 * tile_noise_stride(kGroups);
     const dim3 grid((rows + kTileWarps * 8 - 1) / (kTileWarps * 8), lp.Q);
-    static bool configured = false;       // per instantiation
-    if (!configured) {
+    const void* fn = (const void*)control_rows_tile_kernel<kGroups, false>;      // per engine = per device
+    if (!e->smem_opted_in.count(fn)) {
         if (cudaFuncSetAttribute(control_rows_tile_kernel<kGroups, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(control_rows_tile_kernel<kGroups, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
             (void)cudaGetLastError();
             return false;
         }
-        configured = true;
+        e->smem_opted_in.insert(fn);
     }
     if (smem > 200 * 1024) return false;
     // (Capping this grid's residency so that it shares every SM with the state kernel was tried — 32 KB of shared memory
@@ -368,9 +378,14 @@ codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
 {
     codegen::StateKernelOptions opt;
     opt.wide_index = e->sdf.wide_index != 0;
-    opt.magic_floor = codegen::magic_floor_is_safe(e->robot, e->sdf);
+    // The two bounds below hold for ANY value of a revolute joint, but only inside the limits of a prismatic one — and the
+    // noise-less rollout (policy parameters) and stomp_b200_evaluate_states (caller's values) are not clamped to the limits:
+    // chains with a prismatic joint keep the index clamps and the saturating conversion.
+    bool has_prismatic = false;
+    for (int d = 0; d < e->robot.num_joints; ++d) has_prismatic = has_prismatic || e->robot.joint[d].prismatic != 0;
+    opt.magic_floor = !has_prismatic && codegen::magic_floor_is_safe(e->robot, e->sdf);
     if (const char* f = std::getenv("STOMP_B200_STATES_FLOOR")) opt.magic_floor = opt.magic_floor && std::strcmp(f, "cvt") != 0;
-    opt.inside_grid = codegen::reach_is_inside_grid(e->robot, e->sdf);
+    opt.inside_grid = !has_prismatic && codegen::reach_is_inside_grid(e->robot, e->sdf);
     if (const char* c = std::getenv("STOMP_B200_STATES_CLAMP")) opt.inside_grid = opt.inside_grid && std::atoi(c) == 0;
     if (const char* b = std::getenv("STOMP_B200_STATES_MIN_BLOCKS")) opt.min_blocks = std::atoi(b);   // tuning knobs
     if (const char* l = std::getenv("STOMP_B200_STATES_LAG")) opt.compare_lag = std::max(0, std::atoi(l));
@@ -693,11 +708,8 @@ int fetch_query_scalars(stomp_b200_engine* e)
 {
     const LoopParams& b = e->base;
     if (int rc = join_side_stream(e)) return rc;
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_cost, b.nl_total, sizeof(double) * e->Q, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_valid, b.nl_valid, e->Q, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_stop, b.stop, sizeof(int32_t) * e->Q, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_iters, b.iters_used, sizeof(int32_t) * e->Q, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_impr, b.last_improvement, sizeof(double) * e->Q, cudaMemcpyDeviceToHost, e->stream));
+    (void)b;
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_scalars, e->d_scalars, e->scalar_bytes, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     resolve_profile(e);
     return 0;
@@ -832,7 +844,9 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     b.use_noise_adaptation = cfg->use_noise_adaptation;
     b.seed = cfg->seed;
     b.noiseless_slot = -1;
+#ifdef STOMP_B200_DEBUG_KNOBS      // measurement builds only: lets the cost kernels skip their work
     if (const char* dbg = std::getenv("STOMP_B200_DEBUG_SKIP")) b.debug_skip = std::atoi(dbg);
+#endif
 
     double* tmp = nullptr;
     CREATE_TRY(dev_alloc(e, &b.theta_all, Q * D * N));
@@ -876,13 +890,21 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.nl_verdict, Q * T));
     CREATE_TRY(dev_alloc(e, &b.nl_control, Q * D * T));
     CREATE_TRY(dev_alloc(e, &b.nl_sums, Q * e->sumw));
-    CREATE_TRY(dev_alloc(e, &b.nl_total, Q));
-    CREATE_TRY(dev_alloc(e, &b.nl_valid, Q));
+    {
+        // the per-query scalars the host reads back live in ONE device block, mirrored by one pinned block: a single
+        // D2H copy per read-back.  Layout: [Q] nl_total | [Q] last_improvement | [Q] stop | [Q] iters_used | [Q] nl_valid
+        e->scalar_bytes = Q * (2 * sizeof(double) + 2 * sizeof(int32_t) + 1);
+        unsigned char* blk = nullptr;
+        CREATE_TRY(dev_alloc(e, &blk, e->scalar_bytes + 16));
+        e->d_scalars = blk;
+        b.nl_total = reinterpret_cast<double*>(blk);
+        b.last_improvement = b.nl_total + Q;
+        b.stop = reinterpret_cast<int32_t*>(b.last_improvement + Q);
+        b.iters_used = b.stop + Q;
+        b.nl_valid = reinterpret_cast<uint8_t*>(b.iters_used + Q);
+    }
     CREATE_TRY(dev_alloc(e, &b.old_cost, Q));
-    CREATE_TRY(dev_alloc(e, &b.last_improvement, Q));
     CREATE_TRY(dev_alloc(e, &b.best_cost, Q));
-    CREATE_TRY(dev_alloc(e, &b.stop, Q));
-    CREATE_TRY(dev_alloc(e, &b.iters_used, Q));
     CREATE_TRY(dev_alloc(e, &e->d_order, Q * S));
     b.chunk = 128;
     e->max_chunks = (int)((S + b.chunk - 1) / b.chunk);
@@ -926,11 +948,12 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
         CREATE_TRY(dev_alloc(e, &tmp, T * (2 * kRBand + 1))); b.Rband = tmp;
         CREATE_CUDA(cudaStreamSynchronize(e->stream));
     }
-    CREATE_CUDA(cudaMallocHost(&e->h_cost, sizeof(double) * Q));
-    CREATE_CUDA(cudaMallocHost(&e->h_impr, sizeof(double) * Q));
-    CREATE_CUDA(cudaMallocHost(&e->h_valid, Q));
-    CREATE_CUDA(cudaMallocHost(&e->h_stop, sizeof(int32_t) * Q));
-    CREATE_CUDA(cudaMallocHost(&e->h_iters, sizeof(int32_t) * Q));
+    CREATE_CUDA(cudaMallocHost(&e->h_scalars, e->scalar_bytes + 16));
+    e->h_cost = reinterpret_cast<double*>(e->h_scalars);
+    e->h_impr = e->h_cost + Q;
+    e->h_stop = reinterpret_cast<int32_t*>(e->h_impr + Q);
+    e->h_iters = e->h_stop + Q;
+    e->h_valid = reinterpret_cast<uint8_t*>(e->h_iters + Q);
     {
         cudaDeviceProp prop;
         CREATE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
@@ -962,11 +985,11 @@ int stomp_b200_destroy(stomp_b200_engine* e)
     for (void* p : e->allocations) cudaFree(p);
     if (e->d_sdf) cudaFree(e->d_sdf);
     for (void* p : e->self_pair_buffers) cudaFree(p);
-    if (e->h_cost) cudaFreeHost(e->h_cost);
-    if (e->h_impr) cudaFreeHost(e->h_impr);
-    if (e->h_valid) cudaFreeHost(e->h_valid);
-    if (e->h_stop) cudaFreeHost(e->h_stop);
-    if (e->h_iters) cudaFreeHost(e->h_iters);
+    if (e->eval_theta) cudaFree(e->eval_theta);
+    if (e->eval_cost) cudaFree(e->eval_cost);
+    if (e->eval_verdict) cudaFree(e->eval_verdict);
+    if (e->eval_valid) cudaFree(e->eval_valid);
+    if (e->h_scalars) cudaFreeHost(e->h_scalars);
     if (e->timer_a) cudaEventDestroy(e->timer_a);
     if (e->timer_b) cudaEventDestroy(e->timer_b);
     if (e->ev_applied) cudaEventDestroy(e->ev_applied);
@@ -1340,6 +1363,13 @@ int stomp_b200_set_policy(stomp_b200_engine* e, int32_t query, const double* par
 {
     if (!e || !parameters_all || !min_control_cost) return STOMP_B200_ERR_INVALID_ARGUMENT;
     if (query < 0 || query >= e->Q) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "query index out of range");
+    // NaN / infinite / absurd joint values never reach the kernels (the reference rejects NaN in checkNaN,
+    // src/MotionPlanners.cpp:563-571); 1e6 rad or m is far beyond any joint and far below where the deterministic
+    // sin / cos reduction stops being exact
+    for (size_t i = 0; i < (size_t)e->D * e->N; ++i)
+        if (!(std::fabs(parameters_all[i]) <= 1e6)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "parameters_all holds a NaN, an infinity or a value beyond 1e6");
+    for (size_t i = 0; i < (size_t)e->D * e->T; ++i)
+        if (!(std::fabs(min_control_cost[i]) <= 1e6)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "min_control_cost holds a NaN, an infinity or a value beyond 1e6");
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     CUDA_TRY(e, cudaMemcpy(e->base.theta_all + (size_t)query * e->D * e->N, parameters_all, sizeof(double) * e->D * e->N, cudaMemcpyHostToDevice));
@@ -1439,6 +1469,27 @@ int stomp_b200_run(stomp_b200_engine* e, int32_t first_iteration, int32_t num_it
     if (int rc = join_side_stream(e)) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     resolve_profile(e);
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_solve(stomp_b200_engine* e, int32_t max_iterations, int32_t poll_every, int32_t* iterations_run)
+{
+    if (!e || max_iterations < 0) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (!e->solving) return fail(e, STOMP_B200_ERR_NOT_READY, "stomp_b200_begin_solve first");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (poll_every <= 0) poll_every = 8;
+    int done = 0;
+    while (done < max_iterations) {
+        const int n = std::min(poll_every, max_iterations - done);
+        for (int i = 0; i < n; ++i)
+            if (int rc = iterate_async(e, done + i, kNoisePhilox, 1)) return rc;
+        done += n;
+        if (int rc = fetch_query_scalars(e)) return rc;     // one pinned block, one synchronisation per poll
+        bool all_stopped = true;
+        for (int q = 0; q < e->Q && all_stopped; ++q) all_stopped = e->h_stop[q] != 0;
+        if (all_stopped) break;
+    }
+    if (iterations_run) *iterations_run = done;
     return STOMP_B200_OK;
 }
 
@@ -1577,6 +1628,35 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
     }
 }
 
+// grow-only device scratch of stomp_b200_evaluate_states (the start / goal validity path calls it per query)
+static int eval_scratch(stomp_b200_engine* e, size_t states, size_t trajectories)
+{
+    if (states * e->D > e->eval_cap_theta) {
+        if (e->eval_theta) cudaFree(e->eval_theta);
+        e->eval_theta = nullptr; e->eval_cap_theta = 0;
+        const size_t cap = std::max<size_t>(states * e->D, 1024);
+        CUDA_TRY(e, cudaMalloc(&e->eval_theta, sizeof(double) * cap));
+        e->eval_cap_theta = cap;
+    }
+    if (states > e->eval_cap_states) {
+        if (e->eval_cost) cudaFree(e->eval_cost);
+        if (e->eval_verdict) cudaFree(e->eval_verdict);
+        e->eval_cost = nullptr; e->eval_verdict = nullptr; e->eval_cap_states = 0;
+        const size_t cap = std::max<size_t>(states, 1024);
+        CUDA_TRY(e, cudaMalloc(&e->eval_cost, sizeof(double) * cap));
+        CUDA_TRY(e, cudaMalloc(&e->eval_verdict, cap));
+        e->eval_cap_states = cap;
+    }
+    if (trajectories > e->eval_cap_traj) {
+        if (e->eval_valid) cudaFree(e->eval_valid);
+        e->eval_valid = nullptr; e->eval_cap_traj = 0;
+        const size_t cap = std::max<size_t>(trajectories, 256);
+        CUDA_TRY(e, cudaMalloc(&e->eval_valid, cap));
+        e->eval_cap_traj = cap;
+    }
+    return 0;
+}
+
 int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_t num_trajectories, int32_t num_steps,
                                double* state_costs, uint8_t* verdicts, uint8_t* validity)
 {
@@ -1584,38 +1664,40 @@ int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_
     if (!e->have_chain || !e->have_spheres || !e->have_sdf) return fail(e, STOMP_B200_ERR_NOT_READY, "chain, spheres and SDF must be set first");
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     const size_t states = (size_t)num_trajectories * num_steps;
-    if (e->self_pairs.n > 0 && states > (size_t)0x7fffff00) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "too many states for one call with self collision on");
-    double* d_theta = nullptr; double* d_cost = nullptr; uint8_t* d_verdict = nullptr; uint8_t* d_valid = nullptr;
-    int rc = STOMP_B200_OK;
-    auto cleanup = [&]() { cudaFree(d_theta); cudaFree(d_cost); cudaFree(d_verdict); cudaFree(d_valid); };
-#define EVAL_TRY(call) do { cudaError_t _err = (call); if (_err != cudaSuccess) { e->last_error = std::string(#call) + ": " + cudaGetErrorString(_err); cleanup(); return STOMP_B200_ERR_CUDA; } } while (0)
-    EVAL_TRY(cudaMalloc(&d_theta, sizeof(double) * states * e->D));
-    EVAL_TRY(cudaMalloc(&d_cost, sizeof(double) * states));
-    EVAL_TRY(cudaMalloc(&d_verdict, states));
-    EVAL_TRY(cudaMalloc(&d_valid, num_trajectories));
-    EVAL_TRY(cudaMemcpyAsync(d_theta, theta, sizeof(double) * states * e->D, cudaMemcpyHostToDevice, e->stream));
+    if (states > (size_t)0x7fffff00) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "too many states for one call");
+    if (int rc = eval_scratch(e, states, (size_t)num_trajectories)) return rc;
+    double* d_theta = e->eval_theta; double* d_cost = e->eval_cost; uint8_t* d_verdict = e->eval_verdict; uint8_t* d_valid = e->eval_valid;
+    // the run-time specialised kernel drops index clamps it can prove redundant for sane joint values; values it cannot
+    // vouch for (NaN, infinities, |q| > 1e6) go through the generic kernel, which clamps and converts with saturation
+    bool sane = true;
+    for (size_t i = 0; i < states * e->D && sane; ++i) sane = std::fabs(theta[i]) <= 1e6;
+    CUDA_TRY(e, cudaMemcpyAsync(d_theta, theta, sizeof(double) * states * e->D, cudaMemcpyHostToDevice, e->stream));
     {
         Scope sc(e, STOMP_B200_KERNEL_COST);
+        resolve_state_kernel(e);
+        StateKernelArgs a;
+        a.rollouts = d_theta; a.state_costs = d_cost; a.verdicts = d_verdict; a.validity = d_valid;
+        a.sums = nullptr; a.s_compact = nullptr; a.stop = nullptr; a.tile_counter = nullptr; a.timeline = nullptr;
+        a.T = num_steps; a.D = e->D; a.slots = num_trajectories; a.gslots = 1; a.sumw = 1; a.num_gen = num_trajectories;
+        a.gen_offset = 0; a.honour_stop = 0; a.debug_skip = 0;
+        a.row_stride = num_steps; a.rollout_stride = (int64_t)e->D * num_steps;
         if (e->self_pairs.n > 0) {
-            StateKernelArgs a;
-            a.rollouts = d_theta; a.state_costs = d_cost; a.verdicts = d_verdict; a.validity = d_valid;
-            a.sums = nullptr; a.s_compact = nullptr; a.stop = nullptr; a.tile_counter = nullptr; a.timeline = nullptr;
-            a.T = num_steps; a.D = e->D; a.slots = num_trajectories; a.gslots = 1; a.sumw = 1; a.num_gen = num_trajectories;
-            a.gen_offset = 0; a.honour_stop = 0; a.debug_skip = 0;
-            a.row_stride = num_steps; a.rollout_stride = (int64_t)e->D * num_steps;
             launch_states_self_collision(e, a, dim3((unsigned)((states + 127) / 128), 1), e->stream);
-        } else
-        evaluate_states_kernel<<<(unsigned)((states + 127) / 128), 128, 0, e->stream>>>(e->robot, e->sdf, d_theta, num_trajectories, num_steps, d_cost, d_verdict, d_valid);
+        } else if (e->spec && sane) {
+            void* args[] = {&a, &e->robot, &e->sdf};
+            const int bt = e->spec->block_threads;
+            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((unsigned)((states + bt - 1) / bt), 1), dim3(bt), args, 0, e->stream));
+        } else {
+            evaluate_states_kernel<<<(unsigned)((states + 127) / 128), 128, 0, e->stream>>>(e->robot, e->sdf, d_theta, num_trajectories, num_steps, d_cost, d_verdict, d_valid);
+        }
     }
-    EVAL_TRY(cudaGetLastError());
-    if (state_costs) EVAL_TRY(cudaMemcpyAsync(state_costs, d_cost, sizeof(double) * states, cudaMemcpyDeviceToHost, e->stream));
-    if (verdicts) EVAL_TRY(cudaMemcpyAsync(verdicts, d_verdict, states, cudaMemcpyDeviceToHost, e->stream));
-    if (validity) EVAL_TRY(cudaMemcpyAsync(validity, d_valid, num_trajectories, cudaMemcpyDeviceToHost, e->stream));
-    EVAL_TRY(cudaStreamSynchronize(e->stream));
-#undef EVAL_TRY
-    cleanup();
+    if (int rc = check_launch(e, "evaluate_states")) return rc;
+    if (state_costs) CUDA_TRY(e, cudaMemcpyAsync(state_costs, d_cost, sizeof(double) * states, cudaMemcpyDeviceToHost, e->stream));
+    if (verdicts) CUDA_TRY(e, cudaMemcpyAsync(verdicts, d_verdict, states, cudaMemcpyDeviceToHost, e->stream));
+    if (validity) CUDA_TRY(e, cudaMemcpyAsync(validity, d_valid, num_trajectories, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     resolve_profile(e);
-    return rc;
+    return STOMP_B200_OK;
 }
 
 int stomp_b200_sphere_centres(stomp_b200_engine* e, const double* q, int32_t n, double* centres)

@@ -3,6 +3,8 @@
 #include <motion_planners/MotionPlanners.hpp>
 
 #include <chrono>
+#include <cmath>
+#include <stdexcept>
 
 namespace motion_planners {
 
@@ -28,11 +30,59 @@ bool MotionPlanners::initialize(PlannerStatus& planner_status)
 bool MotionPlanners::reInitializePlanner() { return planner_ && planner_->reInitializePlanner(); }
 bool MotionPlanners::reInitializePlanner(const int& num_time_steps) { return planner_ && planner_->reInitializeTimeSteps(num_time_steps); }
 
-// reference :91-128: the start state must be collision free
+// reference :563-571
+bool MotionPlanners::checkNaN(const base::samples::Joints& joint_value) const
+{
+    for (size_t i = 0; i < joint_value.elements.size(); i++)
+        if (std::isnan(joint_value.elements.at(i).position)) return false;
+    return true;
+}
+
+// Picks the planning-group joints out of `given` BY NAME, in the planning group's order (reference :108-125,196-211): a
+// full-robot joint state, or the same joints in another order, gives the same request.  Beyond the reference: a value
+// outside the joint's limits is refused here — the planner clamps every sample to the limits (OptimizationTask::filter),
+// so such a start / goal can never be the end of a sampled trajectory.
+bool MotionPlanners::selectPlanningGroupJoints(const base::samples::Joints& given, const char* what, base::samples::Joints& out,
+                                               bool& within_limits) const
+{
+    std::vector<std::pair<std::string, urdf::Joint> > group;
+    if (!robot_model_->getPlanningGroupJointInformation(robot_model_->getPlanningGroupName(), group)) return false;
+    out.clear();
+    out.resize(group.size());
+    within_limits = true;
+    for (size_t i = 0; i < group.size(); i++) {
+        try {
+            out.names.at(i) = group.at(i).first;
+            out.elements.at(i) = given.getElementByName(group.at(i).first);
+        } catch (const std::exception&) {
+            LOG_ERROR_S << "[MotionPlanners]: Joint " << group.at(i).first << " is given in planning group but is not available in the given " << what << " value";
+            return false;
+        }
+        const double q = out.elements.at(i).position;
+        const urdf::Joint& j = group.at(i).second;
+        if (j.type != urdf::Joint::CONTINUOUS && (q < j.lower || q > j.upper)) {
+            LOG_ERROR_S << "[MotionPlanners]: " << what << " value " << q << " of joint " << group.at(i).first << " is outside its limits [" << j.lower << ", " << j.upper << "]";
+            within_limits = false;
+        }
+    }
+    return true;
+}
+
+// reference :91-128: no NaN, collision free, then the start taken joint by joint by name
 bool MotionPlanners::checkStartState(const base::samples::Joints& current_robot_status, PlannerStatus& planner_status)
 {
-    if (current_robot_status.empty()) {
+    if (current_robot_status.empty() || !checkNaN(current_robot_status)) {
         planner_status.statuscode = PlannerStatus::START_JOINTANGLES_NOT_AVAILABLE;
+        return false;
+    }
+    base::samples::Joints start;
+    bool within_limits = true;
+    if (!selectPlanningGroupJoints(current_robot_status, "start", start, within_limits)) {
+        planner_status.statuscode = PlannerStatus::START_JOINTANGLES_NOT_AVAILABLE;
+        return false;
+    }
+    if (!within_limits) {
+        planner_status.statuscode = PlannerStatus::INVALID_START_STATE;
         return false;
     }
     double collision_cost = 0.0;
@@ -41,14 +91,14 @@ bool MotionPlanners::checkStartState(const base::samples::Joints& current_robot_
         planner_status.statuscode = PlannerStatus::START_STATE_IN_COLLISION;
         return false;
     }
-    initial_joint_status_ = current_robot_status;
+    initial_joint_status_ = start;
     return true;
 }
 
 // reference :130-160
 bool MotionPlanners::checkGoalState(const base::samples::Joints& goal, PlannerStatus& planner_status)
 {
-    if (goal.empty()) {
+    if (goal.empty() || !checkNaN(goal)) {
         planner_status.statuscode = PlannerStatus::GOAL_JOINTANGLES_NOT_AVAILABLE;
         return false;
     }
@@ -58,16 +108,36 @@ bool MotionPlanners::checkGoalState(const base::samples::Joints& goal, PlannerSt
         planner_status.statuscode = PlannerStatus::GOAL_STATE_IN_COLLISION;
         return false;
     }
-    goal_joint_status_ = goal;
+    planner_status.statuscode = PlannerStatus::PLANNING_REQUEST_SUCCESS;
     return true;
 }
 
-// reference :188-219 (joint-space target)
+// reference :188-219 (joint-space target): the goal is assembled by name before it is checked
 bool MotionPlanners::assignPlanningRequest(const base::samples::Joints& start_jointvalues, const base::samples::Joints& target_jointvalues,
                                            PlannerStatus& planner_status)
 {
     if (!checkStartState(start_jointvalues, planner_status)) return false;
-    if (!checkGoalState(target_jointvalues, planner_status)) return false;
+    if (target_jointvalues.empty()) {
+        planner_status.statuscode = PlannerStatus::GOAL_JOINTANGLES_NOT_AVAILABLE;
+        return false;
+    }
+    base::samples::Joints goal;
+    bool within_limits = true;
+    if (!selectPlanningGroupJoints(target_jointvalues, "target", goal, within_limits)) {
+        planner_status.statuscode = PlannerStatus::GOAL_JOINTANGLES_NOT_AVAILABLE;
+        return false;
+    }
+    if (!checkNaN(goal)) {
+        planner_status.statuscode = PlannerStatus::GOAL_JOINTANGLES_NOT_AVAILABLE;
+        return false;
+    }
+    if (!within_limits) {
+        planner_status.statuscode = PlannerStatus::INVALID_GOAL_STATE;
+        return false;
+    }
+    if (!checkGoalState(goal, planner_status)) return false;
+    goal_joint_status_ = goal;
+    constrainted_target_.use_constraint = motion_planners::NO_CONSTRAINT;
     planner_status.statuscode = PlannerStatus::PLANNING_REQUEST_SUCCESS;
     return true;
 }

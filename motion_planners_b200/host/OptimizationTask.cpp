@@ -96,7 +96,19 @@ void OptimizationTask::updatePolicy()
 
 stomp_b200_engine* OptimizationTask::engine()
 {
-    if (engine_) return engine_;
+    if (engine_) {
+        // a world object added / removed / moved since the engine was configured (reference: handleCollisionObjectInWorld,
+        // updateOctomap take effect at once): rebuild the distance field on the device before the next use
+        if (scene_revision_ != robot_model_->sceneRevision()) {
+            const int rc = robot_model_->configureScene(engine_);
+            if (rc) {
+                LOG_ERROR_S << "[OptimizationTask]: " << stomp_b200_status_string(rc) << ": " << stomp_b200_last_error(engine_);
+                return nullptr;
+            }
+            scene_revision_ = robot_model_->sceneRevision();
+        }
+        return engine_;
+    }
     stomp_b200_config cfg;
     stomp_b200_default_config(&cfg);
     cfg.num_time_steps = stomp_config_.num_time_steps_;
@@ -126,7 +138,9 @@ stomp_b200_engine* OptimizationTask::engine()
         LOG_ERROR_S << "[OptimizationTask]: " << stomp_b200_status_string(rc) << ": " << stomp_b200_last_error(engine_);
         stomp_b200_destroy(engine_);
         engine_ = nullptr;
+        return nullptr;
     }
+    scene_revision_ = robot_model_->sceneRevision();
     return engine_;
 }
 

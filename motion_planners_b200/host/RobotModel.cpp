@@ -68,18 +68,16 @@ void parse_triplet(const std::string& text, double out[3])
 
 struct UrdfLinkGeometry { bool has = false; int kind = 0; double size[3] = {0, 0, 0}; double origin[3] = {0, 0, 0}; };
 
+// signed distance to one primitive: the formulas of the device builder (csrc/sdf_builder.cuh), operation for operation
 double obstacle_distance(const Obstacle& o, double x, double y, double z)
 {
-    const double d[3] = {x - o.centre[0], y - o.centre[1], z - o.centre[2]};
-    if (o.kind == 0) return std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) - o.size[0];
-    double q[3], outside = 0.0, inside = -1e300;
-    for (int i = 0; i < 3; ++i) {
-        q[i] = std::fabs(d[i]) - o.size[i];
-        const double m = std::max(q[i], 0.0);
-        outside += m * m;
-        inside = std::max(inside, q[i]);
-    }
-    return std::sqrt(outside) + std::min(inside, 0.0);
+    const double dx = x - o.centre[0], dy = y - o.centre[1], dz = z - o.centre[2];
+    if (o.kind == 0) return std::sqrt((dx * dx + dy * dy) + dz * dz) - o.size[0];
+    const double qx = std::fabs(dx) - o.size[0], qy = std::fabs(dy) - o.size[1], qz = std::fabs(dz) - o.size[2];
+    const double ox = std::fmax(qx, 0.0), oy = std::fmax(qy, 0.0), oz = std::fmax(qz, 0.0);
+    const double outside = std::sqrt((ox * ox + oy * oy) + oz * oz);
+    const double inside = std::fmin(std::fmax(std::fmax(qx, qy), qz), 0.0);
+    return outside + inside;
 }
 
 }  // namespace
@@ -99,7 +97,7 @@ bool RobotModel::initialization()
     if (config_.self_collision && !config_.srdf_file.empty() && !loadSrdf(config_.srdf_file)) return false;
     if (!config_.environment_file.empty() && !loadEnvironment(config_.environment_file)) return false;
     if (spheres_.empty()) { LOG_ERROR_S << "[RobotModel]: no collision spheres"; return false; }
-    if (sdf_dirty_ && !buildSdf()) return false;
+    // the distance field itself is built on the device when an engine is configured (configureScene)
     joint_state_.assign(chain_.size(), 0.0);
     return true;
 }
@@ -199,7 +197,7 @@ bool RobotModel::loadUrdf(const std::string& path)
         o.name = j.child_link_name;
         for (int i = 0; i < 3; ++i) { o.centre[i] = j.origin_xyz[i] + it->second.origin[i]; o.size[i] = it->second.size[i]; }
         obstacles_.push_back(o);
-        sdf_dirty_ = true;
+        sceneChanged();
     }
     return !chain_.empty();
 }
@@ -331,37 +329,70 @@ void RobotModel::setSdfGrid(int resolution, const double lower[3], const double 
     sdf_resolution_ = resolution;
     std::copy(lower, lower + 3, sdf_lower_);
     std::copy(upper, upper + 3, sdf_upper_);
-    sdf_dirty_ = true;
+    sceneChanged();
 }
 
 void RobotModel::setSdf(const SignedDistanceField& sdf)
 {
     sdf_ = sdf;
     sdf_dirty_ = false;
+    sdf_explicit_ = true;
+    ++scene_revision_;
+}
+
+bool RobotModel::removeObstacle(const std::string& name)
+{
+    for (size_t i = 0; i < obstacles_.size(); ++i)
+        if (obstacles_[i].name == name) {
+            obstacles_.erase(obstacles_.begin() + i);
+            sceneChanged();
+            return true;
+        }
+    return false;
+}
+
+void RobotModel::setOccupancy(const int dims[3], const double origin[3], double voxel, const std::vector<unsigned char>& occupied)
+{
+    std::copy(dims, dims + 3, occ_dims_);
+    std::copy(origin, origin + 3, occ_origin_);
+    occ_voxel_ = voxel;
+    occupancy_ = occupied;
+    sceneChanged();
+}
+
+// cubic voxels sized by the x extent of the configured box
+void RobotModel::gridGeometry(int dims[3], double origin[3], double& voxel) const
+{
+    const int n = std::max(2, sdf_resolution_);
+    voxel = (sdf_upper_[0] - sdf_lower_[0]) / n;
+    for (int i = 0; i < 3; ++i) {
+        origin[i] = sdf_lower_[i];
+        dims[i] = std::max(1, (int)std::lround((sdf_upper_[i] - sdf_lower_[i]) / voxel));
+    }
 }
 
 bool RobotModel::buildSdf()
 {
-    const int n = sdf_resolution_;
-    if (n < 2) return false;
-    // cubic voxels sized by the x extent (the synthetic scenes are cubes)
-    const double h = (sdf_upper_[0] - sdf_lower_[0]) / n;
-    sdf_.voxel = h;
-    for (int i = 0; i < 3; ++i) {
-        sdf_.origin[i] = sdf_lower_[i];
-        sdf_.dims[i] = std::max(1, (int)std::lround((sdf_upper_[i] - sdf_lower_[i]) / h));
-    }
-    sdf_.grid.assign((size_t)sdf_.dims[0] * sdf_.dims[1] * sdf_.dims[2], 1e30f);
+    if (sdf_resolution_ < 2) return false;
+    gridGeometry(sdf_.dims, sdf_.origin, sdf_.voxel);
+    const double h = sdf_.voxel;
+    sdf_.grid.assign((size_t)sdf_.dims[0] * sdf_.dims[1] * sdf_.dims[2], 0.0f);
     for (int z = 0; z < sdf_.dims[2]; ++z)
         for (int y = 0; y < sdf_.dims[1]; ++y)
             for (int x = 0; x < sdf_.dims[0]; ++x) {
-                const double px = sdf_.origin[0] + (x + 0.5) * h, py = sdf_.origin[1] + (y + 0.5) * h, pz = sdf_.origin[2] + (z + 0.5) * h;
-                double d = 1e30;
-                for (const auto& o : obstacles_) d = std::min(d, obstacle_distance(o, px, py, pz));
+                const double px = sdf_.origin[0] + ((double)x + 0.5) * h, py = sdf_.origin[1] + ((double)y + 0.5) * h, pz = sdf_.origin[2] + ((double)z + 0.5) * h;
+                double d = INFINITY;
+                for (const auto& o : obstacles_) d = std::fmin(d, obstacle_distance(o, px, py, pz));
                 sdf_.grid[((size_t)z * sdf_.dims[1] + y) * sdf_.dims[0] + x] = (float)d;
             }
     sdf_dirty_ = false;
     return true;
+}
+
+const SignedDistanceField& RobotModel::sdf()
+{
+    if (sdf_dirty_ && !sdf_explicit_) buildSdf();
+    return sdf_;
 }
 
 void RobotModel::getPlanningGroupJointsName(const std::string&, std::vector<std::string>& names) const
@@ -435,12 +466,51 @@ int RobotModel::configureEngine(stomp_b200_engine* engine) const
         rc = stomp_b200_set_self_collision(engine, (int32_t)pairs.size(), flat.data());
         if (rc) return rc;
     }
-    return stomp_b200_set_sdf(engine, sdf_.dims, sdf_.origin, sdf_.voxel, sdf_.grid.data());
+    return configureScene(engine);
+}
+
+int RobotModel::configureScene(stomp_b200_engine* engine) const
+{
+    if (sdf_explicit_) return stomp_b200_set_sdf(engine, sdf_.dims, sdf_.origin, sdf_.voxel, sdf_.grid.data());
+    if (!occupancy_.empty()) {
+        // primitives present next to an occupancy world are voxelised into it (centre of the voxel inside the primitive)
+        std::vector<unsigned char> occ = occupancy_;
+        if (!obstacles_.empty())
+            for (int z = 0; z < occ_dims_[2]; ++z)
+                for (int y = 0; y < occ_dims_[1]; ++y)
+                    for (int x = 0; x < occ_dims_[0]; ++x) {
+                        unsigned char& v = occ[((size_t)z * occ_dims_[1] + y) * occ_dims_[0] + x];
+                        if (v) continue;
+                        const double px = occ_origin_[0] + ((double)x + 0.5) * occ_voxel_, py = occ_origin_[1] + ((double)y + 0.5) * occ_voxel_,
+                                     pz = occ_origin_[2] + ((double)z + 0.5) * occ_voxel_;
+                        for (const auto& o : obstacles_)
+                            if (obstacle_distance(o, px, py, pz) < 0.0) { v = 1; break; }
+                    }
+        return stomp_b200_build_sdf_occupancy(engine, occ_dims_, occ_origin_, occ_voxel_, occ.data());
+    }
+    int dims[3];
+    double origin[3], voxel;
+    gridGeometry(dims, origin, voxel);
+    const int n = (int)obstacles_.size();
+    std::vector<int32_t> kind((size_t)std::max(n, 1));
+    std::vector<double> centre(3 * (size_t)std::max(n, 1)), size(3 * (size_t)std::max(n, 1));
+    for (int i = 0; i < n; ++i) {
+        kind[i] = obstacles_[i].kind;
+        for (int a = 0; a < 3; ++a) { centre[3 * i + a] = obstacles_[i].centre[a]; size[3 * i + a] = obstacles_[i].size[a]; }
+    }
+    return stomp_b200_build_sdf_primitives(engine, dims, origin, voxel, n, kind.data(), centre.data(), size.data());
 }
 
 bool RobotModel::ensureValidityEngine()
 {
-    if (validity_engine_) return true;
+    if (validity_engine_) {
+        if (validity_revision_ != scene_revision_) {      // the scene changed since: rebuild the field before answering
+            const int rc = configureScene(validity_engine_);
+            if (rc) { LOG_ERROR_S << "[RobotModel]: " << stomp_b200_last_error(validity_engine_); return false; }
+            validity_revision_ = scene_revision_;
+        }
+        return true;
+    }
     stomp_b200_config cfg;
     stomp_b200_default_config(&cfg);
     cfg.num_time_steps = 2;
@@ -451,6 +521,7 @@ bool RobotModel::ensureValidityEngine()
     if (rc) { LOG_ERROR_S << "[RobotModel]: stomp_b200_create failed: " << stomp_b200_status_string(rc); validity_engine_ = nullptr; return false; }
     rc = configureEngine(validity_engine_);
     if (rc) { LOG_ERROR_S << "[RobotModel]: " << stomp_b200_last_error(validity_engine_); return false; }
+    validity_revision_ = scene_revision_;
     return true;
 }
 

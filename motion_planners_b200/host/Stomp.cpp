@@ -75,6 +75,22 @@ bool Stomp::runIterations(int first_iteration, int num_iterations, bool honour_s
     return true;
 }
 
+// The loop of StompPlanner::solve (reference StompPlanner.cpp:96-141) queued on the device: no host round trip per
+// iteration; the stop rule (:117) is evaluated on the device after every noise-less rollout and freezes the query.
+bool Stomp::solveOnDevice(int max_iterations, int& iterations_used)
+{
+    if (!initialized_) return false;
+    int32_t queued = 0;
+    const int rc = stomp_b200_solve(engine_, max_iterations, 0, &queued);
+    if (rc) {
+        LOG_ERROR_S << "[Stomp]: " << stomp_b200_status_string(rc) << ": " << stomp_b200_last_error(engine_);
+        return false;
+    }
+    if (!syncPolicyFromDevice()) return false;
+    iterations_used = last_iterations_used_;
+    return true;
+}
+
 bool Stomp::syncPolicyFromDevice()
 {
     if (!initialized_) return false;

@@ -6,6 +6,7 @@
 #include <cassert>
 #include <cmath>
 #include <sstream>
+#include <string>
 
 namespace motion_planners {
 
@@ -62,6 +63,28 @@ bool StompPlanner::reInitializeTimeSteps(const int& num_time_steps)
     return reInitializePlanner();
 }
 
+// Writes the planner's current parameters_all_ (free part) into `solution` (reference StompPlanner.cpp:148-163).
+void StompPlanner::fillSolution(base::JointsTrajectory& solution) const
+{
+    const int first_free = stomp::DIFF_RULE_LENGTH - 1;
+    const size_t D = planning_group_joints_name_.size();
+    solution.names.resize(D);
+    solution.elements.resize(D);
+    for (int d = 0; d < stomp_config_.num_dimensions_; d++) {
+        solution.names.at(d) = planning_group_joints_name_.at(d);
+        solution.elements.at(d).resize(stomp_config_.num_time_steps_);
+        for (int t = 0; t < stomp_config_.num_time_steps_; t++)
+            solution.elements.at(d).at(t).position = optimization_task_->policy_->parameters_all_[d](t + first_free);
+    }
+}
+
+// reference StompPlanner.cpp:65-174.  Two drivers of the same device loop:
+//   * the production path queues the whole loop on the device (stomp::Stomp::solveOnDevice -> stomp_b200_solve): the stop
+//     rule of :117 is evaluated there after every noise-less rollout, the host only polls a flag every few iterations;
+//   * with the debug dumps of :122-141 switched on, the host needs the rollouts of every iteration, so it drives one
+//     iteration at a time (runSingleIteration) and applies the stop rule itself, as the reference does.
+// Both end with the LAST parameters as the solution and PATH_FOUND iff the last noise-less cost is below 1 and the last
+// improvement within min_cost_improvement (:165-173).
 bool StompPlanner::solve(base::JointsTrajectory& solution, PlannerStatus& planner_status)
 {
     optimization_task_->setOptimizationConstraints(constraints_);
@@ -71,89 +94,78 @@ bool StompPlanner::solve(base::JointsTrajectory& solution, PlannerStatus& planne
         stomp_.reset();
         return false;
     }
-
-    if ((debug_config_.save_noiseless_trajectories_) || (debug_config_.save_noisy_trajectories_)) mkdir(debug_config_.output_dir_.c_str(), 0755);
-    FILE* num_rollouts_file = NULL;
-    if (debug_config_.save_noisy_trajectories_) {
-        std::stringstream name;
-        name << debug_config_.output_dir_ << "/num_rollouts.txt";
-        num_rollouts_file = fopen(name.str().c_str(), "w");
-    }
-    if (debug_config_.save_noiseless_trajectories_) {
-        std::stringstream sss;
-        sss << debug_config_.output_dir_ << "/noiseless_0.txt";
-        optimization_task_->policy_->writeToFile(sss.str());
-    }
-    tmp_policy = *optimization_task_->policy_;
-
-    double old_cost = 0.0;
-    double cost_improvement = 0.0;
-    double current_trajectory_totalcost = 0.0;
     num_iterations_ = 0;
-
-    for (int i = 0; i < stomp_config_.num_iterations_; i++) {
-        num_iterations_++;
-        if (!stomp_->runSingleIteration(i)) {
+    const bool dumps = debug_config_.save_noiseless_trajectories_ || debug_config_.save_noisy_trajectories_;
+    bool path_found = false;
+    if (!dumps) {
+        int used = 0;
+        if (!stomp_->solveOnDevice(stomp_config_.num_iterations_, used)) {
             planner_status.statuscode = motion_planners::PlannerStatus::CRASH;
             stomp_.reset();
             return false;
         }
-        current_trajectory_totalcost = stomp_->getNoiselessRolloutTotalCost();
-        cost_improvement = current_trajectory_totalcost - old_cost;
-        old_cost = current_trajectory_totalcost;
-        LOG_DEBUG_S << "Iteration = " << i << ". Total Cost = " << current_trajectory_totalcost << " . Cost improvement = " << cost_improvement;
+        num_iterations_ = used;
+        path_found = stomp_->pathFound();
+        LOG_DEBUG_S << "Iterations = " << used << ". Total Cost = " << stomp_->getNoiselessRolloutTotalCost();
+        stomp_.reset();
+    } else {
+        if (!solveWithDumps(planner_status, path_found)) return false;
+    }
+    fillSolution(solution);
+    planner_status.statuscode = path_found ? motion_planners::PlannerStatus::PATH_FOUND : motion_planners::PlannerStatus::NO_PATH_FOUND;
+    return path_found;
+}
 
-        // Stop criterion: a total cost below 1 means no timestep is in collision (each costs 1)
-        if ((current_trajectory_totalcost < 1) && (fabs(cost_improvement) < stomp_config_.min_cost_improvement_)) break;
-
-        if (debug_config_.save_noisy_trajectories_ && num_rollouts_file) {
+// the host-driven loop, one device iteration per step, with the reference's per-iteration files
+// (noiseless_<i>.txt, noisy_<i>_<j>.txt, num_rollouts.txt; StompPlanner.cpp:79-93,122-141)
+bool StompPlanner::solveWithDumps(PlannerStatus& planner_status, bool& path_found)
+{
+    const std::string& dir = debug_config_.output_dir_;
+    mkdir(dir.c_str(), 0755);
+    FILE* counts = debug_config_.save_noisy_trajectories_ ? fopen((dir + "/num_rollouts.txt").c_str(), "w") : NULL;
+    if (debug_config_.save_noiseless_trajectories_) optimization_task_->policy_->writeToFile(dir + "/noiseless_0.txt");
+    tmp_policy = *optimization_task_->policy_;
+    double previous = 0.0, improvement = 0.0, cost = 0.0;
+    for (int it = 0; it < stomp_config_.num_iterations_; it++) {
+        num_iterations_++;
+        if (!stomp_->runSingleIteration(it)) {
+            planner_status.statuscode = motion_planners::PlannerStatus::CRASH;
+            if (counts) fclose(counts);
+            stomp_.reset();
+            return false;
+        }
+        cost = stomp_->getNoiselessRolloutTotalCost();
+        improvement = cost - previous;
+        previous = cost;
+        LOG_DEBUG_S << "Iteration = " << it << ". Total Cost = " << cost << " . Cost improvement = " << improvement;
+        // a total cost below 1 means no time step is in collision (each costs 1)
+        if ((cost < 1) && (fabs(improvement) < stomp_config_.min_cost_improvement_)) break;
+        if (counts) {
             std::vector<stomp::Rollout> rollouts;
             stomp_->getAllRollouts(rollouts);
-            fprintf(num_rollouts_file, "%d\n", int(rollouts.size()));
-            for (unsigned int j = 0; j < rollouts.size(); ++j) {
-                std::stringstream ss2;
-                ss2 << debug_config_.output_dir_ << "/noisy_" << i + 1 << "_" << j << ".txt";
+            fprintf(counts, "%d\n", int(rollouts.size()));
+            for (size_t j = 0; j < rollouts.size(); ++j) {
                 tmp_policy.setParameters(rollouts[j].parameters_noise_);
-                tmp_policy.writeToFile(ss2.str());
+                tmp_policy.writeToFile(dir + "/noisy_" + std::to_string(it + 1) + "_" + std::to_string(j) + ".txt");
             }
         }
         if (debug_config_.save_noiseless_trajectories_) {
-            // the parameters live on the device during the solve: fetch them for the dump
-            std::vector<base::VectorXd> p;
-            std::stringstream ss;
-            ss << debug_config_.output_dir_ << "/noiseless_" << i + 1 << ".txt";
-            if (stomp_->getParameters(p)) {
-                tmp_policy.setParameters(p);
-                tmp_policy.writeToFile(ss.str());
+            std::vector<base::VectorXd> current;      // the parameters live on the device during the solve
+            if (stomp_->getParameters(current)) {
+                tmp_policy.setParameters(current);
+                tmp_policy.writeToFile(dir + "/noiseless_" + std::to_string(it + 1) + ".txt");
             }
         }
     }
-    if (num_rollouts_file) fclose(num_rollouts_file);
-
-    // parameters_all_ <- device (the reference's policy object is updated in place by updateParameters)
-    const bool synced = stomp_->syncPolicyFromDevice();
+    if (counts) fclose(counts);
+    const bool synced = stomp_->syncPolicyFromDevice();     // parameters_all_ <- device
     stomp_.reset();
     if (!synced) {
         planner_status.statuscode = motion_planners::PlannerStatus::CRASH;
         return false;
     }
-
-    const int start = stomp::DIFF_RULE_LENGTH - 1;
-    solution.names.resize(planning_group_joints_name_.size());
-    solution.elements.resize(planning_group_joints_name_.size());
-    for (int d = 0; d < stomp_config_.num_dimensions_; d++) {
-        solution.names.at(d) = planning_group_joints_name_.at(d);
-        solution.elements.at(d).resize(stomp_config_.num_time_steps_);
-        for (int i = 0; i < stomp_config_.num_time_steps_; i++)
-            solution.elements.at(d).at(i).position = optimization_task_->policy_->parameters_all_[d](i + start);
-    }
-
-    if ((current_trajectory_totalcost < 1) && (fabs(cost_improvement) <= stomp_config_.min_cost_improvement_)) {
-        planner_status.statuscode = motion_planners::PlannerStatus::PATH_FOUND;
-        return true;
-    } else
-        planner_status.statuscode = motion_planners::PlannerStatus::NO_PATH_FOUND;
-    return false;
+    path_found = (cost < 1) && (fabs(improvement) <= stomp_config_.min_cost_improvement_);
+    return true;
 }
 
 void StompPlanner::setStartGoalTrajectory(const base::samples::Joints& start, const base::samples::Joints& goal)

@@ -59,8 +59,11 @@ def test_invalid_configurations_are_rejected_before_touching_the_device():
     cfg.num_time_steps, cfg.num_dimensions = 20, 40      # too many joints
     cfg.min_rollouts = cfg.max_rollouts = cfg.num_rollouts_per_iteration = 4
     assert L.stomp_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
-    cfg.num_dimensions, cfg.use_projection = 7, 1         # shipped-disabled switch, not built
+    cfg.num_dimensions, cfg.use_cumulative_costs = 7, 0   # per-time-step costs ...
+    cfg.min_rollouts, cfg.max_rollouts = 2, 8             # ... with rollout reuse: a combination that is not built
     assert L.stomp_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == binding.ERR_UNSUPPORTED
+    cfg.use_cumulative_costs, cfg.shard_mode = 1, 7       # no such sharding mode
+    assert L.stomp_b200_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert L.stomp_b200_status_string(-2).decode().startswith("no CUDA device")
 
 

@@ -621,3 +621,65 @@ def test_projection_in_per_timestep_mode():
         np.testing.assert_allclose(e.tensor("updates")[0], o.updates(), rtol=RTOL, atol=1e-13)
         np.testing.assert_allclose(e.tensor("parameters")[0], o.parameters(), rtol=RTOL, atol=1e-12)
         np.testing.assert_allclose(cost[0], o.noiseless()["total_cost"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("poll_every", [0, 1, 5])
+def test_device_solve_loop_equals_the_host_driven_loop(poll_every):
+    """stomp_b200_solve (the loop StompPlanner::solve queues on the device, stop rule evaluated there) against the
+    reference's control flow driven from the host: iterate, read the noise-less cost, break when it is below 1 and the
+    improvement below min_cost_improvement (StompPlanner.cpp:96-118).  Same iteration count, same final trajectory bit
+    for bit, whatever the polling period (iterations queued past the stop are no-ops)."""
+    pb = P.single_arm_problem(K=32, T=20, sdf_n=64)
+    a = binding.engine_for_problem(pb)
+    b = binding.engine_for_problem(pb)
+    a.begin_solve(); b.begin_solve()
+    old, used = 0.0, 0
+    for it in range(40):
+        cost, valid, stop = a.iterate(it)
+        used += 1
+        improvement = cost[0] - old
+        old = cost[0]
+        if cost[0] < 1 and abs(improvement) < a.cfg.min_cost_improvement:
+            assert bool(stop[0])
+            break
+        assert not bool(stop[0])
+    queued = b.solve(40, poll_every)
+    ra, rb = a.finish_solve(), b.finish_solve()
+    assert rb["iterations"][0] == used == ra["iterations"][0]
+    assert queued >= used and (poll_every != 1 or queued == used)
+    np.testing.assert_array_equal(ra["solution"], rb["solution"])
+    assert ra["cost"][0] == rb["cost"][0] and bool(ra["found"][0]) == bool(rb["found"][0])
+    assert used < 40 and rb["found"][0]
+
+
+def test_on_device_sampler_covariance():
+    """The Philox path's distribution (the parity tests inject their noise): standard normals with the right moments, and
+    unit noise L * eps whose sample covariance is R^-1 = L L^T — the covariance MultivariateGaussian is constructed with
+    (PolicyImprovement.cpp:95-99).  Normals are FP32 Box-Muller from 24-bit uniforms (|z| <= 5.9): documented in DESIGN.md."""
+    pb = P.single_arm_problem(K=4096, T=40, sdf_n=64)
+    e = binding.engine_for_problem(pb, keep_debug_tensors=True)
+    pol = e.policy
+    e.begin_solve()
+    eps_all, unit_all = [], []
+    for it in range(3):
+        e.iterate(it)
+        eps_all.append(e.tensor("epsilon")[0].reshape(-1, 40))
+        unit_all.append(e.tensor("unit_noise")[0].reshape(-1, 40))
+    z = np.concatenate(eps_all)                # [3 * 4096 * 7][40]
+    u = np.concatenate(unit_all)
+    n = z.shape[0]
+    assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.var() - 1) < 5 * np.sqrt(2 / z.size)
+    assert abs((z ** 3).mean()) < 5 * np.sqrt(15 / z.size) and abs((z ** 4).mean() - 3) < 5 * np.sqrt(96 / z.size)
+    assert 4.0 < np.abs(z).max() <= 5.95
+    # identity covariance of eps: every entry within 6 standard errors
+    ce = z.T @ z / n
+    assert np.abs(ce - np.eye(40)).max() < 6 / np.sqrt(n) * np.sqrt(2)
+    # covariance of the unit noise against R^-1, entry-wise within 6 standard errors sqrt((S_ii S_jj + S_ij^2) / n)
+    S = pol["L"] @ pol["L"].T
+    np.testing.assert_allclose(S, pol["Rinv"], rtol=1e-6, atol=1e-9 * np.abs(pol["Rinv"]).max())
+    cu = u.T @ u / n
+    se = np.sqrt((np.outer(np.diag(S), np.diag(S)) + S ** 2) / n)
+    assert (np.abs(cu - S) / se).max() < 6.0
+    # columns (rollout, joint) are independent draws: neighbouring columns are uncorrelated
+    r = np.corrcoef(z[:-1].ravel(), z[1:].ravel())[0, 1]
+    assert abs(r) < 5 / np.sqrt(z.size)

@@ -48,3 +48,20 @@ def test_test_motion_planners_finds_a_path():
     goal = [-1.5, -1.5, -1.5, 1.5, -1.5, -1.5, -0.5]
     assert max(abs(a - b) for a, b in zip(first, start)) < 0.35
     assert max(abs(a - b) for a, b in zip(last, goal)) < 0.35
+
+
+@pytest.mark.gpu
+def test_requests_by_joint_name_and_late_scene_changes(tmp_path):
+    """MotionPlanners facade: start / goal assembled by joint name, NaN / missing / out-of-limit values refused, and a
+    world object added after initialize() reaches the validity checks and the next solve (tests/cpp/scene_and_request_test.cpp)."""
+    _build()
+    exe = str(tmp_path / "scene_and_request_test")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "scene_and_request_test.cpp"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "motion_planners_b200"), "-lmotion_planners_b200", "-lstomp_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "motion_planners_b200")], check=True)
+    out = subprocess.run([exe, os.path.join(ROOT, "test")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    for name in ("request_by_name", "refused_requests", "scene_change_reaches_the_validity_checks",
+                 "scene_change_reaches_the_next_solve"):
+        assert f"ok {name}" in out.stdout
