@@ -117,6 +117,8 @@ struct stomp_b200_engine {
 
     LoopParams base;                // pointers + constants; per-iteration fields filled in iterate
     double* proj2[2] = {nullptr, nullptr};
+    double* d_Lband = nullptr;               // [T][8] rows of L^-1 for the recurrence sampler
+    int sampler_mode = 0;                    // 0 recurrence (default), 1 DMMA contraction, 2 FMA-pipe contraction (STOMP_B200_SAMPLER)
     double* d_Mproj = nullptr; double* d_Minv = nullptr;   // projection_matrix_ / its inverse (use_projection only)
     double* state2[2] = {nullptr, nullptr};
     uint8_t* verdict2[2] = {nullptr, nullptr};
@@ -136,6 +138,7 @@ struct stomp_b200_engine {
     bool solving = false;
     int num_rollouts = 0;           // num_rollouts_ after the previous iteration (global)
     int last_gen = 0, last_local = 0, last_noiseless_slot = -1;
+    bool last_noise_from_rollouts = false;   // the last iteration did not write `noise` (read-backs say so)
     int last_wblocks = 1;           // partial sums of the weights left in wpart by the last iteration
     bool fuse_weights_allowed = true;   // STOMP_B200_FUSE_WEIGHTS=0 at creation keeps K7 / K8 / K9 as separate kernels
     bool noiseless_valid = false, adapted_valid = false;
@@ -336,6 +339,38 @@ int launch_sample(stomp_b200_engine* e, const LoopParams& lp)
 
 enum NoiseMode { kNoisePhilox = 0, kNoiseUnit = 1, kNoiseEpsilon = 2 };
 
+// the control-cost operator has the shape the fused / register-window kernels are written for: one rule with taps
+// -2 .. +2, Toeplitz R of half bandwidth <= 4, even T
+bool rows_shape_is_shipped(const stomp_b200_engine* e, const LoopParams& rl)
+{
+    const bool fast = rl.st_n > 0 && rl.num_rules == 1 && (rl.r_toeplitz || !rl.use_noise_adaptation) && e->T % 2 == 0 && e->N >= 12;
+    if (!fast) return false;
+    for (int j = 0; j < rl.st_n; ++j)
+        if (!(rl.st_off[j] > -3 && rl.st_off[j] < 3)) return false;
+    return rl.rband_halfwidth <= 4;
+}
+
+// recurrence sampler (L^-1 is banded); fuse: control-cost sums + n^T R n in the same pass
+template <bool kPhilox>
+int launch_sample_banded(stomp_b200_engine* e, const LoopParams& lp, bool fuse)
+{
+    const int nkb = (lp.num_gen + 31) / 32;
+    const dim3 grid((unsigned)(nkb * lp.D), (unsigned)lp.Q);
+    const size_t smem = sizeof(double) * banded_sampler_smem_doubles(lp.T, lp.N, lp.lband_halfwidth <= 4 ? 4 : 6);
+    auto launch = [&](auto kernel) -> int {
+        const void* fn = (const void*)kernel;
+        if (smem > 48 * 1024 && !e->smem_opted_in.count(fn)) {       // long trajectories: the 32 x T tile passes 48 KB
+            CUDA_TRY(e, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+            e->smem_opted_in.insert(fn);
+        }
+        Scope s(e, STOMP_B200_KERNEL_SAMPLE);
+        kernel<<<grid, kBandedThreads, smem, e->stream>>>(lp, e->limits);
+        return check_launch(e, "sample_rollouts_banded_kernel");
+    };
+    if (lp.lband_halfwidth <= 4) return fuse ? launch(sample_rollouts_banded_kernel<4, kPhilox, true>) : launch(sample_rollouts_banded_kernel<4, kPhilox, false>);
+    return fuse ? launch(sample_rollouts_banded_kernel<6, kPhilox, true>) : launch(sample_rollouts_banded_kernel<6, kPhilox, false>);
+}
+
 // one Stomp::runSingleIteration for all local queries, queued on the stream (no host synchronisation)
 // eight-rows-per-warp control-cost kernel (kernels.cuh): instantiated for the group counts of the usual T
 template <int kGroups>
@@ -475,8 +510,30 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         e->base.proj = lp.proj; e->base.state_costs = lp.state_costs; e->base.verdicts = lp.verdicts;
     }
 
+    // padding-only rows of the control costs: constants of a solve, needed by the fused sampler and the row kernels
+    if (e->edge_dirty && lp.num_rules == 1) {
+        edge_rows_kernel<<<e->Q, 64, 0, e->stream>>>(lp);
+        e->launch_count++;
+        if (int rc = check_launch(e, "edge_rows_kernel")) return rc;
+        e->edge_dirty = false;
+    }
     // ---- generate (K1-K3) ----
-    if (mode == kNoiseUnit) {
+    // on-device noise goes through the recurrence sampler (L^-1 is banded) with the control-cost rows fused in; injected
+    // epsilon goes through the contraction with the caller's L (parity mode) unless STOMP_B200_SAMPLER=banded
+    const bool banded = lp.Lband != nullptr && mode != kNoiseUnit &&
+                        ((mode == kNoisePhilox && (e->sampler_mode == 0 || e->sampler_mode == 3)) || (mode == kNoiseEpsilon && e->sampler_mode == 3));
+    const bool fused_rows = banded && !lp.Mproj && rows_shape_is_shipped(e, lp);
+    // the shipped large-K loop (fused sampler, fused weights / update kernel, nothing reads `noise` back): the noise
+    // tensor is not materialised — weights_update_kernel subtracts theta from the rollout rows it streams
+    {
+        const bool fuse_weights_ahead = e->fuse_weights_allowed && world == 1 && !e->profiling && !e->reuse_possible && reused == 0 && c.use_cumulative_costs;
+        lp.noise_from_rollouts = (fused_rows && fuse_weights_ahead && !c.keep_debug_tensors && !lp.control_costs && !lp.proj) ? 1 : 0;
+        static const bool lean_allowed = !(std::getenv("STOMP_B200_LEAN_NOISE") && std::strcmp(std::getenv("STOMP_B200_LEAN_NOISE"), "0") == 0);
+        if (!lean_allowed) lp.noise_from_rollouts = 0;
+    }
+    if (banded) {
+        if (int rc = (mode == kNoisePhilox ? launch_sample_banded<true>(e, lp, fused_rows) : launch_sample_banded<false>(e, lp, fused_rows))) return rc;
+    } else if (mode == kNoiseUnit) {
         Scope sc(e, STOMP_B200_KERNEL_SAMPLE);
         const int per_query = gen_local * e->D * e->T;
         dim3 grid(std::min(1024, (per_query + 255) / 256), e->Q);
@@ -492,7 +549,8 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     // other (different columns of `sums`), both latency-bound at < 50 % occupancy -> run side by side on two
     // streams; serial on the main stream while per-kernel profiling is on ----
     static const bool overlap_allowed = !(std::getenv("STOMP_B200_OVERLAP") && std::strcmp(std::getenv("STOMP_B200_OVERLAP"), "0") == 0);
-    const bool overlap_rows = overlap_allowed && !e->profiling && e->rows_stream != nullptr;
+    const bool rows_needed = !(fused_rows && !lp.control_costs);      // the fused sampler already left C_d and n^T R n
+    const bool overlap_rows = overlap_allowed && !e->profiling && e->rows_stream != nullptr && rows_needed;
     cudaStream_t rows_stream = overlap_rows ? e->rows_stream : e->stream;
     if (overlap_rows) {
         CUDA_TRY(e, cudaEventRecord(e->ev_sampled, e->stream));
@@ -501,12 +559,6 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     {
         const int rows = gen_local * e->D;
         Scope sc(e, STOMP_B200_KERNEL_ROWS);
-        if (e->edge_dirty && lp.num_rules == 1) {   // padding-only rows of the control costs: constants of a solve
-            edge_rows_kernel<<<e->Q, 64, 0, rows_stream>>>(lp);
-            e->launch_count++;
-            if (int rc = check_launch(e, "edge_rows_kernel")) return rc;
-            e->edge_dirty = false;
-        }
         auto launch_rows = [&](const LoopParams& rl) -> int {
             // one rule with Toeplitz interior rows, Toeplitz R, even T and 16-byte aligned rows: the register-window kernel
             const bool fast = rl.st_n > 0 && rl.num_rules == 1 && (rl.r_toeplitz || !rl.use_noise_adaptation) && e->T % 2 == 0 && e->N >= 12;
@@ -542,6 +594,15 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
             LoopParams qpass = lp; qpass.rows_noise = lp.noise; qpass.rows_mask = 2; qpass.control_costs = nullptr;
             e->launch_count++;
             if (int rc = launch_rows(qpass)) return rc;
+        } else if (fused_rows) {
+            // the sampler left C_d and n^T R n; only the per-time-step control costs (read-backs, per-time-step mode) are missing
+            if (lp.control_costs) {
+                LoopParams store = lp; store.rows_mask = 0;
+                if (int rc = launch_rows(store)) return rc;
+            } else {
+                e->kernel_launches[STOMP_B200_KERNEL_ROWS]--;     // nothing launched in this scope
+                e->launch_count--;
+            }
         } else {
             if (int rc = launch_rows(lp)) return rc;
         }
@@ -594,6 +655,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     // one launch for K7-K9 when nothing sits between them (no exchange, no reused rollouts, no per-kernel profiling)
     const bool per_timestep = !c.use_cumulative_costs;
     const bool fuse_weights = e->fuse_weights_allowed && world == 1 && !e->profiling && !e->reuse_possible && reused == 0 && !per_timestep;
+    if (lp.noise_from_rollouts && !fuse_weights) return fail(e, STOMP_B200_ERR_CUDA, "internal: noise not materialised but the fused update kernel is not in use");
     const int nchunks = std::max(1, (lp.num_local + lp.chunk - 1) / lp.chunk);
     lp.nchunks = nchunks;
     if (fuse_weights) {
@@ -641,6 +703,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
         if (int rc = check_launch(e, "apply_update_kernel")) return rc;
     }
     e->last_wblocks = lp.wblocks;
+    e->last_noise_from_rollouts = lp.noise_from_rollouts != 0;
     // ---- noise-less rollout (K10) on the side stream: overlaps the next iteration's sampling and costs ----
     {
         CUDA_TRY(e, cudaEventRecord(e->ev_applied, e->stream));
@@ -945,6 +1008,7 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
         CREATE_TRY(dev_alloc(e, &tmp, D)); b.min_stddev = tmp;
         CREATE_CUDA(cudaMemcpyAsync(tmp, cfg->noise_min_stddev, sizeof(double) * D, cudaMemcpyHostToDevice, e->stream));
         CREATE_TRY(dev_alloc(e, &tmp, T * T)); b.Lt = tmp;
+        CREATE_TRY(dev_alloc(e, &e->d_Lband, T * 8));
         CREATE_TRY(dev_alloc(e, &tmp, T * (2 * kRBand + 1))); b.Rband = tmp;
         CREATE_CUDA(cudaStreamSynchronize(e->stream));
     }
@@ -960,6 +1024,7 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
         e->num_sms = prop.multiProcessorCount;
         const char* sampler = std::getenv("STOMP_B200_SAMPLER");
         e->use_dmma = !(sampler && std::string(sampler) == "simt");
+        e->sampler_mode = !sampler ? 0 : (std::string(sampler) == "dmma" ? 1 : (std::string(sampler) == "simt" ? 2 : (std::string(sampler) == "banded" ? 3 : 0)));
     }
     CREATE_CUDA(cudaFuncSetAttribute(noiseless_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CREATE_CUDA(cudaFuncSetAttribute(reuse_rollouts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -1310,6 +1375,47 @@ int stomp_b200_get_sdf(stomp_b200_engine* e, float* out, size_t count, int32_t d
     return STOMP_B200_OK;
 }
 
+// Rows of B = L^-1 for the recurrence sampler (kernels.cuh: sample_rollouts_banded_kernel).  R = U U^T with U upper
+// triangular and banded (Cholesky run from the last row up, long double), B = U^T.  The table is accepted only if the
+// recurrence reproduces columns of the caller's L (so a caller that hands in some other factor keeps the contraction).
+static bool build_sampler_band(const double* R, const double* L, int T, int hw, std::vector<double>& table)
+{
+    if (hw < 1 || hw > kRBand) return false;
+    std::vector<long double> U((size_t)T * (hw + 1), 0.0L);      // U[i][i + o] at [i][o]
+    auto u = [&](int i, int k) -> long double& { return U[(size_t)i * (hw + 1) + (k - i)]; };
+    for (int j = T - 1; j >= 0; --j) {
+        long double sdiag = R[(size_t)j * T + j];
+        for (int k = j + 1; k <= std::min(T - 1, j + hw); ++k) sdiag -= u(j, k) * u(j, k);
+        if (!(sdiag > 0.0L)) return false;
+        u(j, j) = sqrtl(sdiag);
+        for (int i = j - 1; i >= std::max(0, j - hw); --i) {
+            long double sij = R[(size_t)i * T + j];
+            for (int k = j + 1; k <= std::min(T - 1, i + hw); ++k) sij -= u(i, k) * u(j, k);
+            u(i, j) = sij / u(j, j);
+        }
+    }
+    table.assign((size_t)T * 8, 0.0);
+    for (int t = 0; t < T; ++t) {
+        const long double inv = 1.0L / u(t, t);
+        table[(size_t)t * 8] = (double)inv;
+        for (int o = 1; o <= hw && t - o >= 0; ++o) table[(size_t)t * 8 + o] = (double)(u(t - o, t) * inv);
+    }
+    // check against the given L: the recurrence applied to unit vectors must give columns of L
+    double lmax = 0.0;
+    for (size_t i = 0; i < (size_t)T * T; ++i) lmax = std::max(lmax, std::fabs(L[i]));
+    const int cols[3] = {0, T / 3, T - 1};
+    std::vector<double> n(T);
+    for (int c : cols) {
+        for (int t = 0; t < T; ++t) {
+            double acc = (t == c ? 1.0 : 0.0) * table[(size_t)t * 8];
+            for (int o = 1; o <= hw && t - o >= 0; ++o) acc -= table[(size_t)t * 8 + o] * n[t - o];
+            n[t] = acc;
+            if (!(std::fabs(n[t] - L[(size_t)t * T + c]) <= 1e-6 * lmax)) return false;
+        }
+    }
+    return true;
+}
+
 int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R, const double* Rinv, const double* L)
 {
     if (!e || !R || !L) return STOMP_B200_ERR_INVALID_ARGUMENT;
@@ -1353,6 +1459,17 @@ int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R, 
         for (int o = 0; o <= kRBand && t + o < T; ++o)
             if (band[(size_t)t * (2 * kRBand + 1) + kRBand + o] != e->base.r_diag[o]) { e->base.r_toeplitz = 0; break; }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    {
+        std::vector<double> table;
+        if (build_sampler_band(R, L, T, hw, table)) {
+            CUDA_TRY(e, cudaMemcpy(e->d_Lband, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
+            e->base.Lband = e->d_Lband;
+            e->base.lband_halfwidth = hw;
+        } else {
+            e->base.Lband = nullptr;
+            e->base.lband_halfwidth = 0;
+        }
+    }
     CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.Lt), Lt.data(), sizeof(double) * Lt.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.Rband), band.data(), sizeof(double) * band.size(), cudaMemcpyHostToDevice));
     e->have_matrices = true;
@@ -1561,7 +1678,9 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
     };
     switch (tensor) {
         case STOMP_B200_ROLLOUTS: return per_query(b.rollouts, nl * D, (size_t)e->slots * D, T * sizeof(double));
-        case STOMP_B200_NOISE: return per_query(b.noise, nl * D, (size_t)e->slots * D, T * sizeof(double));
+        case STOMP_B200_NOISE:
+            if (e->last_noise_from_rollouts) return fail(e, STOMP_B200_ERR_NOT_READY, "noise_ was not materialised in this configuration (keep_debug_tensors keeps it)");
+            return per_query(b.noise, nl * D, (size_t)e->slots * D, T * sizeof(double));
         case STOMP_B200_STATE_COSTS: return per_query(b.state_costs, nl, e->slots, T * sizeof(double));
         case STOMP_B200_VERDICTS: return per_query(b.verdicts, nl, e->slots, T);
         case STOMP_B200_CONTROL_COSTS:

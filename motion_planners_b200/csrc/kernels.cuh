@@ -98,6 +98,9 @@ struct LoopParams {
     int32_t st_off[7];
     double st_coef[7];
     double st_dense[7];       // the same taps as a dense row, offsets -3 .. +3 (zeros included)
+    // recurrence sampler (sample_rollouts_banded_kernel): rows of L^-1, which is banded — see the kernel's comment
+    const double* Lband;      // [T][8]: [0] = 1 / B[t][t], [o] = B[t][t-o] / B[t][t] for o = 1 .. 6 (zero beyond the band / before row 0), [7] unused
+    int32_t lband_halfwidth;  // band of B = L^-1 below the diagonal (4 for the acceleration rule); 0 = table not available
     // M-matrix projection (PolicyImprovement::use_projection_, PolicyImprovement.cpp:421-440,706,750-801); all null / 0
     // in the shipped configuration, where M is the identity
     const double* Mproj;      // [T][T] projection_matrix_ = R^-1 with column p scaled by 1 / (T * R^-1[p][p]), row major
@@ -106,6 +109,7 @@ struct LoopParams {
     const double* rows_noise; // what the control-cost row kernels read: noise (default) or noise_proj
     int32_t rows_mask;        // bit 0: write C_d (control-cost sums), bit 1: write n^T R n; 3 = both (one pass, M = I)
     int32_t per_timestep_minmax;   // per-time-step costs only: min / max per time step (variant at PolicyImprovement.cpp:518-528)
+    int32_t noise_from_rollouts;   // the sampler did not write `noise`: weights_update_kernel forms rollouts - theta itself
 };
 
 // the joint limits of OptimizationTask::filter: all the sampling kernels need of the robot (0.5 KB of kernel parameters
@@ -203,10 +207,14 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
 }
 
 // four standard normals for column `column` (global (query, rollout, joint) index), time steps 4*u4..4*u4+3
+__device__ __forceinline__ void philox_normals_keyed(uint2 key, uint32_t iteration, uint32_t column, uint32_t u4, double z[4]);
 __device__ __forceinline__ void philox_normals(uint64_t seed, uint32_t iteration, uint32_t column, uint32_t u4, double z[4])
 {
-    const uint4 r = philox4x32_10(make_uint4(column, u4, iteration, 0x53544F4Du),
-                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    philox_normals_keyed(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), iteration, column, u4, z);
+}
+__device__ __forceinline__ void philox_normals_keyed(uint2 key, uint32_t iteration, uint32_t column, uint32_t u4, double z[4])
+{
+    const uint4 r = philox4x32_10(make_uint4(column, u4, iteration, 0x53544F4Du), key);
     const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f);
@@ -214,7 +222,10 @@ __device__ __forceinline__ void philox_normals(uint64_t seed, uint32_t iteration
     // Box-Muller on the SFU (MUFU.LG2 / SIN / COS / RSQ): the library logf / sincospif made this function ~200
     // instructions and 38 % of the sampler's instruction stream (profiles/r1y); the uniforms carry 24 bits, the
     // intrinsics' ~2^-21 absolute error is below that resolution
-    const float ra = __fsqrt_rn(-2.0f * __logf(u1)), rb = __fsqrt_rn(-2.0f * __logf(u3));
+    // r = sqrt(-2 ln u) = sqrt(-2 ln 2 * log2 u): MUFU.LG2, one multiply, MUFU.SQRT (approximate: no denormal slow path)
+    float ra, rb;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(-1.3862943611198906f * __log2f(u1)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(-1.3862943611198906f * __log2f(u3)));
     float sa, ca, sb, cb;
     __sincosf(6.28318530717958647692f * u2 - 3.14159265358979323846f, &sa, &ca);     // argument in [-pi, pi): the SFU's accurate range
     __sincosf(6.28318530717958647692f * u4f - 3.14159265358979323846f, &sb, &cb);
@@ -629,6 +640,335 @@ project_noise_dmma_kernel(const __grid_constant__ LoopParams p)
                 }
             }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same sample without the contraction.  L = chol(R^-1) (MultivariateGaussian.hpp:81) is dense, but its INVERSE is
+// banded: factor the banded R = U U^T with U UPPER triangular (a Cholesky factorisation run from the last row up; U has R's
+// half bandwidth b, 4 for the shipped acceleration rule).  Then R^-1 = U^-T U^-1 with U^-T lower triangular and positive
+// on the diagonal, and the Cholesky factor is unique, so L = U^-T exactly and
+//     n = L eps   <=>   U^T n = eps   <=>   n_t = (eps_t - sum_{o=1..b} U[t-o][t] n_{t-o}) / U[t][t]:
+// a b-term recurrence per column, O(T b) instead of the O(T^2 / 2) contraction — 65 x fewer FP64 operations at T = 100,
+// and the FP64 pipe is what bounds this loop (DMMA and DFMA share it: tools/fp64_mixed.cu, profiles/r3_fp64_mixed.json).
+// It is also the more accurate statement of the same map: against a long-double solve the recurrence is good to 1e-14,
+// while L as the reference computes it (fullPivLu().inverse() then llt(), cond(R) = 6e6 at T = 100) carries 7e-11 — the
+// two agree to that 7e-11 (3e-10 at T = 200), inside the 1e-9 bar; tests/test_gpu_parity.py holds both statements.
+// The host builds the table from R (engine.cu: build_sampler_band) and checks it against the L it was given; injected
+// epsilon (parity mode) and matrices that fail the check go through the DMMA contraction above with the caller's L.
+//
+// Mapping: one CTA (four warps) = 32 rollouts of ONE joint of one query; the 32 x T tile of eps / unit noise / samples
+// lives in shared memory (odd row stride: walks along t by one lane per rollout and walks along t by consecutive lanes
+// are both conflict free).  Phases, separated by CTA barriers; seven CTAs per SM keep 28 warps in flight:
+//   1. eps: lane = rollout, the warps share the groups of four time steps — same Philox counters as the contraction
+//      kernels, so the same seed gives the same eps — or copy the injected eps;
+//   2. the recurrence: warp 0, lane = rollout, sequential in t, band rows of L^-1 from a shared-memory table; the n_{t-1}
+//      term is the only one on the critical path;
+//   3a. lane = rollout again, each warp a quarter of the time steps, sequential in t: mean shift p1 * mincc + p2 * theta +
+//      new_stddev * n, joint-limit clamp (the sample replaces the unit noise in the tile), noise = clamped - theta, and —
+//      kFuse — the control-cost stencil and n^T R n from a 5-wide window of the noise that slides through REGISTERS (the
+//      six noise values a quarter needs from its neighbours are taken before anyone overwrites the tile): K5 / K6 cost
+//      no pass over `noise` in HBM, no kernel of their own, no shuffle.  The stencil uses linearity:
+//      (D x)_i = (D theta_all)_i + sum_m c_m noise[i - 8 + m], the first term a per-CTA table;
+//   3b. lane = time step: the tile leaves as coalesced rows of `rollouts` and `noise` (= sample - theta).
+// kFuse needs the shipped shape of the operator (one 5-tap rule, Toeplitz R with half bandwidth <= 4); otherwise the row
+// kernels run afterwards.  kB: band of the recurrence, 4 or 6.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBandedThreads = 128;
+__host__ __device__ inline int banded_tile_stride(int T) { return T | 1; }
+__host__ __device__ inline int banded_band_doubles(int T, int kB) { return (T * (kB + 1) > 256 + 2 * T) ? T * (kB + 1) : 256 + 2 * T; }
+__host__ __device__ inline size_t banded_sampler_smem_doubles(int T, int N, int kB)
+{
+    // tile [32][T | 1] | band [T][kB + 1], reused after phase 2 for [256] partial sums + mean [T] + theta [T] | (D theta_all)_i [N].
+    // 30.8 KB at T = 100: SEVEN CTAs per SM, which is what the 896 tiles of BASELINE config 3 need to be one wave on 148 SMs
+    return (size_t)32 * banded_tile_stride(T) + (size_t)banded_band_doubles(T, kB) + (size_t)N;
+}
+
+template <int kB, bool kPhilox, bool kFuse>
+__global__ void __launch_bounds__(kBandedThreads, 7)
+sample_rollouts_banded_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ JointLimits robot)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 0);
+    const int T = p.T, D = p.D, N = p.N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nkb = (p.num_gen + 31) >> 5;
+    const int d = blockIdx.x / nkb, kb = blockIdx.x - d * nkb;
+    const int k0 = kb * 32;
+    const int ncol = min(32, p.num_gen - k0);                // live rollouts of this tile
+    const int S = banded_tile_stride(T);
+    const bool debug_stores = p.store_unit != 0;
+    const bool live = lane < ncol;                           // lane = rollout phases
+
+    double* s_tile = smem;                                   // [32][S]
+    double* s_band = s_tile + 32 * S;                        // [T][kB + 1]: 1 / B_tt, B_{t,t-1} / B_tt, ...
+    double* s_dth = s_band + banded_band_doubles(T, kB);     // [N]  (D theta_all)_i for the interior rows 3 .. N-4
+    double* s_part = s_band;                                 // after phase 2 the band table is dead: [2][4][32] partial sums of phase 3a,
+    double* s_mean = s_band + 256;                           //   [T] p1 * mincc + p2 * theta (the first two terms of the mean-shifted sample)
+    double* s_th = s_mean + T;                               //   [T] theta
+    const double* th_all = p.theta_all + ((size_t)q * D + d) * N;
+    const double* mc_row = p.mincc + ((size_t)q * D + d) * T;
+    const double c1 = p.st_dense[1], c2 = p.st_dense[2], c3 = p.st_dense[3], c4 = p.st_dense[4], c5 = p.st_dense[5];
+    for (int i = tid; i < T * (kB + 1); i += kBandedThreads) {
+        const int t = i / (kB + 1), o = i - t * (kB + 1);
+        s_band[i] = p.Lband[t * 8 + o];
+    }
+    if (kFuse)
+        for (int i = tid; i < N; i += kBandedThreads) {
+            double v = 0.0;
+            if (i >= 3 && i < N - 3) {
+                v = c1 * th_all[i - 2];
+                v = fma(c2, th_all[i - 1], v); v = fma(c3, th_all[i], v); v = fma(c4, th_all[i + 1], v); v = fma(c5, th_all[i + 2], v);
+            }
+            s_dth[i] = v;
+        }
+    // ---- phase 1: eps ----
+    if (live) {
+        const int ngroups = (T + 3) >> 2;
+        // global column of this rollout and joint: the Philox counter of the contraction kernels
+        const uint32_t gcol = (uint32_t)(((uint32_t)(p.query_offset + q) * (uint32_t)p.gen_global + (uint32_t)(p.gen_offset + k0 + lane)) * (uint32_t)D + (uint32_t)d);
+        const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        const uint32_t iteration = (uint32_t)p.iteration;
+        double* dst = s_tile + lane * S;
+        double* eps_row = p.epsilon + (((size_t)q * p.num_gen + (k0 + lane)) * D + d) * T;
+        for (int g = warp; g < ngroups; g += kBandedThreads / 32) {
+            const int tg = 4 * g;
+            double z[4];
+            if (kPhilox) {
+                philox_normals_keyed(key, iteration, gcol, (uint32_t)g, z);
+                if (debug_stores) {
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        if (tg + m < T) eps_row[tg + m] = z[m];
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) z[m] = (tg + m < T) ? eps_row[tg + m] : 0.0;
+            }
+            if (tg + 3 < T) { dst[tg] = z[0]; dst[tg + 1] = z[1]; dst[tg + 2] = z[2]; dst[tg + 3] = z[3]; }
+            else {
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (tg + m < T) dst[tg + m] = z[m];
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: the recurrence, in place (eps -> unit noise) ----
+    if (warp == 0 && live) {
+        double h[kB];
+#pragma unroll
+        for (int o = 0; o < kB; ++o) h[o] = 0.0;
+        double* col = s_tile + lane * S;
+        // Blocks of four steps: every shared-memory load of the block (eps of this rollout, warp-uniform band rows) is issued
+        // before its first store — the compiler cannot prove that `col` and the band table do not alias and would otherwise
+        // expose a shared-memory round trip per step (measured: 88 cycles per step, 4.5 us per tile).  Inside a block the
+        // terms of n_{t-2} .. n_{t-kB} come first and n_{t-1} last: one DFMA per step on the critical path.
+        int t = 0;
+        for (; t + 4 <= T; t += 4) {
+            double e[4], bb[4][kB + 1];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                e[m] = col[t + m];
+#pragma unroll
+                for (int o = 0; o <= kB; ++o) bb[m][o] = s_band[(t + m) * (kB + 1) + o];
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                double acc = e[m] * bb[m][0];
+#pragma unroll
+                for (int o = kB - 1; o >= 0; --o) acc = fma(-bb[m][1 + o], h[o], acc);
+#pragma unroll
+                for (int o = kB - 1; o > 0; --o) h[o] = h[o - 1];
+                h[0] = acc;
+                e[m] = acc;
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) col[t + m] = e[m];
+        }
+        for (; t < T; ++t) {
+            const double* b = s_band + t * (kB + 1);
+            double acc = col[t] * b[0];
+#pragma unroll
+            for (int o = kB - 1; o >= 0; --o) acc = fma(-b[1 + o], h[o], acc);
+#pragma unroll
+            for (int o = kB - 1; o > 0; --o) h[o] = h[o - 1];
+            h[0] = acc;
+            col[t] = acc;
+        }
+    }
+    __syncthreads();
+    // ---- phase 3a: lane = rollout, warp w = time steps [a, b) ----
+    const double* cf = p.coef + ((size_t)q * D + d) * 3;
+    const double p1 = cf[0], p2 = cf[1], sd = cf[2];
+    for (int t = tid; t < T; t += kBandedThreads) {
+        const double th = th_all[kPad + t];
+        s_th[t] = th;
+        s_mean[t] = p1 * mc_row[t] + p2 * th;
+    }
+    __syncthreads();
+    const double lo = robot.lower[d], hi = robot.upper[d];
+    const double r0 = p.r_diag[0], r1 = 2.0 * p.r_diag[1], r2 = 2.0 * p.r_diag[2], r3 = 2.0 * p.r_diag[3], r4 = 2.0 * p.r_diag[4];
+    const int Tq = (T + 3) >> 2;
+    const int a = warp * Tq, b = min(T, a + Tq);
+    const bool has_steps = a < T;
+    const bool last = has_steps && b == T;
+    double* col = s_tile + lane * S;
+    // clamped sample for unit noise `unit` at time step s: the arithmetic of shift_clamp_store (PolicyImprovement.cpp:262-269)
+    auto sample_of = [&](int s, double unit, double& theta) {
+        theta = s_th[s];
+        double v = s_mean[s] + sd * unit;
+        if (v < lo) v = lo;
+        if (v > hi) v = hi;
+        return v;
+    };
+    // noise values this quarter needs from its neighbours (4 behind, 2 ahead), taken before the tile is overwritten
+    double hm4 = 0.0, hm3 = 0.0, hm2 = 0.0, hm1 = 0.0, hp0 = 0.0, hp1 = 0.0;
+    if (kFuse && has_steps && live) {
+        double th;
+        if (a - 4 >= 0) hm4 = sample_of(a - 4, col[a - 4], th) - th;
+        if (a - 3 >= 0) hm3 = sample_of(a - 3, col[a - 3], th) - th;
+        if (a - 2 >= 0) hm2 = sample_of(a - 2, col[a - 2], th) - th;
+        if (a - 1 >= 0) hm1 = sample_of(a - 1, col[a - 1], th) - th;
+        if (b < T) hp0 = sample_of(b, col[b], th) - th;
+        if (b + 1 < T) hp1 = sample_of(b + 1, col[b + 1], th) - th;
+    }
+    if (debug_stores) {                                      // read-backs of the unit noise (parity tests): rows of the tile as they are now
+        for (int c = warp * 8; c < min(warp * 8 + 8, ncol); ++c) {
+            double* unit_row = p.unit_noise + (((size_t)q * p.num_gen + (k0 + c)) * D + d) * T;
+            for (int t = lane; t < T; t += 32) unit_row[t] = s_tile[c * S + t];
+        }
+    }
+    __syncthreads();
+    double ss = 0.0, quad = 0.0;
+    if (has_steps && live) {
+        double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0, w4 = 0.0;     // noise[s-4 .. s]
+        // noise[s] enters the window: row i = (s - 2) + 6 of the differentiation matrix is complete, and so is the n^T R n term of s
+        auto push = [&](double nz, int s, bool row, bool term) {
+            w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = nz;
+            if (row) {
+                double sacc = s_dth[s - 2 + kPad];
+                sacc = fma(c1, w0, sacc); sacc = fma(c2, w1, sacc); sacc = fma(c3, w2, sacc); sacc = fma(c4, w3, sacc); sacc = fma(c5, w4, sacc);
+                ss = fma(sacc, sacc, ss);
+            }
+            if (term) {
+                double qs = r0 * w4;
+                qs = fma(r1, w3, qs); qs = fma(r2, w2, qs); qs = fma(r3, w1, qs); qs = fma(r4, w0, qs);
+                quad = fma(w4, qs, quad);                    // n_s (R_ss n_s + 2 sum_{o>0} R_{s,s-o} n_{s-o}): each pair once; zero outside [0, T)
+            }
+        };
+        // rows t' = s - 2 owned by this quarter: [a, b); the first quarter also -3 .. -1 (start padding), the last one also
+        // T .. T + 2 (goal padding)
+        const int own_lo = (a == 0) ? -3 : a, own_hi = last ? T + 3 : b;
+        auto owns = [&](int s) { return s - 2 >= own_lo && s - 2 < own_hi; };
+        if (kFuse) {
+            push(hm4, a - 4, false, false); push(hm3, a - 3, false, false); push(hm2, a - 2, false, false);
+            push(hm1, a - 1, owns(a - 1), false);            // s = -1 completes row -3 (all-zero noise)
+        }
+        int s = a;
+        // the first two steps complete rows of the previous quarter (unless this is the first one): generic path
+        for (; s < min(a + 2, b); ++s) {
+            double theta;
+            const double v = sample_of(s, col[s], theta);
+            col[s] = v;
+            if (kFuse) push(v - theta, s, owns(s), true);
+        }
+        // blocks of five steps (the window's rotation period: no register moves), loads before stores as in phase 2
+        for (; s + 5 <= b; s += 5) {
+            double u[5], th[5], mn[5], dt5[5];
+#pragma unroll
+            for (int m = 0; m < 5; ++m) { u[m] = col[s + m]; th[m] = s_th[s + m]; mn[m] = s_mean[s + m]; if (kFuse) dt5[m] = s_dth[s + m - 2 + kPad]; }
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                double v = mn[m] + sd * u[m];
+                if (v < lo) v = lo;
+                if (v > hi) v = hi;
+                u[m] = v;
+                if (kFuse) {
+                    const double nz = v - th[m];
+                    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = nz;
+                    double sacc = dt5[m];
+                    sacc = fma(c1, w0, sacc); sacc = fma(c2, w1, sacc); sacc = fma(c3, w2, sacc); sacc = fma(c4, w3, sacc); sacc = fma(c5, w4, sacc);
+                    ss = fma(sacc, sacc, ss);
+                    double qs = r0 * w4;
+                    qs = fma(r1, w3, qs); qs = fma(r2, w2, qs); qs = fma(r3, w1, qs); qs = fma(r4, w0, qs);
+                    quad = fma(w4, qs, quad);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 5; ++m) col[s + m] = u[m];
+        }
+        for (; s < b; ++s) {
+            double theta;
+            const double v = sample_of(s, col[s], theta);
+            col[s] = v;
+            if (kFuse) push(v - theta, s, owns(s), true);
+        }
+        if (kFuse) {
+            if (!last) { push(hp0, b, owns(b), false); push(hp1, b + 1, owns(b + 1), false); }
+            else {
+#pragma unroll
+                for (int j = 0; j < 5; ++j) push(0.0, T + j, owns(T + j), false);   // rows up to T + 2 = N - 4: zero noise
+            }
+        }
+    }
+    __syncthreads();
+    if (kFuse) {
+        s_part[warp * 32 + lane] = ss;
+        s_part[128 + warp * 32 + lane] = quad;
+    }
+    __syncthreads();
+    // ---- phase 3b: lane = time step; warp w writes rollouts 8 w .. 8 w + 7 of the tile ----
+    {
+        double* const proj = p.proj;
+        const bool store_noise = p.noise_from_rollouts == 0;
+        const int row_stride = D * T;                        // doubles between the rows of consecutive rollouts of one joint
+        const int c_begin = warp * 8, c_end = min(c_begin + 8, ncol);
+        double* out_v = p.rollouts + (((size_t)q * p.slots + (k0 + c_begin)) * D + d) * T;
+        double* out_n = p.noise + (((size_t)q * p.slots + (k0 + c_begin)) * D + d) * T;
+        const double* tile_row = s_tile + c_begin * S;
+        // theta of this lane's time steps, once for all rows (T <= STOMP_B200_MAX_TIME_STEPS = 256: eight per lane)
+        double th_reg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) th_reg[j] = (lane + 32 * j < T) ? s_th[lane + 32 * j] : 0.0;
+        for (int c = c_begin; c < c_end; ++c, out_v += row_stride, out_n += row_stride, tile_row += S) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int t = lane + 32 * j;
+                if (t < T) {
+                    const double v = tile_row[t];
+                    out_v[t] = v;
+                    if (store_noise) out_n[t] = v - th_reg[j];
+                }
+            }
+            if (proj) {                                      // configurations with rollout reuse: computeProjectedNoise with M = I (PolicyImprovement.cpp:430-440)
+                double* proj_row = proj + (((size_t)q * p.slots + (k0 + c)) * D + d) * T;
+                for (int t = lane; t < T; t += 32) { const double th = th_all[kPad + t]; proj_row[t] = th + (tile_row[t] - th); }
+            }
+        }
+    }
+    if (warp == 0 && live) {
+        const int k = k0 + lane;
+        double* srow = p.sums + ((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw;
+        if (kFuse) {
+            const double* ec = p.edge_cost + ((size_t)q * D + d) * 6;
+            const double edge = ((ec[0] + ec[1]) + (ec[2] + ec[3])) + (ec[4] + ec[5]);
+            const double sw = p.rule_sqrt_w[0];
+            const double kappa = (p.dt * p.control_cost_weight) * (sw * sw);
+            const double ss_all = (s_part[lane] + s_part[32 + lane]) + (s_part[64 + lane] + s_part[96 + lane]);
+            const double quad_all = (s_part[128 + lane] + s_part[160 + lane]) + (s_part[192 + lane] + s_part[224 + lane]);
+            const double C_d = kappa * ss_all + edge;
+            srow[1 + d] = C_d;
+            if (p.c_compact) p.c_compact[((size_t)q * D + d) * p.gslots + (p.gen_offset + k)] = C_d;
+            srow[1 + 2 * D + d] = p.use_noise_adaptation ? quad_all : 0.0;
+        }
+        if (d == 0) {                   // S_k = sum_t state cost is accumulated with atomics by the state kernel: zeroed here
+            srow[0] = 0.0;
+            if (p.s_compact) p.s_compact[(size_t)q * p.gslots + (p.gen_offset + k)] = 0.0;
+        }
+    }
+    tls.end();
 }
 
 // injected unit noise (parity mode): epilogue only
@@ -1777,21 +2117,27 @@ weights_update_kernel(const __grid_constant__ LoopParams p)
         const int t = t0 + lt;
         double acc = 0.0;
         if (t < T) {
-            const double* nz = p.noise + (((size_t)q * p.slots + k_begin) * D + d) * T + t;
+            // noise_ = parameters_noise_ - parameters_ (PolicyImprovement.cpp:803-810).  When the sampler did not materialise it
+            // (LoopParams::noise_from_rollouts) it is formed here from the rollout row and theta — the same subtraction of the
+            // same two doubles — which halves the sampler's write burst; theta is only updated by the last CTA of this launch,
+            // after every chunk CTA has finished streaming.
+            const bool from_rollouts = p.noise_from_rollouts != 0;
+            const double* nz = (from_rollouts ? p.rollouts : p.noise) + (((size_t)q * p.slots + k_begin) * D + d) * T + t;
+            const double th_t = from_rollouts ? p.theta_all[((size_t)q * D + d) * p.N + kPad + t] : 0.0;
             const size_t stride = (size_t)D * T;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int k = half;
             for (; k + 30 < nk; k += 32) {       // rows k, k+2, ..., k+30
                 double v[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) v[u] = nz[(size_t)(k + 2 * u) * stride];
+                for (int u = 0; u < 16; ++u) v[u] = nz[(size_t)(k + 2 * u) * stride] - th_t;
 #pragma unroll
                 for (int u = 0; u < 16; u += 4) {
                     a0 += v[u] * sp[k + 2 * u]; a1 += v[u + 1] * sp[k + 2 * u + 2];
                     a2 += v[u + 2] * sp[k + 2 * u + 4]; a3 += v[u + 3] * sp[k + 2 * u + 6];
                 }
             }
-            for (; k < nk; k += 2) a0 += nz[(size_t)k * stride] * sp[k];
+            for (; k < nk; k += 2) a0 += (nz[(size_t)k * stride] - th_t) * sp[k];
             acc = (a0 + a1) + (a2 + a3);
         }
         if (half == 1) s_half[lt] = acc;
