@@ -327,6 +327,7 @@ def run_ours(args):
     flusher = L2Flusher(local) if args.l2 == "flush" else None
 
     eng_kind = eng.state_kernel_kind()
+    exchange = eng.exchange_kind()
 
     # clocks / throttle reasons are sampled from before the warm-up to the end of the last measured pass: the timed
     # region itself lasts a few milliseconds, less than one nvidia-smi sampling period
@@ -357,6 +358,7 @@ def run_ours(args):
             total_ms += eng.timer_end()
             it += 1
     launches = eng.launch_count() - launches0
+    replays0 = eng.graph_replays()
     dist_barrier(dist, local)
     total_ms = dist_max(dist, total_ms, local)
     value = states_per_step * args.steps / (total_ms * 1e-3)
@@ -367,6 +369,7 @@ def run_ours(args):
     eng.run(it, args.steps)
     steady_ms = dist_max(dist, eng.timer_end(), local)
     it += args.steps
+    graph_replays = eng.graph_replays() - replays0      # of the steady-state pass: one cudaGraphLaunch per iteration when the loop is captured
 
     # ---- per-kernel pass for the roofline of the dominant kernel (rollout cost) ----
     eng.set_profiling(True)
@@ -461,13 +464,14 @@ def run_ours(args):
         "config": {"workload": w["label"], "name": args.workload, "K": K, "T": T, "D": D, "S": S, "Q": Q,
                    "sdf": list(map(int, problem.sdf.dims)), "sharding": ("queries" if shard_mode == 1 else "rollouts") if world > 1 else "none",
                    "l2": "flushed (256 MiB write) between timed iterations" if flusher else "not flushed",
-                   "noise": "on-device Philox4x32-10"},
+                   "noise": "on-device Philox4x32-10", "exchange": exchange[0] + (": " + exchange[1] if world > 1 else "")},
         "clocks": clocks,
         "e2e": {"value": states_per_step * e2e_iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_iters,
                 "d2h_bytes_per_step": d2h / e2e_iters,
                 "what": "set_policy + begin_solve + one stomp_b200_iterate per step (noise-less cost / validity / stop "
                         "flag read back every step) + finish_solve (solution read back), host wall clock"},
         "gpu_launches": int(launches),
+        "graph_replays": int(graph_replays),
         "parity_ok": parity_ok, "parity": parity_detail,
         "query_sharded_c4": c4,
         "steady_state": {"value": states_per_step * args.steps / (steady_ms * 1e-3), "ms_per_step": steady_ms / args.steps,

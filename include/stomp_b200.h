@@ -256,6 +256,12 @@ int stomp_b200_codegen_selftest(char* log, size_t log_capacity);
 #define STOMP_B200_COMM_ID_BYTES 128
 int stomp_b200_comm_unique_id(void* id_out /*[128]*/);
 int stomp_b200_comm_init(stomp_b200_engine* e, const void* id /*[128]*/);
+/* How the two per-iteration exchanges of a rollout-sharded engine travel: 2 = peer-mapped mailboxes over NVLink, written
+ * and awaited from inside the weights / update kernel (the default when cudaIpc works between the ranks); 1 = NCCL
+ * all-gather + all-reduce (STOMP_B200_EXCHANGE=nccl, or the mailboxes could not be mapped: note says why); 0 = nothing is
+ * exchanged (one GPU, or query sharding).  In mode 2 the rollout-indexed read-backs (costs, probabilities) of
+ * stomp_b200_get_tensor are collective calls: every rank must ask for them in the same order. */
+int32_t stomp_b200_exchange_kind(stomp_b200_engine* e, char* note, size_t note_capacity);
 
 /* ---- measurement ----------------------------------------------------------------------------------- */
 enum stomp_b200_kernel {
@@ -281,6 +287,10 @@ int stomp_b200_set_timeline(stomp_b200_engine* e, int32_t on);
 int stomp_b200_get_timeline(stomp_b200_engine* e, int32_t max_iterations, double* begin_end_us, int32_t* num_iterations);
 /* total kernel launches issued by this engine since creation */
 int64_t stomp_b200_launch_count(const stomp_b200_engine* e);
+/* iterations that ran as one cudaGraphLaunch: steady-state iterations of the on-device-sampler loop (no rollout reuse, no
+ * read-back tensors kept) are captured once and replayed; their kernels are counted in stomp_b200_launch_count as usual.
+ * STOMP_B200_GRAPH=0 in the environment at stomp_b200_create switches the replay off. */
+int64_t stomp_b200_graph_replays(const stomp_b200_engine* e);
 /* device-side timing of a region on the engine's stream: begin / end record events, end returns ms */
 int stomp_b200_timer_begin(stomp_b200_engine* e);
 int stomp_b200_timer_end(stomp_b200_engine* e, double* elapsed_ms);

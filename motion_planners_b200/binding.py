@@ -34,8 +34,8 @@ SYMBOLS = [
     "stomp_b200_host_initial_trajectory", "stomp_b200_begin_solve", "stomp_b200_iterate",
     "stomp_b200_next_num_generated", "stomp_b200_run", "stomp_b200_solve", "stomp_b200_finish_solve", "stomp_b200_num_rollouts",
     "stomp_b200_get_tensor", "stomp_b200_evaluate_states", "stomp_b200_sphere_centres", "stomp_b200_comm_unique_id",
-    "stomp_b200_comm_init", "stomp_b200_set_profiling", "stomp_b200_kernel_stats", "stomp_b200_reset_kernel_stats",
-    "stomp_b200_set_timeline", "stomp_b200_get_timeline", "stomp_b200_launch_count", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
+    "stomp_b200_comm_init", "stomp_b200_exchange_kind", "stomp_b200_set_profiling", "stomp_b200_kernel_stats", "stomp_b200_reset_kernel_stats",
+    "stomp_b200_set_timeline", "stomp_b200_get_timeline", "stomp_b200_launch_count", "stomp_b200_graph_replays", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
     "stomp_b200_state_kernel_kind", "stomp_b200_state_kernel_source", "stomp_b200_codegen_selftest",
     "stomp_b200_set_cost_cumulation", "stomp_b200_set_self_collision",
     "stomp_b200_build_sdf_primitives", "stomp_b200_build_sdf_occupancy", "stomp_b200_get_sdf",
@@ -121,8 +121,12 @@ def lib():
         L.stomp_b200_set_timeline.argtypes = [vp, C.c_int32]
         L.stomp_b200_get_timeline.argtypes = [vp, C.c_int32, dp, ip]
         L.stomp_b200_launch_count.argtypes = [vp]
+        L.stomp_b200_graph_replays.argtypes = [vp]
+        L.stomp_b200_graph_replays.restype = C.c_int64
         L.stomp_b200_state_kernel_kind.argtypes = [vp, C.c_char_p, C.c_size_t]
         L.stomp_b200_state_kernel_kind.restype = C.c_int32
+        L.stomp_b200_exchange_kind.argtypes = [vp, C.c_char_p, C.c_size_t]
+        L.stomp_b200_exchange_kind.restype = C.c_int32
         L.stomp_b200_state_kernel_source.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.stomp_b200_codegen_selftest.argtypes = [C.c_char_p, C.c_size_t]
         L.stomp_b200_set_cost_cumulation.argtypes = [vp, C.c_int32]
@@ -414,6 +418,14 @@ class Engine:
         buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
         self._check(lib().stomp_b200_comm_init(self.h, buf), "stomp_b200_comm_init")
 
+    def exchange_kind(self):
+        """("peer" | "nccl" | "none", note): how a rollout-sharded engine exchanges its per-iteration scalars."""
+        note = C.create_string_buffer(1024)
+        rc = lib().stomp_b200_exchange_kind(self.h, note, len(note))
+        if rc < 0:
+            self._check(rc, "stomp_b200_exchange_kind")
+        return {2: "peer", 1: "nccl"}.get(rc, "none"), note.value.decode()
+
     def set_profiling(self, on):
         self._check(lib().stomp_b200_set_profiling(self.h, int(on)), "stomp_b200_set_profiling")
 
@@ -440,6 +452,9 @@ class Engine:
 
     def launch_count(self):
         return lib().stomp_b200_launch_count(self.h)
+
+    def graph_replays(self):
+        return lib().stomp_b200_graph_replays(self.h)
 
     def set_cost_cumulation(self, use_cumulative_costs: bool):
         """stomp::Stomp::setCostCumulation."""

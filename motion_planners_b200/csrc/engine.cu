@@ -132,6 +132,31 @@ struct stomp_b200_engine {
     cudaStream_t rows_stream = nullptr;      // control-cost rows, side by side with the state kernel
     cudaEvent_t ev_sampled = nullptr, ev_rows = nullptr;
     bool noiseless_pending = false;          // ev_noiseless recorded and not yet waited for by the main stream
+    // The noise-less rollout of iteration i is LAUNCHED at the start of iteration i + 1 (or by the first call that needs its
+    // result), not at the end of i: on the device nothing changes — it still runs on the side stream under the next
+    // sampling — but an iteration then has the fork / join shape [noise-less of i-1 || sample, cost of i] -> update of i
+    // that a CUDA graph can hold.
+    bool nl_deferred = false;
+    LoopParams nl_lp;                        // parameters of the iteration whose noise-less rollout is owed
+    // steady-state iterations replayed from CUDA graphs (iterate_async): one per (honour_stop, noise-less rollout owed)
+    struct IterationGraph {
+        cudaGraphExec_t exec = nullptr;
+        int gen = -1, n = -1;                            // shape the graph was captured for
+        unsigned long long config_epoch = 0;
+        int64_t launches = 0;                            // kernel nodes (what a replay adds to launch_count)
+        int num_rollouts = 0, last_gen = 0, last_local = 0, last_noiseless_slot = -1, last_wblocks = 1;   // host bookkeeping after the iteration
+        bool last_noise_from_rollouts = false, peer = false;
+        LoopParams nl_lp;
+    };
+    IterationGraph graphs[2][2];
+    unsigned long long config_epoch = 1;     // bumped by every setter whose values are baked into kernel parameters
+    bool graphs_allowed = true;              // STOMP_B200_GRAPH=0 at creation switches the replay off
+    int eligible_streak = 0;                 // graph-eligible iterations run un-captured since the configuration last changed
+    unsigned long long streak_epoch = 0;
+    uint32_t* d_counters = nullptr;          // [0] iteration, [1] exchange epoch (LoopParams::counters)
+    long long dev_iteration_next = -1;       // value counters[0] will hold when the queued work has run; -1 unknown
+    long long dev_epoch_next = -1;           // likewise counters[1] (the epoch of the LAST exchange queued)
+    int64_t graph_launches = 0;
     double* d_theta_all_init = nullptr;   // policy as uploaded by set_policy (restored by begin_solve? no: the policy persists)
 
     // PolicyImprovement bookkeeping (PolicyImprovement.cpp:170-186)
@@ -170,6 +195,16 @@ struct stomp_b200_engine {
     long long timeline_count = 0;
 
     ncclComm_t comm = nullptr;
+    // rollout sharding over peer-mapped mailboxes (kernels.cuh: weights_update_peer_kernel); NCCL stays the bootstrap, the
+    // read-back gather and the fallback (STOMP_B200_EXCHANGE=nccl, or cudaIpc unavailable)
+    PeerExchange px;
+    bool peer_ready = false;
+    uint32_t peer_epoch = 0, barrier_ticket = 0;
+    void* peer_box_own = nullptr;
+    std::vector<void*> peer_opened;
+    int32_t* d_peer_error = nullptr; int32_t* h_peer_error = nullptr;
+    std::string exchange_note = "single GPU: no exchange";
+    bool tables_gathered = true;             // rollout-indexed tables complete on this rank (peer mode gathers them lazily for read-backs)
 
     // grow-only scratch of stomp_b200_evaluate_states
     double* eval_theta = nullptr; double* eval_cost = nullptr; uint8_t* eval_verdict = nullptr; uint8_t* eval_valid = nullptr;
@@ -448,7 +483,49 @@ void resolve_state_kernel(stomp_b200_engine* e)
     }
 }
 
-int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop)
+// the state kernel on the T noise-less states + noiseless_rollout_kernel (K10 + the wrapper's stop rule) for the iteration
+// recorded in e->nl_lp, on the side stream, behind everything queued on the main stream so far
+int launch_noiseless(stomp_b200_engine* e)
+{
+    const LoopParams& lp = e->nl_lp;
+    e->nl_deferred = false;
+    CUDA_TRY(e, cudaEventRecord(e->ev_applied, e->stream));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->side_stream, e->ev_applied, 0));
+    const size_t smem = sizeof(double) * ((size_t)e->D * e->N + e->T + e->sumw);
+    e->launch_count++;
+    e->kernel_launches[STOMP_B200_KERNEL_APPLY]++;
+    int states_done = 0;
+    if (e->self_pairs.n > 0 || e->spec) {
+        // the verdicts of the T noise-less states from the specialised state kernel, reading the padded policy rows in
+        // place (2.5x faster than the generic FK inside noiseless_rollout_kernel, which sits at the end of every
+        // isolated iteration)
+        StateKernelArgs a;
+        a.rollouts = lp.theta_all + kPad; a.state_costs = lp.nl_state; a.verdicts = lp.nl_verdict; a.validity = lp.nl_valid;
+        a.sums = nullptr; a.s_compact = nullptr; a.stop = lp.stop; a.tile_counter = nullptr; a.timeline = nullptr;
+        a.T = lp.T; a.D = lp.D; a.slots = 1; a.gslots = 1; a.sumw = lp.sumw; a.num_gen = 1; a.gen_offset = 0;
+        a.honour_stop = lp.honour_stop; a.debug_skip = 0;
+        a.row_stride = lp.N; a.rollout_stride = (int64_t)lp.D * lp.N;
+        if (e->self_pairs.n > 0) {
+            launch_states_self_collision(e, a, dim3((lp.T + 127) / 128, e->Q), e->side_stream);
+            if (int rc = check_launch(e, "states_self_collision_kernel")) return rc;
+            e->launch_count++;
+        } else {
+            void* args[] = {&a, &e->robot, &e->sdf};
+            const int bt = e->spec->block_threads;
+            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + bt - 1) / bt, e->Q), dim3(bt), args, 0, e->side_stream));
+            e->launch_count++;
+        }
+        states_done = 1;
+    }
+    noiseless_rollout_kernel<<<e->Q, 256, smem, e->side_stream>>>(lp, e->robot, e->sdf, states_done);
+    if (int rc = check_launch(e, "noiseless_rollout_kernel")) return rc;
+    CUDA_TRY(e, cudaEventRecord(e->ev_noiseless, e->side_stream));
+    e->noiseless_pending = true;
+    return 0;
+}
+
+
+int iterate_body(stomp_b200_engine* e, int iteration, int mode, int honour_stop, bool on_graph)
 {
     const stomp_b200_config& c = e->cfg;
     const int world = c.shard_mode == 0 ? c.world_size : 1;
@@ -479,6 +556,10 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     lp.honour_stop = honour_stop;
     lp.iteration = iteration;
     lp.store_unit = c.keep_debug_tensors;
+    lp.counters = on_graph ? e->d_counters : nullptr;
+    // the noise-less rollout of the previous iteration: side stream, under this iteration's sampling and costs
+    if (e->nl_deferred)
+        if (int rc = launch_noiseless(e)) return rc;
     if (e->timeline_on) {
         lp.timeline = e->d_timeline + (size_t)(e->timeline_count % kTimelineRing) * kTimelineKernels * 2;
         e->timeline_count++;
@@ -525,8 +606,11 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     const bool fused_rows = banded && !lp.Mproj && rows_shape_is_shipped(e, lp);
     // the shipped large-K loop (fused sampler, fused weights / update kernel, nothing reads `noise` back): the noise
     // tensor is not materialised — weights_update_kernel subtracts theta from the rollout rows it streams
+    // rollout sharding: both exchanges inside weights_update_peer_kernel over the peer-mapped mailboxes (every rank takes
+    // the same decision: the flags involved are set alike on all ranks)
+    const bool peer = world > 1 && e->peer_ready && !e->profiling && c.use_cumulative_costs && e->fuse_weights_allowed;
     {
-        const bool fuse_weights_ahead = e->fuse_weights_allowed && world == 1 && !e->profiling && !e->reuse_possible && reused == 0 && c.use_cumulative_costs;
+        const bool fuse_weights_ahead = e->fuse_weights_allowed && (world == 1 || peer) && !e->profiling && !e->reuse_possible && reused == 0 && c.use_cumulative_costs;
         lp.noise_from_rollouts = (fused_rows && fuse_weights_ahead && !c.keep_debug_tensors && !lp.control_costs && !lp.proj) ? 1 : 0;
         static const bool lean_allowed = !(std::getenv("STOMP_B200_LEAN_NOISE") && std::strcmp(std::getenv("STOMP_B200_LEAN_NOISE"), "0") == 0);
         if (!lean_allowed) lp.noise_from_rollouts = 0;
@@ -646,19 +730,29 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     }
 
     // ---- exchange 1: per-rollout cost scalars ----
-    if (world > 1) {
-        if (!e->comm) return fail(e, STOMP_B200_ERR_NOT_READY, "world_size > 1 needs stomp_b200_comm_init");
+    if (world > 1 && !e->comm) return fail(e, STOMP_B200_ERR_NOT_READY, "world_size > 1 needs stomp_b200_comm_init");
+    if (world > 1 && !peer) {
+        e->tables_gathered = true;
         const size_t count = (size_t)gen_local * e->sumw;
         NCCL_TRY(e, g_nccl.AllGather(lp.sums + (size_t)c.rank * count, lp.sums, count, ncclFloat64, e->comm, e->stream));
     }
 
     // one launch for K7-K9 when nothing sits between them (no exchange, no reused rollouts, no per-kernel profiling)
     const bool per_timestep = !c.use_cumulative_costs;
-    const bool fuse_weights = e->fuse_weights_allowed && world == 1 && !e->profiling && !e->reuse_possible && reused == 0 && !per_timestep;
+    const bool fuse_weights = e->fuse_weights_allowed && (world == 1 || peer) && !e->profiling && !e->reuse_possible && reused == 0 && !per_timestep;
     if (lp.noise_from_rollouts && !fuse_weights) return fail(e, STOMP_B200_ERR_CUDA, "internal: noise not materialised but the fused update kernel is not in use");
     const int nchunks = std::max(1, (lp.num_local + lp.chunk - 1) / lp.chunk);
     lp.nchunks = nchunks;
-    if (fuse_weights) {
+    if (peer) {
+        lp.wblocks = 1;
+        e->px.epoch = ++e->peer_epoch;
+        e->px.epoch_ptr = on_graph ? e->d_counters + 1 : nullptr;
+        e->tables_gathered = false;
+        const size_t smem = sizeof(double) * std::max<size_t>(2 * (size_t)lp.chunk, (size_t)e->T + 2);
+        Scope sc(e, STOMP_B200_KERNEL_UPDATE);
+        weights_update_peer_kernel<<<dim3(lp.nchunks * e->D), kUpdateThreads, smem, e->stream>>>(lp, e->px);
+        if (int rc = check_launch(e, "weights_update_peer_kernel")) return rc;
+    } else if (fuse_weights) {
         lp.wblocks = 1;
         const size_t smem = sizeof(double) * std::max<size_t>(2 * (size_t)lp.chunk, (size_t)e->T + 2);
         Scope sc(e, STOMP_B200_KERNEL_UPDATE);
@@ -704,41 +798,10 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     }
     e->last_wblocks = lp.wblocks;
     e->last_noise_from_rollouts = lp.noise_from_rollouts != 0;
-    // ---- noise-less rollout (K10) on the side stream: overlaps the next iteration's sampling and costs ----
-    {
-        CUDA_TRY(e, cudaEventRecord(e->ev_applied, e->stream));
-        CUDA_TRY(e, cudaStreamWaitEvent(e->side_stream, e->ev_applied, 0));
-        const size_t smem = sizeof(double) * ((size_t)e->D * e->N + e->T + e->sumw);
-        e->launch_count++;
-        e->kernel_launches[STOMP_B200_KERNEL_APPLY]++;
-        int states_done = 0;
-        if (e->self_pairs.n > 0 || e->spec) {
-            // the verdicts of the T noise-less states from the specialised state kernel, reading the padded policy rows in
-            // place (2.5x faster than the generic FK inside noiseless_rollout_kernel, which sits at the end of every
-            // isolated iteration)
-            StateKernelArgs a;
-            a.rollouts = lp.theta_all + kPad; a.state_costs = lp.nl_state; a.verdicts = lp.nl_verdict; a.validity = lp.nl_valid;
-            a.sums = nullptr; a.s_compact = nullptr; a.stop = lp.stop; a.tile_counter = nullptr; a.timeline = nullptr;
-            a.T = lp.T; a.D = lp.D; a.slots = 1; a.gslots = 1; a.sumw = lp.sumw; a.num_gen = 1; a.gen_offset = 0;
-            a.honour_stop = lp.honour_stop; a.debug_skip = 0;
-            a.row_stride = lp.N; a.rollout_stride = (int64_t)lp.D * lp.N;
-            if (e->self_pairs.n > 0) {
-                launch_states_self_collision(e, a, dim3((lp.T + 127) / 128, e->Q), e->side_stream);
-                if (int rc = check_launch(e, "states_self_collision_kernel")) return rc;
-                e->launch_count++;
-            } else {
-                void* args[] = {&a, &e->robot, &e->sdf};
-                const int bt = e->spec->block_threads;
-                CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + bt - 1) / bt, e->Q), dim3(bt), args, 0, e->side_stream));
-                e->launch_count++;
-            }
-            states_done = 1;
-        }
-        noiseless_rollout_kernel<<<e->Q, 256, smem, e->side_stream>>>(lp, e->robot, e->sdf, states_done);
-        if (int rc = check_launch(e, "noiseless_rollout_kernel")) return rc;
-        CUDA_TRY(e, cudaEventRecord(e->ev_noiseless, e->side_stream));
-        e->noiseless_pending = true;
-    }
+    // ---- noise-less rollout (K10): owed; launched on the side stream by the next iteration or the next join ----
+    e->nl_lp = lp;
+    e->nl_deferred = true;
+    if (on_graph && !peer) ++e->peer_epoch;       // the sampler advances counters[1] on every replayed iteration: keep the host's mirror in step
 
     e->num_rollouts = n;
     e->last_gen = gen_local;
@@ -746,6 +809,220 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     e->last_noiseless_slot = lp.noiseless_slot;
     e->noiseless_valid = true;
     if (c.use_noise_adaptation) e->adapted_valid = true;
+    return 0;
+}
+
+__global__ void set_counters_kernel(uint32_t* counters, uint32_t iteration, uint32_t epoch)
+{
+    counters[0] = iteration;
+    counters[1] = epoch;
+}
+
+// host state an iteration changes (restored when a capture has to be abandoned)
+struct HostIterationState {
+    int num_rollouts, last_gen, last_local, last_noiseless_slot, last_wblocks, cur;
+    bool last_noise_from_rollouts, noiseless_valid, adapted_valid, nl_deferred, noiseless_pending, edge_dirty, tables_gathered;
+    uint32_t peer_epoch;
+    int64_t launch_count;
+    LoopParams nl_lp, base;
+    void save(const stomp_b200_engine* e)
+    {
+        num_rollouts = e->num_rollouts; last_gen = e->last_gen; last_local = e->last_local; last_noiseless_slot = e->last_noiseless_slot;
+        last_wblocks = e->last_wblocks; cur = e->cur; last_noise_from_rollouts = e->last_noise_from_rollouts;
+        noiseless_valid = e->noiseless_valid; adapted_valid = e->adapted_valid; nl_deferred = e->nl_deferred;
+        noiseless_pending = e->noiseless_pending; edge_dirty = e->edge_dirty; tables_gathered = e->tables_gathered;
+        peer_epoch = e->peer_epoch; launch_count = e->launch_count; nl_lp = e->nl_lp; base = e->base;
+    }
+    void restore(stomp_b200_engine* e) const
+    {
+        e->num_rollouts = num_rollouts; e->last_gen = last_gen; e->last_local = last_local; e->last_noiseless_slot = last_noiseless_slot;
+        e->last_wblocks = last_wblocks; e->cur = cur; e->last_noise_from_rollouts = last_noise_from_rollouts;
+        e->noiseless_valid = noiseless_valid; e->adapted_valid = adapted_valid; e->nl_deferred = nl_deferred;
+        e->noiseless_pending = noiseless_pending; e->edge_dirty = edge_dirty; e->tables_gathered = tables_gathered;
+        e->peer_epoch = peer_epoch; e->launch_count = launch_count; e->nl_lp = nl_lp; e->base = base;
+    }
+};
+
+// One Stomp::runSingleIteration for all local queries, queued on the stream (no host synchronisation).  Steady-state
+// iterations of the shipped large-K loop — on-device sampler, fused weights / update kernel (single GPU or peer exchange),
+// no rollout reuse, nothing per-iteration left in the kernel parameters — are captured ONCE into a CUDA graph with the shape
+//     [noise-less rollout of the previous iteration || sampler -> state kernel] -> weights / update
+// and replayed with one cudaGraphLaunch: the kernel-to-kernel launch gaps and the host's per-launch cost (which bounds a
+// rollout shard of a few hundred rollouts) go away.  The iteration number and the exchange epoch are device-side counters
+// then (LoopParams::counters).  Everything else runs iterate_body directly.
+int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop)
+{
+    const stomp_b200_config& c = e->cfg;
+    const int world = c.shard_mode == 0 ? c.world_size : 1;
+    bool eligible = e->graphs_allowed && e->d_counters && mode == kNoisePhilox && !e->profiling && !e->timeline_on && !e->reuse_possible &&
+                    e->noiseless_valid && c.use_cumulative_costs && !c.keep_debug_tensors && !e->edge_dirty && !c.use_projection &&
+                    e->base.Lband != nullptr && (e->sampler_mode == 0 || e->sampler_mode == 3) && e->fuse_weights_allowed &&
+                    (world == 1 || e->peer_ready) && c.num_rollouts_per_iteration % world == 0 &&
+                    !e->noiseless_pending && (!e->nl_deferred || e->nl_lp.honour_stop == honour_stop);
+    if (eligible && !e->adapted_valid)          // sigma is a per-iteration kernel parameter unless it does not decay
+        for (int d = 0; d < e->D; ++d) eligible = eligible && c.noise_decay[d] == 1.0;
+    if (!eligible) return iterate_body(e, iteration, mode, honour_stop, false);
+    if (e->streak_epoch != e->config_epoch) { e->streak_epoch = e->config_epoch; e->eligible_streak = 0; }
+    if (e->eligible_streak < 2) {               // every kernel of the steady iteration has run before anything is captured
+        e->eligible_streak++;
+        return iterate_body(e, iteration, mode, honour_stop, false);
+    }
+    const int gen = c.num_rollouts_per_iteration, n = gen + 1;
+    stomp_b200_engine::IterationGraph& g = e->graphs[honour_stop ? 1 : 0][e->nl_deferred ? 1 : 0];
+    if (e->dev_iteration_next != iteration || e->dev_epoch_next != (long long)e->peer_epoch) {
+        set_counters_kernel<<<1, 1, 0, e->stream>>>(e->d_counters, (uint32_t)iteration, e->peer_epoch);
+        e->launch_count++;
+        if (int rc = check_launch(e, "set_counters_kernel")) return rc;
+    }
+    if (!g.exec || g.config_epoch != e->config_epoch || g.gen != gen || g.n != n) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        HostIterationState before;
+        before.save(e);
+        cudaGraph_t graph = nullptr;
+        cudaError_t err = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+        int rc = 0;
+        if (err == cudaSuccess) {
+            rc = iterate_body(e, iteration, mode, honour_stop, true);
+            err = cudaStreamEndCapture(e->stream, &graph);
+            if (err == cudaSuccess && rc == 0) err = cudaGraphInstantiate(&g.exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (err != cudaSuccess || rc != 0) {    // no graph on this engine: run the iteration directly from the saved state
+            (void)cudaGetLastError();
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            before.restore(e);
+            e->graphs_allowed = false;
+            e->dev_iteration_next = e->dev_epoch_next = -1;
+            return iterate_body(e, iteration, mode, honour_stop, false);
+        }
+        g.config_epoch = e->config_epoch; g.gen = gen; g.n = n;
+        g.launches = e->launch_count - before.launch_count;
+        g.num_rollouts = e->num_rollouts; g.last_gen = e->last_gen; g.last_local = e->last_local;
+        g.last_noiseless_slot = e->last_noiseless_slot; g.last_wblocks = e->last_wblocks;
+        g.last_noise_from_rollouts = e->last_noise_from_rollouts; g.peer = world > 1;
+        g.nl_lp = e->nl_lp;
+    } else {
+        // replay: the host bookkeeping the body would have done
+        ++e->peer_epoch;
+        e->launch_count += g.launches;
+        e->num_rollouts = g.num_rollouts; e->last_gen = g.last_gen; e->last_local = g.last_local;
+        e->last_noiseless_slot = g.last_noiseless_slot; e->last_wblocks = g.last_wblocks;
+        e->last_noise_from_rollouts = g.last_noise_from_rollouts;
+        if (g.peer) e->tables_gathered = false;
+        e->noiseless_valid = true;
+        if (c.use_noise_adaptation) e->adapted_valid = true;
+        e->noiseless_pending = false;
+        e->nl_lp = g.nl_lp; e->nl_lp.iteration = iteration;
+        e->nl_deferred = true;
+    }
+    CUDA_TRY(e, cudaGraphLaunch(g.exec, e->stream));
+    e->graph_launches++;
+    e->dev_iteration_next = (long long)iteration + 1;
+    e->dev_epoch_next = (long long)e->peer_epoch;
+    return 0;
+}
+
+// Peer-exchange mode leaves the rollout-indexed tables (sums, probabilities, total costs) rank-local: nothing on the data
+// path needs them in full.  Read-backs do, so stomp_b200_get_tensor completes them first — a COLLECTIVE call in that mode
+// (every rank asks for the same tensors in the same order; tests and bench.py's parity check do).
+int gather_tables_for_readback(stomp_b200_engine* e)
+{
+    if (e->tables_gathered || !e->comm) return 0;
+    const stomp_b200_config& c = e->cfg;
+    const size_t gl = (size_t)e->last_gen;
+    const LoopParams& b = e->base;
+    NCCL_TRY(e, g_nccl.AllGather(b.sums + (size_t)c.rank * gl * e->sumw, b.sums, gl * e->sumw, ncclFloat64, e->comm, e->stream));
+    NCCL_TRY(e, g_nccl.AllGather(b.prob + (size_t)c.rank * gl * e->D, b.prob, gl * e->D, ncclFloat64, e->comm, e->stream));
+    NCCL_TRY(e, g_nccl.AllGather(b.fprob + (size_t)c.rank * gl * e->D, b.fprob, gl * e->D, ncclFloat64, e->comm, e->stream));
+    NCCL_TRY(e, g_nccl.AllGather(b.total_cost + (size_t)c.rank * gl, b.total_cost, gl, ncclFloat64, e->comm, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->tables_gathered = true;
+    return 0;
+}
+
+void release_peer_exchange(stomp_b200_engine* e)
+{
+    for (void* p : e->peer_opened) cudaIpcCloseMemHandle(p);
+    e->peer_opened.clear();
+    if (e->peer_box_own) cudaFree(e->peer_box_own);
+    e->peer_box_own = nullptr;
+    e->peer_ready = false;
+}
+
+// Maps every rank's mailbox into this process (cudaIpc; the handles travel through one ncclAllGather).  All ranks switch
+// to the peer exchange together or not at all: the outcome is agreed with an all-reduce(min).  On any failure the NCCL
+// exchange stays in place and exchange_note says why.
+int setup_peer_exchange(stomp_b200_engine* e)
+{
+    const stomp_b200_config& c = e->cfg;
+    const int W = c.world_size;
+    e->exchange_note = "NCCL all-gather + all-reduce";
+    if (const char* x = std::getenv("STOMP_B200_EXCHANGE"))
+        if (std::strcmp(x, "nccl") == 0) { e->exchange_note += " (STOMP_B200_EXCHANGE=nccl)"; return 0; }
+    if (W > kMaxPeers) { e->exchange_note += " (more than 8 ranks)"; return 0; }
+    const size_t bytes = peer_box_bytes(W, e->D, e->T);
+    int ok = 1;
+    std::string why;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof mine);
+    if (cudaMalloc(&e->peer_box_own, bytes) != cudaSuccess) { ok = 0; why = "cudaMalloc of the mailbox failed"; (void)cudaGetLastError(); }
+    if (ok && cudaMemsetAsync(e->peer_box_own, 0, bytes, e->stream) != cudaSuccess) { ok = 0; why = "cudaMemset"; (void)cudaGetLastError(); }
+    if (ok && cudaIpcGetMemHandle(&mine, e->peer_box_own) != cudaSuccess) { ok = 0; why = "cudaIpcGetMemHandle failed"; (void)cudaGetLastError(); }
+    // handles of all ranks (64 bytes each) + one int32 status per rank
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    const size_t rec = 64 + 16;
+    unsigned char* d_rec = nullptr;
+    CUDA_TRY(e, cudaMalloc(&d_rec, rec * W));
+    std::vector<unsigned char> h_rec(rec * W, 0);
+    std::memcpy(h_rec.data() + rec * c.rank, &mine, 64);
+    std::memcpy(h_rec.data() + rec * c.rank + 64, &ok, sizeof(int));
+    cudaError_t err = cudaMemcpyAsync(d_rec + rec * c.rank, h_rec.data() + rec * c.rank, rec, cudaMemcpyHostToDevice, e->stream);
+    if (err != cudaSuccess) { cudaFree(d_rec); e->last_error = "peer exchange: staging copy failed"; return STOMP_B200_ERR_CUDA; }
+    ncclResult_t nr = g_nccl.AllGather(d_rec + rec * c.rank, d_rec, rec, ncclChar, e->comm, e->stream);
+    if (nr != ncclSuccess) { cudaFree(d_rec); e->last_error = std::string("peer exchange: ncclAllGather: ") + g_nccl.GetErrorString(nr); return STOMP_B200_ERR_NCCL; }
+    err = cudaMemcpyAsync(h_rec.data(), d_rec, rec * W, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) { cudaFree(d_rec); e->last_error = "peer exchange: handle read-back failed"; return STOMP_B200_ERR_CUDA; }
+    for (int r = 0; r < W && ok; ++r) {
+        int theirs = 0;
+        std::memcpy(&theirs, h_rec.data() + rec * r + 64, sizeof(int));
+        if (!theirs) { ok = 0; why = "rank " + std::to_string(r) + " could not export its mailbox"; }
+    }
+    std::memset(&e->px, 0, sizeof(e->px));
+    for (int r = 0; r < W && ok; ++r) {
+        if (r == c.rank) { e->px.box[r] = static_cast<unsigned char*>(e->peer_box_own); continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, h_rec.data() + rec * r, 64);
+        void* mapped = nullptr;
+        if (cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            ok = 0; why = std::string("cudaIpcOpenMemHandle of rank ") + std::to_string(r) + ": " + cudaGetErrorString(cudaGetLastError());
+        } else {
+            e->peer_opened.push_back(mapped);
+            e->px.box[r] = static_cast<unsigned char*>(mapped);
+        }
+    }
+    // agreement: min over the ranks of "every mailbox is mapped here"
+    int32_t* d_ok = reinterpret_cast<int32_t*>(d_rec);
+    int32_t h_ok = ok;
+    err = cudaMemcpyAsync(d_ok, &h_ok, sizeof h_ok, cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) {
+        nr = g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, e->comm, e->stream);
+        if (nr != ncclSuccess) { cudaFree(d_rec); e->last_error = std::string("peer exchange: ncclAllReduce: ") + g_nccl.GetErrorString(nr); return STOMP_B200_ERR_NCCL; }
+        err = cudaMemcpyAsync(&h_ok, d_ok, sizeof h_ok, cudaMemcpyDeviceToHost, e->stream);
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(d_rec);
+    if (err != cudaSuccess) { e->last_error = "peer exchange: agreement failed"; return STOMP_B200_ERR_CUDA; }
+    if (!h_ok) {
+        release_peer_exchange(e);
+        e->exchange_note += " (peer mailboxes unavailable: " + (why.empty() ? std::string("another rank failed") : why) + ")";
+        return 0;
+    }
+    e->px.world = W; e->px.rank = c.rank; e->px.epoch = 0; e->px.epoch_ptr = nullptr; e->px.error = e->d_peer_error;
+    e->px.D = e->D; e->px.T = e->T;
+    e->peer_epoch = 0; e->barrier_ticket = 0;
+    e->peer_ready = true;
+    e->exchange_note = "peer mailboxes over NVLink (cudaIpc), both exchanges inside weights_update_peer_kernel";
     return 0;
 }
 
@@ -760,6 +1037,8 @@ int ready_to_solve(stomp_b200_engine* e)
 
 int join_side_stream(stomp_b200_engine* e)
 {
+    if (e->nl_deferred)
+        if (int rc = launch_noiseless(e)) return rc;
     if (e->noiseless_pending) {
         CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_noiseless, 0));
         e->noiseless_pending = false;
@@ -775,6 +1054,8 @@ int fetch_query_scalars(stomp_b200_engine* e)
     CUDA_TRY(e, cudaMemcpyAsync(e->h_scalars, e->d_scalars, e->scalar_bytes, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     resolve_profile(e);
+    if (e->peer_ready && *e->h_peer_error != 0)
+        return fail(e, STOMP_B200_ERR_NCCL, "peer exchange: a rank did not publish within 4 s (rank missing, or ranks not running the same iterations)");
     return 0;
 }
 
@@ -956,10 +1237,13 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     {
         // the per-query scalars the host reads back live in ONE device block, mirrored by one pinned block: a single
         // D2H copy per read-back.  Layout: [Q] nl_total | [Q] last_improvement | [Q] stop | [Q] iters_used | [Q] nl_valid
-        e->scalar_bytes = Q * (2 * sizeof(double) + 2 * sizeof(int32_t) + 1);
+        const size_t per_query_bytes = Q * (2 * sizeof(double) + 2 * sizeof(int32_t) + 1);
+        const size_t err_off = (per_query_bytes + 7) & ~(size_t)7;           // int32 flag of the peer exchange, after the per-query block
+        e->scalar_bytes = err_off + sizeof(int32_t);
         unsigned char* blk = nullptr;
         CREATE_TRY(dev_alloc(e, &blk, e->scalar_bytes + 16));
         e->d_scalars = blk;
+        e->d_peer_error = reinterpret_cast<int32_t*>(blk + err_off);
         b.nl_total = reinterpret_cast<double*>(blk);
         b.last_improvement = b.nl_total + Q;
         b.stop = reinterpret_cast<int32_t*>(b.last_improvement + Q);
@@ -969,7 +1253,19 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.old_cost, Q));
     CREATE_TRY(dev_alloc(e, &b.best_cost, Q));
     CREATE_TRY(dev_alloc(e, &e->d_order, Q * S));
-    b.chunk = 128;
+    // rollouts per CTA of the weights / update kernels: the kernels are latency chains (cost scan -> exp -> stream of the
+    // chunk's rows -> last-CTA reduction), so shorter chunks finish sooner — as long as the grid stays ONE wave (three
+    // 256-thread CTAs per SM at 80 registers).  Measured at K = 4096 on one GPU: 128 -> 14.2 us (231 CTAs), 64 -> 15.4 us
+    // (455 CTAs: a second wave), 32 -> 24.6 us; a rollout shard of 2048 / 512 rollouts gets 64 / 32.
+    {
+        cudaDeviceProp prop;
+        CREATE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+        e->num_sms = prop.multiProcessorCount;
+        int chunk = 128;
+        while (chunk > 32 && (long long)((S + chunk / 2 - 1) / (chunk / 2)) * (long long)D * (long long)Q <= 3LL * e->num_sms) chunk /= 2;
+        if (const char* ck = std::getenv("STOMP_B200_CHUNK")) { const int v = std::atoi(ck); if (v == 32 || v == 64 || v == 128) chunk = v; }
+        b.chunk = chunk;
+    }
     e->max_chunks = (int)((S + b.chunk - 1) / b.chunk);
     CREATE_TRY(dev_alloc(e, &b.partial, Q * e->max_chunks * D * (T + 2)));
     b.wblocks_cap = (int)((GS + 255) / 256);
@@ -979,6 +1275,8 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.s_compact, Q * GS));
     CREATE_TRY(dev_alloc(e, &b.c_compact, Q * D * GS));
     CREATE_TRY(dev_alloc(e, &b.tile_counter, 4));
+    CREATE_TRY(dev_alloc(e, &e->d_counters, 4));
+    if (const char* gr = std::getenv("STOMP_B200_GRAPH")) e->graphs_allowed = std::strcmp(gr, "0") != 0;
     CREATE_TRY(dev_alloc(e, &e->d_timeline, (size_t)kTimelineRing * kTimelineKernels * 2));
     b.world_size = world;
 
@@ -1018,6 +1316,9 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     e->h_stop = reinterpret_cast<int32_t*>(e->h_impr + Q);
     e->h_iters = e->h_stop + Q;
     e->h_valid = reinterpret_cast<uint8_t*>(e->h_iters + Q);
+    e->h_peer_error = reinterpret_cast<int32_t*>(e->h_scalars + (e->scalar_bytes - sizeof(int32_t)));
+    *e->h_peer_error = 0;
+    std::memset(&e->px, 0, sizeof(e->px));
     {
         cudaDeviceProp prop;
         CREATE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
@@ -1046,6 +1347,10 @@ int stomp_b200_destroy(stomp_b200_engine* e)
     if (e->rows_stream) cudaStreamSynchronize(e->rows_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     resolve_profile(e);
+    for (auto& row : e->graphs)
+        for (auto& g : row)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+    release_peer_exchange(e);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* p : e->allocations) cudaFree(p);
     if (e->d_sdf) cudaFree(e->d_sdf);
@@ -1123,6 +1428,7 @@ int stomp_b200_set_chain(stomp_b200_engine* e, int32_t num_joints, const double*
         if (r.joint[d].prismatic || !r.joint[d].fixed_rot_identity || r.joint[d].axis_kind == kAxisGeneral) r.simple_chain = 0;
     e->have_chain = true;
     e->spec_resolved = false;
+    e->config_epoch++;
     return STOMP_B200_OK;
 }
 
@@ -1164,6 +1470,7 @@ int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int3
     for (int d = 1; d <= STOMP_B200_MAX_DIMS; ++d) r.sphere_begin[d] = std::max(r.sphere_begin[d], r.sphere_begin[d - 1]);
     e->have_spheres = true;
     e->spec_resolved = false;
+    e->config_epoch++;
     e->self_pairs.n = 0;   // indices and radii of an earlier pair list no longer apply
     return STOMP_B200_OK;
 }
@@ -1174,6 +1481,7 @@ int stomp_b200_set_self_collision(stomp_b200_engine* e, int32_t num_pairs, const
     if (!e->have_spheres) return fail(e, STOMP_B200_ERR_NOT_READY, "stomp_b200_set_spheres comes first");
     const RobotParams& r = e->robot;
     const int S = r.num_spheres, D = e->D;
+    e->config_epoch++;
     if (num_pairs > S * (S - 1) / 2) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "more pairs than distinct sphere pairs");
     std::vector<int> link_of((size_t)S, 0);
     for (int d = 0; d < D; ++d)
@@ -1273,6 +1581,7 @@ static int adopt_sdf_geometry(stomp_b200_engine* e, const int32_t dims[3], const
     e->sdf_origin[0] = origin[0]; e->sdf_origin[1] = origin[1]; e->sdf_origin[2] = origin[2];
     e->sdf_voxel = voxel_size;
     e->spec_resolved = false;
+    e->config_epoch++;
     return STOMP_B200_OK;
 }
 
@@ -1473,6 +1782,7 @@ int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R, 
     CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.Lt), Lt.data(), sizeof(double) * Lt.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.Rband), band.data(), sizeof(double) * band.size(), cudaMemcpyHostToDevice));
     e->have_matrices = true;
+    e->config_epoch++;
     return STOMP_B200_OK;
 }
 
@@ -1488,6 +1798,7 @@ int stomp_b200_set_policy(stomp_b200_engine* e, int32_t query, const double* par
     for (size_t i = 0; i < (size_t)e->D * e->T; ++i)
         if (!(std::fabs(min_control_cost[i]) <= 1e6)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "min_control_cost holds a NaN, an infinity or a value beyond 1e6");
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (int rc = join_side_stream(e)) return rc;      // an owed noise-less rollout belongs to the policy as it is now
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     CUDA_TRY(e, cudaMemcpy(e->base.theta_all + (size_t)query * e->D * e->N, parameters_all, sizeof(double) * e->D * e->N, cudaMemcpyHostToDevice));
     CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.mincc) + (size_t)query * e->D * e->T, min_control_cost, sizeof(double) * e->D * e->T, cudaMemcpyHostToDevice));
@@ -1647,6 +1958,9 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
     const LoopParams& b = e->base;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     resolve_profile(e);
+    if (tensor == STOMP_B200_CUMULATIVE_COSTS || tensor == STOMP_B200_FULL_COSTS || tensor == STOMP_B200_TOTAL_COST ||
+        tensor == STOMP_B200_PROBABILITIES || tensor == STOMP_B200_FULL_PROBABILITIES)
+        if (int rc = gather_tables_for_readback(e)) return rc;
     const size_t Q = e->Q, T = e->T, D = e->D, N = e->N;
     const size_t nl = e->last_local;      // local rollouts of the last iteration
     const size_t ng = e->num_rollouts;    // rollouts in the rollout-indexed tables
@@ -1861,7 +2175,17 @@ int stomp_b200_comm_init(stomp_b200_engine* e, const void* id)
     ncclUniqueId uid;
     std::memcpy(&uid, id, sizeof(uid));
     NCCL_TRY(e, g_nccl.CommInitRank(&e->comm, e->cfg.world_size, uid, e->cfg.rank));
+    e->config_epoch++;
+    if (e->cfg.shard_mode == 0 && e->cfg.world_size > 1) return setup_peer_exchange(e);
     return STOMP_B200_OK;
+}
+
+int32_t stomp_b200_exchange_kind(stomp_b200_engine* e, char* note, size_t note_capacity)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (note && note_capacity) std::snprintf(note, note_capacity, "%s", e->exchange_note.c_str());
+    if (e->cfg.shard_mode != 0 || e->cfg.world_size <= 1 || !e->comm) return 0;
+    return e->peer_ready ? 2 : 1;
 }
 
 int stomp_b200_set_profiling(stomp_b200_engine* e, int32_t on)
@@ -1935,6 +2259,7 @@ int stomp_b200_reset_kernel_stats(stomp_b200_engine* e)
 }
 
 int64_t stomp_b200_launch_count(const stomp_b200_engine* e) { return e ? e->launch_count : 0; }
+int64_t stomp_b200_graph_replays(const stomp_b200_engine* e) { return e ? e->graph_launches : 0; }
 
 int stomp_b200_timer_begin(stomp_b200_engine* e)
 {
@@ -1942,6 +2267,13 @@ int stomp_b200_timer_begin(stomp_b200_engine* e)
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     if (int rc = join_side_stream(e)) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (e->peer_ready) {
+        // the ranks of a sharded engine start the timed region together: a device-side barrier over the mailboxes, so that
+        // no rank's bracket contains another rank's head start
+        peer_barrier_kernel<<<1, 32, 0, e->stream>>>(e->px, ++e->barrier_ticket);
+        e->launch_count++;
+        if (int rc = check_launch(e, "peer_barrier_kernel")) return rc;
+    }
     CUDA_TRY(e, cudaEventRecord(e->timer_a, e->stream));
     return STOMP_B200_OK;
 }
@@ -2054,5 +2386,6 @@ int stomp_b200_set_cost_cumulation(stomp_b200_engine* e, int32_t use_cumulative_
         if (!b.pt_minden) { if (int rc = dev_alloc(e, &b.pt_minden, Q * D * 2)) return rc; }
     }
     e->cfg.use_cumulative_costs = use_cumulative_costs ? 1 : 0;
+    e->config_epoch++;
     return STOMP_B200_OK;
 }

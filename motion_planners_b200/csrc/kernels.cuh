@@ -110,6 +110,12 @@ struct LoopParams {
     int32_t rows_mask;        // bit 0: write C_d (control-cost sums), bit 1: write n^T R n; 3 = both (one pass, M = I)
     int32_t per_timestep_minmax;   // per-time-step costs only: min / max per time step (variant at PolicyImprovement.cpp:518-528)
     int32_t noise_from_rollouts;   // the sampler did not write `noise`: weights_update_kernel forms rollouts - theta itself
+    // iterations replayed from a CUDA graph (engine.cu: GraphKey) cannot carry per-iteration kernel parameters: the
+    // iteration number (Philox counter) and the epoch of the peer exchange then live on the device.  counters[0] =
+    // iteration, read by the sampler and advanced by the weights / update kernel; counters[1] = exchange epoch, read by
+    // weights_update_peer_kernel and advanced by the sampler — reader and writer are never the same launch.  Null: the
+    // values in `iteration` / PeerExchange::epoch apply.
+    uint32_t* counters;
 };
 
 // the joint limits of OptimizationTask::filter: all the sampling kernels need of the robot (0.5 KB of kernel parameters
@@ -689,6 +695,7 @@ sample_rollouts_banded_kernel(const __grid_constant__ LoopParams p, const __grid
 {
     extern __shared__ __align__(16) double smem[];
     const int q = blockIdx.y;
+    if (p.counters && blockIdx.x == 0 && q == 0 && threadIdx.x == 0) p.counters[1] += 1u;    // next exchange epoch (graph replay)
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 0);
     const int T = p.T, D = p.D, N = p.N;
@@ -729,7 +736,7 @@ sample_rollouts_banded_kernel(const __grid_constant__ LoopParams p, const __grid
         // global column of this rollout and joint: the Philox counter of the contraction kernels
         const uint32_t gcol = (uint32_t)(((uint32_t)(p.query_offset + q) * (uint32_t)p.gen_global + (uint32_t)(p.gen_offset + k0 + lane)) * (uint32_t)D + (uint32_t)d);
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-        const uint32_t iteration = (uint32_t)p.iteration;
+        const uint32_t iteration = p.counters ? p.counters[0] : (uint32_t)p.iteration;
         double* dst = s_tile + lane * S;
         double* eps_row = p.epsilon + (((size_t)q * p.num_gen + (k0 + lane)) * D + d) * T;
         for (int g = warp; g < ngroups; g += kBandedThreads / 32) {
@@ -2064,6 +2071,7 @@ weights_update_kernel(const __grid_constant__ LoopParams p)
     __shared__ double scratch[32];
     __shared__ double s_half[128];
     const int d = blockIdx.y, q = blockIdx.z, c = blockIdx.x;
+    if (p.counters && c == 0 && d == 0 && q == 0 && threadIdx.x == 0) p.counters[0] += 1u;   // next iteration number (graph replay)
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 3);
     const int T = p.T, D = p.D, tid = threadIdx.x, n = p.num_rollouts;
@@ -2272,6 +2280,8 @@ __device__ __forceinline__ void apply_update_body(const LoopParams& p, int q, in
 {
     const int T = p.T, D = p.D, N = p.N;
     __syncthreads();
+    if (from_partials == 3) from_partials = 2;      // weights_update_peer_kernel: s_cols already holds the unnormalised sums over all ranks
+    else
     for (int t = threadIdx.x; t < T + 2; t += blockDim.x) {
         double u;
         if (from_partials) {
@@ -2341,6 +2351,247 @@ apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 4);
     apply_update_body(p, q, d, from_partials, nchunks, smem);
+    tls.end();
+}
+
+// =====================================================================================================
+// Rollout sharding without a collective library on the data path.  Every rank maps the
+// other ranks' MAILBOX (cudaIpc, engine.cu: setup_peer_exchange) and the two exchanges of an iteration happen inside ONE
+// kernel, weights_update_peer_kernel, as plain stores over NVLink and spins on the rank's own memory:
+//   A. the min / max of cumulative_costs_[d] over the rank's own rollouts (2 doubles per joint) -> every rank takes the
+//      min / max over the ranks: the same two numbers the single-GPU scan finds, so the weights are bit-identical;
+//   B. the rank's unnormalised partial sums [T + 2] per joint (update row, adaptation numerator, sum of the weights) ->
+//      every rank adds the rows in RANK ORDER (deterministic, identical on all ranks) and applies the update.
+// Transport: every double travels as two self-validating 8-byte words {epoch : 32 | half of the bits : 32} (the "LL"
+// scheme: an aligned 8-byte store is atomic, so a word whose tag equals the exchange's epoch IS the data).  No fence, no
+// separate flag, no release / acquire pair: one NVLink crossing per exchange.  (The first version — data, then
+// __threadfence_system, then a release flag — cost 13 us per iteration on two B200s: MEMBAR.SYS is slow.)  The epoch is
+// one per iteration, the same on every rank; slots are double buffered by its parity (a rank reaches exchange A of epoch
+// e + 2 only after every rank has published B of e + 1, i.e. after it finished reading epoch e).  A spin that lasts 4 s
+// sets the error flag, which every later wait honours: a missing rank costs seconds, never a hung GPU.
+// Mailbox layout (bytes from the base; W ranks, D joints, T time steps):
+//   A [2][W][D][2 doubles as 4 words] | B [2][W][D][T + 2 doubles as 2 (T + 2) words] | barrier [W] u32
+// =====================================================================================================
+constexpr int kMaxPeers = 8;
+struct PeerExchange {
+    unsigned char* box[kMaxPeers];   // mailbox of every rank, own included (own: plain device memory)
+    int32_t world, rank;
+    uint32_t epoch;                  // this iteration's exchange number (>= 1) unless epoch_ptr is set
+    const uint32_t* epoch_ptr;       // device-side epoch (iterations replayed from a CUDA graph), or null
+    int32_t* error;                  // device flag: a wait timed out
+    int32_t D, T;
+};
+__host__ __device__ inline size_t peer_off_b(int W, int D) { return (size_t)2 * W * D * 32; }
+__host__ __device__ inline size_t peer_off_barrier(int W, int D, int T) { return peer_off_b(W, D) + (size_t)2 * W * D * (T + 2) * 16; }
+__host__ __device__ inline size_t peer_box_bytes(int W, int D, int T) { return peer_off_barrier(W, D, T) + 64; }
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// waits until *flag has reached `epoch`; false (and the error flag) after 4 s, or at once when the flag is already set
+__device__ __forceinline__ bool peer_wait(const uint32_t* flag, uint32_t epoch, int32_t* error)
+{
+    unsigned long long t0 = 0;
+    int polls = 0;
+    while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+        if (++polls == 256) {
+            polls = 0;
+            if (*(volatile int32_t*)error) return false;
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) { atomicExch(error, 1); return false; }
+        }
+    }
+    return true;
+}
+// one double as two tagged words, 16 bytes at dst (16-byte aligned)
+__device__ __forceinline__ void ll_store(unsigned char* dst, double v, uint32_t epoch)
+{
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v), tag = (unsigned long long)epoch << 32;
+    const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+}
+// spins until both words at src carry `epoch`; 0.0 (and the error flag) after 4 s
+__device__ __forceinline__ double ll_load(const unsigned char* src, uint32_t epoch, int32_t* error)
+{
+    unsigned long long w0, w1, t0 = 0;
+    int polls = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+        if ((uint32_t)(w0 >> 32) == epoch && (uint32_t)(w1 >> 32) == epoch) break;
+        if (++polls == 256) {
+            polls = 0;
+            if (*(volatile int32_t*)error) return 0.0;
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) { atomicExch(error, 1); return 0.0; }
+        }
+    }
+    return __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+}
+
+// all ranks meet on the device (timer brackets of a sharded run start together); one warp
+__global__ void peer_barrier_kernel(const __grid_constant__ PeerExchange px, uint32_t ticket)
+{
+    const int r = threadIdx.x;
+    if (r >= px.world) return;
+    const size_t off = peer_off_barrier(px.world, px.D, px.T);
+    st_release_sys(reinterpret_cast<uint32_t*>(px.box[r] + off) + px.rank, ticket);
+    peer_wait(reinterpret_cast<const uint32_t*>(px.box[px.rank] + off) + r, ticket, px.error);
+}
+
+// K7 + K8 + K9 of a rollout-sharded engine (one query): weights_update_kernel with the two exchanges inside.
+// grid: nchunks * D CTAs in one dimension; the D CTAs that publish exchange A come first in dispatch order and no CTA
+// ever waits for another CTA of its own grid before publishing, so the spins cannot starve a publisher of an SM.
+__global__ void __launch_bounds__(kUpdateThreads)
+weights_update_peer_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ PeerExchange px)
+{
+    extern __shared__ double smem[];   // [chunk] weights, [chunk] weight * quad ; later [T + 2] column sums
+    __shared__ double scratch[32];
+    __shared__ double s_half[128];
+    __shared__ double s_mm[2 * kMaxPeers];
+    __shared__ int s_last;
+    const int q = 0;
+    if (p.counters && blockIdx.x == 0 && threadIdx.x == 0) p.counters[0] += 1u;              // next iteration number (graph replay)
+    if (query_frozen(p, q)) return;
+    TimelineScope tls(p, 3);
+    const int T = p.T, D = p.D, tid = threadIdx.x, W = px.world, rank = px.rank;
+    const int nchunks = p.nchunks;
+    int c, d;
+    if ((int)blockIdx.x < D) { c = 0; d = blockIdx.x; }
+    else { const int r = blockIdx.x - D; d = r / (nchunks - 1); c = 1 + (r - d * (nchunks - 1)); }
+    const uint32_t epoch = px.epoch_ptr ? __ldcg(px.epoch_ptr) : px.epoch;
+    const int parity = (int)(epoch & 1u);
+    const int half = tid >> 7, lt = tid & 127;
+    const int k_begin = c * p.chunk, k_end = min(p.num_local, (c + 1) * p.chunk);
+    const int nk = k_end - k_begin;
+    double* sp = smem;
+    double* sq = smem + p.chunk;
+    if (c == 0 && d == 0 && p.noiseless_slot >= 0) materialise_noiseless(p, q, tid, blockDim.x);
+
+    // ---- min / max of cumulative_costs_[d] over this rank's rollouts; exchange A ----
+    const double* S = p.s_compact + (size_t)q * p.gslots;
+    const double* C = p.c_compact + ((size_t)q * D + d) * p.gslots;
+    const double* nl = p.nl_sums + (size_t)q * p.sumw;
+    auto cum_of = [&](int g) { return (g == p.noiseless_gslot) ? 1.0 * (nl[0] + nl[1 + d]) : 1.0 * (S[g] + C[g]); };
+    double mn = 1e300, mx = -1e300;
+#pragma unroll 8
+    for (int k = tid; k < p.num_gen; k += kUpdateThreads) {
+        const double cum = cum_of(p.gen_offset + k);
+        mn = fmin(mn, cum); mx = fmax(mx, cum);
+    }
+    if (tid == 0 && p.noiseless_gslot >= 0) { const double cum = cum_of(p.noiseless_gslot); mn = fmin(mn, cum); mx = fmax(mx, cum); }
+    mn = block_reduce<1>(mn, scratch); mx = block_reduce<2>(mx, scratch);
+    const size_t slot_mine = ((size_t)parity * W + rank) * D + d;
+    if (c == 0 && tid < W && tid != rank) {
+        unsigned char* dst = px.box[tid] + slot_mine * 32;
+        ll_store(dst, mn, epoch);
+        ll_store(dst + 16, mx, epoch);
+    }
+    if (tid < W) {
+        double vmn = mn, vmx = mx;
+        if (tid != rank) {
+            const unsigned char* src = px.box[rank] + (((size_t)parity * W + tid) * D + d) * 32;
+            vmn = ll_load(src, epoch, px.error);
+            vmx = ll_load(src + 16, epoch, px.error);
+        }
+        s_mm[2 * tid] = vmn; s_mm[2 * tid + 1] = vmx;
+    }
+    __syncthreads();
+    for (int r = 0; r < W; ++r) { mn = fmin(mn, s_mm[2 * r]); mx = fmax(mx, s_mm[2 * r + 1]); }
+    double den = mx - mn;
+    if (den < 1e-8) den = 1e-8;
+    const double h = p.cost_scaling_h;
+
+    // ---- unnormalised weights of this chunk ----
+    double psum_part = 0.0;
+    for (int k = k_begin + tid; k < k_end; k += blockDim.x) {
+        const int g = (k == p.noiseless_slot) ? p.noiseless_gslot : p.gen_offset + k;
+        const double pr = 1.0 * exp(((-h) * (cum_of(g) - mn)) / den);      // importance_weight_ = 1
+        const size_t o = ((size_t)q * p.gslots + g) * D + d;
+        p.prob[o] = pr;
+        p.fprob[o] = pr;
+        // the noise-less rollout is replicated on every rank: only the first rank counts it in the sum of the weights
+        if (!(k == p.noiseless_slot && rank != 0)) psum_part += pr;
+        double w = pr, fq = 0.0;
+        if (k == p.noiseless_slot) w = 0.0;       // zero noise: contributes nothing (PolicyImprovement.cpp:407-410)
+        else if (p.use_noise_adaptation) fq = pr * p.sums[((size_t)q * p.gslots + g) * p.sumw + 1 + 2 * D + d];
+        sp[k - k_begin] = w;
+        sq[k - k_begin] = fq;
+        if (d == 0) {   // total_cost_ (:451-462)
+            const double* s = cost_row(p, q, g);
+            double cost = s[0];
+            for (int dd = 0; dd < D; ++dd) cost += s[1 + dd];
+            p.total_cost[(size_t)q * p.gslots + g] = cost;
+        }
+    }
+    __syncthreads();
+    double* out = p.partial + (((size_t)q * nchunks + c) * D + d) * (T + 2);
+    for (int t0 = 0; t0 < T; t0 += 128) {
+        const int t = t0 + lt;
+        double acc = 0.0;
+        if (t < T) {
+            const bool from_rollouts = p.noise_from_rollouts != 0;
+            const double* nz = (from_rollouts ? p.rollouts : p.noise) + (((size_t)q * p.slots + k_begin) * D + d) * T + t;
+            const double th_t = from_rollouts ? p.theta_all[((size_t)q * D + d) * p.N + kPad + t] : 0.0;
+            const size_t stride = (size_t)D * T;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = half;
+            for (; k + 30 < nk; k += 32) {       // rows k, k+2, ..., k+30
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = nz[(size_t)(k + 2 * u) * stride] - th_t;
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    a0 += v[u] * sp[k + 2 * u]; a1 += v[u + 1] * sp[k + 2 * u + 2];
+                    a2 += v[u + 2] * sp[k + 2 * u + 4]; a3 += v[u + 3] * sp[k + 2 * u + 6];
+                }
+            }
+            for (; k < nk; k += 2) a0 += (nz[(size_t)k * stride] - th_t) * sp[k];
+            acc = (a0 + a1) + (a2 + a3);
+        }
+        if (half == 1) s_half[lt] = acc;
+        __syncthreads();
+        if (half == 0 && t < T) out[t] = acc + s_half[lt];
+        __syncthreads();
+    }
+    double numer = 0.0;
+    for (int k = tid; k < nk; k += blockDim.x) numer += sq[k];
+    numer = block_reduce<0>(numer, scratch);
+    psum_part = block_reduce<0>(psum_part, scratch);
+    if (tid == 0) { out[T] = numer; out[T + 1] = psum_part; }
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(p.done_counter + (size_t)q * D + d, 1u) == (unsigned)nchunks - 1u) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        // ---- exchange B: this rank's sums in chunk order -> every mailbox; then all ranks' rows in rank order ----
+        const size_t offb = peer_off_b(W, D);
+        for (int t = tid; t < T + 2; t += blockDim.x) {
+            double mine = 0.0;
+            const double* col = p.partial + ((size_t)q * nchunks * D + d) * (T + 2) + t;
+            const size_t stride = (size_t)D * (T + 2);
+#pragma unroll 8
+            for (int cc = 0; cc < nchunks; ++cc) mine += __ldcg(col + (size_t)cc * stride);
+            for (int r = 0; r < W; ++r)
+                if (r != rank) ll_store(px.box[r] + offb + (slot_mine * (T + 2) + t) * 16, mine, epoch);
+            double u = 0.0;
+            for (int r = 0; r < W; ++r)
+                u += (r == rank) ? mine : ll_load(px.box[rank] + offb + ((((size_t)parity * W + r) * D + d) * (T + 2) + t) * 16, epoch, px.error);
+            smem[t] = u;
+        }
+        apply_update_body(p, q, d, 3, nchunks, smem);
+        if (tid == 0) p.done_counter[(size_t)q * D + d] = 0u;
+    }
     tls.end();
 }
 

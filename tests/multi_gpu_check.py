@@ -23,41 +23,62 @@ def main():
     dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     dev = f"cuda:{local}"
 
-    # ---- (a) rollout sharding ----
-    K, T = 64 * world, 60
-    pb = P.single_arm_problem(K=K, T=T, sdf_n=64)
-    single = binding.engine_for_problem(pb, device=local, keep_debug_tensors=True)
-    shard = binding.engine_for_problem(pb, device=local, world_size=world, rank=rank, shard_mode=0, keep_debug_tensors=True)
-    uid = binding.comm_unique_id() if rank == 0 else b""
-    shard.comm_init(sharding.broadcast_bytes(dist, uid, binding.COMM_ID_BYTES, dev))
-    single.begin_solve(); shard.begin_solve()
-    off, cnt = sharding.rollout_shard(K, world, rank)
-    for it in range(5):
-        c1, v1, s1 = single.iterate(it)
-        c2, v2, s2 = shard.iterate(it)
-        n, g = shard.num_rollouts()
-        assert g == cnt and n == K + (1 if it > 0 else 0), (n, g)
-        # the local shard of the generated rollouts is the matching slice of the single-GPU run
-        np.testing.assert_array_equal(shard.tensor("epsilon")[0], single.tensor("epsilon")[0][off:off + cnt])
-        np.testing.assert_allclose(shard.tensor("rollouts")[0][:cnt], single.tensor("rollouts")[0][off:off + cnt], rtol=1e-9, atol=1e-12)
-        np.testing.assert_array_equal(shard.tensor("verdicts")[0][:cnt], single.tensor("verdicts")[0][off:off + cnt])
-        # rollout-indexed tables are complete and identical on every rank
-        np.testing.assert_allclose(shard.tensor("total_cost")[0], single.tensor("total_cost")[0], rtol=1e-9)
-        np.testing.assert_allclose(shard.tensor("probabilities")[0], single.tensor("probabilities")[0], rtol=1e-9, atol=1e-300)
-        np.testing.assert_allclose(shard.tensor("updates")[0], single.tensor("updates")[0], rtol=1e-9, atol=1e-13)
-        np.testing.assert_allclose(shard.tensor("parameters")[0], single.tensor("parameters")[0], rtol=1e-9, atol=1e-12)
-        np.testing.assert_allclose(shard.tensor("stddevs")[0], single.tensor("stddevs")[0], rtol=1e-9)
-        np.testing.assert_allclose(c2, c1, rtol=1e-9)
-        assert bool(v1[0]) == bool(v2[0])
-        # every rank holds the same parameters bit for bit (all-reduce result is identical on all ranks)
-        mine = torch.from_numpy(shard.tensor("parameters")[0]).to(dev)
-        ref = mine.clone()
-        dist.broadcast(ref, 0)
-        assert torch.equal(mine, ref)
-    shard.run(5, 3)
-    r = shard.finish_solve()
-    assert r["iterations"][0] == 8
-    single.close(); shard.close()
+    # ---- (a) rollout sharding, with both transports of the two exchanges ----
+    kinds = []
+    for transport in ("default", "nccl"):
+        if transport == "nccl":
+            os.environ["STOMP_B200_EXCHANGE"] = "nccl"
+        else:
+            os.environ.pop("STOMP_B200_EXCHANGE", None)
+        K, T = 64 * world, 60
+        pb = P.single_arm_problem(K=K, T=T, sdf_n=64)
+        single = binding.engine_for_problem(pb, device=local, keep_debug_tensors=True)
+        shard = binding.engine_for_problem(pb, device=local, world_size=world, rank=rank, shard_mode=0, keep_debug_tensors=True)
+        uid = binding.comm_unique_id() if rank == 0 else b""
+        shard.comm_init(sharding.broadcast_bytes(dist, uid, binding.COMM_ID_BYTES, dev))
+        kinds.append(shard.exchange_kind())
+        if transport == "nccl":
+            assert kinds[-1][0] == "nccl", kinds[-1]
+        single.begin_solve(); shard.begin_solve()
+        off, cnt = sharding.rollout_shard(K, world, rank)
+        for it in range(5):
+            c1, v1, s1 = single.iterate(it)
+            c2, v2, s2 = shard.iterate(it)
+            n, g = shard.num_rollouts()
+            assert g == cnt and n == K + (1 if it > 0 else 0), (n, g)
+            # the local shard of the generated rollouts is the matching slice of the single-GPU run
+            np.testing.assert_array_equal(shard.tensor("epsilon")[0], single.tensor("epsilon")[0][off:off + cnt])
+            np.testing.assert_allclose(shard.tensor("rollouts")[0][:cnt], single.tensor("rollouts")[0][off:off + cnt], rtol=1e-9, atol=1e-12)
+            np.testing.assert_array_equal(shard.tensor("verdicts")[0][:cnt], single.tensor("verdicts")[0][off:off + cnt])
+            # rollout-indexed tables are complete and identical on every rank (a collective read-back in peer mode)
+            np.testing.assert_allclose(shard.tensor("total_cost")[0], single.tensor("total_cost")[0], rtol=1e-9)
+            np.testing.assert_allclose(shard.tensor("probabilities")[0], single.tensor("probabilities")[0], rtol=1e-9, atol=1e-300)
+            np.testing.assert_allclose(shard.tensor("updates")[0], single.tensor("updates")[0], rtol=1e-9, atol=1e-13)
+            np.testing.assert_allclose(shard.tensor("parameters")[0], single.tensor("parameters")[0], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(shard.tensor("stddevs")[0], single.tensor("stddevs")[0], rtol=1e-9)
+            np.testing.assert_allclose(c2, c1, rtol=1e-9)
+            assert bool(v1[0]) == bool(v2[0])
+            # every rank holds the same parameters bit for bit (the rows are added in rank order on every rank)
+            mine = torch.from_numpy(shard.tensor("parameters")[0]).to(dev)
+            ref = mine.clone()
+            dist.broadcast(ref, 0)
+            assert torch.equal(mine, ref)
+        shard.run(5, 3)
+        r = shard.finish_solve()
+        assert r["iterations"][0] == 8
+        # the lean loop (no debug tensors, noise not materialised) against the single-GPU lean loop
+        single2 = binding.engine_for_problem(pb, device=local)
+        shard2 = binding.engine_for_problem(pb, device=local, world_size=world, rank=rank, shard_mode=0)
+        uid = binding.comm_unique_id() if rank == 0 else b""
+        shard2.comm_init(sharding.broadcast_bytes(dist, uid, binding.COMM_ID_BYTES, dev))
+        single2.begin_solve(); shard2.begin_solve()
+        single2.run(0, 6); shard2.run(0, 6)
+        a2, b2 = single2.finish_solve(), shard2.finish_solve()
+        np.testing.assert_allclose(b2["solution"], a2["solution"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(b2["cost"], a2["cost"], rtol=1e-9)
+        for eng in (single, shard, single2, shard2):
+            eng.close()
+    os.environ.pop("STOMP_B200_EXCHANGE", None)
 
     # ---- (b) query sharding ----
     Q = 3 * world + 1
@@ -75,7 +96,7 @@ def main():
 
     dist.barrier(device_ids=[local])
     if rank == 0:
-        print(f"multi_gpu_check ok: world={world}")
+        print(f"multi_gpu_check ok: world={world}; exchange of the default transport: {kinds[0]}; forced: {kinds[1]}")
     dist.destroy_process_group()
 
 

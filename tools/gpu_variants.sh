@@ -1,8 +1,8 @@
 #!/bin/bash
+# timeline of the C3 loop under environment knobs.  usage: tools/gpu_variants.sh <tag> "VAR=val VAR2=val" "..." ...
+tag=${1:-x}; shift
 mkdir -p gpurun_out
-out=gpurun_out/variants_$1.txt; : > $out
-IFS='|' read -ra VARS <<< "$2"
-for v in "${VARS[@]}"; do
-  echo "=== $v" | tee -a $out
-  env $v timeout 300 python tools/timeline.py c3 40 2>&1 | grep -E "per iteration|sample |cost |rows|period" | tee -a $out
+for v in "$@"; do
+  echo "=== $v"
+  env $v timeout 300 python tools/timeline.py c3 40 2>&1 | grep -E "per iteration|median  |gaps|period" | tee -a gpurun_out/variants_$tag.txt
 done

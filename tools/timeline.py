@@ -10,13 +10,26 @@ from motion_planners_b200 import binding
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 pb = bench.make_problem(name)
-e = binding.engine_for_problem(pb, shard_mode=1 if bench.WORKLOADS[name]["kind"] == "batch" else 0)
+import os
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+shard_mode = 1 if bench.WORKLOADS[name]["kind"] == "batch" else 0
+e = binding.engine_for_problem(pb, device=local, world_size=world, rank=rank, shard_mode=shard_mode)
+if world > 1:      # under torchrun: rollout (or query) sharding over the ranks; rank 0 prints its own timeline
+    _, _, _, dist = bench.dist_setup(world)
+    if shard_mode == 0:
+        uid = binding.comm_unique_id() if rank == 0 else bytes(128)
+        e.comm_init(bench.broadcast_bytes(dist, uid, local))
+    print_ = print
+    def print(*a, **k):
+        if rank == 0:
+            print_(*a, **k)
+    print(f"{world} ranks, exchange: {e.exchange_kind()}")
 e.begin_solve()
 e.run(0, 5)
 e.set_timeline(True)
 flush = len(sys.argv) > 3 and sys.argv[3] == "flush"      # isolated iterations on a cold L2, as bench.py times `value`
 if flush:
-    fl = bench.L2Flusher(0)
+    fl = bench.L2Flusher(local)
     ms = 0.0
     for i in range(iters):
         fl.flush()
