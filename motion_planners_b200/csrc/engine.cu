@@ -460,6 +460,11 @@ codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
     if (const char* b = std::getenv("STOMP_B200_STATES_MIN_BLOCKS")) opt.min_blocks = std::atoi(b);   // tuning knobs
     if (const char* l = std::getenv("STOMP_B200_STATES_LAG")) opt.compare_lag = std::max(0, std::atoi(l));
     if (const char* j = std::getenv("STOMP_B200_STATES_STAGE")) opt.stage_joints = std::atoi(j) != 0;
+    // sines / cosines ahead of the chain walk: measured neutral on the 7-joint arm (15.5 vs 15.6 us at C3), a gain on the
+    // 14-joint dual arm (46.8 -> 44.0 us at C5; profiles/r3i_state_kernel_variants*.txt)
+    opt.batch_sincos = e->robot.num_joints > 8 ? e->robot.num_joints : 0;
+    if (const char* bs = std::getenv("STOMP_B200_STATES_BATCH")) opt.batch_sincos = std::max(0, std::atoi(bs));
+    if (const char* fo = std::getenv("STOMP_B200_STATES_FOLD")) opt.fold_identity = std::atoi(fo) != 0;
     if (const char* t = std::getenv("STOMP_B200_STATES_BLOCK")) { const int v = std::atoi(t); if (v == 64 || v == 128 || v == 256) opt.block_threads = v; }
     return opt;
 }
@@ -485,12 +490,17 @@ void resolve_state_kernel(stomp_b200_engine* e)
 
 // the state kernel on the T noise-less states + noiseless_rollout_kernel (K10 + the wrapper's stop rule) for the iteration
 // recorded in e->nl_lp, on the side stream, behind everything queued on the main stream so far
-int launch_noiseless(stomp_b200_engine* e)
+int launch_noiseless(stomp_b200_engine* e, bool on_main_stream)
 {
     const LoopParams& lp = e->nl_lp;
     e->nl_deferred = false;
-    CUDA_TRY(e, cudaEventRecord(e->ev_applied, e->stream));
-    CUDA_TRY(e, cudaStreamWaitEvent(e->side_stream, e->ev_applied, 0));
+    // on_main_stream: the caller is about to wait for the result (a join), nothing is there to overlap with — queue the two
+    // kernels behind the update kernel directly; the cross-stream hand-over alone cost 13 us of every isolated iteration
+    cudaStream_t nl_stream = on_main_stream ? e->stream : e->side_stream;
+    if (!on_main_stream) {
+        CUDA_TRY(e, cudaEventRecord(e->ev_applied, e->stream));
+        CUDA_TRY(e, cudaStreamWaitEvent(e->side_stream, e->ev_applied, 0));
+    }
     const size_t smem = sizeof(double) * ((size_t)e->D * e->N + e->T + e->sumw);
     e->launch_count++;
     e->kernel_launches[STOMP_B200_KERNEL_APPLY]++;
@@ -506,21 +516,23 @@ int launch_noiseless(stomp_b200_engine* e)
         a.honour_stop = lp.honour_stop; a.debug_skip = 0;
         a.row_stride = lp.N; a.rollout_stride = (int64_t)lp.D * lp.N;
         if (e->self_pairs.n > 0) {
-            launch_states_self_collision(e, a, dim3((lp.T + 127) / 128, e->Q), e->side_stream);
+            launch_states_self_collision(e, a, dim3((lp.T + 127) / 128, e->Q), nl_stream);
             if (int rc = check_launch(e, "states_self_collision_kernel")) return rc;
             e->launch_count++;
         } else {
             void* args[] = {&a, &e->robot, &e->sdf};
             const int bt = e->spec->block_threads;
-            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + bt - 1) / bt, e->Q), dim3(bt), args, 0, e->side_stream));
+            CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + bt - 1) / bt, e->Q), dim3(bt), args, 0, nl_stream));
             e->launch_count++;
         }
         states_done = 1;
     }
-    noiseless_rollout_kernel<<<e->Q, 256, smem, e->side_stream>>>(lp, e->robot, e->sdf, states_done);
+    noiseless_rollout_kernel<<<e->Q, 256, smem, nl_stream>>>(lp, e->robot, e->sdf, states_done);
     if (int rc = check_launch(e, "noiseless_rollout_kernel")) return rc;
-    CUDA_TRY(e, cudaEventRecord(e->ev_noiseless, e->side_stream));
-    e->noiseless_pending = true;
+    if (!on_main_stream) {
+        CUDA_TRY(e, cudaEventRecord(e->ev_noiseless, e->side_stream));
+        e->noiseless_pending = true;
+    }
     return 0;
 }
 
@@ -559,7 +571,7 @@ int iterate_body(stomp_b200_engine* e, int iteration, int mode, int honour_stop,
     lp.counters = on_graph ? e->d_counters : nullptr;
     // the noise-less rollout of the previous iteration: side stream, under this iteration's sampling and costs
     if (e->nl_deferred)
-        if (int rc = launch_noiseless(e)) return rc;
+        if (int rc = launch_noiseless(e, false)) return rc;
     if (e->timeline_on) {
         lp.timeline = e->d_timeline + (size_t)(e->timeline_count % kTimelineRing) * kTimelineKernels * 2;
         e->timeline_count++;
@@ -1038,7 +1050,7 @@ int ready_to_solve(stomp_b200_engine* e)
 int join_side_stream(stomp_b200_engine* e)
 {
     if (e->nl_deferred)
-        if (int rc = launch_noiseless(e)) return rc;
+        if (int rc = launch_noiseless(e, true)) return rc;
     if (e->noiseless_pending) {
         CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_noiseless, 0));
         e->noiseless_pending = false;

@@ -245,8 +245,13 @@ __device__ __forceinline__ size_t sdf_index(const SdfParams& g, double cx, doubl
 // decision (axis kind, zero masks, fixed rotation, prismatic, chain restart, index width) a template
 // argument, so that the instantiated code is straight-line and every constant a direct constant-bank operand.
 // ---------------------------------------------------------------------------------------------------
-template <int kKind, int kOMask, bool kFixedRot, bool kPrismatic, bool kRestart>
-__device__ __forceinline__ void apply_joint_static(Frame& f, const JointParams& j, double q)
+template <int kKind>
+__device__ __forceinline__ void rotate_joint_static(Frame& f, const JointParams& j, double s, double c);
+
+// everything of a joint that comes before its rotation: chain restart, origin, fixed rotation; for a prismatic joint
+// also the translation along its axis (the joint is then complete)
+template <int kOMask, bool kFixedRot, bool kPrismatic, bool kRestart>
+__device__ __forceinline__ void place_joint_static(Frame& f, const JointParams& j, double q)
 {
     if (kRestart) frame_identity(f);
     if (kOMask & 1) { f.px = fma(f.r00, j.o[0], f.px); f.py = fma(f.r10, j.o[0], f.py); f.pz = fma(f.r20, j.o[0], f.pz); }
@@ -273,10 +278,25 @@ __device__ __forceinline__ void apply_joint_static(Frame& f, const JointParams& 
         f.px = fma(q, dx, f.px);
         f.py = fma(q, dy, f.py);
         f.pz = fma(q, dz, f.pz);
-        return;
     }
+}
+
+template <int kKind, int kOMask, bool kFixedRot, bool kPrismatic, bool kRestart>
+__device__ __forceinline__ void apply_joint_static(Frame& f, const JointParams& j, double q)
+{
+    place_joint_static<kOMask, kFixedRot, kPrismatic, kRestart>(f, j, q);
+    if (kPrismatic) return;
     double s, c;
     det_sincos(q, s, c);
+    rotate_joint_static<kKind>(f, j, s, c);
+}
+
+// the rotation of a revolute joint from the sine / cosine of its value: the tail of apply_joint_static, also called on
+// its own by the generated kernel when it evaluates all sines and cosines of a state up front (state_codegen.hpp:
+// StateKernelOptions::batch_sincos) — the same operations on the same operands either way
+template <int kKind>
+__device__ __forceinline__ void rotate_joint_static(Frame& f, const JointParams& j, double s, double c)
+{
     if (kKind >= kAxisNegX && kKind <= kAxisNegZ) s = -s;
     constexpr int kind = (kKind >= kAxisNegX && kKind <= kAxisNegZ) ? kKind - 3 : kKind;
     const double ns = -s;
@@ -325,6 +345,9 @@ __device__ __forceinline__ int voxel_floor_magic(double v) { return __double2loi
 
 // kInside: the host has proved that no sphere centre can leave the grid (state_codegen.hpp: reach_is_inside_grid), so
 // the clamps — six VIMNMX per sphere, an eighth of the kernel's instructions — are identities and are left out.
+template <bool kWide, bool kMagic, bool kInside>
+__device__ __forceinline__ const float* voxel_of_centre(double cx, double cy, double cz, const SdfParams& g);
+
 template <int kMask, bool kWide, bool kMagic, bool kInside>
 __device__ __forceinline__ const float* sphere_voxel_static(const Frame& f, const SphereParams& sp, const SdfParams& g)
 {
@@ -332,6 +355,14 @@ __device__ __forceinline__ const float* sphere_voxel_static(const Frame& f, cons
     if (kMask & 1) { cx = fma(f.r00, sp.l[0], cx); cy = fma(f.r10, sp.l[0], cy); cz = fma(f.r20, sp.l[0], cz); }
     if (kMask & 2) { cx = fma(f.r01, sp.l[1], cx); cy = fma(f.r11, sp.l[1], cy); cz = fma(f.r21, sp.l[1], cz); }
     if (kMask & 4) { cx = fma(f.r02, sp.l[2], cx); cy = fma(f.r12, sp.l[2], cy); cz = fma(f.r22, sp.l[2], cz); }
+    return voxel_of_centre<kWide, kMagic, kInside>(cx, cy, cz, g);
+}
+
+// address of the voxel under a centre (the tail of sphere_voxel_static; the generated kernel calls it directly when it
+// has formed the centre itself, state_codegen.hpp: fold_identity)
+template <bool kWide, bool kMagic, bool kInside>
+__device__ __forceinline__ const float* voxel_of_centre(double cx, double cy, double cz, const SdfParams& g)
+{
     const double vx = fma(cx, g.inv_h, g.offx), vy = fma(cy, g.inv_h, g.offy), vz = fma(cz, g.inv_h, g.offz);
     int ix = kMagic ? voxel_floor_magic(vx) : __double2int_rz(vx);
     int iy = kMagic ? voxel_floor_magic(vy) : __double2int_rz(vy);

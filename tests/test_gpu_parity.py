@@ -325,7 +325,10 @@ def test_specialised_state_kernel_equals_generic_kernel_and_oracle(shape, medium
     kind, note = spec.state_kernel_kind()
     assert kind == "specialised", note
     src = spec.state_kernel_source()
-    assert src.count("apply_joint_static<") == D and src.count("sphere_voxel_static<") == pb.spheres.link.size
+    # one sine / cosine evaluation per revolute joint and one gather per sphere, however the chain walk is emitted
+    revolute = D - int(np.count_nonzero(pb.chain.prismatic))
+    assert src.count("det_sincos(q") == revolute
+    assert src.count("voxel_of_centre<") == pb.spheres.link.size
     monkeypatch.setenv("STOMP_B200_STATES", "generic")
     gen = binding.engine_for_problem(pb, keep_debug_tensors=True)
     assert gen.state_kernel_kind()[0] == "generic"
