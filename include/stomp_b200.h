@@ -68,7 +68,9 @@ typedef struct stomp_b200_config {
                                             {0,0,1,0} for every joint and time step (OptimizationTask.cpp:32-33) */
     double cost_scaling_h;               /* 10.0 (PolicyImprovement.cpp:55) */
     int32_t use_noise_adaptation;        /* use_noise_adaptation_ */
-    int32_t use_cumulative_costs;        /* 1 (PolicyImprovement.cpp:56); 0 = per-time-step costs: one GPU, no rollout reuse */
+    int32_t use_cumulative_costs;        /* 1 (PolicyImprovement.cpp:56): costs summed over the trajectory; 0 = per-time-step costs;
+                                            2 = forward cumulation, cumulative_costs_(t) = sum_{t' >= t} (the variant commented out at
+                                            :473-477).  0 and 2: one GPU, no rollout reuse */
     int32_t use_projection;              /* 0 (PolicyImprovement.cpp:57); 1 = M-matrix projected noise / update
                                             (PolicyImprovement.cpp:421-440,706,750-801); needs Rinv */
     int32_t per_timestep_minmax;         /* 0 = shipped global min/max; 1 = variant commented out at :518-528 (differs
@@ -187,7 +189,8 @@ int stomp_b200_run(stomp_b200_engine* e, int32_t first_iteration, int32_t num_it
 int stomp_b200_solve(stomp_b200_engine* e, int32_t max_iterations, int32_t poll_every, int32_t* iterations_run);
 
 /* Stomp::setCostCumulation (stomp/src/Stomp.cpp:356-359): 1 = costs summed over the trajectory (the default), 0 = costs
- * and probabilities per time step (PolicyImprovement.cpp:473-481).  0 is built for one GPU without rollout reuse, else
+ * and probabilities per time step (PolicyImprovement.cpp:473-481), 2 = forward cumulation (cost-to-go, :473-477).  0 and 2
+ * are built for one GPU without rollout reuse, else
  * STOMP_B200_ERR_UNSUPPORTED.  Also settable at creation (stomp_b200_config::use_cumulative_costs). */
 int stomp_b200_set_cost_cumulation(stomp_b200_engine* e, int32_t use_cumulative_costs);
 
@@ -239,6 +242,19 @@ int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_
  * list.  While a list is set the state kernel is the generic-FK self-collision kernel
  * (stomp_b200_state_kernel_kind returns 2). */
 int stomp_b200_set_self_collision(stomp_b200_engine* e, int32_t num_pairs, const int32_t* pairs /*[num_pairs][2]*/);
+
+/* ---- alternative state costs (both off by default = the reference's shipped 0 / 1 collision cost).
+ * smooth obstacle cost: the state cost becomes smooth_weight * sum_s max(0, (r_s + smooth_margin) - d_s) over the link
+ *   spheres — it grows with the penetration into the clearance band instead of jumping to 1 (the non-boolean obstacles of
+ *   the reference's stomp/test/stomp_2d_test.cpp:337-363, carried over to spheres and a distance field);
+ * joint-constraint cost: OptimizationTask::computeJointsConstraintCost / getConstrainDifference
+ *   (src/planners/src/wrappers/stomp/OptimizationTask.cpp:206-237; its call at :169-172 is commented out in the reference):
+ *   + weight * sum_d max(0, |value_d - q_d| - tolerance_d) on every time step.
+ * The verdicts / validity stay the binary collision test.  Applies to the loop, the noise-less rollout and
+ * stomp_b200_evaluate_states.  value / tolerance [D] may be NULL when use_joint_constraint == 0.  Not with rollout sharding. */
+int stomp_b200_set_cost_extras(stomp_b200_engine* e, int32_t use_smooth_cost, double smooth_margin, double smooth_weight,
+                               int32_t use_joint_constraint, const double* value /*[D]*/, const double* tolerance /*[D]*/,
+                               double joint_constraint_weight);
 
 /* sphere centres in the world frame for n joint configurations q [n][D] -> [n][S][3] */
 int stomp_b200_sphere_centres(stomp_b200_engine* e, const double* q, int32_t n, double* centres);

@@ -37,7 +37,7 @@ SYMBOLS = [
     "stomp_b200_comm_init", "stomp_b200_exchange_kind", "stomp_b200_set_profiling", "stomp_b200_kernel_stats", "stomp_b200_reset_kernel_stats",
     "stomp_b200_set_timeline", "stomp_b200_get_timeline", "stomp_b200_launch_count", "stomp_b200_graph_replays", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
     "stomp_b200_state_kernel_kind", "stomp_b200_state_kernel_source", "stomp_b200_codegen_selftest",
-    "stomp_b200_set_cost_cumulation", "stomp_b200_set_self_collision",
+    "stomp_b200_set_cost_cumulation", "stomp_b200_set_self_collision", "stomp_b200_set_cost_extras",
     "stomp_b200_build_sdf_primitives", "stomp_b200_build_sdf_occupancy", "stomp_b200_get_sdf",
 ]
 
@@ -125,6 +125,7 @@ def lib():
         L.stomp_b200_graph_replays.restype = C.c_int64
         L.stomp_b200_state_kernel_kind.argtypes = [vp, C.c_char_p, C.c_size_t]
         L.stomp_b200_state_kernel_kind.restype = C.c_int32
+        L.stomp_b200_set_cost_extras.argtypes = [vp, C.c_int32, C.c_double, C.c_double, C.c_int32, dp, dp, C.c_double]
         L.stomp_b200_exchange_kind.argtypes = [vp, C.c_char_p, C.c_size_t]
         L.stomp_b200_exchange_kind.restype = C.c_int32
         L.stomp_b200_state_kernel_source.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -417,6 +418,16 @@ class Engine:
     def comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
         self._check(lib().stomp_b200_comm_init(self.h, buf), "stomp_b200_comm_init")
+
+    def set_cost_extras(self, smooth=None, joint_constraint=None):
+        """smooth: (margin, weight) or None; joint_constraint: (value [D], tolerance [D], weight) or None."""
+        sm = smooth or (0.0, 1.0)
+        if joint_constraint is not None:
+            v, tol, w = _c64(joint_constraint[0]), _c64(joint_constraint[1]), float(joint_constraint[2])
+            rc = lib().stomp_b200_set_cost_extras(self.h, int(smooth is not None), float(sm[0]), float(sm[1]), 1, _dp(v), _dp(tol), w)
+        else:
+            rc = lib().stomp_b200_set_cost_extras(self.h, int(smooth is not None), float(sm[0]), float(sm[1]), 0, None, None, 1.0)
+        self._check(rc, "stomp_b200_set_cost_extras")
 
     def exchange_kind(self):
         """("peer" | "nccl" | "none", note): how a rollout-sharded engine exchanges its per-iteration scalars."""

@@ -109,7 +109,11 @@ struct stomp_b200_engine {
     SdfParams sdf;
     float* d_sdf = nullptr;
     size_t sdf_count = 0;
+    float* d_bricks = nullptr;      // bricked copy of the grid (STOMP_B200_SDF_LAYOUT=brick), else null
+    size_t brick_count = 0;
     double sdf_origin[3] = {0, 0, 0}, sdf_voxel = 0;
+    CostExtras extras;              // stomp_b200_set_cost_extras; all zero: the shipped 0 / 1 state cost
+    bool extras_on = false;
     SelfPairs self_pairs = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};   // stomp_b200_set_self_collision; n == 0: world collisions only
     std::vector<void*> self_pair_buffers;
     bool have_chain = false, have_spheres = false, have_sdf = false, have_matrices = false;
@@ -465,6 +469,7 @@ codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
     opt.batch_sincos = e->robot.num_joints > 8 ? e->robot.num_joints : 0;
     if (const char* bs = std::getenv("STOMP_B200_STATES_BATCH")) opt.batch_sincos = std::max(0, std::atoi(bs));
     if (const char* fo = std::getenv("STOMP_B200_STATES_FOLD")) opt.fold_identity = std::atoi(fo) != 0;
+    opt.brick_sdf = e->sdf.bricks != nullptr && opt.fold_identity;
     if (const char* t = std::getenv("STOMP_B200_STATES_BLOCK")) { const int v = std::atoi(t); if (v == 64 || v == 128 || v == 256) opt.block_threads = v; }
     return opt;
 }
@@ -527,7 +532,7 @@ int launch_noiseless(stomp_b200_engine* e, bool on_main_stream)
         }
         states_done = 1;
     }
-    noiseless_rollout_kernel<<<e->Q, 256, smem, nl_stream>>>(lp, e->robot, e->sdf, states_done);
+    noiseless_rollout_kernel<<<e->Q, 256, smem, nl_stream>>>(lp, e->robot, e->sdf, states_done, e->extras);
     if (int rc = check_launch(e, "noiseless_rollout_kernel")) return rc;
     if (!on_main_stream) {
         CUDA_TRY(e, cudaEventRecord(e->ev_noiseless, e->side_stream));
@@ -620,9 +625,9 @@ int iterate_body(stomp_b200_engine* e, int iteration, int mode, int honour_stop,
     // tensor is not materialised — weights_update_kernel subtracts theta from the rollout rows it streams
     // rollout sharding: both exchanges inside weights_update_peer_kernel over the peer-mapped mailboxes (every rank takes
     // the same decision: the flags involved are set alike on all ranks)
-    const bool peer = world > 1 && e->peer_ready && !e->profiling && c.use_cumulative_costs && e->fuse_weights_allowed;
+    const bool peer = world > 1 && e->peer_ready && !e->profiling && c.use_cumulative_costs == 1 && e->fuse_weights_allowed;
     {
-        const bool fuse_weights_ahead = e->fuse_weights_allowed && (world == 1 || peer) && !e->profiling && !e->reuse_possible && reused == 0 && c.use_cumulative_costs;
+        const bool fuse_weights_ahead = e->fuse_weights_allowed && (world == 1 || peer) && !e->profiling && !e->reuse_possible && reused == 0 && c.use_cumulative_costs == 1;
         lp.noise_from_rollouts = (fused_rows && fuse_weights_ahead && !c.keep_debug_tensors && !lp.control_costs && !lp.proj) ? 1 : 0;
         static const bool lean_allowed = !(std::getenv("STOMP_B200_LEAN_NOISE") && std::strcmp(std::getenv("STOMP_B200_LEAN_NOISE"), "0") == 0);
         if (!lean_allowed) lp.noise_from_rollouts = 0;
@@ -725,6 +730,13 @@ int iterate_body(stomp_b200_engine* e, int iteration, int mode, int honour_stop,
         } else if (e->robot.simple_chain) rollout_states_kernel<true><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
         else rollout_states_kernel<false><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
         if (int rc = check_launch(e, "rollout_states_kernel")) return rc;
+        if (e->extras_on) {     // alternative state costs: a pass of their own, then S_k in a fixed order
+            state_cost_extras_kernel<<<dim3((states + 127) / 128, e->Q), 128, 0, e->stream>>>(lp, e->robot, e->sdf, e->extras);
+            if (int rc = check_launch(e, "state_cost_extras_kernel")) return rc;
+            state_row_sums_kernel<<<dim3((gen_local + 7) / 8, e->Q), 256, 0, e->stream>>>(lp);
+            if (int rc = check_launch(e, "state_row_sums_kernel")) return rc;
+            e->launch_count += 2;
+        }
     }
     if (overlap_rows) CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_rows, 0));
     // ---- the noise-less rollout of the previous iteration is needed from here on ----
@@ -750,7 +762,7 @@ int iterate_body(stomp_b200_engine* e, int iteration, int mode, int honour_stop,
     }
 
     // one launch for K7-K9 when nothing sits between them (no exchange, no reused rollouts, no per-kernel profiling)
-    const bool per_timestep = !c.use_cumulative_costs;
+    const bool per_timestep = c.use_cumulative_costs != 1;      // 0: per-time-step costs; 2: forward cumulation (cost-to-go)
     const bool fuse_weights = e->fuse_weights_allowed && (world == 1 || peer) && !e->profiling && !e->reuse_possible && reused == 0 && !per_timestep;
     if (lp.noise_from_rollouts && !fuse_weights) return fail(e, STOMP_B200_ERR_CUDA, "internal: noise not materialised but the fused update kernel is not in use");
     const int nchunks = std::max(1, (lp.num_local + lp.chunk - 1) / lp.chunk);
@@ -782,6 +794,11 @@ int iterate_body(stomp_b200_engine* e, int iteration, int mode, int honour_stop,
     const bool fuse_apply = world == 1 && !e->profiling && !per_timestep;     // the apply step rides on the update kernel's last chunk CTA
     if (per_timestep) {      // Stomp::setCostCumulation(false): probabilities per time step
         Scope sc(e, STOMP_B200_KERNEL_UPDATE);
+        lp.forward_cumulation = c.use_cumulative_costs == 2 ? 1 : 0;
+        if (lp.forward_cumulation) {
+            pertimestep_suffix_kernel<<<dim3((lp.num_local * e->D + 127) / 128, e->Q), 128, 0, e->stream>>>(lp);
+            if (int rc = check_launch(e, "pertimestep_suffix_kernel")) return rc;
+        }
         pertimestep_minmax_kernel<<<dim3(e->D, e->Q), 1024, 0, e->stream>>>(lp);
         if (int rc = check_launch(e, "pertimestep_minmax_kernel")) return rc;
         pertimestep_update_kernel<<<dim3((e->T + 127) / 128, e->D, e->Q), 128, 0, e->stream>>>(lp);
@@ -867,7 +884,7 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
     const stomp_b200_config& c = e->cfg;
     const int world = c.shard_mode == 0 ? c.world_size : 1;
     bool eligible = e->graphs_allowed && e->d_counters && mode == kNoisePhilox && !e->profiling && !e->timeline_on && !e->reuse_possible &&
-                    e->noiseless_valid && c.use_cumulative_costs && !c.keep_debug_tensors && !e->edge_dirty && !c.use_projection &&
+                    e->noiseless_valid && c.use_cumulative_costs == 1 && !c.keep_debug_tensors && !e->edge_dirty && !c.use_projection && !e->extras_on &&
                     e->base.Lband != nullptr && (e->sampler_mode == 0 || e->sampler_mode == 3) && e->fuse_weights_allowed &&
                     (world == 1 || e->peer_ready) && c.num_rollouts_per_iteration % world == 0 &&
                     !e->noiseless_pending && (!e->nl_deferred || e->nl_lp.honour_stop == honour_stop);
@@ -1001,6 +1018,7 @@ int setup_peer_exchange(stomp_b200_engine* e)
         if (!theirs) { ok = 0; why = "rank " + std::to_string(r) + " could not export its mailbox"; }
     }
     std::memset(&e->px, 0, sizeof(e->px));
+    std::memset(&e->extras, 0, sizeof(e->extras));
     for (int r = 0; r < W && ok; ++r) {
         if (r == c.rank) { e->px.box[r] = static_cast<unsigned char*>(e->peer_box_own); continue; }
         cudaIpcMemHandle_t h;
@@ -1129,7 +1147,8 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
         return STOMP_B200_ERR_INVALID_ARGUMENT;
     if (cfg->shard_mode != 0 && cfg->shard_mode != 1) return STOMP_B200_ERR_INVALID_ARGUMENT;
     // Stomp::setCostCumulation(false): built for the plain case (one GPU, no rollout reuse)
-    if (!cfg->use_cumulative_costs && (cfg->world_size > 1 || cfg->num_rollouts_per_iteration < cfg->max_rollouts ||
+    if (cfg->use_cumulative_costs < 0 || cfg->use_cumulative_costs > 2) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (cfg->use_cumulative_costs != 1 && (cfg->world_size > 1 || cfg->num_rollouts_per_iteration < cfg->max_rollouts ||
                                        cfg->min_rollouts > cfg->num_rollouts_per_iteration))
         return STOMP_B200_ERR_UNSUPPORTED;
     if (cfg->shard_mode == 0 && cfg->world_size > 1 && cfg->num_queries != 1) return STOMP_B200_ERR_UNSUPPORTED;
@@ -1225,8 +1244,9 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     }
     b.state_costs = e->state2[0]; b.verdicts = e->verdict2[0]; b.proj = e->proj2[0];
     CREATE_TRY(dev_alloc(e, &b.validity, Q * S));
-    if (cfg->keep_debug_tensors || !cfg->use_cumulative_costs) CREATE_TRY(dev_alloc(e, &b.control_costs, Q * S * D * T));
-    if (!cfg->use_cumulative_costs) {
+    if (cfg->keep_debug_tensors || cfg->use_cumulative_costs != 1) CREATE_TRY(dev_alloc(e, &b.control_costs, Q * S * D * T));
+    if (cfg->use_cumulative_costs == 2) CREATE_TRY(dev_alloc(e, &b.pt_cum, Q * S * D * T));
+    if (cfg->use_cumulative_costs != 1) {
         CREATE_TRY(dev_alloc(e, &b.pt_prob, Q * GS * D * T));
         CREATE_TRY(dev_alloc(e, &b.pt_minden, Q * D * 2));
     }
@@ -1366,6 +1386,7 @@ int stomp_b200_destroy(stomp_b200_engine* e)
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* p : e->allocations) cudaFree(p);
     if (e->d_sdf) cudaFree(e->d_sdf);
+    if (e->d_bricks) cudaFree(e->d_bricks);
     for (void* p : e->self_pair_buffers) cudaFree(p);
     if (e->eval_theta) cudaFree(e->eval_theta);
     if (e->eval_cost) cudaFree(e->eval_cost);
@@ -1487,6 +1508,33 @@ int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int3
     return STOMP_B200_OK;
 }
 
+int stomp_b200_set_cost_extras(stomp_b200_engine* e, int32_t use_smooth_cost, double smooth_margin, double smooth_weight,
+                               int32_t use_joint_constraint, const double* value, const double* tolerance, double joint_constraint_weight)
+{
+    if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (use_joint_constraint && (!value || !tolerance)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "joint constraint needs value and tolerance");
+    if (use_smooth_cost && !(smooth_margin >= 0.0 && smooth_weight >= 0.0)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "smooth cost: margin and weight must be >= 0");
+    if ((use_smooth_cost || use_joint_constraint) && e->cfg.shard_mode == 0 && e->cfg.world_size > 1)
+        return fail(e, STOMP_B200_ERR_UNSUPPORTED, "alternative state costs are built for one GPU (and for query sharding)");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    if (int rc = join_side_stream(e)) return rc;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    std::memset(&e->extras, 0, sizeof(e->extras));
+    e->extras.smooth = use_smooth_cost ? 1 : 0;
+    e->extras.smooth_margin = smooth_margin;
+    e->extras.smooth_weight = smooth_weight;
+    e->extras.joint_constraint = use_joint_constraint ? 1 : 0;
+    e->extras.jc_weight = joint_constraint_weight;
+    for (int d = 0; d < e->D && use_joint_constraint; ++d) {
+        if (!(std::fabs(value[d]) <= 1e6) || !(tolerance[d] >= 0.0)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "joint constraint: bad value or tolerance");
+        e->extras.jc_value[d] = value[d];
+        e->extras.jc_tolerance[d] = tolerance[d];
+    }
+    e->extras_on = use_smooth_cost || use_joint_constraint;
+    e->config_epoch++;
+    return STOMP_B200_OK;
+}
+
 int stomp_b200_set_self_collision(stomp_b200_engine* e, int32_t num_pairs, const int32_t* pairs)
 {
     if (!e || num_pairs < 0 || (num_pairs > 0 && !pairs)) return STOMP_B200_ERR_INVALID_ARGUMENT;
@@ -1597,6 +1645,25 @@ static int adopt_sdf_geometry(stomp_b200_engine* e, const int32_t dims[3], const
     return STOMP_B200_OK;
 }
 
+// STOMP_B200_SDF_LAYOUT=brick: a second copy of the finished grid in 4 x 4 x 2 bricks for the specialised state kernel
+static int build_sdf_bricks(stomp_b200_engine* e)
+{
+    e->sdf.bricks = nullptr;
+    const char* layout = std::getenv("STOMP_B200_SDF_LAYOUT");
+    if (!layout || std::strcmp(layout, "brick") != 0) return STOMP_B200_OK;
+    const int nbx = (e->sdf.nx + 3) / 4, nby = (e->sdf.ny + 3) / 4, nbz = (e->sdf.nz + 1) / 2;
+    const size_t count = (size_t)nbx * nby * nbz * 32;
+    if (e->d_bricks && e->brick_count != count) { cudaFree(e->d_bricks); e->d_bricks = nullptr; }
+    if (!e->d_bricks) { CUDA_TRY(e, cudaMalloc(&e->d_bricks, count * sizeof(float))); e->brick_count = count; }
+    brick_sdf_kernel<<<(unsigned)((count + 255) / 256), 256, 0, e->stream>>>(e->d_sdf, e->d_bricks, e->sdf.nx, e->sdf.ny, e->sdf.nz, nbx, nby, count);
+    e->launch_count++;
+    if (int rc = check_launch(e, "brick_sdf_kernel")) return rc;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->sdf.bricks = e->d_bricks; e->sdf.nbx = nbx; e->sdf.nby = nby;
+    e->spec_resolved = false;
+    return STOMP_B200_OK;
+}
+
 int stomp_b200_set_sdf(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size, const float* grid)
 {
     if (!e || !dims || !origin || !grid || !(voxel_size > 0.0)) return STOMP_B200_ERR_INVALID_ARGUMENT;
@@ -1604,7 +1671,7 @@ int stomp_b200_set_sdf(stomp_b200_engine* e, const int32_t dims[3], const double
     if (int rc = adopt_sdf_geometry(e, dims, origin, voxel_size)) return rc;
     CUDA_TRY(e, cudaMemcpy(e->d_sdf, grid, e->sdf_count * sizeof(float), cudaMemcpyHostToDevice));
     e->have_sdf = true;
-    return STOMP_B200_OK;
+    return build_sdf_bricks(e);
 }
 
 int stomp_b200_build_sdf_primitives(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
@@ -1638,7 +1705,7 @@ int stomp_b200_build_sdf_primitives(stomp_b200_engine* e, const int32_t dims[3],
     cudaFree(d_list);
     if (err != cudaSuccess) { e->last_error = std::string("build_sdf_primitives: ") + cudaGetErrorString(err); return STOMP_B200_ERR_CUDA; }
     e->have_sdf = true;
-    return STOMP_B200_OK;
+    return build_sdf_bricks(e);
 }
 
 int stomp_b200_build_sdf_occupancy(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
@@ -1677,7 +1744,7 @@ int stomp_b200_build_sdf_occupancy(stomp_b200_engine* e, const int32_t dims[3], 
     cleanup();
     if (err != cudaSuccess) { e->last_error = std::string("build_sdf_occupancy: ") + cudaGetErrorString(err); return STOMP_B200_ERR_CUDA; }
     e->have_sdf = true;
-    return STOMP_B200_OK;
+    return build_sdf_bricks(e);
 }
 
 int stomp_b200_get_sdf(stomp_b200_engine* e, float* out, size_t count, int32_t dims_out[3], double origin_out[3], double* voxel_size_out)
@@ -2013,12 +2080,12 @@ int stomp_b200_get_tensor(stomp_b200_engine* e, int32_t tensor, void* out, size_
             if (!b.control_costs) return fail(e, STOMP_B200_ERR_NOT_READY, "control costs need keep_debug_tensors");
             return per_query(b.control_costs, nl * D, (size_t)e->slots * D, T * sizeof(double));
         case STOMP_B200_CUMULATIVE_COSTS:
-            if (!e->cfg.use_cumulative_costs) return fail(e, STOMP_B200_ERR_UNSUPPORTED, "per-time-step mode: cumulative costs = state costs + control costs, read those");
+            if (e->cfg.use_cumulative_costs != 1) return fail(e, STOMP_B200_ERR_UNSUPPORTED, "per-time-step / forward-cumulation mode: cumulative costs follow from state costs + control costs, read those");
             return from_sums(5);
         case STOMP_B200_FULL_COSTS: return from_sums(6);
         case STOMP_B200_TOTAL_COST: return from_sums(7);
         case STOMP_B200_PROBABILITIES:
-            if (!e->cfg.use_cumulative_costs) return per_query(b.pt_prob, ng * D, (size_t)e->gslots * D, T * sizeof(double));
+            if (e->cfg.use_cumulative_costs != 1) return per_query(b.pt_prob, ng * D, (size_t)e->gslots * D, T * sizeof(double));
             // fall through
         case STOMP_B200_FULL_PROBABILITIES: {
             // the device tables hold exp(-h (c - min) / den); divide by their sum (wpart), exactly as
@@ -2137,6 +2204,11 @@ int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_
         }
     }
     if (int rc = check_launch(e, "evaluate_states")) return rc;
+    if (e->extras_on) {
+        evaluate_extras_kernel<<<(unsigned)((states + 127) / 128), 128, 0, e->stream>>>(e->robot, e->sdf, e->extras, d_theta, num_trajectories, num_steps, d_cost);
+        e->launch_count++;
+        if (int rc = check_launch(e, "evaluate_extras_kernel")) return rc;
+    }
     if (state_costs) CUDA_TRY(e, cudaMemcpyAsync(state_costs, d_cost, sizeof(double) * states, cudaMemcpyDeviceToHost, e->stream));
     if (verdicts) CUDA_TRY(e, cudaMemcpyAsync(verdicts, d_verdict, states, cudaMemcpyDeviceToHost, e->stream));
     if (validity) CUDA_TRY(e, cudaMemcpyAsync(validity, d_valid, num_trajectories, cudaMemcpyDeviceToHost, e->stream));
@@ -2387,7 +2459,8 @@ int stomp_b200_codegen_selftest(char* log, size_t log_capacity)
 int stomp_b200_set_cost_cumulation(stomp_b200_engine* e, int32_t use_cumulative_costs)
 {
     if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
-    if (!use_cumulative_costs) {
+    if (use_cumulative_costs < 0 || use_cumulative_costs > 2) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (use_cumulative_costs != 1) {
         if (e->cfg.world_size > 1 || e->reuse_possible)
             return fail(e, STOMP_B200_ERR_UNSUPPORTED, "per-time-step costs are built for one GPU without rollout reuse");
         CUDA_TRY(e, cudaSetDevice(e->cfg.device));
@@ -2396,8 +2469,9 @@ int stomp_b200_set_cost_cumulation(stomp_b200_engine* e, int32_t use_cumulative_
         if (!b.control_costs) { if (int rc = dev_alloc(e, &b.control_costs, Q * S * D * T)) return rc; }
         if (!b.pt_prob) { if (int rc = dev_alloc(e, &b.pt_prob, Q * GS * D * T)) return rc; }
         if (!b.pt_minden) { if (int rc = dev_alloc(e, &b.pt_minden, Q * D * 2)) return rc; }
+        if (use_cumulative_costs == 2 && !b.pt_cum) { if (int rc = dev_alloc(e, &b.pt_cum, Q * S * D * T)) return rc; }
     }
-    e->cfg.use_cumulative_costs = use_cumulative_costs ? 1 : 0;
+    e->cfg.use_cumulative_costs = use_cumulative_costs;
     e->config_epoch++;
     return STOMP_B200_OK;
 }

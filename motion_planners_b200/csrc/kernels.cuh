@@ -116,6 +116,11 @@ struct LoopParams {
     // weights_update_peer_kernel and advanced by the sampler — reader and writer are never the same launch.  Null: the
     // values in `iteration` / PeerExchange::epoch apply.
     uint32_t* counters;
+    // forward cumulation (use_cumulative_costs == 2: cumulative_costs_[d](t) = sum_{t' >= t} total_costs_[d](t'), the
+    // variant commented out at PolicyImprovement.cpp:473-477): the suffix sums, [Q][slots][D][T]; rides on the
+    // per-time-step kernels
+    double* pt_cum;
+    int32_t forward_cumulation;
 };
 
 // the joint limits of OptimizationTask::filter: all the sampling kernels need of the robot (0.5 KB of kernel parameters
@@ -1607,6 +1612,102 @@ rollout_states_kernel(const __grid_constant__ LoopParams p, const __grid_constan
     tls.end();
 }
 
+// -----------------------------------------------------------------------------------------------------
+// Alternative state costs (both off in the shipped configuration, stomp_b200_set_cost_extras):
+//   smooth obstacle cost: weight * sum_s max(0, (r_s + margin) - d_s) over the link spheres in index order, in place of
+//     the 0 / 1 verdict cost — the non-boolean obstacle shape of stomp/test/stomp_2d_test.cpp:337-363 for spheres and a
+//     distance field;
+//   joint-constraint cost: OptimizationTask::computeJointsConstraintCost / getConstrainDifference
+//     (src/wrappers/stomp/OptimizationTask.cpp:206-237; the call at :169-172 is commented out in the reference):
+//     + weight * sum_d max(0, |value_d - q_d| - tolerance_d).
+// They run as a pass of their own after the state kernel (generic FK; the verdicts stay the state kernel's), followed by
+// a fixed-order row sum for S_k — costs are no longer small integers, so the state kernel's atomic count does not serve.
+// -----------------------------------------------------------------------------------------------------
+struct CostExtras {
+    int32_t smooth, joint_constraint;
+    double smooth_margin, smooth_weight, jc_weight;
+    double jc_value[STOMP_B200_MAX_DIMS], jc_tolerance[STOMP_B200_MAX_DIMS];
+};
+
+template <class JointValue>
+__device__ __forceinline__ double extra_state_cost(const RobotParams& robot, const SdfParams& sdf, const CostExtras& x,
+                                                   JointValue joint_value, double binary_cost)
+{
+    double cost = binary_cost;
+    if (x.smooth) {
+        Frame f;
+        frame_identity(f);
+        double pen = 0.0;
+        for (int d = 0; d < robot.num_joints; ++d) {
+            apply_joint<false>(f, robot.joint[d], joint_value(d));
+            for (int s = robot.sphere_begin[d]; s < robot.sphere_begin[d + 1]; ++s) {
+                double cx, cy, cz;
+                sphere_centre(f, robot.sphere[s], cx, cy, cz);
+                const double soft = robot.sphere[s].r + x.smooth_margin;
+                const double depth = soft - (double)__ldg(sdf.grid + sdf_index(sdf, cx, cy, cz));
+                if (depth > 0.0) pen = pen + depth;
+            }
+        }
+        cost = x.smooth_weight * pen;
+    }
+    if (x.joint_constraint) {
+        double cc = 0.0;
+        for (int d = 0; d < robot.num_joints; ++d) {
+            const double diff = x.jc_tolerance[d] - fabs(x.jc_value[d] - joint_value(d));
+            if (diff < 0.0) cc = cc + (-1.0 * diff);
+        }
+        cost = cost + x.jc_weight * cc;
+    }
+    return cost;
+}
+
+// rewrites state_costs of the generated rollouts; thread per (rollout, time step)
+__global__ void __launch_bounds__(128)
+state_cost_extras_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
+                         const __grid_constant__ SdfParams sdf, const __grid_constant__ CostExtras x)
+{
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.num_gen * T) return;
+    const int k = idx / T, t = idx - k * T;
+    const double* xq = p.rollouts + ((size_t)q * p.slots + k) * D * T + t;
+    const size_t o = ((size_t)q * p.slots + k) * T + t;
+    p.state_costs[o] = extra_state_cost(robot, sdf, x, [&](int d) { return xq[(size_t)d * T]; }, p.state_costs[o]);
+}
+
+// S_k = sum_t state_costs[k][t] of the generated rollouts, one warp per rollout, fixed order
+__global__ void __launch_bounds__(256)
+state_row_sums_kernel(const __grid_constant__ LoopParams p)
+{
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= p.num_gen) return;
+    const double* row = p.state_costs + ((size_t)q * p.slots + k) * p.T;
+    double s = 0.0;
+    for (int t = lane; t < p.T; t += 32) s += row[t];
+    s = warp_sum(s);
+    if (lane == 0) {
+        p.sums[((size_t)q * p.gslots + (p.gen_offset + k)) * p.sumw] = s;
+        if (p.s_compact) p.s_compact[(size_t)q * p.gslots + (p.gen_offset + k)] = s;
+    }
+}
+
+// the same pass for stomp_b200_evaluate_states: theta [K][D][Tq], costs [K][Tq]
+__global__ void __launch_bounds__(128)
+evaluate_extras_kernel(const __grid_constant__ RobotParams robot, const __grid_constant__ SdfParams sdf, const __grid_constant__ CostExtras x,
+                       const double* __restrict__ theta, int K, int Tq, double* __restrict__ costs)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)K * Tq) return;
+    const int k = (int)(idx / Tq), t = (int)(idx - (size_t)k * Tq);
+    const double* base = theta + (size_t)k * robot.num_joints * Tq + t;
+    costs[idx] = extra_state_cost(robot, sdf, x, [&](int d) { return base[(size_t)d * Tq]; }, costs[idx]);
+}
+
 // the noise-less rollout record written out as the regular rollout slot the reference appends
 // (PolicyImprovement.cpp:304-308): parameters = the current policy parameters, zero noise, the recorded costs.
 // Called by one CTA of rollout_weights_kernel (before the update changes the parameters); the loop itself
@@ -2180,6 +2281,27 @@ weights_update_kernel(const __grid_constant__ LoopParams p)
 // and come from rollout_weights_kernel.  Not a shipped configuration: simple kernels, rollouts walked in index order
 // like the reference does.  Needs the per-time-step control costs (control_costs, folded) of every slot.
 // -----------------------------------------------------------------------------------------------------
+// cost-to-go per (rollout, joint): cum(T-1) = total(T-1), cum(t) = total(t) + cum(t+1); thread per (rollout, joint)
+__global__ void __launch_bounds__(128)
+pertimestep_suffix_kernel(const __grid_constant__ LoopParams p)      // grid (ceil(n D / 128), Q)
+{
+    const int q = blockIdx.y;
+    if (query_frozen(p, q)) return;
+    const int T = p.T, D = p.D, n = p.num_local;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * D) return;
+    const int k = e / D, d = e - k * D;
+    const double* st = p.state_costs + ((size_t)q * p.slots + k) * T;
+    const double* cc = p.control_costs + (((size_t)q * p.slots + k) * D + d) * T;
+    double* out = p.pt_cum + (((size_t)q * p.slots + k) * D + d) * T;
+    double acc = 1.0 * (st[T - 1] + cc[T - 1]);
+    out[T - 1] = acc;
+    for (int t = T - 2; t >= 0; --t) {
+        acc = 1.0 * (st[t] + cc[t]) + acc;
+        out[t] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 pertimestep_minmax_kernel(const __grid_constant__ LoopParams p)      // grid (D, Q)
 {
@@ -2190,7 +2312,8 @@ pertimestep_minmax_kernel(const __grid_constant__ LoopParams p)      // grid (D,
     double mn = 1e300, mx = -1e300;
     for (int e = threadIdx.x; e < n * T; e += blockDim.x) {
         const int k = e / T, t = e - k * T;
-        const double c = 1.0 * (p.state_costs[((size_t)q * p.slots + k) * T + t] + p.control_costs[(((size_t)q * p.slots + k) * D + d) * T + t]);
+        const double c = p.forward_cumulation ? p.pt_cum[(((size_t)q * p.slots + k) * D + d) * T + t]
+                                              : 1.0 * (p.state_costs[((size_t)q * p.slots + k) * T + t] + p.control_costs[(((size_t)q * p.slots + k) * D + d) * T + t]);
         mn = fmin(mn, c); mx = fmax(mx, c);
     }
     mn = block_reduce<1>(mn, scratch); mx = block_reduce<2>(mx, scratch);
@@ -2214,6 +2337,7 @@ pertimestep_update_kernel(const __grid_constant__ LoopParams p)      // grid (ce
     double* upd = p.updbuf + ((size_t)q * D + d) * (T + 2);
     if (t < T) {
         auto cost_of = [&](int k) {
+            if (p.forward_cumulation) return p.pt_cum[(((size_t)q * p.slots + k) * D + d) * T + t];
             return 1.0 * (p.state_costs[((size_t)q * p.slots + k) * T + t] + p.control_costs[(((size_t)q * p.slots + k) * D + d) * T + t]);
         };
         if (p.per_timestep_minmax) {     // min / max over the rollouts of THIS time step (the variant at PolicyImprovement.cpp:518-528)
@@ -2603,7 +2727,7 @@ weights_update_peer_kernel(const __grid_constant__ LoopParams p, const __grid_co
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
 noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_constant__ RobotParams robot,
-                         const __grid_constant__ SdfParams sdf, int states_done)
+                         const __grid_constant__ SdfParams sdf, int states_done, const __grid_constant__ CostExtras extras)
 {
     extern __shared__ double smem[];
     const int q = blockIdx.x;
@@ -2630,6 +2754,14 @@ noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_cons
         }
     }
     __syncthreads();
+    if (extras.smooth || extras.joint_constraint) {     // alternative state costs of the noise-less states (see CostExtras)
+        for (int t = tid; t < T; t += blockDim.x) {
+            const double* xq = sx + kPad + t;
+            sstate[t] = extra_state_cost(robot, sdf, extras, [&](int d) { return xq[(size_t)d * N]; }, sstate[t]);
+            p.nl_state[(size_t)q * T + t] = sstate[t];
+        }
+        __syncthreads();
+    }
     // control costs (noise = 0: parameters + 0.0 is exact) and sums
     const RowCoefficients rc = load_row_coefficients(p);
     for (int task = warp; task < D + 1; task += nwarps) {

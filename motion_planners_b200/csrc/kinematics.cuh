@@ -69,6 +69,11 @@ struct SdfParams {
     int32_t wide_index;        // 1 when nx*ny*nz does not fit 31 bits
     double offx, offy, offz;   // -(origin * inv_h)
     double inv_h;
+    // optional second copy of the grid in 4 x 4 x 2-voxel bricks of 128 bytes (one L2 line per brick; measurement of
+    // DESIGN.md 4 "SDF staging", STOMP_B200_SDF_LAYOUT=brick): voxel (x, y, z) lives at
+    //   (((z >> 1) * nby + (y >> 2)) * nbx + (x >> 2)) * 32 + (z & 1) * 16 + (y & 3) * 4 + (x & 3);  null: not built
+    const float* bricks;
+    int32_t nbx, nby;
 };
 
 // Deterministic sin/cos (also run on the host for the fixed rpy rotations of stomp_b200_set_chain, so
@@ -345,7 +350,7 @@ __device__ __forceinline__ int voxel_floor_magic(double v) { return __double2loi
 
 // kInside: the host has proved that no sphere centre can leave the grid (state_codegen.hpp: reach_is_inside_grid), so
 // the clamps — six VIMNMX per sphere, an eighth of the kernel's instructions — are identities and are left out.
-template <bool kWide, bool kMagic, bool kInside>
+template <bool kWide, bool kMagic, bool kInside, bool kBrick = false>
 __device__ __forceinline__ const float* voxel_of_centre(double cx, double cy, double cz, const SdfParams& g);
 
 template <int kMask, bool kWide, bool kMagic, bool kInside>
@@ -360,7 +365,7 @@ __device__ __forceinline__ const float* sphere_voxel_static(const Frame& f, cons
 
 // address of the voxel under a centre (the tail of sphere_voxel_static; the generated kernel calls it directly when it
 // has formed the centre itself, state_codegen.hpp: fold_identity)
-template <bool kWide, bool kMagic, bool kInside>
+template <bool kWide, bool kMagic, bool kInside, bool kBrick>
 __device__ __forceinline__ const float* voxel_of_centre(double cx, double cy, double cz, const SdfParams& g)
 {
     const double vx = fma(cx, g.inv_h, g.offx), vy = fma(cy, g.inv_h, g.offy), vz = fma(cz, g.inv_h, g.offz);
@@ -371,6 +376,11 @@ __device__ __forceinline__ const float* voxel_of_centre(double cx, double cy, do
         ix = min(max(ix, 0), g.nx - 1);
         iy = min(max(iy, 0), g.ny - 1);
         iz = min(max(iz, 0), g.nz - 1);
+    }
+    if (kBrick) {
+        const unsigned in = (unsigned)(((iz & 1) << 4) | ((iy & 3) << 2) | (ix & 3));
+        if (kWide) return g.bricks + ((((size_t)(iz >> 1) * (size_t)g.nby + (size_t)(iy >> 2)) * (size_t)g.nbx + (size_t)(ix >> 2)) * 32 + in);
+        return g.bricks + ((unsigned)(((iz >> 1) * g.nby + (iy >> 2)) * g.nbx + (ix >> 2)) * 32u + in);
     }
     if (kWide) return g.grid + (((size_t)iz * (size_t)g.ny + (size_t)iy) * (size_t)g.nx + (size_t)ix);
     return g.grid + (unsigned)((iz * g.ny + iy) * g.nx + ix);

@@ -59,6 +59,7 @@ def lib():
         L.oracle_set_spheres.argtypes = [vp, C.c_int, ip, dp, dp]
         L.oracle_set_sdf.argtypes = [vp, ip, dp, C.c_double, C.POINTER(C.c_float)]
         L.oracle_set_self_collision.argtypes = [vp, C.c_int, ip]
+        L.oracle_set_cost_extras.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, C.c_double]
         L.oracle_set_start_goal.argtypes = [vp, dp, dp]
         L.oracle_set_initial_trajectory.argtypes = [vp, dp]
         L.oracle_get_policy.argtypes = [vp, dp, dp, dp, dp, dp, dp]
@@ -166,6 +167,16 @@ class Oracle:
         """pairs: [n][2] sphere indices checked against each other; empty switches the check off"""
         pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
         rc = lib().oracle_set_self_collision(self.h, len(pr), _ip(pr))
+        assert rc == 0, rc
+
+    def set_cost_extras(self, smooth=None, joint_constraint=None):
+        """smooth: (margin, weight) or None; joint_constraint: (value [D], tolerance [D], weight) or None"""
+        sm = smooth or (0.0, 1.0)
+        if joint_constraint is not None:
+            v, tol, w = _c64(joint_constraint[0]), _c64(joint_constraint[1]), float(joint_constraint[2])
+            rc = lib().oracle_set_cost_extras(self.h, int(smooth is not None), float(sm[0]), float(sm[1]), 1, _dp(v), _dp(tol), w)
+        else:
+            rc = lib().oracle_set_cost_extras(self.h, int(smooth is not None), float(sm[0]), float(sm[1]), 0, None, None, 1.0)
         assert rc == 0, rc
 
     def set_sdf(self, sdf, analytic=None):

@@ -278,6 +278,17 @@ static inline bool sphere_collides(const SdfSpec& g, const double c[3], double r
     return (d - radius) < 0.0;
 }
 
+// distance the grid holds under a centre, as a double (the number sphere_collides compares with the radius)
+static inline double sphere_distance(const SdfSpec& g, const double c[3])
+{
+    const size_t idx = sdf_index(g, c);
+    if (g.grid) return (double)g.grid[idx];
+    const size_t plane = (size_t)g.nx * (size_t)g.ny;
+    const int iz = (int)(idx / plane), iy = (int)((idx - (size_t)iz * plane) / (size_t)g.nx);
+    const int ix = (int)(idx - (size_t)iz * plane - (size_t)iy * (size_t)g.nx);
+    return (double)primitive_field_value(g.prims, g.num_prims, g.ox, g.oy, g.oz, g.h, ix, iy, iz);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Self collision (the "self" half of robot_model's isStateValid; the reference's SRDF lists the link
 // pairs that are NOT checked: test/data/kuka_iiwa.srdf:46-70).  A pair of link spheres (i, j) collides

@@ -22,7 +22,7 @@ struct oracle_config {
     double movement_duration, control_cost_weight, min_cost_improvement;
     double noise_stddev[32], noise_decay[32], noise_min_stddev[32];
     int32_t use_noise_adaptation, use_openmp;
-    int32_t use_cumulative_costs;   // reference default 1 (PolicyImprovement.cpp:56)
+    int32_t use_cumulative_costs;   // reference default 1 (PolicyImprovement.cpp:56); 0 per time step; 2 forward cumulation (:473-477)
     int32_t use_projection;         // reference default 0 (PolicyImprovement.cpp:57)
     int32_t per_timestep_minmax;    // 0 = shipped behaviour; 1 = variant commented out at :518-528
     int32_t dense_control_costs;    // 1 = keep the reference's O(N^2) evaluation forms (CPU baseline)
@@ -70,6 +70,7 @@ void apply_switches(OracleHandle* h)
     pi.dense_control_costs_ = h->cfg.dense_control_costs != 0;
     pi.per_timestep_minmax_ = h->cfg.per_timestep_minmax != 0;
     pi.setCostCumulation(h->cfg.use_cumulative_costs != 0);
+    pi.forward_cumulation_ = h->cfg.use_cumulative_costs == 2;      // 2 = forward cumulation (cost-to-go)
     if ((h->cfg.use_projection != 0) != pi.use_projection_) {
         pi.use_projection_ = h->cfg.use_projection != 0;
         pi.preComputeProjectionMatrices();
@@ -127,6 +128,27 @@ int oracle_set_spheres(void* hp, int S, const int32_t* link, const double* xyz, 
         sp.link = link[s];
         for (int i = 0; i < 3; ++i) sp.l[i] = xyz[3 * s + i];
         sp.r = radius[s];
+    }
+    return 0;
+}
+
+// alternative state costs (stomp_oracle.hpp: SphereSdfTask): smooth obstacle cost and / or joint-constraint cost;
+// value / tolerance [D] may be NULL when use_joint_constraint == 0
+int oracle_set_cost_extras(void* hp, int use_smooth, double smooth_margin, double smooth_weight, int use_joint_constraint,
+                           const double* value, const double* tolerance, double jc_weight)
+{
+    OracleHandle* h = static_cast<OracleHandle*>(hp);
+    if (!h || !h->task) return -1;
+    h->task->smooth_cost_ = use_smooth != 0;
+    h->task->smooth_margin_ = smooth_margin;
+    h->task->smooth_weight_ = smooth_weight;
+    h->task->joint_constraint_ = use_joint_constraint != 0;
+    h->task->jc_weight_ = jc_weight;
+    const int D = h->task->stomp_config_.num_dimensions_;
+    if (use_joint_constraint) {
+        if (!value || !tolerance) return -1;
+        h->task->jc_value_.assign(value, value + D);
+        h->task->jc_tolerance_.assign(tolerance, tolerance + D);
     }
     return 0;
 }
@@ -498,7 +520,12 @@ int oracle_state_costs(void* hp, const double* theta, int K, double* costs, uint
         for (int t = 0; t < T; ++t) {
             for (int d = 0; d < D; ++d) q[d] = theta[((size_t)k * D + d) * T + t];
             bool hit = h->task->stateCollides(q.data());
-            if (costs) costs[(size_t)k * T + t] = hit ? 1.0 : 0.0;
+            if (costs) {      // SphereSdfTask::execute's cost of the state, alternative costs included
+                double c = hit ? 1.0 : 0.0;
+                if (h->task->smooth_cost_) c = h->task->statePenetration(q.data());
+                if (h->task->joint_constraint_) c += h->task->jointConstraintCost(q.data());
+                costs[(size_t)k * T + t] = c;
+            }
             if (verdict) verdict[(size_t)k * T + t] = hit ? 1 : 0;
             if (validity && t == T - 1) validity[k] = hit ? 0 : 1;
         }

@@ -662,7 +662,10 @@ bool PolicyImprovement::computeRolloutCumulativeCosts(Rollout& rollout)
     for (int d = 0; d < num_dimensions_; ++d) {
         for (int t = 0; t < T; ++t) rollout.total_costs_[d][t] = rollout.state_costs_[t] + rollout.control_costs_[d][t];
         rollout.cumulative_costs_[d] = rollout.total_costs_[d];
-        if (use_cumulative_costs_) {
+        if (use_cumulative_costs_ && forward_cumulation_) {
+            // "this is forward cumulation": the variant the reference keeps commented out at :473-477 (cost-to-go)
+            for (int t = T - 2; t >= 0; --t) rollout.cumulative_costs_[d][t] += rollout.cumulative_costs_[d][t + 1];
+        } else if (use_cumulative_costs_) {
             double s = 0.0;
             for (int t = 0; t < T; ++t) s += rollout.total_costs_[d][t];
             for (int t = 0; t < T; ++t) rollout.cumulative_costs_[d][t] = 1.0 * s;
@@ -929,6 +932,36 @@ bool SphereSdfTask::stateCollides(const double* q) const
     return hit;
 }
 
+double SphereSdfTask::statePenetration(const double* q) const
+{
+    Frame f; frame_identity(f);
+    size_t s = 0;
+    double pen = 0.0;
+    for (size_t d = 0; d < joints_.size(); ++d) {
+        apply_joint(f, joints_[d], q[d]);
+        while (s < spheres_.size() && spheres_[s].link == (int)d) {
+            double c[3];
+            sphere_centre(f, spheres_[s], c);
+            const double soft = spheres_[s].r + smooth_margin_;
+            const double depth = soft - sphere_distance(sdf_, c);
+            if (depth > 0.0) pen = pen + depth;
+            ++s;
+        }
+    }
+    return smooth_weight_ * pen;
+}
+
+// OptimizationTask::getConstrainDifference (OptimizationTask.cpp:218-237), same statement order
+double SphereSdfTask::jointConstraintCost(const double* q) const
+{
+    double constraint_cost = 0.0;
+    for (size_t i = 0; i < jc_value_.size(); ++i) {
+        const double diff_value = jc_tolerance_[i] - std::fabs(jc_value_[i] - q[i]);
+        if (diff_value < 0.0) constraint_cost = constraint_cost + (-1.0 * diff_value);
+    }
+    return jc_weight_ * constraint_cost;
+}
+
 // OptimizationTask.cpp:137-204: the trajectory evaluated is `parameters` (not the projected one);
 // validity is overwritten at every timestep and so reports the last timestep only.
 bool SphereSdfTask::execute(const std::vector<Vec>& parameters, const std::vector<Vec>& /*projected_parameters*/,
@@ -943,7 +976,9 @@ bool SphereSdfTask::execute(const std::vector<Vec>& parameters, const std::vecto
         double collision_cost;
         if (stateCollides(q.data())) { collision_cost = 1.0; validity = false; }
         else { collision_cost = 0.0; validity = true; }
+        if (smooth_cost_) collision_cost = statePenetration(q.data());
         costs[t] = collision_cost;
+        if (joint_constraint_) costs[t] += jointConstraintCost(q.data());     // computeJointsConstraintCost (:206-216)
     }
     return true;
 }

@@ -166,6 +166,7 @@ public:
     double cost_scaling_h_;
     bool use_cumulative_costs_, use_projection_;
     bool dense_control_costs_ = false;   // evaluation form only, same doubles either way
+    bool forward_cumulation_ = false;    // cumulative_costs_ = cost-to-go: the commented-out variant at :473-477 (switch, default off)
     bool per_timestep_minmax_ = false;   // the commented-out variant at :518-528 (switch, default off)
     std::shared_ptr<CovariantMovementPrimitive> policy_;
     std::vector<Mat> control_costs_, inv_control_costs_, projection_matrix_, inv_projection_matrix_;
@@ -223,6 +224,21 @@ public:
     double getControlCostWeight() override { return stomp_config_.control_cost_weight_; }
     // verdict of one joint configuration (what robot_model's updateJointGroup + isStateValid returned)
     bool stateCollides(const double* q) const;
+    // Alternative state costs, both off by default:
+    //  smooth obstacle cost — the cost of a state grows with the penetration of the link spheres into the clearance band
+    //    instead of jumping to 1 (the shape of the non-boolean obstacles of stomp/test/stomp_2d_test.cpp:337-363, carried
+    //    over to spheres and a distance field): weight * sum_s max(0, (r_s + margin) - d_s), spheres in index order;
+    //  joint-constraint cost — OptimizationTask::computeJointsConstraintCost / getConstrainDifference
+    //    (src/wrappers/stomp/OptimizationTask.cpp:206-237; its call at :169-172 is commented out in the reference):
+    //    weight * sum_d max(0, |value_d - q_d| - tolerance_d), added to the state cost.
+    // Validity stays the binary verdict either way.
+    double statePenetration(const double* q) const;
+    double jointConstraintCost(const double* q) const;
+    bool smooth_cost_ = false;
+    double smooth_margin_ = 0.0, smooth_weight_ = 1.0;
+    bool joint_constraint_ = false;
+    Vec jc_value_, jc_tolerance_;
+    double jc_weight_ = 1.0;
     void sphereCentres(const double* q, double* centres /*[S][3]*/) const;
 
     StompConfig stomp_config_;

@@ -774,3 +774,81 @@ def test_fused_control_cost_sums_of_the_recurrence_sampler(monkeypatch):
                     np.testing.assert_allclose(eng.tensor("parameters")[0], o.parameters(), rtol=RTOL, atol=1e-12)
                     np.testing.assert_allclose(eng.tensor("stddevs")[0], o.stddevs(), rtol=RTOL)
                     np.testing.assert_allclose(c, cost, rtol=RTOL)
+
+
+def test_forward_cumulation_variant():
+    """cumulative_costs_(t) = sum_{t' >= t} total_costs_(t'): the "forward cumulation" the reference keeps commented out at
+    PolicyImprovement.cpp:473-477, selected with use_cumulative_costs = 2.  Cost-to-go differs per time step, so the
+    per-time-step probability machinery runs; against the oracle's statement of the three commented lines."""
+    pb = P.single_arm_problem(K=24, T=40, sdf_n=64)
+    T, D, K = pb.num_time_steps, pb.chain.num_dimensions, pb.num_rollouts
+    o, e, pol = _projection_pair(pb, use_cumulative_costs=2)
+    o_total, _, _ = _projection_pair(pb)
+    o.begin_solve(); e.begin_solve(); o_total.begin_solve()
+    rng = np.random.default_rng(31)
+    for it in range(4):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((K, D, T)))
+        o.iterate(it, noise=unit)
+        cost, valid, _ = e.iterate(it, noise=unit[None])
+        p_ref = o.field("probabilities")
+        assert not np.all(p_ref == p_ref[:, :, :1])           # the probabilities do depend on the time step
+        cum = o.field("cumulative_costs")
+        assert np.all(np.diff(cum, axis=2) <= 1e-12)           # cost-to-go falls along the trajectory
+        np.testing.assert_allclose(e.tensor("probabilities")[0], p_ref, rtol=RTOL, atol=1e-300)
+        np.testing.assert_allclose(e.tensor("full_probabilities")[0], o.field("full_probabilities"), rtol=RTOL, atol=1e-300)
+        np.testing.assert_allclose(e.tensor("updates")[0], o.updates(), rtol=RTOL, atol=1e-13)
+        np.testing.assert_allclose(e.tensor("parameters")[0], o.parameters(), rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(e.tensor("stddevs")[0], o.stddevs(), rtol=RTOL)
+        np.testing.assert_allclose(cost[0], o.noiseless()["total_cost"], rtol=RTOL)
+    o_total.iterate(0, noise=unit)
+    assert not np.allclose(o_total.parameters(), o.parameters())
+
+
+@pytest.mark.parametrize("mode", ["smooth", "joint_constraint", "both"])
+def test_alternative_state_costs(mode, medium_problem):
+    """the smooth obstacle cost (penetration of the link spheres into the clearance band, the non-boolean
+    obstacle shape of stomp_2d_test.cpp:337-363) and the joint-constraint cost of OptimizationTask::computeJointsConstraintCost
+    (OptimizationTask.cpp:206-237, call commented out in the reference).  State costs are no longer 0 / 1: the whole
+    iteration against the oracle, the verdicts still bit-exact."""
+    pb = medium_problem
+    T, D, K = pb.num_time_steps, pb.chain.num_dimensions, pb.num_rollouts
+    o, e, pol = _pair(pb)
+    smooth = (0.05, 3.0) if mode in ("smooth", "both") else None
+    jc = None
+    if mode in ("joint_constraint", "both"):
+        mid = 0.5 * (np.asarray(pb.start).reshape(-1)[:D] + np.asarray(pb.goal).reshape(-1)[:D])
+        jc = (mid, np.full(D, 0.3), 0.7)
+    o.set_cost_extras(smooth=smooth, joint_constraint=jc)
+    e.set_cost_extras(smooth=smooth, joint_constraint=jc)
+    o.begin_solve(); e.begin_solve()
+    rng = np.random.default_rng(37)
+    seen_fraction = False
+    for it in range(3):
+        unit = np.einsum("tu,kdu->kdt", pol["L"], rng.standard_normal((K, D, T)))
+        o.iterate(it, noise=unit)
+        cost, valid, _ = e.iterate(it, noise=unit[None])
+        sc_ref = o.field("state_costs")
+        seen_fraction = seen_fraction or bool(np.any((sc_ref > 0) & (sc_ref != 1.0)))
+        np.testing.assert_allclose(e.tensor("state_costs")[0], sc_ref, rtol=RTOL, atol=1e-15)
+        np.testing.assert_array_equal(e.tensor("rollout_validity")[0], o.rollout_validity())
+        np.testing.assert_allclose(e.tensor("total_cost")[0], o.field("total_cost"), rtol=RTOL)
+        np.testing.assert_allclose(e.tensor("probabilities")[0], o.field("probabilities"), rtol=RTOL, atol=1e-300)
+        np.testing.assert_allclose(e.tensor("updates")[0], o.updates(), rtol=RTOL, atol=1e-13)
+        np.testing.assert_allclose(e.tensor("parameters")[0], o.parameters(), rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(e.tensor("stddevs")[0], o.stddevs(), rtol=RTOL)
+        nl = o.noiseless()
+        np.testing.assert_allclose(cost[0], nl["total_cost"], rtol=RTOL)
+        np.testing.assert_allclose(e.tensor("noiseless_state_costs")[0], nl["state_costs"], rtol=RTOL, atol=1e-15)
+        assert bool(valid[0]) == nl["valid"]
+    assert seen_fraction, "the problem never produced a non-binary state cost"
+    # the stand-alone cost call carries the same costs
+    theta = e.tensor("rollouts")[0][:4]
+    costs, verdicts, validity = e.evaluate_states(theta)
+    rc, rv, _ = o.state_costs(theta, threads=1)
+    np.testing.assert_array_equal(verdicts.astype(bool), rv.astype(bool))
+    np.testing.assert_allclose(costs, rc, rtol=RTOL, atol=1e-15)
+    # switching the extras off restores the 0 / 1 cost
+    e.set_cost_extras()
+    costs01, _, _ = e.evaluate_states(theta)
+    np.testing.assert_array_equal(costs01, verdicts.astype(np.float64))
+    assert not np.array_equal(costs01, costs)
