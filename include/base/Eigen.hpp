@@ -29,6 +29,21 @@ private:
     std::vector<double> v_;
 };
 
+class Vector3d {   // positions / dimensions of world objects (base::Vector3d of base-types)
+public:
+    Vector3d() : v_{0.0, 0.0, 0.0} {}
+    Vector3d(double x, double y, double z) : v_{x, y, z} {}
+    static Vector3d Zero() { return Vector3d(); }
+    double& x() { return v_[0]; } double& y() { return v_[1]; } double& z() { return v_[2]; }
+    double x() const { return v_[0]; } double y() const { return v_[1]; } double z() const { return v_[2]; }
+    double& operator()(int i) { return v_[i]; }
+    double operator()(int i) const { return v_[i]; }
+    double& operator[](int i) { return v_[i]; }
+    double operator[](int i) const { return v_[i]; }
+private:
+    double v_[3];
+};
+
 class MatrixXd {   // row major
 public:
     MatrixXd() : r_(0), c_(0) {}

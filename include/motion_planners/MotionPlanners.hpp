@@ -27,6 +27,12 @@ public:
     bool usePredictedTrajectory(base::JointsTrajectory& input_trajectory, PlannerStatus& planner_status);
     void setStartAndGoal();
     bool solve(base::JointsTrajectory& solution, PlannerStatus& planner_status, double& time_taken);
+    // world and grasp objects, octomap (reference src/MotionPlanners.cpp:162-173,416-495): they change the scene the distance
+    // field is built from (on the device, before the next validity check or solve) resp. the sphere list of the arm
+    bool handleCollisionObjectInWorld(const ModelObject& known_object);
+    bool handleGraspObject(const ModelObject& known_object);
+    void updateOctomap(const OccupiedLeaves& octomap);
+    void assignOctomapPlanningScene(const OccupiedLeaves& octomap);
     std::shared_ptr<robot_model::RobotModel> getRobotModel() { return robot_model_; }
 
     AbstractPlannerPtr planner_;

@@ -31,7 +31,9 @@ struct Joint {
 namespace robot_model {
 
 struct CollisionSphere { int link; double xyz[3]; double radius; };      // link = index of the chain joint
-struct Obstacle { int kind; double centre[3]; double size[3]; std::string name; };   // kind 0 sphere (size[0] = r), 1 box (half extents)
+struct Obstacle { int kind; double centre[3]; double size[3]; std::string name; };   // kind 0 sphere (size[0] = r), 1 box (half extents), 2 cylinder along z (radius, half height)
+struct MeshObstacle { std::string name; std::vector<double> triangles; bool solid = true; };   // triangles [n][3][3] in the world frame
+struct GraspObject { std::string name; std::vector<CollisionSphere> spheres; };            // spheres in the frame of the link they ride on
 
 struct SignedDistanceField {
     int dims[3] = {0, 0, 0};
@@ -81,7 +83,24 @@ public:
     // before the next query / solve, so a change takes effect immediately, as in the reference.
     void addObstacle(const Obstacle& o) { obstacles_.push_back(o); sceneChanged(); }
     bool removeObstacle(const std::string& name);
-    void clearObstacles() { obstacles_.clear(); sceneChanged(); }
+    void clearObstacles() { obstacles_.clear(); meshes_.clear(); leaf_centres_.clear(); leaf_sizes_.clear(); sceneChanged(); }
+    // mesh world objects (the reference's MESH model objects): voxelised on the device, conservatively, interior filled when
+    // `solid`; and an octomap as its occupied leaves (assignOctomapPlanningScene / updateOctomap): centres [m][3], edge
+    // lengths [m].  With either present the field is the exact distance transform of the voxelised scene
+    // (stomp_b200_build_sdf_scene) on the grid of setSdfGrid (or of setOccupancy); primitives are voxelised into it too.
+    void addMeshObstacle(const MeshObstacle& m) { meshes_.push_back(m); sceneChanged(); }
+    bool addMeshObstacleFromStl(const std::string& name, const std::string& path, const double position[3], const double scale[3] = nullptr, bool solid = true);
+    void setOctomapLeaves(const std::vector<double>& centres, const std::vector<double>& sizes) { leaf_centres_ = centres; leaf_sizes_ = sizes; sceneChanged(); }
+    const std::vector<MeshObstacle>& meshObstacles() const { return meshes_; }
+    // grasped objects (MotionPlanners::handleGraspObject -> robot_model addGraspObject / removeGraspObject): the object's
+    // spheres ride on the chain link `link_name` (the tip link when empty) from now on; engines pick the new sphere list up
+    // before their next use, like a scene change
+    bool addGraspObject(const GraspObject& object, const std::string& link_name);
+    bool removeGraspObject(const std::string& name);
+    // spheres for every chain link that has none, fitted to the link's collision mesh / primitive of the URDF
+    // (MeshTools.hpp: fitSpheres); returns the number of links that received spheres
+    int fitSpheresFromUrdfGeometry(int max_spheres_per_link = 6, double padding = 0.0);
+    unsigned long robotRevision() const { return robot_revision_; }
     // occupancy world [nz][ny][nx] (a voxelised mesh, or an octomap's leaves at the grid's resolution): the field is then
     // its exact Euclidean distance transform; primitives present at the same time are voxelised into it
     void setOccupancy(const int dims[3], const double origin[3], double voxel, const std::vector<unsigned char>& occupied);
@@ -111,12 +130,21 @@ private:
     std::vector<CollisionSphere> spheres_;
     std::vector<std::pair<std::string, std::string> > disabled_link_pairs_;
     std::vector<Obstacle> obstacles_;
+    std::vector<MeshObstacle> meshes_;
+    std::vector<double> leaf_centres_, leaf_sizes_;
+    std::vector<CollisionSphere> link_spheres_;           // the robot's own spheres (spheres_ = these + the grasp objects')
+    std::vector<std::pair<GraspObject, int> > grasp_objects_;   // object, chain link index
+    struct LinkGeometry { std::string link; int kind = -1; double size[3] = {0, 0, 0}; double origin[3] = {0, 0, 0}; std::string mesh_file; double mesh_scale[3] = {1, 1, 1}; };
+    std::vector<LinkGeometry> link_geometry_;             // collision geometry of the URDF links, for sphere fitting
+    unsigned long robot_revision_ = 1;                    // bumped when the sphere list changes
+    void rebuildSphereList();
     SignedDistanceField sdf_;
     int sdf_resolution_ = 64;
     double sdf_lower_[3] = {-1.5, -1.5, -1.5}, sdf_upper_[3] = {1.5, 1.5, 1.5};
     bool sdf_dirty_ = true;
     bool sdf_explicit_ = false;             // sdf_ was handed in by setSdf and is what the engines get
     unsigned long scene_revision_ = 1;
+    unsigned long validity_robot_revision_ = 0;
     unsigned long validity_revision_ = 0;   // scene revision validity_engine_ was configured at
     std::vector<unsigned char> occupancy_;  // [nz][ny][nx], empty: primitive world
     int occ_dims_[3] = {0, 0, 0};

@@ -120,7 +120,8 @@ int stomp_b200_set_sdf(stomp_b200_engine* e, const int32_t dims[3], const double
  * (src/MotionPlanners.cpp:162-173 assignOctomapPlanningScene / updateOctomap, :416-495 handleCollisionObjectInWorld /
  * handleGraspObject; include/motion_planners/Config.hpp:14-35).  Here they become the distance field the state kernel
  * gathers from, without a host grid or a host-to-device copy of it:
- *   primitives: kind[i] 0 = sphere (size[i][0] = radius), 1 = box (size[i] = half extents); exact signed distance of
+ *   primitives: kind[i] 0 = sphere (size[i][0] = radius), 1 = box (size[i] = half extents), 2 = cylinder along z
+ *     (size[i] = radius, half height) — the reference's PrimitiveObject types box / cylinder / sphere; exact signed distance of
  *     the union at every voxel centre origin + (i + 0.5) * voxel_size, FP64, rounded to binary32;
  *   occupancy [nz][ny][nx] uint8 (a voxelised mesh, or the leaves of an octomap at the grid's resolution): exact
  *     Euclidean distance transform, centre to centre, positive outside the occupied set and negative inside.
@@ -130,6 +131,17 @@ int stomp_b200_build_sdf_primitives(stomp_b200_engine* e, const int32_t dims[3],
                                     const double* size /*[n][3]*/);
 int stomp_b200_build_sdf_occupancy(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
                                    const uint8_t* occupied /*[nz][ny][nx]*/);
+/* The general scene: the union of
+ *   a triangle mesh (the reference's MESH model objects; triangles [n][3 vertices][xyz] in the grid's frame), voxelised
+ *     conservatively on the device (a voxel is occupied when its cube touches a triangle); solid != 0 also fills the
+ *     interior of closed meshes (free voxels the grid's boundary cannot reach);
+ *   octomap leaves (occupied cubes: centre [m][3] and edge length [m]; a voxel is occupied when its centre lies in a leaf);
+ *   an occupancy grid (may be NULL);
+ * followed by the exact distance transform of stomp_b200_build_sdf_occupancy.  Any of the three parts may be empty. */
+int stomp_b200_build_sdf_scene(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
+                               int32_t num_triangles, const double* triangles /*[n][3][3] or NULL*/, int32_t solid,
+                               int32_t num_leaves, const double* leaf_centres /*[m][3] or NULL*/,
+                               const double* leaf_sizes /*[m] or NULL*/, const uint8_t* occupied /*[nz][ny][nx] or NULL*/);
 int stomp_b200_get_sdf(stomp_b200_engine* e, float* out, size_t count, int32_t dims_out[3], double origin_out[3],
                        double* voxel_size_out);
 

@@ -37,7 +37,13 @@ public:
     virtual bool getPolicy(boost::shared_ptr<stomp::CovariantMovementPrimitive>& policy);
     virtual bool setPolicy(const boost::shared_ptr<stomp::CovariantMovementPrimitive> policy);
     virtual double getControlCostWeight();
-    void setOptimizationConstraints(ConstraintPlanning constraints) { constraints_ = constraints; }
+    void setOptimizationConstraints(ConstraintPlanning constraints) { constraints_ = constraints; costs_dirty_ = true; }
+    // The reference computes the joint-constraint cost in computeJointsConstraintCost (OptimizationTask.cpp:206-216) but keeps
+    // its call in execute() commented out (:169-172).  Off by default here too; when switched on, a JOINTS_CONSTRAINT set
+    // with setOptimizationConstraints adds weight * sum_d max(0, |value_d - q_d| - tolerance_d) to every state cost.
+    void useJointsConstraintCost(bool on, double weight = 1.0) { use_joints_constraint_cost_ = on; joints_constraint_weight_ = weight; costs_dirty_ = true; }
+    // Smooth obstacle cost in place of the 0 / 1 collision cost (see stomp_b200_set_cost_extras); off by default.
+    void useSmoothObstacleCost(bool on, double margin = 0.05, double weight = 1.0) { use_smooth_cost_ = on; smooth_margin_ = margin; smooth_weight_ = weight; costs_dirty_ = true; }
 
     // the device engine for this task's configuration, created on first use
     stomp_b200_engine* engine();
@@ -55,7 +61,11 @@ private:
     std::vector<std::string> planning_group_joints_names_;
     std::vector<double> lower_limits_, upper_limits_;
     ConstraintPlanning constraints_;
+    bool use_joints_constraint_cost_ = false, use_smooth_cost_ = false, costs_dirty_ = false;
+    double joints_constraint_weight_ = 1.0, smooth_margin_ = 0.05, smooth_weight_ = 1.0;
+    bool applyCostSwitches();
     stomp_b200_engine* engine_ = nullptr;
+    unsigned long robot_revision_ = 0;    // robot_model_->robotRevision() the engine's sphere list was uploaded at (grasp objects change it)
     unsigned long scene_revision_ = 0;    // robot_model_->sceneRevision() the engine's distance field was built at
 };
 

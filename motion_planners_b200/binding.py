@@ -38,7 +38,7 @@ SYMBOLS = [
     "stomp_b200_set_timeline", "stomp_b200_get_timeline", "stomp_b200_launch_count", "stomp_b200_graph_replays", "stomp_b200_timer_begin", "stomp_b200_timer_end", "stomp_b200_synchronize",
     "stomp_b200_state_kernel_kind", "stomp_b200_state_kernel_source", "stomp_b200_codegen_selftest",
     "stomp_b200_set_cost_cumulation", "stomp_b200_set_self_collision", "stomp_b200_set_cost_extras",
-    "stomp_b200_build_sdf_primitives", "stomp_b200_build_sdf_occupancy", "stomp_b200_get_sdf",
+    "stomp_b200_build_sdf_primitives", "stomp_b200_build_sdf_occupancy", "stomp_b200_build_sdf_scene", "stomp_b200_get_sdf",
 ]
 
 
@@ -97,6 +97,7 @@ def lib():
         L.stomp_b200_set_self_collision.argtypes = [vp, C.c_int32, ip]
         L.stomp_b200_build_sdf_primitives.argtypes = [vp, ip, dp, C.c_double, C.c_int32, ip, dp, dp]
         L.stomp_b200_build_sdf_occupancy.argtypes = [vp, ip, dp, C.c_double, u8p]
+        L.stomp_b200_build_sdf_scene.argtypes = [vp, ip, dp, C.c_double, C.c_int32, dp, C.c_int32, C.c_int32, dp, dp, u8p]
         L.stomp_b200_get_sdf.argtypes = [vp, C.POINTER(C.c_float), C.c_size_t, ip, dp, dp]
         L.stomp_b200_set_control_cost_matrices.argtypes = [vp, dp, dp, dp]
         L.stomp_b200_set_policy.argtypes = [vp, C.c_int32, dp, dp]
@@ -293,6 +294,20 @@ class Engine:
         org = _c64(origin)
         self._check(lib().stomp_b200_build_sdf_occupancy(self.h, _ip(dims), _dp(org), float(voxel),
                                                          occ.ctypes.data_as(C.POINTER(C.c_uint8))), "stomp_b200_build_sdf_occupancy")
+
+    def build_sdf_scene(self, dims, origin, voxel, triangles=None, solid=False, leaf_centres=None, leaf_sizes=None, occupied=None):
+        """Mesh (triangles [n][3][3]) + octomap leaves (centres [m][3], edge lengths [m]) + occupancy grid -> signed distance
+        field, voxelised and transformed on the device (stomp_b200_build_sdf_scene)."""
+        dims = np.ascontiguousarray(dims, dtype=np.int32)
+        org = _c64(origin)
+        tri = _c64(triangles).reshape(-1, 9) if triangles is not None else np.zeros((0, 9))
+        lc = _c64(leaf_centres).reshape(-1, 3) if leaf_centres is not None else np.zeros((0, 3))
+        ls = _c64(leaf_sizes).reshape(-1) if leaf_sizes is not None else np.zeros(0)
+        occ = np.ascontiguousarray(occupied, dtype=np.uint8) if occupied is not None else None
+        u8 = C.POINTER(C.c_uint8)
+        self._check(lib().stomp_b200_build_sdf_scene(self.h, _ip(dims), _dp(org), float(voxel), len(tri), _dp(tri) if len(tri) else None,
+                                                     int(solid), len(ls), _dp(lc) if len(ls) else None, _dp(ls) if len(ls) else None,
+                                                     occ.ctypes.data_as(u8) if occ is not None else None), "stomp_b200_build_sdf_scene")
 
     def get_sdf(self):
         """(grid float32 [nz][ny][nx], origin[3], voxel) of the field the engine holds."""

@@ -1682,7 +1682,7 @@ int stomp_b200_build_sdf_primitives(stomp_b200_engine* e, const int32_t dims[3],
     if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || dims[1] > 65535 || dims[2] > 65535) return STOMP_B200_ERR_INVALID_ARGUMENT;
     if (num_primitives > kMaxPrimitives) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "too many primitives for one call (256)");
     for (int i = 0; i < num_primitives; ++i)
-        if (kind[i] != 0 && kind[i] != 1) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "primitive kind must be 0 (sphere) or 1 (box)");
+        if (kind[i] < 0 || kind[i] > 2) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "primitive kind must be 0 (sphere), 1 (box) or 2 (cylinder along z)");
     if (int rc = adopt_sdf_geometry(e, dims, origin, voxel_size)) return rc;
     std::vector<PrimitiveList> host(1);
     PrimitiveList& pl = host[0];
@@ -1708,22 +1708,16 @@ int stomp_b200_build_sdf_primitives(stomp_b200_engine* e, const int32_t dims[3],
     return build_sdf_bricks(e);
 }
 
-int stomp_b200_build_sdf_occupancy(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
-                                   const uint8_t* occupied)
+// exact signed Euclidean distance transform of a device occupancy grid into e->d_sdf (geometry already adopted)
+static int edt_from_device_occupancy(stomp_b200_engine* e, const uint8_t* d_occ, const char* what)
 {
-    if (!e || !dims || !origin || !occupied || !(voxel_size > 0.0)) return STOMP_B200_ERR_INVALID_ARGUMENT;
-    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || dims[0] > 1024 || dims[1] > 1024 || dims[2] > 1024)
-        return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "occupancy grids are limited to 1024 voxels per axis (exact int32 squared distances)");
-    if (int rc = adopt_sdf_geometry(e, dims, origin, voxel_size)) return rc;
     const size_t count = e->sdf_count;
-    const int nx = dims[0], ny = dims[1], nz = dims[2];
-    uint8_t* d_occ = nullptr; int32_t* d_a = nullptr; int32_t* d_b = nullptr; int32_t* d_c = nullptr;
-    auto cleanup = [&]() { cudaFree(d_occ); cudaFree(d_a); cudaFree(d_b); cudaFree(d_c); };
-    cudaError_t err = cudaMalloc(&d_occ, count);
-    if (err == cudaSuccess) err = cudaMalloc(&d_a, count * sizeof(int32_t));
+    const int nx = e->sdf.nx, ny = e->sdf.ny, nz = e->sdf.nz;
+    int32_t* d_a = nullptr; int32_t* d_b = nullptr; int32_t* d_c = nullptr;
+    auto cleanup = [&]() { cudaFree(d_a); cudaFree(d_b); cudaFree(d_c); };
+    cudaError_t err = cudaMalloc(&d_a, count * sizeof(int32_t));
     if (err == cudaSuccess) err = cudaMalloc(&d_b, count * sizeof(int32_t));
     if (err == cudaSuccess) err = cudaMalloc(&d_c, count * sizeof(int32_t));
-    if (err == cudaSuccess) err = cudaMemcpyAsync(d_occ, occupied, count, cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) {
         const unsigned blocks = (unsigned)((count + 255) / 256);
         edt_seed_kernel<<<blocks, 256, 0, e->stream>>>(d_occ, d_a, d_b, count);
@@ -1736,13 +1730,89 @@ int stomp_b200_build_sdf_occupancy(stomp_b200_engine* e, const int32_t dims[3], 
         };
         transform(d_a);
         transform(d_b);
-        finish_edt_kernel<<<blocks, 256, 0, e->stream>>>(d_occ, d_a, d_b, e->d_sdf, voxel_size, count);
+        finish_edt_kernel<<<blocks, 256, 0, e->stream>>>(d_occ, d_a, d_b, e->d_sdf, e->sdf_voxel, count);
         e->launch_count += 8;
         err = cudaGetLastError();
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
     cleanup();
-    if (err != cudaSuccess) { e->last_error = std::string("build_sdf_occupancy: ") + cudaGetErrorString(err); return STOMP_B200_ERR_CUDA; }
+    if (err != cudaSuccess) { e->last_error = std::string(what) + ": " + cudaGetErrorString(err); return STOMP_B200_ERR_CUDA; }
+    return STOMP_B200_OK;
+}
+
+int stomp_b200_build_sdf_occupancy(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
+                                   const uint8_t* occupied)
+{
+    return stomp_b200_build_sdf_scene(e, dims, origin, voxel_size, 0, nullptr, 0, 0, nullptr, nullptr, occupied);
+}
+
+int stomp_b200_build_sdf_scene(stomp_b200_engine* e, const int32_t dims[3], const double origin[3], double voxel_size,
+                               int32_t num_triangles, const double* triangles, int32_t solid, int32_t num_leaves,
+                               const double* leaf_centres, const double* leaf_sizes, const uint8_t* occupied)
+{
+    if (!e || !dims || !origin || !(voxel_size > 0.0) || num_triangles < 0 || num_leaves < 0) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if ((num_triangles > 0 && !triangles) || (num_leaves > 0 && (!leaf_centres || !leaf_sizes))) return STOMP_B200_ERR_INVALID_ARGUMENT;
+    if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || dims[0] > 1024 || dims[1] > 1024 || dims[2] > 1024)
+        return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "occupancy grids are limited to 1024 voxels per axis (exact int32 squared distances)");
+    for (size_t i = 0; i < (size_t)num_triangles * 9; ++i)
+        if (!(std::fabs(triangles[i]) <= 1e9)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "mesh vertex is not finite");
+    for (int i = 0; i < num_leaves; ++i)
+        if (!(leaf_sizes[i] > 0.0) || !(std::fabs(leaf_centres[3 * i]) <= 1e9) || !(std::fabs(leaf_centres[3 * i + 1]) <= 1e9) || !(std::fabs(leaf_centres[3 * i + 2]) <= 1e9))
+            return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "octomap leaf: centre not finite or size not positive");
+    if (int rc = adopt_sdf_geometry(e, dims, origin, voxel_size)) return rc;
+    const size_t count = e->sdf_count;
+    const int nx = dims[0], ny = dims[1], nz = dims[2];
+    uint8_t* d_occ = nullptr; uint8_t* d_out = nullptr; double* d_tri = nullptr; double* d_leaf = nullptr; int* d_flag = nullptr;
+    auto cleanup = [&]() { cudaFree(d_occ); cudaFree(d_out); cudaFree(d_tri); cudaFree(d_leaf); cudaFree(d_flag); };
+    cudaError_t err = cudaMalloc(&d_occ, count);
+    if (err == cudaSuccess) err = occupied ? cudaMemcpyAsync(d_occ, occupied, count, cudaMemcpyHostToDevice, e->stream) : cudaMemsetAsync(d_occ, 0, count, e->stream);
+    if (err == cudaSuccess && num_triangles > 0) {
+        err = cudaMalloc(&d_tri, sizeof(double) * 9 * (size_t)num_triangles);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d_tri, triangles, sizeof(double) * 9 * (size_t)num_triangles, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) {
+            voxelise_triangles_kernel<<<num_triangles, 128, 0, e->stream>>>(d_tri, num_triangles, d_occ, nx, ny, nz, origin[0], origin[1], origin[2], voxel_size);
+            e->launch_count++;
+            err = cudaGetLastError();
+        }
+        if (err == cudaSuccess && solid) {      // interior of the closed shells: free voxels the boundary cannot reach
+            err = cudaMalloc(&d_out, count);
+            if (err == cudaSuccess) err = cudaMalloc(&d_flag, sizeof(int));
+            if (err == cudaSuccess) {
+                flood_seed_kernel<<<(unsigned)((count + 255) / 256), 256, 0, e->stream>>>(d_occ, d_out, nx, ny, nz);
+                e->launch_count++;
+                for (int round = 0; round < 4096 && err == cudaSuccess; ++round) {
+                    int changed = 0;
+                    err = cudaMemsetAsync(d_flag, 0, sizeof(int), e->stream);
+                    flood_sweep_kernel<<<(ny * nz + 127) / 128, 128, 0, e->stream>>>(d_occ, d_out, nx, 1, ny, nx, nz, (long long)nx * ny, d_flag);
+                    flood_sweep_kernel<<<(nx * nz + 127) / 128, 128, 0, e->stream>>>(d_occ, d_out, ny, nx, nx, 1, nz, (long long)nx * ny, d_flag);
+                    flood_sweep_kernel<<<(nx * ny + 127) / 128, 128, 0, e->stream>>>(d_occ, d_out, nz, (long long)nx * ny, nx, 1, ny, nx, d_flag);
+                    e->launch_count += 3;
+                    if (err == cudaSuccess) err = cudaMemcpyAsync(&changed, d_flag, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+                    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+                    if (!changed) break;
+                }
+                if (err == cudaSuccess) {
+                    flood_fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, e->stream>>>(d_occ, d_out, count);
+                    e->launch_count++;
+                    err = cudaGetLastError();
+                }
+            }
+        }
+    }
+    if (err == cudaSuccess && num_leaves > 0) {
+        err = cudaMalloc(&d_leaf, sizeof(double) * 4 * (size_t)num_leaves);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d_leaf, leaf_centres, sizeof(double) * 3 * (size_t)num_leaves, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d_leaf + 3 * (size_t)num_leaves, leaf_sizes, sizeof(double) * (size_t)num_leaves, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) {
+            voxelise_leaves_kernel<<<num_leaves, 32, 0, e->stream>>>(d_leaf, d_leaf + 3 * (size_t)num_leaves, num_leaves, d_occ, nx, ny, nz, origin[0], origin[1], origin[2], voxel_size);
+            e->launch_count++;
+            err = cudaGetLastError();
+        }
+    }
+    if (err != cudaSuccess) { cleanup(); e->last_error = std::string("build_sdf_scene: ") + cudaGetErrorString(err); return STOMP_B200_ERR_CUDA; }
+    const int rc = edt_from_device_occupancy(e, d_occ, "build_sdf_scene");
+    cleanup();
+    if (rc) return rc;
     e->have_sdf = true;
     return build_sdf_bricks(e);
 }

@@ -1,6 +1,7 @@
 // motion_planners::MotionPlanners facade, reduced to the calls on the STOMP path
 // (reference src/MotionPlanners.cpp:16-60,91-160,175-219,497-515).
 #include <motion_planners/MotionPlanners.hpp>
+#include <robot_model/MeshTools.hpp>
 
 #include <chrono>
 #include <cmath>
@@ -167,5 +168,80 @@ bool MotionPlanners::solve(base::JointsTrajectory& solution, PlannerStatus& plan
     time_taken = elapsed.count();
     return res;
 }
+
+// ---- world / grasp objects (reference src/MotionPlanners.cpp:416-495) ----
+namespace {
+
+// the object's triangles in the frame it is given in (primitives are meshed for the sphere fit of grasp objects)
+bool object_triangles(const ModelObject& o, std::vector<double>& tris)
+{
+    const double c[3] = {o.relative_pose.position.x(), o.relative_pose.position.y(), o.relative_pose.position.z()};
+    if (o.model_type == collision_detection::MESH) return robot_model::loadStl(o.object_path, tris, nullptr, c);
+    if (o.model_type != collision_detection::PRIMITIVES) return false;
+    const collision_detection::PrimitiveObject& p = o.primitive_object;
+    if (p.primitive_type == collision_detection::BOX) {
+        const double half[3] = {0.5 * p.dimensions.x(), 0.5 * p.dimensions.y(), 0.5 * p.dimensions.z()};
+        robot_model::appendBoxMesh(c, half, tris);
+    } else if (p.primitive_type == collision_detection::CYLINDER) robot_model::appendCylinderMesh(c, p.radius, 0.5 * p.height, tris);
+    else if (p.primitive_type == collision_detection::SPHERE) robot_model::appendSphereMesh(c, p.radius, tris);
+    else return false;
+    return true;
+}
+
+}  // namespace
+
+bool MotionPlanners::handleCollisionObjectInWorld(const ModelObject& known_object)
+{
+    if (known_object.operation == collision_detection::RESET) { LOG_INFO_S << "[MotionPlanners]: Received known object with RESET"; return false; }
+    if (known_object.model_type == collision_detection::UNDEFINED) { LOG_INFO_S << "[MotionPlanners]: object " << known_object.object_name << " is of UNDEFINED type"; return false; }
+    if (known_object.operation == collision_detection::REMOVE) {
+        if (known_object.model_type == collision_detection::OCTREE) { LOG_WARN_S << "[MotionPlanners]: removing a region from the octomap: hand in the updated leaves with updateOctomap"; return false; }
+        return robot_model_->removeObstacle(known_object.object_name);
+    }
+    if (known_object.operation != collision_detection::ADD) return false;
+    if (!known_object.relative_pose.orientation_is_identity) { LOG_ERROR_S << "[MotionPlanners]: world objects must be axis aligned in the world frame"; return false; }
+    const base::Vector3d& c = known_object.relative_pose.position;
+    if (known_object.model_type == collision_detection::PRIMITIVES) {
+        const collision_detection::PrimitiveObject& p = known_object.primitive_object;
+        robot_model::Obstacle o;
+        o.name = known_object.object_name;
+        o.centre[0] = c.x(); o.centre[1] = c.y(); o.centre[2] = c.z();
+        if (p.primitive_type == collision_detection::BOX) { o.kind = 1; o.size[0] = 0.5 * p.dimensions.x(); o.size[1] = 0.5 * p.dimensions.y(); o.size[2] = 0.5 * p.dimensions.z(); }
+        else if (p.primitive_type == collision_detection::CYLINDER) { o.kind = 2; o.size[0] = p.radius; o.size[1] = 0.5 * p.height; o.size[2] = 0.0; }
+        else if (p.primitive_type == collision_detection::SPHERE) { o.kind = 0; o.size[0] = o.size[1] = o.size[2] = p.radius; }
+        else return false;
+        robot_model_->removeObstacle(o.name);
+        robot_model_->addObstacle(o);
+        return true;
+    }
+    if (known_object.model_type == collision_detection::MESH) {
+        const double pos[3] = {c.x(), c.y(), c.z()};
+        robot_model_->removeObstacle(known_object.object_name);
+        return robot_model_->addMeshObstacleFromStl(known_object.object_name, known_object.object_path, pos);
+    }
+    return false;
+}
+
+bool MotionPlanners::handleGraspObject(const ModelObject& known_object)
+{
+    if (known_object.operation == collision_detection::RESET) { LOG_INFO_S << "[MotionPlanners]: Received grasp object with RESET"; return false; }
+    if (known_object.operation == collision_detection::REMOVE) return robot_model_->removeGraspObject(known_object.object_name);
+    if (known_object.operation != collision_detection::ADD) return false;
+    std::vector<double> tris;
+    if (!object_triangles(known_object, tris)) return false;
+    robot_model::GraspObject g;
+    g.name = known_object.object_name;
+    for (const auto& f : robot_model::fitSpheres(tris, 8, 0.0)) {
+        robot_model::CollisionSphere s;
+        s.link = 0;
+        for (int i = 0; i < 3; ++i) s.xyz[i] = f.xyz[i];
+        s.radius = f.radius;
+        g.spheres.push_back(s);
+    }
+    return robot_model_->addGraspObject(g, known_object.attach_link_name);
+}
+
+void MotionPlanners::updateOctomap(const OccupiedLeaves& octomap) { robot_model_->setOctomapLeaves(octomap.centres, octomap.sizes); }
+void MotionPlanners::assignOctomapPlanningScene(const OccupiedLeaves& octomap) { robot_model_->setOctomapLeaves(octomap.centres, octomap.sizes); }
 
 }  // namespace motion_planners

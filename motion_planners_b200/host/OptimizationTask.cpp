@@ -94,11 +94,36 @@ void OptimizationTask::updatePolicy()
     movement_dt_ = policy_->getMovementDt();
 }
 
+// alternative state costs -> the engine (stomp_b200_set_cost_extras); the shipped configuration sends all-off
+bool OptimizationTask::applyCostSwitches()
+{
+    costs_dirty_ = false;
+    const int D = stomp_config_.num_dimensions_;
+    const bool jc = use_joints_constraint_cost_ && constraints_.use_constraint == motion_planners::JOINTS_CONSTRAINT &&
+                    (int)constraints_.joint_constraint.value.size() == D && (int)constraints_.joint_constraint.tolerance.size() == D;
+    std::vector<double> value(D, 0.0), tolerance(D, 0.0);
+    for (int d = 0; d < D && jc; ++d) { value[d] = constraints_.joint_constraint.value(d); tolerance[d] = constraints_.joint_constraint.tolerance(d); }
+    const int rc = stomp_b200_set_cost_extras(engine_, use_smooth_cost_ ? 1 : 0, smooth_margin_, smooth_weight_, jc ? 1 : 0,
+                                              value.data(), tolerance.data(), joints_constraint_weight_);
+    if (rc) LOG_ERROR_S << "[OptimizationTask]: " << stomp_b200_status_string(rc) << ": " << stomp_b200_last_error(engine_);
+    return rc == 0;
+}
+
 stomp_b200_engine* OptimizationTask::engine()
 {
     if (engine_) {
+        if (costs_dirty_ && !applyCostSwitches()) return nullptr;
         // a world object added / removed / moved since the engine was configured (reference: handleCollisionObjectInWorld,
         // updateOctomap take effect at once): rebuild the distance field on the device before the next use
+        if (robot_revision_ != robot_model_->robotRevision()) {       // a grasp object was attached / removed: new sphere list (+ scene)
+            const int rc = robot_model_->configureEngine(engine_);
+            if (rc) {
+                LOG_ERROR_S << "[OptimizationTask]: " << stomp_b200_status_string(rc) << ": " << stomp_b200_last_error(engine_);
+                return nullptr;
+            }
+            robot_revision_ = robot_model_->robotRevision();
+            scene_revision_ = robot_model_->sceneRevision();
+        }
         if (scene_revision_ != robot_model_->sceneRevision()) {
             const int rc = robot_model_->configureScene(engine_);
             if (rc) {
@@ -141,6 +166,8 @@ stomp_b200_engine* OptimizationTask::engine()
         return nullptr;
     }
     scene_revision_ = robot_model_->sceneRevision();
+    robot_revision_ = robot_model_->robotRevision();
+    if ((costs_dirty_ || use_smooth_cost_ || use_joints_constraint_cost_) && !applyCostSwitches()) return nullptr;
     return engine_;
 }
 

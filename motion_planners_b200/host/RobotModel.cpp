@@ -1,5 +1,6 @@
 // robot_model::RobotModel shim: URDF joint chain + link spheres + environment SDF for the CUDA path.
 #include <robot_model/RobotModel.hpp>
+#include <robot_model/MeshTools.hpp>
 
 #include <algorithm>
 #include <cmath>
@@ -66,13 +67,18 @@ void parse_triplet(const std::string& text, double out[3])
     for (int i = 0; i < 3; ++i) ss >> out[i];
 }
 
-struct UrdfLinkGeometry { bool has = false; int kind = 0; double size[3] = {0, 0, 0}; double origin[3] = {0, 0, 0}; };
+struct UrdfLinkGeometry { bool has = false; int kind = 0; double size[3] = {0, 0, 0}; double origin[3] = {0, 0, 0}; std::string mesh_file; double mesh_scale[3] = {1, 1, 1}; };
 
 // signed distance to one primitive: the formulas of the device builder (csrc/sdf_builder.cuh), operation for operation
 double obstacle_distance(const Obstacle& o, double x, double y, double z)
 {
     const double dx = x - o.centre[0], dy = y - o.centre[1], dz = z - o.centre[2];
     if (o.kind == 0) return std::sqrt((dx * dx + dy * dy) + dz * dz) - o.size[0];
+    if (o.kind == 2) {
+        const double qr = std::sqrt(dx * dx + dy * dy) - o.size[0], qh = std::fabs(dz) - o.size[1];
+        const double orr = std::fmax(qr, 0.0), oh = std::fmax(qh, 0.0);
+        return std::sqrt(orr * orr + oh * oh) + std::fmin(std::fmax(qr, qh), 0.0);
+    }
     const double qx = std::fabs(dx) - o.size[0], qy = std::fabs(dy) - o.size[1], qz = std::fabs(dz) - o.size[2];
     const double ox = std::fmax(qx, 0.0), oy = std::fmax(qy, 0.0), oz = std::fmax(qz, 0.0);
     const double outside = std::sqrt((ox * ox + oy * oy) + oz * oz);
@@ -139,6 +145,18 @@ bool RobotModel::loadUrdf(const std::string& path)
             UrdfLinkGeometry& g = link_geometry[current_link];
             g.has = true; g.kind = 0;
             g.size[0] = std::atof(tag.attr["radius"].c_str());
+        } else if (!current_link.empty() && in_collision && tag.name == "cylinder" && !tag.closing) {
+            UrdfLinkGeometry& g = link_geometry[current_link];
+            g.has = true; g.kind = 2;
+            g.size[0] = std::atof(tag.attr["radius"].c_str());
+            g.size[1] = 0.5 * std::atof(tag.attr["length"].c_str());
+        } else if (!current_link.empty() && in_collision && tag.name == "mesh" && !tag.closing) {
+            // <mesh filename="package://.../collision/link_1.stl" scale="..."/> (reference test/data/kuka_iiwa.urdf): kept for
+            // sphere fitting; the path is taken relative to the URDF's directory when it is not absolute
+            UrdfLinkGeometry& g = link_geometry[current_link];
+            g.has = true; g.kind = 3;
+            g.mesh_file = tag.attr["filename"];
+            if (tag.attr.count("scale")) parse_triplet(tag.attr["scale"], g.mesh_scale);
         } else if (tag.name == "joint" && !tag.closing && current_link.empty() && tag.attr.count("type")) {
             joint = urdf::Joint();
             joint.name = tag.attr["name"];
@@ -186,12 +204,28 @@ bool RobotModel::loadUrdf(const std::string& path)
         tip_link_ = link;
         if (!config_.tip_link.empty() && link == config_.tip_link) break;
     }
+    // collision geometry of the chain links: what fitSpheresFromUrdfGeometry fits spheres to
+    link_geometry_.clear();
+    const std::string urdf_dir = path.find('/') == std::string::npos ? std::string(".") : path.substr(0, path.rfind('/'));
+    for (const auto& j : chain_) {
+        auto it = link_geometry.find(j.child_link_name);
+        if (it == link_geometry.end() || !it->second.has) continue;
+        LinkGeometry g;
+        g.link = j.child_link_name; g.kind = it->second.kind;
+        for (int i = 0; i < 3; ++i) { g.size[i] = it->second.size[i]; g.origin[i] = it->second.origin[i]; g.mesh_scale[i] = it->second.mesh_scale[i]; }
+        std::string file = it->second.mesh_file;
+        const std::string pkg = "package://";
+        if (file.compare(0, pkg.size(), pkg) == 0) { file = file.substr(pkg.size()); const size_t slash = file.find('/'); if (slash != std::string::npos) file = file.substr(slash + 1); }
+        if (!file.empty() && file[0] != '/') file = urdf_dir + "/" + file;
+        g.mesh_file = file;
+        link_geometry_.push_back(g);
+    }
     // links with a primitive collision body fixed to the base link are obstacles of the environment
     // (box_1 in reference test/data/kuka_iiwa.urdf:29-56)
     for (const auto& j : all_joints_) {
         if (j.type != urdf::Joint::FIXED || j.parent_link_name != base_link_) continue;
         auto it = link_geometry.find(j.child_link_name);
-        if (it == link_geometry.end() || !it->second.has) continue;
+        if (it == link_geometry.end() || !it->second.has || it->second.kind == 3) continue;
         Obstacle o;
         o.kind = it->second.kind;
         o.name = j.child_link_name;
@@ -299,9 +333,10 @@ bool RobotModel::loadEnvironment(const std::string& path)
             Obstacle o;
             o.name = key;
             const std::string kind = v[0].as<std::string>();
-            o.kind = kind == "sphere" ? 0 : 1;
+            o.kind = kind == "sphere" ? 0 : (kind == "cylinder" ? 2 : 1);
             for (int i = 0; i < 3; ++i) o.centre[i] = v[1 + i].as<double>();
             if (o.kind == 0) { o.size[0] = o.size[1] = o.size[2] = v[4].as<double>(); }
+            else if (o.kind == 2) { if (v.size() < 6) continue; o.size[0] = v[4].as<double>(); o.size[1] = v[5].as<double>(); o.size[2] = 0.0; }
             else { if (v.size() < 7) continue; for (int i = 0; i < 3; ++i) o.size[i] = v[4 + i].as<double>(); }
             addObstacle(o);
         }
@@ -320,8 +355,72 @@ void RobotModel::setChain(const std::vector<urdf::Joint>& chain, const std::stri
 
 void RobotModel::setSpheres(const std::vector<CollisionSphere>& spheres)
 {
-    spheres_ = spheres;
+    link_spheres_ = spheres;
+    rebuildSphereList();
+}
+
+// spheres_ = the robot's own spheres + the spheres of the grasped objects, sorted by link (what the engines take)
+void RobotModel::rebuildSphereList()
+{
+    spheres_ = link_spheres_;
+    for (const auto& g : grasp_objects_)
+        for (CollisionSphere s : g.first.spheres) { s.link = g.second; spheres_.push_back(s); }
     std::stable_sort(spheres_.begin(), spheres_.end(), [](const CollisionSphere& a, const CollisionSphere& b) { return a.link < b.link; });
+    ++robot_revision_;
+}
+
+bool RobotModel::addGraspObject(const GraspObject& object, const std::string& link_name)
+{
+    int link = (int)chain_.size() - 1;
+    if (!link_name.empty()) {
+        link = -1;
+        for (size_t d = 0; d < chain_.size(); ++d) if (chain_[d].child_link_name == link_name) link = (int)d;
+    }
+    if (link < 0 || object.spheres.empty()) return false;
+    removeGraspObject(object.name);
+    grasp_objects_.push_back(std::make_pair(object, link));
+    rebuildSphereList();
+    return true;
+}
+
+bool RobotModel::removeGraspObject(const std::string& name)
+{
+    for (size_t i = 0; i < grasp_objects_.size(); ++i)
+        if (grasp_objects_[i].first.name == name) { grasp_objects_.erase(grasp_objects_.begin() + i); rebuildSphereList(); return true; }
+    return false;
+}
+
+bool RobotModel::addMeshObstacleFromStl(const std::string& name, const std::string& path, const double position[3], const double scale[3], bool solid)
+{
+    MeshObstacle m;
+    m.name = name; m.solid = solid;
+    if (!loadStl(path, m.triangles, scale, position)) { LOG_ERROR_S << "[RobotModel]: cannot read STL " << path; return false; }
+    addMeshObstacle(m);
+    return true;
+}
+
+int RobotModel::fitSpheresFromUrdfGeometry(int max_spheres_per_link, double padding)
+{
+    int fitted = 0;
+    std::vector<CollisionSphere> all = link_spheres_;
+    for (size_t d = 0; d < chain_.size(); ++d) {
+        bool has = false;
+        for (const auto& s : link_spheres_) has = has || s.link == (int)d;
+        if (has) continue;
+        const LinkGeometry* g = nullptr;
+        for (const auto& lg : link_geometry_) if (lg.link == chain_[d].child_link_name) g = &lg;
+        if (!g) continue;
+        std::vector<double> tris;
+        if (g->kind == 3) { if (!loadStl(g->mesh_file, tris, g->mesh_scale, g->origin)) continue; }
+        else if (g->kind == 1) appendBoxMesh(g->origin, g->size, tris);
+        else if (g->kind == 2) appendCylinderMesh(g->origin, g->size[0], g->size[1], tris);
+        else appendSphereMesh(g->origin, g->size[0], tris);
+        const std::vector<FittedSphere> fit = fitSpheres(tris, max_spheres_per_link, padding);
+        for (const auto& f : fit) { CollisionSphere s; s.link = (int)d; for (int i = 0; i < 3; ++i) s.xyz[i] = f.xyz[i]; s.radius = f.radius; all.push_back(s); }
+        if (!fit.empty()) ++fitted;
+    }
+    if (fitted) setSpheres(all);
+    return fitted;
 }
 
 void RobotModel::setSdfGrid(int resolution, const double lower[3], const double upper[3])
@@ -342,6 +441,8 @@ void RobotModel::setSdf(const SignedDistanceField& sdf)
 
 bool RobotModel::removeObstacle(const std::string& name)
 {
+    for (size_t i = 0; i < meshes_.size(); ++i)
+        if (meshes_[i].name == name) { meshes_.erase(meshes_.begin() + i); sceneChanged(); return true; }
     for (size_t i = 0; i < obstacles_.size(); ++i)
         if (obstacles_[i].name == name) {
             obstacles_.erase(obstacles_.begin() + i);
@@ -472,6 +573,41 @@ int RobotModel::configureEngine(stomp_b200_engine* engine) const
 int RobotModel::configureScene(stomp_b200_engine* engine) const
 {
     if (sdf_explicit_) return stomp_b200_set_sdf(engine, sdf_.dims, sdf_.origin, sdf_.voxel, sdf_.grid.data());
+    if (!meshes_.empty() || !leaf_sizes_.empty()) {
+        // meshes and / or octomap leaves: everything becomes occupancy on one grid — the occupancy world's grid when there
+        // is one, else the grid of setSdfGrid; primitives are voxelised into it on the host (voxel centre inside), meshes and
+        // leaves on the device
+        int dims[3];
+        double origin[3], voxel;
+        if (!occupancy_.empty()) { std::copy(occ_dims_, occ_dims_ + 3, dims); std::copy(occ_origin_, occ_origin_ + 3, origin); voxel = occ_voxel_; }
+        else gridGeometry(dims, origin, voxel);
+        std::vector<unsigned char> occ;
+        if (!occupancy_.empty()) occ = occupancy_;
+        if (!obstacles_.empty()) {
+            if (occ.empty()) occ.assign((size_t)dims[0] * dims[1] * dims[2], 0);
+            for (int z = 0; z < dims[2]; ++z)
+                for (int y = 0; y < dims[1]; ++y)
+                    for (int x = 0; x < dims[0]; ++x) {
+                        unsigned char& v = occ[((size_t)z * dims[1] + y) * dims[0] + x];
+                        if (v) continue;
+                        const double px = origin[0] + ((double)x + 0.5) * voxel, py = origin[1] + ((double)y + 0.5) * voxel, pz = origin[2] + ((double)z + 0.5) * voxel;
+                        for (const auto& o : obstacles_)
+                            if (obstacle_distance(o, px, py, pz) < 0.0) { v = 1; break; }
+                    }
+        }
+        // one call per solidity class: solid meshes first (the interior fill sees only them), then the rest on top
+        std::vector<double> solid_tris, shell_tris;
+        for (const auto& m : meshes_) (m.solid ? solid_tris : shell_tris).insert((m.solid ? solid_tris : shell_tris).end(), m.triangles.begin(), m.triangles.end());
+        if (!shell_tris.empty() && !solid_tris.empty()) {
+            LOG_WARN_S << "[RobotModel]: shell and solid meshes in one scene: all treated as solid";
+            solid_tris.insert(solid_tris.end(), shell_tris.begin(), shell_tris.end());
+            shell_tris.clear();
+        }
+        const std::vector<double>& tris = solid_tris.empty() ? shell_tris : solid_tris;
+        return stomp_b200_build_sdf_scene(engine, dims, origin, voxel, (int32_t)(tris.size() / 9), tris.empty() ? nullptr : tris.data(),
+                                          solid_tris.empty() ? 0 : 1, (int32_t)leaf_sizes_.size(), leaf_sizes_.empty() ? nullptr : leaf_centres_.data(),
+                                          leaf_sizes_.empty() ? nullptr : leaf_sizes_.data(), occ.empty() ? nullptr : occ.data());
+    }
     if (!occupancy_.empty()) {
         // primitives present next to an occupancy world are voxelised into it (centre of the voxel inside the primitive)
         std::vector<unsigned char> occ = occupancy_;
@@ -504,6 +640,13 @@ int RobotModel::configureScene(stomp_b200_engine* engine) const
 bool RobotModel::ensureValidityEngine()
 {
     if (validity_engine_) {
+        if (validity_robot_revision_ != robot_revision_) {      // the sphere list changed (grasp object): chain, spheres, scene again
+            const int rc = configureEngine(validity_engine_);
+            if (rc) { LOG_ERROR_S << "[RobotModel]: " << stomp_b200_last_error(validity_engine_); return false; }
+            validity_robot_revision_ = robot_revision_;
+            validity_robot_revision_ = robot_revision_;
+    validity_revision_ = scene_revision_;
+        }
         if (validity_revision_ != scene_revision_) {      // the scene changed since: rebuild the field before answering
             const int rc = configureScene(validity_engine_);
             if (rc) { LOG_ERROR_S << "[RobotModel]: " << stomp_b200_last_error(validity_engine_); return false; }

@@ -90,6 +90,7 @@ def lib():
         L.oracle_set_sdf_primitives.argtypes = [vp, ip, dp, C.c_double, C.c_int, ip, dp, dp]
         L.oracle_build_sdf_primitives.argtypes = [ip, dp, C.c_double, C.c_int, ip, dp, dp, C.POINTER(C.c_float)]
         L.oracle_build_sdf_occupancy.argtypes = [ip, C.c_double, u8p, C.POINTER(C.c_float)]
+        L.oracle_voxelise_scene.argtypes = [ip, dp, C.c_double, C.c_int, dp, C.c_int, C.c_int, dp, dp, u8p, u8p]
         _lib = L
     return _lib
 
@@ -336,6 +337,24 @@ def build_sdf_primitives(dims, origin, voxel, kind, centre, size):
     rc = lib().oracle_build_sdf_primitives(_ip(dims), _dp(org), float(voxel), len(kind), _ip(kind), _dp(centre), _dp(size),
                                            out.ctypes.data_as(C.POINTER(C.c_float)))
     assert rc == 0
+    return out
+
+
+def voxelise_scene(dims, origin, voxel, triangles=None, solid=False, leaf_centres=None, leaf_sizes=None, occupied=None):
+    """Occupancy [nz][ny][nx] (uint8) of a mesh (triangles [n][3][3]), octomap leaves and / or a given occupancy grid: the
+    CPU statement of stomp_b200_build_sdf_scene's voxelisation."""
+    dims = np.ascontiguousarray(dims, dtype=np.int32)
+    org = _c64(origin)
+    tri = _c64(triangles).reshape(-1, 9) if triangles is not None else np.zeros((0, 9))
+    lc = _c64(leaf_centres).reshape(-1, 3) if leaf_centres is not None else np.zeros((0, 3))
+    ls = _c64(leaf_sizes).reshape(-1) if leaf_sizes is not None else np.zeros(0)
+    occ_in = np.ascontiguousarray(occupied, dtype=np.uint8) if occupied is not None else None
+    out = np.zeros((int(dims[2]), int(dims[1]), int(dims[0])), dtype=np.uint8)
+    u8 = C.POINTER(C.c_uint8)
+    rc = lib().oracle_voxelise_scene(_ip(dims), _dp(org), float(voxel), len(tri), _dp(tri) if len(tri) else None, int(solid),
+                                     len(ls), _dp(lc) if len(ls) else None, _dp(ls) if len(ls) else None,
+                                     occ_in.ctypes.data_as(u8) if occ_in is not None else None, out.ctypes.data_as(u8))
+    assert rc == 0, rc
     return out
 
 

@@ -125,6 +125,11 @@ static inline double primitive_distance(const PrimitiveSpec& pr, double px, doub
 {
     const double dx = px - pr.c[0], dy = py - pr.c[1], dz = pz - pr.c[2];
     if (pr.kind == 0) return std::sqrt((dx * dx + dy * dy) + dz * dz) - pr.s[0];
+    if (pr.kind == 2) {   // cylinder along z: s[0] radius, s[1] half height
+        const double qr = std::sqrt(dx * dx + dy * dy) - pr.s[0], qh = std::fabs(dz) - pr.s[1];
+        const double orr = std::fmax(qr, 0.0), oh = std::fmax(qh, 0.0);
+        return std::sqrt(orr * orr + oh * oh) + std::fmin(std::fmax(qr, qh), 0.0);
+    }
     const double qx = std::fabs(dx) - pr.s[0], qy = std::fabs(dy) - pr.s[1], qz = std::fabs(dz) - pr.s[2];
     const double ox = std::fmax(qx, 0.0), oy = std::fmax(qy, 0.0), oz = std::fmax(qz, 0.0);
     const double outside = std::sqrt((ox * ox + oy * oy) + oz * oz);

@@ -227,6 +227,109 @@ int oracle_build_sdf_primitives(const int32_t* dims, const double* origin, doubl
     return 0;
 }
 
+// ---- meshes and octomap leaves -> occupancy (restates csrc/sdf_builder.cuh: voxelise_triangles_kernel,
+// voxelise_leaves_kernel, the boundary flood) ----
+static bool triangle_overlaps_box(const double* tri, double cx, double cy, double cz, double hh)
+{
+    const double v0x = tri[0] - cx, v0y = tri[1] - cy, v0z = tri[2] - cz;
+    const double v1x = tri[3] - cx, v1y = tri[4] - cy, v1z = tri[5] - cz;
+    const double v2x = tri[6] - cx, v2y = tri[7] - cy, v2z = tri[8] - cz;
+    using std::fmin; using std::fmax; using std::fabs;
+    if (fmin(fmin(v0x, v1x), v2x) > hh || fmax(fmax(v0x, v1x), v2x) < -hh) return false;
+    if (fmin(fmin(v0y, v1y), v2y) > hh || fmax(fmax(v0y, v1y), v2y) < -hh) return false;
+    if (fmin(fmin(v0z, v1z), v2z) > hh || fmax(fmax(v0z, v1z), v2z) < -hh) return false;
+    const double e0x = v1x - v0x, e0y = v1y - v0y, e0z = v1z - v0z;
+    const double e1x = v2x - v1x, e1y = v2y - v1y, e1z = v2z - v1z;
+    const double e2x = v0x - v2x, e2y = v0y - v2y, e2z = v0z - v2z;
+    const double nx = e0y * e1z - e0z * e1y, ny = e0z * e1x - e0x * e1z, nz = e0x * e1y - e0y * e1x;
+    const double dist = (nx * v0x + ny * v0y) + nz * v0z;
+    const double rad = hh * ((fabs(nx) + fabs(ny)) + fabs(nz));
+    if (dist > rad || dist < -rad) return false;
+    auto separated = [&](double ax, double ay, double az) {
+        const double p0 = (ax * v0x + ay * v0y) + az * v0z;
+        const double p1 = (ax * v1x + ay * v1y) + az * v1z;
+        const double p2 = (ax * v2x + ay * v2y) + az * v2z;
+        const double r = hh * ((fabs(ax) + fabs(ay)) + fabs(az));
+        return fmin(fmin(p0, p1), p2) > r || fmax(fmax(p0, p1), p2) < -r;
+    };
+    if (separated(0.0, -e0z, e0y) || separated(e0z, 0.0, -e0x) || separated(-e0y, e0x, 0.0)) return false;
+    if (separated(0.0, -e1z, e1y) || separated(e1z, 0.0, -e1x) || separated(-e1y, e1x, 0.0)) return false;
+    if (separated(0.0, -e2z, e2y) || separated(e2z, 0.0, -e2x) || separated(-e2y, e2x, 0.0)) return false;
+    return true;
+}
+
+static void voxel_range(double a, double b, double origin, double inv_h, int n, int& lo, int& hi)
+{
+    const double fa = std::floor((a - origin) * inv_h), fb = std::floor((b - origin) * inv_h);
+    lo = (int)std::fmax(fa - 1.0, 0.0);
+    hi = (int)std::fmin(fb + 1.0, (double)(n - 1));
+    if (!(fb + 1.0 >= 0.0) || !(fa - 1.0 <= (double)(n - 1))) { lo = 1; hi = 0; }
+}
+
+// occupancy [nz][ny][nx] of a scene: mesh (conservative, optionally solid), octomap leaves, given occupancy (or NULL)
+int oracle_voxelise_scene(const int32_t* dims, const double* origin, double h, int num_triangles, const double* triangles, int solid,
+                          int num_leaves, const double* leaf_centres, const double* leaf_sizes, const uint8_t* occupied, uint8_t* occ)
+{
+    const int nx = dims[0], ny = dims[1], nz = dims[2];
+    const size_t count = (size_t)nx * ny * nz;
+    const double inv_h = 1.0 / h, hh = (0.5 * h) * 1.000000001;     // inflated by 1e-9: see voxelise_triangles_kernel
+    for (size_t i = 0; i < count; ++i) occ[i] = occupied ? occupied[i] : 0;
+    for (int tr = 0; tr < num_triangles; ++tr) {
+        const double* t = triangles + (size_t)tr * 9;
+        int x0, x1, y0, y1, z0, z1;
+        voxel_range(std::fmin(std::fmin(t[0], t[3]), t[6]), std::fmax(std::fmax(t[0], t[3]), t[6]), origin[0], inv_h, nx, x0, x1);
+        voxel_range(std::fmin(std::fmin(t[1], t[4]), t[7]), std::fmax(std::fmax(t[1], t[4]), t[7]), origin[1], inv_h, ny, y0, y1);
+        voxel_range(std::fmin(std::fmin(t[2], t[5]), t[8]), std::fmax(std::fmax(t[2], t[5]), t[8]), origin[2], inv_h, nz, z0, z1);
+        for (int z = z0; z <= z1; ++z)
+            for (int y = y0; y <= y1; ++y)
+                for (int x = x0; x <= x1; ++x) {
+                    const double cx = origin[0] + ((double)x + 0.5) * h, cy = origin[1] + ((double)y + 0.5) * h, cz = origin[2] + ((double)z + 0.5) * h;
+                    if (triangle_overlaps_box(t, cx, cy, cz, hh)) occ[((size_t)z * ny + y) * nx + x] = 1;
+                }
+    }
+    if (num_triangles > 0 && solid) {       // breadth-first flood of the free voxels from the grid's boundary
+        std::vector<uint8_t> outside(count, 0);
+        std::vector<size_t> queue;
+        auto push = [&](int x, int y, int z) {
+            const size_t i = ((size_t)z * ny + y) * nx + x;
+            if (!occ[i] && !outside[i]) { outside[i] = 1; queue.push_back(i); }
+        };
+        for (int z = 0; z < nz; ++z)
+            for (int y = 0; y < ny; ++y)
+                for (int x = 0; x < nx; ++x)
+                    if (x == 0 || y == 0 || z == 0 || x == nx - 1 || y == ny - 1 || z == nz - 1) push(x, y, z);
+        for (size_t head = 0; head < queue.size(); ++head) {
+            const size_t i = queue[head];
+            const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / ((size_t)nx * ny));
+            if (x > 0) push(x - 1, y, z);
+            if (x < nx - 1) push(x + 1, y, z);
+            if (y > 0) push(x, y - 1, z);
+            if (y < ny - 1) push(x, y + 1, z);
+            if (z > 0) push(x, y, z - 1);
+            if (z < nz - 1) push(x, y, z + 1);
+        }
+        for (size_t i = 0; i < count; ++i) if (!outside[i]) occ[i] = 1;
+    }
+    for (int lf = 0; lf < num_leaves; ++lf) {
+        const double half = 0.5 * leaf_sizes[lf];
+        int lo[3], hi[3];
+        const int nn[3] = {nx, ny, nz};
+        bool empty = false;
+        for (int a = 0; a < 3; ++a) {
+            const double c = leaf_centres[(size_t)lf * 3 + a];
+            const double fl = std::ceil((c - half - origin[a]) * inv_h - 0.5), fh = std::floor((c + half - origin[a]) * inv_h - 0.5);
+            lo[a] = (int)std::fmax(fl, 0.0);
+            hi[a] = (int)std::fmin(fh, (double)(nn[a] - 1));
+            if (!(fh >= 0.0) || !(fl <= (double)(nn[a] - 1))) empty = true;
+        }
+        if (empty) continue;
+        for (int z = lo[2]; z <= hi[2]; ++z)
+            for (int y = lo[1]; y <= hi[1]; ++y)
+                for (int x = lo[0]; x <= hi[0]; ++x) occ[((size_t)z * ny + y) * nx + x] = 1;
+    }
+    return 0;
+}
+
 // exact Euclidean distance transform of an occupancy grid [nz][ny][nx], signed (positive outside, negative inside),
 // centre to centre, in metres: h * sqrt(min squared voxel distance), rounded to binary32.  Brute force per line with the
 // same three separable min-plus passes over integer squared distances as the CUDA builder (exact, so the order of the

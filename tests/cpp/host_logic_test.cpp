@@ -9,6 +9,8 @@
 
 #include <PlannerFactory.hpp>
 #include <motion_planners/MotionPlanners.hpp>
+#include <robot_model/MeshTools.hpp>
+#include <vector>
 #include <stomp_b200.h>
 
 #define CHECK(cond)                                                                  \
@@ -100,6 +102,80 @@ int main(int argc, char** argv)
         robot->setSelfCollision(false);
     }
     std::puts("ok robot_model");
+
+    // ---- meshes: STL input, sphere fitting, grasp objects, world objects ----
+    {
+        // a 0.1 x 0.14 x 0.6 box as a binary and as an ASCII STL
+        std::vector<double> box;
+        const double bc[3] = {0.02, -0.01, 0.3}, bh[3] = {0.05, 0.07, 0.3};
+        robot_model::appendBoxMesh(bc, bh, box);
+        CHECK(box.size() == 12u * 9u);
+        const std::string bin = "/tmp/stomp_b200_host_test_box.stl", asc = "/tmp/stomp_b200_host_test_box_ascii.stl";
+        {
+            FILE* f = std::fopen(bin.c_str(), "wb");
+            char header[80] = "solid binary box";     // a binary file that starts with "solid": recognised by its size
+            std::fwrite(header, 1, 80, f);
+            const unsigned n = 12; std::fwrite(&n, 4, 1, f);
+            for (unsigned i = 0; i < n; ++i) {
+                float rec[12] = {0, 0, 0};
+                for (int k = 0; k < 9; ++k) rec[3 + k] = (float)box[i * 9 + k];
+                std::fwrite(rec, 4, 12, f);
+                const unsigned short attr = 0; std::fwrite(&attr, 2, 1, f);
+            }
+            std::fclose(f);
+            f = std::fopen(asc.c_str(), "w");
+            std::fprintf(f, "solid box\n");
+            for (unsigned i = 0; i < n; ++i) {
+                std::fprintf(f, " facet normal 0 0 0\n  outer loop\n");
+                for (int k = 0; k < 3; ++k) std::fprintf(f, "   vertex %.9g %.9g %.9g\n", box[i * 9 + 3 * k], box[i * 9 + 3 * k + 1], box[i * 9 + 3 * k + 2]);
+                std::fprintf(f, "  endloop\n endfacet\n");
+            }
+            std::fprintf(f, "endsolid box\n");
+            std::fclose(f);
+        }
+        std::vector<double> from_bin, from_asc;
+        const double shift[3] = {1.0, 0.0, -1.0}, scale[3] = {2.0, 1.0, 1.0};
+        CHECK(robot_model::loadStl(bin, from_bin) && from_bin.size() == box.size());
+        CHECK(robot_model::loadStl(asc, from_asc, scale, shift) && from_asc.size() == box.size());
+        for (size_t i = 0; i < box.size(); ++i) {
+            CHECK(std::fabs(from_bin[i] - box[i]) < 1e-6);
+            CHECK(std::fabs(from_asc[i] - (box[i] * scale[i % 3] + shift[i % 3])) < 1e-6);
+        }
+        std::vector<double> none;
+        CHECK(!robot_model::loadStl("/tmp/stomp_b200_no_such_file.stl", none) && none.empty());
+        // sphere fit: slabs along the long (z) axis, every vertex covered, radii close to the slab's half diagonal
+        const auto fit = robot_model::fitSpheres(box, 8, 0.0);
+        CHECK(fit.size() >= 3 && fit.size() <= 8);
+        for (size_t v = 0; v < box.size() / 3; ++v) {
+            bool covered = false;
+            for (const auto& sp : fit) {
+                double d2 = 0; for (int a = 0; a < 3; ++a) d2 += (box[3 * v + a] - sp.xyz[a]) * (box[3 * v + a] - sp.xyz[a]);
+                covered = covered || std::sqrt(d2) <= sp.radius;
+            }
+            CHECK(covered);
+        }
+        for (const auto& sp : fit) { CHECK(sp.radius < 0.2 && std::fabs(sp.xyz[0] - 0.02) < 1e-9 && std::fabs(sp.xyz[1] + 0.01) < 1e-9); }
+        CHECK(robot_model::fitSpheres(box, 1, 0.01).size() == 1);
+        // grasp object: its spheres join the tip link's, the robot revision moves, removal restores the list
+        const size_t s0 = robot->spheres().size();
+        const unsigned long r0 = robot->robotRevision();
+        robot_model::GraspObject go;
+        go.name = "bottle";
+        for (const auto& sp : fit) { robot_model::CollisionSphere cs; cs.link = 0; for (int a = 0; a < 3; ++a) cs.xyz[a] = sp.xyz[a]; cs.radius = sp.radius; go.spheres.push_back(cs); }
+        CHECK(robot->addGraspObject(go, "") && robot->spheres().size() == s0 + fit.size() && robot->robotRevision() > r0);
+        CHECK(robot->spheres().back().link == 6);
+        CHECK(!robot->addGraspObject(go, "no_such_link"));
+        CHECK(robot->addGraspObject(go, "link_3") && robot->spheres().size() == s0 + fit.size());      // re-attached, not duplicated
+        CHECK(robot->removeGraspObject("bottle") && robot->spheres().size() == s0 && !robot->removeGraspObject("bottle"));
+        // world objects: mesh from STL, cylinder primitive, octomap leaves -> scene revision moves
+        const unsigned long sr = robot->sceneRevision();
+        const double pos[3] = {0.4, 0.4, 0.0};
+        CHECK(robot->addMeshObstacleFromStl("crate", bin, pos) && robot->meshObstacles().size() == 1 && robot->sceneRevision() > sr);
+        CHECK(robot->removeObstacle("crate") && robot->meshObstacles().empty());
+        robot->setOctomapLeaves({0.3, 0.3, 0.3}, {0.1});
+        robot->setOctomapLeaves({}, {});
+    }
+    std::puts("ok meshes");
 
     // ---- CovariantMovementPrimitive against the C-ABI host policy ----
     const int T = 20, D = 7, N = T + 12;

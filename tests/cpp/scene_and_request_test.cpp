@@ -8,6 +8,7 @@
 #include <iostream>
 
 #include <motion_planners/MotionPlanners.hpp>
+#include <robot_model/MeshTools.hpp>
 
 using namespace motion_planners;
 
@@ -136,5 +137,76 @@ int main(int argc, char** argv)
         if (found) CHECK(new_hits == 0);
     }
     std::puts("ok scene_change_reaches_the_next_solve");
+    CHECK(robot->removeObstacle("late_wall"));
+
+    // world objects as the reference's callers hand them in (MotionPlanners::handleCollisionObjectInWorld, updateOctomap): a mesh
+    // (STL), a cylinder and octomap leaves go through the device voxeliser + distance transform (stomp_b200_build_sdf_scene)
+    {
+        auto state_valid = [&](const std::vector<double>& q) {
+            double cost = 0.0;
+            robot->updateJointGroup(joints(names, q));
+            return robot->isStateValid(cost);
+        };
+        CHECK(state_valid(start));
+        // where is the arm at `start`?  put objects on the tip: the last sphere's centre from a probe engine is not exposed,
+        // so use a leaf / mesh large enough around the known reach of the start pose: the blocker's place is on the straight
+        // line, the arm at `start` passes near (0.25, 0.2, 0.9)
+        std::vector<double> crate;
+        const double zero[3] = {0, 0, 0}, half[3] = {0.9, 0.9, 0.9};
+        robot_model::appendBoxMesh(zero, half, crate);         // a crate that swallows most of the workspace above the base
+        const std::string stl = "/tmp/stomp_b200_scene_test_crate.stl";
+        {
+            FILE* f = std::fopen(stl.c_str(), "wb");
+            char header[80] = "crate"; std::fwrite(header, 1, 80, f);
+            const unsigned n = (unsigned)(crate.size() / 9); std::fwrite(&n, 4, 1, f);
+            for (unsigned i = 0; i < n; ++i) {
+                float rec[12] = {0, 0, 0};
+                for (int k = 0; k < 9; ++k) rec[3 + k] = (float)crate[i * 9 + k];
+                std::fwrite(rec, 4, 12, f);
+                const unsigned short attr = 0; std::fwrite(&attr, 2, 1, f);
+            }
+            std::fclose(f);
+        }
+        ModelObject mesh;
+        mesh.operation = collision_detection::ADD; mesh.model_type = collision_detection::MESH;
+        mesh.object_name = "crate"; mesh.object_path = stl;
+        mesh.relative_pose.position = base::Vector3d(0.0, 0.0, 1.2);
+        CHECK(planner.handleCollisionObjectInWorld(mesh));
+        CHECK(!state_valid(start));                                   // the solid crate (interior filled) holds the arm
+        mesh.operation = collision_detection::REMOVE;
+        CHECK(planner.handleCollisionObjectInWorld(mesh) && state_valid(start));
+        ModelObject cyl;
+        cyl.operation = collision_detection::ADD; cyl.model_type = collision_detection::PRIMITIVES; cyl.object_name = "column";
+        cyl.primitive_object.primitive_type = collision_detection::CYLINDER; cyl.primitive_object.radius = 1.0; cyl.primitive_object.height = 1.6;
+        cyl.relative_pose.position = base::Vector3d(0.0, 0.0, 1.0);
+        CHECK(planner.handleCollisionObjectInWorld(cyl) && !state_valid(start));
+        cyl.operation = collision_detection::REMOVE;
+        CHECK(planner.handleCollisionObjectInWorld(cyl) && state_valid(start));
+        OccupiedLeaves leaves;
+        for (int i = -4; i <= 4; ++i) for (int j = -4; j <= 4; ++j) for (int k = 1; k <= 9; ++k) {
+            leaves.centres.push_back(0.2 * i); leaves.centres.push_back(0.2 * j); leaves.centres.push_back(0.2 * k); leaves.sizes.push_back(0.2);
+        }
+        planner.updateOctomap(leaves);
+        CHECK(!state_valid(start));
+        planner.updateOctomap(OccupiedLeaves());
+        CHECK(state_valid(start));
+        // a grasp object: its spheres ride on the tip link; a long rod held at the tip reaches the floor obstacle the bare arm clears
+        ModelObject rod;
+        rod.operation = collision_detection::ADD; rod.model_type = collision_detection::PRIMITIVES; rod.object_name = "rod";
+        rod.primitive_object.primitive_type = collision_detection::BOX; rod.primitive_object.dimensions = base::Vector3d(0.05, 0.05, 3.0);
+        const size_t spheres_before = robot->spheres().size();
+        CHECK(planner.handleGraspObject(rod) && robot->spheres().size() > spheres_before);
+        robot_model::Obstacle shell;       // a thick spherical band far out: only the 1.5 m rod ends can be in it
+        shell.kind = 1; shell.name = "far_wall"; shell.centre[0] = 0.0; shell.centre[1] = 0.0; shell.centre[2] = -1.2; shell.size[0] = 1.5; shell.size[1] = 1.5; shell.size[2] = 0.25;
+        robot->addObstacle(shell);
+        const bool with_rod = state_valid(start);
+        rod.operation = collision_detection::REMOVE;
+        CHECK(planner.handleGraspObject(rod) && robot->spheres().size() == spheres_before);
+        const bool without_rod = state_valid(start);
+        std::printf("far wall: valid with the rod %d, without %d\n", (int)with_rod, (int)without_rod);
+        CHECK(without_rod);
+        robot->removeObstacle("far_wall");
+    }
+    std::puts("ok world_objects_meshes_octomap_grasp");
     return 0;
 }

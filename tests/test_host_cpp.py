@@ -23,7 +23,7 @@ def test_host_logic_cpp(tmp_path):
                     "-Wl,-rpath," + os.path.join(ROOT, "motion_planners_b200")], check=True)
     out = subprocess.run([exe, os.path.join(ROOT, "test")], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
-    for name in ("yaml_and_stomp_config", "robot_model", "planner_api", "policy"):
+    for name in ("yaml_and_stomp_config", "robot_model", "meshes", "planner_api", "policy"):
         assert f"ok {name}" in out.stdout
 
 
@@ -63,5 +63,5 @@ def test_requests_by_joint_name_and_late_scene_changes(tmp_path):
     out = subprocess.run([exe, os.path.join(ROOT, "test")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     for name in ("request_by_name", "refused_requests", "scene_change_reaches_the_validity_checks",
-                 "scene_change_reaches_the_next_solve"):
+                 "scene_change_reaches_the_next_solve", "world_objects_meshes_octomap_grasp"):
         assert f"ok {name}" in out.stdout

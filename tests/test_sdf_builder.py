@@ -111,3 +111,104 @@ def test_lazy_problem_builds_its_field_on_the_device(medium_problem):
     got, _, _ = e.get_sdf()
     assert np.array_equal(got.view(np.uint32), pb.sdf.grid.view(np.uint32))
     e.close()
+
+
+# ---- meshes, octomap leaves, cylinders ------------------------------------------------------------------------------
+def _icosphere(radius, centre, subdivisions=2):
+    """Closed triangle mesh of a sphere [n][3][3] (subdivided icosahedron)."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    tris = np.array([[v[a], v[b], v[c]] for a, b, c in f])
+    for _ in range(subdivisions):
+        a, b, c = tris[:, 0], tris[:, 1], tris[:, 2]
+        ab, bc, ca = (a + b) / 2, (b + c) / 2, (c + a) / 2
+        tris = np.concatenate([np.stack([a, ab, ca], 1), np.stack([b, bc, ab], 1), np.stack([c, ca, bc], 1), np.stack([ab, bc, ca], 1)])
+    tris = tris / np.linalg.norm(tris, axis=2, keepdims=True) * radius
+    return tris + np.asarray(centre)
+
+
+def _box_mesh(lo, hi):
+    lo, hi = np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)
+    c = np.array([[lo[0] if i & 1 == 0 else hi[0], lo[1] if i & 2 == 0 else hi[1], lo[2] if i & 4 == 0 else hi[2]] for i in range(8)])
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    return np.array([[c[a], c[b], c[cc]] for a, b, cc, d in quads] + [[c[a], c[cc], c[d]] for a, b, cc, d in quads])
+
+
+def test_oracle_cylinder_field_equals_the_numpy_formula():
+    dims = np.array([40, 36, 44], dtype=np.int32); origin = np.array([-1.0, -0.9, -1.1]); h = 0.05
+    kind = np.array([2, 0], dtype=np.int32)
+    centre = np.array([[0.1, -0.05, 0.2], [-0.6, 0.5, -0.4]]); size = np.array([[0.3, 0.45, 0.0], [0.2, 0.0, 0.0]])
+    got = ob.build_sdf_primitives(dims, origin, h, kind, centre, size)
+    z, y, x = np.meshgrid(*(origin[2 - a] + (np.arange(dims[2 - a]) + 0.5) * h for a in range(3)), indexing="ij")
+    dx, dy, dz = x - 0.1, y + 0.05, z - 0.2
+    qr, qh = np.sqrt(dx * dx + dy * dy) - 0.3, np.abs(dz) - 0.45
+    cyl = np.sqrt(np.maximum(qr, 0) ** 2 + np.maximum(qh, 0) ** 2) + np.minimum(np.maximum(qr, qh), 0)
+    sph = np.sqrt((x + 0.6) ** 2 + (y - 0.5) ** 2 + (z + 0.4) ** 2) - 0.2
+    np.testing.assert_allclose(got, np.minimum(cyl, sph).astype(np.float32), rtol=1e-6, atol=1e-7)
+    assert (got < 0).any()
+
+
+def test_oracle_mesh_voxelisation_of_a_sphere_and_a_box():
+    """Conservative surface voxelisation + interior fill: the occupied set of a closed mesh contains every voxel whose
+    centre is inside the solid and nothing farther than one voxel diagonal outside it."""
+    dims = np.array([48, 40, 44], dtype=np.int32); origin = np.array([-0.6, -0.5, -0.55]); h = 0.025
+    tris = _icosphere(0.31, (0.02, -0.01, 0.03), subdivisions=3)
+    shell = ob.voxelise_scene(dims, origin, h, triangles=tris, solid=False)
+    solid = ob.voxelise_scene(dims, origin, h, triangles=tris, solid=True)
+    z, y, x = np.meshgrid(*(origin[2 - a] + (np.arange(dims[2 - a]) + 0.5) * h for a in range(3)), indexing="ij")
+    r = np.sqrt((x - 0.02) ** 2 + (y + 0.01) ** 2 + (z - 0.03) ** 2)
+    assert shell.sum() < solid.sum()
+    assert np.all(solid[r < 0.31 - 0.005] == 1)                      # inside the solid (the icosphere is inscribed: small slack)
+    assert np.all(solid[r > 0.31 + h * 3 ** 0.5 * 0.5 + 1e-9] == 0)   # no voxel farther than half a diagonal from the surface
+    assert np.all(shell[np.abs(r - 0.31) > h * 3 ** 0.5 * 0.5 + 0.006] == 0)
+    # a box whose faces lie exactly on voxel boundaries: the closed-set rule also takes the voxels that only touch it
+    bx = ob.voxelise_scene(dims, origin, h, triangles=_box_mesh((-0.1, -0.2, -0.05), (0.15, 0.1, 0.2)), solid=True)
+    inside = (x > -0.1) & (x < 0.15) & (y > -0.2) & (y < 0.1) & (z > -0.05) & (z < 0.2)
+    assert np.all(bx[inside] == 1)
+    grown = (x > -0.1 - h) & (x < 0.15 + h) & (y > -0.2 - h) & (y < 0.1 + h) & (z > -0.05 - h) & (z < 0.2 + h)
+    assert np.all(bx[~grown] == 0)
+    # octomap leaves: cubes whose centres' voxels are exactly those with centre inside
+    lv = ob.voxelise_scene(dims, origin, h, leaf_centres=[[0.0, 0.0, 0.0], [0.3, 0.2, -0.3]], leaf_sizes=[0.1, 0.2])
+    ref = ((np.abs(x) <= 0.05) & (np.abs(y) <= 0.05) & (np.abs(z) <= 0.05)) | ((np.abs(x - 0.3) <= 0.1) & (np.abs(y - 0.2) <= 0.1) & (np.abs(z + 0.3) <= 0.1))
+    assert lv.sum() > 0 and np.abs(lv.astype(int) - ref.astype(int)).sum() <= 0.02 * ref.sum()    # boundary ties only
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solid", [False, True])
+def test_cuda_scene_builder_is_bit_identical_to_the_oracle(solid):
+    """stomp_b200_build_sdf_scene: mesh + octomap leaves + occupancy, voxelised and transformed on the device, against the
+    oracle's voxelisation followed by its distance transform."""
+    rng = np.random.default_rng(12)
+    dims = np.array([56, 44, 50], dtype=np.int32); origin = np.array([-0.7, -0.55, -0.6]); h = 0.025
+    tris = np.concatenate([_icosphere(0.22, (0.1, -0.05, 0.02), 2), _box_mesh((-0.5, -0.4, -0.45), (-0.2, -0.15, 0.1)),
+                           _icosphere(0.3, (0.6, 0.5, 0.55), 1)])          # the last one sticks out of the grid
+    leaves_c = rng.uniform(-0.6, 0.6, (40, 3)); leaves_s = rng.choice([0.025, 0.05, 0.1], 40)
+    occ_in = (rng.random((50, 44, 56)) < 0.002).astype(np.uint8)
+    occ_ref = ob.voxelise_scene(dims, origin, h, triangles=tris, solid=solid, leaf_centres=leaves_c, leaf_sizes=leaves_s, occupied=occ_in)
+    ref = ob.build_sdf_occupancy(occ_ref, h)
+    e = binding.Engine(num_time_steps=10, num_dimensions=7, min_rollouts=2, max_rollouts=2, num_rollouts_per_iteration=2)
+    e.build_sdf_scene(dims, origin, h, triangles=tris, solid=solid, leaf_centres=leaves_c, leaf_sizes=leaves_s, occupied=occ_in)
+    got, org, vox = e.get_sdf()
+    assert np.array_equal((got < 0), occ_ref != 0)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # each part on its own
+    for kw in (dict(triangles=tris, solid=solid), dict(leaf_centres=leaves_c, leaf_sizes=leaves_s), dict(occupied=occ_in)):
+        e.build_sdf_scene(dims, origin, h, **kw)
+        assert np.array_equal(e.get_sdf()[0] < 0, ob.voxelise_scene(dims, origin, h, **kw) != 0)
+    e.close()
+
+
+@pytest.mark.gpu
+def test_cuda_cylinder_primitive_is_bit_identical_to_the_oracle():
+    dims = np.array([40, 36, 44], dtype=np.int32); origin = np.array([-1.0, -0.9, -1.1]); h = 0.05
+    kind = np.array([2, 1, 0, 2], dtype=np.int32)
+    centre = np.array([[0.1, -0.05, 0.2], [-0.5, 0.4, 0.1], [0.5, 0.5, -0.5], [0.0, 0.3, -0.6]])
+    size = np.array([[0.3, 0.45, 0.0], [0.2, 0.1, 0.3], [0.25, 0, 0], [0.1, 0.2, 0.0]])
+    ref = ob.build_sdf_primitives(dims, origin, h, kind, centre, size)
+    e = binding.Engine(num_time_steps=10, num_dimensions=7, min_rollouts=2, max_rollouts=2, num_rollouts_per_iteration=2)
+    e.build_sdf_primitives(dims, origin, h, kind, centre, size)
+    assert np.array_equal(e.get_sdf()[0].view(np.uint32), ref.view(np.uint32))
+    e.close()
