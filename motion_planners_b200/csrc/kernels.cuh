@@ -77,7 +77,8 @@ struct LoopParams {
     double* nl_state;         // [Q][T]
     uint8_t* nl_verdict;      // [Q][T]
     double* nl_control;       // [Q][D][T]
-    double* nl_sums;          // [Q][sumw]
+    double* nl_sums;          // [Q][sumw]  record of the noise-less rollout this iteration READS (appended as rollout K)
+    double* nl_sums_next;     // [Q][sumw]  record the update of this iteration WRITES for the next one (the two alternate)
     double* nl_total;         // [Q]
     uint8_t* nl_valid;        // [Q]
     double* old_cost;         // [Q]
@@ -142,6 +143,18 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+// Programmatic dependent launch: the three kernels of a steady iteration (sampler -> state kernel -> weights / update)
+// are launched with cudaLaunchAttributeProgrammaticStreamSerialization.  Each lets its successor's CTAs become resident
+// at once (trigger at the top) and itself waits for its predecessor's completion and memory flush before it reads
+// anything (wait, also at the top: the first thing every one of them reads — the stop flag — is a predecessor's output).
+// What is hidden is the launch latency between dependent kernels, 2 - 3 us each on B200.  Both are no-ops in a kernel
+// launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger_and_wait()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 struct TimelineScope {
     unsigned long long* slot;
     __device__ __forceinline__ TimelineScope(const LoopParams& p, int kernel) : slot(p.timeline ? p.timeline + 2 * kernel : nullptr)
@@ -700,6 +713,7 @@ sample_rollouts_banded_kernel(const __grid_constant__ LoopParams p, const __grid
 {
     extern __shared__ __align__(16) double smem[];
     const int q = blockIdx.y;
+    pdl_trigger_and_wait();
     if (p.counters && blockIdx.x == 0 && q == 0 && threadIdx.x == 0) p.counters[1] += 1u;    // next exchange epoch (graph replay)
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 0);
@@ -1105,7 +1119,7 @@ __device__ __forceinline__ void control_cost_sums(const LoopParams& p, const Row
             c = control_cost_row_table(p, x, i);
         }
         c_sum += c;
-        if (i < T) s_sum += state[i];
+        if (state && i < T) s_sum += state[i];
     }
     c_sum = warp_sum(c_sum);
     s_sum = warp_sum(s_sum);
@@ -2070,7 +2084,7 @@ __device__ __forceinline__ void apply_update_body(const LoopParams& p, int q, in
 // __threadfence — also does the work of apply_update_kernel: it sums the partials in chunk order (so the result does
 // not depend on which CTA came last) and updates the parameters and the noise magnitude.  One launch and one
 // drain / fill gap less per iteration.
-// dynamic shared memory: max(2 * chunk, T + 2) doubles.
+// dynamic shared memory: max(2 * chunk, T + 2 + N) doubles (the last CTA of a joint also stages the updated row: apply_update_body).
 __global__ void __launch_bounds__(kUpdateThreads)
 weighted_update_kernel(const __grid_constant__ LoopParams p, int fuse_apply)
 {
@@ -2172,6 +2186,7 @@ weights_update_kernel(const __grid_constant__ LoopParams p)
     __shared__ double scratch[32];
     __shared__ double s_half[128];
     const int d = blockIdx.y, q = blockIdx.z, c = blockIdx.x;
+    pdl_trigger_and_wait();
     if (p.counters && c == 0 && d == 0 && q == 0 && threadIdx.x == 0) p.counters[0] += 1u;   // next iteration number (graph replay)
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 3);
@@ -2404,6 +2419,11 @@ __device__ __forceinline__ void apply_update_body(const LoopParams& p, int q, in
 {
     const int T = p.T, D = p.D, N = p.N;
     __syncthreads();
+    if (p.nl_sums_next)       // the padding (start / goal) of the row whose control costs are taken at the end: requested now, off the critical path
+        for (int i = threadIdx.x; i < 2 * kPad; i += blockDim.x) {
+            const int j = i < kPad ? i : T + i;
+            s_cols[(T + 2) + j] = p.theta_all[((size_t)q * D + d) * N + j];
+        }
     if (from_partials == 3) from_partials = 2;      // weights_update_peer_kernel: s_cols already holds the unnormalised sums over all ranks
     else
     for (int t = threadIdx.x; t < T + 2; t += blockDim.x) {
@@ -2452,7 +2472,10 @@ __device__ __forceinline__ void apply_update_body(const LoopParams& p, int q, in
                 u /= 1.0;
             }
             p.updates[((size_t)q * D + d) * T + t] = u;
-            p.theta_all[((size_t)q * D + d) * N + kPad + t] += 1.0 * u;
+            double* th = p.theta_all + ((size_t)q * D + d) * N + kPad + t;
+            const double updated = *th + 1.0 * u;
+            *th = updated;
+            if (p.nl_sums_next) s_cols[(T + 2) + kPad + t] = updated;       // the updated row, staged for its control costs below
         } else if (p.use_noise_adaptation) {
             const double denom = (from_partials == 2) ? s_cols[T + 1] / psum : s_cols[T + 1];
             p.fprob_sum[(size_t)q * D + d] = denom;
@@ -2464,9 +2487,44 @@ __device__ __forceinline__ void apply_update_body(const LoopParams& p, int q, in
             store_sampler_coefficients(p, q, d, sd);
         }
     }
+    // ---- control costs of the UPDATED row: the control half of the noise-less rollout (Stomp::doNoiselessRollout,
+    // Stomp.cpp:253-272; noise = 0) is known the moment the parameters are — computed here, by the CTA that just wrote the
+    // row, into the record the NEXT iteration reads; the state half rides on the next state kernel launch ----
+    if (p.nl_sums_next) {
+        double* s_row = s_cols + (T + 2);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            const RowCoefficients rc = load_row_coefficients(p);
+            double C_d, cum_d;
+            if (p.control_costs == nullptr && p.num_rules == 1 && rc.fast) {
+                // the shipped loop: interior rows from the staged row, the six padding-only rows from edge_cost (constants of
+                // the solve, edge_rows_kernel) — no table walk on the critical path of the update kernel
+                double c_sum = 0.0;
+                for (int i = 3 + lane; i < N - 3; i += 32) {
+                    const double* xi = s_row + i - 3;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int o = 0; o < 7; ++o) acc += rc.c[o] * xi[o];
+                    const double Ax = acc * rc.sqrt_w;
+                    c_sum += rc.dtw * (Ax * Ax);
+                }
+                c_sum = warp_sum(c_sum);
+                const double* ec = p.edge_cost + ((size_t)q * D + d) * 6;
+                C_d = c_sum + (((ec[0] + ec[1]) + (ec[2] + ec[3])) + (ec[4] + ec[5]));
+            } else {
+                control_cost_sums(p, rc, s_row, nullptr, lane, C_d, cum_d);
+                control_cost_store(p, s_row, lane, p.nl_control + ((size_t)q * D + d) * T);
+            }
+            if (lane == 0) {
+                double* nl = p.nl_sums_next + (size_t)q * p.sumw;
+                nl[1 + d] = C_d; nl[1 + D + d] = C_d; nl[1 + 2 * D + d] = 0.0;
+            }
+        }
+    }
 }
 
-// dynamic shared memory: T + 2 doubles
+// dynamic shared memory: T + 2 + N doubles
 __global__ void __launch_bounds__(256)
 apply_update_kernel(const __grid_constant__ LoopParams p, int from_partials, int nchunks)
 {
@@ -2583,6 +2641,7 @@ weights_update_peer_kernel(const __grid_constant__ LoopParams p, const __grid_co
     __shared__ double s_mm[2 * kMaxPeers];
     __shared__ int s_last;
     const int q = 0;
+    pdl_trigger_and_wait();
     if (p.counters && blockIdx.x == 0 && threadIdx.x == 0) p.counters[0] += 1u;              // next iteration number (graph replay)
     if (query_frozen(p, q)) return;
     TimelineScope tls(p, 3);
@@ -2778,7 +2837,7 @@ noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_cons
         }
     }
     __syncthreads();
-    for (int e = tid; e < p.sumw; e += blockDim.x) p.nl_sums[(size_t)q * p.sumw + e] = ssum[e];
+    for (int e = tid; e < p.sumw; e += blockDim.x) p.nl_sums_next[(size_t)q * p.sumw + e] = ssum[e];     // the record the next iteration reads
     if (tid == 0) {
         double cost = ssum[0];
         for (int d = 0; d < D; ++d) cost += ssum[1 + d];

@@ -386,6 +386,30 @@ __device__ __forceinline__ const float* voxel_of_centre(double cx, double cy, do
     return g.grid + (unsigned)((iz * g.ny + iy) * g.nx + ix);
 }
 
+// The state half of the noise-less rollout (Stomp::doNoiselessRollout, stomp/src/Stomp.cpp:253-272) and the wrapper's stop
+// rule (src/wrappers/stomp/StompPlanner.cpp:107-118) as a TAIL of the state kernel: T extra states read from the padded
+// policy rows, and the thread that finishes last — found with one packed atomic: hits in the low half, finished states in
+// the high half — adds the control costs the update kernel left in the record, and does the bookkeeping.  theta == null:
+// no tail.
+struct NoiselessTail {
+    const double* theta;           // [Q][D][N] + kPad: first free parameter of joint 0
+    int32_t row_stride;            // N
+    int32_t sumw;
+    int64_t query_stride;          // D * N
+    double* state;                 // [Q][T]   noiseless_rollout_.state_costs_
+    uint8_t* verdict;              // [Q][T]
+    uint8_t* valid;                // [Q]      last_noiseless_rollout_valid_
+    double* sums;                  // [Q][sumw] the record: [0] <- S, [1 .. D] control-cost sums (already there)
+    double* total;                 // [Q] noise-less total cost
+    double* best;                  // [Q]
+    double* old_cost;              // [Q]
+    double* improvement;           // [Q]
+    int32_t* iters;                // [Q]
+    int32_t* stop;                 // [Q]
+    uint32_t* counter;             // [Q] zero between launches
+    double min_cost_improvement;
+};
+
 // arguments of the specialised state kernel (the subset of LoopParams that rollout_states_kernel reads)
 struct StateKernelArgs {
     const double* rollouts;        // [Q][slots][D][T]
@@ -400,6 +424,7 @@ struct StateKernelArgs {
     int32_t T, D, slots, gslots, sumw, num_gen, gen_offset, honour_stop, debug_skip;
     int32_t row_stride;            // doubles between consecutive joints of one rollout (T; N for the padded policy rows)
     int64_t rollout_stride;        // doubles between consecutive rollouts (D * T)
+    NoiselessTail nl;
 };
 
 }  // namespace stomp_b200

@@ -13,6 +13,12 @@ print({k:d[k] for k in ('value','ms_per_step','gpu_launches','graph_replays')}, 
 print('roofline', d['roofline']['frac'], d['roofline']['avg_launch_ms'], 'kernels', d['kernel_ms_per_step'])
 print('c4', d['query_sharded_c4'])
 PY
+STOMP_B200_PDL=0 timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline --skip-c4 > gpurun_out/bench_c3_${tag}_nopdl.json 2>/dev/null
+python - gpurun_out/bench_c3_${tag}_nopdl.json <<'PY'
+import json,sys
+d=json.loads([l for l in open(sys.argv[1]) if l.startswith('{')][-1])
+print('NO PDL:', {k:d[k] for k in ('value','ms_per_step','gpu_launches','graph_replays')}, 'steady', d['steady_state'], 'e2e', d['e2e']['value'])
+PY
 STOMP_B200_GRAPH=0 timeout 600 python bench.py --steps 20 --warmup 5 --skip-cpu-baseline --skip-c4 > gpurun_out/bench_c3_${tag}_nograph.json 2>/dev/null
 python - gpurun_out/bench_c3_${tag}_nograph.json <<'PY'
 import json,sys

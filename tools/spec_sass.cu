@@ -43,6 +43,7 @@ int main(int argc, char** argv)
     if (getenv("BATCH")) opt.batch_sincos = atoi(getenv("BATCH"));
     if (getenv("BLOCK")) opt.block_threads = atoi(getenv("BLOCK"));
     if (getenv("FOLD")) opt.fold_identity = atoi(getenv("FOLD")) != 0;
+    if (getenv("NOTAIL")) opt.no_tail = atoi(getenv("NOTAIL")) != 0;
     const std::string src = codegen::generate_state_kernel_source(r, opt);
     std::vector<char> cubin; std::string log, err;
     if (!codegen::compile_to_cubin(src, cubin, log, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }

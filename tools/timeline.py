@@ -60,5 +60,6 @@ print("  gaps " + "->".join(names[k] for k in order) + " (median us):", [round(f
 nxt = tl[1:, 0, 0] - tl[:-1, last, 1]
 print(f"  gap {names[last]} -> next sample (median us):", round(float(np.median(nxt)), 1))
 print("  iteration period (median us):", round(float(np.median(tl[1:, 0, 0] - tl[:-1, 0, 0])), 1))
-print(f"  noiseless start after {names[last]} end (median us):", round(float(np.median(tl[:, 5, 0] - tl[:, last, 1])), 1),
+if not np.all(tl[:, 5, 0] < 0):      # absent when the noise-less rollout rides on the state kernel (specialised kernel)
+  print(f"  noiseless start after {names[last]} end (median us):", round(float(np.median(tl[:, 5, 0] - tl[:, last, 1])), 1),
       " noiseless end before the next weights / update start:", round(float(np.median(tl[1:, 2 if 2 in order else 3, 0] - tl[:-1, 5, 1])), 1))
