@@ -309,7 +309,12 @@ cudaError_t launch_dependent(const stomp_b200_engine* e, int which, const void* 
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
-    cfg.numAttrs = (e->pdl_mask >> which) & 1;
+    // A dependent's CTAs become resident wherever room is while the kernel before it drains.  A grid that fills the GPU
+    // anyway loses nothing; a small one gets packed onto the few SMs that were free first and runs slower than the gap it
+    // saved (sampler of a 2048-rollout shard: 12.8 -> 18.6 us, profiles/r3u_pdl_two_gpus.txt): those launch the ordinary way.
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    const bool fills = which == 0 ? ctas >= 5LL * e->num_sms : (which == 2 ? ctas >= (long long)e->num_sms : true);
+    cfg.numAttrs = (((e->pdl_mask >> which) & 1) && fills) ? 1 : 0;
     return cudaLaunchKernelExC(&cfg, kernel, args);
 }
 
