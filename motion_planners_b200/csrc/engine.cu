@@ -972,6 +972,9 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
                     (world == 1 || e->peer_ready) && c.num_rollouts_per_iteration % world == 0 &&
                     !e->noiseless_pending && (!e->nl_deferred || e->nl_lp.honour_stop == honour_stop);
     eligible = eligible && noiseless_tail_available(e);      // the side-stream rollout bakes per-iteration state into its parameters
+    // the first iteration after a join (the owed rollout was flushed for the caller) happens once per call: not worth a
+    // capture (~0.15 ms) of its own
+    eligible = eligible && e->nl_deferred;
     if (eligible && !e->adapted_valid)          // sigma is a per-iteration kernel parameter unless it does not decay
         for (int d = 0; d < e->D; ++d) eligible = eligible && c.noise_decay[d] == 1.0;
     if (!eligible) return iterate_body(e, iteration, mode, honour_stop, false);
