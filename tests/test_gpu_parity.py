@@ -852,3 +852,36 @@ def test_alternative_state_costs(mode, medium_problem):
     costs01, _, _ = e.evaluate_states(theta)
     np.testing.assert_array_equal(costs01, verdicts.astype(np.float64))
     assert not np.array_equal(costs01, costs)
+
+
+def test_graph_replay_and_dependent_launch_change_nothing(medium_problem, monkeypatch):
+    """Steady iterations replay from CUDA graphs (device-side iteration counter, double-buffered noise-less record) and the
+    sampler / update kernels are launched as programmatic dependents: the same kernels on the same data, so the whole solve
+    is bit for bit the one plain launches give — parameters, noise-less cost, iteration count, stop behaviour."""
+    pb = medium_problem
+    results, replays = [], []
+    for graph, pdl in (("1", "5"), ("0", "0"), ("1", "0"), ("0", "5")):
+        monkeypatch.setenv("STOMP_B200_GRAPH", graph)
+        monkeypatch.setenv("STOMP_B200_PDL", pdl)
+        e = binding.engine_for_problem(pb)
+        e.begin_solve()
+        e.run(0, 7)                      # queued back to back: graphs from the fourth iteration on
+        e.run(7, 1)                      # a lone iteration: plain launches, the noise-less tail launched alone at the join
+        e.run(8, 6, honour_stop=True)
+        replays.append(e.graph_replays())
+        r = e.finish_solve()
+        results.append((r["solution"].copy(), r["cost"].copy(), r["iterations"].copy(), e.tensor("stddevs").copy()))
+        e.close()
+    assert replays[0] > 0 and replays[2] > 0 and replays[1] == 0 and replays[3] == 0
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            np.testing.assert_array_equal(a, b)
+    # and the device-side solve loop on top of graphs: same answer as the host-paced loop without them
+    monkeypatch.setenv("STOMP_B200_GRAPH", "1"); monkeypatch.setenv("STOMP_B200_PDL", "5")
+    e1 = binding.engine_for_problem(pb); e1.begin_solve(); e1.solve(25, 4); r1 = e1.finish_solve(); n1 = e1.graph_replays(); e1.close()
+    monkeypatch.setenv("STOMP_B200_GRAPH", "0"); monkeypatch.setenv("STOMP_B200_PDL", "0")
+    e2 = binding.engine_for_problem(pb); e2.begin_solve(); e2.solve(25, 1); r2 = e2.finish_solve(); e2.close()
+    assert n1 > 0
+    np.testing.assert_array_equal(r1["solution"], r2["solution"])
+    np.testing.assert_array_equal(r1["iterations"], r2["iterations"])
+    np.testing.assert_array_equal(r1["cost"], r2["cost"])
