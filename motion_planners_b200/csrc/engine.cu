@@ -116,6 +116,13 @@ struct stomp_b200_engine {
     bool extras_on = false;
     SelfPairs self_pairs = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};   // stomp_b200_set_self_collision; n == 0: world collisions only
     std::vector<void*> self_pair_buffers;
+    // the pair rule inside a run-time specialised kernel (state_codegen.hpp: SelfPairStructure): structure, FP32 thresholds
+    // (lo[P], hi[P], block[B]: the SelfBands kernel parameter) and the kernel, resolved at the first launch after a change
+    codegen::SelfPairStructure self_structure;
+    std::vector<float> self_bands;
+    const codegen::SpecialisedKernel* spec_self = nullptr;
+    bool spec_self_resolved = false;
+    std::string spec_self_note;
     bool have_chain = false, have_spheres = false, have_sdf = false, have_matrices = false;
     std::vector<uint8_t> have_policy;
 
@@ -197,6 +204,19 @@ struct stomp_b200_engine {
     unsigned char* h_scalars = nullptr;      // the pinned block the five mirrors above point into
     unsigned char* d_scalars = nullptr;      // its device counterpart (LoopParams nl_total / last_improvement / stop / iters_used / nl_valid)
     size_t scalar_bytes = 0;
+    // Progress words the device writes straight into host memory (mapped, pinned): [Q][2] = (noise-less rollouts recorded,
+    // stopped).  stomp_b200_solve queues iterations against them — a bounded number ahead of the device — instead of
+    // synchronising every poll_every iterations: no bubbles, at most `solve_ahead` no-op iterations behind the stop.
+    volatile int32_t* h_note = nullptr;
+    int solve_ahead = 1;                     // STOMP_B200_SOLVE_AHEAD at creation; 0: the synchronising poll loop
+    // results of the last read-back, valid until something is queued again: finish_solve after solve touches no device
+    bool scalars_fresh = false, solution_fresh = false;
+    bool note_writers_in_flight = false;     // kernels queued since the last synchronisation of the main stream
+    double* h_solution = nullptr;            // pinned [Q][D][T], allocated on first use
+    // pinned staging of stomp_b200_set_policy: [Q][D*N + D*T]; a slot is rewritten only after its copy has gone out
+    double* h_policy = nullptr;
+    std::vector<uint8_t> policy_in_flight;
+    cudaEvent_t ev_policy = nullptr;
 
     // measurement
     bool profiling = false;
@@ -336,8 +356,46 @@ void launch_states_self_collision_t(stomp_b200_engine* e, const StateKernelArgs&
     else states_self_collision_kernel<kCap, false><<<grid, 128, 0, stream>>>(a, e->robot, e->sdf, e->self_pairs);
 }
 
-void launch_states_self_collision(stomp_b200_engine* e, const StateKernelArgs& a, dim3 grid, cudaStream_t stream)
+codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e);
+
+// the specialised kernel with the pair rule for the pair list as it is now, or null (then states_self_collision_kernel runs)
+void resolve_self_kernel(stomp_b200_engine* e)
 {
+    if (e->spec_self_resolved) return;
+    e->spec_self_resolved = true;
+    e->spec_self = nullptr;
+    const char* mode = std::getenv("STOMP_B200_SELF");
+    if (mode && std::strcmp(mode, "generic") == 0) { e->spec_self_note = "STOMP_B200_SELF=generic"; return; }
+    const char* smode = std::getenv("STOMP_B200_STATES");
+    if (smode && std::strcmp(smode, "generic") == 0) { e->spec_self_note = "STOMP_B200_STATES=generic"; return; }
+    if (e->self_pairs.n <= 0 || e->self_pairs.n > codegen::kSelfPairCap || e->self_bands.empty()) { e->spec_self_note = "pair list too long for the generated kernel"; return; }
+    for (int d = 0; d < e->robot.num_joints; ++d)      // the FP32 bands rest on a bound of the centres that unclamped prismatic values can break
+        if (e->robot.joint[d].prismatic) { e->spec_self_note = "prismatic joint"; return; }
+    codegen::StateKernelOptions opt = state_kernel_options(e);
+    if (!opt.fold_identity || opt.brick_sdf || opt.stage_joints) { e->spec_self_note = "state kernel options without the pair rule"; return; }
+    opt.self = &e->self_structure;
+    opt.no_tail = true;          // the noise-less rollout of a pair-rule engine is a launch of its own (noiseless_tail_available)
+    opt.block_threads = 128;
+    if (const char* t = std::getenv("STOMP_B200_SELF_BLOCK")) { const int v = std::atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) opt.block_threads = v; }
+    // the FP32 centres of the spheres that still have partners ahead stay in registers: left alone the dual arm's walk takes
+    // 228 of them (8 warps per SM); bounded to 168 (12 warps per SM) a dozen values spill
+    opt.min_blocks = std::max(1, 384 / opt.block_threads);
+    if (const char* t = std::getenv("STOMP_B200_SELF_MIN_BLOCKS")) opt.min_blocks = std::max(0, std::atoi(t));
+    std::string err;
+    e->spec_self = codegen::specialised_state_kernel(e->robot, opt, err);
+    e->spec_self_note = e->spec_self ? std::string() : err;
+}
+
+void launch_states_self_collision(stomp_b200_engine* e, const StateKernelArgs& a, dim3 grid, cudaStream_t stream, bool sane = true)
+{
+    resolve_self_kernel(e);
+    if (e->spec_self && sane) {
+        const unsigned bt = (unsigned)e->spec_self->block_threads;
+        const unsigned blocks = (unsigned)(((size_t)grid.x * 128 + bt - 1) / bt);     // the callers size their grids for 128-thread CTAs
+        void* args[] = {(void*)&a, &e->robot, &e->sdf, &e->self_pairs, e->self_bands.data()};
+        (void)cudaLaunchKernel((const void*)e->spec_self->kernel, dim3(blocks, grid.y), dim3(bt), args, 0, stream);
+        return;
+    }
     const int S = e->robot.num_spheres;
     if (S <= 32) launch_states_self_collision_t<32>(e, a, grid, stream);
     else if (S <= 64) launch_states_self_collision_t<64>(e, a, grid, stream);
@@ -504,7 +562,7 @@ codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
     if (const char* bs = std::getenv("STOMP_B200_STATES_BATCH")) opt.batch_sincos = std::max(0, std::atoi(bs));
     if (const char* fo = std::getenv("STOMP_B200_STATES_FOLD")) opt.fold_identity = std::atoi(fo) != 0;
     opt.brick_sdf = e->sdf.bricks != nullptr && opt.fold_identity;
-    if (const char* t = std::getenv("STOMP_B200_STATES_BLOCK")) { const int v = std::atoi(t); if (v == 64 || v == 128 || v == 256) opt.block_threads = v; }
+    if (const char* t = std::getenv("STOMP_B200_STATES_BLOCK")) { const int v = std::atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) opt.block_threads = v; }
     return opt;
 }
 
@@ -540,7 +598,7 @@ void fill_noiseless_tail(const stomp_b200_engine* e, const LoopParams& lp, doubl
     nl.theta = lp.theta_all + kPad; nl.row_stride = lp.N; nl.sumw = lp.sumw; nl.query_stride = (int64_t)lp.D * lp.N;
     nl.state = lp.nl_state; nl.verdict = lp.nl_verdict; nl.valid = lp.nl_valid; nl.sums = record;
     nl.total = lp.nl_total; nl.best = lp.best_cost; nl.old_cost = lp.old_cost; nl.improvement = lp.last_improvement;
-    nl.iters = lp.iters_used; nl.stop = lp.stop; nl.counter = e->d_nl_counter; nl.min_cost_improvement = lp.min_cost_improvement;
+    nl.iters = lp.iters_used; nl.stop = lp.stop; nl.counter = e->d_nl_counter; nl.note = lp.note; nl.min_cost_improvement = lp.min_cost_improvement;
 }
 
 // the state kernel on the T noise-less states + noiseless_rollout_kernel (K10 + the wrapper's stop rule) for the iteration
@@ -964,6 +1022,8 @@ struct HostIterationState {
 // then (LoopParams::counters).  Everything else runs iterate_body directly.
 int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop, bool allow_graph = true)
 {
+    e->scalars_fresh = false; e->solution_fresh = false;
+    e->note_writers_in_flight = true;
     const stomp_b200_config& c = e->cfg;
     const int world = c.shard_mode == 0 ? c.world_size : 1;
     bool eligible = allow_graph && e->graphs_allowed && e->d_counters && mode == kNoisePhilox && !e->profiling && !e->timeline_on && !e->reuse_possible &&
@@ -1164,13 +1224,24 @@ int join_side_stream(stomp_b200_engine* e)
     return 0;
 }
 
-int fetch_query_scalars(stomp_b200_engine* e)
+// One read-back per poll: the per-query scalars (one pinned block) and, on request, the solution rows
+// parameters_all_[d][6 + t] (StompPlanner.cpp:148-163) into their pinned mirror; one synchronisation for both.
+constexpr size_t kSolutionMirrorCap = (size_t)64 << 20;
+int fetch_query_scalars(stomp_b200_engine* e, bool with_solution = false)
 {
-    const LoopParams& b = e->base;
     if (int rc = join_side_stream(e)) return rc;
-    (void)b;
     CUDA_TRY(e, cudaMemcpyAsync(e->h_scalars, e->d_scalars, e->scalar_bytes, cudaMemcpyDeviceToHost, e->stream));
+    const size_t sol_bytes = sizeof(double) * (size_t)e->Q * e->D * e->T;
+    if (with_solution && sol_bytes <= kSolutionMirrorCap) {
+        if (!e->h_solution) CUDA_TRY(e, cudaMallocHost(&e->h_solution, sol_bytes));
+        CUDA_TRY(e, cudaMemcpy2DAsync(e->h_solution, sizeof(double) * e->T, e->base.theta_all + kPad, sizeof(double) * e->N,
+                                      sizeof(double) * e->T, (size_t)e->Q * e->D, cudaMemcpyDeviceToHost, e->stream));
+    } else with_solution = false;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->note_writers_in_flight = false;
+    e->scalars_fresh = true;
+    e->solution_fresh = with_solution;
+    std::fill(e->policy_in_flight.begin(), e->policy_in_flight.end(), 0);
     resolve_profile(e);
     if (e->peer_ready && *e->h_peer_error != 0)
         return fail(e, STOMP_B200_ERR_NCCL, "peer exchange: a rank did not publish within 4 s (rank missing, or ranks not running the same iterations)");
@@ -1442,6 +1513,18 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     e->h_valid = reinterpret_cast<uint8_t*>(e->h_iters + Q);
     e->h_peer_error = reinterpret_cast<int32_t*>(e->h_scalars + (e->scalar_bytes - sizeof(int32_t)));
     *e->h_peer_error = 0;
+    {
+        void* note = nullptr;
+        CREATE_CUDA(cudaHostAlloc(&note, sizeof(int32_t) * 2 * Q, cudaHostAllocMapped));
+        std::memset(note, 0, sizeof(int32_t) * 2 * Q);
+        e->h_note = static_cast<volatile int32_t*>(note);
+        void* dnote = nullptr;
+        CREATE_CUDA(cudaHostGetDevicePointer(&dnote, note, 0));
+        e->base.note = static_cast<int32_t*>(dnote);
+        if (const char* s = std::getenv("STOMP_B200_SOLVE_AHEAD")) e->solve_ahead = std::max(0, std::min(16, std::atoi(s)));
+        e->policy_in_flight.assign(Q, 0);
+        CREATE_CUDA(cudaEventCreateWithFlags(&e->ev_policy, cudaEventDisableTiming));
+    }
     std::memset(&e->px, 0, sizeof(e->px));
     {
         cudaDeviceProp prop;
@@ -1486,6 +1569,10 @@ int stomp_b200_destroy(stomp_b200_engine* e)
     if (e->eval_verdict) cudaFree(e->eval_verdict);
     if (e->eval_valid) cudaFree(e->eval_valid);
     if (e->h_scalars) cudaFreeHost(e->h_scalars);
+    if (e->h_note) cudaFreeHost(const_cast<int32_t*>(e->h_note));
+    if (e->h_solution) cudaFreeHost(e->h_solution);
+    if (e->h_policy) cudaFreeHost(e->h_policy);
+    if (e->ev_policy) cudaEventDestroy(e->ev_policy);
     if (e->timer_a) cudaEventDestroy(e->timer_a);
     if (e->timer_b) cudaEventDestroy(e->timer_b);
     if (e->ev_applied) cudaEventDestroy(e->ev_applied);
@@ -1598,6 +1685,7 @@ int stomp_b200_set_spheres(stomp_b200_engine* e, int32_t num_spheres, const int3
     e->spec_resolved = false;
     e->config_epoch++;
     e->self_pairs.n = 0;   // indices and radii of an earlier pair list no longer apply
+    e->spec_self = nullptr; e->spec_self_resolved = false; e->self_bands.clear();
     return STOMP_B200_OK;
 }
 
@@ -1684,6 +1772,45 @@ int stomp_b200_set_self_collision(stomp_b200_engine* e, int32_t num_pairs, const
             block_limit2.push_back(sum * sum);
         }
         block.back().w = p + 1;
+    }
+    // ---- the same rule for the generated kernel: FP32 centres in registers, thresholds conservative on both sides ----
+    e->spec_self = nullptr; e->spec_self_resolved = false;
+    e->self_structure = codegen::SelfPairStructure();
+    e->self_bands.clear();
+    if (num_pairs > 0 && num_pairs <= codegen::kSelfPairCap) {
+        // B bounds |coordinate| of any sphere centre (chain reach, state_codegen.hpp).  A centre rounded to binary32 is off by
+        // <= 2^-24 B per axis, a difference of two by <= 2^-22 B per axis (its own rounding included): the FP32 distance of a
+        // pair is within delta = sqrt(3) 2^-22 B of the FP64 one, and its square carries three more roundings (rho).  The
+        // FP64 rule's own rounding (1e-16 relative) disappears in the slack of delta.
+        double band_scale = 1.0;
+        if (const char* bsc = std::getenv("STOMP_B200_SELF_BAND")) band_scale = std::max(1.0, std::atof(bsc));   // test knob: widens the undecided band
+        const double B = codegen::centre_bound(r);
+        const double delta = (1.7320508075688773 * std::ldexp(B, -22) * 1.05 + 1e-12) * band_scale;
+        const double rho = std::ldexp(1.0, -21);
+        auto down = [](double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; };
+        auto up = [](double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; };
+        std::vector<float> lo((size_t)num_pairs), hi((size_t)num_pairs), blockf(block.size());
+        for (int p = 0; p < num_pairs; ++p) {
+            const double ell = r.sphere[ij[p].x].r + r.sphere[ij[p].y].r;
+            const double inner = std::max(0.0, ell - delta), outer = ell + delta;
+            lo[p] = down(inner * inner * (1.0 - rho));
+            hi[p] = up(outer * outer * (1.0 + rho));
+            e->self_structure.i.push_back(ij[p].x);
+            e->self_structure.j.push_back(ij[p].y);
+        }
+        for (size_t b = 0; b < block.size(); ++b) {
+            // bounding centres are means of up to n FP32 centres: off by a few 2^-24 B; the cull must keep every block that
+            // holds a pair the bands above would not call clear
+            const int na = r.sphere_begin[block[b].x + 1] - r.sphere_begin[block[b].x], nb = r.sphere_begin[block[b].y + 1] - r.sphere_begin[block[b].y];
+            const double delta_b = std::ldexp(B, -17) * (1.0 + (na + nb) / 32.0);
+            const double reach2 = (bound_radius[block[b].x] + bound_radius[block[b].y]) * (1.0 + 1e-6) + delta_b + 2.0 * delta;
+            blockf[b] = up(reach2 * reach2 * (1.0 + 4.0 * rho));
+            e->self_structure.blocks.push_back({block[b].x, block[b].y, block[b].z, block[b].w});
+        }
+        e->self_bands.insert(e->self_bands.end(), lo.begin(), lo.end());
+        e->self_bands.insert(e->self_bands.end(), hi.begin(), hi.end());
+        e->self_bands.insert(e->self_bands.end(), blockf.begin(), blockf.end());
+        if (blockf.empty()) e->self_bands.push_back(0.f);
     }
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -2041,9 +2168,28 @@ int stomp_b200_set_policy(stomp_b200_engine* e, int32_t query, const double* par
         if (!(std::fabs(min_control_cost[i]) <= 1e6)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "min_control_cost holds a NaN, an infinity or a value beyond 1e6");
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     if (int rc = join_side_stream(e)) return rc;      // an owed noise-less rollout belongs to the policy as it is now
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    CUDA_TRY(e, cudaMemcpy(e->base.theta_all + (size_t)query * e->D * e->N, parameters_all, sizeof(double) * e->D * e->N, cudaMemcpyHostToDevice));
-    CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.mincc) + (size_t)query * e->D * e->T, min_control_cost, sizeof(double) * e->D * e->T, cudaMemcpyHostToDevice));
+    e->scalars_fresh = false; e->solution_fresh = false;
+    // stream-ordered copies out of a pinned staging slot per query: no synchronisation, the caller's buffers are free on return
+    const size_t na = (size_t)e->D * e->N, nm = (size_t)e->D * e->T, slot = na + nm;
+    if (!e->h_policy && sizeof(double) * slot * e->Q <= ((size_t)256 << 20))
+        if (cudaMallocHost(&e->h_policy, sizeof(double) * slot * e->Q) != cudaSuccess) { e->h_policy = nullptr; cudaGetLastError(); }
+    if (e->h_policy) {
+        if (e->policy_in_flight[query]) {      // the slot's previous copy may still be reading it
+            CUDA_TRY(e, cudaEventSynchronize(e->ev_policy));
+            std::fill(e->policy_in_flight.begin(), e->policy_in_flight.end(), 0);
+        }
+        double* stage = e->h_policy + slot * query;
+        std::memcpy(stage, parameters_all, sizeof(double) * na);
+        std::memcpy(stage + na, min_control_cost, sizeof(double) * nm);
+        CUDA_TRY(e, cudaMemcpyAsync(e->base.theta_all + (size_t)query * na, stage, sizeof(double) * na, cudaMemcpyHostToDevice, e->stream));
+        CUDA_TRY(e, cudaMemcpyAsync(const_cast<double*>(e->base.mincc) + (size_t)query * nm, stage + na, sizeof(double) * nm, cudaMemcpyHostToDevice, e->stream));
+        CUDA_TRY(e, cudaEventRecord(e->ev_policy, e->stream));
+        e->policy_in_flight[query] = 1;
+    } else {
+        CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+        CUDA_TRY(e, cudaMemcpy(e->base.theta_all + (size_t)query * na, parameters_all, sizeof(double) * na, cudaMemcpyHostToDevice));
+        CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.mincc) + (size_t)query * nm, min_control_cost, sizeof(double) * nm, cudaMemcpyHostToDevice));
+    }
     e->have_policy[query] = 1;
     e->edge_dirty = true;
     return STOMP_B200_OK;
@@ -2087,6 +2233,16 @@ int stomp_b200_begin_solve(stomp_b200_engine* e)
     e->last_gen = 0; e->last_local = 0; e->last_noiseless_slot = -1;
     if (int rc = join_side_stream(e)) return rc;
     e->nl_deferred = false;
+    e->scalars_fresh = false; e->solution_fresh = false;
+    if (e->h_note) {
+        // the progress words are reset from the host: no kernel that could still write them may be in flight (after a
+        // finish_solve none is; policy uploads queued since are copies)
+        if (e->note_writers_in_flight) {
+            CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+            e->note_writers_in_flight = false;
+        }
+        for (int i = 0; i < 2 * e->Q; ++i) e->h_note[i] = 0;
+    }
     CUDA_TRY(e, cudaMemsetAsync(e->d_nl_counter, 0, sizeof(uint32_t) * e->Q, e->stream));
     reset_solve_state_kernel<<<(e->Q + 127) / 128, 128, 0, e->stream>>>(e->base);
     e->launch_count++;
@@ -2143,6 +2299,7 @@ int stomp_b200_run(stomp_b200_engine* e, int32_t first_iteration, int32_t num_it
         if (int rc = iterate_async(e, first_iteration + i, kNoisePhilox, honour_stop ? 1 : 0, allow_graph)) return rc;
     if (int rc = join_side_stream(e)) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    e->note_writers_in_flight = false;
     resolve_profile(e);
     return STOMP_B200_OK;
 }
@@ -2154,12 +2311,50 @@ int stomp_b200_solve(stomp_b200_engine* e, int32_t max_iterations, int32_t poll_
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     if (poll_every <= 0) poll_every = 8;
     int done = 0;
+    // Paced by the device's progress words (one query set on one GPU, or query sharding: no exchange couples the ranks):
+    // iteration i is queued once the noise-less rollout of iteration i - 1 - solve_ahead has been recorded, so the device
+    // never runs dry (the rest of the running iteration is the host's slack) and at most solve_ahead iterations are queued
+    // behind a stop.  One synchronisation per call, at the end.  Rollout sharding keeps the synchronising poll loop: every
+    // rank has to queue the same iterations (the exchange epochs are counted per queued iteration).
+    const bool paced = e->h_note != nullptr && e->solve_ahead > 0 && !(e->cfg.shard_mode == 0 && e->cfg.world_size > 1);
+    if (paced) {
+        unsigned spins = 0;
+        while (done < max_iterations) {
+            bool all_stopped = true;
+            int recorded = INT32_MAX;
+            for (int q = 0; q < e->Q; ++q) {
+                if (e->h_note[2 * q + 1] != 0) continue;
+                all_stopped = false;
+                { const int r = e->h_note[2 * q]; if (r < recorded) recorded = r; }
+            }
+            if (all_stopped) break;
+            bool go = done <= recorded + e->solve_ahead;
+            if (!go && (++spins & 255u) == 0) {
+                // nothing left on the stream and still no word: the record rides on a launch that is not queued yet
+                const cudaError_t qs = cudaStreamQuery(e->stream);
+                if (qs == cudaSuccess) go = true;
+                else if (qs != cudaErrorNotReady) { e->last_error = std::string("stomp_b200_solve: ") + cudaGetErrorString(qs); return STOMP_B200_ERR_CUDA; }
+            }
+            if (!go) {
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+                continue;
+            }
+            if (int rc = iterate_async(e, done, kNoisePhilox, 1)) return rc;
+            ++done;
+            spins = 0;
+        }
+        if (int rc = fetch_query_scalars(e, true)) return rc;
+        if (iterations_run) *iterations_run = done;
+        return STOMP_B200_OK;
+    }
     while (done < max_iterations) {
         const int n = std::min(poll_every, max_iterations - done);
         for (int i = 0; i < n; ++i)
             if (int rc = iterate_async(e, done + i, kNoisePhilox, 1)) return rc;
         done += n;
-        if (int rc = fetch_query_scalars(e)) return rc;     // one pinned block, one synchronisation per poll
+        if (int rc = fetch_query_scalars(e, true)) return rc;     // one pinned block, one synchronisation per poll
         bool all_stopped = true;
         for (int q = 0; q < e->Q && all_stopped; ++q) all_stopped = e->h_stop[q] != 0;
         if (all_stopped) break;
@@ -2173,11 +2368,14 @@ int stomp_b200_finish_solve(stomp_b200_engine* e, double* solution, int32_t* sta
 {
     if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
-    if (int rc = fetch_query_scalars(e)) return rc;
+    // straight after stomp_b200_solve both mirrors are current and no device call is made here
+    if (!e->scalars_fresh || (solution && !e->solution_fresh))
+        if (int rc = fetch_query_scalars(e, solution != nullptr)) return rc;
     if (solution) {
         // parameters_all_[d][6 + t]  (StompPlanner.cpp:148-163)
-        CUDA_TRY(e, cudaMemcpy2D(solution, sizeof(double) * e->T, e->base.theta_all + kPad, sizeof(double) * e->N,
-                                 sizeof(double) * e->T, (size_t)e->Q * e->D, cudaMemcpyDeviceToHost));
+        if (e->solution_fresh) std::memcpy(solution, e->h_solution, sizeof(double) * (size_t)e->Q * e->D * e->T);
+        else CUDA_TRY(e, cudaMemcpy2D(solution, sizeof(double) * e->T, e->base.theta_all + kPad, sizeof(double) * e->N,
+                                      sizeof(double) * e->T, (size_t)e->Q * e->D, cudaMemcpyDeviceToHost));
     }
     for (int q = 0; q < e->Q; ++q) {
         if (status)
@@ -2362,7 +2560,7 @@ int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_
         a.gen_offset = 0; a.honour_stop = 0; a.debug_skip = 0;
         a.row_stride = num_steps; a.rollout_stride = (int64_t)e->D * num_steps;
         if (e->self_pairs.n > 0) {
-            launch_states_self_collision(e, a, dim3((unsigned)((states + 127) / 128), 1), e->stream);
+            launch_states_self_collision(e, a, dim3((unsigned)((states + 127) / 128), 1), e->stream, sane);
         } else if (e->spec && sane) {
             void* args[] = {&a, &e->robot, &e->sdf};
             const int bt = e->spec->block_threads;
@@ -2563,7 +2761,12 @@ int32_t stomp_b200_state_kernel_kind(stomp_b200_engine* e, char* note, size_t no
     resolve_state_kernel(e);
     if (note && note_capacity) {
         std::string text = e->spec ? ("specialised, " + std::to_string(e->spec->registers) + " registers") : ("generic: " + e->spec_note);
-        if (e->self_pairs.n > 0) text = "self-collision kernel (" + std::to_string(e->self_pairs.n) + " sphere pairs), generic FK";
+        if (e->self_pairs.n > 0) {
+            resolve_self_kernel(e);
+            text = "self-collision kernel (" + std::to_string(e->self_pairs.n) + " sphere pairs), " +
+                   (e->spec_self ? "pair rule inside the specialised kernel (FP32 bands, FP64 where undecided), " + std::to_string(e->spec_self->registers) + " registers"
+                                 : "generic FK: " + e->spec_self_note);
+        }
         std::snprintf(note, note_capacity, "%s", text.c_str());
     }
     if (e->self_pairs.n > 0) return 2;
@@ -2616,6 +2819,30 @@ int stomp_b200_codegen_selftest(char* log, size_t log_capacity)
             rc = STOMP_B200_ERR_CUDA;
         } else {
             all_log += "ok: " + std::to_string(cubin.size()) + " byte cubin (" + codegen::cache().nvrtc.where + ") " + clog + "\n";
+        }
+    }
+    if (rc == STOMP_B200_OK) {      // the same walk with the sphere-pair rule inside: every sphere of the first chain against every one of the second
+        codegen::SelfPairStructure sp;
+        std::vector<int> link_of((size_t)sph, 0);
+        for (int d = 0; d < 8; ++d) for (int k = r.sphere_begin[d]; k < r.sphere_begin[d + 1]; ++k) link_of[k] = d;
+        for (int i = 0; i < r.sphere_begin[4]; ++i)
+            for (int j = r.sphere_begin[4]; j < sph; ++j) {
+                const int la = link_of[i], lb = link_of[j];
+                if (sp.blocks.empty() || sp.blocks.back().la != la || sp.blocks.back().lb != lb) sp.blocks.push_back({la, lb, (int)sp.i.size(), (int)sp.i.size()});
+                sp.i.push_back(i); sp.j.push_back(j);
+                sp.blocks.back().end = (int)sp.i.size();
+            }
+        sp.blocks.push_back({7, 7, (int)sp.i.size(), (int)sp.i.size() + 1});      // a pair inside one link: no cull
+        sp.i.push_back(sph - 2); sp.j.push_back(sph - 1);
+        std::vector<char> cubin;
+        std::string clog;
+        codegen::StateKernelOptions opt;
+        opt.magic_floor = true; opt.inside_grid = true; opt.no_tail = true; opt.self = &sp;
+        if (!codegen::compile_to_cubin(codegen::generate_state_kernel_source(r, opt), cubin, clog, err)) {
+            all_log += err;
+            rc = STOMP_B200_ERR_CUDA;
+        } else {
+            all_log += "ok (pair rule, " + std::to_string(sp.i.size()) + " pairs): " + std::to_string(cubin.size()) + " byte cubin " + clog + "\n";
         }
     }
     if (log && log_capacity) std::snprintf(log, log_capacity, "%s", all_log.c_str());

@@ -86,6 +86,7 @@ struct LoopParams {
     double* best_cost;        // [Q]
     int32_t* stop;            // [Q]
     int32_t* iters_used;      // [Q]
+    int32_t* note;            // [Q][2] host-mapped pinned progress words (iterations recorded, stopped) written next to iters_used / stop; may be null
     // control-cost operator
     const double* diff_band;  // [rules][N][7]
     const double* Lt;         // [T][T]  Lt[u][t] = L[t][u]
@@ -1778,14 +1779,7 @@ evaluate_states_kernel(const __grid_constant__ RobotParams robot, const __grid_c
 // accepts: verdicts stay those of the plain list walk (what the oracle does).  Measured on the dual-arm workload
 // (K=2048, T=150, 560 pairs): 635 us as a plain list walk.
 // =====================================================================================================
-struct SelfPairs {
-    const int2* ij;              // [n] sphere indices, x < y, sorted by (link of x, link of y)
-    const double* limit2;        // [n] (r_x + r_y)^2
-    const int4* block;           // [nblocks] (link a, link b, first pair, end pair)
-    const double* block_limit2;  // [nblocks] (bound_a + bound_b)^2 of the inflated bounding radii
-    const double* link_bound;    // [D][4] bounding sphere of a link's spheres in the link frame: x, y, z, (unused)
-    int32_t n, nblocks;
-};
+// struct SelfPairs: kinematics.cuh (the run-time specialised kernel with the pair rule takes it too)
 
 template <int kSphereCapacity, bool kSimple>   // thread-local centre storage sized by the host to the robot (32 / 64 / 128)
 __global__ void __launch_bounds__(128)
@@ -2846,8 +2840,15 @@ noiseless_rollout_kernel(const __grid_constant__ LoopParams p, const __grid_cons
         const double improvement = cost - p.old_cost[q];
         p.old_cost[q] = cost;
         p.last_improvement[q] = improvement;
-        p.iters_used[q] += 1;
-        if ((cost < 1) && (fabs(improvement) < p.min_cost_improvement)) p.stop[q] = 1;
+        const int recorded = p.iters_used[q] + 1;
+        p.iters_used[q] = recorded;
+        const bool stop_now = (cost < 1) && (fabs(improvement) < p.min_cost_improvement);
+        if (stop_now) p.stop[q] = 1;
+        if (p.note) {      // progress words in host memory (stomp_b200_solve paces its queue by them)
+            volatile int* note = p.note + 2 * q;
+            if (stop_now) note[1] = 1;
+            note[0] = recorded;
+        }
     }
     tls.end();
 }

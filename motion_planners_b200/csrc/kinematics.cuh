@@ -407,7 +407,18 @@ struct NoiselessTail {
     int32_t* iters;                // [Q]
     int32_t* stop;                 // [Q]
     uint32_t* counter;             // [Q] zero between launches
+    int32_t* note;                 // [Q][2] host-mapped pinned words (iterations recorded, stopped) the host paces stomp_b200_solve by; may be null
     double min_cost_improvement;
+};
+
+// the sphere-pair rule (stomp_b200_set_self_collision): the list as the host sorted it
+struct SelfPairs {
+    const int2* ij;              // [n] sphere indices, x < y, sorted by (link of x, link of y)
+    const double* limit2;        // [n] (r_x + r_y)^2
+    const int4* block;           // [nblocks] (link a, link b, first pair, end pair)
+    const double* block_limit2;  // [nblocks] (bound_a + bound_b)^2 of the inflated bounding radii
+    const double* link_bound;    // [D][4] bounding sphere of a link's spheres in the link frame: x, y, z, (unused)
+    int32_t n, nblocks;
 };
 
 // arguments of the specialised state kernel (the subset of LoopParams that rollout_states_kernel reads)

@@ -73,7 +73,7 @@ def test_generated_state_kernel_compiles_for_sm_100a_without_a_device():
     prismatic joint, chain restart, every zero mask, narrow and wide voxel index) and compiles both to sm_100a cubins."""
     rc, log = binding.codegen_selftest()
     assert rc == 0, log
-    assert log.count("byte cubin") == 2
+    assert log.count("byte cubin") == 3 and "pair rule" in log      # narrow and wide SDF index, and the walk with the sphere-pair rule inside
 
 
 def test_header_is_plain_c():

@@ -630,13 +630,15 @@ def test_projection_in_per_timestep_mode():
         np.testing.assert_allclose(cost[0], o.noiseless()["total_cost"], rtol=RTOL)
 
 
-@pytest.mark.parametrize("poll_every", [0, 1, 5])
-def test_device_solve_loop_equals_the_host_driven_loop(poll_every):
+@pytest.mark.parametrize("poll_every,ahead", [(0, 1), (0, 3), (0, 0), (1, 0), (5, 0)])
+def test_device_solve_loop_equals_the_host_driven_loop(poll_every, ahead, monkeypatch):
     """stomp_b200_solve (the loop StompPlanner::solve queues on the device, stop rule evaluated there) against the
     reference's control flow driven from the host: iterate, read the noise-less cost, break when it is below 1 and the
     improvement below min_cost_improvement (StompPlanner.cpp:96-118).  Same iteration count, same final trajectory bit
-    for bit, whatever the polling period (iterations queued past the stop are no-ops)."""
+    for bit, whether the host paces its queue by the device's progress words (ahead > 0, the default) or synchronises
+    every poll_every iterations (iterations queued past the stop are no-ops)."""
     pb = P.single_arm_problem(K=32, T=20, sdf_n=64)
+    monkeypatch.setenv("STOMP_B200_SOLVE_AHEAD", str(ahead))
     a = binding.engine_for_problem(pb)
     b = binding.engine_for_problem(pb)
     a.begin_solve(); b.begin_solve()
@@ -653,7 +655,10 @@ def test_device_solve_loop_equals_the_host_driven_loop(poll_every):
     queued = b.solve(40, poll_every)
     ra, rb = a.finish_solve(), b.finish_solve()
     assert rb["iterations"][0] == used == ra["iterations"][0]
-    assert queued >= used and (poll_every != 1 or queued == used)
+    if ahead > 0:
+        assert used <= queued <= used + ahead + 1  # the record of iteration i rides on iteration i + 1; `ahead` more may be queued behind it
+    else:
+        assert queued >= used and (poll_every != 1 or queued == used)
     np.testing.assert_array_equal(ra["solution"], rb["solution"])
     assert ra["cost"][0] == rb["cost"][0] and bool(ra["found"][0]) == bool(rb["found"][0])
     assert used < 40 and rb["found"][0]
@@ -879,7 +884,8 @@ def test_graph_replay_and_dependent_launch_change_nothing(medium_problem, monkey
     # and the device-side solve loop on top of graphs: same answer as the host-paced loop without them
     monkeypatch.setenv("STOMP_B200_GRAPH", "1"); monkeypatch.setenv("STOMP_B200_PDL", "5")
     e1 = binding.engine_for_problem(pb); e1.begin_solve(); e1.solve(25, 4); r1 = e1.finish_solve(); n1 = e1.graph_replays(); e1.close()
-    monkeypatch.setenv("STOMP_B200_GRAPH", "0"); monkeypatch.setenv("STOMP_B200_PDL", "0")
+    # ... and the host pacing its queue by the device's progress words (the default) instead of synchronising every poll
+    monkeypatch.setenv("STOMP_B200_GRAPH", "0"); monkeypatch.setenv("STOMP_B200_PDL", "0"); monkeypatch.setenv("STOMP_B200_SOLVE_AHEAD", "0")
     e2 = binding.engine_for_problem(pb); e2.begin_solve(); e2.solve(25, 1); r2 = e2.finish_solve(); e2.close()
     assert n1 > 0
     np.testing.assert_array_equal(r1["solution"], r2["solution"])

@@ -100,6 +100,7 @@ def test_gpu_self_collision_verdicts_are_bit_exact():
     o = _oracle(pb, pairs)
     e = _engine(pb, pairs, o.policy())
     assert e.state_kernel_kind()[0] == "self-collision"
+    assert "pair rule inside the specialised kernel" in e.state_kernel_kind()[1]
     rng = np.random.default_rng(7)
     theta = rng.uniform(pb.chain.lower[None, :, None], pb.chain.upper[None, :, None], (128, 14, pb.num_time_steps))
     costs, verdicts, validity = e.evaluate_states(theta)
@@ -149,3 +150,34 @@ def test_gpu_self_collision_in_the_loop():
         assert bool(valid[0]) == nl["valid"]
         np.testing.assert_array_equal(e.tensor("noiseless_state_costs")[0], nl["state_costs"])
     assert differs        # the pair rule changed costs in this scene: the comparison above exercised it
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("band", ["1", "3e4"])
+def test_gpu_pair_rule_in_the_specialised_kernel_equals_the_list_walk(band, monkeypatch):
+    """The pair rule inside the run-time specialised kernel decides in FP32 on register-resident centres and hands the
+    undecided states (a pair within micrometres of touching) to an FP64 walk; the verdicts must be those of the plain FP64
+    list walk (states_self_collision_kernel, what the oracle does) on every state.  band = 3e4 widens the undecided band
+    from micrometres to centimetres, so that the FP64 walk runs for a large share of the states."""
+    from motion_planners_b200 import binding
+    pb, pairs = _dual_arm(K=8, T=30, sdf_n=96)
+    o = _oracle(pb, pairs)
+    monkeypatch.setenv("STOMP_B200_SELF_BAND", band)
+    fast = _engine(pb, pairs, o.policy())
+    assert "pair rule inside" in fast.state_kernel_kind()[1]         # (the kernel is chosen at the first launch or query)
+    monkeypatch.setenv("STOMP_B200_SELF", "generic")
+    slow = _engine(pb, pairs, o.policy())
+    assert "generic FK" in slow.state_kernel_kind()[1]
+    rng = np.random.default_rng(11)
+    theta = rng.uniform(pb.chain.lower[None, :, None], pb.chain.upper[None, :, None], (2048, 14, 30))
+    # a cluster of states where the arms nearly touch: interpolate between a clear and a colliding posture
+    a, b = theta[:64, :, :1], theta[64:128, :, :1]
+    theta[:64] = a + (b - a) * np.linspace(0.0, 1.0, 30)[None, None, :]
+    cf, vf, valf = fast.evaluate_states(theta)
+    cs, vs, vals = slow.evaluate_states(theta)
+    np.testing.assert_array_equal(vf, vs)
+    np.testing.assert_array_equal(cf, cs)
+    np.testing.assert_array_equal(valf, vals)
+    rc, rv, rval = o.state_costs(theta[:96], threads=4)
+    np.testing.assert_array_equal(vf[:96], rv)
+    assert 0.02 < vf.mean() < 0.98

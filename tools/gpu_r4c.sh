@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+O=gpurun_out
+python -m pytest tests/test_self_collision.py -m gpu -x -q > $O/pytest_gpu_r4c.log 2>&1; tail -5 $O/pytest_gpu_r4c.log
+python tools/self_collision_loop.py 6 && ncu --set full --clock-control none --import-source on -k regex:stomp_b200_states_specialised -s 6 -c 1 -o $O/prof_r4c_self python tools/self_collision_loop.py 6 > $O/ncu_r4c.log 2>&1
+ncu -i $O/prof_r4c_self.ncu-rep --page raw --csv > $O/prof_r4c_self_raw.csv 2>/dev/null
+ncu -i $O/prof_r4c_self.ncu-rep --page source --csv > $O/prof_r4c_self_src.csv 2>/dev/null
+ls -la $O/prof_r4c_self*

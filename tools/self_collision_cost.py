@@ -19,7 +19,13 @@ def main():
     inside = [(a, b) for base in (0, 7) for a in range(base, base + 7) for b in range(a + 1, base + 7)]
     pairs = P.self_collision_pairs(pb.chain, pb.spheres, disabled_links=inside)
     out = {"workload": f"dual arm K={K} T={T} D=14 S=48 sdf={n}^3", "pairs": int(len(pairs))}
-    for label, pr in (("world_only", np.zeros((0, 2), dtype=np.int32)), ("with_self_collision", pairs)):
+    none = np.zeros((0, 2), dtype=np.int32)
+    variants = [("world_only", none, {}), ("list_walk_generic_fk", pairs, {"STOMP_B200_SELF": "generic"})]
+    for bt, mb in ((128, 3), (128, 2), (128, 4), (64, 6), (64, 8), (96, 4), (256, 1)):
+        variants.append((f"pair_rule_in_specialised_kernel_block{bt}_minblocks{mb}", pairs,
+                         {"STOMP_B200_SELF": "spec", "STOMP_B200_SELF_BLOCK": str(bt), "STOMP_B200_SELF_MIN_BLOCKS": str(mb)}))
+    for label, pr, env in variants:
+        os.environ.update(env)
         e = binding.engine_for_problem(pb)
         e.set_self_collision(pr)
         e.begin_solve()
@@ -30,6 +36,7 @@ def main():
         e.run(35, 10)
         stats = {k: round(1e3 * v[0] / max(v[1], 1), 2) for k, v in e.kernel_stats().items() if v[1]}
         out[label] = {"kind": e.state_kernel_kind()[1], "us_per_iteration": round(1e3 * ms / 30, 1), "kernel_us": stats}
+        e.close()
     print(json.dumps(out, indent=1))
 
 

@@ -44,6 +44,28 @@ int main(int argc, char** argv)
     if (getenv("BLOCK")) opt.block_threads = atoi(getenv("BLOCK"));
     if (getenv("FOLD")) opt.fold_identity = atoi(getenv("FOLD")) != 0;
     if (getenv("NOTAIL")) opt.no_tail = atoi(getenv("NOTAIL")) != 0;
+    codegen::SelfPairStructure sp;
+    if (dual && getenv("PAIRS")) {      // the sphere-pair rule inside the kernel: every sphere of the first arm (object included) against every one of the second
+        std::vector<int> link_of((size_t)s, 0);
+        for (int d = 0; d < r.num_joints; ++d) for (int k = r.sphere_begin[d]; k < r.sphere_begin[d + 1]; ++k) link_of[k] = d;
+        for (int i = 0; i < r.sphere_begin[7]; ++i)
+            for (int j = r.sphere_begin[7]; j < s; ++j) { sp.i.push_back(i); sp.j.push_back(j); }
+        std::vector<size_t> order(sp.i.size());
+        for (size_t p = 0; p < order.size(); ++p) order[p] = p;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+            return std::make_pair(link_of[sp.i[a]], link_of[sp.j[a]]) < std::make_pair(link_of[sp.i[b]], link_of[sp.j[b]]); });
+        codegen::SelfPairStructure sorted;
+        for (size_t p : order) {
+            const int la = link_of[sp.i[p]], lb = link_of[sp.j[p]];
+            if (sorted.blocks.empty() || sorted.blocks.back().la != la || sorted.blocks.back().lb != lb)
+                sorted.blocks.push_back({la, lb, (int)sorted.i.size(), (int)sorted.i.size()});
+            sorted.i.push_back(sp.i[p]); sorted.j.push_back(sp.j[p]);
+            sorted.blocks.back().end = (int)sorted.i.size();
+        }
+        sp = sorted;
+        opt.self = &sp; opt.no_tail = true;
+        std::printf("%zu pairs in %zu link-pair blocks\n", sp.i.size(), sp.blocks.size());
+    }
     const std::string src = codegen::generate_state_kernel_source(r, opt);
     std::vector<char> cubin; std::string log, err;
     if (!codegen::compile_to_cubin(src, cubin, log, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 1; }
