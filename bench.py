@@ -405,15 +405,18 @@ def run_ours(args):
 
     # ---- end to end: the call sequence StompPlanner::solve makes, host buffers in and out ----
     # What StompPlanner::solve does (motion_planners_b200/host/StompPlanner.cpp -> stomp::Stomp::solveOnDevice): policy up,
-    # stomp_b200_solve — the loop queued on the device, the stop rule evaluated there, the host polling the pinned scalars every
-    # 8 iterations — solution down.  Iterations past a query's stop are no-ops, so the rate counts the iterations the queries
-    # really ran (finish_solve's iterations_used).
+    # stomp_b200_solve — the loop queued on the device, the stop rule evaluated there, the host queueing one iteration ahead of the
+    # progress words the device writes into pinned host memory (rollout sharding: a synchronising poll every 8 iterations) —
+    # solution and scalars down in one read-back.  Iterations past a query's stop are no-ops, so the rate counts the iterations
+    # the queries really ran (finish_solve's iterations_used).
     e2e_iters = args.steps
     poll_every = 8
     pol = eng.policy
     h2d = (pol["params_all"].nbytes + pol["mincc"].nbytes) * eng.Q
-    polls = (e2e_iters + poll_every - 1) // poll_every + 1
-    d2h = eng.Q * (D * T * 8 + 8 + 4 + 4) + polls * (eng.Q * 25 + 12)
+    paced = not (world > 1 and shard_mode == 0)
+    polls = 1 if paced else (e2e_iters + poll_every - 1) // poll_every + 1
+    # per query: the solution + per poll the scalar block (and the solution again when polling) + 8 bytes of progress words per iteration
+    d2h = polls * (eng.Q * (D * T * 8 + 25) + 12) + (eng.Q * 8 * 6 if paced else 0)
     dist_barrier(dist, local)
     t0 = time.perf_counter()
     e2e_ran, e2e_solves = 0.0, 0
@@ -495,8 +498,8 @@ def run_ours(args):
         "e2e": {"value": states_per_step * e2e_ran / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / max(e2e_ran, 1.0),
                 "d2h_bytes_per_step": d2h / max(e2e_ran, 1.0), "iterations_run": e2e_ran, "solves": e2e_solves,
                 "what": "whole planning queries, the call sequence of StompPlanner::solve — set_policy (H2D) + begin_solve + stomp_b200_solve "
-                        "(loop queued on the device, stop rule there, pinned scalars polled every 8 iterations) + finish_solve (solution "
-                        "D2H) — repeated until `steps` iterations have really run; host wall clock over the iterations that did work"},
+                        "(loop queued on the device, stop rule there, the host one iteration ahead of the device's progress words in pinned memory; "
+                        "one read-back of solution + scalars) + finish_solve — repeated until `steps` iterations have really run; host wall clock over the iterations that did work"},
         "gpu_launches": int(launches),
         "graph_replays": int(graph_replays),
         "parity_ok": parity_ok, "parity": parity_detail,

@@ -379,6 +379,8 @@ void resolve_self_kernel(stomp_b200_engine* e)
     if (const char* t = std::getenv("STOMP_B200_SELF_BLOCK")) { const int v = std::atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) opt.block_threads = v; }
     // the FP32 centres of the spheres that still have partners ahead stay in registers: left alone the dual arm's walk takes
     // 228 of them (8 warps per SM); bounded to 168 (12 warps per SM) a dozen values spill
+    opt.rollout_lanes = true;
+    if (const char* t = std::getenv("STOMP_B200_SELF_LANES")) opt.rollout_lanes = std::strcmp(t, "time") != 0;
     opt.min_blocks = std::max(1, 384 / opt.block_threads);
     if (const char* t = std::getenv("STOMP_B200_SELF_MIN_BLOCKS")) opt.min_blocks = std::max(0, std::atoi(t));
     std::string err;
@@ -391,7 +393,8 @@ void launch_states_self_collision(stomp_b200_engine* e, const StateKernelArgs& a
     resolve_self_kernel(e);
     if (e->spec_self && sane) {
         const unsigned bt = (unsigned)e->spec_self->block_threads;
-        const unsigned blocks = (unsigned)(((size_t)grid.x * 128 + bt - 1) / bt);     // the callers size their grids for 128-thread CTAs
+        unsigned blocks = (unsigned)(((size_t)grid.x * 128 + bt - 1) / bt);     // the callers size their grids for 128-thread CTAs
+        if (e->spec_self->rollout_lanes) blocks = (unsigned)((a.num_gen + 31) / 32) * (unsigned)((a.T + (int)(bt / 32) - 1) / (int)(bt / 32));
         void* args[] = {(void*)&a, &e->robot, &e->sdf, &e->self_pairs, e->self_bands.data()};
         (void)cudaLaunchKernel((const void*)e->spec_self->kernel, dim3(blocks, grid.y), dim3(bt), args, 0, stream);
         return;
@@ -562,6 +565,7 @@ codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
     if (const char* bs = std::getenv("STOMP_B200_STATES_BATCH")) opt.batch_sincos = std::max(0, std::atoi(bs));
     if (const char* fo = std::getenv("STOMP_B200_STATES_FOLD")) opt.fold_identity = std::atoi(fo) != 0;
     opt.brick_sdf = e->sdf.bricks != nullptr && opt.fold_identity;
+    if (const char* x = std::getenv("STOMP_B200_STATES_PER_THREAD")) opt.states_per_thread = std::atoi(x) == 2 ? 2 : 1;
     if (const char* t = std::getenv("STOMP_B200_STATES_BLOCK")) { const int v = std::atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) opt.block_threads = v; }
     return opt;
 }
@@ -863,7 +867,8 @@ int iterate_body(stomp_b200_engine* e, int iteration, int mode, int honour_stop,
         } else if (e->spec) {
             void* args[] = {&a, &e->robot, &e->sdf};
             const int bt = e->spec->block_threads;
-            const int blocks = (states + bt - 1) / bt + (tail_in_state_kernel ? (e->T + bt - 1) / bt : 0);    // main CTAs, then the tail's
+            const int per_thread = e->spec->states_per_thread;
+            const int blocks = ((states + per_thread - 1) / per_thread + bt - 1) / bt + (tail_in_state_kernel ? (e->T + bt - 1) / bt : 0);    // main CTAs, then the tail's
             CUDA_TRY(e, launch_dependent(e, 1, (const void*)e->spec->kernel, dim3(blocks, e->Q), dim3(bt), 0, e->stream, args));
         } else if (e->robot.simple_chain) rollout_states_kernel<true><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);
         else rollout_states_kernel<false><<<grid, 256, 0, e->stream>>>(lp, e->robot, e->sdf);

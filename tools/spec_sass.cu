@@ -44,6 +44,8 @@ int main(int argc, char** argv)
     if (getenv("BLOCK")) opt.block_threads = atoi(getenv("BLOCK"));
     if (getenv("FOLD")) opt.fold_identity = atoi(getenv("FOLD")) != 0;
     if (getenv("NOTAIL")) opt.no_tail = atoi(getenv("NOTAIL")) != 0;
+    if (getenv("LANES")) opt.rollout_lanes = true;
+    if (getenv("SPT")) opt.states_per_thread = atoi(getenv("SPT"));
     codegen::SelfPairStructure sp;
     if (dual && getenv("PAIRS")) {      // the sphere-pair rule inside the kernel: every sphere of the first arm (object included) against every one of the second
         std::vector<int> link_of((size_t)s, 0);
