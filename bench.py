@@ -417,12 +417,14 @@ def run_ours(args):
     polls = 1 if paced else (e2e_iters + poll_every - 1) // poll_every + 1
     # per query: the solution + per poll the scalar block (and the solution again when polling) + 8 bytes of progress words per iteration
     d2h = polls * (eng.Q * (D * T * 8 + 25) + 12) + (eng.Q * 8 * 6 if paced else 0)
+    # the host buffers of the requests: one policy per local query (the same synthetic request for all of them)
+    host_params = np.ascontiguousarray(np.broadcast_to(pol["params_all"], (eng.Q,) + pol["params_all"].shape))
+    host_mincc = np.ascontiguousarray(np.broadcast_to(pol["mincc"], (eng.Q,) + pol["mincc"].shape))
     dist_barrier(dist, local)
     t0 = time.perf_counter()
     e2e_ran, e2e_solves = 0.0, 0
     while e2e_ran < e2e_iters and e2e_solves < 64:                   # whole planning queries until `steps` iterations have really run
-        for ql in range(eng.Q):
-            eng.set_policy(ql, pol["params_all"], pol["mincc"])      # H2D
+        eng.set_policies(0, host_params, host_mincc)                 # H2D
         eng.begin_solve()
         eng.solve(e2e_iters, poll_every)                             # D2H per poll: noise-less cost, improvement, stop flag, iteration count, validity
         e2e_result = eng.finish_solve()                              # D2H: solution

@@ -157,6 +157,10 @@ int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R /
  * min_control_cost_parameters_free_ [D][T] */
 int stomp_b200_set_policy(stomp_b200_engine* e, int32_t query, const double* parameters_all /*[D][N]*/,
                           const double* min_control_cost /*[D][T]*/);
+/* the same for `count` consecutive local queries starting at first_query, arrays query-major: one pair of copies for a
+ * whole batch of planning requests (StompPlanner::setStartGoalTrajectory of every request of a batch) */
+int stomp_b200_set_policies(stomp_b200_engine* e, int32_t first_query, int32_t count,
+                            const double* parameters_all /*[count][D][N]*/, const double* min_control_cost /*[count][D][T]*/);
 
 /* Host-side (CPU, one-time per query shape) CovariantMovementPrimitive::initialize +
  * computeLinearControlCosts + (optionally) setToMinControlCost.  initial_all [D][N] is the padded

@@ -30,7 +30,7 @@ KERNELS = dict(sample=0, cost=1, weights=2, update=3, apply=4, reuse=5, rows=6)
 SYMBOLS = [
     "stomp_b200_default_config", "stomp_b200_abi_version", "stomp_b200_status_string", "stomp_b200_last_error",
     "stomp_b200_create", "stomp_b200_destroy", "stomp_b200_set_chain", "stomp_b200_set_spheres", "stomp_b200_set_sdf",
-    "stomp_b200_set_control_cost_matrices", "stomp_b200_set_policy", "stomp_b200_host_policy",
+    "stomp_b200_set_control_cost_matrices", "stomp_b200_set_policy", "stomp_b200_set_policies", "stomp_b200_host_policy",
     "stomp_b200_host_initial_trajectory", "stomp_b200_begin_solve", "stomp_b200_iterate",
     "stomp_b200_next_num_generated", "stomp_b200_run", "stomp_b200_solve", "stomp_b200_finish_solve", "stomp_b200_num_rollouts",
     "stomp_b200_get_tensor", "stomp_b200_evaluate_states", "stomp_b200_sphere_centres", "stomp_b200_comm_unique_id",
@@ -101,6 +101,7 @@ def lib():
         L.stomp_b200_get_sdf.argtypes = [vp, C.POINTER(C.c_float), C.c_size_t, ip, dp, dp]
         L.stomp_b200_set_control_cost_matrices.argtypes = [vp, dp, dp, dp]
         L.stomp_b200_set_policy.argtypes = [vp, C.c_int32, dp, dp]
+        L.stomp_b200_set_policies.argtypes = [vp, C.c_int32, C.c_int32, dp, dp]
         L.stomp_b200_host_policy.argtypes = [C.c_int32, C.c_int32, C.c_double, dp, dp, C.c_int32, dp, dp, dp, dp, dp]
         L.stomp_b200_host_initial_trajectory.argtypes = [C.c_int32, C.c_int32, dp, dp, dp]
         L.stomp_b200_begin_solve.argtypes = [vp]
@@ -330,6 +331,12 @@ class Engine:
         pa, mc = _c64(params_all), _c64(mincc)
         assert pa.shape == (self.D, self.N) and mc.shape == (self.D, self.T)
         self._check(lib().stomp_b200_set_policy(self.h, query, _dp(pa), _dp(mc)), "stomp_b200_set_policy")
+
+    def set_policies(self, first_query, params_all, mincc):
+        """a batch of consecutive queries in one call: params_all [count][D][N], mincc [count][D][T]"""
+        pa, mc = _c64(params_all), _c64(mincc)
+        assert pa.ndim == 3 and pa.shape[1:] == (self.D, self.N) and mc.shape == (pa.shape[0], self.D, self.T)
+        self._check(lib().stomp_b200_set_policies(self.h, first_query, pa.shape[0], _dp(pa), _dp(mc)), "stomp_b200_set_policies")
 
     def set_problem(self, problem, policy=None):
         """Scene + StompPlanner::setStartGoalTrajectory for every local query.  `policy`, when given, is a

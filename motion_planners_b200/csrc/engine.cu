@@ -213,7 +213,7 @@ struct stomp_b200_engine {
     bool scalars_fresh = false, solution_fresh = false;
     bool note_writers_in_flight = false;     // kernels queued since the last synchronisation of the main stream
     double* h_solution = nullptr;            // pinned [Q][D][T], allocated on first use
-    // pinned staging of stomp_b200_set_policy: [Q][D*N + D*T]; a slot is rewritten only after its copy has gone out
+    // pinned staging of stomp_b200_set_policies: [Q][D*N] then [Q][D*T]; a slot is rewritten only after its copy has gone out
     double* h_policy = nullptr;
     std::vector<uint8_t> policy_in_flight;
     cudaEvent_t ev_policy = nullptr;
@@ -2160,44 +2160,56 @@ int stomp_b200_set_control_cost_matrices(stomp_b200_engine* e, const double* R, 
     return STOMP_B200_OK;
 }
 
-int stomp_b200_set_policy(stomp_b200_engine* e, int32_t query, const double* parameters_all, const double* min_control_cost)
+int stomp_b200_set_policies(stomp_b200_engine* e, int32_t first_query, int32_t count, const double* parameters_all, const double* min_control_cost)
 {
     if (!e || !parameters_all || !min_control_cost) return STOMP_B200_ERR_INVALID_ARGUMENT;
-    if (query < 0 || query >= e->Q) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "query index out of range");
+    if (count < 1 || first_query < 0 || first_query + count > e->Q) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "query range out of bounds");
+    const size_t na = (size_t)e->D * e->N, nm = (size_t)e->D * e->T;
     // NaN / infinite / absurd joint values never reach the kernels (the reference rejects NaN in checkNaN,
     // src/MotionPlanners.cpp:563-571); 1e6 rad or m is far beyond any joint and far below where the deterministic
     // sin / cos reduction stops being exact
-    for (size_t i = 0; i < (size_t)e->D * e->N; ++i)
+    for (size_t i = 0; i < na * count; ++i)
         if (!(std::fabs(parameters_all[i]) <= 1e6)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "parameters_all holds a NaN, an infinity or a value beyond 1e6");
-    for (size_t i = 0; i < (size_t)e->D * e->T; ++i)
+    for (size_t i = 0; i < nm * count; ++i)
         if (!(std::fabs(min_control_cost[i]) <= 1e6)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "min_control_cost holds a NaN, an infinity or a value beyond 1e6");
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     if (int rc = join_side_stream(e)) return rc;      // an owed noise-less rollout belongs to the policy as it is now
     e->scalars_fresh = false; e->solution_fresh = false;
-    // stream-ordered copies out of a pinned staging slot per query: no synchronisation, the caller's buffers are free on return
-    const size_t na = (size_t)e->D * e->N, nm = (size_t)e->D * e->T, slot = na + nm;
-    if (!e->h_policy && sizeof(double) * slot * e->Q <= ((size_t)256 << 20))
-        if (cudaMallocHost(&e->h_policy, sizeof(double) * slot * e->Q) != cudaSuccess) { e->h_policy = nullptr; cudaGetLastError(); }
+    // stream-ordered copies out of pinned staging (theta rows of all queries, then the min-control-cost rows: the two device
+    // tensors are query-major too, so a batch is two copies): no synchronisation, the caller's buffers are free on return
+    const size_t total = (na + nm) * (size_t)e->Q;
+    if (!e->h_policy && sizeof(double) * total <= ((size_t)256 << 20))
+        if (cudaMallocHost(&e->h_policy, sizeof(double) * total) != cudaSuccess) { e->h_policy = nullptr; cudaGetLastError(); }
+    double* d_theta = e->base.theta_all + (size_t)first_query * na;
+    double* d_mincc = const_cast<double*>(e->base.mincc) + (size_t)first_query * nm;
     if (e->h_policy) {
-        if (e->policy_in_flight[query]) {      // the slot's previous copy may still be reading it
+        bool busy = false;
+        for (int q = first_query; q < first_query + count; ++q) busy = busy || e->policy_in_flight[q];
+        if (busy) {      // a slot's previous copy may still be reading it
             CUDA_TRY(e, cudaEventSynchronize(e->ev_policy));
             std::fill(e->policy_in_flight.begin(), e->policy_in_flight.end(), 0);
         }
-        double* stage = e->h_policy + slot * query;
-        std::memcpy(stage, parameters_all, sizeof(double) * na);
-        std::memcpy(stage + na, min_control_cost, sizeof(double) * nm);
-        CUDA_TRY(e, cudaMemcpyAsync(e->base.theta_all + (size_t)query * na, stage, sizeof(double) * na, cudaMemcpyHostToDevice, e->stream));
-        CUDA_TRY(e, cudaMemcpyAsync(const_cast<double*>(e->base.mincc) + (size_t)query * nm, stage + na, sizeof(double) * nm, cudaMemcpyHostToDevice, e->stream));
+        double* stage_theta = e->h_policy + (size_t)first_query * na;
+        double* stage_mincc = e->h_policy + (size_t)e->Q * na + (size_t)first_query * nm;
+        std::memcpy(stage_theta, parameters_all, sizeof(double) * na * count);
+        std::memcpy(stage_mincc, min_control_cost, sizeof(double) * nm * count);
+        CUDA_TRY(e, cudaMemcpyAsync(d_theta, stage_theta, sizeof(double) * na * count, cudaMemcpyHostToDevice, e->stream));
+        CUDA_TRY(e, cudaMemcpyAsync(d_mincc, stage_mincc, sizeof(double) * nm * count, cudaMemcpyHostToDevice, e->stream));
         CUDA_TRY(e, cudaEventRecord(e->ev_policy, e->stream));
-        e->policy_in_flight[query] = 1;
+        for (int q = first_query; q < first_query + count; ++q) e->policy_in_flight[q] = 1;
     } else {
         CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-        CUDA_TRY(e, cudaMemcpy(e->base.theta_all + (size_t)query * na, parameters_all, sizeof(double) * na, cudaMemcpyHostToDevice));
-        CUDA_TRY(e, cudaMemcpy(const_cast<double*>(e->base.mincc) + (size_t)query * nm, min_control_cost, sizeof(double) * nm, cudaMemcpyHostToDevice));
+        CUDA_TRY(e, cudaMemcpy(d_theta, parameters_all, sizeof(double) * na * count, cudaMemcpyHostToDevice));
+        CUDA_TRY(e, cudaMemcpy(d_mincc, min_control_cost, sizeof(double) * nm * count, cudaMemcpyHostToDevice));
     }
-    e->have_policy[query] = 1;
+    for (int q = first_query; q < first_query + count; ++q) e->have_policy[q] = 1;
     e->edge_dirty = true;
     return STOMP_B200_OK;
+}
+
+int stomp_b200_set_policy(stomp_b200_engine* e, int32_t query, const double* parameters_all, const double* min_control_cost)
+{
+    return stomp_b200_set_policies(e, query, 1, parameters_all, min_control_cost);
 }
 
 int stomp_b200_host_policy(int32_t num_time_steps, int32_t num_dimensions, double movement_duration,

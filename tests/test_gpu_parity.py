@@ -274,6 +274,35 @@ def test_batch_of_queries_equals_separate_engines():
         np.testing.assert_allclose(got["solution"][q], o.parameters(), rtol=0, atol=1e-7)
 
 
+def test_batched_policy_upload_equals_the_per_query_calls():
+    """stomp_b200_set_policies (one pair of stream-ordered copies for a batch of requests) against stomp_b200_set_policy per
+    query: the same solves bit for bit, also when the policies are uploaded again right after a solve (re-planning), and
+    ranges beyond the engine's queries are refused."""
+    Q, K, T = 5, 16, 40
+    pb = P.batch_problem(Q=Q, K=K, T=T, sdf_n=64)
+    a = binding.engine_for_problem(pb)
+    b = binding.engine_for_problem(pb)
+    pols = [binding.host_policy(binding.host_initial_trajectory(pb.start[q], pb.goal[q], T), a.cfg.movement_duration,
+                                tuple(a.cfg.derivative_weights)) for q in range(Q)]
+    pa = np.stack([p_["params_all"] for p_ in pols]); mc = np.stack([p_["mincc"] for p_ in pols])
+    for round_ in range(2):
+        for q in range(Q):
+            a.set_policy(q, pa[q], mc[q])
+        b.set_policies(0, pa[:2], mc[:2])
+        b.set_policies(2, pa[2:], mc[2:])
+        a.begin_solve(); b.begin_solve()
+        a.solve(12); b.solve(12)
+        ra, rb = a.finish_solve(), b.finish_solve()
+        np.testing.assert_array_equal(ra["solution"], rb["solution"])
+        np.testing.assert_array_equal(ra["iterations"], rb["iterations"])
+        np.testing.assert_array_equal(ra["cost"], rb["cost"])
+    with pytest.raises(Exception):
+        b.set_policies(Q - 1, pa[:2], mc[:2])
+    bad = pa.copy(); bad[1, 0, 3] = np.nan
+    with pytest.raises(Exception):
+        b.set_policies(0, bad, mc)
+
+
 def test_full_size_properties_config3():
     # BASELINE config 3 shape: K=4096, T=100, 7-DoF, 256^3 SDF — size-independent properties
     pb = P.single_arm_problem(K=4096, T=100, sdf_n=256)
