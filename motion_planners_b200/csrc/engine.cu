@@ -565,6 +565,7 @@ codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
     if (const char* bs = std::getenv("STOMP_B200_STATES_BATCH")) opt.batch_sincos = std::max(0, std::atoi(bs));
     if (const char* fo = std::getenv("STOMP_B200_STATES_FOLD")) opt.fold_identity = std::atoi(fo) != 0;
     opt.brick_sdf = e->sdf.bricks != nullptr && opt.fold_identity;
+    if (const char* pf = std::getenv("STOMP_B200_STATES_PREFETCH")) opt.prefetch_joints = std::atoi(pf);
     if (const char* x = std::getenv("STOMP_B200_STATES_PER_THREAD")) opt.states_per_thread = std::atoi(x) == 2 ? 2 : 1;
     if (const char* t = std::getenv("STOMP_B200_STATES_BLOCK")) { const int v = std::atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) opt.block_threads = v; }
     return opt;
