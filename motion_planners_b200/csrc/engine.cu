@@ -173,7 +173,7 @@ struct stomp_b200_engine {
     // sampler — its CTAs would become resident beside the sampler's, whose 31 KB of shared memory each keep the SM in its
     // large-shared-memory / small-L1 split, and the state kernel's gathers then run against a sliver of L1: 16.5 -> 34 us
     // (profiles/r3r_pdl_edges.txt).  In-process A / B (profiles/r3s_ab_steady.txt): 56.5 us per iteration against 59.6.
-    int pdl_mask = 5;
+    int pdl_mask = 13;                       // + bit 3: the noise-less tail launched alone at a join (84.8 -> 83.9 us per isolated C3 iteration, profiles/r4j_pdl_tail.txt)
     bool graphs_allowed = true;              // STOMP_B200_GRAPH=0 at creation switches the replay off
     int eligible_streak = 0;                 // graph-eligible iterations run un-captured since the configuration last changed
     unsigned long long streak_epoch = 0;
@@ -625,7 +625,10 @@ int launch_noiseless(stomp_b200_engine* e, bool on_main_stream)
         fill_noiseless_tail(e, lp, e->nl_sums2[e->nl_parity], a.nl);
         void* args[] = {&a, &e->robot, &e->sdf};
         const int bt = e->spec->block_threads;
-        CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + bt - 1) / bt, e->Q), dim3(bt), args, 0, st));
+        // at a join (the caller waits) the tail follows the update kernel on the main stream: as a programmatic dependent its
+        // CTAs are resident and waiting when the update kernel's last CTA retires (bit 3 of STOMP_B200_PDL)
+        if (on_main_stream) CUDA_TRY(e, launch_dependent(e, 3, (const void*)e->spec->kernel, dim3((lp.T + bt - 1) / bt, e->Q), dim3(bt), 0, st, args));
+        else CUDA_TRY(e, cudaLaunchKernel((const void*)e->spec->kernel, dim3((lp.T + bt - 1) / bt, e->Q), dim3(bt), args, 0, st));
         e->launch_count++;
         e->kernel_launches[STOMP_B200_KERNEL_APPLY]++;
         if (!on_main_stream) {
@@ -1477,7 +1480,7 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.tile_counter, 4));
     CREATE_TRY(dev_alloc(e, &e->d_counters, 4));
     if (const char* gr = std::getenv("STOMP_B200_GRAPH")) e->graphs_allowed = std::strcmp(gr, "0") != 0;
-    if (const char* pd = std::getenv("STOMP_B200_PDL")) e->pdl_mask = std::atoi(pd) & 7;
+    if (const char* pd = std::getenv("STOMP_B200_PDL")) e->pdl_mask = std::atoi(pd) & 15;
     CREATE_TRY(dev_alloc(e, &e->d_timeline, (size_t)kTimelineRing * kTimelineKernels * 2));
     b.world_size = world;
 

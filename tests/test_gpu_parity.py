@@ -894,7 +894,7 @@ def test_graph_replay_and_dependent_launch_change_nothing(medium_problem, monkey
     is bit for bit the one plain launches give — parameters, noise-less cost, iteration count, stop behaviour."""
     pb = medium_problem
     results, replays = [], []
-    for graph, pdl in (("1", "5"), ("0", "0"), ("1", "0"), ("0", "5")):
+    for graph, pdl in (("1", "13"), ("0", "0"), ("1", "0"), ("0", "13")):
         monkeypatch.setenv("STOMP_B200_GRAPH", graph)
         monkeypatch.setenv("STOMP_B200_PDL", pdl)
         e = binding.engine_for_problem(pb)
@@ -911,7 +911,7 @@ def test_graph_replay_and_dependent_launch_change_nothing(medium_problem, monkey
         for a, b in zip(results[0], other):
             np.testing.assert_array_equal(a, b)
     # and the device-side solve loop on top of graphs: same answer as the host-paced loop without them
-    monkeypatch.setenv("STOMP_B200_GRAPH", "1"); monkeypatch.setenv("STOMP_B200_PDL", "5")
+    monkeypatch.setenv("STOMP_B200_GRAPH", "1"); monkeypatch.setenv("STOMP_B200_PDL", "13")
     e1 = binding.engine_for_problem(pb); e1.begin_solve(); e1.solve(25, 4); r1 = e1.finish_solve(); n1 = e1.graph_replays(); e1.close()
     # ... and the host pacing its queue by the device's progress words (the default) instead of synchronising every poll
     monkeypatch.setenv("STOMP_B200_GRAPH", "0"); monkeypatch.setenv("STOMP_B200_PDL", "0"); monkeypatch.setenv("STOMP_B200_SOLVE_AHEAD", "0")
