@@ -198,10 +198,14 @@ int stomp_b200_run(stomp_b200_engine* e, int32_t first_iteration, int32_t num_it
 
 /* The whole iteration loop of StompPlanner::solve (StompPlanner.cpp:96-141) on the device: up to max_iterations
  * iterations with the on-device sampler and the stop rule honoured per query (a stopped query is frozen exactly where
- * the reference's `break` leaves it: parameters, noise-less cost, iteration count).  The host looks at the stop flags
- * every poll_every iterations (<= 0: 8) — one pinned read-back and one synchronisation — and stops queueing once every
- * query has stopped; iterations queued past a query's stop are no-ops for it.  iterations_run (may be NULL) =
- * iterations queued; the per-query counts come from stomp_b200_finish_solve. */
+ * the reference's `break` leaves it: parameters, noise-less cost, iteration count).  The host queues iterations one
+ * ahead of two progress words per query (noise-less rollouts recorded, stopped) that the device writes into mapped pinned
+ * host memory, stops queueing once every query has stopped and synchronises once, at the end; that read-back brings the
+ * per-query scalars and the solution rows into pinned mirrors, so that a stomp_b200_finish_solve straight after makes no
+ * device call.  Rollout-sharded engines (every rank has to queue the same iterations) look at the stop flags every
+ * poll_every iterations instead (<= 0: 8; one pinned read-back and one synchronisation per poll).  Iterations queued past
+ * a query's stop are no-ops for it.  iterations_run (may be NULL) = iterations queued; the per-query counts come from
+ * stomp_b200_finish_solve. */
 int stomp_b200_solve(stomp_b200_engine* e, int32_t max_iterations, int32_t poll_every, int32_t* iterations_run);
 
 /* Stomp::setCostCumulation (stomp/src/Stomp.cpp:356-359): 1 = costs summed over the trajectory (the default), 0 = costs
