@@ -2375,7 +2375,9 @@ int stomp_b200_solve(stomp_b200_engine* e, int32_t max_iterations, int32_t poll_
         for (int i = 0; i < n; ++i)
             if (int rc = iterate_async(e, done + i, kNoisePhilox, 1)) return rc;
         done += n;
-        if (int rc = fetch_query_scalars(e, true)) return rc;     // one pinned block, one synchronisation per poll
+        // one pinned block, one synchronisation per poll; a small solution rides along so that finish_solve finds it there
+        const bool small_solution = sizeof(double) * (size_t)e->Q * e->D * e->T <= ((size_t)256 << 10);
+        if (int rc = fetch_query_scalars(e, small_solution)) return rc;
         bool all_stopped = true;
         for (int q = 0; q < e->Q && all_stopped; ++q) all_stopped = e->h_stop[q] != 0;
         if (all_stopped) break;
