@@ -271,7 +271,7 @@ int stomp_b200_set_self_collision(stomp_b200_engine* e, int32_t num_pairs, const
  *   (src/planners/src/wrappers/stomp/OptimizationTask.cpp:206-237; its call at :169-172 is commented out in the reference):
  *   + weight * sum_d max(0, |value_d - q_d| - tolerance_d) on every time step.
  * The verdicts / validity stay the binary collision test.  Applies to the loop, the noise-less rollout and
- * stomp_b200_evaluate_states.  value / tolerance [D] may be NULL when use_joint_constraint == 0.  Not with rollout sharding. */
+ * stomp_b200_evaluate_states.  value / tolerance [D] may be NULL when use_joint_constraint == 0.  Works with rollout and query sharding (set it on every rank). */
 int stomp_b200_set_cost_extras(stomp_b200_engine* e, int32_t use_smooth_cost, double smooth_margin, double smooth_weight,
                                int32_t use_joint_constraint, const double* value /*[D]*/, const double* tolerance /*[D]*/,
                                double joint_constraint_weight);

@@ -1704,8 +1704,6 @@ int stomp_b200_set_cost_extras(stomp_b200_engine* e, int32_t use_smooth_cost, do
     if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
     if (use_joint_constraint && (!value || !tolerance)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "joint constraint needs value and tolerance");
     if (use_smooth_cost && !(smooth_margin >= 0.0 && smooth_weight >= 0.0)) return fail(e, STOMP_B200_ERR_INVALID_ARGUMENT, "smooth cost: margin and weight must be >= 0");
-    if ((use_smooth_cost || use_joint_constraint) && e->cfg.shard_mode == 0 && e->cfg.world_size > 1)
-        return fail(e, STOMP_B200_ERR_UNSUPPORTED, "alternative state costs are built for one GPU (and for query sharding)");
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     if (int rc = join_side_stream(e)) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));

@@ -80,6 +80,40 @@ def main():
             eng.close()
     os.environ.pop("STOMP_B200_EXCHANGE", None)
 
+    # ---- (a') rollout sharding with the alternative state costs and with the sphere-pair rule: per-rollout work, the two
+    # exchanges see the same S_k + C_k,d scalars whatever the state cost is made of ----
+    for case in ("extras", "pairs"):
+        if case == "extras":
+            K, T = 32 * world, 40
+            pbx = P.single_arm_problem(K=K, T=T, sdf_n=64)
+        else:
+            K, T = 16 * world, 30
+            pbx = P.dual_arm_problem(K=K, T=T, sdf_n=64)
+        D = pbx.chain.num_dimensions
+        one = binding.engine_for_problem(pbx, device=local, keep_debug_tensors=True)
+        many = binding.engine_for_problem(pbx, device=local, world_size=world, rank=rank, shard_mode=0, keep_debug_tensors=True)
+        uid = binding.comm_unique_id() if rank == 0 else b""
+        many.comm_init(sharding.broadcast_bytes(dist, uid, binding.COMM_ID_BYTES, dev))
+        for eng in (one, many):
+            if case == "extras":
+                eng.set_cost_extras(smooth=(0.08, 2.0), joint_constraint=(np.zeros(D), np.full(D, 0.5), 0.3))
+            else:
+                inside = [(a, b) for base in (0, 7) for a in range(base, base + 7) for b in range(a + 1, base + 7)]
+                eng.set_self_collision(P.self_collision_pairs(pbx.chain, pbx.spheres, disabled_links=inside))
+        one.begin_solve(); many.begin_solve()
+        off, cnt = sharding.rollout_shard(K, world, rank)
+        for it in range(4):
+            c1, v1, s1 = one.iterate(it)
+            c2, v2, s2 = many.iterate(it)
+            np.testing.assert_array_equal(many.tensor("verdicts")[0][:cnt], one.tensor("verdicts")[0][off:off + cnt])
+            np.testing.assert_allclose(many.tensor("state_costs")[0][:cnt], one.tensor("state_costs")[0][off:off + cnt], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(many.tensor("total_cost")[0], one.tensor("total_cost")[0], rtol=1e-9)
+            np.testing.assert_allclose(many.tensor("probabilities")[0], one.tensor("probabilities")[0], rtol=1e-9, atol=1e-300)
+            np.testing.assert_allclose(many.tensor("parameters")[0], one.tensor("parameters")[0], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(c2, c1, rtol=1e-9)
+            assert bool(v1[0]) == bool(v2[0])
+        one.close(); many.close()
+
     # ---- (b) query sharding ----
     Q = 3 * world + 1
     pbq = P.batch_problem(Q=Q, K=16, T=30, sdf_n=64)
