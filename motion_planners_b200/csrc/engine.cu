@@ -196,6 +196,7 @@ struct stomp_b200_engine {
     // the chain / spheres / SDF changed
     const codegen::SpecialisedKernel* spec = nullptr;
     bool spec_resolved = false;
+    int32_t* d_static_hit = nullptr;         // verdict of the spheres no joint value moves (stomp_b200_static_spheres), rewritten whenever the state kernel is resolved
     std::string spec_note;          // why the generic kernel is in use, when it is
 
     // pinned host mirrors of the per-query scalars
@@ -566,6 +567,7 @@ codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
     if (const char* fo = std::getenv("STOMP_B200_STATES_FOLD")) opt.fold_identity = std::atoi(fo) != 0;
     opt.brick_sdf = e->sdf.bricks != nullptr && opt.fold_identity;
     if (const char* pf = std::getenv("STOMP_B200_STATES_PREFETCH")) opt.prefetch_joints = std::atoi(pf);
+    if (const char* hs = std::getenv("STOMP_B200_STATES_STATIC")) opt.hoist_static = std::atoi(hs) != 0;     // A / B: 0 walks every sphere per state
     if (const char* x = std::getenv("STOMP_B200_STATES_PER_THREAD")) opt.states_per_thread = std::atoi(x) == 2 ? 2 : 1;
     if (const char* t = std::getenv("STOMP_B200_STATES_BLOCK")) { const int v = std::atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) opt.block_threads = v; }
     return opt;
@@ -583,11 +585,45 @@ void resolve_state_kernel(stomp_b200_engine* e)
     std::string err;
     e->spec = codegen::specialised_state_kernel(e->robot, state_kernel_options(e), err);
     e->spec_note = e->spec ? std::string() : err;
+    if (e->spec && e->spec->static_kernel) {
+        // Spheres on the axis of a chain's first joint do not move with the state: one thread walks them here, with the
+        // statements the state kernel would have issued, and every state starts from that verdict.  Robot, spheres or scene
+        // changing resets spec_resolved (set_chain / set_spheres / the SDF setters and builders), which brings us back here;
+        // the launch is ordered on the main stream behind the copy or build that produced the grid.
+        cudaError_t rc = cudaSuccess;
+        if (!e->d_static_hit) {
+            rc = cudaMalloc((void**)&e->d_static_hit, sizeof(int32_t));
+            if (rc == cudaSuccess) e->allocations.push_back(e->d_static_hit);
+        }
+        if (rc == cudaSuccess) {
+            void* args[] = {&e->robot, &e->sdf, &e->d_static_hit};
+            rc = cudaLaunchKernel((const void*)e->spec->static_kernel, dim3(1), dim3(32), args, 0, e->stream);
+            e->launch_count++;
+        }
+        if (rc != cudaSuccess) {
+            (void)cudaGetLastError();
+            err = std::string("stomp_b200_static_spheres: ") + cudaGetErrorString(rc);
+            e->spec = nullptr;
+            e->spec_note = err;
+        }
+    }
     if (!e->spec) {     // still a CUDA kernel, but say so: the generic kernel is ~2x slower
         static bool told = false;
         if (!told) std::fprintf(stderr, "stomp_b200: the specialised state kernel is unavailable, using the generic one: %s\n", err.c_str());
         told = true;
     }
+}
+
+// the two arguments of the specialised kernel that come from the engine rather than from the loop: the verdict of the static
+// spheres, and the multiplier that replaces idx / T where the host can prove it exact (M = floor(2^32 / T) + 1 has
+// M T = 2^32 + r with 0 < r <= T, so umulhi(idx, M) = floor(idx / T + idx r / (T 2^32)) = idx / T whenever idx r < 2^32)
+void finish_state_args(const stomp_b200_engine* e, StateKernelArgs& a)
+{
+    a.static_hit = (e->spec && e->spec->static_kernel) ? e->d_static_hit : nullptr;
+    const unsigned long long T = (unsigned long long)std::max(a.T, 0), n = (unsigned long long)std::max(a.num_gen, 0);
+    a.t_magic = (T >= 2 && n * T * T < (1ull << 32)) ? (uint32_t)((1ull << 32) / T + 1) : 0u;
+    static const bool divide = std::getenv("STOMP_B200_STATES_DIV") && std::atoi(std::getenv("STOMP_B200_STATES_DIV")) != 0;   // A / B: the division sequence
+    if (divide) a.t_magic = 0u;
 }
 
 // the noise-less rollout as a tail of the specialised state kernel (no self-collision pairs, 0 / 1 state costs)
@@ -623,6 +659,7 @@ int launch_noiseless(stomp_b200_engine* e, bool on_main_stream)
         a.stop = lp.stop; a.T = lp.T; a.D = lp.D; a.slots = 1; a.gslots = 1; a.sumw = lp.sumw; a.num_gen = 0;
         a.honour_stop = lp.honour_stop; a.row_stride = lp.T; a.rollout_stride = (int64_t)lp.D * lp.T;
         fill_noiseless_tail(e, lp, e->nl_sums2[e->nl_parity], a.nl);
+        finish_state_args(e, a);
         void* args[] = {&a, &e->robot, &e->sdf};
         const int bt = e->spec->block_threads;
         // at a join (the caller waits) the tail follows the update kernel on the main stream: as a programmatic dependent its
@@ -658,6 +695,7 @@ int launch_noiseless(stomp_b200_engine* e, bool on_main_stream)
         a.T = lp.T; a.D = lp.D; a.slots = 1; a.gslots = 1; a.sumw = lp.sumw; a.num_gen = 1; a.gen_offset = 0;
         a.honour_stop = lp.honour_stop; a.debug_skip = 0;
         a.row_stride = lp.N; a.rollout_stride = (int64_t)lp.D * lp.N;
+        finish_state_args(e, a);
         if (e->self_pairs.n > 0) {
             launch_states_self_collision(e, a, dim3((lp.T + 127) / 128, e->Q), nl_stream);
             if (int rc = check_launch(e, "states_self_collision_kernel")) return rc;
@@ -866,6 +904,7 @@ int iterate_body(stomp_b200_engine* e, int iteration, int mode, int honour_stop,
         a.gen_offset = lp.gen_offset; a.honour_stop = lp.honour_stop; a.debug_skip = lp.debug_skip;
         a.row_stride = lp.T; a.rollout_stride = (int64_t)lp.D * lp.T;
         if (tail_in_state_kernel) fill_noiseless_tail(e, lp, lp.nl_sums, a.nl);
+        finish_state_args(e, a);
         if (e->self_pairs.n > 0) {
             launch_states_self_collision(e, a, dim3((states + 127) / 128, e->Q), e->stream);
         } else if (e->spec) {
@@ -2580,6 +2619,7 @@ int stomp_b200_evaluate_states(stomp_b200_engine* e, const double* theta, int32_
         a.T = num_steps; a.D = e->D; a.slots = num_trajectories; a.gslots = 1; a.sumw = 1; a.num_gen = num_trajectories;
         a.gen_offset = 0; a.honour_stop = 0; a.debug_skip = 0;
         a.row_stride = num_steps; a.rollout_stride = (int64_t)e->D * num_steps;
+        finish_state_args(e, a);
         if (e->self_pairs.n > 0) {
             launch_states_self_collision(e, a, dim3((unsigned)((states + 127) / 128), 1), e->stream, sane);
         } else if (e->spec && sane) {
@@ -2798,7 +2838,8 @@ int stomp_b200_state_kernel_source(stomp_b200_engine* e, char* buffer, size_t ca
 {
     if (!e) return STOMP_B200_ERR_INVALID_ARGUMENT;
     if (!e->have_chain || !e->have_spheres) return fail(e, STOMP_B200_ERR_NOT_READY, "chain and spheres come first");
-    const std::string src = codegen::generate_state_kernel_source(e->robot, state_kernel_options(e));
+    // the source of the kernel this engine launches; for an engine on the generic kernel, what would be generated
+    const std::string src = (e->spec_resolved && e->spec) ? e->spec->source : codegen::generate_state_kernel_source(e->robot, state_kernel_options(e));
     if (needed) *needed = src.size() + 1;
     if (buffer && capacity) std::snprintf(buffer, capacity, "%s", src.c_str());
     return STOMP_B200_OK;

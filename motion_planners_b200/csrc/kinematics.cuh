@@ -436,6 +436,11 @@ struct StateKernelArgs {
     int32_t row_stride;            // doubles between consecutive joints of one rollout (T; N for the padded policy rows)
     int64_t rollout_stride;        // doubles between consecutive rollouts (D * T)
     NoiselessTail nl;
+    // verdict of the spheres whose centres no joint value moves (state_codegen.hpp: FoldingEmitter::centre_is_static), written
+    // once per robot / scene by stomp_b200_static_spheres; null when the kernel walks every sphere itself
+    const int32_t* static_hit;
+    // floor(2^32 / T) + 1 when num_gen * T * T < 2^32 (then umulhi(idx, t_magic) == idx / T for every state index), else 0
+    uint32_t t_magic;
 };
 
 }  // namespace stomp_b200

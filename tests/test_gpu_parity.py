@@ -380,6 +380,92 @@ def test_specialised_state_kernel_equals_generic_kernel_and_oracle(shape, medium
     assert hits > 0
 
 
+def test_static_spheres_are_walked_once_per_scene_and_follow_scene_changes(monkeypatch):
+    """Spheres on the axis of a chain's first joint do not move with the state; the generated module evaluates them in
+    stomp_b200_static_spheres, once per robot / scene, and the walk starts from that verdict.  The verdicts must stay those
+    of the kernel that walks every sphere per state (STOMP_B200_STATES_STATIC=0), of the generic kernel and of the oracle —
+    also when the scene changes under a live engine: an obstacle put on the base column condemns every state, and taking it
+    away again clears them."""
+    import copy
+    pb = P.single_arm_problem(K=16, T=40, sdf_n=64)
+    D, T, K = pb.chain.num_dimensions, pb.num_time_steps, pb.num_rollouts
+    e = binding.engine_for_problem(pb, keep_debug_tensors=True)
+    assert e.state_kernel_kind()[0] == "specialised"
+    src = e.state_kernel_source()
+    assert "stomp_b200_static_spheres" in src and "static_spheres_hit" in src
+    import re
+    n_static = int(re.search(r"// (\d+) static spheres", src).group(1))
+    assert n_static >= 1
+    # the walk gathers for every sphere but the static ones
+    walk = src.split("bool state_hit(", 1)[1]
+    assert walk.count("voxel_of_centre<") == pb.spheres.link.size - n_static
+    monkeypatch.setenv("STOMP_B200_STATES_STATIC", "0")
+    full = binding.engine_for_problem(pb, keep_debug_tensors=True)
+    assert full.state_kernel_kind()[0] == "specialised"                       # the kernel is resolved here, under the switch
+    assert "stomp_b200_static_spheres" not in full.state_kernel_source()
+    monkeypatch.delenv("STOMP_B200_STATES_STATIC")
+    monkeypatch.setenv("STOMP_B200_STATES", "generic")
+    gen = binding.engine_for_problem(pb, keep_debug_tensors=True)
+    assert gen.state_kernel_kind()[0] == "generic"
+    monkeypatch.delenv("STOMP_B200_STATES")
+    o = Oracle(num_time_steps=T, num_dimensions=D, min_rollouts=K, max_rollouts=K, num_rollouts_per_iteration=K,
+               noise_stddev=pb.noise_stddev)
+    o.set_problem(pb)
+    rng = np.random.default_rng(5)
+    theta = rng.uniform(-1.5, 1.5, size=(K, D, T))
+    centre0 = e.sphere_centres(np.zeros(D))[0, 0]          # a static sphere: the same for every q
+    np.testing.assert_array_equal(e.sphere_centres(theta[:, :, 0])[:, 0], np.broadcast_to(centre0, (K, 3)))
+
+    def scene(blocked):
+        sdf = copy.copy(pb.sdf)
+        grid = np.array(pb.sdf.grid, dtype=np.float32, copy=True)
+        if blocked:     # a small obstacle where the first sphere sits: distance 0 in its voxel and the ones around it
+            ix, iy, iz = np.floor((centre0 - pb.sdf.origin) / pb.sdf.voxel).astype(int)
+            grid[iz - 1:iz + 2, iy - 1:iy + 2, ix - 1:ix + 2] = 0.0
+        sdf.grid = grid
+        return sdf
+
+    import contextlib
+
+    @contextlib.contextmanager
+    def switch(name, value):       # the state kernel is resolved again after every scene change, under the switches of that moment
+        if name:
+            monkeypatch.setenv(name, value)
+        try:
+            yield
+        finally:
+            if name:
+                monkeypatch.delenv(name)
+
+    seen = []
+    for blocked in (False, True, False):
+        sdf = scene(blocked)
+        o.set_sdf(sdf)
+        _, vo, _ = o.state_costs(theta, threads=4)
+        v = {}
+        for tag, eng, name, value in (("hoisted", e, None, None), ("full", full, "STOMP_B200_STATES_STATIC", "0"), ("generic", gen, "STOMP_B200_STATES", "generic")):
+            with switch(name, value):
+                eng.set_sdf(sdf)
+                _, v[tag], _ = eng.evaluate_states(theta)
+                assert (eng.state_kernel_kind()[0] == "generic") == (tag == "generic")
+                if tag != "generic":
+                    assert ("stomp_b200_static_spheres" in eng.state_kernel_source()) == (tag == "hoisted")
+                if tag != "generic":     # and through the loop (graph replays included): the flag reaches the rollouts and the noise-less tail
+                    eng.begin_solve()
+                    for it in range(3):
+                        eng.iterate(it)
+                    v[tag + " loop"] = (eng.tensor("verdicts")[0], eng.tensor("parameters")[0], eng.tensor("rollouts")[0])
+        np.testing.assert_array_equal(v["hoisted"], v["full"])
+        np.testing.assert_array_equal(v["hoisted"], v["generic"])
+        np.testing.assert_array_equal(v["hoisted"], vo)
+        for a, b in zip(v["hoisted loop"], v["full loop"]):
+            np.testing.assert_array_equal(a, b)
+        if blocked:
+            assert v["hoisted loop"][0][:K].all()
+        seen.append(int(v["hoisted"].sum()))
+    assert seen[1] == K * T and seen[0] < K * T and seen[2] == seen[0]
+
+
 @pytest.mark.parametrize("T", [20, 25, 40, 60, 100, 150, 200])
 def test_trajectory_lengths_cover_every_kernel_variant(T):
     """T selects the kernel instantiations: tiles per slab of the DMMA sampler (4 / 7 / 10 / 13, one or two slabs), groups

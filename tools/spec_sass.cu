@@ -47,6 +47,7 @@ int main(int argc, char** argv)
     if (getenv("LANES")) opt.rollout_lanes = true;
     if (getenv("SPT")) opt.states_per_thread = atoi(getenv("SPT"));
     if (getenv("PREFETCH")) opt.prefetch_joints = atoi(getenv("PREFETCH"));
+    if (getenv("STATIC")) opt.hoist_static = atoi(getenv("STATIC")) != 0;
     codegen::SelfPairStructure sp;
     if (dual && getenv("PAIRS")) {      // the sphere-pair rule inside the kernel: every sphere of the first arm (object included) against every one of the second
         std::vector<int> link_of((size_t)s, 0);
