@@ -175,6 +175,8 @@ struct stomp_b200_engine {
     // (profiles/r3r_pdl_edges.txt).  In-process A / B (profiles/r3s_ab_steady.txt): 56.5 us per iteration against 59.6.
     int pdl_mask = 13;                       // + bit 3: the noise-less tail launched alone at a join (84.8 -> 83.9 us per isolated C3 iteration, profiles/r4j_pdl_tail.txt)
     bool graphs_allowed = true;              // STOMP_B200_GRAPH=0 at creation switches the replay off
+    bool graph_over_overlap = false;         // STOMP_B200_GRAPH=2: replay graphs even where plain launches would overlap the sampler with the update kernel
+    bool early_sampler = true;               // STOMP_B200_SAMPLER_EARLY=0: the sampler waits for its predecessor before it draws (kernels.cuh)
     int eligible_streak = 0;                 // graph-eligible iterations run un-captured since the configuration last changed
     unsigned long long streak_epoch = 0;
     uint32_t* d_counters = nullptr;          // [0] iteration, [1] exchange epoch (LoopParams::counters)
@@ -750,6 +752,7 @@ int iterate_body(stomp_b200_engine* e, int iteration, int mode, int honour_stop,
     lp.iteration = iteration;
     lp.store_unit = c.keep_debug_tensors;
     lp.counters = on_graph ? e->d_counters : nullptr;
+    lp.early_sampler = e->early_sampler ? 1 : 0;
     lp.nl_sums = e->nl_sums2[e->nl_parity];
     lp.nl_sums_next = e->nl_sums2[e->nl_parity ^ 1];
     // the noise-less rollout of the previous iteration: a tail of this iteration's state kernel launch when that kernel is the
@@ -1034,6 +1037,8 @@ __global__ void set_counters_kernel(uint32_t* counters, uint32_t iteration, uint
 {
     counters[0] = iteration;
     counters[1] = epoch;
+    counters[2] = iteration;     // the sampler's own copy and its ticket counter (LoopParams::counters)
+    counters[3] = 0u;
 }
 
 // host state an iteration changes (restored when a capture has to be abandoned)
@@ -1080,6 +1085,14 @@ int iterate_async(stomp_b200_engine* e, int iteration, int mode, int honour_stop
                     (world == 1 || e->peer_ready) && c.num_rollouts_per_iteration % world == 0 &&
                     !e->noiseless_pending && (!e->nl_deferred || e->nl_lp.honour_stop == honour_stop);
     eligible = eligible && noiseless_tail_available(e);      // the side-stream rollout bakes per-iteration state into its parameters
+    // A sampler that is launched as a programmatic dependent of the previous iteration's update kernel draws its noise beside
+    // it (LoopParams::early_sampler); a graph boundary is a full dependency and would undo that.  On one GPU with a grid that
+    // fills it the loop is GPU-bound either way, and plain launches keep the overlap: 50.2 against 58.1 us per C3 iteration
+    // (profiles/r5d_early_sampler_ab.txt).  Shards and small problems (no dependent launch of the sampler) keep the graph.
+    if (eligible && e->early_sampler && (e->pdl_mask & 1) && !e->graph_over_overlap) {
+        const long long sampler_ctas = (long long)((c.num_rollouts_per_iteration / world + 31) / 32) * e->D * e->Q;
+        if (sampler_ctas >= 5LL * e->num_sms) eligible = false;
+    }
     // the first iteration after a join (the owed rollout was flushed for the caller) happens once per call: not worth a
     // capture (~0.15 ms) of its own
     eligible = eligible && e->nl_deferred;
@@ -1518,8 +1531,9 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     CREATE_TRY(dev_alloc(e, &b.c_compact, Q * D * GS));
     CREATE_TRY(dev_alloc(e, &b.tile_counter, 4));
     CREATE_TRY(dev_alloc(e, &e->d_counters, 4));
-    if (const char* gr = std::getenv("STOMP_B200_GRAPH")) e->graphs_allowed = std::strcmp(gr, "0") != 0;
+    if (const char* gr = std::getenv("STOMP_B200_GRAPH")) { e->graphs_allowed = std::strcmp(gr, "0") != 0; e->graph_over_overlap = std::strcmp(gr, "2") == 0; }
     if (const char* pd = std::getenv("STOMP_B200_PDL")) e->pdl_mask = std::atoi(pd) & 15;
+    if (const char* es = std::getenv("STOMP_B200_SAMPLER_EARLY")) e->early_sampler = std::strcmp(es, "0") != 0;
     CREATE_TRY(dev_alloc(e, &e->d_timeline, (size_t)kTimelineRing * kTimelineKernels * 2));
     b.world_size = world;
 

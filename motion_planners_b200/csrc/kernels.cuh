@@ -114,15 +114,21 @@ struct LoopParams {
     int32_t noise_from_rollouts;   // the sampler did not write `noise`: weights_update_kernel forms rollouts - theta itself
     // iterations replayed from a CUDA graph (engine.cu: GraphKey) cannot carry per-iteration kernel parameters: the
     // iteration number (Philox counter) and the epoch of the peer exchange then live on the device.  counters[0] =
-    // iteration, read by the sampler and advanced by the weights / update kernel; counters[1] = exchange epoch, read by
-    // weights_update_peer_kernel and advanced by the sampler — reader and writer are never the same launch.  Null: the
-    // values in `iteration` / PeerExchange::epoch apply.
+    // iteration, advanced by the weights / update kernel (nobody reads it any more); counters[1] = exchange epoch, read by
+    // weights_update_peer_kernel and advanced by the sampler — reader and writer are never the same launch; counters[2] =
+    // the sampler's own iteration number, which every CTA of a launch reads before it takes a ticket in counters[3], the last
+    // ticket holder advancing it (so that a sampler that starts under its predecessor never depends on when the
+    // predecessor gets to its increment).  Null: the values in `iteration` / PeerExchange::epoch apply.
     uint32_t* counters;
     // forward cumulation (use_cumulative_costs == 2: cumulative_costs_[d](t) = sum_{t' >= t} total_costs_[d](t'), the
     // variant commented out at PolicyImprovement.cpp:473-477): the suffix sums, [Q][slots][D][T]; rides on the
     // per-time-step kernels
     double* pt_cum;
     int32_t forward_cumulation;
+    // the recurrence sampler draws and shapes its unit noise (phases 1 and 2) BEFORE it waits for its predecessor: nothing in
+    // them depends on what an iteration computes.  Launched as a programmatic dependent of the weights / update kernel, that
+    // part runs beside it (sample_rollouts_banded_kernel)
+    int32_t early_sampler;
 };
 
 // the joint limits of OptimizationTask::filter: all the sampling kernels need of the robot (0.5 KB of kernel parameters
@@ -714,9 +720,30 @@ sample_rollouts_banded_kernel(const __grid_constant__ LoopParams p, const __grid
 {
     extern __shared__ __align__(16) double smem[];
     const int q = blockIdx.y;
-    pdl_trigger_and_wait();
-    if (p.counters && blockIdx.x == 0 && q == 0 && threadIdx.x == 0) p.counters[1] += 1u;    // next exchange epoch (graph replay)
-    if (query_frozen(p, q)) return;
+    // Phases 1 and 2 (Philox + Box-Muller, the recurrence: two thirds of this kernel's instructions) read nothing an iteration
+    // writes — band table, seed, iteration number — so with `early` the wait for the predecessor (the weights / update
+    // kernel of the previous iteration, when this launch is its programmatic dependent) comes after them: the CTAs become
+    // resident at the predecessor's trigger and work beside a kernel that leaves four fifths of the warp slots empty.
+    const bool early = kPhilox && p.early_sampler != 0;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    uint32_t iteration = (uint32_t)p.iteration;
+    if (p.counters) {
+        iteration = *(volatile const uint32_t*)(p.counters + 2);
+        __syncthreads();                                     // every thread of the CTA has its copy
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned ticket = atomicAdd(p.counters + 3, 1u);
+            if (ticket == gridDim.x * gridDim.y - 1u) {      // every CTA of this launch has read counters[2]
+                p.counters[3] = 0u;
+                p.counters[2] = iteration + 1u;
+            }
+        }
+    }
+    if (!early) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (p.counters && blockIdx.x == 0 && q == 0 && threadIdx.x == 0) p.counters[1] += 1u;    // next exchange epoch (graph replay)
+        if (query_frozen(p, q)) return;
+    }
     TimelineScope tls(p, 0);
     const int T = p.T, D = p.D, N = p.N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -741,22 +768,12 @@ sample_rollouts_banded_kernel(const __grid_constant__ LoopParams p, const __grid
         const int t = i / (kB + 1), o = i - t * (kB + 1);
         s_band[i] = p.Lband[t * 8 + o];
     }
-    if (kFuse)
-        for (int i = tid; i < N; i += kBandedThreads) {
-            double v = 0.0;
-            if (i >= 3 && i < N - 3) {
-                v = c1 * th_all[i - 2];
-                v = fma(c2, th_all[i - 1], v); v = fma(c3, th_all[i], v); v = fma(c4, th_all[i + 1], v); v = fma(c5, th_all[i + 2], v);
-            }
-            s_dth[i] = v;
-        }
     // ---- phase 1: eps ----
     if (live) {
         const int ngroups = (T + 3) >> 2;
         // global column of this rollout and joint: the Philox counter of the contraction kernels
         const uint32_t gcol = (uint32_t)(((uint32_t)(p.query_offset + q) * (uint32_t)p.gen_global + (uint32_t)(p.gen_offset + k0 + lane)) * (uint32_t)D + (uint32_t)d);
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-        const uint32_t iteration = p.counters ? p.counters[0] : (uint32_t)p.iteration;
         double* dst = s_tile + lane * S;
         double* eps_row = p.epsilon + (((size_t)q * p.num_gen + (k0 + lane)) * D + d) * T;
         for (int g = warp; g < ngroups; g += kBandedThreads / 32) {
@@ -825,10 +842,24 @@ sample_rollouts_banded_kernel(const __grid_constant__ LoopParams p, const __grid
             col[t] = acc;
         }
     }
+    if (early) {                                             // from here on: the parameters and scales the previous iteration left
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (p.counters && blockIdx.x == 0 && q == 0 && threadIdx.x == 0) p.counters[1] += 1u;    // next exchange epoch (graph replay)
+        if (query_frozen(p, q)) return;
+    }
     __syncthreads();
     // ---- phase 3a: lane = rollout, warp w = time steps [a, b) ----
     const double* cf = p.coef + ((size_t)q * D + d) * 3;
     const double p1 = cf[0], p2 = cf[1], sd = cf[2];
+    if (kFuse)
+        for (int i = tid; i < N; i += kBandedThreads) {
+            double v = 0.0;
+            if (i >= 3 && i < N - 3) {
+                v = c1 * th_all[i - 2];
+                v = fma(c2, th_all[i - 1], v); v = fma(c3, th_all[i], v); v = fma(c4, th_all[i + 1], v); v = fma(c5, th_all[i + 2], v);
+            }
+            s_dth[i] = v;
+        }
     for (int t = tid; t < T; t += kBandedThreads) {
         const double th = th_all[kPad + t];
         s_th[t] = th;

@@ -974,6 +974,33 @@ def test_alternative_state_costs(mode, medium_problem):
     assert not np.array_equal(costs01, costs)
 
 
+def test_sampler_that_draws_before_it_waits_changes_nothing(monkeypatch):
+    """With enough rollouts to fill the GPU the sampler is a programmatic dependent of the previous iteration's update kernel and
+    draws and shapes its noise (phases 1 and 2) before it waits for it (LoopParams::early_sampler); such loops are launched
+    plainly, because a graph boundary would serialise the two kernels again.  Whatever the combination — early or late wait,
+    plain launches or graph replays (which take the sampler's own iteration counter and its ticket) — the kernels see the same
+    data: parameters, costs and standard deviations are bit for bit the same."""
+    pb = P.single_arm_problem(K=4096, T=100, sdf_n=64)
+    results, replays = [], []
+    for graph, early in (("1", "1"), ("2", "1"), ("0", "0"), ("2", "0"), ("0", "1")):
+        monkeypatch.setenv("STOMP_B200_GRAPH", graph)
+        monkeypatch.setenv("STOMP_B200_SAMPLER_EARLY", early)
+        e = binding.engine_for_problem(pb)
+        e.begin_solve()
+        e.run(0, 9)
+        e.run(9, 1)
+        e.run(10, 5, honour_stop=True)
+        replays.append(e.graph_replays())
+        r = e.finish_solve()
+        results.append((e.tensor("parameters").copy(), r["solution"].copy(), r["cost"].copy(), r["iterations"].copy(), e.tensor("stddevs").copy()))
+        e.close()
+    # default (graphs allowed): this loop overlaps, so it is not replayed; STOMP_B200_GRAPH=2 insists on the graph
+    assert replays[0] == 0 and replays[1] > 0 and replays[2] == 0 and replays[3] > 0 and replays[4] == 0
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            np.testing.assert_array_equal(a, b)
+
+
 def test_graph_replay_and_dependent_launch_change_nothing(medium_problem, monkeypatch):
     """Steady iterations replay from CUDA graphs (device-side iteration counter, double-buffered noise-less record) and the
     sampler / update kernels are launched as programmatic dependents: the same kernels on the same data, so the whole solve
