@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+O=gpurun_out
+mkdir -p $O
+for v in "STOMP_B200_UPDATE_SMEM_KB=100" "STOMP_B200_UPDATE_SMEM_KB=60" "STOMP_B200_UPDATE_SMEM_KB=100 STOMP_B200_UPDATE_CARVEOUT=100"; do
+  echo "== $v"; env $v timeout 300 python tools/timeline.py c3 40 2>&1 | tail -9
+done > $O/r5j_update_smem_pad.txt 2>&1; cat $O/r5j_update_smem_pad.txt
