@@ -465,9 +465,9 @@ def run_ours(args):
     achieved_path = alg_bytes / ((avg_cost_ms + avg_rows_ms) * 1e-3) / 1e9 if cost_ms > 0 else None
     kind, kind_note = eng_kind
     # FP64 arithmetic of the state kernel: FP64-pipe warp instructions per state from the kernel's SASS
-    # FP64-pipe instructions of the generated kernel, counted in its SASS (tools/spec_sass.cu): iiwa 254 DFMA + 79 DADD +
-    # 47 DMUL of 840; dual arm with the grasped object (DUAL=1) 640 + 186 + 110 of 1792
-    fp64_ops = {(7, 20): 345, (14, 48): 856}.get((D, S))
+    # FP64-pipe instructions of the generated kernel, counted in its SASS (tools/spec_sass.cu): iiwa 224 DFMA + 63 DADD +
+    # 48 DMUL of 749 executed; dual arm with the grasped object (DUAL=1) 574 + 152 + 110
+    fp64_ops = {(7, 20): 335, (14, 48): 836}.get((D, S))
     fp64_peak = 18.43e12          # profiles/r1_fp64_peak_b200.json: DFMA / DADD / DMUL issue rate, thread-ops/s
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
