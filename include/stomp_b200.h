@@ -324,8 +324,10 @@ int stomp_b200_get_timeline(stomp_b200_engine* e, int32_t max_iterations, double
 /* total kernel launches issued by this engine since creation */
 int64_t stomp_b200_launch_count(const stomp_b200_engine* e);
 /* iterations that ran as one cudaGraphLaunch: steady-state iterations of the on-device-sampler loop (no rollout reuse, no
- * read-back tensors kept) are captured once and replayed; their kernels are counted in stomp_b200_launch_count as usual.
- * STOMP_B200_GRAPH=0 in the environment at stomp_b200_create switches the replay off. */
+ * read-back tensors kept) of rollout shards and small problems are captured once and replayed; their kernels are counted in
+ * stomp_b200_launch_count as usual.  Loops whose sampler fills the GPU are launched plainly instead: their sampler draws its
+ * noise beside the previous iteration's update kernel (programmatic dependent launch), which a graph boundary would undo.
+ * STOMP_B200_GRAPH=0 in the environment at stomp_b200_create switches the replay off, =2 replays those loops too. */
 int64_t stomp_b200_graph_replays(const stomp_b200_engine* e);
 /* device-side timing of a region on the engine's stream: begin / end record events, end returns ms */
 int stomp_b200_timer_begin(stomp_b200_engine* e);
