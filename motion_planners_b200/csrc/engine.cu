@@ -1440,7 +1440,9 @@ int stomp_b200_create(const stomp_b200_config* cfg, stomp_b200_engine** out)
     b.seed = cfg->seed;
     b.noiseless_slot = -1;
 #ifdef STOMP_B200_DEBUG_KNOBS      // measurement builds only: lets the cost kernels skip their work
+#ifdef STOMP_B200_DEBUG_KNOBS     // measurement builds only (add -DSTOMP_B200_DEBUG_KNOBS to NVFLAGS): a shipped library never skips work
     if (const char* dbg = std::getenv("STOMP_B200_DEBUG_SKIP")) b.debug_skip = std::atoi(dbg);
+#endif
 #endif
 
     double* tmp = nullptr;
