@@ -496,8 +496,8 @@ def run_ours(args):
                    "sdf": list(map(int, problem.sdf.dims)), "sharding": ("queries" if shard_mode == 1 else "rollouts") if world > 1 else "none",
                    "l2": "flushed (256 MiB write) between timed iterations" if flusher else "not flushed",
                    "noise": "on-device Philox4x32-10", "exchange": exchange[0] + (": " + exchange[1] if world > 1 else ""),
-                   "timed": "CUDA events on the engine's stream, per step: one recorded on the idle stream before stomp_b200_run, one "
-                            "that call records behind the last kernel it queues (before its closing host wait); max over ranks, summed over the steps"},
+                   "timed": "CUDA events on the engine's stream, per step: one stomp_b200_run records on the idle stream at its entry, one "
+                            "it records behind the last kernel it queues (before its closing host wait); max over ranks, summed over the steps"},
         "clocks": clocks,
         "e2e": {"value": states_per_step * e2e_ran / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / max(e2e_ran, 1.0),
                 "d2h_bytes_per_step": d2h / max(e2e_ran, 1.0), "iterations_run": e2e_ran, "solves": e2e_solves,

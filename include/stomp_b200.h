@@ -330,8 +330,9 @@ int64_t stomp_b200_launch_count(const stomp_b200_engine* e);
  * STOMP_B200_GRAPH=0 in the environment at stomp_b200_create switches the replay off, =2 replays those loops too. */
 int64_t stomp_b200_graph_replays(const stomp_b200_engine* e);
 /* device-side timing of a region on the engine's stream: begin waits for the stream, records an event and arms the timer;
- * a stomp_b200_run inside the region records the end event behind the last kernel it queues (before its own closing wait),
- * else stomp_b200_timer_end records it; end waits for that event and returns the milliseconds between the two */
+ * the first stomp_b200_run inside the region moves that event to its own entry (the stream is idle in between), every
+ * stomp_b200_run records the end event behind the last kernel it queues (before its own closing wait); without a run call
+ * (solve, iterate) the region is begin .. end as called.  end waits for the end event and returns the milliseconds. */
 int stomp_b200_timer_begin(stomp_b200_engine* e);
 int stomp_b200_timer_end(stomp_b200_engine* e, double* elapsed_ms);
 int stomp_b200_synchronize(stomp_b200_engine* e);
