@@ -1,16 +1,22 @@
 // Host orchestration + C ABI (include/stomp_b200.h) of the B200 STOMP rollout loop.
 //
-// One engine = one GPU; a main stream plus two helper streams (control-cost rows beside the state kernel; the
-// noise-less rollout under the next iteration's sampling).  The per-iteration sequence mirrors
-// stomp::Stomp::runSingleIteration (reference src/planners/stomp/src/Stomp.cpp:274-301):
-//   doGenRollouts      -> [reuse_rollouts_kernel] sample_rollouts_dmma_kernel (| sample_rollouts_kernel | shift_rollouts_kernel)
-//   doExecuteRollouts  -> stomp_b200_states_specialised (generated, state_codegen.hpp; | rollout_states_kernel)
-//   setRolloutCosts    -> control_rows_tile_kernel (| control_rows_fast_kernel | control_rows_kernel) [reused_control_cost_kernel]
+// One engine = one GPU; a main stream plus two helper streams for the fallback paths (control-cost rows beside the state
+// kernel; a two-kernel noise-less rollout under the next iteration's sampling).  The per-iteration sequence mirrors
+// stomp::Stomp::runSingleIteration (reference src/planners/stomp/src/Stomp.cpp:274-301); shipped loop first, fallbacks after |:
+//   doGenRollouts      -> [reuse_rollouts_kernel] sample_rollouts_banded_kernel (recurrence through the banded L^-1, control-cost
+//                         rows fused; draws before it waits for the previous update kernel) | sample_rollouts_dmma_kernel
+//                         (injected epsilon, factors without a band table) | sample_rollouts_kernel | shift_rollouts_kernel
+//   doExecuteRollouts  -> stomp_b200_states_specialised (generated, state_codegen.hpp; static spheres once per scene by
+//                         stomp_b200_static_spheres) | rollout_states_kernel; states_self_collision_kernel / the generated
+//                         pair-rule kernel with a sphere-pair list; state_extras_kernel for the alternative costs
+//   setRolloutCosts    -> inside the sampler | control_rows_tile_kernel | control_rows_fast_kernel | control_rows_kernel
+//                         [reused_control_cost_kernel]
 //   improvePolicy + updateParameters
-//                      -> weights_update_kernel on one GPU; with several GPUs, rollout reuse or per-kernel profiling:
-//                         [allgather] rollout_weights_kernel, weighted_update_kernel, reduce_partials_kernel, [allreduce],
-//                         apply_update_kernel
-//   doNoiselessRollout -> the state kernel on the T noise-less states + noiseless_rollout_kernel (side stream)
+//                      -> weights_update_kernel on one GPU, weights_update_peer_kernel (both exchanges over NVLink mailboxes) on
+//                         rollout shards | with the NCCL exchange, rollout reuse or per-kernel profiling: [allgather]
+//                         rollout_weights_kernel, weighted_update_kernel, reduce_partials_kernel, [allreduce], apply_update_kernel
+//   doNoiselessRollout -> control costs in the update kernel's last CTA per joint, the T states as a tail of the next state kernel
+//                         launch (alone at a join) | the state kernel on the T states + noiseless_rollout_kernel (side stream)
 // The rollout bookkeeping (PolicyImprovement.cpp:170-186,304-308) is host integer arithmetic and stays here.
 #include <algorithm>
 #include <cmath>

@@ -153,9 +153,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 // Programmatic dependent launch: the three kernels of a steady iteration (sampler -> state kernel -> weights / update)
 // are launched with cudaLaunchAttributeProgrammaticStreamSerialization.  Each lets its successor's CTAs become resident
 // at once (trigger at the top) and itself waits for its predecessor's completion and memory flush before it reads
-// anything (wait, also at the top: the first thing every one of them reads — the stop flag — is a predecessor's output).
-// What is hidden is the launch latency between dependent kernels, 2 - 3 us each on B200.  Both are no-ops in a kernel
-// launched the ordinary way.
+// anything an iteration writes (wait at the top for the state and update kernels: the first thing they read — the stop
+// flag — is a predecessor's output; the recurrence sampler first draws and shapes its noise, which depends on nothing an
+// iteration computes, and waits before its phase 3).  What is hidden is the launch latency between dependent kernels, 2 - 3 us
+// each on B200, and — for the sampler — the part of it that runs beside the update kernel.  Both instructions are no-ops in
+// a kernel launched the ordinary way.
 __device__ __forceinline__ void pdl_trigger_and_wait()
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
