@@ -8,7 +8,7 @@
 //                         (injected epsilon, factors without a band table) | sample_rollouts_kernel | shift_rollouts_kernel
 //   doExecuteRollouts  -> stomp_b200_states_specialised (generated, state_codegen.hpp; static spheres once per scene by
 //                         stomp_b200_static_spheres) | rollout_states_kernel; states_self_collision_kernel / the generated
-//                         pair-rule kernel with a sphere-pair list; state_extras_kernel for the alternative costs
+//                         pair-rule kernel with a sphere-pair list; state_cost_extras_kernel for the alternative costs
 //   setRolloutCosts    -> inside the sampler | control_rows_tile_kernel | control_rows_fast_kernel | control_rows_kernel
 //                         [reused_control_cost_kernel]
 //   improvePolicy + updateParameters
