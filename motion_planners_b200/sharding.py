@@ -1,9 +1,11 @@
 """Host-side plumbing for more than one GPU (one process per GPU, torch.distributed for the rendezvous).
 
-The data path has exactly two exchanges per iteration in rollout-sharded mode, both issued
-by the C library on its own CUDA stream through NCCL:
-  1. all-gather of the per-rollout cost scalars  (S, C_d, cum_d)            [K/G][1+2D] per rank
-  2. all-reduce(sum) of the update rows + adaptation numerators              [D][T+1]
+The data path has exactly two exchanges per iteration in rollout-sharded mode, both inside the C
+library's weights_update_peer_kernel as tagged 8-byte words written into peer-mapped mailboxes over NVLink:
+  A. the min / max of the rank's own cumulative costs per joint                [D][2] per rank
+  B. the rank's unnormalised partial sums (update row, adaptation numerator, sum of weights)   [D][T+2] per rank
+(with STOMP_B200_EXCHANGE=nccl, or where the mailboxes cannot be mapped: an NCCL all-gather of the per-rollout cost
+scalars [K/G][1+3D] and an all-reduce of [D][T+2]),
 and none in query-sharded mode.  This module holds what the *host* has to get right: the partition of
 rollouts / queries over ranks, the broadcast of the NCCL unique id, and max-over-ranks timing.  The
 functions take any initialised torch.distributed backend (nccl on GPUs, gloo in the CPU tests).

@@ -135,8 +135,8 @@ def test_warm_start_matches_the_reference():
 
 def test_per_timestep_costs_match_the_reference():
     # Stomp::setCostCumulation(false): cumulative_costs_[d] = total_costs_[d], probabilities vary with the time step
-    # (PolicyImprovement.cpp:473-481,497-582).  Not what StompPlanner ships (and not built on the GPU yet: SURVEY 8f
-    # rank 4), but it pins the restatement's other branch.
+    # (PolicyImprovement.cpp:473-481,497-582).  Not what StompPlanner ships; it pins the restatement's other branch, which the
+    # GPU's per-time-step kernels are compared with in tests/test_gpu_parity.py.
     pb = P.single_arm_problem(K=12, T=30, sdf_n=64)
     o, r = _pair(pb, 12, 12, 12, use_cumulative_costs=False)
     _run(o, r, 4, seed=8, cumulative=False)
