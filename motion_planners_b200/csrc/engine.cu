@@ -2914,11 +2914,16 @@ int stomp_b200_codegen_selftest(char* log, size_t log_capacity)
         opt.wide_index = wide != 0;
         opt.magic_floor = wide == 0;
         opt.inside_grid = wide == 0;
-        if (!codegen::compile_to_cubin(codegen::generate_state_kernel_source(r, opt), cubin, clog, err)) {
+        const std::string src = codegen::generate_state_kernel_source(r, opt);
+        if (!codegen::compile_to_cubin(src, cubin, clog, err)) {
             all_log += err;
             rc = STOMP_B200_ERR_CUDA;
         } else {
-            all_log += "ok: " + std::to_string(cubin.size()) + " byte cubin (" + codegen::cache().nvrtc.where + ") " + clog + "\n";
+            // both chains of the synthetic structure start with a sphere at the joint's origin: evaluated by stomp_b200_static_spheres
+            const size_t at = src.find(" static spheres\n");
+            const size_t from = at == std::string::npos ? at : src.rfind("// ", at);
+            const std::string statics = from == std::string::npos ? std::string("no static spheres") : src.substr(from + 3, at - from - 3) + " static spheres";
+            all_log += "ok: " + std::to_string(cubin.size()) + " byte cubin (" + codegen::cache().nvrtc.where + "), " + statics + " " + clog + "\n";
         }
     }
     if (rc == STOMP_B200_OK) {      // the same walk with the sphere-pair rule inside: every sphere of the first chain against every one of the second

@@ -74,6 +74,11 @@ def test_generated_state_kernel_compiles_for_sm_100a_without_a_device():
     rc, log = binding.codegen_selftest()
     assert rc == 0, log
     assert log.count("byte cubin") == 3 and "pair rule" in log      # narrow and wide SDF index, and the walk with the sphere-pair rule inside
+    # the first sphere of each of the two chains sits at its joint's origin: no joint value moves it, so it leaves the walk for
+    # stomp_b200_static_spheres (state_codegen.hpp: FoldingEmitter::centre_is_static); the second chain starts with an x axis
+    import re
+    counts = [int(n) for n in re.findall(r"(\d+) static spheres", log)]
+    assert len(counts) == 2 and all(c >= 1 for c in counts), log
 
 
 def test_header_is_plain_c():
