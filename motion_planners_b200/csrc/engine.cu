@@ -567,6 +567,10 @@ codegen::StateKernelOptions state_kernel_options(const stomp_b200_engine* e)
     opt.inside_grid = !has_prismatic && codegen::reach_is_inside_grid(e->robot, e->sdf);
     if (const char* c = std::getenv("STOMP_B200_STATES_CLAMP")) opt.inside_grid = opt.inside_grid && std::atoi(c) == 0;
     if (const char* b = std::getenv("STOMP_B200_STATES_MIN_BLOCKS")) opt.min_blocks = std::atoi(b);   // tuning knobs
+    // links between issuing a link's gathers and comparing them.  With the static spheres out of the walk the 7-joint arm is
+    // fastest comparing one link later (16.1 against 16.9 us at lag 2 and 17.7 at lag 0, C3 in the loop; 16.9 / 17.8 / 18.4
+    // isolated and flushed), the 14-joint dual arm two links later (41.5 against 44.0 us at lag 1): profiles/r5s_*
+    opt.compare_lag = e->robot.num_joints > 8 ? 2 : 1;
     if (const char* l = std::getenv("STOMP_B200_STATES_LAG")) opt.compare_lag = std::max(0, std::atoi(l));
     if (const char* j = std::getenv("STOMP_B200_STATES_STAGE")) opt.stage_joints = std::atoi(j) != 0;
     // sines / cosines ahead of the chain walk: measured neutral on the 7-joint arm (15.5 vs 15.6 us at C3), a gain on the
