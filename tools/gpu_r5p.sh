@@ -1,7 +1,7 @@
 #!/bin/bash
 # N GPUs on the round's final code: the C3 bench line under torchrun (sharded-vs-single parity_ok inside, query-sharded C4 beside it)
 cd "$(dirname "$0")/.."
-n=${1:-8}; tag=r5p
+n=${1:-8}; tag=${2:-r5p}
 mkdir -p gpurun_out
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $n --steps 20 --warmup 5 --skip-cpu-baseline > gpurun_out/scale_c3_n${n}_$tag.json 2> gpurun_out/scale_c3_n${n}_$tag.err; echo "n$n rc=$?"
 python - gpurun_out/scale_c3_n${n}_$tag.json <<'PY'
